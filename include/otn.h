@@ -1,0 +1,131 @@
+/*
+ * libotn -- C ABI of the B200-native (sm_100a, FP64) Stiefel trust-region fit of trotterised Kraus/LPDO channels.
+ *
+ * The reference (EmilianoG-byte/opentn) is pure Python and defines no FFI; its boundary for this path is a set of
+ * Python callables with fixed signatures.  Each entry point below names the reference interface
+ * (file:line under the reference tree) whose arithmetic it replaces.  `INTEGRATION.md` shows the ctypes stub a
+ * maintainer of the reference would add; `opentn_b200/_lib.py` is that stub in this repository.
+ *
+ * Conventions
+ *   - every array is row-major float64 (int32 for index/status arrays); no torch / numpy types cross this boundary;
+ *   - every data pointer may be a HOST or a DEVICE pointer (detected with cudaPointerGetAttributes); host arrays are
+ *     staged through the handle's device buffers, device arrays are used in place;
+ *   - an isometry batch is x[batch][m][n][p]; model FULL: n = d^N * K, p = d^N; model LOCAL: n = d^2 * K, p = d^2
+ *     (row index a*K + k, E_k = x[k::K, :], opentn/transformations.py:716-726);
+ *   - superoperators are D x D with D = d^(2N), row (out, out*), column (in, in*), row-major vectorisation;
+ *   - tangent vectors cross the boundary as (n,p) matrices (basis independent), not as (A-upper,B) coefficient vectors;
+ *   - return value 0 = success, negative = error (message via otn_last_error(), thread local);
+ *   - a handle is not thread-safe; distinct handles are independent.  All work of a call is enqueued on the handle's
+ *     stream and the call returns after that stream has been synchronised.
+ */
+#ifndef OTN_H
+#define OTN_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct otn_problem otn_problem;
+
+enum { OTN_MODEL_FULL = 0, OTN_MODEL_LOCAL = 1 };
+enum { OTN_METRIC_EUCLIDEAN = 0, OTN_METRIC_CANONICAL = 1 };
+
+/* status bits reported per instance by otn_tr_run / otn_retract */
+enum { OTN_STATUS_OK = 0, OTN_STATUS_NAN = 1, OTN_STATUS_NOT_SPD = 2, OTN_STATUS_NEG_DISCRIMINANT = 4 };
+
+const char* otn_last_error(void);
+int otn_version(void);
+
+/* ---- problem handle ------------------------------------------------------------------------------------------------
+ * A handle owns: the targets exp(tau L) (n_targets of them, real parts [n_targets][D][D]; imaginary parts may be NULL
+ * and only contribute the constant ||Im T||^2 under the square root), the index tables of the local->full embedding,
+ * all work matrices for `max_batch` instances, and one CUDA stream.
+ * Replaces the closure  f = lambda xi: frobenius_norm(model(xi), target)  the reference notebooks build
+ * (experiments/trust_region_pauli_noise.ipynb cell 21) with model = model_stiefel_local (optimization.py:106) or
+ * model_Ys_stiefel (optimization.py:147). */
+int otn_create(otn_problem** out, int N, int d, int m, int K, int model, int metric, int max_batch, int n_targets,
+               const double* target_re, const double* target_im, int device);
+void otn_destroy(otn_problem* p);
+/* target id of each instance (default: all 0) */
+int otn_set_target_index(otn_problem* p, const int* index, int batch);
+/* metric of the Riemannian gradient / connection: (alpha0, alpha1) of stiefel.py:398-409; OTN_METRIC_* presets */
+int otn_set_metric(otn_problem* p, int metric);
+/* n, p, D, m, per-instance workspace bytes */
+int otn_query(const otn_problem* p, int* n, int* pp, int* D, int* m, long long* workspace_bytes);
+/* the handle's cudaStream_t (as void*) so a host framework can order its own work after ours */
+void* otn_stream(const otn_problem* p);
+
+/* ---- model / cost layer ---------------------------------------------------------------------------------------------
+ * otn_model     : M[batch][D][D] = Y_m ... Y_1        model_stiefel_local / model_Ys_stiefel (optimization.py:106,147)
+ * otn_cost      : f[batch] = || M - T ||_F            frobenius_norm (optimization.py:56-61)
+ * otn_cost_grad : + Riemannian gradient rgrad[batch][m][n][p]   gradient_stiefel_general (stiefel.py:411-426);
+ *                 egrad (nullable) receives what jax.grad(func)(xi) returns (stiefel.py:423)
+ * otn_triple    : unit of work U1 = (f, rgrad, H eta) sharing the primal pass; H eta is
+ *                 P_X(riemannian_connection(jvp(rgrad)[eta], rgrad, eta, x)), i.e. one matrix-vector product with the
+ *                 matrix riemannian_hessian_vec builds column by column (stiefel.py:477-544), as tangent matrices
+ * otn_hvp_cached: H eta at the x of the most recent otn_cost_grad / otn_triple call on this handle (what
+ *                 truncated_cg's `hess @ d` needs, trust_region_rcopt.py:116) */
+int otn_model(otn_problem* p, const double* x, int batch, double* M);
+int otn_cost(otn_problem* p, const double* x, int batch, double* f);
+int otn_cost_grad(otn_problem* p, const double* x, int batch, double* f, double* rgrad, double* egrad);
+int otn_triple(otn_problem* p, const double* x, const double* eta, int batch, double* f, double* rgrad, double* heta);
+int otn_hvp_cached(otn_problem* p, const double* eta, int batch, double* heta);
+
+/* ---- representation layer (stateless; `device` selects the GPU) -----------------------------------------------------
+ * otn_ortho2super : Y[count][dim^2][dim^2] = sum_k E_k (x) E_k      ortho2super (transformations.py:743-749),
+ *                   == kraus2superop of E_k = x[k::K,:] (transformations.py:170-180)
+ * otn_embed_local : Yfull[count][D][D] from Yloc[count][d^4][d^4]     create_supertensored_from_local(pbc=True)
+ *                   (transformations.py:405-429) + convert_supertensored2liouvillianfull(shift_pbc) (:484-490)
+ * otn_compose     : M[count][D][D] = Ys[count][m-1] @ ... @ Ys[count][0]   compose_superops_list (transformations.py:841-851) */
+int otn_ortho2super(const double* x, int count, int dim, int K, double* Y, int device);
+int otn_embed_local(const double* Yloc, int count, int N, int d, int shift_pbc, double* Yfull, int device);
+int otn_compose(const double* Ys, int count, int m, int D, double* M, int device);
+
+/* ---- manifold layer (stateless) ---------------------------------------------------------------------------------------
+ * otn_project       : Z - X sym(X^T Z)                                   project (stiefel.py:23-30)
+ * otn_rgrad_map     : Z/a0 + (1/a1 - 2/a0)/2 X X^T Z - 1/(2 a1) X Z^T X   gradient_ambient2riemannian (stiefel.py:398-409)
+ * otn_retract       : polar factor of X + eta                            polar_decomposition_rectangular (stiefel.py:323-330);
+ *                     status (nullable, int[count]) gets OTN_STATUS_NOT_SPD where (X+eta)^T(X+eta) is not positive definite
+ * otn_canonical_dot : out[batch] = sum_l tr(a_l^T (I - x_l x_l^T / 2) b_l)   canonical_metric (stiefel.py:76-83) summed over
+ *                     the m isometries of an instance (= Euclidean dot of the coefficient vectors of stiefel.py:453-466) */
+int otn_project(const double* x, const double* z, int count, int n, int p, double* out, int device);
+int otn_rgrad_map(const double* x, const double* z, int count, int n, int p, double alpha0, double alpha1, double* out, int device);
+int otn_retract(const double* x, const double* eta, int count, int n, int p, double* out, int* status, int device);
+int otn_canonical_dot(const double* x, const double* a, const double* b, int batch, int m, int n, int p, double* out, int device);
+
+/* ---- optimiser layer --------------------------------------------------------------------------------------------------
+ * Batched Riemannian trust region (Absil Alg. 10) with Steihaug truncated CG (Alg. 11), one independent run per instance,
+ * all instances advanced in lock-step with per-instance masks:  riemannian_trust_region_optimize + truncated_cg
+ * (trust_region_rcopt.py:5-166) with gradfunc = gradient_stiefel_vec, hessfunc = riemannian_hessian_vec (matrix-free),
+ * retract = retract_stiefel. */
+typedef struct {
+    double rho_trust;    /* 0.125  (trust_region_rcopt.py:36) */
+    double radius_init;  /* 0.01   (:37)  used when radius_inout == NULL */
+    double maxradius;    /* 0.1    (:38) */
+    int niter;           /* 20     (:39) */
+    int tcg_maxiter;     /* <= 0 => 2 * (m * dof) (:107) */
+    double tcg_abstol;   /* 1e-8   (:108) */
+    double tcg_reltol;   /* 1e-6   (:109) */
+} otn_tr_params;
+
+typedef struct {
+    double* f_iter;      /* [niter][batch]  cost BEFORE step k (same meaning as the reference's f_iter) ; nullable */
+    double* rho;         /* [niter][batch]  nullable */
+    double* radius;      /* [niter][batch]  radius AFTER the update of step k ; nullable */
+    int* n_cg;           /* [niter][batch]  Hessian-vector products used by tCG in step k ; nullable */
+    int* on_boundary;    /* [niter][batch]  nullable */
+    int* accepted;       /* [niter][batch]  nullable */
+    double* x_iter;      /* [niter+1][batch][m][n][p] iterate history (save_x=True) ; nullable */
+    double* radius_inout;/* [batch] initial radii in, final radii out (warm restart, :37) ; nullable */
+    int* status;         /* [batch] OTN_STATUS_* bits ; nullable */
+    long long hvp_total; /* out: Hessian-vector products evaluated over all instances (incl. the model-value one, :67) */
+} otn_tr_report;
+
+void otn_tr_default_params(otn_tr_params* prm);
+/* x [batch][m][n][p] in/out: on return the iterate after the last step (x_iter[-1] of the reference) */
+int otn_tr_run(otn_problem* p, double* x, int batch, const otn_tr_params* prm, otn_tr_report* rep);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OTN_H */

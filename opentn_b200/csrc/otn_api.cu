@@ -1,0 +1,821 @@
+// libotn: C ABI (include/otn.h) over the sm_100a kernels.  No torch, no cuBLAS/cuSOLVER: every arithmetic site of the hot path
+// runs in the hand-written kernels of gemm_dmma.cuh / assemble.cuh / stiefel.cuh / tr.cuh.
+#include "../../include/otn.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "assemble.cuh"
+#include "gemm_dmma.cuh"
+#include "stiefel.cuh"
+#include "tr.cuh"
+
+using namespace otn;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return -1;
+}
+#define CUDA_TRY(expr)                                                                                          \
+    do {                                                                                                        \
+        cudaError_t e__ = (expr);                                                                               \
+        if (e__ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+#define OTN_TRY(expr)         \
+    do {                      \
+        int r__ = (expr);     \
+        if (r__ != 0) return r__; \
+    } while (0)
+
+extern "C" const char* otn_last_error(void) { return g_err.c_str(); }
+extern "C" int otn_version(void) { return 100; }
+
+static bool is_device_ptr(const void* p) {
+    if (p == nullptr) return false;
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// grow-only device buffer
+struct DevBuf {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr; cap = 0;
+        CUDA_TRY(cudaMalloc(&ptr, bytes));
+        cap = bytes;
+        return 0;
+    }
+    void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(ptr); }
+};
+
+// input: returns a device pointer holding `bytes` of `src` (in place when src is already on the device)
+static int stage_in(const void* src, size_t bytes, DevBuf& buf, cudaStream_t st, const void** out) {
+    if (src == nullptr) { *out = nullptr; return 0; }
+    if (is_device_ptr(src)) { *out = src; return 0; }
+    OTN_TRY(buf.ensure(bytes));
+    CUDA_TRY(cudaMemcpyAsync(buf.ptr, src, bytes, cudaMemcpyHostToDevice, st));
+    *out = buf.ptr;
+    return 0;
+}
+// output: device pointer to compute into; `finish_out` copies back if dst is a host pointer
+static int stage_out(void* dst, size_t bytes, DevBuf& buf, void** out) {
+    if (dst == nullptr) { *out = nullptr; return 0; }
+    if (is_device_ptr(dst)) { *out = dst; return 0; }
+    OTN_TRY(buf.ensure(bytes));
+    *out = buf.ptr;
+    return 0;
+}
+static int finish_out(void* dst, const void* dev, size_t bytes, cudaStream_t st) {
+    if (dst == nullptr || dst == dev) return 0;
+    CUDA_TRY(cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+template <class K>
+static int set_smem(K kern, size_t bytes) {
+    if (bytes > 227 * 1024) return fail("kernel needs %zu bytes of shared memory (> 227 KB): isometry too large for the fused path", bytes);
+    if (bytes > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// embedding index tables (transformations.py:431-444, 473-482)
+// ---------------------------------------------------------------------------------------------------------------------
+static int ipow(int b, int e) { int r = 1; while (e-- > 0) r *= b; return r; }
+
+static void build_embed_tables(int N, int d, std::vector<unsigned>& tab, std::vector<int>& inv) {
+    const int nax = 2 * N, nf = N / 2, q = ipow(d, 4), D = ipow(d, 2 * N);
+    // moveaxis(source_one_side -> destination_one_side) on the 2N axes of one side
+    std::vector<int> src, dst;
+    for (int i = 0; i < (N - 2) / 2; ++i) { src.push_back(2 + 4 * i); src.push_back(3 + 4 * i); }
+    for (int i = N; i < 2 * N - 2; ++i) dst.push_back(i);
+    std::vector<int> order;
+    for (int a = 0; a < nax; ++a) if (std::find(src.begin(), src.end(), a) == src.end()) order.push_back(a);
+    std::vector<std::pair<int, int>> ds;
+    for (size_t i = 0; i < src.size(); ++i) ds.push_back({dst[i], src[i]});
+    std::sort(ds.begin(), ds.end());
+    for (auto& pr : ds) order.insert(order.begin() + pr.first, pr.second);
+    tab.assign(2 * (size_t)D, 0u);
+    for (int shift = 0; shift < 2; ++shift) {
+        std::vector<int> perm(nax);  // new axis j <- old (tensored) axis perm[j]
+        for (int j = 0; j < nax; ++j) {
+            int jj = j;
+            if (shift) {  // transpose(idx), idx = [1..N-1, 0, N+1..2N-1, N]
+                jj = (j < N) ? ((j + 1) % N) : (N + ((j - N + 1) % N));
+            }
+            perm[j] = order[jj];
+        }
+        for (int r = 0; r < D; ++r) {
+            int rem = r, rt = 0;
+            for (int j = nax - 1; j >= 0; --j) {
+                const int digit = rem % d;
+                rem /= d;
+                rt += digit * ipow(d, nax - 1 - perm[j]);
+            }
+            unsigned packed = 0;
+            for (int f = 0; f < nf; ++f) packed |= (unsigned)((rt / ipow(q, nf - 1 - f)) % q) << (8 * f);
+            tab[(size_t)shift * D + r] = packed;
+        }
+    }
+    const int per = D / q;
+    inv.assign((size_t)2 * nf * q * per, 0);
+    for (int shift = 0; shift < 2; ++shift)
+        for (int f = 0; f < nf; ++f) {
+            std::vector<int> fill(q, 0);
+            for (int r = 0; r < D; ++r) {
+                const int i = (tab[(size_t)shift * D + r] >> (8 * f)) & 0xff;
+                inv[(((size_t)shift * nf + f) * q + i) * per + fill[i]++] = r;
+            }
+        }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// the handle
+// ---------------------------------------------------------------------------------------------------------------------
+struct otn_problem {
+    int N, d, m, K, model, metric, max_batch, n_targets, device;
+    int dim;        // isometry column count p (= d^N full, d^2 local)
+    int n, p, np;   // isometry shape
+    int D, q, nf;   // superoperator side; local superoperator side; kron factors
+    long long SZ;   // D*D
+    double alpha0, alpha1;
+    cudaStream_t stream = nullptr;
+    // constants
+    double* T_re = nullptr;      // [n_targets][SZ]
+    double* im2 = nullptr;       // [n_targets]
+    int* tindex = nullptr;       // [max_batch]
+    unsigned* tab = nullptr; int* inv = nullptr;
+    // work matrices, per instance [m][SZ] unless noted
+    double *Y = nullptr, *P = nullptr, *G = nullptr, *W = nullptr, *Yd = nullptr, *Pd = nullptr;
+    double *Gd = nullptr;        // [2][SZ]
+    double *Wd = nullptr;        // [SZ]
+    // local model: [m][q*q] and per-factor partials [m][nf][q*q]
+    double *Yl = nullptr, *Yld = nullptr, *Wl = nullptr, *Wld = nullptr;
+    // small per-instance state
+    double *x = nullptr, *eta = nullptr, *zraw = nullptr, *zdraw = nullptr;   // [m][np]
+    double *part_f = nullptr, *part_s = nullptr;                              // [tiles]
+    int tiles = 0;
+    int cached_batch = 0;        // primal cache valid for this many instances (0 = none)
+    // staging for host callers
+    DevBuf in_x, in_eta, out_a, out_b, out_c, out_f, out_M;
+    TrState tr;                  // trust-region state (tr.cuh)
+    DevBuf tr_buf;
+    EmbedTables tables() const { return EmbedTables{tab, inv, D, q, nf}; }
+};
+
+static int check_batch(otn_problem* h, int batch) {
+    if (h == nullptr) return fail("null handle");
+    if (batch < 1 || batch > h->max_batch) return fail("batch %d outside [1, max_batch=%d]", batch, h->max_batch);
+    CUDA_TRY(cudaSetDevice(h->device));
+    return 0;
+}
+
+extern "C" void otn_destroy(otn_problem* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void* ptr : {(void*)h->T_re, (void*)h->im2, (void*)h->tindex, (void*)h->tab, (void*)h->inv, (void*)h->Y, (void*)h->P,
+                      (void*)h->G, (void*)h->W, (void*)h->Yd, (void*)h->Pd, (void*)h->Gd, (void*)h->Wd, (void*)h->Yl, (void*)h->Yld,
+                      (void*)h->Wl, (void*)h->Wld, (void*)h->x, (void*)h->eta, (void*)h->zraw, (void*)h->zdraw, (void*)h->part_f,
+                      (void*)h->part_s})
+        if (ptr) cudaFree(ptr);
+    for (DevBuf* b : {&h->in_x, &h->in_eta, &h->out_a, &h->out_b, &h->out_c, &h->out_f, &h->out_M, &h->tr_buf}) b->release();
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int otn_create(otn_problem** out, int N, int d, int m, int K, int model, int metric, int max_batch, int n_targets,
+                          const double* target_re, const double* target_im, int device) {
+    if (out == nullptr) return fail("out is null");
+    *out = nullptr;
+    if (d < 2 || N < 1 || m < 1 || K < 1 || max_batch < 1 || n_targets < 1) return fail("bad size argument");
+    if (model != OTN_MODEL_FULL && model != OTN_MODEL_LOCAL) return fail("model must be OTN_MODEL_FULL or OTN_MODEL_LOCAL");
+    if (model == OTN_MODEL_LOCAL && (N % 2 != 0)) return fail("Only even number of sites allowed");  // transformations.py:414
+    if (target_re == nullptr) return fail("target_re is null");
+    if (K > ASM_MAXK) return fail("Kraus rank %d > %d not supported", K, ASM_MAXK);
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail("device %d not available (%d CUDA devices)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail("libotn is built for sm_100a (B200); device %d is sm_%d%d", device, prop.major, prop.minor);
+
+    double dD = std::pow((double)d, 2.0 * N);
+    if (dD > 16384.0) return fail("D = d^(2N) too large");
+    otn_problem* h = new otn_problem();
+    h->N = N; h->d = d; h->m = m; h->K = K; h->model = model; h->max_batch = max_batch; h->n_targets = n_targets; h->device = device;
+    h->D = ipow(d, 2 * N);
+    h->SZ = (long long)h->D * h->D;
+    h->q = ipow(d, 4);
+    h->nf = N / 2;
+    h->dim = (model == OTN_MODEL_FULL) ? ipow(d, N) : d * d;
+    h->p = h->dim; h->n = h->dim * K; h->np = h->n * h->p;
+    if (h->p > ST_MAXP) { delete h; return fail("isometry with p = %d columns > %d not supported", h->dim, ST_MAXP); }
+    if (model == OTN_MODEL_LOCAL && (h->nf > 4 || h->q > 255)) { delete h; return fail("local model supports N <= 8 and d <= 3"); }
+    if ((long long)max_batch * m > 65535) { delete h; return fail("max_batch * m must be <= 65535 (split the batch)"); }
+    *out = h;  // from here on failures go through otn_destroy by the caller? no: clean up ourselves
+    auto bail = [&](int rc) { otn_destroy(h); *out = nullptr; return rc; };
+#define CREATE_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { fail("%s failed: %s", #expr, cudaGetErrorString(e__)); return bail(-1); } } while (0)
+    if (otn_set_metric(h, metric) != 0) return bail(-1);
+    CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    const size_t B = (size_t)max_batch, SZ = (size_t)h->SZ, M = (size_t)m;
+    // targets
+    CREATE_TRY(cudaMalloc(&h->T_re, n_targets * SZ * 8));
+    CREATE_TRY(cudaMemcpy(h->T_re, target_re, n_targets * SZ * 8, cudaMemcpyDefault));
+    {
+        std::vector<double> im2(n_targets, 0.0);
+        if (target_im != nullptr) {
+            std::vector<double> tmp(SZ);
+            for (int t = 0; t < n_targets; ++t) {
+                CREATE_TRY(cudaMemcpy(tmp.data(), target_im + (size_t)t * SZ, SZ * 8, cudaMemcpyDefault));
+                double s = 0.0;
+                for (size_t i = 0; i < SZ; ++i) s += tmp[i] * tmp[i];
+                im2[t] = s;
+            }
+        }
+        CREATE_TRY(cudaMalloc(&h->im2, n_targets * 8));
+        CREATE_TRY(cudaMemcpy(h->im2, im2.data(), n_targets * 8, cudaMemcpyHostToDevice));
+    }
+    CREATE_TRY(cudaMalloc(&h->tindex, B * 4));
+    CREATE_TRY(cudaMemset(h->tindex, 0, B * 4));
+    if (model == OTN_MODEL_LOCAL) {
+        std::vector<unsigned> tab; std::vector<int> inv;
+        build_embed_tables(N, d, tab, inv);
+        CREATE_TRY(cudaMalloc(&h->tab, tab.size() * 4));
+        CREATE_TRY(cudaMemcpy(h->tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMalloc(&h->inv, inv.size() * 4));
+        CREATE_TRY(cudaMemcpy(h->inv, inv.data(), inv.size() * 4, cudaMemcpyHostToDevice));
+        const size_t q2 = (size_t)h->q * h->q;
+        CREATE_TRY(cudaMalloc(&h->Yl, B * M * q2 * 8));
+        CREATE_TRY(cudaMalloc(&h->Yld, B * M * q2 * 8));
+        CREATE_TRY(cudaMalloc(&h->Wl, B * M * h->nf * q2 * 8));
+        CREATE_TRY(cudaMalloc(&h->Wld, B * M * h->nf * q2 * 8));
+    }
+    for (double** ptr : {&h->Y, &h->P, &h->G, &h->W, &h->Yd, &h->Pd}) CREATE_TRY(cudaMalloc(ptr, B * M * SZ * 8));
+    CREATE_TRY(cudaMalloc(&h->Gd, B * 2 * SZ * 8));
+    CREATE_TRY(cudaMalloc(&h->Wd, B * SZ * 8));
+    for (double** ptr : {&h->x, &h->eta, &h->zraw, &h->zdraw}) CREATE_TRY(cudaMalloc(ptr, B * M * h->np * 8));
+    h->tiles = gemm_plan(h->D, h->D, max_batch).tiles;
+    {   // the plan (hence the tile count) may differ for smaller batches: size for the worst case
+        int t1 = gemm_plan(h->D, h->D, 1).tiles;
+        h->tiles = std::max(h->tiles, t1);
+    }
+    CREATE_TRY(cudaMalloc(&h->part_f, B * h->tiles * 8));
+    CREATE_TRY(cudaMalloc(&h->part_s, B * h->tiles * 8));
+#undef CREATE_TRY
+    return 0;
+}
+
+extern "C" int otn_set_metric(otn_problem* h, int metric) {
+    if (!h) return fail("null handle");
+    if (metric == OTN_METRIC_EUCLIDEAN) { h->alpha0 = 1.0; h->alpha1 = 1.0; }         // stiefel.py:456-457
+    else if (metric == OTN_METRIC_CANONICAL) { h->alpha0 = 1.0; h->alpha1 = 0.5; }    // stiefel.py:458-459
+    else return fail("%d is not a valid metric value", metric);
+    h->metric = metric;
+    return 0;
+}
+
+extern "C" int otn_set_target_index(otn_problem* h, const int* index, int batch) {
+    OTN_TRY(check_batch(h, batch));
+    std::vector<int> host(batch);
+    CUDA_TRY(cudaMemcpy(host.data(), index, batch * 4, cudaMemcpyDefault));
+    for (int b = 0; b < batch; ++b)
+        if (host[b] < 0 || host[b] >= h->n_targets) return fail("target index %d of instance %d outside [0, %d)", host[b], b, h->n_targets);
+    CUDA_TRY(cudaMemcpy(h->tindex, host.data(), batch * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int otn_query(const otn_problem* h, int* n, int* pp, int* D, int* m, long long* ws) {
+    if (!h) return fail("null handle");
+    if (n) *n = h->n;
+    if (pp) *pp = h->p;
+    if (D) *D = h->D;
+    if (m) *m = h->m;
+    if (ws) *ws = (6LL * h->m + 3) * h->SZ * 8 + 4LL * h->m * h->np * 8;
+    return 0;
+}
+
+extern "C" void* otn_stream(const otn_problem* h) { return h ? (void*)h->stream : nullptr; }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// pipeline pieces (all enqueue on h->stream; x / eta are device pointers [batch][m][np])
+// ---------------------------------------------------------------------------------------------------------------------
+static GemmParams gp(const otn_problem* h, int batch, const int* active) {
+    GemmParams p{};
+    p.D = h->D; p.row0 = 0; p.rows = h->D; p.batch = batch; p.active = active; p.epi = EPI_NONE;
+    return p;
+}
+static inline double* layer_ptr(double* base, int l, long long SZ) { return base + (long long)l * SZ; }
+
+// layer superoperators Y_l (and tangents Yd_l) for all instances
+static int build_layers(otn_problem* h, const double* x, const double* eta, int batch, const int* active, bool primal) {
+    const int items = batch * h->m;
+    const bool tangent = eta != nullptr;
+    const size_t smem = (size_t)h->np * 8 * (tangent ? 2 : 1);
+    double* Yout = (h->model == OTN_MODEL_FULL) ? h->Y : h->Yl;
+    double* Ydout = (h->model == OTN_MODEL_FULL) ? h->Yd : h->Yld;
+    const long long ostride = (h->model == OTN_MODEL_FULL) ? h->SZ : (long long)h->q * h->q;
+    dim3 grid(h->dim, items);
+    if (tangent && primal) {
+        OTN_TRY(set_smem(assemble_kernel<true, true>, smem));
+        assemble_kernel<true, true><<<grid, ASM_THREADS, smem, h->stream>>>(x, eta, Yout, Ydout, ostride, h->dim, h->K, active, h->m);
+    } else if (tangent) {
+        OTN_TRY(set_smem(assemble_kernel<true, false>, smem));
+        assemble_kernel<true, false><<<grid, ASM_THREADS, smem, h->stream>>>(x, eta, Yout, Ydout, ostride, h->dim, h->K, active, h->m);
+    } else {
+        OTN_TRY(set_smem(assemble_kernel<false, true>, smem));
+        assemble_kernel<false, true><<<grid, ASM_THREADS, smem, h->stream>>>(x, eta, Yout, Ydout, ostride, h->dim, h->K, active, h->m);
+    }
+    CUDA_TRY(cudaGetLastError());
+    if (h->model == OTN_MODEL_LOCAL) {
+        dim3 g2((h->D + EMB_ROWS - 1) / EMB_ROWS, items);
+        const size_t sm2 = (size_t)h->q * h->q * 8 * 2;
+        if (tangent && primal) embed_kernel<true, true><<<g2, EMB_THREADS, sm2, h->stream>>>(h->Yl, h->Yld, h->Y, h->Yd, h->tables(), active, h->m);
+        else if (tangent) embed_kernel<true, false><<<g2, EMB_THREADS, sm2, h->stream>>>(h->Yl, h->Yld, h->Y, h->Yd, h->tables(), active, h->m);
+        else embed_kernel<false, true><<<g2, EMB_THREADS, sm2, h->stream>>>(h->Yl, h->Yld, h->Y, h->Yd, h->tables(), active, h->m);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return 0;
+}
+
+__global__ void resid_kernel(const double* __restrict__ Y, long long sY, const double* __restrict__ T, long long sT, const int* tindex,
+                             double* __restrict__ R, long long sR, const double* __restrict__ Rdot, long long sRd, double* partial,
+                             long long SZ, const int* active) {
+    // m == 1 only (no GEMM to fuse into): R = Y - T and partial = ||R||^2, or partial = <R, Rdot> when Rdot != nullptr
+    const int b = blockIdx.x;
+    if (active != nullptr && active[b] == 0) return;
+    __shared__ double red[8];
+    double s = 0.0;
+    if (Rdot == nullptr) {
+        const double* t = T + (long long)(tindex ? tindex[b] : 0) * sT;
+        for (long long i = threadIdx.x; i < SZ; i += blockDim.x) {
+            const double v = Y[b * sY + i] - t[i];
+            R[b * sR + i] = v;
+            s = fma(v, v, s);
+        }
+    } else {
+        for (long long i = threadIdx.x; i < SZ; i += blockDim.x) s = fma(R[b * sR + i], Rdot[b * sRd + i], s);
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < 8; ++w) tot += red[w];
+        partial[b] = tot;
+    }
+}
+
+// forward chain: P_l = Y_l P_{l-1}; the last product writes the residual R = M - Re T into G[m-1] (or M itself into Mout)
+static int forward_chain(otn_problem* h, int batch, const int* active, double* Mout, int* tiles_used) {
+    const long long SZ = h->SZ, S = (long long)h->m * SZ;
+    const int m = h->m;
+    *tiles_used = gemm_plan(h->D, h->D, batch).tiles;
+    if (m == 1) {
+        if (Mout) { CUDA_TRY(cudaMemcpyAsync(Mout, h->Y, (size_t)batch * SZ * 8, cudaMemcpyDeviceToDevice, h->stream)); return 0; }
+        resid_kernel<<<batch, 256, 0, h->stream>>>(h->Y, S, h->T_re, SZ, h->tindex, h->G, S, nullptr, 0, h->part_f, SZ, active);
+        *tiles_used = 1;
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
+    for (int l = 1; l < m; ++l) {
+        GemmParams p = gp(h, batch, active);
+        p.A1 = layer_ptr(h->Y, l, SZ); p.sA1 = S;
+        p.B1 = (l == 1) ? h->Y : layer_ptr(h->P, l - 1, SZ); p.sB1 = S;
+        if (l < m - 1) { p.C = layer_ptr(h->P, l, SZ); p.sC = S; }
+        else if (Mout) { p.C = Mout; p.sC = SZ; }
+        else {
+            p.C = layer_ptr(h->G, m - 1, SZ); p.sC = S;
+            p.epi = EPI_RESID; p.E = h->T_re; p.sE = SZ; p.e_index = h->tindex; p.partial = h->part_f;
+        }
+        CUDA_TRY(gemm_launch(p, false, false, h->stream));
+    }
+    return 0;
+}
+
+// reverse chain on the unscaled residual: G_{l-1} = Y_l^T G_l ; W_l = G_l P_{l-1}^T ; zraw_l = back_assemble(W_l)
+static int back_layer(otn_problem* h, int batch, const int* active, int l, const double* x, bool tangent, const double* eta) {
+    // pulls the cotangent of layer l (W_l, and for the tangent pass Wd) back to the isometry
+    const long long SZ = h->SZ, S = (long long)h->m * SZ;
+    const double* Wfull = (l == 0) ? h->G : layer_ptr(h->W, l, SZ);                  // W_0 = G_0
+    const double* Wdfull = nullptr; long long sWd = 0;
+    if (tangent) { Wdfull = (l == 0) ? h->Gd + (long long)h->tr.gd_final * SZ : h->Wd; sWd = (l == 0) ? 2 * SZ : SZ; }
+    const double* Wsup = Wfull; long long sW = S; const double* Wdsup = Wdfull; long long sWds = sWd; int nslices = 1;
+    if (h->model == OTN_MODEL_LOCAL) {
+        const int q2 = h->q * h->q;
+        dim3 g((h->nf * q2 + 7) / 8, batch);
+        const size_t sm = (size_t)q2 * 8 * 2;
+        if (!tangent) back_embed_kernel<false><<<g, BEM_THREADS, sm, h->stream>>>(Wfull, nullptr, S, 0, h->Yl, h->Yld, h->Wl, h->Wld, h->tables(), active, h->m, l);
+        else back_embed_kernel<true><<<g, BEM_THREADS, sm, h->stream>>>(Wfull, Wdfull, S, sWd, h->Yl, h->Yld, h->Wl, h->Wld, h->tables(), active, h->m, l);
+        CUDA_TRY(cudaGetLastError());
+        const long long ls = (long long)h->nf * q2;
+        Wsup = h->Wl + (long long)l * ls; sW = (long long)h->m * ls;
+        Wdsup = h->Wld + (long long)l * ls; sWds = sW;
+        nslices = h->nf;
+    }
+    const int dim = h->dim;
+    const size_t wsz = (size_t)dim * dim * (dim + 1);
+    dim3 grid(dim, batch);
+    if (!tangent) {
+        const size_t sm = (wsz + h->np) * 8;
+        OTN_TRY(set_smem(back_assemble_kernel<false>, sm));
+        back_assemble_kernel<false><<<grid, BAS_THREADS, sm, h->stream>>>(Wsup, nullptr, sW, 0, nslices, x, nullptr, h->zraw, nullptr, dim, h->K, active, h->m, l);
+    } else {
+        const size_t sm = (2 * wsz + 2 * h->np) * 8;
+        OTN_TRY(set_smem(back_assemble_kernel<true>, sm));
+        back_assemble_kernel<true><<<grid, BAS_THREADS, sm, h->stream>>>(Wsup, Wdsup, sW, sWds, nslices, x, eta, nullptr, h->zdraw, dim, h->K, active, h->m, l);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+static int reverse_chain(otn_problem* h, int batch, const int* active, const double* x) {
+    const long long SZ = h->SZ, S = (long long)h->m * SZ;
+    for (int l = h->m - 1; l >= 1; --l) {
+        GemmParams p = gp(h, batch, active);                       // W_l = G_l P_{l-1}^T
+        p.A1 = layer_ptr(h->G, l, SZ); p.sA1 = S;
+        p.B1 = (l == 1) ? h->Y : layer_ptr(h->P, l - 1, SZ); p.sB1 = S;
+        p.C = layer_ptr(h->W, l, SZ); p.sC = S;
+        CUDA_TRY(gemm_launch(p, false, true, h->stream));
+        GemmParams r = gp(h, batch, active);                       // G_{l-1} = Y_l^T G_l
+        r.A1 = layer_ptr(h->Y, l, SZ); r.sA1 = S;
+        r.B1 = layer_ptr(h->G, l, SZ); r.sB1 = S;
+        r.C = layer_ptr(h->G, l - 1, SZ); r.sC = S;
+        CUDA_TRY(gemm_launch(r, true, false, h->stream));
+        OTN_TRY(back_layer(h, batch, active, l, x, false, nullptr));
+    }
+    OTN_TRY(back_layer(h, batch, active, 0, x, false, nullptr));
+    return 0;
+}
+
+// tangent pass: needs the primal cache (Y, P, G, W, zraw, part_f) of the same x
+static int tangent_pass(otn_problem* h, int batch, const int* active, const double* x, const double* eta, bool layers_built) {
+    const long long SZ = h->SZ, S = (long long)h->m * SZ;
+    const int m = h->m;
+    if (!layers_built) OTN_TRY(build_layers(h, x, eta, batch, active, false));
+    // forward tangent: Pd_l = Yd_l P_{l-1} + Y_l Pd_{l-1};  last one is Mdot -> Gd[0], with <R, Mdot> partials
+    int cur = 0;
+    if (m == 1) {
+        CUDA_TRY(cudaMemcpy2DAsync(h->Gd, 2 * SZ * 8, h->Yd, S * 8, SZ * 8, batch, cudaMemcpyDeviceToDevice, h->stream));
+        resid_kernel<<<batch, 256, 0, h->stream>>>(nullptr, 0, nullptr, 0, nullptr, h->G, S, h->Gd, 2 * SZ, h->part_s, SZ, active);
+        CUDA_TRY(cudaGetLastError());
+    }
+    for (int l = 1; l < m; ++l) {
+        GemmParams p = gp(h, batch, active);
+        p.A1 = layer_ptr(h->Yd, l, SZ); p.sA1 = S;
+        p.B1 = (l == 1) ? h->Y : layer_ptr(h->P, l - 1, SZ); p.sB1 = S;
+        p.A2 = layer_ptr(h->Y, l, SZ); p.sA2 = S;
+        p.B2 = (l == 1) ? h->Yd : layer_ptr(h->Pd, l - 1, SZ); p.sB2 = S;
+        if (l < m - 1) { p.C = layer_ptr(h->Pd, l, SZ); p.sC = S; }
+        else {
+            p.C = h->Gd; p.sC = 2 * SZ;
+            p.epi = EPI_DOT; p.E = layer_ptr(h->G, m - 1, SZ); p.sE = S; p.partial = h->part_s;
+        }
+        CUDA_TRY(gemm_launch(p, false, false, h->stream));
+    }
+    // reverse tangent
+    for (int l = m - 1; l >= 1; --l) {
+        const double* Ghat = h->Gd + (long long)cur * SZ;
+        const double* Pprev = (l == 1) ? h->Y : layer_ptr(h->P, l - 1, SZ);
+        const double* Pdprev = (l == 1) ? h->Yd : layer_ptr(h->Pd, l - 1, SZ);
+        GemmParams p = gp(h, batch, active);                       // What_l = Ghat_l P_{l-1}^T + G_l Pd_{l-1}^T
+        p.A1 = Ghat; p.sA1 = 2 * SZ; p.B1 = Pprev; p.sB1 = S;
+        p.A2 = layer_ptr(h->G, l, SZ); p.sA2 = S; p.B2 = Pdprev; p.sB2 = S;
+        p.C = h->Wd; p.sC = SZ;
+        CUDA_TRY(gemm_launch(p, false, true, h->stream));
+        GemmParams r = gp(h, batch, active);                       // Ghat_{l-1} = Yd_l^T G_l + Y_l^T Ghat_l
+        r.A1 = layer_ptr(h->Yd, l, SZ); r.sA1 = S; r.B1 = layer_ptr(h->G, l, SZ); r.sB1 = S;
+        r.A2 = layer_ptr(h->Y, l, SZ); r.sA2 = S; r.B2 = Ghat; r.sB2 = 2 * SZ;
+        r.C = h->Gd + (long long)(1 - cur) * SZ; r.sC = 2 * SZ;
+        CUDA_TRY(gemm_launch(r, true, false, h->stream));
+        OTN_TRY(back_layer(h, batch, active, l, x, true, eta));
+        cur = 1 - cur;
+    }
+    h->tr.gd_final = cur;
+    OTN_TRY(back_layer(h, batch, active, 0, x, true, eta));
+    return 0;
+}
+
+static int riem_launch(otn_problem* h, int batch, const int* active, int tiles, const double* x, const double* eta, bool hvp,
+                       double* f, double* rgrad, double* egrad, double* heta) {
+    RiemParams P{};
+    P.x = x; P.zraw = h->zraw; P.eta = eta; P.zdraw = h->zdraw; P.part_f = h->part_f; P.part_s = h->part_s; P.im2 = h->im2;
+    P.tindex = h->tindex; P.tiles = tiles; P.f_out = f; P.rgrad = rgrad; P.egrad = egrad; P.heta = heta;
+    P.n = h->n; P.p = h->p; P.m = h->m; P.alpha0 = h->alpha0; P.alpha1 = h->alpha1; P.active = active;
+    const size_t pp = (size_t)h->p * h->p;
+    if (!hvp) {
+        const size_t sm = (2 * (size_t)h->np + 8 * pp) * 8;
+        OTN_TRY(set_smem(riem_kernel<false>, sm));
+        riem_kernel<false><<<batch * h->m, ST_THREADS, sm, h->stream>>>(P);
+    } else {
+        const size_t sm = (4 * (size_t)h->np + 8 * pp) * 8;
+        OTN_TRY(set_smem(riem_kernel<true>, sm));
+        riem_kernel<true><<<batch * h->m, ST_THREADS, sm, h->stream>>>(P);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// device-level building blocks shared with the trust-region driver
+int otn_dev_cost(otn_problem* h, const double* x, int batch, const int* active, double* f) {
+    int tiles;
+    OTN_TRY(build_layers(h, x, nullptr, batch, active, true));
+    OTN_TRY(forward_chain(h, batch, active, nullptr, &tiles));
+    cost_from_partials_kernel<<<(batch + 127) / 128, 128, 0, h->stream>>>(h->part_f, tiles, h->im2, h->tindex, f, batch, active);
+    CUDA_TRY(cudaGetLastError());
+    h->cached_batch = 0;
+    return 0;
+}
+int otn_dev_cost_grad(otn_problem* h, const double* x, int batch, const int* active, double* f, double* rgrad, double* egrad) {
+    int tiles;
+    OTN_TRY(build_layers(h, x, nullptr, batch, active, true));
+    OTN_TRY(forward_chain(h, batch, active, nullptr, &tiles));
+    OTN_TRY(reverse_chain(h, batch, active, x));
+    OTN_TRY(riem_launch(h, batch, active, tiles, x, nullptr, false, f, rgrad, egrad, nullptr));
+    h->tr.tiles = tiles;
+    return 0;
+}
+int otn_dev_hvp(otn_problem* h, const double* x, const double* eta, int batch, const int* active, double* heta) {
+    OTN_TRY(tangent_pass(h, batch, active, x, eta, false));
+    OTN_TRY(riem_launch(h, batch, active, h->tr.tiles, x, eta, true, nullptr, nullptr, nullptr, heta));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// public model / cost entry points
+// ---------------------------------------------------------------------------------------------------------------------
+static size_t xbytes(const otn_problem* h, int batch) { return (size_t)batch * h->m * h->np * 8; }
+
+// keep a device copy of x for the cached-HVP path when the caller's x is a host array (device x is referenced in place
+// only during the call, so it is copied too)
+static int keep_x(otn_problem* h, const double* xdev, int batch) {
+    if (xdev != h->x) CUDA_TRY(cudaMemcpyAsync(h->x, xdev, xbytes(h, batch), cudaMemcpyDeviceToDevice, h->stream));
+    return 0;
+}
+
+extern "C" int otn_model(otn_problem* h, const double* x, int batch, double* M) {
+    OTN_TRY(check_batch(h, batch));
+    if (!x || !M) return fail("null argument");
+    const void* xd; void* Md; int tiles;
+    OTN_TRY(stage_in(x, xbytes(h, batch), h->in_x, h->stream, &xd));
+    OTN_TRY(stage_out(M, (size_t)batch * h->SZ * 8, h->out_M, &Md));
+    OTN_TRY(build_layers(h, (const double*)xd, nullptr, batch, nullptr, true));
+    OTN_TRY(forward_chain(h, batch, nullptr, (double*)Md, &tiles));
+    OTN_TRY(finish_out(M, Md, (size_t)batch * h->SZ * 8, h->stream));
+    h->cached_batch = 0;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int otn_cost(otn_problem* h, const double* x, int batch, double* f) {
+    OTN_TRY(check_batch(h, batch));
+    if (!x || !f) return fail("null argument");
+    const void* xd; void* fd;
+    OTN_TRY(stage_in(x, xbytes(h, batch), h->in_x, h->stream, &xd));
+    OTN_TRY(stage_out(f, (size_t)batch * 8, h->out_f, &fd));
+    OTN_TRY(otn_dev_cost(h, (const double*)xd, batch, nullptr, (double*)fd));
+    OTN_TRY(finish_out(f, fd, (size_t)batch * 8, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int otn_cost_grad(otn_problem* h, const double* x, int batch, double* f, double* rgrad, double* egrad) {
+    OTN_TRY(check_batch(h, batch));
+    if (!x) return fail("null argument");
+    const void* xd; void *fd, *gd, *ed;
+    OTN_TRY(stage_in(x, xbytes(h, batch), h->in_x, h->stream, &xd));
+    OTN_TRY(stage_out(f, (size_t)batch * 8, h->out_f, &fd));
+    OTN_TRY(stage_out(rgrad, xbytes(h, batch), h->out_a, &gd));
+    OTN_TRY(stage_out(egrad, xbytes(h, batch), h->out_b, &ed));
+    OTN_TRY(keep_x(h, (const double*)xd, batch));
+    OTN_TRY(otn_dev_cost_grad(h, h->x, batch, nullptr, (double*)fd, (double*)gd, (double*)ed));
+    h->cached_batch = batch;
+    OTN_TRY(finish_out(f, fd, (size_t)batch * 8, h->stream));
+    OTN_TRY(finish_out(rgrad, gd, xbytes(h, batch), h->stream));
+    OTN_TRY(finish_out(egrad, ed, xbytes(h, batch), h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int otn_triple(otn_problem* h, const double* x, const double* eta, int batch, double* f, double* rgrad, double* heta) {
+    OTN_TRY(check_batch(h, batch));
+    if (!x || !eta) return fail("null argument");
+    const void *xd, *ed; void *fd, *gd, *hd;
+    OTN_TRY(stage_in(x, xbytes(h, batch), h->in_x, h->stream, &xd));
+    OTN_TRY(stage_in(eta, xbytes(h, batch), h->in_eta, h->stream, &ed));
+    OTN_TRY(stage_out(f, (size_t)batch * 8, h->out_f, &fd));
+    OTN_TRY(stage_out(rgrad, xbytes(h, batch), h->out_a, &gd));
+    OTN_TRY(stage_out(heta, xbytes(h, batch), h->out_c, &hd));
+    OTN_TRY(keep_x(h, (const double*)xd, batch));
+    int tiles;
+    // primal + tangent layers in one assembly pass, then forward / reverse / tangent chains
+    OTN_TRY(build_layers(h, h->x, (const double*)ed, batch, nullptr, true));
+    OTN_TRY(forward_chain(h, batch, nullptr, nullptr, &tiles));
+    h->tr.tiles = tiles;
+    OTN_TRY(reverse_chain(h, batch, nullptr, h->x));
+    OTN_TRY(tangent_pass(h, batch, nullptr, h->x, (const double*)ed, true));
+    OTN_TRY(riem_launch(h, batch, nullptr, tiles, h->x, (const double*)ed, true, (double*)fd, (double*)gd, nullptr, (double*)hd));
+    h->cached_batch = batch;
+    OTN_TRY(finish_out(f, fd, (size_t)batch * 8, h->stream));
+    OTN_TRY(finish_out(rgrad, gd, xbytes(h, batch), h->stream));
+    OTN_TRY(finish_out(heta, hd, xbytes(h, batch), h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int otn_hvp_cached(otn_problem* h, const double* eta, int batch, double* heta) {
+    OTN_TRY(check_batch(h, batch));
+    if (!eta || !heta) return fail("null argument");
+    if (h->cached_batch < batch) return fail("no primal cache for %d instances: call otn_cost_grad or otn_triple first", batch);
+    const void* ed; void* hd;
+    OTN_TRY(stage_in(eta, xbytes(h, batch), h->in_eta, h->stream, &ed));
+    OTN_TRY(stage_out(heta, xbytes(h, batch), h->out_c, &hd));
+    OTN_TRY(otn_dev_hvp(h, h->x, (const double*)ed, batch, nullptr, (double*)hd));
+    OTN_TRY(finish_out(heta, hd, xbytes(h, batch), h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// stateless representation / manifold entry points: per-thread scratch + the legacy default stream of `device`
+// ---------------------------------------------------------------------------------------------------------------------
+struct Scratch { DevBuf a, b, c, o, s; };
+static thread_local Scratch g_scratch[16];
+
+static int use_device(int device) {
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev || device >= 16) return fail("device %d not available", device);
+    CUDA_TRY(cudaSetDevice(device));
+    return 0;
+}
+
+extern "C" int otn_ortho2super(const double* x, int count, int dim, int K, double* Y, int device) {
+    if (!x || !Y || count < 1 || dim < 1 || K < 1) return fail("bad argument");
+    if (K > ASM_MAXK) return fail("Kraus rank %d > %d not supported", K, ASM_MAXK);
+    OTN_TRY(use_device(device));
+    Scratch& S = g_scratch[device];
+    const size_t np = (size_t)dim * K * dim, d4 = (size_t)dim * dim * dim * dim;
+    const void* xd; void* Yd;
+    OTN_TRY(stage_in(x, count * np * 8, S.a, 0, &xd));
+    OTN_TRY(stage_out(Y, count * d4 * 8, S.o, &Yd));
+    OTN_TRY(set_smem(assemble_kernel<false, true>, np * 8));
+    for (int c0 = 0; c0 < count; c0 += 32768) {
+        const int c = std::min(32768, count - c0);
+        assemble_kernel<false, true><<<dim3(dim, c), ASM_THREADS, np * 8>>>((const double*)xd + c0 * np, nullptr, (double*)Yd + c0 * d4,
+                                                                              nullptr, (long long)d4, dim, K, nullptr, 1);
+    }
+    CUDA_TRY(cudaGetLastError());
+    OTN_TRY(finish_out(Y, Yd, count * d4 * 8, 0));
+    CUDA_TRY(cudaDeviceSynchronize());
+    return 0;
+}
+
+extern "C" int otn_embed_local(const double* Yloc, int count, int N, int d, int shift_pbc, double* Yfull, int device) {
+    if (!Yloc || !Yfull || count < 1) return fail("bad argument");
+    if (N % 2 != 0) return fail("Only even number of sites allowed");
+    if (N / 2 > 4 || ipow(d, 4) > 255) return fail("embedding supports N <= 8 and d <= 3");
+    OTN_TRY(use_device(device));
+    Scratch& S = g_scratch[device];
+    std::vector<unsigned> tab; std::vector<int> inv;
+    build_embed_tables(N, d, tab, inv);
+    const int D = ipow(d, 2 * N), q = ipow(d, 4);
+    OTN_TRY(S.s.ensure(tab.size() * 4));
+    CUDA_TRY(cudaMemcpy(S.s.ptr, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+    const size_t q2 = (size_t)q * q, SZ = (size_t)D * D;
+    const void* yd; void* Yd;
+    OTN_TRY(stage_in(Yloc, count * q2 * 8, S.a, 0, &yd));
+    OTN_TRY(stage_out(Yfull, count * SZ * 8, S.o, &Yd));
+    EmbedTables T{S.s.as<unsigned>(), nullptr, D, q, N / 2};
+    // layer parity selects the table: pass m = 2 and offset the item index so that (item % 2) == shift
+    // (simplest: launch per item with an explicit table pointer)
+    if (shift_pbc) T.tab += D;
+    for (int c = 0; c < count; ++c) {
+        EmbedTables Tc = T;
+        embed_kernel<false, true><<<dim3((D + EMB_ROWS - 1) / EMB_ROWS, 1), EMB_THREADS, q2 * 16>>>(
+            (const double*)yd + c * q2, nullptr, (double*)Yd + c * SZ, nullptr, Tc, nullptr, 2);
+    }
+    CUDA_TRY(cudaGetLastError());
+    OTN_TRY(finish_out(Yfull, Yd, count * SZ * 8, 0));
+    CUDA_TRY(cudaDeviceSynchronize());
+    return 0;
+}
+
+extern "C" int otn_compose(const double* Ys, int count, int m, int D, double* M, int device) {
+    if (!Ys || !M || count < 1 || m < 1 || D < 1) return fail("bad argument");
+    OTN_TRY(use_device(device));
+    Scratch& S = g_scratch[device];
+    const size_t SZ = (size_t)D * D;
+    const void* yd; void* Md;
+    OTN_TRY(stage_in(Ys, count * m * SZ * 8, S.a, 0, &yd));
+    OTN_TRY(stage_out(M, count * SZ * 8, S.o, &Md));
+    if (m == 1) { CUDA_TRY(cudaMemcpy(Md, yd, count * SZ * 8, cudaMemcpyDeviceToDevice)); }
+    OTN_TRY(S.b.ensure(2 * count * SZ * 8));
+    const double* prev = (const double*)yd; long long sprev = (long long)m * SZ;
+    for (int l = 1; l < m; ++l) {
+        GemmParams p{};
+        p.D = D; p.rows = D; p.batch = count; p.epi = EPI_NONE;
+        p.A1 = (const double*)yd + l * SZ; p.sA1 = (long long)m * SZ;
+        p.B1 = prev; p.sB1 = sprev;
+        double* outp = (l == m - 1) ? (double*)Md : S.b.as<double>() + (size_t)(l & 1) * count * SZ;
+        p.C = outp; p.sC = SZ;
+        CUDA_TRY(gemm_launch(p, false, false, 0));
+        prev = outp; sprev = SZ;
+    }
+    OTN_TRY(finish_out(M, Md, count * SZ * 8, 0));
+    CUDA_TRY(cudaDeviceSynchronize());
+    return 0;
+}
+
+static int project_like(const double* x, const double* z, int count, int n, int p, int mode, double a0, double a1, double* out, int device) {
+    if (!x || !z || !out || count < 1 || n < p || p < 1) return fail("bad argument");
+    if (p > ST_MAXP) return fail("p = %d > %d not supported", p, ST_MAXP);
+    OTN_TRY(use_device(device));
+    Scratch& S = g_scratch[device];
+    const size_t np = (size_t)n * p;
+    const void *xd, *zd; void* od;
+    OTN_TRY(stage_in(x, count * np * 8, S.a, 0, &xd));
+    OTN_TRY(stage_in(z, count * np * 8, S.b, 0, &zd));
+    OTN_TRY(stage_out(out, count * np * 8, S.o, &od));
+    const size_t sm = (2 * np + 2 * (size_t)p * p) * 8;
+    OTN_TRY(set_smem(project_kernel, sm));
+    project_kernel<<<count, ST_THREADS, sm>>>((const double*)xd, (const double*)zd, (double*)od, n, p, mode, a0, a1);
+    CUDA_TRY(cudaGetLastError());
+    OTN_TRY(finish_out(out, od, count * np * 8, 0));
+    CUDA_TRY(cudaDeviceSynchronize());
+    return 0;
+}
+extern "C" int otn_project(const double* x, const double* z, int count, int n, int p, double* out, int device) {
+    return project_like(x, z, count, n, p, 0, 1.0, 1.0, out, device);
+}
+extern "C" int otn_rgrad_map(const double* x, const double* z, int count, int n, int p, double a0, double a1, double* out, int device) {
+    if (!(a0 > 0.0) || !(a1 > 0.0)) return fail("alpha0 and alpha1 must be positive");
+    return project_like(x, z, count, n, p, 1, a0, a1, out, device);
+}
+
+extern "C" int otn_retract(const double* x, const double* eta, int count, int n, int p, double* out, int* status, int device) {
+    if (!x || !out || count < 1 || n < p || p < 1) return fail("bad argument");
+    if (p > ST_MAXP) return fail("p = %d > %d not supported", p, ST_MAXP);
+    OTN_TRY(use_device(device));
+    Scratch& S = g_scratch[device];
+    const size_t np = (size_t)n * p;
+    const void *xd, *ed; void *od, *sd;
+    OTN_TRY(stage_in(x, count * np * 8, S.a, 0, &xd));
+    OTN_TRY(stage_in(eta, count * np * 8, S.b, 0, &ed));
+    OTN_TRY(stage_out(out, count * np * 8, S.o, &od));
+    OTN_TRY(stage_out(status, (size_t)count * 4, S.s, &sd));
+    if (sd) CUDA_TRY(cudaMemset(sd, 0, (size_t)count * 4));
+    const size_t sm = (np + 3 * (size_t)p * p) * 8;
+    OTN_TRY(set_smem(retract_kernel, sm));
+    retract_kernel<<<count, ST_THREADS, sm>>>((const double*)xd, (const double*)ed, (double*)od, n, p, 1, nullptr, (int*)sd);
+    CUDA_TRY(cudaGetLastError());
+    OTN_TRY(finish_out(out, od, count * np * 8, 0));
+    OTN_TRY(finish_out(status, sd, (size_t)count * 4, 0));
+    CUDA_TRY(cudaDeviceSynchronize());
+    return 0;
+}
+
+extern "C" int otn_canonical_dot(const double* x, const double* a, const double* b, int batch, int m, int n, int p, double* out, int device) {
+    if (!x || !a || !b || !out || batch < 1 || m < 1 || n < p || p < 1) return fail("bad argument");
+    if (p > ST_MAXP) return fail("p = %d > %d not supported", p, ST_MAXP);
+    OTN_TRY(use_device(device));
+    Scratch& S = g_scratch[device];
+    const size_t bytes = (size_t)batch * m * n * p * 8;
+    const void *xd, *ad, *bd; void* od;
+    OTN_TRY(stage_in(x, bytes, S.a, 0, &xd));
+    OTN_TRY(stage_in(a, bytes, S.b, 0, &ad));
+    OTN_TRY(stage_in(b, bytes, S.c, 0, &bd));
+    OTN_TRY(stage_out(out, (size_t)batch * 8, S.o, &od));
+    const size_t sm = (3 * (size_t)n * p + 2 * (size_t)p * p) * 8;
+    OTN_TRY(set_smem(cdot_kernel, sm));
+    cdot_kernel<<<batch, ST_THREADS, sm>>>((const double*)xd, (const double*)ad, (const double*)bd, (double*)od, n, p, m, nullptr);
+    CUDA_TRY(cudaGetLastError());
+    OTN_TRY(finish_out(out, od, (size_t)batch * 8, 0));
+    CUDA_TRY(cudaDeviceSynchronize());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// trust region
+// ---------------------------------------------------------------------------------------------------------------------
+#include "tr_driver.inl"

@@ -1,0 +1,352 @@
+// Small batched Stiefel-manifold kernels (sites F, G-epilogue, H, J, K of the hot path).  One CTA per isometry
+// ("item" = instance * m + layer); everything for one (n,p) isometry lives in shared memory; HBM-bound:
+// algorithmic traffic = (#inputs + #outputs) * n*p*8 bytes per item.
+//
+//   riem_kernel<HVP>   egrad -> rgrad                      gradient_ambient2riemannian, opentn/stiefel.py:398-409
+//                      (+ HVP) d(rgrad)[eta] -> connection riemannian_connection, stiefel.py:468-475
+//                      -> tangent projection               what parametrization_from_tangent (:266-300) keeps of z
+//   project_kernel     Z - X sym(X^T Z)                    project, stiefel.py:23-30
+//   retract_kernel     polar factor of X + eta             polar_decomposition_rectangular, stiefel.py:323-330
+//                      as (X+eta) (A^T A)^{-1/2}, A = X+eta, inverse square root by a parallel cyclic Jacobi eigensolver
+//   cdot_kernel        sum_l tr(a_l^T (I - x_l x_l^T/2) b_l)  canonical_metric, stiefel.py:76-83  (== the Euclidean dot of the
+//                      (A-upper, B) coefficient vectors used by truncated_cg, trust_region_rcopt.py:111-131)
+#pragma once
+#include "otn_common.cuh"
+
+namespace otn {
+
+constexpr int ST_THREADS = 256;
+constexpr int ST_MAXP = 16;  // p <= 16 (dim = d^N <= 16 or d^2 = 4)
+
+// G[i][j] = sum_r A[r][i] * B[r][j]   (p x p), fixed summation order => deterministic
+__device__ __forceinline__ void gram(const double* A, const double* B, double* G, int n, int p) {
+    for (int o = threadIdx.x; o < p * p; o += ST_THREADS) {
+        const int i = o / p, j = o - i * p;
+        double s = 0.0;
+        for (int r = 0; r < n; ++r) s = fma(A[r * p + i], B[r * p + j], s);
+        G[o] = s;
+    }
+}
+
+// Out[r][j] = alpha * Out[r][j] + sum_i A[r][i] * G[i][j]   (GT: use G[j][i])
+template <bool GT>
+__device__ __forceinline__ void addmul(double* Out, double alpha, const double* A, const double* G, int n, int p) {
+    for (int o = threadIdx.x; o < n * p; o += ST_THREADS) {
+        const int r = o / p, j = o - r * p;
+        double s = alpha * Out[o];
+        for (int i = 0; i < p; ++i) s = fma(A[r * p + i], GT ? G[j * p + i] : G[i * p + j], s);
+        Out[o] = s;
+    }
+}
+
+struct RiemParams {
+    const double* x;       // [items][n*p]
+    const double* zraw;    // [items][n*p]  unscaled Euclidean gradient:  egrad = zraw / f
+    const double* eta;     // HVP: tangent direction
+    const double* zdraw;   // HVP: unscaled derivative part, see below
+    const double* part_f;  // [batch][tiles] partial sums of ||Re R||^2
+    const double* part_s;  // HVP: [batch][tiles] partial sums of <Re R, Mdot>
+    const double* im2;     // [n_targets] ||Im T||^2
+    const int* tindex;     // [batch] target id (nullptr = 0)
+    int tiles;
+    double* f_out;         // [batch] (written by layer 0)
+    double* rgrad;         // [items][n*p]  (nullable in HVP mode)
+    double* egrad;         // optional
+    double* heta;          // HVP out
+    int n, p, m;
+    double alpha0, alpha1;
+    const int* active;
+};
+
+// smem layout: X | E(eta) | Z->nu | Zd->Dnu->z | grams (8 * p*p)
+template <bool HVP>
+__global__ void __launch_bounds__(ST_THREADS) riem_kernel(const RiemParams P) {
+    extern __shared__ __align__(16) double sm[];
+    const int item = blockIdx.x, inst = item / P.m, layer = item - inst * P.m;
+    if (P.active != nullptr && P.active[inst] == 0) return;
+    const int n = P.n, p = P.p, np = n * p, pp = p * p;
+    double* X = sm;
+    double* E = X + np;
+    double* Z = E + (HVP ? np : 0);
+    double* Zd = Z + np;
+    double* G = Zd + (HVP ? np : 0);
+    __shared__ double sc[2];
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int t = 0; t < P.tiles; ++t) s += P.part_f[(long long)inst * P.tiles + t];
+        s += P.im2[P.tindex ? P.tindex[inst] : 0];
+        const double f = sqrt(s);
+        sc[0] = f;
+        if (HVP) {
+            double d = 0.0;
+            for (int t = 0; t < P.tiles; ++t) d += P.part_s[(long long)inst * P.tiles + t];
+            sc[1] = d;  // <Re R, Mdot> = f * fdot
+        }
+        if (layer == 0 && P.f_out != nullptr) P.f_out[inst] = f;
+    }
+    __syncthreads();
+    const double f = sc[0], inv_f = 1.0 / f;
+    const long long base = (long long)item * np;
+    for (int i = threadIdx.x; i < np; i += ST_THREADS) {
+        X[i] = P.x[base + i];
+        const double zr = P.zraw[base + i];
+        Z[i] = zr * inv_f;
+        if (HVP) {
+            E[i] = P.eta[base + i];
+            // Zdot = (1/f) zdraw - (fdot / f^2) zraw,   fdot = sc[1] / f
+            Zd[i] = P.zdraw[base + i] * inv_f - zr * (sc[1] * inv_f * inv_f * inv_f);
+        }
+    }
+    __syncthreads();
+    if (!HVP && P.egrad != nullptr)
+        for (int i = threadIdx.x; i < np; i += ST_THREADS) P.egrad[base + i] = Z[i];
+    const double a0 = P.alpha0, a1 = P.alpha1;
+    const double c1 = 0.5 * ((1.0 / a1) - (2.0 / a0)), c2 = 0.5 * (1.0 / a1), kap = (a0 - a1) / a0;
+    double* XZ = G;            // X^T Z
+    double* XZd = G + pp;      // X^T Zd
+    double* XE = G + 2 * pp;   // X^T eta
+    double* EZ = G + 3 * pp;   // eta^T Z
+    double* Gn = G + 4 * pp;   // c1 XZ - c2 XZ^T
+    double* Gd = G + 5 * pp;
+    double* T0 = G + 6 * pp;
+    double* T1 = G + 7 * pp;
+    gram(X, Z, XZ, n, p);
+    if (HVP) { gram(X, Zd, XZd, n, p); gram(X, E, XE, n, p); gram(E, Z, EZ, n, p); }
+    __syncthreads();
+    for (int o = threadIdx.x; o < pp; o += ST_THREADS) {
+        const int i = o / p, j = o - i * p, ot = j * p + i;
+        Gn[o] = c1 * XZ[o] - c2 * XZ[ot];
+        if (HVP) Gd[o] = c1 * (EZ[o] + XZd[o]) - c2 * (XZd[ot] + EZ[ot]);
+    }
+    __syncthreads();
+    // Dnu = Zd/a0 + eta Gn + X Gd   (in place over Zd; must precede the in-place update of Z)
+    if (HVP) {
+        addmul<false>(Zd, 1.0 / a0, E, Gn, n, p);
+        __syncthreads();
+        addmul<false>(Zd, 1.0, X, Gd, n, p);
+    }
+    // nu = Z/a0 + X Gn   (in place over Z)
+    addmul<false>(Z, 1.0 / a0, X, Gn, n, p);
+    __syncthreads();
+    if (P.rgrad != nullptr)
+        for (int i = threadIdx.x; i < np; i += ST_THREADS) P.rgrad[base + i] = Z[i];
+    if (!HVP) return;
+    double* Nu = Z;
+    double* EN = XZ;   // eta^T nu   (reuse)
+    double* XN = XZd;  // X^T nu
+    gram(E, Nu, EN, n, p);
+    gram(X, Nu, XN, n, p);
+    __syncthreads();
+    // Gz = (EN + EN^T)/2 - kap (XE XN^T + XN XE^T)
+    for (int o = threadIdx.x; o < pp; o += ST_THREADS) {
+        const int i = o / p, j = o - i * p;
+        double s = 0.0;
+        for (int k = 0; k < p; ++k) s += XE[i * p + k] * XN[j * p + k] + XN[i * p + k] * XE[j * p + k];
+        T0[o] = 0.5 * (EN[o] + EN[j * p + i]) - kap * s;
+    }
+    __syncthreads();
+    // z = Dnu + X Gz + kap (eta XN^T + nu XE^T)
+    addmul<false>(Zd, 1.0, X, T0, n, p);
+    __syncthreads();
+    if (kap != 0.0) {
+        for (int o = threadIdx.x; o < pp; o += ST_THREADS) { T0[o] = kap * XN[o]; T1[o] = kap * XE[o]; }
+        __syncthreads();
+        addmul<true>(Zd, 1.0, E, T0, n, p);
+        __syncthreads();
+        addmul<true>(Zd, 1.0, Nu, T1, n, p);
+        __syncthreads();
+    }
+    // H eta = z - X sym(X^T z)
+    gram(X, Zd, T0, n, p);
+    __syncthreads();
+    for (int o = threadIdx.x; o < pp; o += ST_THREADS) {
+        const int i = o / p, j = o - i * p;
+        T1[o] = -0.5 * (T0[o] + T0[j * p + i]);
+    }
+    __syncthreads();
+    addmul<false>(Zd, 1.0, X, T1, n, p);
+    __syncthreads();
+    for (int i = threadIdx.x; i < np; i += ST_THREADS) P.heta[base + i] = Zd[i];
+}
+
+// cost only: f[b] = sqrt(sum partial + im2)
+__global__ void cost_from_partials_kernel(const double* part_f, int tiles, const double* im2, const int* tindex, double* f,
+                                          int batch, const int* active) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    if (active != nullptr && active[b] == 0) return;
+    double s = 0.0;
+    for (int t = 0; t < tiles; ++t) s += part_f[(long long)b * tiles + t];
+    f[b] = sqrt(s + im2[tindex ? tindex[b] : 0]);
+}
+
+// out = a0inv * Z + c1 X X^T Z - c2 X Z^T X   (general metric; (1,1) => project for tangent-normal split)
+// mode 0: project (Z - X sym(X^T Z));  mode 1: gradient_ambient2riemannian(alpha0, alpha1)
+__global__ void __launch_bounds__(ST_THREADS) project_kernel(const double* __restrict__ x, const double* __restrict__ z,
+                                                             double* __restrict__ out, int n, int p, int mode, double a0, double a1) {
+    extern __shared__ __align__(16) double sm[];
+    const int np = n * p, pp = p * p;
+    double* X = sm;
+    double* Z = X + np;
+    double* G = Z + np;
+    double* Gn = G + pp;
+    const long long base = (long long)blockIdx.x * np;
+    for (int i = threadIdx.x; i < np; i += ST_THREADS) { X[i] = x[base + i]; Z[i] = z[base + i]; }
+    __syncthreads();
+    gram(X, Z, G, n, p);
+    __syncthreads();
+    double c1, c2, s0;
+    if (mode == 0) { c1 = -0.5; c2 = 0.5; s0 = 1.0; }
+    else { c1 = 0.5 * ((1.0 / a1) - (2.0 / a0)); c2 = 0.5 * (1.0 / a1); s0 = 1.0 / a0; }
+    for (int o = threadIdx.x; o < pp; o += ST_THREADS) {
+        const int i = o / p, j = o - i * p;
+        Gn[o] = c1 * G[o] - c2 * G[j * p + i];
+    }
+    __syncthreads();
+    addmul<false>(Z, s0, X, Gn, n, p);
+    __syncthreads();
+    for (int i = threadIdx.x; i < np; i += ST_THREADS) out[base + i] = Z[i];
+}
+
+// ---- symmetric eigen-decomposition of a p x p SPD matrix by parallel cyclic Jacobi (one warp) -----------------------
+// S (in/out: diag holds eigenvalues), V (out: eigenvectors in columns).  p <= ST_MAXP.  Round-robin pairing gives
+// floor(p/2) disjoint rotations per step; column and row phases are separated by __syncwarp.
+__device__ inline void jacobi_eig_warp(double* S, double* V, int p, double* cs /* 2*ST_MAXP */, int* pairs /* 2*ST_MAXP */) {
+    const int lane = threadIdx.x & 31;
+    const int pe = (p + 1) & ~1;  // even player count (a dummy sits out when p is odd)
+    const int half = pe / 2;
+    for (int i = lane; i < p * p; i += 32) V[i] = (i / p == i % p) ? 1.0 : 0.0;
+    __syncwarp();
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0;
+        for (int i = lane; i < p * p; i += 32) {
+            const int r = i / p, c = i % p;
+            if (r != c) off += S[i] * S[i];
+        }
+        off = warp_sum(off);
+        double dg = 0.0;
+        for (int i = lane; i < p; i += 32) dg += S[i * p + i] * S[i * p + i];
+        dg = warp_sum(dg);
+        if (off <= 1e-34 * dg) break;
+        for (int step = 0; step < pe - 1; ++step) {
+            // round-robin tournament: player pe-1 fixed, others rotate
+            if (lane < half) {
+                int a = (lane == 0) ? pe - 1 : (step + lane) % (pe - 1);
+                int b = (step + pe - 1 - lane) % (pe - 1);
+                int i = min(a, b), j = max(a, b);
+                double c = 1.0, s = 0.0;
+                if (j < p) {
+                    const double apq = S[i * p + j];
+                    if (apq != 0.0) {
+                        const double theta = (S[j * p + j] - S[i * p + i]) / (2.0 * apq);
+                        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                        c = 1.0 / sqrt(t * t + 1.0);
+                        s = t * c;
+                    }
+                } else { i = j = 0; }
+                pairs[2 * lane] = i; pairs[2 * lane + 1] = j;
+                cs[2 * lane] = c; cs[2 * lane + 1] = s;
+            }
+            __syncwarp();
+            // column phase: S <- S J, V <- V J
+            for (int w = lane; w < half * p; w += 32) {
+                const int q = w / p, r = w - q * p, i = pairs[2 * q], j = pairs[2 * q + 1];
+                if (i == j) continue;
+                const double c = cs[2 * q], s = cs[2 * q + 1];
+                const double si = S[r * p + i], sj = S[r * p + j];
+                S[r * p + i] = c * si - s * sj; S[r * p + j] = s * si + c * sj;
+                const double vi = V[r * p + i], vj = V[r * p + j];
+                V[r * p + i] = c * vi - s * vj; V[r * p + j] = s * vi + c * vj;
+            }
+            __syncwarp();
+            // row phase: S <- J^T S
+            for (int w = lane; w < half * p; w += 32) {
+                const int q = w / p, r = w - q * p, i = pairs[2 * q], j = pairs[2 * q + 1];
+                if (i == j) continue;
+                const double c = cs[2 * q], s = cs[2 * q + 1];
+                const double si = S[i * p + r], sj = S[j * p + r];
+                S[i * p + r] = c * si - s * sj; S[j * p + r] = s * si + c * sj;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// retract: out = A (A^T A)^{-1/2},  A = X + eta.   status[item] = 1 if A^T A is not positive definite.
+__global__ void __launch_bounds__(ST_THREADS) retract_kernel(const double* __restrict__ x, const double* __restrict__ eta,
+                                                             double* __restrict__ out, int n, int p, int m, const int* active,
+                                                             int* status) {
+    extern __shared__ __align__(16) double sm[];
+    const int item = blockIdx.x;
+    if (active != nullptr && active[item / m] == 0) return;
+    const int np = n * p, pp = p * p;
+    double* A = sm;
+    double* S = A + np;
+    double* V = S + pp;
+    double* Q = V + pp;
+    __shared__ double cs[2 * ST_MAXP];
+    __shared__ int pairs[2 * ST_MAXP];
+    const long long base = (long long)item * np;
+    for (int i = threadIdx.x; i < np; i += ST_THREADS) A[i] = x[base + i] + (eta ? eta[base + i] : 0.0);
+    __syncthreads();
+    gram(A, A, S, n, p);
+    __syncthreads();
+    if (threadIdx.x < 32) jacobi_eig_warp(S, V, p, cs, pairs);
+    __syncthreads();
+    // Q = V diag(lambda^{-1/2}) V^T
+    for (int o = threadIdx.x; o < pp; o += ST_THREADS) {
+        const int i = o / p, j = o - i * p;
+        double s = 0.0;
+        for (int k = 0; k < p; ++k) s += V[i * p + k] * V[j * p + k] / sqrt(S[k * p + k]);
+        Q[o] = s;
+    }
+    if (threadIdx.x == 0 && status != nullptr) {
+        int bad = 0;
+        for (int k = 0; k < p; ++k) if (!(S[k * p + k] > 0.0)) bad = 1;
+        if (bad) atomicOr(&status[item / m], 2);
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < np; o += ST_THREADS) {
+        const int r = o / p, j = o - r * p;
+        double s = 0.0;
+        for (int i = 0; i < p; ++i) s = fma(A[r * p + i], Q[i * p + j], s);
+        out[base + o] = s;
+    }
+}
+
+// canonical dot per instance: out[b] = sum_l [ <a_l, b_l> - 1/2 <x_l^T a_l, x_l^T b_l> ];  one CTA per instance
+__global__ void __launch_bounds__(ST_THREADS) cdot_kernel(const double* __restrict__ x, const double* __restrict__ a,
+                                                          const double* __restrict__ bb, double* __restrict__ out, int n, int p,
+                                                          int m, const int* active) {
+    extern __shared__ __align__(16) double sm[];
+    const int inst = blockIdx.x;
+    if (active != nullptr && active[inst] == 0) return;
+    const int np = n * p, pp = p * p;
+    double* X = sm;
+    double* A = X + np;
+    double* B = A + np;
+    double* GA = B + np;
+    double* GB = GA + pp;
+    __shared__ double red[ST_THREADS / 32];
+    double total = 0.0;  // only meaningful in thread 0
+    for (int l = 0; l < m; ++l) {
+        const long long base = ((long long)inst * m + l) * np;
+        for (int i = threadIdx.x; i < np; i += ST_THREADS) { X[i] = x[base + i]; A[i] = a[base + i]; B[i] = bb[base + i]; }
+        __syncthreads();
+        gram(X, A, GA, n, p);
+        gram(X, B, GB, n, p);
+        double s = 0.0;
+        for (int i = threadIdx.x; i < np; i += ST_THREADS) s = fma(A[i], B[i], s);
+        __syncthreads();
+        for (int o = threadIdx.x; o < pp; o += ST_THREADS) s = fma(-0.5 * GA[o], GB[o], s);
+        s = warp_sum(s);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int w = 0; w < ST_THREADS / 32; ++w) total += red[w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[inst] = total;
+}
+
+}  // namespace otn

@@ -1,0 +1,240 @@
+// Batched Riemannian trust region + Steihaug truncated CG (site K of the hot path), lock-step over instances with
+// per-instance masks.  Restates opentn/trust_region_rcopt.py:5-166 on (n,p) tangent matrices with the canonical inner
+// product  <a,b>_x = sum_l tr(a_l^T (I - x_l x_l^T/2) b_l), which equals the Euclidean dot product of the reference's
+// (A-upper, B) coefficient vectors (stiefel.py:266-300, 453-466), so every scalar the reference's tCG computes
+// (rsq, dHd, alpha, beta, t, rho) is reproduced without ever forming X_perp.
+#pragma once
+#include "otn_common.cuh"
+#include "stiefel.cuh"
+
+namespace otn {
+
+struct TrState {
+    int gd_final = 0;   // which half of the Gd ping-pong buffer holds Ghat_0 after the tangent reverse sweep
+    int tiles = 1;      // partial-sum tiles of the cached forward pass
+    // device arrays (allocated by the driver)
+    double *g = nullptr, *r = nullptr, *z = nullptr, *d = nullptr, *Hd = nullptr, *xn = nullptr;   // [B][m][np]
+    double *radius = nullptr, *fx = nullptr, *fn = nullptr, *rsq = nullptr, *stoptol = nullptr, *gz = nullptr, *zHz = nullptr;
+    int *tcg_active = nullptr, *on_boundary = nullptr, *n_cg = nullptr, *status = nullptr, *accepted = nullptr, *n_active = nullptr;
+    double* rho = nullptr;
+    int cap_batch = 0;
+};
+
+struct TcgParams {
+    const double* x;
+    double *r, *z, *d;
+    const double* Hd;
+    const double* g;
+    double *radius, *rsq, *stoptol;
+    int *tcg_active, *on_boundary, *n_cg, *status, *n_active;
+    int n, p, m, maxiter;
+    double abstol, reltol;
+};
+
+// block-wide sum of `nv` per-thread values, fixed order (warp shuffle tree, then warps in index order)
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* red /* [NV][8] */, double (&out)[NV]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double s = warp_sum(v[i]);
+        if (lane == 0) red[i * 8 + warp] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double s = 0.0;
+        for (int w = 0; w < ST_THREADS / 32; ++w) s += red[i * 8 + w];
+        out[i] = s;
+    }
+    __syncthreads();
+}
+
+// r = g, z = 0, d = -g, rsq = <g,g>, stoptol = max(abstol, reltol sqrt(rsq))     trust_region_rcopt.py:110-114
+__global__ void __launch_bounds__(ST_THREADS) tcg_init_kernel(const TcgParams P) {
+    extern __shared__ __align__(16) double sm[];
+    const int inst = blockIdx.x;
+    const int np = P.n * P.p, pp = P.p * P.p;
+    double* X = sm;
+    double* A = X + np;
+    double* GA = A + np;
+    __shared__ double red[8];
+    double v[1] = {0.0};
+    for (int l = 0; l < P.m; ++l) {
+        const long long base = ((long long)inst * P.m + l) * np;
+        for (int i = threadIdx.x; i < np; i += ST_THREADS) {
+            const double gv = P.g[base + i];
+            X[i] = P.x[base + i]; A[i] = gv;
+            P.r[base + i] = gv; P.z[base + i] = 0.0; P.d[base + i] = -gv;
+            v[0] = fma(gv, gv, v[0]);
+        }
+        __syncthreads();
+        gram(X, A, GA, P.n, P.p);
+        __syncthreads();
+        for (int o = threadIdx.x; o < pp; o += ST_THREADS) v[0] = fma(-0.5 * GA[o], GA[o], v[0]);
+        __syncthreads();
+    }
+    double out[1];
+    block_sum<1>(v, red, out);
+    if (threadIdx.x == 0) {
+        P.rsq[inst] = out[0];
+        P.stoptol[inst] = fmax(P.abstol, P.reltol * sqrt(out[0]));
+        P.tcg_active[inst] = 1;
+        P.on_boundary[inst] = 0;
+        P.n_cg[inst] = 0;
+    }
+}
+
+// one tCG iteration given Hd = H d                                              trust_region_rcopt.py:116-132, 137-166
+__global__ void __launch_bounds__(ST_THREADS) tcg_step_kernel(const TcgParams P) {
+    extern __shared__ __align__(16) double sm[];
+    const int inst = blockIdx.x;
+    if (P.tcg_active[inst] == 0) return;
+    const int np = P.n * P.p, pp = P.p * P.p;
+    double* X = sm;
+    double* A = X + np;       // d
+    double* B = A + np;       // Hd
+    double* C = B + np;       // z  (pass A) / r (pass B)
+    double* GA = C + np;
+    double* GB = GA + pp;
+    double* GC = GB + pp;
+    __shared__ double red[4 * 8];
+    __shared__ double sc[4];
+    __shared__ int flag;
+    // ---- pass A: dHd, dsq, zd, zz
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int l = 0; l < P.m; ++l) {
+        const long long base = ((long long)inst * P.m + l) * np;
+        for (int i = threadIdx.x; i < np; i += ST_THREADS) {
+            const double dv = P.d[base + i], hv = P.Hd[base + i], zv = P.z[base + i];
+            X[i] = P.x[base + i]; A[i] = dv; B[i] = hv; C[i] = zv;
+            v[0] = fma(dv, hv, v[0]); v[1] = fma(dv, dv, v[1]); v[2] = fma(zv, dv, v[2]); v[3] = fma(zv, zv, v[3]);
+        }
+        __syncthreads();
+        gram(X, A, GA, P.n, P.p); gram(X, B, GB, P.n, P.p); gram(X, C, GC, P.n, P.p);
+        __syncthreads();
+        for (int o = threadIdx.x; o < pp; o += ST_THREADS) {
+            v[0] = fma(-0.5 * GA[o], GB[o], v[0]); v[1] = fma(-0.5 * GA[o], GA[o], v[1]);
+            v[2] = fma(-0.5 * GC[o], GA[o], v[2]); v[3] = fma(-0.5 * GC[o], GC[o], v[3]);
+        }
+        __syncthreads();
+    }
+    double o4[4];
+    block_sum<4>(v, red, o4);
+    if (threadIdx.x == 0) {
+        const double dHd = o4[0], dsq = o4[1], zd = o4[2], zz = o4[3];
+        const double radius = P.radius[inst], rsq = P.rsq[inst];
+        double t = 0.0;
+        int fl = 0;  // 0 = interior CG update, 1 = move to boundary and stop, 2 = failed
+        if (dsq != 0.0) {  // _move_to_boundary (:137-152); dsq == 0 leaves z unchanged
+            const double pq = zd / dsq, q = (zz - radius * radius) / dsq;
+            const double disc = pq * pq - q;
+            if (disc < 0.0) { fl = 2; atomicOr(&P.status[inst], 4); }      // solve_quadratic_equation raises (:159-160)
+            else if (pq == 0.0) t = sqrt(-q);
+            else {
+                const double x1 = -(pq + (pq > 0.0 ? 1.0 : -1.0) * sqrt(disc));
+                const double x2 = q / x1;
+                t = fmax(x1, x2);
+            }
+        }
+        const double alpha = rsq / dHd;
+        if (fl == 0 && (dHd <= 0.0 || alpha > t)) fl = 1;
+        if (fl == 0 && !(alpha == alpha)) { fl = 2; atomicOr(&P.status[inst], 1); }
+        sc[0] = t; sc[1] = alpha;
+        flag = fl;
+        P.n_cg[inst] += 1;
+    }
+    __syncthreads();
+    const int fl = flag;
+    if (fl == 2) { if (threadIdx.x == 0) P.tcg_active[inst] = 0; return; }
+    if (fl == 1) {  // z += t d ; on_boundary                                    (:120-122)
+        const double t = sc[0];
+        for (int l = 0; l < P.m; ++l) {
+            const long long base = ((long long)inst * P.m + l) * np;
+            for (int i = threadIdx.x; i < np; i += ST_THREADS) P.z[base + i] = fma(t, P.d[base + i], P.z[base + i]);
+        }
+        if (threadIdx.x == 0) { P.tcg_active[inst] = 0; P.on_boundary[inst] = 1; }
+        return;
+    }
+    // ---- pass B: r += alpha Hd ; z += alpha d ; rsq_next                        (:124-126)
+    const double alpha = sc[1];
+    double w[1] = {0.0};
+    for (int l = 0; l < P.m; ++l) {
+        const long long base = ((long long)inst * P.m + l) * np;
+        for (int i = threadIdx.x; i < np; i += ST_THREADS) {
+            const double rv = fma(alpha, P.Hd[base + i], P.r[base + i]);
+            P.r[base + i] = rv;
+            P.z[base + i] = fma(alpha, P.d[base + i], P.z[base + i]);
+            X[i] = P.x[base + i]; C[i] = rv;
+            w[0] = fma(rv, rv, w[0]);
+        }
+        __syncthreads();
+        gram(X, C, GC, P.n, P.p);
+        __syncthreads();
+        for (int o = threadIdx.x; o < pp; o += ST_THREADS) w[0] = fma(-0.5 * GC[o], GC[o], w[0]);
+        __syncthreads();
+    }
+    double o1[1];
+    block_sum<1>(w, red, o1);
+    if (threadIdx.x == 0) {
+        const double rsq_next = o1[0];
+        int stop = 0;
+        if (sqrt(rsq_next) <= P.stoptol[inst]) stop = 1;                          // (:127-129)
+        if (P.n_cg[inst] >= P.maxiter) stop = 1;                                  // (:115, 133-134)
+        sc[2] = rsq_next / P.rsq[inst];                                           // beta (:130)
+        P.rsq[inst] = rsq_next;
+        flag = stop;
+        if (stop) P.tcg_active[inst] = 0; else atomicAdd(P.n_active, 1);
+    }
+    __syncthreads();
+    if (flag) return;
+    const double beta = sc[2];
+    for (int l = 0; l < P.m; ++l) {                                               // d = -r + beta d (:131)
+        const long long base = ((long long)inst * P.m + l) * np;
+        for (int i = threadIdx.x; i < np; i += ST_THREADS) P.d[base + i] = fma(beta, P.d[base + i], -P.r[base + i]);
+    }
+}
+
+struct TrUpdateParams {
+    double *radius, *rho;
+    const double *fx, *fn, *gz, *zHz;
+    const int* on_boundary;
+    int *accepted, *status;
+    double rho_trust, maxradius;
+    int batch;
+    // history rows for this iteration (nullable)
+    double *h_rho, *h_radius; int *h_ncg, *h_onb, *h_acc; const int* n_cg;
+};
+
+// rho, radius update, acceptance                                                  trust_region_rcopt.py:67-77
+__global__ void tr_update_kernel(const TrUpdateParams P) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= P.batch) return;
+    const double rho = (P.fn[b] - P.fx[b]) / (P.gz[b] + 0.5 * P.zHz[b]);
+    double radius = P.radius[b];
+    if (rho < 0.25) radius *= 0.25;
+    else if (rho > 0.75 && P.on_boundary[b]) radius = fmin(2.0 * radius, P.maxradius);
+    const int acc = rho > P.rho_trust ? 1 : 0;
+    if (!(rho == rho)) atomicOr(&P.status[b], 1);
+    P.radius[b] = radius; P.rho[b] = rho; P.accepted[b] = acc;
+    if (P.h_rho) P.h_rho[b] = rho;
+    if (P.h_radius) P.h_radius[b] = radius;
+    if (P.h_ncg) P.h_ncg[b] = P.n_cg[b];
+    if (P.h_onb) P.h_onb[b] = P.on_boundary[b];
+    if (P.h_acc) P.h_acc[b] = acc;
+}
+
+// x <- x_next where accepted
+__global__ void select_copy_kernel(double* __restrict__ x, const double* __restrict__ xn, const int* __restrict__ accepted, long long per) {
+    const int b = blockIdx.y;
+    if (!accepted[b]) return;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.x * blockDim.x)
+        x[b * per + i] = xn[b * per + i];
+}
+
+__global__ void fill_kernel(double* a, double v, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = v;
+}
+
+}  // namespace otn

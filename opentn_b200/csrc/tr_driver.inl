@@ -1,0 +1,133 @@
+// Host driver of the batched trust region (included by otn_api.cu).  Mirrors riemannian_trust_region_optimize
+// (opentn/trust_region_rcopt.py:5-89): per iteration  grad -> tCG (hess @ d) -> retract -> f(x), f(x_next) -> rho -> radius/accept.
+
+extern "C" void otn_tr_default_params(otn_tr_params* prm) {
+    if (!prm) return;
+    prm->rho_trust = 0.125; prm->radius_init = 0.01; prm->maxradius = 0.1; prm->niter = 20;
+    prm->tcg_maxiter = 0; prm->tcg_abstol = 1e-8; prm->tcg_reltol = 1e-6;
+}
+
+static int tr_alloc(otn_problem* h) {
+    TrState& t = h->tr;
+    if (t.cap_batch >= h->max_batch) return 0;
+    const size_t B = (size_t)h->max_batch, V = B * h->m * h->np;
+    const size_t bytes = 6 * V * 8 + 8 * B * 8 + 8 * B * 4 + 64;
+    OTN_TRY(h->tr_buf.ensure(bytes));
+    char* base = h->tr_buf.as<char>();
+    auto take = [&](size_t nbytes) { char* r = base; base += (nbytes + 15) / 16 * 16; return r; };
+    t.g = (double*)take(V * 8); t.r = (double*)take(V * 8); t.z = (double*)take(V * 8); t.d = (double*)take(V * 8);
+    t.Hd = (double*)take(V * 8); t.xn = (double*)take(V * 8);
+    t.radius = (double*)take(B * 8); t.fx = (double*)take(B * 8); t.fn = (double*)take(B * 8); t.rsq = (double*)take(B * 8);
+    t.stoptol = (double*)take(B * 8); t.gz = (double*)take(B * 8); t.zHz = (double*)take(B * 8); t.rho = (double*)take(B * 8);
+    t.tcg_active = (int*)take(B * 4); t.on_boundary = (int*)take(B * 4); t.n_cg = (int*)take(B * 4); t.status = (int*)take(B * 4);
+    t.accepted = (int*)take(B * 4); t.n_active = (int*)take(16);
+    t.cap_batch = h->max_batch;
+    return 0;
+}
+
+static int cdot_launch(otn_problem* h, const double* x, const double* a, const double* b, int batch, double* out) {
+    const size_t sm = (3 * (size_t)h->np + 2 * (size_t)h->p * h->p) * 8;
+    OTN_TRY(set_smem(cdot_kernel, sm));
+    cdot_kernel<<<batch, ST_THREADS, sm, h->stream>>>(x, a, b, out, h->n, h->p, h->m, nullptr);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int otn_tr_run(otn_problem* h, double* x, int batch, const otn_tr_params* prm_in, otn_tr_report* rep) {
+    OTN_TRY(check_batch(h, batch));
+    if (!x) return fail("null argument");
+    otn_tr_params prm;
+    if (prm_in) prm = *prm_in; else otn_tr_default_params(&prm);
+    if (!(prm.rho_trust >= 0.0 && prm.rho_trust < 0.25)) return fail("need 0 <= rho_trust < 0.25");   // trust_region_rcopt.py:47
+    if (prm.niter < 0) return fail("niter must be >= 0");
+    OTN_TRY(tr_alloc(h));
+    TrState& t = h->tr;
+    cudaStream_t st = h->stream;
+    const size_t V = xbytes(h, batch);
+    const long long per = (long long)h->m * h->np;
+    const int dof = h->p * (h->p - 1) / 2 + h->p * (h->n - h->p);
+    const int maxiter = prm.tcg_maxiter > 0 ? prm.tcg_maxiter : 2 * h->m * dof;                        // :107
+
+    const void* xin;
+    OTN_TRY(stage_in(x, V, h->in_x, st, &xin));
+    if (xin != h->x) CUDA_TRY(cudaMemcpyAsync(h->x, xin, V, cudaMemcpyDeviceToDevice, st));
+    if (rep && rep->radius_inout) CUDA_TRY(cudaMemcpyAsync(t.radius, rep->radius_inout, (size_t)batch * 8, cudaMemcpyDefault, st));
+    else { fill_kernel<<<(batch + 127) / 128, 128, 0, st>>>(t.radius, prm.radius_init, batch); CUDA_TRY(cudaGetLastError()); }
+    CUDA_TRY(cudaMemsetAsync(t.status, 0, (size_t)batch * 4, st));
+    if (rep) rep->hvp_total = 0;
+    long long hvps = 0;
+    auto hist_d = [&](double* base, int k) -> double* { return base ? base + (size_t)k * batch : nullptr; };
+    auto hist_i = [&](int* base, int k) -> int* { return base ? base + (size_t)k * batch : nullptr; };
+    // history rows may live on the host: stage per-iteration rows through small device buffers
+    DevBuf& hb = h->out_b;
+    OTN_TRY(hb.ensure((size_t)batch * 8 * 2 + (size_t)batch * 4 * 3 + 64));
+    double* d_hrho = hb.as<double>(); double* d_hrad = d_hrho + batch;
+    int* d_hncg = (int*)(d_hrad + batch); int* d_honb = d_hncg + batch; int* d_hacc = d_honb + batch;
+
+    if (rep && rep->x_iter) CUDA_TRY(cudaMemcpyAsync(rep->x_iter, h->x, V, cudaMemcpyDefault, st));     // x_iter = [x] (:52)
+
+    TcgParams tp{};
+    tp.x = h->x; tp.r = t.r; tp.z = t.z; tp.d = t.d; tp.Hd = t.Hd; tp.g = t.g; tp.radius = t.radius; tp.rsq = t.rsq;
+    tp.stoptol = t.stoptol; tp.tcg_active = t.tcg_active; tp.on_boundary = t.on_boundary; tp.n_cg = t.n_cg; tp.status = t.status;
+    tp.n_active = t.n_active; tp.n = h->n; tp.p = h->p; tp.m = h->m; tp.maxiter = maxiter; tp.abstol = prm.tcg_abstol; tp.reltol = prm.tcg_reltol;
+    const size_t pp = (size_t)h->p * h->p;
+    const size_t sm_init = (2 * (size_t)h->np + pp) * 8, sm_step = (4 * (size_t)h->np + 3 * pp) * 8;
+    OTN_TRY(set_smem(tcg_init_kernel, sm_init));
+    OTN_TRY(set_smem(tcg_step_kernel, sm_step));
+    const size_t sm_ret = ((size_t)h->np + 3 * pp) * 8;
+    OTN_TRY(set_smem(retract_kernel, sm_ret));
+
+    for (int k = 0; k < prm.niter; ++k) {
+        // grad = gradfunc(x) ; fx = f(x)  (same primal pass)                                       (:59, :63)
+        OTN_TRY(otn_dev_cost_grad(h, h->x, batch, nullptr, t.fx, t.g, nullptr));
+        if (rep && rep->f_iter) CUDA_TRY(cudaMemcpyAsync(hist_d(rep->f_iter, k), t.fx, (size_t)batch * 8, cudaMemcpyDefault, st));
+        // eta, on_boundary = truncated_cg(grad, hess, radius)                                      (:61)
+        tcg_init_kernel<<<batch, ST_THREADS, sm_init, st>>>(tp);
+        CUDA_TRY(cudaGetLastError());
+        int n_active = batch;
+        for (int j = 0; j < maxiter && n_active > 0; ++j) {
+            OTN_TRY(otn_dev_hvp(h, h->x, t.d, batch, t.tcg_active, t.Hd));
+            hvps += n_active;
+            CUDA_TRY(cudaMemsetAsync(t.n_active, 0, 4, st));
+            tcg_step_kernel<<<batch, ST_THREADS, sm_step, st>>>(tp);
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpyAsync(&n_active, t.n_active, 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+        }
+        // model decrease  <grad, eta> + 1/2 <eta, hess @ eta>                                       (:67)
+        OTN_TRY(otn_dev_hvp(h, h->x, t.z, batch, nullptr, t.Hd));
+        hvps += batch;
+        OTN_TRY(cdot_launch(h, h->x, t.g, t.z, batch, t.gz));
+        OTN_TRY(cdot_launch(h, h->x, t.z, t.Hd, batch, t.zHz));
+        // x_next = retract(x, eta) ; f(x_next)                                                     (:62, :67)
+        retract_kernel<<<batch * h->m, ST_THREADS, sm_ret, st>>>(h->x, t.z, t.xn, h->n, h->p, h->m, nullptr, t.status);
+        CUDA_TRY(cudaGetLastError());
+        OTN_TRY(otn_dev_cost(h, t.xn, batch, nullptr, t.fn));
+        TrUpdateParams up{};
+        up.radius = t.radius; up.rho = t.rho; up.fx = t.fx; up.fn = t.fn; up.gz = t.gz; up.zHz = t.zHz; up.on_boundary = t.on_boundary;
+        up.accepted = t.accepted; up.status = t.status; up.rho_trust = prm.rho_trust; up.maxradius = prm.maxradius; up.batch = batch;
+        up.h_rho = d_hrho; up.h_radius = d_hrad; up.h_ncg = d_hncg; up.h_onb = d_honb; up.h_acc = d_hacc; up.n_cg = t.n_cg;
+        tr_update_kernel<<<(batch + 127) / 128, 128, 0, st>>>(up);
+        CUDA_TRY(cudaGetLastError());
+        select_copy_kernel<<<dim3(8, batch), 256, 0, st>>>(h->x, t.xn, t.accepted, per);                 // (:76-77)
+        CUDA_TRY(cudaGetLastError());
+        if (rep) {
+            if (rep->rho) CUDA_TRY(cudaMemcpyAsync(hist_d(rep->rho, k), d_hrho, (size_t)batch * 8, cudaMemcpyDefault, st));
+            if (rep->radius) CUDA_TRY(cudaMemcpyAsync(hist_d(rep->radius, k), d_hrad, (size_t)batch * 8, cudaMemcpyDefault, st));
+            if (rep->n_cg) CUDA_TRY(cudaMemcpyAsync(hist_i(rep->n_cg, k), d_hncg, (size_t)batch * 4, cudaMemcpyDefault, st));
+            if (rep->on_boundary) CUDA_TRY(cudaMemcpyAsync(hist_i(rep->on_boundary, k), d_honb, (size_t)batch * 4, cudaMemcpyDefault, st));
+            if (rep->accepted) CUDA_TRY(cudaMemcpyAsync(hist_i(rep->accepted, k), d_hacc, (size_t)batch * 4, cudaMemcpyDefault, st));
+            if (rep->x_iter) CUDA_TRY(cudaMemcpyAsync(rep->x_iter + (size_t)(k + 1) * batch * per, h->x, V, cudaMemcpyDefault, st));
+        }
+        CUDA_TRY(cudaStreamSynchronize(st));   // history staging buffers are reused next iteration
+    }
+    h->cached_batch = 0;
+    if (x != h->x) CUDA_TRY(cudaMemcpyAsync(x, h->x, V, cudaMemcpyDefault, st));
+    if (rep) {
+        if (rep->radius_inout) CUDA_TRY(cudaMemcpyAsync(rep->radius_inout, t.radius, (size_t)batch * 8, cudaMemcpyDefault, st));
+        if (rep->status) CUDA_TRY(cudaMemcpyAsync(rep->status, t.status, (size_t)batch * 4, cudaMemcpyDefault, st));
+        rep->hvp_total = hvps;
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}

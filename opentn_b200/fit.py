@@ -1,0 +1,281 @@
+"""`StiefelFit`: the cost closure of the reference notebooks as an object the accelerated path can recognise.
+
+The reference builds, in user code (experiments/trust_region_pauli_noise.ipynb cell 21),
+
+    f_stiefel = lambda xi: frobenius_norm(model_stiefel_local(xi, N, d), exp_Lvec)
+
+and hands it to `gradient_stiefel_vec(xi, f_stiefel, metric)` / `riemannian_hessian_vec(xi, f_stiefel, metric)`, which
+differentiate the opaque closure with JAX.  Here the same closure is `StiefelFit(exp_Lvec, model='local', N=N, d=d)`:
+callable as `f(xi) -> float`, and carrying batched `.cost / .cost_grad / .triple / .hvp / .tr_run` methods that run
+on the GPU through libotn (include/otn.h).  Arbitrary Python closures are not supported (no CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import MODEL_FULL, MODEL_LOCAL, METRIC_CANONICAL, METRIC_EUCLIDEAN, OtnError, as_f64, check, ptr
+
+_METRICS = {"euclidean": METRIC_EUCLIDEAN, "canonical": METRIC_CANONICAL}
+
+
+def metric_id(metric: str) -> int:
+    if metric not in _METRICS:
+        raise ValueError(f"{metric} is not a valid metric value")  # same message as stiefel.py:461
+    return _METRICS[metric]
+
+
+def _is_cuda_tensor(a) -> bool:
+    return hasattr(a, "is_cuda") and bool(a.is_cuda)
+
+
+class _Handle:
+    """Owns one otn_problem."""
+
+    def __init__(self, N, d, m, K, model, metric, max_batch, targets_re, targets_im, device):
+        lib = _lib.load()
+        self._lib = lib
+        self.h = C.c_void_p()
+        n_targets = targets_re.shape[0]
+        check(lib.otn_create(C.byref(self.h), N, d, m, K, model, metric, max_batch, n_targets, ptr(targets_re),
+                             ptr(targets_im), device))
+        n, p, D, mm = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        ws = C.c_longlong()
+        check(lib.otn_query(self.h, C.byref(n), C.byref(p), C.byref(D), C.byref(mm), C.byref(ws)))
+        self.n, self.p, self.D, self.m, self.workspace_bytes = n.value, p.value, D.value, mm.value, ws.value
+        self.max_batch = max_batch
+
+    def close(self):
+        if self.h:
+            self._lib.otn_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class StiefelFit:
+    """Cost `|| model(xs) - target ||_F` on a product of Stiefel manifolds, evaluated on the GPU.
+
+    model='local': `model_stiefel_local(xs, N, d)` (optimization.py:106-137), isometries (d^2 K, d^2)
+    model='full' : `model_Ys_stiefel(xs)`          (optimization.py:147-151), isometries (d^N K, d^N)
+    `target` is one (D, D) array (real or complex) or a stack (n_targets, D, D); with several targets each instance of a
+    batch selects its own through `target_index`.
+    """
+
+    def __init__(self, target, model="local", N=None, d=2, metric="canonical", max_batch=1, device=0):
+        if model not in ("local", "full"):
+            raise ValueError("model must be 'local' or 'full'")
+        t = np.asarray(target)
+        if t.ndim == 2:
+            t = t[None]
+        if t.ndim != 3 or t.shape[1] != t.shape[2]:
+            raise ValueError("target must be (D, D) or (n_targets, D, D)")
+        D = t.shape[1]
+        if N is None:
+            N = int(round(np.log(D) / (2 * np.log(d))))
+        if d ** (2 * N) != D:
+            raise ValueError(f"target side {D} != d^(2N) = {d ** (2 * N)}")
+        self.N, self.d, self.D = N, d, D
+        self.model = model
+        self.metric = metric
+        metric_id(metric)
+        self.device = device
+        self.max_batch = max_batch
+        self._t_re = np.ascontiguousarray(t.real, dtype=np.float64)
+        self._t_im = np.ascontiguousarray(t.imag, dtype=np.float64) if np.iscomplexobj(t) and np.any(t.imag) else None
+        self.target = np.asarray(target)
+        self._handles = {}
+        self._tindex = None
+        self._tindex_ver = 0
+        self.p = d ** N if model == "full" else d * d
+        self.last_report = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _handle(self, m, K, batch) -> _Handle:
+        key = (m, K)
+        h = self._handles.get(key)
+        if h is None or h.max_batch < batch:
+            if h is not None:
+                h.close()
+            cap = max(batch, self.max_batch)
+            h = _Handle(self.N, self.d, m, K, MODEL_LOCAL if self.model == "local" else MODEL_FULL, metric_id(self.metric),
+                        cap, self._t_re, self._t_im, self.device)
+            h.tindex_ver = 0
+            self._handles[key] = h
+        return h
+
+    def set_target_index(self, index):
+        """Target id of each instance of subsequent batched calls (default all 0)."""
+        self._tindex = None if index is None else np.ascontiguousarray(index, dtype=np.int32)
+        self._tindex_ver += 1
+
+    def _prep(self, xs):
+        """-> (array-like [B, m, n, p] float64 contiguous, B, m, K, single, is_cuda)"""
+        if _is_cuda_tensor(xs):
+            import torch
+            if xs.dtype != torch.float64:
+                raise TypeError("device tensors must be float64")
+            x = xs.contiguous()
+            single = x.dim() == 3
+            if single:
+                x = x.unsqueeze(0)
+            if x.dim() != 4:
+                raise ValueError("x must be [B, m, n, p]")
+            shape = tuple(x.shape)
+            cuda = True
+        else:
+            if isinstance(xs, (list, tuple)):
+                xs = np.stack([np.asarray(a) for a in xs])
+            x = np.asarray(xs)
+            if np.iscomplexobj(x):
+                if np.abs(x.imag).max() > 0:
+                    raise NotImplementedError("complex isometries are not supported (the reference's Stiefel path is real: "
+                                              "stiefel.py:29-44 'TODO: add back the conj')")
+                x = x.real
+            single = x.ndim == 3
+            if single:
+                x = x[None]
+            if x.ndim != 4:
+                raise ValueError("x must be a list of m (n,p) isometries, or an array [m,n,p] / [B,m,n,p]")
+            x = as_f64(x)
+            shape = x.shape
+            cuda = False
+        B, m, n, p = shape
+        if p != self.p or n % p != 0:
+            raise ValueError(f"isometry shape ({n},{p}) does not fit model '{self.model}' with p = {self.p}")
+        return x, B, m, n // p, single, cuda
+
+    def _bind(self, h: _Handle, B):
+        if h.tindex_ver == self._tindex_ver:
+            return
+        if self._tindex is None:
+            idx = np.zeros(h.max_batch, dtype=np.int32)
+        else:
+            if len(self._tindex) < B:
+                raise ValueError("target_index shorter than the batch")
+            idx = self._tindex
+        check(h._lib.otn_set_target_index(h.h, ptr(idx), min(len(idx), h.max_batch)))
+        h.tindex_ver = self._tindex_ver
+
+    @staticmethod
+    def _empty_like(x, shape, cuda, dtype=np.float64):
+        if cuda:
+            import torch
+            return torch.empty(shape, dtype=torch.float64 if dtype == np.float64 else torch.int32, device=x.device)
+        return np.empty(shape, dtype=dtype)
+
+    def set_metric(self, metric):
+        self.metric = metric
+        mid = metric_id(metric)
+        for h in self._handles.values():
+            check(h._lib.otn_set_metric(h.h, mid))
+
+    # ------------------------------------------------------------------ evaluations
+    def __call__(self, xs):
+        """f(xs) for one instance -> python float (drop-in for the reference's cost closure); for a batch -> array."""
+        f = self.cost(xs)
+        return f
+
+    def model_matrix(self, xs):
+        x, B, m, K, single, cuda = self._prep(xs)
+        h = self._handle(m, K, B)
+        M = self._empty_like(x, (B, self.D, self.D), cuda)
+        check(h._lib.otn_model(h.h, ptr(x), B, ptr(M)))
+        return M[0] if single else M
+
+    def cost(self, xs):
+        x, B, m, K, single, cuda = self._prep(xs)
+        h = self._handle(m, K, B)
+        self._bind(h, B)
+        f = self._empty_like(x, (B,), cuda)
+        check(h._lib.otn_cost(h.h, ptr(x), B, ptr(f)))
+        return float(f[0]) if single else f
+
+    def cost_grad(self, xs, want_egrad=False):
+        """-> (f, rgrad[, egrad]); gradients as (n,p) tangent matrices stacked like the input."""
+        x, B, m, K, single, cuda = self._prep(xs)
+        h = self._handle(m, K, B)
+        self._bind(h, B)
+        f = self._empty_like(x, (B,), cuda)
+        g = self._empty_like(x, tuple(x.shape), cuda)
+        e = self._empty_like(x, tuple(x.shape), cuda) if want_egrad else None
+        check(h._lib.otn_cost_grad(h.h, ptr(x), B, ptr(f), ptr(g), ptr(e)))
+        self._cached = (h, B)
+        if single:
+            return (float(f[0]), g[0], e[0]) if want_egrad else (float(f[0]), g[0])
+        return (f, g, e) if want_egrad else (f, g)
+
+    def triple(self, xs, etas, out=None):
+        """Unit of work U1: (f, rgrad, H eta) sharing the primal pass."""
+        x, B, m, K, single, cuda = self._prep(xs)
+        e, B2, m2, K2, _, cuda2 = self._prep(etas)
+        if (B, m, K, cuda) != (B2, m2, K2, cuda2):
+            raise ValueError("xs and etas must have the same shape and residency")
+        h = self._handle(m, K, B)
+        self._bind(h, B)
+        if out is None:
+            f = self._empty_like(x, (B,), cuda)
+            g = self._empty_like(x, tuple(x.shape), cuda)
+            hv = self._empty_like(x, tuple(x.shape), cuda)
+        else:
+            f, g, hv = out
+        check(h._lib.otn_triple(h.h, ptr(x), ptr(e), B, ptr(f), ptr(g), ptr(hv)))
+        self._cached = (h, B)
+        if single:
+            return float(f[0]), g[0], hv[0]
+        return f, g, hv
+
+    def hvp_cached(self, etas):
+        """H eta at the x of the latest cost_grad / triple call."""
+        cached = getattr(self, "_cached", None)
+        if cached is None:
+            raise OtnError("no primal cache: call cost_grad or triple first")
+        h, B = cached
+        e, B2, m2, K2, single, cuda = self._prep(etas)
+        if B2 != B:
+            raise ValueError("batch differs from the cached primal pass")
+        hv = self._empty_like(e, tuple(e.shape), cuda)
+        check(h._lib.otn_hvp_cached(h.h, ptr(e), B, ptr(hv)))
+        return hv[0] if single else hv
+
+    def hvp(self, xs, etas):
+        return self.triple(xs, etas)[2]
+
+    # ------------------------------------------------------------------ batched trust region
+    def tr_run(self, xs, niter=20, rho_trust=0.125, radius_init=0.01, maxradius=0.1, tcg_maxiter=0, tcg_abstol=1e-8,
+               tcg_reltol=1e-6, save_x=False, radius=None):
+        """Batched device-side trust region.  Returns (x_final, report dict).  `xs` [B,m,n,p] (or one instance)."""
+        x, B, m, K, single, cuda = self._prep(xs)
+        h = self._handle(m, K, B)
+        self._bind(h, B)
+        if cuda:
+            xw = x.clone()
+        else:
+            xw = x.copy()
+        prm = _lib.TrParams(rho_trust, radius_init, maxradius, niter, tcg_maxiter, tcg_abstol, tcg_reltol)
+        f_iter = np.empty((niter, B)); rho = np.empty((niter, B)); rad = np.empty((niter, B))
+        n_cg = np.empty((niter, B), dtype=np.int32); onb = np.empty((niter, B), dtype=np.int32); acc = np.empty((niter, B), dtype=np.int32)
+        status = np.zeros(B, dtype=np.int32)
+        x_iter = np.empty((niter + 1,) + tuple(x.shape)) if save_x else None
+        rad_io = None
+        if radius is not None:
+            rad_io = np.ascontiguousarray(np.broadcast_to(np.asarray(radius, dtype=np.float64), (B,)).copy())
+        else:
+            rad_io = np.full(B, radius_init)
+        rep = _lib.TrReport(ptr(f_iter), ptr(rho), ptr(rad), ptr(n_cg), ptr(onb), ptr(acc), ptr(x_iter), ptr(rad_io), ptr(status), 0)
+        check(h._lib.otn_tr_run(h.h, ptr(xw), B, C.byref(prm), C.byref(rep)))
+        report = dict(f_iter=f_iter, rho=rho, radius_iter=rad, n_cg=n_cg, on_boundary=onb, accepted=acc, status=status,
+                      radius=rad_io, hvp_total=rep.hvp_total, x_iter=x_iter)
+        self.last_report = report
+        return (xw[0] if single else xw), report
+
+    def close(self):
+        for h in self._handles.values():
+            h.close()
+        self._handles = {}

@@ -1,0 +1,108 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Tolerances: cost and gradient 1e-10 relative (north star); in practice they agree to ~1e-13."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+N, d = 4, 2
+
+
+def rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def P():
+    from oracle import port
+    return port
+
+
+@pytest.fixture(scope="module")
+def targets(P):
+    Lp = P.create_2local_liouvillians(P.pspl_lindbladians(1.0), N, d, pbc=True)[0]
+    Lk = P.create_2local_liouvillians(P.get_kitaev_nn_linbladian(1.0), N, d, pbc=True)[0]
+    return dict(pspl_tau1=P.exp_operator_dt(Lp, 1.0), pspl_tau05=P.exp_operator_dt(Lp, 0.5),
+                kitaev_pbc_tau05=P.exp_operator_dt(Lk, 0.5), kitaev_obc_tau4=P.kitaev_fullsites_target())
+
+
+def _random_batch(P, B, m, n, p, seed):
+    rng = np.random.default_rng(seed)
+    xs = np.array([[P.random_stiefel(n, p, rng) for _ in range(m)] for _ in range(B)])
+    et = np.array([[P.project(x, rng.standard_normal((n, p))) for x in xb] for xb in xs])
+    return xs, et
+
+
+@pytest.mark.parametrize("metric", ["canonical", "euclidean"])
+@pytest.mark.parametrize("m,K", [(3, 16), (3, 4), (1, 2), (2, 5)])
+def test_full_model_triple(P, targets, metric, m, K):
+    from opentn_b200 import StiefelFit
+    T = targets["kitaev_obc_tau4"]
+    B = 3
+    xs, et = _random_batch(P, B, m, 16 * K, 16, 7 + K)
+    fit = StiefelFit(T, model="full", N=N, d=d, metric=metric, max_batch=B)
+    f, g, h = fit.triple(xs, et)
+    spec = P.CostSpec(T, "full")
+    for b in range(B):
+        fo, go, ho = P.triple(spec, list(xs[b]), list(et[b]), metric)
+        assert abs(f[b] - fo) / fo < 1e-12
+        assert rel(g[b], np.array(go)) < 1e-10
+        assert rel(h[b], np.array(ho)) < 1e-10
+    # cost-only and cost+grad entry points agree with the triple
+    np.testing.assert_allclose(fit.cost(xs), f, rtol=1e-14)
+    f2, g2, e2 = fit.cost_grad(xs, want_egrad=True)
+    np.testing.assert_allclose(f2, f, rtol=1e-14)
+    np.testing.assert_allclose(g2, g, rtol=0, atol=1e-14)
+    for b in range(B):
+        assert rel(e2[b], np.array(P.egrad(spec, list(xs[b])))) < 1e-10
+    # cached HVP (what tCG uses) == triple's HVP
+    h2 = fit.hvp_cached(et)
+    np.testing.assert_allclose(h2, h, rtol=0, atol=1e-13)
+    fit.close()
+
+
+@pytest.mark.parametrize("metric", ["canonical", "euclidean"])
+@pytest.mark.parametrize("m,K,tname", [(3, 10, "pspl_tau1"), (9, 16, "kitaev_pbc_tau05"), (5, 2, "pspl_tau05")])
+def test_local_model_triple(P, targets, metric, m, K, tname):
+    from opentn_b200 import StiefelFit
+    T = targets[tname]
+    B = 2
+    xs, et = _random_batch(P, B, m, 4 * K, 4, 11 + m)
+    fit = StiefelFit(T, model="local", N=N, d=d, metric=metric, max_batch=B)
+    f, g, h = fit.triple(xs, et)
+    spec = P.CostSpec(T, "local", N, d)
+    for b in range(B):
+        fo, go, ho = P.triple(spec, list(xs[b]), list(et[b]), metric)
+        assert abs(f[b] - fo) / fo < 1e-12
+        assert rel(g[b], np.array(go)) < 1e-10
+        assert rel(h[b], np.array(ho)) < 1e-10
+    M = fit.model_matrix(xs)
+    for b in range(B):
+        np.testing.assert_allclose(M[b], P.model_stiefel_local(list(xs[b]), N, d), rtol=0, atol=1e-13)
+    fit.close()
+
+
+def test_golden_costs_on_gpu(P, targets, goldens):
+    """Every cost anchor of the reference (notebook prints / .npy artefacts) through the CUDA path."""
+    from opentn_b200 import StiefelFit
+    fit = StiefelFit(targets["pspl_tau1"], model="local", N=N, d=d)
+    assert abs(fit(list(goldens["ref/xs0_pspl_n1_K10"])) - goldens["known/pspl_n1_tau1_K10_cost0"]) < 1e-13
+    assert abs(fit(goldens["art/xs_timestep_1_opt_4"]) - goldens["known/pspl_opt_cost_n1"]) < 1e-14
+    assert abs(fit(goldens["art/xs_timestep_4_opt_9"]) - goldens["ref/cost_xs_timestep_4_opt_9"]) < 1e-14
+    hist = [fit(x) for x in goldens["art/xs_timestep_1_opt_first8"]]
+    np.testing.assert_allclose(hist, goldens["art/f_pauli_n1_tau1_rank10"][:8], rtol=1e-11)
+    fit05 = StiefelFit(targets["pspl_tau05"], model="local", N=N, d=d)
+    for n_ in (2, 3, 4):
+        f = fit05(goldens[f"art/x_pauli_n{n_}_rank_10_tau05"])
+        assert abs(f - goldens[f"ref/cost_x_pauli_n{n_}_rank_10_tau05"]) / f < 1e-11
+    fk = StiefelFit(targets["kitaev_pbc_tau05"], model="local", N=N, d=d)
+    f0 = fk(goldens["ref/xs0_kitaev_tau05_n4_K16"])
+    assert abs(f0 - goldens["known/kitaev_n4_tau05_K16_cost0"]) / f0 < 1e-10   # cancellation-limited anchor (f ~ 5.7e-5)
+    f1 = fk(goldens["art/x_kitaev_n4_rank_16"])
+    assert abs(f1 - goldens["ref/cost_x_kitaev_n4_rank_16"]) / f1 < 1e-10
+    ff = StiefelFit(targets["kitaev_obc_tau4"], model="full", N=N, d=d)
+    xr4 = goldens["art/data_trust_region_stiefel_r4_xs"].real
+    assert abs(ff(xr4) - goldens["ref/cost_fullsites_r4_xs"]) < 1e-13
+    for x in (fit, fit05, fk, ff):
+        x.close()
