@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""Benchmark of the Stiefel trust-region hot path on B200 (contract: see the round brief / DESIGN.md section "Measurement").
+
+Workload (BASELINE.json configs[2], SURVEY 8d "C3"): Kitaev chain N=4 (D=256), full-sites ansatz, m=3 layers, Kraus rank 16,
+x [B,3,256,16], B = 1024 random-init instances per GPU, target exp(4 L) (pbc=False).  One *step* = one unit of work U1 per
+instance of the batch: (f, rgrad, H eta) = cost + Riemannian gradient + Hessian-vector product sharing the primal pass.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm
+  python bench.py --impl reference [...]                           # the reference's CPU algorithm (oracle port) on host cores
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cost+grad+HVP evals/sec (n=4 rank-16 Kitaev full-sites batch)"
+UNIT = "evals/s"
+N_SITES, D_LOC, M_LAYERS, K_RANK, BATCH = 4, 2, 3, 16, 1024
+DIM = D_LOC ** N_SITES
+NROWS, D_SUP = DIM * K_RANK, DIM * DIM
+# algorithmic FLOPs per unit U1: 9(m-1) real D^3 products + assembly and its reverse/tangent variants
+FLOPS_PER_TRIPLE = 9 * (M_LAYERS - 1) * 2 * D_SUP ** 3 + 6 * M_LAYERS * 2 * K_RANK * D_SUP ** 2
+GEMM_FLOPS_PER_TRIPLE = 9 * (M_LAYERS - 1) * 2 * D_SUP ** 3
+
+
+def workload_config(extra=None):
+    cfg = {"workload": "C3: Kitaev gamma=1 N=4 tau=4 obc, full-sites ansatz m=3 K=16, x[B,3,256,16], B=1024 random-init "
+                       "instances per GPU, unit U1 = (f, rgrad, H eta)",
+           "batch_per_gpu": BATCH, "N": N_SITES, "D": D_SUP, "m": M_LAYERS, "K": K_RANK, "metric_tensor": "canonical",
+           "cache": "inputs + work matrices per step = 10.9 GB >> 126 MB L2 (no flush needed)"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def make_inputs(first, count):
+    """Instances first..first+count-1 of C3: x = qf(G) with G ~ N(0,1), default_rng(1234+b), sign-fixed QR;
+    eta = P_x(G'), default_rng(10^6+b), scaled to canonical norm 1.  Pure NumPy host set-up (not timed)."""
+    import numpy as np
+    xs = np.empty((count, M_LAYERS, NROWS, DIM))
+    et = np.empty_like(xs)
+    for i in range(count):
+        rng = np.random.default_rng(1234 + first + i)
+        for l in range(M_LAYERS):
+            q, r = np.linalg.qr(rng.standard_normal((NROWS, DIM)))
+            xs[i, l] = q * np.sign(np.diag(r))
+        rng2 = np.random.default_rng(10 ** 6 + first + i)
+        nrm = 0.0
+        for l in range(M_LAYERS):
+            x = xs[i, l]
+            g = rng2.standard_normal((NROWS, DIM))
+            xtg = x.T @ g
+            e = g - x @ (0.5 * (xtg + xtg.T))
+            et[i, l] = e
+            xe = x.T @ e
+            nrm += np.sum(e * e) - 0.5 * np.sum(xe * xe)
+        et[i] /= np.sqrt(nrm)
+    return xs, et
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm (oracle port, NumPy) on the host cores
+# ---------------------------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    first, count = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    from oracle import port as P
+    T = P.kitaev_fullsites_target(N_SITES, D_LOC, 1.0, 4.0, False)
+    spec = P.CostSpec(T, "full")
+    xs, et = make_inputs(first, count)
+    P.triple(spec, list(xs[0]), list(et[0]), "canonical")  # warm the BLAS / page in
+    t0 = time.perf_counter()
+    acc = 0.0
+    for i in range(count):
+        f, g, h = P.triple(spec, list(xs[i]), list(et[i]), "canonical")
+        acc += f
+    return time.perf_counter() - t0, acc
+
+
+def cpu_triples_per_sec(sample_per_core=16, cores=None):
+    """Throughput of the oracle port: one instance per process, min(B, cores) processes, 1 BLAS thread each
+    (BASELINE.md section 3 protocol)."""
+    import multiprocessing as mp
+    cores = cores or os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(0, 1)] * cores)  # spawn + import warm-up
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, [(c * sample_per_core, sample_per_core) for c in range(cores)])
+        wall = time.perf_counter() - t0
+    inner = max(r[0] for r in res)
+    total = cores * sample_per_core
+    return total / inner, cores, total, wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    per_core = 32
+    values = []
+    for _ in range(min(args.warmup, 1)):
+        cpu_triples_per_sec(2, cores)
+    t_ms = []
+    for _ in range(args.steps):
+        v, c, total, wall = cpu_triples_per_sec(per_core, cores)
+        values.append(v)
+        t_ms.append(1e3 * total / v)
+    v = statistics.median(values)
+    sample = f"{cores * per_core} instances of C3 per step ({per_core} per process x {cores} processes, 1 BLAS thread each)"
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": statistics.median(t_ms), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config({"sample": sample}),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference = opentn's algorithm restated in NumPy (oracle/port.py; JAX is not installable here), "
+                    "matrix-free HVP (BASELINE.md baseline (ii))"}
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, smax, reasons, power = [], [], set(), []
+        for ln in out.strip().splitlines():
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); smax.append(float(parts[2])); power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, p in zip(sm, power) if p > 0.5 * max(power)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "power_w_max": max(power), "samples": len(sm)}
+
+
+def measure_fp64_peak(torch):
+    """cuBLAS DGEMM 8192^3 through torch.matmul -- the measuring stick for the FP64 tensor roofline (MEASURED_PEAKS.json
+    carries bf16 only).  Library call used as a ruler, never on the product path."""
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    torch.matmul(a, b)
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b); e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    torch.cuda.empty_cache()
+    return 2 * n ** 3 / best / 1e9  # TFLOP/s
+
+
+def run_gpu(args):
+    import ctypes as C
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from opentn_b200 import StiefelFit, _lib
+    from opentn_b200 import transformations as T
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = _lib.load()
+
+    # ---- set-up (not timed): target, inputs -----------------------------------------------------------------------
+    Lvec = T.create_kitaev_liouvillians(N_SITES, D_LOC, 1.0, pbc=False)[0]
+    target = T.exp_operator_dt(Lvec, 4.0)
+    xs_h, et_h = make_inputs(rank * BATCH, BATCH)          # weak scaling: every rank owns its own B instances
+    x_pin = torch.from_numpy(xs_h).pin_memory()
+    e_pin = torch.from_numpy(et_h).pin_memory()
+    x_dev = x_pin.cuda(non_blocking=True)
+    e_dev = e_pin.cuda(non_blocking=True)
+    f_dev = torch.empty(BATCH, dtype=torch.float64, device="cuda")
+    g_dev = torch.empty_like(x_dev)
+    h_dev = torch.empty_like(x_dev)
+    f_pin = torch.empty(BATCH, dtype=torch.float64).pin_memory()
+    g_pin = torch.empty_like(x_pin).pin_memory()
+    h_pin = torch.empty_like(x_pin).pin_memory()
+    torch.cuda.synchronize()
+
+    fit = StiefelFit(target, model="full", N=N_SITES, d=D_LOC, metric="canonical", max_batch=BATCH, device=local_rank)
+    handle = fit._handle(M_LAYERS, K_RANK, BATCH)
+    stream = torch.cuda.current_stream()
+    _lib.check(lib.otn_set_stream(handle.h, C.c_void_p(stream.cuda_stream)))   # so that torch.cuda.Event brackets our kernels
+
+    def step_device():
+        _lib.check(lib.otn_triple(handle.h, x_dev.data_ptr(), e_dev.data_ptr(), BATCH, f_dev.data_ptr(), g_dev.data_ptr(), h_dev.data_ptr()))
+
+    def step_e2e():
+        _lib.check(lib.otn_triple(handle.h, x_pin.data_ptr(), e_pin.data_ptr(), BATCH, f_pin.data_ptr(), g_pin.data_ptr(), h_pin.data_ptr()))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    peak_tf = measure_fp64_peak(torch) if rank == 0 else None
+
+    # ---- device-resident timing (`value`) ----------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    lib.otn_profile_enable(handle.h, 1)
+    launches0 = lib.otn_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = lib.otn_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    pms = (C.c_double * 6)(); pln = (C.c_longlong * 6)(); pfl = (C.c_double * 6)()
+    _lib.check(lib.otn_profile_read(handle.h, pms, pln, pfl))
+    lib.otn_profile_enable(handle.h, 0)
+    ms_per_step = ms_total / args.steps
+    value = world * BATCH * args.steps / (ms_total * 1e-3)
+
+    # ---- end-to-end timing: pinned host buffers through the C ABI, H2D + D2H inside the timed region -----------------
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record(stream)
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = world * BATCH * args.steps / (ms_e2e * 1e-3)
+    h2d = 2 * x_pin.numel() * 8
+    d2h = 2 * x_pin.numel() * 8 + BATCH * 8
+
+    # ---- parity spot check on the timed data (device vs host path) and final gather (the only collective) -------------
+    assert torch.allclose(f_dev.cpu(), f_pin, rtol=1e-13, atol=0), "device-resident and host-staged paths disagree"
+    gather_ms = None
+    if world > 1:
+        allf = [torch.empty_like(f_dev) for _ in range(world)]
+        barrier()
+        e0.record(stream)
+        dist.all_gather(allf, f_dev)
+        e1.record(stream)
+        barrier()
+        gather_ms = max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- TR iterations / s (unit U2) on the same batch ------------------------------------------------------------------
+    tr = None
+    if not args.no_tr:
+        niter = 3
+        fit.tr_run(x_dev, niter=1)  # warm-up
+        barrier()
+        e0.record(stream)
+        _, rep = fit.tr_run(x_dev, niter=niter)
+        e1.record(stream)
+        barrier()
+        ms_tr = max_over_ranks(e0.elapsed_time(e1))
+        tr = {"iters_per_sec": world * BATCH * niter / (ms_tr * 1e-3), "unit": "TR iterations/s (all instances)", "niter": niter,
+              "n_cg_mean": float(rep["n_cg"].mean()), "hvp_total_rank0": int(rep["hvp_total"]), "ms_per_iter_batch": ms_tr / niter,
+              "accept_rate": float(rep["accepted"].mean())}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (chain GEMM on the FP64 tensor pipe) -------------------------------------------
+    gemm_ms, gemm_n, gemm_fl = pms[0], pln[0], pfl[0]
+    achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+    peak_file = None
+    try:
+        peak_file = json.load(open(os.path.join(ROOT, "profiles", "fp64_peaks_r01.json")))["dgemm_8192"] / 1e3
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "kernel": "gemm_dmma_kernel (FP64 DMMA.8x8x4)", "achieved": achieved, "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved and peak_tf else None, "traffic": None,
+                "peak_source": "cuBLAS DGEMM 8192^3 via torch.matmul, best of 3, measured in this run (MEASURED_PEAKS.json has no "
+                               "FP64 figure; DMMA issue-rate ceiling 148 SM x 128 flop/clk x 1.965 GHz = 37.2 TFLOP/s)",
+                "peak_committed_r01": peak_file,
+                "launches_timed": int(gemm_n), "avg_launch_ms": gemm_ms / gemm_n if gemm_n else None,
+                "algorithmic_flops_per_launch": gemm_fl / gemm_n if gemm_n else None,
+                "kernel_share_of_step": gemm_ms / ms_total,
+                "other_kernels_ms_per_step": {"assembly": pms[1] / args.steps, "back_assembly": pms[2] / args.steps,
+                                              "riemannian_epilogue": pms[3] / args.steps, "other": pms[5] / args.steps},
+                "step_tflops_algorithmic": FLOPS_PER_TRIPLE * BATCH / (ms_per_step * 1e-3) / 1e12}
+
+    cpu = None
+    if not args.no_cpu:
+        v, cores, total, wall = cpu_triples_per_sec(32)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{total} instances of the same workload ({total // cores} per process x {cores} processes, 1 BLAS thread each, "
+                         f"{wall:.1f} s wall)"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "tr": tr, "final_gather_ms": gather_ms}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-tr", action="store_true", help="skip the TR iterations/s leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

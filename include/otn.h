@@ -54,6 +54,18 @@ int otn_set_metric(otn_problem* p, int metric);
 int otn_query(const otn_problem* p, int* n, int* pp, int* D, int* m, long long* workspace_bytes);
 /* the handle's cudaStream_t (as void*) so a host framework can order its own work after ours */
 void* otn_stream(const otn_problem* p);
+/* run on the caller's stream instead (e.g. torch.cuda.current_stream().cuda_stream); the handle no longer owns it */
+int otn_set_stream(otn_problem* p, void* stream);
+
+/* ---- measurement hooks (bench.py) ------------------------------------------------------------------------------------
+ * otn_launch_count   : kernels launched by this library in this process so far
+ * otn_profile_enable : when on, every kernel launch of the handle is bracketed by a CUDA-event pair on its stream
+ * otn_profile_read   : sums (and clears) the recorded timings per category
+ *                      [0]=chain GEMM  [1]=Kraus assembly/embedding  [2]=back-assembly  [3]=Riemannian epilogue  [4]=TR/tCG  [5]=other
+ *                      ms[6], launches[6], flops[6] (algorithmic flops of the recorded launches) */
+long long otn_launch_count(void);
+int otn_profile_enable(otn_problem* p, int on);
+int otn_profile_read(otn_problem* p, double* ms, long long* launches, double* flops);
 
 /* ---- model / cost layer ---------------------------------------------------------------------------------------------
  * otn_model     : M[batch][D][D] = Y_m ... Y_1        model_stiefel_local / model_Ys_stiefel (optimization.py:106,147)

@@ -42,6 +42,10 @@ SIGNATURES = {
     "otn_query": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                             C.POINTER(C.c_longlong)]),
     "otn_stream": (C.c_void_p, [C.c_void_p]),
+    "otn_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "otn_launch_count": (C.c_longlong, []),
+    "otn_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "otn_profile_read": (C.c_int, [C.c_void_p, _dp, C.c_void_p, _dp]),
     "otn_model": (C.c_int, [C.c_void_p, _dp, C.c_int, _dp]),
     "otn_cost": (C.c_int, [C.c_void_p, _dp, C.c_int, _dp]),
     "otn_cost_grad": (C.c_int, [C.c_void_p, _dp, C.c_int, _dp, _dp, _dp]),

@@ -264,3 +264,272 @@ __global__ void __launch_bounds__(BAS_THREADS) back_assemble_kernel(const double
 }
 
 }  // namespace otn
+
+// ==================================================================================================================
+// Tensor-core (DMMA.8x8x4) versions for dim % 8 == 0 (full-sites model: dim = d^N = 16).  The SIMT kernels above need one
+// shared-memory load per FMA and ran ~9x slower than the HBM floor; here a row (a,b) of Y is vec(X_a^T X_b), a dim x dim x K
+// product fed from fragments (1 LDS per 256 FMA), so the kernels become store / L2-read bound.
+// smem rows are padded to dim+4 doubles (bank-conflict-free fragment loads), Kraus index padded with zero rows.
+// ==================================================================================================================
+namespace otn {
+
+template <int DIM, bool TANGENT, bool PRIMAL>
+__global__ void __launch_bounds__(256) assemble_mma_kernel(const double* __restrict__ x, const double* __restrict__ eta,
+                                                           double* __restrict__ Y, double* __restrict__ Yd, long long out_stride,
+                                                           int K, const int* active, int m) {
+    extern __shared__ __align__(16) double sm[];
+    constexpr int LD = DIM + 4, MI = DIM / 8;
+    const int item = blockIdx.y, a = blockIdx.x;
+    if (active != nullptr && active[item / m] == 0) return;
+    const int Kp = (K + 3) & ~3;
+    const int rows = DIM * Kp;
+    double* xs = sm;
+    double* es = sm + rows * LD;
+    const long long np = (long long)DIM * K * DIM;
+    const double* xg = x + (long long)item * np;
+    const double* eg = TANGENT ? eta + (long long)item * np : nullptr;
+    for (int i = threadIdx.x; i < rows * DIM; i += 256) {
+        const int r = i / DIM, c = i - r * DIM, aa = r / Kp, k = r - aa * Kp;
+        const bool ok = k < K;
+        xs[r * LD + c] = ok ? xg[(aa * K + k) * DIM + c] : 0.0;
+        if (TANGENT) es[r * LD + c] = ok ? eg[(aa * K + k) * DIM + c] : 0.0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    for (int b = warp; b < DIM; b += 8) {
+        double acc[MI][MI][2], accd[MI][MI][2];
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < MI; ++j) { acc[i][j][0] = acc[i][j][1] = 0.0; accd[i][j][0] = accd[i][j][1] = 0.0; }
+        for (int kk = 0; kk < Kp; kk += 4) {
+            double xa[MI], xb[MI], ea[MI], eb[MI];
+#pragma unroll
+            for (int i = 0; i < MI; ++i) {
+                xa[i] = xs[(a * Kp + kk + t) * LD + i * 8 + g];
+                xb[i] = xs[(b * Kp + kk + t) * LD + i * 8 + g];
+                if (TANGENT) { ea[i] = es[(a * Kp + kk + t) * LD + i * 8 + g]; eb[i] = es[(b * Kp + kk + t) * LD + i * 8 + g]; }
+            }
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < MI; ++j) {
+                    if (PRIMAL) dmma884(acc[i][j][0], acc[i][j][1], xa[i], xb[j]);
+                    if (TANGENT) { dmma884(accd[i][j][0], accd[i][j][1], ea[i], xb[j]); dmma884(accd[i][j][0], accd[i][j][1], xa[i], eb[j]); }
+                }
+        }
+        const long long row = (long long)item * out_stride + (long long)(a * DIM + b) * (DIM * DIM);
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < MI; ++j) {
+                const int off = (i * 8 + g) * DIM + j * 8 + 2 * t;
+                if (PRIMAL) *reinterpret_cast<double2*>(Y + row + off) = make_double2(acc[i][j][0], acc[i][j][1]);
+                if (TANGENT) *reinterpret_cast<double2*>(Yd + row + off) = make_double2(accd[i][j][0], accd[i][j][1]);
+            }
+    }
+}
+
+// Z[(a,k),c] = 2 sum_{b,d} W[(a,b),(c,d)] x[(b,k),d]   (+ tangent: Wd * x + W * eta); W is swap-symmetric (see below).
+// 8 warps split the b range; per-warp partial tiles are summed in warp order (deterministic).
+template <int DIM, bool TANGENT>
+__global__ void __launch_bounds__(256) back_assemble_mma_kernel(const double* __restrict__ W, const double* __restrict__ Wd,
+                                                                long long w_stride, long long wd_stride, int nslices,
+                                                                const double* __restrict__ x, const double* __restrict__ eta,
+                                                                double* __restrict__ Z, double* __restrict__ Zd, int K,
+                                                                const int* active, int m, int layer) {
+    extern __shared__ __align__(16) double sm[];
+    constexpr int LD = DIM + 4, MI = DIM / 8, D2 = DIM * DIM, WSZ = DIM * DIM * LD;
+    const int inst = blockIdx.y, a = blockIdx.x;
+    if (active != nullptr && active[inst] == 0) return;
+    const int item = inst * m + layer;
+    const int Kp = (K + 7) & ~7, NI = Kp / 8;
+    const int xrows = DIM * Kp;
+    double* wds = sm;                          // cotangent to contract with x   (W in primal mode, Wd in tangent mode)
+    double* ws = wds + WSZ;                    // tangent mode only: W, contracted with eta
+    double* xs = ws + (TANGENT ? WSZ : 0);
+    double* es = xs + xrows * LD;
+    double* part = es + (TANGENT ? xrows * LD : 0);   // [8][DIM][Kp]
+    const long long np = (long long)DIM * K * DIM;
+    for (int i = threadIdx.x; i < xrows * DIM; i += 256) {
+        const int r = i / DIM, c = i - r * DIM, bb = r / Kp, k = r - bb * Kp;
+        const bool ok = k < K;
+        xs[r * LD + c] = ok ? x[(long long)item * np + (bb * K + k) * DIM + c] : 0.0;
+        if (TANGENT) es[r * LD + c] = ok ? eta[(long long)item * np + (bb * K + k) * DIM + c] : 0.0;
+    }
+    const double* Wb = W + (long long)inst * w_stride;
+    const double* Wdb = TANGENT ? Wd + (long long)inst * wd_stride : nullptr;
+    (void)nslices;
+    // nslices == 1 on this path (the per-factor slices only exist for the local model, which has dim = 4).
+    // Loads are issued in fully unrolled batches so that each thread keeps NU (x2) requests in flight (the first version
+    // looped load->store and was latency bound at ~1 CTA/SM).
+    constexpr int NU = DIM * D2 / 256;
+    {   // pass 1: rows (a,b), columns (c,d): coalesced along (c,d)
+        double v[NU], vd[NU];
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+            const int idx = threadIdx.x + u * 256;
+            const long long gi = (long long)a * DIM * D2 + idx;   // (a*DIM + b)*D2 + cd with idx = b*D2 + cd
+            v[u] = Wb[gi];
+            if (TANGENT) vd[u] = Wdb[gi];
+        }
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+            const int idx = threadIdx.x + u * 256;
+            const int b = idx / D2, cd = idx - b * D2, c = cd / DIM, dd = cd - c * DIM;
+            if (TANGENT) { ws[(b * DIM + c) * LD + dd] = v[u]; wds[(b * DIM + c) * LD + dd] = vd[u]; }
+            else wds[(b * DIM + c) * LD + dd] = v[u];
+        }
+    }
+    __syncthreads();
+    // No second (transposed) pass: the reverse chain runs on the swap-symmetric residual (see otn_create), so
+    // W[(b,a),(d,c)] == W[(a,b),(c,d)] and W + swap(W) = 2 W; the factor 2 is applied at the output.
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    double acc[MI][4][2];                       // NI <= 4  (K <= 32)
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int b = warp; b < DIM; b += 8) {
+#pragma unroll
+        for (int d0 = 0; d0 < DIM; d0 += 4) {
+            double wa[MI], w0[MI];
+#pragma unroll
+            for (int i = 0; i < MI; ++i) {
+                wa[i] = wds[(b * DIM + i * 8 + g) * LD + d0 + t];
+                if (TANGENT) w0[i] = ws[(b * DIM + i * 8 + g) * LD + d0 + t];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j < NI) {
+                    const double xb = xs[(b * Kp + j * 8 + g) * LD + d0 + t];
+                    const double eb = TANGENT ? es[(b * Kp + j * 8 + g) * LD + d0 + t] : 0.0;
+#pragma unroll
+                    for (int i = 0; i < MI; ++i) {
+                        dmma884(acc[i][j][0], acc[i][j][1], wa[i], xb);
+                        if (TANGENT) dmma884(acc[i][j][0], acc[i][j][1], w0[i], eb);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j < NI) {
+                const int c = i * 8 + g, k = j * 8 + 2 * t;
+                part[(warp * DIM + c) * Kp + k] = acc[i][j][0];
+                part[(warp * DIM + c) * Kp + k + 1] = acc[i][j][1];
+            }
+    __syncthreads();
+    for (int o = threadIdx.x; o < K * DIM; o += 256) {
+        const int k = o / DIM, c = o - k * DIM;
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += part[(w * DIM + c) * Kp + k];
+        const long long og = (long long)item * np + (a * K + k) * DIM + c;
+        if (TANGENT) Zd[og] = 2.0 * s; else Z[og] = 2.0 * s;
+    }
+}
+
+}  // namespace otn
+
+// ==================================================================================================================
+// Streaming back-assembly (third version; replaces back_assemble_mma_kernel on the hot path).
+//   out[(a,k),c]  (+)=  2 * sum_{b,d} W[(a,b),(c,d)] * u[(b,k),d]          u = x or eta, W swap-symmetric
+// One CTA per (instance, layer) streams the whole D x D cotangent once through a 3-stage cp.async ring (one stage = the
+// DIM rows {(a,b)}_a of a fixed b, 32 KB at DIM = 16), so ~64 KB per SM are in flight while the previous stage is consumed
+// by DMMA.  Viewed as a GEMM: M = DIM^2 rows (a,c), N = K, contraction (b,d) = DIM^2; each warp owns DIM^2/8 output rows,
+// so there is no cross-warp reduction and the summation order is fixed.
+// The tangent needs two cotangents with two right-hand sides (Wd*x + W*eta): two launches, the second accumulating.
+// ==================================================================================================================
+namespace otn {
+
+template <int DIM>
+struct BasCfg {
+    static constexpr int LD = DIM + 4, STAGES = 3, D2 = DIM * DIM;
+    static constexpr int STAGE_ELEMS = DIM * DIM * LD;           // [a][c][LD]
+    static size_t smem_bytes(int K) { return (size_t)(STAGES * STAGE_ELEMS + DIM * ((K + 7) & ~7) * LD) * 8; }
+};
+
+template <int DIM>
+__global__ void __launch_bounds__(256) back_assemble_stream_kernel(const double* __restrict__ W, long long w_stride,
+                                                                   const double* __restrict__ u, double* __restrict__ out,
+                                                                   int K, int accumulate, const int* active, int m, int layer) {
+    using Cfg = BasCfg<DIM>;
+    constexpr int LD = Cfg::LD, D2 = Cfg::D2, ST = Cfg::STAGES;
+    constexpr int MI = D2 / 64;                 // 8-row blocks per warp (8 warps share D2 rows)
+    extern __shared__ __align__(16) double sm[];
+    const int inst = blockIdx.x;
+    if (active != nullptr && active[inst] == 0) return;
+    const int item = inst * m + layer;
+    const int Kp = (K + 7) & ~7, NI = Kp / 8;
+    double* stage = sm;
+    double* us = sm + ST * Cfg::STAGE_ELEMS;    // [b][k (padded)][LD]
+    const long long np = (long long)DIM * K * DIM;
+    const double* Wb = W + (long long)inst * w_stride;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+
+    auto load_stage = [&](int b, int s) {
+        // rows (a, b) for a = 0..DIM-1: global row a*DIM + b, D2 doubles each -> smem [a][c][d]
+        double* dst = stage + s * Cfg::STAGE_ELEMS;
+        constexpr int CH = D2 / 2;              // 16-byte chunks per row
+        for (int id = tid; id < DIM * CH; id += 256) {
+            const int a = id / CH, ch = id - a * CH, c = (2 * ch) / DIM, dd = 2 * ch - c * DIM;
+            cp_async16(dst + (a * DIM + c) * LD + dd, Wb + (long long)(a * DIM + b) * D2 + 2 * ch);
+        }
+    };
+#pragma unroll
+    for (int s = 0; s < ST - 1; ++s) { load_stage(s, s); cp_async_commit(); }
+    for (int i = tid; i < DIM * Kp * DIM; i += 256) {
+        const int r = i / DIM, c = i - r * DIM, bb = r / Kp, k = r - bb * Kp;
+        us[r * LD + c] = (k < K) ? u[(long long)item * np + (bb * K + k) * DIM + c] : 0.0;
+    }
+    double acc[MI][4][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int b = 0; b < DIM; ++b) {
+        cp_async_wait<ST - 2>();
+        __syncthreads();
+        if (b + ST - 1 < DIM) load_stage(b + ST - 1, (b + ST - 1) % ST);
+        cp_async_commit();
+        const double* As = stage + (b % ST) * Cfg::STAGE_ELEMS;
+#pragma unroll
+        for (int d0 = 0; d0 < DIM; d0 += 4) {
+            double wa[MI];
+#pragma unroll
+            for (int i = 0; i < MI; ++i) wa[i] = As[(warp * (MI * 8) + i * 8 + g) * LD + d0 + t];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j < NI) {
+                    const double ub = us[(b * Kp + j * 8 + g) * LD + d0 + t];
+#pragma unroll
+                    for (int i = 0; i < MI; ++i) dmma884(acc[i][j][0], acc[i][j][1], wa[i], ub);
+                }
+        }
+    }
+    cp_async_wait<0>();
+    // row index R = (a, c) = warp*(MI*8) + i*8 + g ; columns k = j*8 + 2t, +1
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+        const int R = warp * (MI * 8) + i * 8 + g, a = R / DIM, c = R - a * DIM;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j < NI) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int k = j * 8 + 2 * t + e;
+                    if (k < K) {
+                        const long long og = (long long)item * np + (a * K + k) * DIM + c;
+                        const double v = 2.0 * acc[i][j][e];
+                        out[og] = accumulate ? out[og] + v : v;
+                    }
+                }
+            }
+    }
+}
+
+}  // namespace otn

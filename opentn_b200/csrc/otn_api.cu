@@ -98,6 +98,31 @@ static int set_smem(K kern, size_t bytes) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// launch accounting + optional per-kernel CUDA-event timing (bench.py's live roofline measurement)
+// ---------------------------------------------------------------------------------------------------------------------
+enum { CAT_GEMM = 0, CAT_ASSEMBLE = 1, CAT_BACK = 2, CAT_RIEM = 3, CAT_TR = 4, CAT_OTHER = 5, CAT_COUNT = 6 };
+static long long g_launches = 0;
+struct ProfRec { int cat; cudaEvent_t e0, e1; double flops; };
+struct Profiler {
+    bool on = false;
+    std::vector<ProfRec> recs;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+};
+struct ProfScope {
+    Profiler* pr; cudaStream_t st; ProfRec rec; bool live;
+    ProfScope(Profiler* p, cudaStream_t s, int cat, double flops, int nkernels = 1) : pr(p), st(s), live(p && p->on) {
+        g_launches += nkernels;
+        if (live) { rec.cat = cat; rec.flops = flops; rec.e0 = pr->get(); rec.e1 = pr->get(); cudaEventRecord(rec.e0, st); }
+    }
+    ~ProfScope() { if (live) { cudaEventRecord(rec.e1, st); pr->recs.push_back(rec); } }
+};
+extern "C" long long otn_launch_count(void) { return g_launches; }
+
+// ---------------------------------------------------------------------------------------------------------------------
 // embedding index tables (transformations.py:431-444, 473-482)
 // ---------------------------------------------------------------------------------------------------------------------
 static int ipow(int b, int e) { int r = 1; while (e-- > 0) r *= b; return r; }
@@ -178,6 +203,8 @@ struct otn_problem {
     // staging for host callers
     DevBuf in_x, in_eta, out_a, out_b, out_c, out_f, out_M;
     TrState tr;                  // trust-region state (tr.cuh)
+    Profiler prof;
+    bool own_stream = true;
     DevBuf tr_buf;
     EmbedTables tables() const { return EmbedTables{tab, inv, D, q, nf}; }
 };
@@ -199,7 +226,9 @@ extern "C" void otn_destroy(otn_problem* h) {
                       (void*)h->part_s})
         if (ptr) cudaFree(ptr);
     for (DevBuf* b : {&h->in_x, &h->in_eta, &h->out_a, &h->out_b, &h->out_c, &h->out_f, &h->out_M, &h->tr_buf}) b->release();
-    if (h->stream) cudaStreamDestroy(h->stream);
+    for (auto& r : h->prof.recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    for (auto e : h->prof.pool) cudaEventDestroy(e);
+    if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
 }
 
@@ -239,19 +268,33 @@ extern "C" int otn_create(otn_problem** out, int N, int d, int m, int K, int mod
     if (otn_set_metric(h, metric) != 0) return bail(-1);
     CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     const size_t B = (size_t)max_batch, SZ = (size_t)h->SZ, M = (size_t)m;
-    // targets
+    // targets.  Every layer superoperator Y = sum_k E_k (x) E_k (and hence every chain product and tangent) is invariant under
+    // the swap S: (a,b) <-> (b,a) applied to rows and columns, so only the swap-symmetric part Ts = (T + S T S)/2 of Re T
+    // carries gradient; the antisymmetric rest and Im T add the constant ||Re T - Ts||^2 + ||Im T||^2 under the square root.
+    // Running the reverse chain on R' = M - Ts makes every cotangent W swap-symmetric, which halves the back-assembly traffic.
     CREATE_TRY(cudaMalloc(&h->T_re, n_targets * SZ * 8));
-    CREATE_TRY(cudaMemcpy(h->T_re, target_re, n_targets * SZ * 8, cudaMemcpyDefault));
     {
-        std::vector<double> im2(n_targets, 0.0);
-        if (target_im != nullptr) {
-            std::vector<double> tmp(SZ);
-            for (int t = 0; t < n_targets; ++t) {
-                CREATE_TRY(cudaMemcpy(tmp.data(), target_im + (size_t)t * SZ, SZ * 8, cudaMemcpyDefault));
-                double s = 0.0;
-                for (size_t i = 0; i < SZ; ++i) s += tmp[i] * tmp[i];
-                im2[t] = s;
+        std::vector<double> im2(n_targets, 0.0), tre(SZ), tsym(SZ), tmp(SZ);
+        const int dm = ipow(d, N), Dn = h->D;
+        for (int t = 0; t < n_targets; ++t) {
+            CREATE_TRY(cudaMemcpy(tre.data(), target_re + (size_t)t * SZ, SZ * 8, cudaMemcpyDefault));
+            double s = 0.0;
+            for (int r = 0; r < Dn; ++r) {
+                const int rs = (r % dm) * dm + r / dm;
+                for (int c = 0; c < Dn; ++c) {
+                    const int cs = (c % dm) * dm + c / dm;
+                    const double v = 0.5 * (tre[(size_t)r * Dn + c] + tre[(size_t)rs * Dn + cs]);
+                    const double a = tre[(size_t)r * Dn + c] - v;
+                    tsym[(size_t)r * Dn + c] = v;
+                    s += a * a;
+                }
             }
+            CREATE_TRY(cudaMemcpy(h->T_re + (size_t)t * SZ, tsym.data(), SZ * 8, cudaMemcpyHostToDevice));
+            if (target_im != nullptr) {
+                CREATE_TRY(cudaMemcpy(tmp.data(), target_im + (size_t)t * SZ, SZ * 8, cudaMemcpyDefault));
+                for (size_t i = 0; i < SZ; ++i) s += tmp[i] * tmp[i];
+            }
+            im2[t] = s;
         }
         CREATE_TRY(cudaMalloc(&h->im2, n_targets * 8));
         CREATE_TRY(cudaMemcpy(h->im2, im2.data(), n_targets * 8, cudaMemcpyHostToDevice));
@@ -317,9 +360,47 @@ extern "C" int otn_query(const otn_problem* h, int* n, int* pp, int* D, int* m, 
 
 extern "C" void* otn_stream(const otn_problem* h) { return h ? (void*)h->stream : nullptr; }
 
+extern "C" int otn_set_stream(otn_problem* h, void* stream) {
+    if (!h) return fail("null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (h->own_stream && h->stream) CUDA_TRY(cudaStreamDestroy(h->stream));
+    h->stream = (cudaStream_t)stream;
+    h->own_stream = false;
+    return 0;
+}
+
+extern "C" int otn_profile_enable(otn_problem* h, int on) {
+    if (!h) return fail("null handle");
+    h->prof.on = on != 0;
+    return 0;
+}
+
+// sums (and clears) the per-category event timings recorded since the last read: ms[6], launches[6], flops[6]
+extern "C" int otn_profile_read(otn_problem* h, double* ms, long long* launches, double* flops) {
+    if (!h) return fail("null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for (int c = 0; c < CAT_COUNT; ++c) { if (ms) ms[c] = 0; if (launches) launches[c] = 0; if (flops) flops[c] = 0; }
+    for (auto& r : h->prof.recs) {
+        float t = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&t, r.e0, r.e1));
+        if (ms) ms[r.cat] += t;
+        if (launches) launches[r.cat] += 1;
+        if (flops) flops[r.cat] += r.flops;
+        h->prof.pool.push_back(r.e0); h->prof.pool.push_back(r.e1);
+    }
+    h->prof.recs.clear();
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // pipeline pieces (all enqueue on h->stream; x / eta are device pointers [batch][m][np])
 // ---------------------------------------------------------------------------------------------------------------------
+static cudaError_t hgemm(otn_problem* h, const GemmParams& p, bool ta, bool tb) {
+    ProfScope ps(&h->prof, h->stream, CAT_GEMM, 2.0 * p.D * (double)p.rows * p.D * p.batch * (p.A2 ? 2 : 1));
+    return gemm_launch(p, ta, tb, h->stream);
+}
 static GemmParams gp(const otn_problem* h, int batch, const int* active) {
     GemmParams p{};
     p.D = h->D; p.row0 = 0; p.rows = h->D; p.batch = batch; p.active = active; p.epi = EPI_NONE;
@@ -331,12 +412,25 @@ static inline double* layer_ptr(double* base, int l, long long SZ) { return base
 static int build_layers(otn_problem* h, const double* x, const double* eta, int batch, const int* active, bool primal) {
     const int items = batch * h->m;
     const bool tangent = eta != nullptr;
+    ProfScope ps(&h->prof, h->stream, CAT_ASSEMBLE, 2.0 * h->K * (double)h->dim * h->dim * h->dim * h->dim * items * ((primal ? 1 : 0) + (tangent ? 2 : 0)),
+                 h->model == OTN_MODEL_LOCAL ? 2 : 1);
     const size_t smem = (size_t)h->np * 8 * (tangent ? 2 : 1);
     double* Yout = (h->model == OTN_MODEL_FULL) ? h->Y : h->Yl;
     double* Ydout = (h->model == OTN_MODEL_FULL) ? h->Yd : h->Yld;
     const long long ostride = (h->model == OTN_MODEL_FULL) ? h->SZ : (long long)h->q * h->q;
     dim3 grid(h->dim, items);
-    if (tangent && primal) {
+    if (h->dim == 16 || h->dim == 8) {
+        const int Kp = (h->K + 3) & ~3;
+        const size_t sm = (size_t)h->dim * Kp * (h->dim + 4) * 8 * (tangent ? 2 : 1);
+#define ASM_MMA(DIMV, TG, PR)                                                                                              \
+    do {                                                                                                                   \
+        OTN_TRY(set_smem(assemble_mma_kernel<DIMV, TG, PR>, sm));                                                          \
+        assemble_mma_kernel<DIMV, TG, PR><<<grid, 256, sm, h->stream>>>(x, eta, Yout, Ydout, ostride, h->K, active, h->m); \
+    } while (0)
+        if (h->dim == 16) { if (tangent && primal) ASM_MMA(16, true, true); else if (tangent) ASM_MMA(16, true, false); else ASM_MMA(16, false, true); }
+        else { if (tangent && primal) ASM_MMA(8, true, true); else if (tangent) ASM_MMA(8, true, false); else ASM_MMA(8, false, true); }
+#undef ASM_MMA
+    } else if (tangent && primal) {
         OTN_TRY(set_smem(assemble_kernel<true, true>, smem));
         assemble_kernel<true, true><<<grid, ASM_THREADS, smem, h->stream>>>(x, eta, Yout, Ydout, ostride, h->dim, h->K, active, h->m);
     } else if (tangent) {
@@ -393,6 +487,7 @@ static int forward_chain(otn_problem* h, int batch, const int* active, double* M
     *tiles_used = gemm_plan(h->D, h->D, batch).tiles;
     if (m == 1) {
         if (Mout) { CUDA_TRY(cudaMemcpyAsync(Mout, h->Y, (size_t)batch * SZ * 8, cudaMemcpyDeviceToDevice, h->stream)); return 0; }
+        ProfScope ps(&h->prof, h->stream, CAT_OTHER, 0.0);
         resid_kernel<<<batch, 256, 0, h->stream>>>(h->Y, S, h->T_re, SZ, h->tindex, h->G, S, nullptr, 0, h->part_f, SZ, active);
         *tiles_used = 1;
         CUDA_TRY(cudaGetLastError());
@@ -408,7 +503,7 @@ static int forward_chain(otn_problem* h, int batch, const int* active, double* M
             p.C = layer_ptr(h->G, m - 1, SZ); p.sC = S;
             p.epi = EPI_RESID; p.E = h->T_re; p.sE = SZ; p.e_index = h->tindex; p.partial = h->part_f;
         }
-        CUDA_TRY(gemm_launch(p, false, false, h->stream));
+        CUDA_TRY(hgemm(h, p, false, false));
     }
     return 0;
 }
@@ -416,6 +511,8 @@ static int forward_chain(otn_problem* h, int batch, const int* active, double* M
 // reverse chain on the unscaled residual: G_{l-1} = Y_l^T G_l ; W_l = G_l P_{l-1}^T ; zraw_l = back_assemble(W_l)
 static int back_layer(otn_problem* h, int batch, const int* active, int l, const double* x, bool tangent, const double* eta) {
     // pulls the cotangent of layer l (W_l, and for the tangent pass Wd) back to the isometry
+    ProfScope ps(&h->prof, h->stream, CAT_BACK, 4.0 * h->K * (double)h->dim * h->dim * h->dim * h->dim * batch * (tangent ? 2 : 1),
+                 (h->model == OTN_MODEL_LOCAL ? 2 : 1) + ((tangent && h->dim >= 8) ? 1 : 0));
     const long long SZ = h->SZ, S = (long long)h->m * SZ;
     const double* Wfull = (l == 0) ? h->G : layer_ptr(h->W, l, SZ);                  // W_0 = G_0
     const double* Wdfull = nullptr; long long sWd = 0;
@@ -434,16 +531,33 @@ static int back_layer(otn_problem* h, int batch, const int* active, int l, const
         nslices = h->nf;
     }
     const int dim = h->dim;
-    const size_t wsz = (size_t)dim * dim * (dim + 1);
     dim3 grid(dim, batch);
-    if (!tangent) {
-        const size_t sm = (wsz + h->np) * 8;
-        OTN_TRY(set_smem(back_assemble_kernel<false>, sm));
-        back_assemble_kernel<false><<<grid, BAS_THREADS, sm, h->stream>>>(Wsup, nullptr, sW, 0, nslices, x, nullptr, h->zraw, nullptr, dim, h->K, active, h->m, l);
+    if (dim == 16 || dim == 8) {
+        // streaming kernel, one CTA per instance; tangent = Wd*x then += W*eta
+#define BAS_STREAM(DIMV)                                                                                                        \
+    do {                                                                                                                        \
+        const size_t sm = BasCfg<DIMV>::smem_bytes(h->K);                                                                       \
+        OTN_TRY(set_smem(back_assemble_stream_kernel<DIMV>, sm));                                                               \
+        if (!tangent) {                                                                                                         \
+            back_assemble_stream_kernel<DIMV><<<batch, 256, sm, h->stream>>>(Wsup, sW, x, h->zraw, h->K, 0, active, h->m, l);   \
+        } else {                                                                                                                \
+            back_assemble_stream_kernel<DIMV><<<batch, 256, sm, h->stream>>>(Wdsup, sWds, x, h->zdraw, h->K, 0, active, h->m, l); \
+            back_assemble_stream_kernel<DIMV><<<batch, 256, sm, h->stream>>>(Wsup, sW, eta, h->zdraw, h->K, 1, active, h->m, l);  \
+        }                                                                                                                       \
+    } while (0)
+        if (dim == 16) BAS_STREAM(16); else BAS_STREAM(8);
+#undef BAS_STREAM
     } else {
-        const size_t sm = (2 * wsz + 2 * h->np) * 8;
-        OTN_TRY(set_smem(back_assemble_kernel<true>, sm));
-        back_assemble_kernel<true><<<grid, BAS_THREADS, sm, h->stream>>>(Wsup, Wdsup, sW, sWds, nslices, x, eta, nullptr, h->zdraw, dim, h->K, active, h->m, l);
+        const size_t wsz = (size_t)dim * dim * (dim + 1);
+        if (!tangent) {
+            const size_t sm = (wsz + h->np) * 8;
+            OTN_TRY(set_smem(back_assemble_kernel<false>, sm));
+            back_assemble_kernel<false><<<grid, BAS_THREADS, sm, h->stream>>>(Wsup, nullptr, sW, 0, nslices, x, nullptr, h->zraw, nullptr, dim, h->K, active, h->m, l);
+        } else {
+            const size_t sm = (2 * wsz + 2 * h->np) * 8;
+            OTN_TRY(set_smem(back_assemble_kernel<true>, sm));
+            back_assemble_kernel<true><<<grid, BAS_THREADS, sm, h->stream>>>(Wsup, Wdsup, sW, sWds, nslices, x, eta, nullptr, h->zdraw, dim, h->K, active, h->m, l);
+        }
     }
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -456,12 +570,12 @@ static int reverse_chain(otn_problem* h, int batch, const int* active, const dou
         p.A1 = layer_ptr(h->G, l, SZ); p.sA1 = S;
         p.B1 = (l == 1) ? h->Y : layer_ptr(h->P, l - 1, SZ); p.sB1 = S;
         p.C = layer_ptr(h->W, l, SZ); p.sC = S;
-        CUDA_TRY(gemm_launch(p, false, true, h->stream));
+        CUDA_TRY(hgemm(h, p, false, true));
         GemmParams r = gp(h, batch, active);                       // G_{l-1} = Y_l^T G_l
         r.A1 = layer_ptr(h->Y, l, SZ); r.sA1 = S;
         r.B1 = layer_ptr(h->G, l, SZ); r.sB1 = S;
         r.C = layer_ptr(h->G, l - 1, SZ); r.sC = S;
-        CUDA_TRY(gemm_launch(r, true, false, h->stream));
+        CUDA_TRY(hgemm(h, r, true, false));
         OTN_TRY(back_layer(h, batch, active, l, x, false, nullptr));
     }
     OTN_TRY(back_layer(h, batch, active, 0, x, false, nullptr));
@@ -477,6 +591,7 @@ static int tangent_pass(otn_problem* h, int batch, const int* active, const doub
     int cur = 0;
     if (m == 1) {
         CUDA_TRY(cudaMemcpy2DAsync(h->Gd, 2 * SZ * 8, h->Yd, S * 8, SZ * 8, batch, cudaMemcpyDeviceToDevice, h->stream));
+        ProfScope ps(&h->prof, h->stream, CAT_OTHER, 0.0);
         resid_kernel<<<batch, 256, 0, h->stream>>>(nullptr, 0, nullptr, 0, nullptr, h->G, S, h->Gd, 2 * SZ, h->part_s, SZ, active);
         CUDA_TRY(cudaGetLastError());
     }
@@ -491,7 +606,7 @@ static int tangent_pass(otn_problem* h, int batch, const int* active, const doub
             p.C = h->Gd; p.sC = 2 * SZ;
             p.epi = EPI_DOT; p.E = layer_ptr(h->G, m - 1, SZ); p.sE = S; p.partial = h->part_s;
         }
-        CUDA_TRY(gemm_launch(p, false, false, h->stream));
+        CUDA_TRY(hgemm(h, p, false, false));
     }
     // reverse tangent
     for (int l = m - 1; l >= 1; --l) {
@@ -502,12 +617,12 @@ static int tangent_pass(otn_problem* h, int batch, const int* active, const doub
         p.A1 = Ghat; p.sA1 = 2 * SZ; p.B1 = Pprev; p.sB1 = S;
         p.A2 = layer_ptr(h->G, l, SZ); p.sA2 = S; p.B2 = Pdprev; p.sB2 = S;
         p.C = h->Wd; p.sC = SZ;
-        CUDA_TRY(gemm_launch(p, false, true, h->stream));
+        CUDA_TRY(hgemm(h, p, false, true));
         GemmParams r = gp(h, batch, active);                       // Ghat_{l-1} = Yd_l^T G_l + Y_l^T Ghat_l
         r.A1 = layer_ptr(h->Yd, l, SZ); r.sA1 = S; r.B1 = layer_ptr(h->G, l, SZ); r.sB1 = S;
         r.A2 = layer_ptr(h->Y, l, SZ); r.sA2 = S; r.B2 = Ghat; r.sB2 = 2 * SZ;
         r.C = h->Gd + (long long)(1 - cur) * SZ; r.sC = 2 * SZ;
-        CUDA_TRY(gemm_launch(r, true, false, h->stream));
+        CUDA_TRY(hgemm(h, r, true, false));
         OTN_TRY(back_layer(h, batch, active, l, x, true, eta));
         cur = 1 - cur;
     }
@@ -518,12 +633,23 @@ static int tangent_pass(otn_problem* h, int batch, const int* active, const doub
 
 static int riem_launch(otn_problem* h, int batch, const int* active, int tiles, const double* x, const double* eta, bool hvp,
                        double* f, double* rgrad, double* egrad, double* heta) {
+    ProfScope ps(&h->prof, h->stream, CAT_RIEM, 0.0);
     RiemParams P{};
     P.x = x; P.zraw = h->zraw; P.eta = eta; P.zdraw = h->zdraw; P.part_f = h->part_f; P.part_s = h->part_s; P.im2 = h->im2;
     P.tindex = h->tindex; P.tiles = tiles; P.f_out = f; P.rgrad = rgrad; P.egrad = egrad; P.heta = heta;
     P.n = h->n; P.p = h->p; P.m = h->m; P.alpha0 = h->alpha0; P.alpha1 = h->alpha1; P.active = active;
     const size_t pp = (size_t)h->p * h->p;
-    if (!hvp) {
+    if ((h->p == 16 || h->p == 8) && h->n % 8 == 0) {
+        const size_t ld = h->p + 4;
+        const size_t sm = ((hvp ? 4 : 2) * (size_t)h->n * ld + 8 * h->p * ld) * 8;
+#define RIEM_MMA(PV)                                                                               \
+    do {                                                                                           \
+        if (!hvp) { OTN_TRY(set_smem(riem_mma_kernel<PV, false>, sm)); riem_mma_kernel<PV, false><<<batch * h->m, ST_THREADS, sm, h->stream>>>(P); } \
+        else { OTN_TRY(set_smem(riem_mma_kernel<PV, true>, sm)); riem_mma_kernel<PV, true><<<batch * h->m, ST_THREADS, sm, h->stream>>>(P); }      \
+    } while (0)
+        if (h->p == 16) RIEM_MMA(16); else RIEM_MMA(8);
+#undef RIEM_MMA
+    } else if (!hvp) {
         const size_t sm = (2 * (size_t)h->np + 8 * pp) * 8;
         OTN_TRY(set_smem(riem_kernel<false>, sm));
         riem_kernel<false><<<batch * h->m, ST_THREADS, sm, h->stream>>>(P);
@@ -541,6 +667,7 @@ int otn_dev_cost(otn_problem* h, const double* x, int batch, const int* active, 
     int tiles;
     OTN_TRY(build_layers(h, x, nullptr, batch, active, true));
     OTN_TRY(forward_chain(h, batch, active, nullptr, &tiles));
+    ProfScope ps(&h->prof, h->stream, CAT_OTHER, 0.0);
     cost_from_partials_kernel<<<(batch + 127) / 128, 128, 0, h->stream>>>(h->part_f, tiles, h->im2, h->tindex, f, batch, active);
     CUDA_TRY(cudaGetLastError());
     h->cached_batch = 0;

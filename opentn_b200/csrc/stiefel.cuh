@@ -350,3 +350,192 @@ __global__ void __launch_bounds__(ST_THREADS) cdot_kernel(const double* __restri
 }
 
 }  // namespace otn
+
+// ==================================================================================================================
+// Tensor-core (DMMA.8x8x4) version of the Riemannian epilogue for p in {8, 16} (full-sites model).  The SIMT version above
+// is a chain of 256-long dependent FMA loops on 8 warps per SM (latency bound: 3 ms per 3072 isometries); here every
+// p x p Gram and every (n x p)(p x p) product is issued as DMMA on padded (LD = p + 4) shared-memory operands.
+// ==================================================================================================================
+namespace otn {
+
+// G_q = A_q^T B_q for q < NG: (P/8)^2 blocks of 8x8 per Gram, blocks dealt to the 8 warps; fixed summation order.
+template <int P, int NG>
+__device__ __forceinline__ void gram_blocks_mma(const double* const (&A)[NG], const double* const (&B)[NG], double* const (&G)[NG],
+                                                int n) {
+    constexpr int LD = P + 4, PB = P / 8, NB = NG * PB * PB;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    for (int bid = warp; bid < NB; bid += ST_THREADS / 32) {
+        const int q = bid / (PB * PB), ij = bid - q * PB * PB, i = ij / PB, j = ij - i * PB;
+        const double* a = A[q] + i * 8 + g;
+        const double* b = B[q] + j * 8 + g;
+        double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;   // two interleaved accumulators (ILP)
+        int r0 = 0;
+        for (; r0 + 8 <= n; r0 += 8) {
+            dmma884(c0, c1, a[(r0 + t) * LD], b[(r0 + t) * LD]);
+            dmma884(d0, d1, a[(r0 + 4 + t) * LD], b[(r0 + 4 + t) * LD]);
+        }
+        for (; r0 < n; r0 += 4) dmma884(c0, c1, a[(r0 + t) * LD], b[(r0 + t) * LD]);
+        double* out = G[q] + (i * 8 + g) * LD + j * 8 + 2 * t;
+        out[0] = c0 + d0; out[1] = c1 + d1;
+    }
+}
+
+// Out = alpha Out + sum_{q<NT} A_q * op(G_q)   (n x P), op = transpose if GT[q]; rows dealt to warps in blocks of 8.
+template <int P, int NT>
+__device__ __forceinline__ void addmul_mma(double* Out, double alpha, const double* const (&A)[NT], const double* const (&G)[NT],
+                                           const bool (&GT)[NT], int n) {
+    constexpr int LD = P + 4, PB = P / 8;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    for (int rb = warp; rb < n / 8; rb += ST_THREADS / 32) {
+        double acc[PB][2];
+#pragma unroll
+        for (int j = 0; j < PB; ++j) {
+            const double* o = Out + (rb * 8 + g) * LD + j * 8 + 2 * t;
+            acc[j][0] = alpha * o[0]; acc[j][1] = alpha * o[1];
+        }
+#pragma unroll
+        for (int q = 0; q < NT; ++q) {
+#pragma unroll
+            for (int i0 = 0; i0 < P; i0 += 4) {
+                const double a = A[q][(rb * 8 + g) * LD + i0 + t];
+#pragma unroll
+                for (int j = 0; j < PB; ++j) {
+                    const double b = GT[q] ? G[q][(j * 8 + g) * LD + i0 + t] : G[q][(i0 + t) * LD + j * 8 + g];
+                    dmma884(acc[j][0], acc[j][1], a, b);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < PB; ++j) {
+            double* o = Out + (rb * 8 + g) * LD + j * 8 + 2 * t;
+            o[0] = acc[j][0]; o[1] = acc[j][1];
+        }
+    }
+}
+
+template <int P, bool HVP>
+__global__ void __launch_bounds__(ST_THREADS) riem_mma_kernel(const RiemParams Pm) {
+    extern __shared__ __align__(16) double sm[];
+    constexpr int LD = P + 4, GS = P * LD;
+    const int item = blockIdx.x, inst = item / Pm.m, layer = item - inst * Pm.m;
+    if (Pm.active != nullptr && Pm.active[inst] == 0) return;
+    const int n = Pm.n, np = n * P, nl = n * LD;
+    double* X = sm;
+    double* E = X + nl;
+    double* Z = E + (HVP ? nl : 0);
+    double* Zd = Z + nl;
+    double* G = Zd + (HVP ? nl : 0);     // 8 Gram-sized slots
+    __shared__ double sc[2];
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int t = 0; t < Pm.tiles; ++t) s += Pm.part_f[(long long)inst * Pm.tiles + t];
+        s += Pm.im2[Pm.tindex ? Pm.tindex[inst] : 0];
+        const double f = sqrt(s);
+        sc[0] = f;
+        if (HVP) {
+            double d = 0.0;
+            for (int t = 0; t < Pm.tiles; ++t) d += Pm.part_s[(long long)inst * Pm.tiles + t];
+            sc[1] = d;
+        }
+        if (layer == 0 && Pm.f_out != nullptr) Pm.f_out[inst] = f;
+    }
+    __syncthreads();
+    const double f = sc[0], inv_f = 1.0 / f;
+    const long long base = (long long)item * np;
+    for (int i = threadIdx.x; i < np; i += ST_THREADS) {
+        const int r = i / P, c = i - r * P, o = r * LD + c;
+        X[o] = Pm.x[base + i];
+        const double zr = Pm.zraw[base + i];
+        const double z = zr * inv_f;
+        Z[o] = z;
+        if (!HVP && Pm.egrad != nullptr) Pm.egrad[base + i] = z;
+        if (HVP) {
+            E[o] = Pm.eta[base + i];
+            Zd[o] = Pm.zdraw[base + i] * inv_f - zr * (sc[1] * inv_f * inv_f * inv_f);
+        }
+    }
+    __syncthreads();
+    const double a0 = Pm.alpha0, a1 = Pm.alpha1;
+    const double c1 = 0.5 * ((1.0 / a1) - (2.0 / a0)), c2 = 0.5 * (1.0 / a1), kap = (a0 - a1) / a0;
+    double *XZ = G, *XZd = G + GS, *XE = G + 2 * GS, *EZ = G + 3 * GS, *Gn = G + 4 * GS, *Gd = G + 5 * GS, *T0 = G + 6 * GS, *T1 = G + 7 * GS;
+    if (HVP) {
+        const double* const As[4] = {X, X, X, E};
+        const double* const Bs[4] = {Z, Zd, E, Z};
+        double* const Gs[4] = {XZ, XZd, XE, EZ};
+        gram_blocks_mma<P, 4>(As, Bs, Gs, n);
+    } else {
+        const double* const As[1] = {X};
+        const double* const Bs[1] = {Z};
+        double* const Gs[1] = {XZ};
+        gram_blocks_mma<P, 1>(As, Bs, Gs, n);
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < P * P; o += ST_THREADS) {
+        const int i = o / P, j = o - i * P, ij = i * LD + j, ji = j * LD + i;
+        Gn[ij] = c1 * XZ[ij] - c2 * XZ[ji];
+        if (HVP) Gd[ij] = c1 * (EZ[ij] + XZd[ij]) - c2 * (XZd[ji] + EZ[ji]);
+    }
+    __syncthreads();
+    if (HVP) {   // Dnu = Zd/a0 + eta Gn + X Gd
+        const double* const As[2] = {E, X};
+        const double* const Gs[2] = {Gn, Gd};
+        const bool GT[2] = {false, false};
+        addmul_mma<P, 2>(Zd, 1.0 / a0, As, Gs, GT, n);
+    }
+    {            // nu = Z/a0 + X Gn
+        const double* const As[1] = {X};
+        const double* const Gs[1] = {Gn};
+        const bool GT[1] = {false};
+        addmul_mma<P, 1>(Z, 1.0 / a0, As, Gs, GT, n);
+    }
+    __syncthreads();
+    if (Pm.rgrad != nullptr)
+        for (int i = threadIdx.x; i < np; i += ST_THREADS) Pm.rgrad[base + i] = Z[(i / P) * LD + (i % P)];
+    if (!HVP) return;
+    double *Nu = Z, *EN = XZ, *XN = XZd;
+    {
+        const double* const As[2] = {E, X};
+        const double* const Bs[2] = {Nu, Nu};
+        double* const Gs[2] = {EN, XN};
+        gram_blocks_mma<P, 2>(As, Bs, Gs, n);
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < P * P; o += ST_THREADS) {   // Gz = (EN + EN^T)/2 - kap (XE XN^T + XN XE^T); T0 = kap XN; T1 = kap XE
+        const int i = o / P, j = o - i * P;
+        double s = 0.0;
+        for (int k = 0; k < P; ++k) s += XE[i * LD + k] * XN[j * LD + k] + XN[i * LD + k] * XE[j * LD + k];
+        Gn[i * LD + j] = 0.5 * (EN[i * LD + j] + EN[j * LD + i]) - kap * s;
+        T0[i * LD + j] = kap * XN[i * LD + j];
+        T1[i * LD + j] = kap * XE[i * LD + j];
+    }
+    __syncthreads();
+    {            // z = Dnu + X Gz + eta (kap XN)^T + nu (kap XE)^T
+        const double* const As[3] = {X, E, Nu};
+        const double* const Gs[3] = {Gn, T0, T1};
+        const bool GT[3] = {false, true, true};
+        addmul_mma<P, 3>(Zd, 1.0, As, Gs, GT, n);
+    }
+    __syncthreads();
+    {            // H eta = z - X sym(X^T z)
+        const double* const As[1] = {X};
+        const double* const Bs[1] = {Zd};
+        double* const Gs[1] = {T0};
+        gram_blocks_mma<P, 1>(As, Bs, Gs, n);
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < P * P; o += ST_THREADS) {
+        const int i = o / P, j = o - i * P;
+        T1[i * LD + j] = -0.5 * (T0[i * LD + j] + T0[j * LD + i]);
+    }
+    __syncthreads();
+    {
+        const double* const As[1] = {X};
+        const double* const Gs[1] = {T1};
+        const bool GT[1] = {false};
+        addmul_mma<P, 1>(Zd, 1.0, As, Gs, GT, n);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < np; i += ST_THREADS) Pm.heta[base + i] = Zd[(i / P) * LD + (i % P)];
+}
+
+}  // namespace otn

@@ -11,7 +11,7 @@ static int tr_alloc(otn_problem* h) {
     TrState& t = h->tr;
     if (t.cap_batch >= h->max_batch) return 0;
     const size_t B = (size_t)h->max_batch, V = B * h->m * h->np;
-    const size_t bytes = 6 * V * 8 + 8 * B * 8 + 8 * B * 4 + 64;
+    const size_t bytes = 6 * (V * 8 + 16) + 8 * (B * 8 + 16) + 6 * (B * 4 + 16) + 64;   // every slice is rounded up to 16 B
     OTN_TRY(h->tr_buf.ensure(bytes));
     char* base = h->tr_buf.as<char>();
     auto take = [&](size_t nbytes) { char* r = base; base += (nbytes + 15) / 16 * 16; return r; };
@@ -28,6 +28,7 @@ static int tr_alloc(otn_problem* h) {
 static int cdot_launch(otn_problem* h, const double* x, const double* a, const double* b, int batch, double* out) {
     const size_t sm = (3 * (size_t)h->np + 2 * (size_t)h->p * h->p) * 8;
     OTN_TRY(set_smem(cdot_kernel, sm));
+    ProfScope ps(&h->prof, h->stream, CAT_TR, 0.0);
     cdot_kernel<<<batch, ST_THREADS, sm, h->stream>>>(x, a, b, out, h->n, h->p, h->m, nullptr);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -82,14 +83,14 @@ extern "C" int otn_tr_run(otn_problem* h, double* x, int batch, const otn_tr_par
         OTN_TRY(otn_dev_cost_grad(h, h->x, batch, nullptr, t.fx, t.g, nullptr));
         if (rep && rep->f_iter) CUDA_TRY(cudaMemcpyAsync(hist_d(rep->f_iter, k), t.fx, (size_t)batch * 8, cudaMemcpyDefault, st));
         // eta, on_boundary = truncated_cg(grad, hess, radius)                                      (:61)
-        tcg_init_kernel<<<batch, ST_THREADS, sm_init, st>>>(tp);
+        { ProfScope ps(&h->prof, st, CAT_TR, 0.0); tcg_init_kernel<<<batch, ST_THREADS, sm_init, st>>>(tp); }
         CUDA_TRY(cudaGetLastError());
         int n_active = batch;
         for (int j = 0; j < maxiter && n_active > 0; ++j) {
             OTN_TRY(otn_dev_hvp(h, h->x, t.d, batch, t.tcg_active, t.Hd));
             hvps += n_active;
             CUDA_TRY(cudaMemsetAsync(t.n_active, 0, 4, st));
-            tcg_step_kernel<<<batch, ST_THREADS, sm_step, st>>>(tp);
+            { ProfScope ps(&h->prof, st, CAT_TR, 0.0); tcg_step_kernel<<<batch, ST_THREADS, sm_step, st>>>(tp); }
             CUDA_TRY(cudaGetLastError());
             CUDA_TRY(cudaMemcpyAsync(&n_active, t.n_active, 4, cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
@@ -100,14 +101,14 @@ extern "C" int otn_tr_run(otn_problem* h, double* x, int batch, const otn_tr_par
         OTN_TRY(cdot_launch(h, h->x, t.g, t.z, batch, t.gz));
         OTN_TRY(cdot_launch(h, h->x, t.z, t.Hd, batch, t.zHz));
         // x_next = retract(x, eta) ; f(x_next)                                                     (:62, :67)
-        retract_kernel<<<batch * h->m, ST_THREADS, sm_ret, st>>>(h->x, t.z, t.xn, h->n, h->p, h->m, nullptr, t.status);
+        { ProfScope ps(&h->prof, st, CAT_TR, 0.0); retract_kernel<<<batch * h->m, ST_THREADS, sm_ret, st>>>(h->x, t.z, t.xn, h->n, h->p, h->m, nullptr, t.status); }
         CUDA_TRY(cudaGetLastError());
         OTN_TRY(otn_dev_cost(h, t.xn, batch, nullptr, t.fn));
         TrUpdateParams up{};
         up.radius = t.radius; up.rho = t.rho; up.fx = t.fx; up.fn = t.fn; up.gz = t.gz; up.zHz = t.zHz; up.on_boundary = t.on_boundary;
         up.accepted = t.accepted; up.status = t.status; up.rho_trust = prm.rho_trust; up.maxradius = prm.maxradius; up.batch = batch;
         up.h_rho = d_hrho; up.h_radius = d_hrad; up.h_ncg = d_hncg; up.h_onb = d_honb; up.h_acc = d_hacc; up.n_cg = t.n_cg;
-        tr_update_kernel<<<(batch + 127) / 128, 128, 0, st>>>(up);
+        { ProfScope ps(&h->prof, st, CAT_TR, 0.0, 2); tr_update_kernel<<<(batch + 127) / 128, 128, 0, st>>>(up); }
         CUDA_TRY(cudaGetLastError());
         select_copy_kernel<<<dim3(8, batch), 256, 0, st>>>(h->x, t.xn, t.accepted, per);                 // (:76-77)
         CUDA_TRY(cudaGetLastError());

@@ -93,6 +93,7 @@ class StiefelFit:
         self._handles = {}
         self._tindex = None
         self._tindex_ver = 0
+        self._cached = None
         self.p = d ** N if model == "full" else d * d
         self.last_report = None
 
@@ -171,6 +172,7 @@ class StiefelFit:
         return np.empty(shape, dtype=dtype)
 
     def set_metric(self, metric):
+        self._cached = None
         self.metric = metric
         mid = metric_id(metric)
         for h in self._handles.values():
@@ -186,6 +188,7 @@ class StiefelFit:
         x, B, m, K, single, cuda = self._prep(xs)
         h = self._handle(m, K, B)
         M = self._empty_like(x, (B, self.D, self.D), cuda)
+        self._cached = None
         check(h._lib.otn_model(h.h, ptr(x), B, ptr(M)))
         return M[0] if single else M
 
@@ -194,6 +197,7 @@ class StiefelFit:
         h = self._handle(m, K, B)
         self._bind(h, B)
         f = self._empty_like(x, (B,), cuda)
+        self._cached = None
         check(h._lib.otn_cost(h.h, ptr(x), B, ptr(f)))
         return float(f[0]) if single else f
 
@@ -206,7 +210,7 @@ class StiefelFit:
         g = self._empty_like(x, tuple(x.shape), cuda)
         e = self._empty_like(x, tuple(x.shape), cuda) if want_egrad else None
         check(h._lib.otn_cost_grad(h.h, ptr(x), B, ptr(f), ptr(g), ptr(e)))
-        self._cached = (h, B)
+        self._cached = (h, B, object())
         if single:
             return (float(f[0]), g[0], e[0]) if want_egrad else (float(f[0]), g[0])
         return (f, g, e) if want_egrad else (f, g)
@@ -226,7 +230,7 @@ class StiefelFit:
         else:
             f, g, hv = out
         check(h._lib.otn_triple(h.h, ptr(x), ptr(e), B, ptr(f), ptr(g), ptr(hv)))
-        self._cached = (h, B)
+        self._cached = (h, B, object())
         if single:
             return float(f[0]), g[0], hv[0]
         return f, g, hv
@@ -236,7 +240,7 @@ class StiefelFit:
         cached = getattr(self, "_cached", None)
         if cached is None:
             raise OtnError("no primal cache: call cost_grad or triple first")
-        h, B = cached
+        h, B, _ = cached
         e, B2, m2, K2, single, cuda = self._prep(etas)
         if B2 != B:
             raise ValueError("batch differs from the cached primal pass")
@@ -268,6 +272,7 @@ class StiefelFit:
             rad_io = np.ascontiguousarray(np.broadcast_to(np.asarray(radius, dtype=np.float64), (B,)).copy())
         else:
             rad_io = np.full(B, radius_init)
+        self._cached = None
         rep = _lib.TrReport(ptr(f_iter), ptr(rho), ptr(rad), ptr(n_cg), ptr(onb), ptr(acc), ptr(x_iter), ptr(rad_io), ptr(status), 0)
         check(h._lib.otn_tr_run(h.h, ptr(xw), B, C.byref(prm), C.byref(rep)))
         report = dict(f_iter=f_iter, rho=rho, radius_iter=rad, n_cg=n_cg, on_boundary=onb, accepted=acc, status=status,

@@ -1,0 +1,80 @@
+"""Host-side mirror of `opentn.optimization` for the Stiefel trust-region path.
+
+`model_stiefel_local`, `model_Ys_stiefel` and `frobenius_norm` keep the reference's signatures
+(optimization.py:106, 147, 56) and evaluate on the GPU through libotn.  The cost closure the reference notebooks build
+from them is `opentn_b200.StiefelFit` here (see fit.py).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .fit import StiefelFit
+from .transformations import (choi2ortho, create_2local_liouvillians, exp_operator_dt, factorize_psd_truncated,
+                              get_kitaev_nn_linbladian, lindbladian2super, super2choi)
+
+_MODEL_CACHE = {}
+
+
+def _model_fit(model, N, d, D, device=0):
+    key = (model, N, d, device)
+    fit = _MODEL_CACHE.get(key)
+    if fit is None:
+        fit = StiefelFit(np.zeros((D, D)), model=model, N=N, d=d, device=device)
+        _MODEL_CACHE[key] = fit
+    return fit
+
+
+def model_stiefel_local(xs, N: int, d: int) -> np.ndarray:
+    """Composition of m two-site layers (odd list index => pbc-shifted pairs), optimization.py:106-137."""
+    return _model_fit("local", N, d, d ** (2 * N)).model_matrix(xs)
+
+
+def model_Ys_stiefel(xs) -> np.ndarray:
+    """Composition of m full-sites layers, optimization.py:147-151.  d = 2 is assumed to infer N from the isometry width."""
+    p = np.asarray(xs[0]).shape[-1]
+    N = int(round(np.log2(p)))
+    if 2 ** N != p:
+        raise ValueError("model_Ys_stiefel: isometry width must be 2^N")
+    return _model_fit("full", N, 2, p * p).model_matrix(xs)
+
+
+def frobenius_norm(A, B, squared: bool = False):
+    """|| A - B ||_F (squared if asked), optimization.py:56-61.  A plain host reduction: inside a fit the residual norm is
+    fused into the last chain GEMM on the device (StiefelFit.cost)."""
+    r = np.asarray(A) - np.asarray(B)
+    s = float(np.sum(r.real ** 2) + (np.sum(r.imag ** 2) if np.iscomplexobj(r) else 0.0))
+    return s if squared else float(np.sqrt(s))
+
+
+def get_general_trotter_local_ansatz(lindbladians, tau, n: int):
+    """[half] + [full]*(2n-1) + [half] two-site superoperators of the Strang splitting, optimization.py:172-185."""
+    if not isinstance(lindbladians, list):
+        lindbladians = [lindbladians]
+    dt = tau / n
+    s = lindbladian2super(Li=lindbladians)
+    half, full = exp_operator_dt(s, dt / 2), exp_operator_dt(s, dt)
+    return [half] + [full] * (2 * n - 1) + [half]
+
+
+def get_kitaev_trotter_local_ansatz(gamma: float, tau, n: int):
+    """optimization.py:161-169"""
+    return get_general_trotter_local_ansatz([get_kitaev_nn_linbladian(gamma)], tau, n)
+
+
+def compute_trotter_approximation_error(d: int, N: int, tau, n: int, Li) -> float:
+    """Cost of the Strang ansatz at its natural Choi rank, optimization.py:215-226 (cost evaluated on the GPU)."""
+    Lvec = create_2local_liouvillians(Li=Li, N=N, d=d, pbc=True)[0]
+    chois = [super2choi(x.real) for x in get_general_trotter_local_ansatz(Li, tau, n)]
+    ranks = [np.linalg.matrix_rank(c) for c in chois]
+    assert len(set(ranks)) == 1, "not all ranks are the same"
+    xs = [choi2ortho(factorize_psd_truncated(c, chi_max=ranks[0])) for c in chois]
+    fit = StiefelFit(exp_operator_dt(Lvec, tau), model="local", N=N, d=d)
+    try:
+        return fit(xs)
+    finally:
+        fit.close()
+
+
+def compute_kitaev_approximation_error(d: int, N: int, gamma: float, tau, n: int) -> float:
+    """optimization.py:187-213"""
+    return compute_trotter_approximation_error(d, N, tau, n, [get_kitaev_nn_linbladian(gamma)])

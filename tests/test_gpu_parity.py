@@ -106,3 +106,40 @@ def test_golden_costs_on_gpu(P, targets, goldens):
     assert abs(ff(xr4) - goldens["ref/cost_fullsites_r4_xs"]) < 1e-13
     for x in (fit, fit05, fk, ff):
         x.close()
+
+
+@pytest.mark.parametrize("model,m,K", [("full", 3, 8), ("local", 4, 3)])
+def test_generic_complex_target(P, model, m, K):
+    """A target that is NOT a physical superoperator (random, complex, no swap symmetry): the device path runs its reverse
+    chain on the swap-symmetrised residual and folds the rest into a constant -- results must still equal the oracle's."""
+    from opentn_b200 import StiefelFit
+    rng = np.random.default_rng(99)
+    T = 0.1 * (rng.standard_normal((256, 256)) + 1j * rng.standard_normal((256, 256)))
+    p = 16 if model == "full" else 4
+    xs, et = _random_batch(P, 2, m, p * K, p, 3)
+    fit = StiefelFit(T, model=model, N=N, d=d, metric="canonical", max_batch=2)
+    f, g, h = fit.triple(xs, et)
+    spec = P.CostSpec(T, model, N, d)
+    for b in range(2):
+        fo, go, ho = P.triple(spec, list(xs[b]), list(et[b]), "canonical")
+        assert abs(f[b] - fo) / fo < 1e-12
+        assert rel(g[b], np.array(go)) < 1e-10
+        assert rel(h[b], np.array(ho)) < 1e-10
+    fit.close()
+
+
+def test_multiple_targets(P, targets):
+    """Per-instance target selection (tau sweep): instance b fits target index[b]."""
+    from opentn_b200 import StiefelFit
+    Ts = np.stack([targets["pspl_tau1"], targets["pspl_tau05"], targets["kitaev_pbc_tau05"]])
+    xs, et = _random_batch(P, 4, 3, 8, 4, 21)
+    fit = StiefelFit(Ts, model="local", N=N, d=d, metric="canonical", max_batch=4)
+    index = [2, 0, 1, 0]
+    fit.set_target_index(index)
+    f, g, h = fit.triple(xs, et)
+    for b in range(4):
+        fo, go, ho = P.triple(P.CostSpec(Ts[index[b]], "local", N, d), list(xs[b]), list(et[b]), "canonical")
+        assert abs(f[b] - fo) / fo < 1e-12
+        assert rel(g[b], np.array(go)) < 1e-10
+        assert rel(h[b], np.array(ho)) < 1e-10
+    fit.close()
