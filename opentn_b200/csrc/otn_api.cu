@@ -205,6 +205,10 @@ struct otn_problem {
     TrState tr;                  // trust-region state (tr.cuh)
     Profiler prof;
     bool own_stream = true;
+    // host-pointer pipeline (otn_triple): chunked H2D / compute / D2H overlap
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    DevBuf pipe_buf;
     DevBuf tr_buf;
     EmbedTables tables() const { return EmbedTables{tab, inv, D, q, nf}; }
 };
@@ -228,6 +232,10 @@ extern "C" void otn_destroy(otn_problem* h) {
     for (DevBuf* b : {&h->in_x, &h->in_eta, &h->out_a, &h->out_b, &h->out_c, &h->out_f, &h->out_M, &h->tr_buf}) b->release();
     for (auto& r : h->prof.recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (auto e : h->prof.pool) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) for (cudaEvent_t e : {h->ev_in[i], h->ev_done[i], h->ev_out[i]}) if (e) cudaEventDestroy(e);
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
+    h->pipe_buf.release();
     if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -744,9 +752,69 @@ extern "C" int otn_cost_grad(otn_problem* h, const double* x, int batch, double*
     return 0;
 }
 
+// one U1 pass over `batch` instances whose x / eta / outputs are device arrays (work matrices of instances 0..batch-1)
+static int triple_device(otn_problem* h, const double* x, const double* eta, int batch, double* f, double* rgrad, double* heta) {
+    int tiles;
+    // primal + tangent layers in one assembly pass, then forward / reverse / tangent chains
+    OTN_TRY(build_layers(h, x, eta, batch, nullptr, true));
+    OTN_TRY(forward_chain(h, batch, nullptr, nullptr, &tiles));
+    h->tr.tiles = tiles;
+    OTN_TRY(reverse_chain(h, batch, nullptr, x));
+    OTN_TRY(tangent_pass(h, batch, nullptr, x, eta, true));
+    OTN_TRY(riem_launch(h, batch, nullptr, tiles, x, eta, true, f, rgrad, nullptr, heta));
+    return 0;
+}
+
+// Host arrays in, host arrays out: the batch is cut into chunks and pipelined over three streams so that the PCIe copies of
+// chunk c+1 (H2D) and chunk c-1 (D2H) overlap the kernels of chunk c.  Double-buffered staging, ordering by events.
+static int triple_pipelined(otn_problem* h, const double* x, const double* eta, int batch, double* f, double* rgrad, double* heta) {
+    const int C = 256;
+    const size_t per = (size_t)h->m * h->np;
+    if (!h->s_in) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
+        }
+    }
+    // staging: per slot  x | eta | rgrad | heta | f
+    const size_t slot_doubles = 4 * (size_t)C * per + C;
+    OTN_TRY(h->pipe_buf.ensure(2 * slot_doubles * 8));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    const int nchunks = (batch + C - 1) / C;
+    for (int c = 0; c < nchunks; ++c) {
+        const int slot = c & 1, b0 = c * C, nb = std::min(C, batch - b0);
+        double* base = h->pipe_buf.as<double>() + slot * slot_doubles;
+        double *dx = base, *de = dx + (size_t)C * per, *dg = de + (size_t)C * per, *dh = dg + (size_t)C * per, *df = dh + (size_t)C * per;
+        if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_done[slot], 0));          // kernels of chunk c-2 finished reading dx/de
+        CUDA_TRY(cudaMemcpyAsync(dx, x + (size_t)b0 * per, nb * per * 8, cudaMemcpyHostToDevice, h->s_in));
+        CUDA_TRY(cudaMemcpyAsync(de, eta + (size_t)b0 * per, nb * per * 8, cudaMemcpyHostToDevice, h->s_in));
+        CUDA_TRY(cudaEventRecord(h->ev_in[slot], h->s_in));
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_in[slot], 0));
+        if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_out[slot], 0));         // D2H of chunk c-2 drained dg/dh/df
+        OTN_TRY(triple_device(h, dx, de, nb, df, dg, dh));
+        CUDA_TRY(cudaEventRecord(h->ev_done[slot], h->stream));
+        CUDA_TRY(cudaStreamWaitEvent(h->s_out, h->ev_done[slot], 0));
+        if (f) CUDA_TRY(cudaMemcpyAsync(f + b0, df, (size_t)nb * 8, cudaMemcpyDeviceToHost, h->s_out));
+        if (rgrad) CUDA_TRY(cudaMemcpyAsync(rgrad + (size_t)b0 * per, dg, nb * per * 8, cudaMemcpyDeviceToHost, h->s_out));
+        if (heta) CUDA_TRY(cudaMemcpyAsync(heta + (size_t)b0 * per, dh, nb * per * 8, cudaMemcpyDeviceToHost, h->s_out));
+        CUDA_TRY(cudaEventRecord(h->ev_out[slot], h->s_out));
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->s_in));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->s_out));
+    h->cached_batch = 0;   // the work matrices hold the last chunk only
+    return 0;
+}
+
 extern "C" int otn_triple(otn_problem* h, const double* x, const double* eta, int batch, double* f, double* rgrad, double* heta) {
     OTN_TRY(check_batch(h, batch));
     if (!x || !eta) return fail("null argument");
+    const bool all_host = !is_device_ptr(x) && !is_device_ptr(eta) && (!f || !is_device_ptr(f)) && (!rgrad || !is_device_ptr(rgrad)) &&
+                          (!heta || !is_device_ptr(heta));
+    if (all_host && batch >= 512) return triple_pipelined(h, x, eta, batch, f, rgrad, heta);
     const void *xd, *ed; void *fd, *gd, *hd;
     OTN_TRY(stage_in(x, xbytes(h, batch), h->in_x, h->stream, &xd));
     OTN_TRY(stage_in(eta, xbytes(h, batch), h->in_eta, h->stream, &ed));
@@ -754,14 +822,7 @@ extern "C" int otn_triple(otn_problem* h, const double* x, const double* eta, in
     OTN_TRY(stage_out(rgrad, xbytes(h, batch), h->out_a, &gd));
     OTN_TRY(stage_out(heta, xbytes(h, batch), h->out_c, &hd));
     OTN_TRY(keep_x(h, (const double*)xd, batch));
-    int tiles;
-    // primal + tangent layers in one assembly pass, then forward / reverse / tangent chains
-    OTN_TRY(build_layers(h, h->x, (const double*)ed, batch, nullptr, true));
-    OTN_TRY(forward_chain(h, batch, nullptr, nullptr, &tiles));
-    h->tr.tiles = tiles;
-    OTN_TRY(reverse_chain(h, batch, nullptr, h->x));
-    OTN_TRY(tangent_pass(h, batch, nullptr, h->x, (const double*)ed, true));
-    OTN_TRY(riem_launch(h, batch, nullptr, tiles, h->x, (const double*)ed, true, (double*)fd, (double*)gd, nullptr, (double*)hd));
+    OTN_TRY(triple_device(h, h->x, (const double*)ed, batch, (double*)fd, (double*)gd, (double*)hd));
     h->cached_batch = batch;
     OTN_TRY(finish_out(f, fd, (size_t)batch * 8, h->stream));
     OTN_TRY(finish_out(rgrad, gd, xbytes(h, batch), h->stream));

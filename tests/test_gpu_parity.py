@@ -143,3 +143,29 @@ def test_multiple_targets(P, targets):
         assert rel(g[b], np.array(go)) < 1e-10
         assert rel(h[b], np.array(ho)) < 1e-10
     fit.close()
+
+
+def test_pipelined_host_path_equals_device_path(P, targets):
+    """otn_triple with host arrays and batch >= 512 takes the chunked H2D/compute/D2H pipeline; results must be bitwise
+    those of the device-resident path (same kernels, same per-instance arithmetic)."""
+    import torch
+    from opentn_b200 import StiefelFit
+    B, K = 600, 2
+    rng = np.random.default_rng(1)
+    g = rng.standard_normal((B, 3, 16 * K, 16))
+    xs = np.linalg.qr(g)[0]
+    z = rng.standard_normal(xs.shape)
+    xtz = np.swapaxes(xs, -1, -2) @ z
+    et = z - xs @ (0.5 * (xtz + np.swapaxes(xtz, -1, -2)))
+    fit = StiefelFit(targets["kitaev_obc_tau4"], model="full", N=N, d=d, metric="canonical", max_batch=B)
+    f_h, g_h, h_h = fit.triple(xs, et)
+    xd, ed = torch.from_numpy(xs).cuda(), torch.from_numpy(et).cuda()
+    f_d, g_d, h_d = fit.triple(xd, ed)
+    np.testing.assert_array_equal(f_h, f_d.cpu().numpy())
+    np.testing.assert_array_equal(g_h, g_d.cpu().numpy())
+    np.testing.assert_array_equal(h_h, h_d.cpu().numpy())
+    spec = P.CostSpec(targets["kitaev_obc_tau4"], "full")
+    for b in (0, 255, 256, 599):
+        fo, go, ho = P.triple(spec, list(xs[b]), list(et[b]), "canonical")
+        assert abs(f_h[b] - fo) / fo < 1e-12 and rel(h_h[b], np.array(ho)) < 1e-10
+    fit.close()

@@ -1,0 +1,66 @@
+"""World-size-2 gloo test (CPU) of the N>1 path: round-robin instance sharding + the single final all-gather."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, total, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from opentn_b200 import sharding
+    from oracle import port as P
+    # tiny full-sites problem (N=2: D=16, isometries (8,4)); the "fit" of the CPU test is the oracle cost + one retraction
+    T = P.exp_operator_dt(P.lindbladian2super([P.get_kitaev_nn_linbladian(1.0)]), 1.0)
+    spec = P.CostSpec(T, "full")
+    rng = np.random.default_rng(0)                      # same inputs on every rank
+    xs_all = torch.from_numpy(np.array([[P.random_stiefel(8, 4, rng) for _ in range(2)] for _ in range(total)]))
+
+    def run_local(x):
+        xn = x.numpy()
+        f = torch.tensor([spec(list(xb)) for xb in xn])
+        return x * 1.0, f, torch.zeros(len(xn), dtype=torch.int32)
+
+    x_all, f_all, s_all = sharding.sharded_fit(run_local, xs_all)
+    idx = sharding.my_instances(total, rank, world)
+    assert list(idx) == list(range(rank, total, world))
+    want = torch.tensor([spec(list(xb)) for xb in xs_all.numpy()])
+    assert torch.equal(f_all, want), (f_all, want)
+    assert torch.equal(x_all, xs_all)
+    assert s_all.shape == (total,)
+    dist.barrier()
+    dist.destroy_process_group()
+    open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+
+
+@pytest.mark.parametrize("total", [7, 8])
+def test_sharded_gather_world2(tmp_path, total):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), total, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
+
+
+def test_shard_sizes():
+    from opentn_b200 import sharding
+    assert sharding.shard_sizes(4096, 8) == [512] * 8
+    assert sharding.shard_sizes(7, 2) == [4, 3]
+    assert sum(sharding.shard_sizes(1000, 8)) == 1000
+    x = torch.arange(5.0)
+    assert torch.equal(sharding.gather_instances(x, 5), x)       # no process group: identity
