@@ -263,12 +263,15 @@ def run_gpu(args):
     peak_tf = measure_fp64_peak(torch) if rank == 0 else None
 
     # ---- device-resident timing (`value`) ----------------------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()          # nvidia-smi samples every 100 ms; "under load" samples are selected by power draw
+    t_warm = time.perf_counter()
+    n_warm = 0
+    while n_warm < max(args.warmup, 3) or time.perf_counter() - t_warm < 0.5:   # >= W steps and >= 0.5 s under load
+        step_device()
+        n_warm += 1
+    barrier()
     lib.otn_profile_enable(handle.h, 1)
     launches0 = lib.otn_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -359,7 +362,7 @@ def run_gpu(args):
                "sample": f"{total} instances of the same workload ({total // cores} per process x {cores} processes, 1 BLAS thread each, "
                          f"{wall:.1f} s wall)"}
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(),
             "clocks": clocks,
@@ -376,7 +379,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libotn.so")
 MODEL_FULL, MODEL_LOCAL = 0, 1
 METRIC_EUCLIDEAN, METRIC_CANONICAL = 0, 1
 STATUS_NAN, STATUS_NOT_SPD, STATUS_NEG_DISCRIMINANT = 1, 2, 4
+FLAG_DENSE = 1
 
 _dp = C.c_void_p  # double* (host or device)
 _ip = C.c_void_p  # int*
@@ -36,6 +37,8 @@ SIGNATURES = {
     "otn_version": (C.c_int, []),
     "otn_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                              _dp, _dp, C.c_int]),
+    "otn_create_ex": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                _dp, _dp, C.c_int, C.c_int]),
     "otn_destroy": (None, [C.c_void_p]),
     "otn_set_target_index": (C.c_int, [C.c_void_p, _ip, C.c_int]),
     "otn_set_metric": (C.c_int, [C.c_void_p, C.c_int]),

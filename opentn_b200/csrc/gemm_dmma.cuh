@@ -31,7 +31,8 @@ struct GemmParams {
     const double* E;                         // EPI_RESID: targets (real part) ; EPI_DOT: residuals
     long long sE;                            // stride of E per instance (EPI_DOT) or per target (EPI_RESID)
     const int* e_index;                      // EPI_RESID: target id per instance (nullptr = 0)
-    double* partial;                         // [batch][tiles] partial sums
+    double* partial;                         // partial sums: partial[b * partial_stride + tile]
+    int partial_stride;                      // >= tiles of this launch (several launches may share one row per instance)
 };
 
 template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool TA, bool TB>
@@ -187,7 +188,7 @@ gemm_dmma_kernel(const GemmParams p) {
         if (tid == 0) {
             double s = 0.0;
             for (int w = 0; w < Cfg::THREADS / 32; ++w) s += red[w];
-            p.partial[(long long)b * tiles + tile] = s;
+            p.partial[(long long)b * p.partial_stride + tile] = s;
         }
     }
 }
@@ -264,14 +265,14 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p) {
         if (tid == 0) {
             double s = 0.0;
             for (int w = 0; w < 8; ++w) s += red[w];
-            p.partial[(long long)b * tiles + tile] = s;
+            p.partial[(long long)b * p.partial_stride + tile] = s;
         }
     }
 }
 
 // ---- host-side dispatch -------------------------------------------------------------------------------------------
 struct GemmPlan {
-    int kind;      // 0 = simt fallback, 1 = dmma 128x128, 2 = dmma 64x64
+    int kind;      // 0 = simt fallback, 1 = dmma 128x128, 2 = dmma 64x64, 3 = dmma 48x48
     int tiles;     // CTAs per instance (for the `partial` buffer)
 };
 
@@ -283,6 +284,8 @@ inline GemmPlan gemm_plan(int D, int rows, int batch) {
         pl.kind = 1; pl.tiles = (rows / 128) * (D / 128);
     } else if (D % 64 == 0 && rows % 64 == 0) {
         pl.kind = 2; pl.tiles = (rows / 64) * (D / 64);
+    } else if (D % 48 == 0 && rows % 48 == 0) {   // the 144 x 144 symmetric block of the structured evaluation
+        pl.kind = 3; pl.tiles = (rows / 48) * (D / 48);
     } else {
         pl.kind = 0; pl.tiles = ((rows + 31) / 32) * ((D + 31) / 32);
     }
@@ -308,6 +311,7 @@ inline cudaError_t gemm_launch_t(const GemmParams& p, cudaStream_t st) {
     GemmPlan pl = gemm_plan(p.D, p.rows, p.batch);
     if (pl.kind == 1) return launch_dmma<128, 128, 16, 64, 32, 3, TA, TB>(p, pl.tiles, st);
     if (pl.kind == 2) return launch_dmma<64, 64, 16, 32, 32, 3, TA, TB>(p, pl.tiles, st);
+    if (pl.kind == 3) return launch_dmma<48, 48, 16, 24, 24, 3, TA, TB>(p, pl.tiles, st);
     gemm_simt_kernel<TA, TB><<<(unsigned)((long long)p.batch * pl.tiles), 256, 0, st>>>(p);
     return cudaGetLastError();
 }

@@ -12,6 +12,7 @@
 #include "assemble.cuh"
 #include "gemm_dmma.cuh"
 #include "stiefel.cuh"
+#include "structured.cuh"
 #include "tr.cuh"
 
 using namespace otn;
@@ -181,7 +182,10 @@ struct otn_problem {
     int dim;        // isometry column count p (= d^N full, d^2 local)
     int n, p, np;   // isometry shape
     int D, q, nf;   // superoperator side; local superoperator side; kron factors
-    long long SZ;   // D*D
+    long long SZ;   // doubles per stored superoperator ("slot"): D*D dense, Ds*Ds + Da*Da in structured mode
+    bool structured = false;   // block-diagonal (swap-symmetric basis) evaluation, see structured.cuh
+    SymLayout sym{};
+    int nblk = 1; int blkD[2] = {0, 0}; long long blkOff[2] = {0, 0}; int blkTiles[2] = {0, 0}; int blkTileOff[2] = {0, 0};
     double alpha0, alpha1;
     cudaStream_t stream = nullptr;
     // constants
@@ -242,6 +246,11 @@ extern "C" void otn_destroy(otn_problem* h) {
 
 extern "C" int otn_create(otn_problem** out, int N, int d, int m, int K, int model, int metric, int max_batch, int n_targets,
                           const double* target_re, const double* target_im, int device) {
+    return otn_create_ex(out, N, d, m, K, model, metric, max_batch, n_targets, target_re, target_im, device, 0);
+}
+
+extern "C" int otn_create_ex(otn_problem** out, int N, int d, int m, int K, int model, int metric, int max_batch, int n_targets,
+                             const double* target_re, const double* target_im, int device, int flags) {
     if (out == nullptr) return fail("out is null");
     *out = nullptr;
     if (d < 2 || N < 1 || m < 1 || K < 1 || max_batch < 1 || n_targets < 1) return fail("bad size argument");
@@ -266,6 +275,23 @@ extern "C" int otn_create(otn_problem** out, int N, int d, int m, int K, int mod
     h->q = ipow(d, 4);
     h->nf = N / 2;
     h->dim = (model == OTN_MODEL_FULL) ? ipow(d, N) : d * d;
+    h->nblk = 1; h->blkD[0] = h->D; h->blkOff[0] = 0;
+    h->structured = (model == OTN_MODEL_FULL) && (h->dim == 16 || h->dim == 8) && !(flags & OTN_FLAG_DENSE);
+    if (h->structured) {
+        SymLayout& L = h->sym;
+        L.dim = h->dim; L.NS = h->dim * (h->dim + 1) / 2; L.NA = h->dim * (h->dim - 1) / 2;
+        auto pad = [](int n) { const int p48 = (n + 47) / 48 * 48, p64 = (n + 63) / 64 * 64; return p48 < p64 ? p48 : p64; };
+        L.Ds = pad(L.NS); L.Da = pad(L.NA);
+        L.off_a = (long long)L.Ds * L.Ds; L.slot = L.off_a + (long long)L.Da * L.Da;
+        h->SZ = L.slot;
+        h->nblk = 2; h->blkD[0] = L.Ds; h->blkD[1] = L.Da; h->blkOff[0] = 0; h->blkOff[1] = L.off_a;
+    }
+    h->tiles = 0;
+    for (int i = 0; i < h->nblk; ++i) {
+        h->blkTiles[i] = gemm_plan(h->blkD[i], h->blkD[i], 1).tiles;
+        h->blkTileOff[i] = h->tiles;
+        h->tiles += h->blkTiles[i];
+    }
     h->p = h->dim; h->n = h->dim * K; h->np = h->n * h->p;
     if (h->p > ST_MAXP) { delete h; return fail("isometry with p = %d columns > %d not supported", h->dim, ST_MAXP); }
     if (model == OTN_MODEL_LOCAL && (h->nf > 4 || h->q > 255)) { delete h; return fail("local model supports N <= 8 and d <= 3"); }
@@ -282,10 +308,11 @@ extern "C" int otn_create(otn_problem** out, int N, int d, int m, int K, int mod
     // Running the reverse chain on R' = M - Ts makes every cotangent W swap-symmetric, which halves the back-assembly traffic.
     CREATE_TRY(cudaMalloc(&h->T_re, n_targets * SZ * 8));
     {
-        std::vector<double> im2(n_targets, 0.0), tre(SZ), tsym(SZ), tmp(SZ);
+        const size_t DD = (size_t)h->D * h->D;
+        std::vector<double> im2(n_targets, 0.0), tre(DD), tsym(DD), tmp(DD), tblk(SZ);
         const int dm = ipow(d, N), Dn = h->D;
         for (int t = 0; t < n_targets; ++t) {
-            CREATE_TRY(cudaMemcpy(tre.data(), target_re + (size_t)t * SZ, SZ * 8, cudaMemcpyDefault));
+            CREATE_TRY(cudaMemcpy(tre.data(), target_re + (size_t)t * DD, DD * 8, cudaMemcpyDefault));
             double s = 0.0;
             for (int r = 0; r < Dn; ++r) {
                 const int rs = (r % dm) * dm + r / dm;
@@ -297,10 +324,27 @@ extern "C" int otn_create(otn_problem** out, int N, int d, int m, int K, int mod
                     s += a * a;
                 }
             }
-            CREATE_TRY(cudaMemcpy(h->T_re + (size_t)t * SZ, tsym.data(), SZ * 8, cudaMemcpyHostToDevice));
+            if (!h->structured) {
+                CREATE_TRY(cudaMemcpy(h->T_re + (size_t)t * SZ, tsym.data(), SZ * 8, cudaMemcpyHostToDevice));
+            } else {
+                // blocks of the symmetrised target: Ts[{ab},{cd}] = u^s_ab . T u^s_cd, Ta[{ab},{cd}] = u^a_ab . T u^a_cd
+                const SymLayout& L = h->sym;
+                std::fill(tblk.begin(), tblk.end(), 0.0);
+                auto at = [&](int a, int b, int c, int e) { return tsym[(size_t)(a * dm + b) * Dn + (c * dm + e)]; };
+                const double h2 = std::sqrt(0.5);
+                for (int a = 0; a < dm; ++a) for (int b = a; b < dm; ++b)
+                    for (int c = 0; c < dm; ++c) for (int e = c; e < dm; ++e) {
+                        // tsym is swap symmetric: T[(b,a),(e,c)] = T[(a,b),(c,e)]
+                        const double na = (a == b) ? h2 : 1.0, nc = (c == e) ? h2 : 1.0;
+                        tblk[(size_t)pair_s(a, b, dm) * L.Ds + pair_s(c, e, dm)] = na * nc * (at(a, b, c, e) + at(a, b, e, c));
+                        if (a < b && c < e)
+                            tblk[L.off_a + (size_t)pair_a(a, b, dm) * L.Da + pair_a(c, e, dm)] = at(a, b, c, e) - at(a, b, e, c);
+                    }
+                CREATE_TRY(cudaMemcpy(h->T_re + (size_t)t * SZ, tblk.data(), SZ * 8, cudaMemcpyHostToDevice));
+            }
             if (target_im != nullptr) {
-                CREATE_TRY(cudaMemcpy(tmp.data(), target_im + (size_t)t * SZ, SZ * 8, cudaMemcpyDefault));
-                for (size_t i = 0; i < SZ; ++i) s += tmp[i] * tmp[i];
+                CREATE_TRY(cudaMemcpy(tmp.data(), target_im + (size_t)t * DD, DD * 8, cudaMemcpyDefault));
+                for (size_t i = 0; i < DD; ++i) s += tmp[i] * tmp[i];
             }
             im2[t] = s;
         }
@@ -322,15 +366,14 @@ extern "C" int otn_create(otn_problem** out, int N, int d, int m, int K, int mod
         CREATE_TRY(cudaMalloc(&h->Wl, B * M * h->nf * q2 * 8));
         CREATE_TRY(cudaMalloc(&h->Wld, B * M * h->nf * q2 * 8));
     }
-    for (double** ptr : {&h->Y, &h->P, &h->G, &h->W, &h->Yd, &h->Pd}) CREATE_TRY(cudaMalloc(ptr, B * M * SZ * 8));
+    for (double** ptr : {&h->Y, &h->P, &h->G, &h->W, &h->Yd, &h->Pd}) {
+        CREATE_TRY(cudaMalloc(ptr, B * M * SZ * 8));
+        if (h->structured) CREATE_TRY(cudaMemset(*ptr, 0, B * M * SZ * 8));   // zero padding of the blocks is an invariant
+    }
     CREATE_TRY(cudaMalloc(&h->Gd, B * 2 * SZ * 8));
     CREATE_TRY(cudaMalloc(&h->Wd, B * SZ * 8));
+    if (h->structured) { CREATE_TRY(cudaMemset(h->Gd, 0, B * 2 * SZ * 8)); CREATE_TRY(cudaMemset(h->Wd, 0, B * SZ * 8)); }
     for (double** ptr : {&h->x, &h->eta, &h->zraw, &h->zdraw}) CREATE_TRY(cudaMalloc(ptr, B * M * h->np * 8));
-    h->tiles = gemm_plan(h->D, h->D, max_batch).tiles;
-    {   // the plan (hence the tile count) may differ for smaller batches: size for the worst case
-        int t1 = gemm_plan(h->D, h->D, 1).tiles;
-        h->tiles = std::max(h->tiles, t1);
-    }
     CREATE_TRY(cudaMalloc(&h->part_f, B * h->tiles * 8));
     CREATE_TRY(cudaMalloc(&h->part_s, B * h->tiles * 8));
 #undef CREATE_TRY
@@ -405,9 +448,20 @@ extern "C" int otn_profile_read(otn_problem* h, double* ms, long long* launches,
 // ---------------------------------------------------------------------------------------------------------------------
 // pipeline pieces (all enqueue on h->stream; x / eta are device pointers [batch][m][np])
 // ---------------------------------------------------------------------------------------------------------------------
-static cudaError_t hgemm(otn_problem* h, const GemmParams& p, bool ta, bool tb) {
-    ProfScope ps(&h->prof, h->stream, CAT_GEMM, 2.0 * p.D * (double)p.rows * p.D * p.batch * (p.A2 ? 2 : 1));
-    return gemm_launch(p, ta, tb, h->stream);
+// one chain product = one launch per diagonal block (1 block in the dense formulation, 2 in the structured one)
+static cudaError_t hgemm(otn_problem* h, const GemmParams& p0, bool ta, bool tb) {
+    for (int i = 0; i < h->nblk; ++i) {
+        GemmParams p = p0;
+        const long long o = h->blkOff[i];
+        p.D = h->blkD[i]; p.row0 = 0; p.rows = h->blkD[i];
+        p.A1 += o; p.B1 += o; p.C += o;
+        if (p.A2) { p.A2 += o; p.B2 += o; }
+        if (p.epi != EPI_NONE) { p.E += o; p.partial += h->blkTileOff[i]; p.partial_stride = h->tiles; }
+        ProfScope ps(&h->prof, h->stream, CAT_GEMM, 2.0 * p.D * (double)p.rows * p.D * p.batch * (p.A2 ? 2 : 1));
+        cudaError_t e = gemm_launch(p, ta, tb, h->stream);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 static GemmParams gp(const otn_problem* h, int batch, const int* active) {
     GemmParams p{};
@@ -427,7 +481,18 @@ static int build_layers(otn_problem* h, const double* x, const double* eta, int 
     double* Ydout = (h->model == OTN_MODEL_FULL) ? h->Yd : h->Yld;
     const long long ostride = (h->model == OTN_MODEL_FULL) ? h->SZ : (long long)h->q * h->q;
     dim3 grid(h->dim, items);
-    if (h->dim == 16 || h->dim == 8) {
+    if (h->structured) {
+        const int Kp = (h->K + 3) & ~3;
+        const size_t sm = ((size_t)h->dim * Kp * (h->dim + 4) * (tangent ? 2 : 1) + (size_t)8 * 2 * h->dim * (h->dim + 1)) * 8;
+#define ASM_SYM(DIMV, TG, PR)                                                                                        \
+    do {                                                                                                             \
+        OTN_TRY(set_smem(assemble_sym_kernel<DIMV, TG, PR>, sm));                                                    \
+        assemble_sym_kernel<DIMV, TG, PR><<<items, 256, sm, h->stream>>>(x, eta, h->Y, h->Yd, h->sym, h->K, active, h->m); \
+    } while (0)
+        if (h->dim == 16) { if (tangent && primal) ASM_SYM(16, true, true); else if (tangent) ASM_SYM(16, true, false); else ASM_SYM(16, false, true); }
+        else { if (tangent && primal) ASM_SYM(8, true, true); else if (tangent) ASM_SYM(8, true, false); else ASM_SYM(8, false, true); }
+#undef ASM_SYM
+    } else if (h->dim == 16 || h->dim == 8) {
         const int Kp = (h->K + 3) & ~3;
         const size_t sm = (size_t)h->dim * Kp * (h->dim + 4) * 8 * (tangent ? 2 : 1);
 #define ASM_MMA(DIMV, TG, PR)                                                                                              \
@@ -488,13 +553,14 @@ __global__ void resid_kernel(const double* __restrict__ Y, long long sY, const d
     }
 }
 
-// forward chain: P_l = Y_l P_{l-1}; the last product writes the residual R = M - Re T into G[m-1] (or M itself into Mout)
-static int forward_chain(otn_problem* h, int batch, const int* active, double* Mout, int* tiles_used) {
+// forward chain: P_l = Y_l P_{l-1}; the last product writes the residual R = M - Ts into G[m-1] (cost / gradient paths) or the
+// model matrix M into P[m-1] (`model_only`, for otn_model)
+static int forward_chain(otn_problem* h, int batch, const int* active, bool model_only, int* tiles_used) {
     const long long SZ = h->SZ, S = (long long)h->m * SZ;
     const int m = h->m;
-    *tiles_used = gemm_plan(h->D, h->D, batch).tiles;
+    *tiles_used = h->tiles;
     if (m == 1) {
-        if (Mout) { CUDA_TRY(cudaMemcpyAsync(Mout, h->Y, (size_t)batch * SZ * 8, cudaMemcpyDeviceToDevice, h->stream)); return 0; }
+        if (model_only) return 0;   // M = Y_0
         ProfScope ps(&h->prof, h->stream, CAT_OTHER, 0.0);
         resid_kernel<<<batch, 256, 0, h->stream>>>(h->Y, S, h->T_re, SZ, h->tindex, h->G, S, nullptr, 0, h->part_f, SZ, active);
         *tiles_used = 1;
@@ -505,13 +571,27 @@ static int forward_chain(otn_problem* h, int batch, const int* active, double* M
         GemmParams p = gp(h, batch, active);
         p.A1 = layer_ptr(h->Y, l, SZ); p.sA1 = S;
         p.B1 = (l == 1) ? h->Y : layer_ptr(h->P, l - 1, SZ); p.sB1 = S;
-        if (l < m - 1) { p.C = layer_ptr(h->P, l, SZ); p.sC = S; }
-        else if (Mout) { p.C = Mout; p.sC = SZ; }
+        if (l < m - 1 || model_only) { p.C = layer_ptr(h->P, l, SZ); p.sC = S; }
         else {
             p.C = layer_ptr(h->G, m - 1, SZ); p.sC = S;
-            p.epi = EPI_RESID; p.E = h->T_re; p.sE = SZ; p.e_index = h->tindex; p.partial = h->part_f;
+            p.epi = EPI_RESID; p.E = h->T_re; p.sE = SZ; p.e_index = h->tindex; p.partial = h->part_f; p.partial_stride = h->tiles;
         }
         CUDA_TRY(hgemm(h, p, false, false));
+    }
+    return 0;
+}
+
+// copy the model matrix of every instance (P[m-1], or Y[0] when m == 1) to a dense [batch][D][D] array
+static int export_model(otn_problem* h, int batch, double* Mout) {
+    const long long SZ = h->SZ, S = (long long)h->m * SZ;
+    const double* src = (h->m == 1) ? h->Y : layer_ptr(h->P, h->m - 1, SZ);
+    ProfScope ps(&h->prof, h->stream, CAT_OTHER, 0.0);
+    if (h->structured) {
+        unblock_kernel<<<148 * 8, 256, 0, h->stream>>>(src, S, Mout, h->sym, batch);
+        CUDA_TRY(cudaGetLastError());
+    } else {
+        const size_t DD = (size_t)h->D * h->D * 8;
+        CUDA_TRY(cudaMemcpy2DAsync(Mout, DD, src, (size_t)S * 8, DD, batch, cudaMemcpyDeviceToDevice, h->stream));
     }
     return 0;
 }
@@ -540,7 +620,21 @@ static int back_layer(otn_problem* h, int batch, const int* active, int l, const
     }
     const int dim = h->dim;
     dim3 grid(dim, batch);
-    if (dim == 16 || dim == 8) {
+    if (h->structured) {
+#define BAS_SYM(DIMV, ASV)                                                                                                       \
+    do {                                                                                                                         \
+        const size_t sm = BasSymCfg<DIMV, ASV>::smem_bytes(h->K);                                                                \
+        OTN_TRY(set_smem(back_assemble_sym_kernel<DIMV, ASV>, sm));                                                              \
+        if (!tangent) {                                                                                                          \
+            back_assemble_sym_kernel<DIMV, ASV><<<batch * ASV, 256, sm, h->stream>>>(Wsup, sW, x, h->zraw, h->sym, h->K, 0, active, h->m, l);   \
+        } else {                                                                                                                 \
+            back_assemble_sym_kernel<DIMV, ASV><<<batch * ASV, 256, sm, h->stream>>>(Wdsup, sWds, x, h->zdraw, h->sym, h->K, 0, active, h->m, l); \
+            back_assemble_sym_kernel<DIMV, ASV><<<batch * ASV, 256, sm, h->stream>>>(Wsup, sW, eta, h->zdraw, h->sym, h->K, 1, active, h->m, l);  \
+        }                                                                                                                        \
+    } while (0)
+        if (dim == 16) BAS_SYM(16, 2); else BAS_SYM(8, 1);
+#undef BAS_SYM
+    } else if (dim == 16 || dim == 8) {
         // streaming kernel, one CTA per instance; tangent = Wd*x then += W*eta
 #define BAS_STREAM(DIMV)                                                                                                        \
     do {                                                                                                                        \
@@ -612,7 +706,7 @@ static int tangent_pass(otn_problem* h, int batch, const int* active, const doub
         if (l < m - 1) { p.C = layer_ptr(h->Pd, l, SZ); p.sC = S; }
         else {
             p.C = h->Gd; p.sC = 2 * SZ;
-            p.epi = EPI_DOT; p.E = layer_ptr(h->G, m - 1, SZ); p.sE = S; p.partial = h->part_s;
+            p.epi = EPI_DOT; p.E = layer_ptr(h->G, m - 1, SZ); p.sE = S; p.partial = h->part_s; p.partial_stride = h->tiles;
         }
         CUDA_TRY(hgemm(h, p, false, false));
     }
@@ -674,7 +768,7 @@ static int riem_launch(otn_problem* h, int batch, const int* active, int tiles, 
 int otn_dev_cost(otn_problem* h, const double* x, int batch, const int* active, double* f) {
     int tiles;
     OTN_TRY(build_layers(h, x, nullptr, batch, active, true));
-    OTN_TRY(forward_chain(h, batch, active, nullptr, &tiles));
+    OTN_TRY(forward_chain(h, batch, active, false, &tiles));
     ProfScope ps(&h->prof, h->stream, CAT_OTHER, 0.0);
     cost_from_partials_kernel<<<(batch + 127) / 128, 128, 0, h->stream>>>(h->part_f, tiles, h->im2, h->tindex, f, batch, active);
     CUDA_TRY(cudaGetLastError());
@@ -684,7 +778,7 @@ int otn_dev_cost(otn_problem* h, const double* x, int batch, const int* active, 
 int otn_dev_cost_grad(otn_problem* h, const double* x, int batch, const int* active, double* f, double* rgrad, double* egrad) {
     int tiles;
     OTN_TRY(build_layers(h, x, nullptr, batch, active, true));
-    OTN_TRY(forward_chain(h, batch, active, nullptr, &tiles));
+    OTN_TRY(forward_chain(h, batch, active, false, &tiles));
     OTN_TRY(reverse_chain(h, batch, active, x));
     OTN_TRY(riem_launch(h, batch, active, tiles, x, nullptr, false, f, rgrad, egrad, nullptr));
     h->tr.tiles = tiles;
@@ -713,10 +807,12 @@ extern "C" int otn_model(otn_problem* h, const double* x, int batch, double* M) 
     if (!x || !M) return fail("null argument");
     const void* xd; void* Md; int tiles;
     OTN_TRY(stage_in(x, xbytes(h, batch), h->in_x, h->stream, &xd));
-    OTN_TRY(stage_out(M, (size_t)batch * h->SZ * 8, h->out_M, &Md));
+    const size_t mbytes = (size_t)batch * h->D * h->D * 8;
+    OTN_TRY(stage_out(M, mbytes, h->out_M, &Md));
     OTN_TRY(build_layers(h, (const double*)xd, nullptr, batch, nullptr, true));
-    OTN_TRY(forward_chain(h, batch, nullptr, (double*)Md, &tiles));
-    OTN_TRY(finish_out(M, Md, (size_t)batch * h->SZ * 8, h->stream));
+    OTN_TRY(forward_chain(h, batch, nullptr, true, &tiles));
+    OTN_TRY(export_model(h, batch, (double*)Md));
+    OTN_TRY(finish_out(M, Md, mbytes, h->stream));
     h->cached_batch = 0;
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return 0;
@@ -757,7 +853,7 @@ static int triple_device(otn_problem* h, const double* x, const double* eta, int
     int tiles;
     // primal + tangent layers in one assembly pass, then forward / reverse / tangent chains
     OTN_TRY(build_layers(h, x, eta, batch, nullptr, true));
-    OTN_TRY(forward_chain(h, batch, nullptr, nullptr, &tiles));
+    OTN_TRY(forward_chain(h, batch, nullptr, false, &tiles));
     h->tr.tiles = tiles;
     OTN_TRY(reverse_chain(h, batch, nullptr, x));
     OTN_TRY(tangent_pass(h, batch, nullptr, x, eta, true));
@@ -973,7 +1069,7 @@ extern "C" int otn_retract(const double* x, const double* eta, int count, int n,
     OTN_TRY(stage_out(out, count * np * 8, S.o, &od));
     OTN_TRY(stage_out(status, (size_t)count * 4, S.s, &sd));
     if (sd) CUDA_TRY(cudaMemset(sd, 0, (size_t)count * 4));
-    const size_t sm = (np + 3 * (size_t)p * p) * 8;
+    const size_t sm = (np + 5 * (size_t)p * p) * 8;
     OTN_TRY(set_smem(retract_kernel, sm));
     retract_kernel<<<count, ST_THREADS, sm>>>((const double*)xd, (const double*)ed, (double*)od, n, p, 1, nullptr, (int*)sd);
     CUDA_TRY(cudaGetLastError());

@@ -227,7 +227,7 @@ __device__ inline void jacobi_eig_warp(double* S, double* V, int p, double* cs /
         double dg = 0.0;
         for (int i = lane; i < p; i += 32) dg += S[i * p + i] * S[i * p + i];
         dg = warp_sum(dg);
-        if (off <= 1e-34 * dg) break;
+        if (off <= 1e-29 * dg) break;   // off-diagonal norm below ~3e-15 relative: converged to rounding
         for (int step = 0; step < pe - 1; ++step) {
             // round-robin tournament: player pe-1 fixed, others rotate
             if (lane < half) {
@@ -272,7 +272,77 @@ __device__ inline void jacobi_eig_warp(double* S, double* V, int p, double* cs /
     }
 }
 
-// retract: out = A (A^T A)^{-1/2},  A = X + eta.   status[item] = 1 if A^T A is not positive definite.
+// Q = G^{-1/2} for a p x p SPD matrix G (dense, row-major), all ST_THREADS threads.
+//   * ||G - I||_F < 0.5 (every trust-region step: G = I + eta^T eta with ||eta|| <= radius <= 0.1): coupled Newton-Schulz
+//     iteration  T = (3I - Z Y)/2, Y <- Y T, Z <- T Z  (Y -> G^{1/2}, Z -> G^{-1/2}), quadratically convergent, p x p products only;
+//   * otherwise: symmetric eigendecomposition by the one-warp Jacobi solver above.
+// Work arrays Y, Z, T: p*p doubles each.  Returns (in every thread) 0 = ok, 2 = G not positive definite.
+__device__ inline int inv_sqrt_spd(const double* G, double* Q, double* Y, double* Z, double* T, int p, double* cs, int* pairs,
+                                   double* red /* >= 9 doubles */) {
+    const int pp = p * p;
+    double dev = 0.0;
+    for (int o = threadIdx.x; o < pp; o += ST_THREADS) { const double e = G[o] - ((o / p == o % p) ? 1.0 : 0.0); dev = fma(e, e, dev); }
+    dev = warp_sum(dev);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dev;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0.0; for (int w = 0; w < ST_THREADS / 32; ++w) t += red[w]; red[8] = t; }
+    __syncthreads();
+    const bool newton = red[8] < 0.25;
+    __syncthreads();
+    if (newton) {
+        for (int o = threadIdx.x; o < pp; o += ST_THREADS) { Y[o] = G[o]; Z[o] = (o / p == o % p) ? 1.0 : 0.0; }
+        __syncthreads();
+        for (int it = 0; it < 30; ++it) {
+            double err = 0.0;
+            for (int o = threadIdx.x; o < pp; o += ST_THREADS) {          // T = (3I - Z Y)/2 ; err = ||I - Z Y||_F^2
+                const int i = o / p, j = o - i * p;
+                double zy = 0.0;
+                for (int k = 0; k < p; ++k) zy = fma(Z[i * p + k], Y[k * p + j], zy);
+                const double id = (i == j) ? 1.0 : 0.0;
+                T[o] = 0.5 * (3.0 * id - zy);
+                err = fma(id - zy, id - zy, err);
+            }
+            err = warp_sum(err);
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = err;
+            __syncthreads();
+            double tot = 0.0;
+            for (int w = 0; w < ST_THREADS / 32; ++w) tot += red[w];
+            if (tot < 1e-30) break;                                        // uniform: every thread sees the same sum
+            double yn[4], zn[4];                                           // pp <= 4 * ST_THREADS is not needed: pp <= 256
+            int cnt = 0;
+            for (int o = threadIdx.x; o < pp; o += ST_THREADS, ++cnt) {
+                const int i = o / p, j = o - i * p;
+                double a = 0.0, b = 0.0;
+                for (int k = 0; k < p; ++k) { a = fma(Y[i * p + k], T[k * p + j], a); b = fma(T[i * p + k], Z[k * p + j], b); }
+                yn[cnt] = a; zn[cnt] = b;
+            }
+            __syncthreads();
+            cnt = 0;
+            for (int o = threadIdx.x; o < pp; o += ST_THREADS, ++cnt) { Y[o] = yn[cnt]; Z[o] = zn[cnt]; }
+            __syncthreads();
+        }
+        __syncthreads();
+        for (int o = threadIdx.x; o < pp; o += ST_THREADS) Q[o] = 0.5 * (Z[o] + Z[(o % p) * p + o / p]);   // symmetrise
+        __syncthreads();
+        return 0;
+    }
+    for (int o = threadIdx.x; o < pp; o += ST_THREADS) Y[o] = G[o];
+    __syncthreads();
+    if (threadIdx.x < 32) jacobi_eig_warp(Y, Z, p, cs, pairs);
+    __syncthreads();
+    for (int o = threadIdx.x; o < pp; o += ST_THREADS) {
+        const int i = o / p, j = o - i * p;
+        double acc = 0.0;
+        for (int k = 0; k < p; ++k) acc += Z[i * p + k] * Z[j * p + k] / sqrt(Y[k * p + k]);
+        Q[o] = acc;
+    }
+    int bad = 0;
+    for (int k = 0; k < p; ++k) if (!(Y[k * p + k] > 0.0)) bad = 2;
+    __syncthreads();
+    return bad;
+}
+
+// retract: out = A (A^T A)^{-1/2},  A = X + eta.   status bit 2 if A^T A is not positive definite.
 __global__ void __launch_bounds__(ST_THREADS) retract_kernel(const double* __restrict__ x, const double* __restrict__ eta,
                                                              double* __restrict__ out, int n, int p, int m, const int* active,
                                                              int* status) {
@@ -284,27 +354,18 @@ __global__ void __launch_bounds__(ST_THREADS) retract_kernel(const double* __res
     double* S = A + np;
     double* V = S + pp;
     double* Q = V + pp;
+    double* Yw = Q + pp;
+    double* Tw = Yw + pp;
     __shared__ double cs[2 * ST_MAXP];
     __shared__ int pairs[2 * ST_MAXP];
+    __shared__ double red[9];
     const long long base = (long long)item * np;
     for (int i = threadIdx.x; i < np; i += ST_THREADS) A[i] = x[base + i] + (eta ? eta[base + i] : 0.0);
     __syncthreads();
     gram(A, A, S, n, p);
     __syncthreads();
-    if (threadIdx.x < 32) jacobi_eig_warp(S, V, p, cs, pairs);
-    __syncthreads();
-    // Q = V diag(lambda^{-1/2}) V^T
-    for (int o = threadIdx.x; o < pp; o += ST_THREADS) {
-        const int i = o / p, j = o - i * p;
-        double s = 0.0;
-        for (int k = 0; k < p; ++k) s += V[i * p + k] * V[j * p + k] / sqrt(S[k * p + k]);
-        Q[o] = s;
-    }
-    if (threadIdx.x == 0 && status != nullptr) {
-        int bad = 0;
-        for (int k = 0; k < p; ++k) if (!(S[k * p + k] > 0.0)) bad = 1;
-        if (bad) atomicOr(&status[item / m], 2);
-    }
+    const int bad = inv_sqrt_spd(S, Q, Yw, V, Tw, p, cs, pairs, red);
+    if (threadIdx.x == 0 && status != nullptr && bad) atomicOr(&status[item / m], bad);
     __syncthreads();
     for (int o = threadIdx.x; o < np; o += ST_THREADS) {
         const int r = o / p, j = o - r * p;
@@ -536,6 +597,102 @@ __global__ void __launch_bounds__(ST_THREADS) riem_mma_kernel(const RiemParams P
     }
     __syncthreads();
     for (int i = threadIdx.x; i < np; i += ST_THREADS) Pm.heta[base + i] = Zd[(i / P) * LD + (i % P)];
+}
+
+}  // namespace otn
+
+
+// ==================================================================================================================
+// DMMA-Gram versions of the canonical dot product and of the polar retraction for p in {8, 16} (padded rows, LD = p + 4)
+// ==================================================================================================================
+namespace otn {
+
+template <int P>
+__global__ void __launch_bounds__(ST_THREADS) cdot_mma_kernel(const double* __restrict__ x, const double* __restrict__ a,
+                                                              const double* __restrict__ bb, double* __restrict__ out, int n, int m,
+                                                              const int* active) {
+    extern __shared__ __align__(16) double sm[];
+    constexpr int LD = P + 4;
+    const int inst = blockIdx.x;
+    if (active != nullptr && active[inst] == 0) return;
+    const int np = n * P, nl = n * LD;
+    double* X = sm;
+    double* A = X + nl;
+    double* B = A + nl;
+    double* GA = B + nl;
+    double* GB = GA + P * LD;
+    __shared__ double red[ST_THREADS / 32];
+    double total = 0.0;
+    for (int l = 0; l < m; ++l) {
+        const long long base = ((long long)inst * m + l) * np;
+        double s = 0.0;
+        for (int i = threadIdx.x; i < np; i += ST_THREADS) {
+            const int o = (i / P) * LD + (i % P);
+            const double av = a[base + i], bv = bb[base + i];
+            X[o] = x[base + i]; A[o] = av; B[o] = bv;
+            s = fma(av, bv, s);
+        }
+        __syncthreads();
+        {
+            const double* const As[2] = {X, X}; const double* const Bs[2] = {A, B}; double* const Gs[2] = {GA, GB};
+            gram_blocks_mma<P, 2>(As, Bs, Gs, n);
+        }
+        __syncthreads();
+        for (int oo = threadIdx.x; oo < P * P; oo += ST_THREADS) { const int o = (oo / P) * LD + (oo % P); s = fma(-0.5 * GA[o], GB[o], s); }
+        s = warp_sum(s);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int w = 0; w < ST_THREADS / 32; ++w) total += red[w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[inst] = total;
+}
+
+template <int P>
+__global__ void __launch_bounds__(ST_THREADS) retract_mma_kernel(const double* __restrict__ x, const double* __restrict__ eta,
+                                                                 double* __restrict__ out, int n, int m, const int* active, int* status) {
+    extern __shared__ __align__(16) double sm[];
+    constexpr int LD = P + 4;
+    const int item = blockIdx.x;
+    if (active != nullptr && active[item / m] == 0) return;
+    const int np = n * P, nl = n * LD;
+    double* A = sm;              // padded
+    double* O = A + nl;          // padded output
+    double* Gp = O + nl;         // padded Gram
+    double* Q = Gp + P * LD;     // padded inverse square root
+    double* S = Q + P * LD;      // dense p x p work arrays
+    double* V = S + P * P;
+    double* Qd = V + P * P;
+    double* Yw = Qd + P * P;
+    double* Tw = Yw + P * P;
+    __shared__ double cs[2 * ST_MAXP];
+    __shared__ int pairs[2 * ST_MAXP];
+    __shared__ double red[9];
+    const long long base = (long long)item * np;
+    for (int i = threadIdx.x; i < np; i += ST_THREADS) {
+        const int o = (i / P) * LD + (i % P);
+        A[o] = x[base + i] + (eta ? eta[base + i] : 0.0);
+        O[o] = 0.0;
+    }
+    __syncthreads();
+    {
+        const double* const As[1] = {A}; const double* const Bs[1] = {A}; double* const Gs[1] = {Gp};
+        gram_blocks_mma<P, 1>(As, Bs, Gs, n);
+    }
+    __syncthreads();
+    for (int oo = threadIdx.x; oo < P * P; oo += ST_THREADS) S[oo] = Gp[(oo / P) * LD + (oo % P)];
+    __syncthreads();
+    const int bad = inv_sqrt_spd(S, Qd, Yw, V, Tw, P, cs, pairs, red);
+    if (threadIdx.x == 0 && status != nullptr && bad) atomicOr(&status[item / m], bad);
+    for (int oo = threadIdx.x; oo < P * P; oo += ST_THREADS) Q[(oo / P) * LD + (oo % P)] = Qd[oo];
+    __syncthreads();
+    {
+        const double* const As[1] = {A}; const double* const Gs[1] = {Q}; const bool GT[1] = {false};
+        addmul_mma<P, 1>(O, 0.0, As, Gs, GT, n);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < np; i += ST_THREADS) out[base + i] = O[(i / P) * LD + (i % P)];
 }
 
 }  // namespace otn

@@ -1,0 +1,255 @@
+// Structured (block-diagonal) evaluation of the full-sites model.
+//
+// Every layer superoperator Y = sum_k E_k (x) E_k commutes with the swap S:(a,b)<->(b,a) of the doubled index, hence so do all
+// chain products, tangents and (after symmetrising the target, see otn_create) all cotangents.  In the orthonormal basis
+//     u^s_{ab} = (e_ab + e_ba)/sqrt2 (a<b),  u^s_{aa} = e_aa          (NS = dim(dim+1)/2 vectors, 136 at dim = 16)
+//     u^a_{ab} = (e_ab - e_ba)/sqrt2 (a<b)                            (NA = dim(dim-1)/2 vectors, 120 at dim = 16)
+// such matrices are block diagonal, Y = Ys (+) Ya with
+//     Ys[{ab},{cd}] = n_ab n_cd sum_k (x_ac x_bd + x_ad x_bc)   (symmetric square of E_k;  n_ab = 1, n_aa = 1/sqrt2)
+//     Ya[{ab},{cd}] =           sum_k (x_ac x_bd - x_ad x_bc)   (exterior square of E_k)
+// so every D^3 product of the dense formulation (transformations.py:841-851) becomes one NS^3 and one NA^3 product:
+// 2(136^3 + 120^3) = 8.5 MFLOP instead of 33.6 MFLOP (3.95x fewer), still on the FP64 tensor pipe.  Blocks are stored
+// zero-padded to the GEMM tile (144 and 128), which keeps the padding exactly zero through every product.
+// The same change of basis applied to the adjoint of the assembly gives (derivation in DESIGN.md section 3):
+//     Z[(a,k),c] = sum_{b,d} ( nu_ab nu_cd Ws[{ab},{cd}] + sg_ab sg_cd Wa[{ab},{cd}] ) x[(b,k),d]
+// with nu_ab = sqrt2 if a == b else 1, sg_ab = +1 (a<b), -1 (a>b), 0 (a == b).
+#pragma once
+#include "otn_common.cuh"
+
+namespace otn {
+
+struct SymLayout {
+    int dim, NS, NA;        // pair counts
+    int Ds, Da;             // padded block sides (leading dimensions)
+    long long off_a;        // offset of the antisymmetric block inside a slot (= Ds*Ds)
+    long long slot;         // Ds*Ds + Da*Da
+};
+
+__host__ __device__ __forceinline__ int pair_s(int a, int b, int dim) { return a * dim - a * (a - 1) / 2 + (b - a); }       // a <= b
+__host__ __device__ __forceinline__ int pair_a(int a, int b, int dim) { return a * dim - a * (a + 1) / 2 + (b - a - 1); }   // a <  b
+
+// ---- assembly into blocks: one CTA per item, the NS unordered pairs {a,b} are dealt to the 8 warps ------------------
+template <int DIM, bool TANGENT, bool PRIMAL>
+__global__ void __launch_bounds__(256) assemble_sym_kernel(const double* __restrict__ x, const double* __restrict__ eta,
+                                                           double* __restrict__ Y, double* __restrict__ Yd, SymLayout L, int K,
+                                                           const int* active, int m) {
+    extern __shared__ __align__(16) double sm[];
+    constexpr int LD = DIM + 4, MI = DIM / 8, LS = DIM + 1, NS = DIM * (DIM + 1) / 2;
+    const int item = blockIdx.x;
+    if (active != nullptr && active[item / m] == 0) return;
+    const int Kp = (K + 3) & ~3, rows = DIM * Kp;
+    double* xs = sm;
+    double* es = xs + rows * LD;
+    double* scr = es + (TANGENT ? rows * LD : 0);        // [8 warps][2][DIM*LS]
+    __shared__ unsigned char pc[NS], pd[NS];
+    const long long np = (long long)DIM * K * DIM;
+    for (int i = threadIdx.x; i < rows * DIM; i += 256) {
+        const int r = i / DIM, c = i - r * DIM, aa = r / Kp, k = r - aa * Kp;
+        const bool ok = k < K;
+        xs[r * LD + c] = ok ? x[(long long)item * np + (aa * K + k) * DIM + c] : 0.0;
+        if (TANGENT) es[r * LD + c] = ok ? eta[(long long)item * np + (aa * K + k) * DIM + c] : 0.0;
+    }
+    for (int i = threadIdx.x; i < DIM * DIM; i += 256) {
+        const int c = i / DIM, dd = i - c * DIM;
+        if (c <= dd) { pc[pair_s(c, dd, DIM)] = (unsigned char)c; pd[pair_s(c, dd, DIM)] = (unsigned char)dd; }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    double* Bp = scr + warp * 2 * DIM * LS;
+    double* Bt = Bp + DIM * LS;
+    double* Ys = Y + (long long)item * L.slot;
+    double* Ya = Ys + L.off_a;
+    double* Yds = Yd + (long long)item * L.slot;
+    double* Yda = Yds + L.off_a;
+    const double rs2 = 0.70710678118654752440;
+    for (int pid = warp; pid < NS; pid += 8) {
+        int a = 0, rem = pid;
+        while (rem >= DIM - a) { rem -= DIM - a; ++a; }
+        const int b = a + rem;
+        double acc[MI][MI][2], accd[MI][MI][2];
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < MI; ++j) { acc[i][j][0] = acc[i][j][1] = 0.0; accd[i][j][0] = accd[i][j][1] = 0.0; }
+        for (int kk = 0; kk < Kp; kk += 4) {
+            double xa[MI], xb[MI], ea[MI], eb[MI];
+#pragma unroll
+            for (int i = 0; i < MI; ++i) {
+                xa[i] = xs[(a * Kp + kk + t) * LD + i * 8 + g];
+                xb[i] = xs[(b * Kp + kk + t) * LD + i * 8 + g];
+                if (TANGENT) { ea[i] = es[(a * Kp + kk + t) * LD + i * 8 + g]; eb[i] = es[(b * Kp + kk + t) * LD + i * 8 + g]; }
+            }
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < MI; ++j) {
+                    if (PRIMAL) dmma884(acc[i][j][0], acc[i][j][1], xa[i], xb[j]);
+                    if (TANGENT) { dmma884(accd[i][j][0], accd[i][j][1], ea[i], xb[j]); dmma884(accd[i][j][0], accd[i][j][1], xa[i], eb[j]); }
+                }
+        }
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < MI; ++j) {
+                const int o = (i * 8 + g) * LS + j * 8 + 2 * t;
+                if (PRIMAL) { Bp[o] = acc[i][j][0]; Bp[o + 1] = acc[i][j][1]; }
+                if (TANGENT) { Bt[o] = accd[i][j][0]; Bt[o + 1] = accd[i][j][1]; }
+            }
+        __syncwarp();
+        const double nab = (a == b) ? rs2 : 1.0;
+        const long long rs = (long long)pair_s(a, b, DIM) * L.Ds;
+        const long long ra = (a < b) ? (long long)pair_a(a, b, DIM) * L.Da : 0;
+        for (int ci = lane; ci < NS; ci += 32) {
+            const int c = pc[ci], dd = pd[ci];
+            const double w = nab * ((c == dd) ? rs2 : 1.0);
+            if (PRIMAL) {
+                const double u = Bp[c * LS + dd], v = Bp[dd * LS + c];
+                Ys[rs + ci] = w * (u + v);
+                if (a < b && c < dd) Ya[ra + pair_a(c, dd, DIM)] = u - v;
+            }
+            if (TANGENT) {
+                const double u = Bt[c * LS + dd], v = Bt[dd * LS + c];
+                Yds[rs + ci] = w * (u + v);
+                if (a < b && c < dd) Yda[ra + pair_a(c, dd, DIM)] = u - v;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- adjoint of the assembly from cotangent blocks --------------------------------------------------------------------
+// AS CTAs per instance, each owning DIM/AS values of the output index a (so that 2 CTAs fit one SM: the first version with one
+// CTA per instance ran at 12 % warp occupancy and was latency bound); every CTA streams the rows {(a,b)}_a of Ws and Wa for
+// b = 0..DIM-1 through a 3-stage cp.async ring, expands them to the dense tile [a][c][d] in shared memory and feeds DMMA.
+template <int DIM, int AS>
+struct BasSymCfg {
+    static constexpr int LD = DIM + 4, STAGES = 3, D2 = DIM * DIM, DA = DIM / AS;
+    static constexpr int RAW = DA * D2;                // [a][NS + NA] doubles per stage (NS + NA == DIM*DIM)
+    static constexpr int DENSE = DA * DIM * LD;        // [a][c][LD]
+    static size_t smem_bytes(int K) { return (size_t)(STAGES * RAW + DENSE + DIM * ((K + 7) & ~7) * LD) * 8; }
+};
+
+template <int DIM, int AS>
+__global__ void __launch_bounds__(256) back_assemble_sym_kernel(const double* __restrict__ W, long long w_stride,
+                                                                const double* __restrict__ u, double* __restrict__ out, SymLayout L,
+                                                                int K, int accumulate, const int* active, int m, int layer) {
+    using Cfg = BasSymCfg<DIM, AS>;
+    constexpr int LD = Cfg::LD, D2 = Cfg::D2, ST = Cfg::STAGES, DA = Cfg::DA, NS = DIM * (DIM + 1) / 2, NA = DIM * (DIM - 1) / 2;
+    constexpr int MI = DA * DIM / 64;                  // 8-row blocks per warp
+    static_assert(MI >= 1 && (DA * D2) % 256 == 0, "unsupported split");
+    extern __shared__ __align__(16) double sm[];
+    const int inst = blockIdx.x / AS, a_lo = (blockIdx.x - inst * AS) * DA;
+    if (active != nullptr && active[inst] == 0) return;
+    const int item = inst * m + layer;
+    const int Kp = (K + 7) & ~7, NI = Kp / 8;
+    double* raw = sm;
+    double* dense = raw + ST * Cfg::RAW;
+    double* us = dense + Cfg::DENSE;
+    const long long np = (long long)DIM * K * DIM;
+    const double* Ws = W + (long long)inst * w_stride;
+    const double* Wa = Ws + L.off_a;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+
+    auto load_stage = [&](int b, int s) {
+        double* dst = raw + s * Cfg::RAW;
+        constexpr int CS = NS / 2, CA = NA / 2;        // 16-byte chunks per row
+        for (int id = tid; id < DA * (CS + CA); id += 256) {
+            const int al = id / (CS + CA), ch = id - al * (CS + CA), a = a_lo + al;
+            const int lo = a < b ? a : b, hi = a < b ? b : a;
+            if (ch < CS) cp_async16(dst + al * D2 + 2 * ch, Ws + (long long)pair_s(lo, hi, DIM) * L.Ds + 2 * ch);
+            else if (a != b) cp_async16(dst + al * D2 + NS + 2 * (ch - CS), Wa + (long long)pair_a(lo, hi, DIM) * L.Da + 2 * (ch - CS));
+        }
+    };
+#pragma unroll
+    for (int s = 0; s < ST - 1; ++s) { load_stage(s, s); cp_async_commit(); }
+    for (int i = tid; i < DIM * Kp * DIM; i += 256) {
+        const int r = i / DIM, c = i - r * DIM, bb = r / Kp, k = r - bb * Kp;
+        us[r * LD + c] = (k < K) ? u[(long long)item * np + (bb * K + k) * DIM + c] : 0.0;
+    }
+    double acc[MI][4][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const double s2 = 1.41421356237309504880;
+    // per-thread constants of the decode step: this thread always expands column pair (c, dd) = tid % D2
+    const int dc_cd = tid % D2, dc_c = dc_cd / DIM, dc_dd = dc_cd - dc_c * DIM, dc_a0 = tid / D2;
+    const int dc_lo = dc_c < dc_dd ? dc_c : dc_dd, dc_hi = dc_c < dc_dd ? dc_dd : dc_c;
+    const int dc_ps = pair_s(dc_lo, dc_hi, DIM), dc_pa = (dc_c != dc_dd) ? pair_a(dc_lo, dc_hi, DIM) : 0;
+    const bool dc_has_a = dc_c != dc_dd, dc_lt = dc_c < dc_dd;
+    const double dc_nu = (dc_c == dc_dd) ? s2 : 1.0;
+    const int dc_off = dc_c * LD + dc_dd;
+
+    for (int b = 0; b < DIM; ++b) {
+        cp_async_wait<ST - 2>();
+        __syncthreads();                                   // stage b landed; every warp is done with the previous dense tile
+        if (b + ST - 1 < DIM) load_stage(b + ST - 1, (b + ST - 1) % ST);
+        cp_async_commit();
+        const double* R = raw + (b % ST) * Cfg::RAW;
+        // decode: dense[a][c][d] = nu_ab nu_cd Ws[{ab},{cd}] + sg_ab sg_cd Wa[{ab},{cd}]   (thread-invariant parts hoisted: dc_*)
+#pragma unroll
+        for (int uu = 0; uu < DA * D2 / 256; ++uu) {
+            const int al = dc_a0 + uu * (256 / D2), a = a_lo + al;
+            double v = ((a == b) ? s2 : 1.0) * dc_nu * R[al * D2 + dc_ps];
+            if (dc_has_a && a != b) {
+                const double w = R[al * D2 + NS + dc_pa];
+                v += ((a < b) == dc_lt) ? w : -w;
+            }
+            dense[al * DIM * LD + dc_off] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int d0 = 0; d0 < DIM; d0 += 4) {
+            double wa[MI];
+#pragma unroll
+            for (int i = 0; i < MI; ++i) wa[i] = dense[(warp * (MI * 8) + i * 8 + g) * LD + d0 + t];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j < NI) {
+                    const double ub = us[(b * Kp + j * 8 + g) * LD + d0 + t];
+#pragma unroll
+                    for (int i = 0; i < MI; ++i) dmma884(acc[i][j][0], acc[i][j][1], wa[i], ub);
+                }
+        }
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+        const int Rw = warp * (MI * 8) + i * 8 + g, a = a_lo + Rw / DIM, c = Rw % DIM;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j < NI) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int k = j * 8 + 2 * t + e;
+                    if (k < K) {
+                        const long long og = (long long)item * np + (a * K + k) * DIM + c;
+                        out[og] = accumulate ? out[og] + acc[i][j][e] : acc[i][j][e];
+                    }
+                }
+            }
+    }
+}
+
+// ---- blocks -> dense superoperator (otn_model in structured mode) ------------------------------------------------------
+//   M[(a,b),(c,d)] = cs_ab cs_cd Ms[{ab},{cd}] + ca_ab ca_cd Ma[{ab},{cd}],  cs = 1 (a==b) else 1/sqrt2,  ca = +-1/sqrt2, 0 on a==b
+__global__ void unblock_kernel(const double* __restrict__ blocks, long long in_stride, double* __restrict__ M, SymLayout L, int batch) {
+    const int D = L.dim * L.dim;
+    const long long tot = (long long)batch * D * D;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
+        const int inst = (int)(i / ((long long)D * D));
+        const int rc = (int)(i - (long long)inst * D * D), r = rc / D, c = rc - r * D;
+        const int a = r / L.dim, b = r - a * L.dim, cc = c / L.dim, dd = c - cc * L.dim;
+        const int rlo = a < b ? a : b, rhi = a < b ? b : a, clo = cc < dd ? cc : dd, chi = cc < dd ? dd : cc;
+        const double* Bs = blocks + (long long)inst * in_stride;
+        const double h = 0.70710678118654752440;
+        double v = ((a == b) ? 1.0 : h) * ((cc == dd) ? 1.0 : h) * Bs[(long long)pair_s(rlo, rhi, L.dim) * L.Ds + pair_s(clo, chi, L.dim)];
+        if (a != b && cc != dd) {
+            const double w = 0.5 * Bs[L.off_a + (long long)pair_a(rlo, rhi, L.dim) * L.Da + pair_a(clo, chi, L.dim)];
+            v += ((a < b) == (cc < dd)) ? w : -w;
+        }
+        M[i] = v;
+    }
+}
+
+}  // namespace otn

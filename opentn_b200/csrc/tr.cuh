@@ -50,29 +50,54 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* red /* [NV][8
     __syncthreads();
 }
 
+// Shared-memory layout of the small kernels below: PT == 0 -> rows of p doubles, Grams on the CUDA cores (any p);
+// PT in {8, 16} -> rows padded to PT + 4 doubles and every Gram issued as DMMA (gram_blocks_mma), which removes the
+// 256-long dependent FMA chains that made the first version of the TR step cost as much as an HVP.
+template <int PT>
+struct TrLay {
+    static __device__ __forceinline__ int ld(int p) { return PT ? PT + 4 : p; }
+};
+
+template <int PT, int NG>
+__device__ __forceinline__ void grams(const double* const (&A)[NG], const double* const (&B)[NG], double* const (&G)[NG], int n, int p) {
+    if constexpr (PT != 0) {
+        gram_blocks_mma<PT, NG>(A, B, G, n);
+    } else {
+#pragma unroll
+        for (int q = 0; q < NG; ++q) gram(A[q], B[q], G[q], n, p);
+    }
+}
+
 // r = g, z = 0, d = -g, rsq = <g,g>, stoptol = max(abstol, reltol sqrt(rsq))     trust_region_rcopt.py:110-114
+template <int PT>
 __global__ void __launch_bounds__(ST_THREADS) tcg_init_kernel(const TcgParams P) {
     extern __shared__ __align__(16) double sm[];
     const int inst = blockIdx.x;
-    const int np = P.n * P.p, pp = P.p * P.p;
+    const int ld = TrLay<PT>::ld(P.p);
+    const int np = P.n * P.p, nl = P.n * ld, pl = P.p * ld;
     double* X = sm;
-    double* A = X + np;
-    double* GA = A + np;
+    double* A = X + nl;
+    double* GA = A + nl;
     __shared__ double red[8];
     double v[1] = {0.0};
     for (int l = 0; l < P.m; ++l) {
         const long long base = ((long long)inst * P.m + l) * np;
         for (int i = threadIdx.x; i < np; i += ST_THREADS) {
             const double gv = P.g[base + i];
-            X[i] = P.x[base + i]; A[i] = gv;
+            const int o = (i / P.p) * ld + (i % P.p);
+            X[o] = P.x[base + i]; A[o] = gv;
             P.r[base + i] = gv; P.z[base + i] = 0.0; P.d[base + i] = -gv;
             v[0] = fma(gv, gv, v[0]);
         }
         __syncthreads();
-        gram(X, A, GA, P.n, P.p);
+        {
+            const double* const As[1] = {X}; const double* const Bs[1] = {A}; double* const Gs[1] = {GA};
+            grams<PT, 1>(As, Bs, Gs, P.n, P.p);
+        }
         __syncthreads();
-        for (int o = threadIdx.x; o < pp; o += ST_THREADS) v[0] = fma(-0.5 * GA[o], GA[o], v[0]);
+        for (int o = threadIdx.x; o < P.p * P.p; o += ST_THREADS) { const double q = GA[(o / P.p) * ld + (o % P.p)]; v[0] = fma(-0.5 * q, q, v[0]); }
         __syncthreads();
+        (void)pl;
     }
     double out[1];
     block_sum<1>(v, red, out);
@@ -86,18 +111,20 @@ __global__ void __launch_bounds__(ST_THREADS) tcg_init_kernel(const TcgParams P)
 }
 
 // one tCG iteration given Hd = H d                                              trust_region_rcopt.py:116-132, 137-166
+template <int PT>
 __global__ void __launch_bounds__(ST_THREADS) tcg_step_kernel(const TcgParams P) {
     extern __shared__ __align__(16) double sm[];
     const int inst = blockIdx.x;
     if (P.tcg_active[inst] == 0) return;
-    const int np = P.n * P.p, pp = P.p * P.p;
+    const int ld = TrLay<PT>::ld(P.p);
+    const int np = P.n * P.p, nl = P.n * ld, pl = P.p * ld, pp = P.p * P.p;
     double* X = sm;
-    double* A = X + np;       // d
-    double* B = A + np;       // Hd
-    double* C = B + np;       // z  (pass A) / r (pass B)
-    double* GA = C + np;
-    double* GB = GA + pp;
-    double* GC = GB + pp;
+    double* A = X + nl;       // d
+    double* B = A + nl;       // Hd
+    double* C = B + nl;       // z  (pass A) / r (pass B)
+    double* GA = C + nl;
+    double* GB = GA + pl;
+    double* GC = GB + pl;
     __shared__ double red[4 * 8];
     __shared__ double sc[4];
     __shared__ int flag;
@@ -107,13 +134,18 @@ __global__ void __launch_bounds__(ST_THREADS) tcg_step_kernel(const TcgParams P)
         const long long base = ((long long)inst * P.m + l) * np;
         for (int i = threadIdx.x; i < np; i += ST_THREADS) {
             const double dv = P.d[base + i], hv = P.Hd[base + i], zv = P.z[base + i];
-            X[i] = P.x[base + i]; A[i] = dv; B[i] = hv; C[i] = zv;
+            const int o = (i / P.p) * ld + (i % P.p);
+            X[o] = P.x[base + i]; A[o] = dv; B[o] = hv; C[o] = zv;
             v[0] = fma(dv, hv, v[0]); v[1] = fma(dv, dv, v[1]); v[2] = fma(zv, dv, v[2]); v[3] = fma(zv, zv, v[3]);
         }
         __syncthreads();
-        gram(X, A, GA, P.n, P.p); gram(X, B, GB, P.n, P.p); gram(X, C, GC, P.n, P.p);
+        {
+            const double* const As[3] = {X, X, X}; const double* const Bs[3] = {A, B, C}; double* const Gs[3] = {GA, GB, GC};
+            grams<PT, 3>(As, Bs, Gs, P.n, P.p);
+        }
         __syncthreads();
-        for (int o = threadIdx.x; o < pp; o += ST_THREADS) {
+        for (int oo = threadIdx.x; oo < pp; oo += ST_THREADS) {
+            const int o = (oo / P.p) * ld + (oo % P.p);
             v[0] = fma(-0.5 * GA[o], GB[o], v[0]); v[1] = fma(-0.5 * GA[o], GA[o], v[1]);
             v[2] = fma(-0.5 * GC[o], GA[o], v[2]); v[3] = fma(-0.5 * GC[o], GC[o], v[3]);
         }
@@ -165,13 +197,17 @@ __global__ void __launch_bounds__(ST_THREADS) tcg_step_kernel(const TcgParams P)
             const double rv = fma(alpha, P.Hd[base + i], P.r[base + i]);
             P.r[base + i] = rv;
             P.z[base + i] = fma(alpha, P.d[base + i], P.z[base + i]);
-            X[i] = P.x[base + i]; C[i] = rv;
+            const int o = (i / P.p) * ld + (i % P.p);
+            X[o] = P.x[base + i]; C[o] = rv;
             w[0] = fma(rv, rv, w[0]);
         }
         __syncthreads();
-        gram(X, C, GC, P.n, P.p);
+        {
+            const double* const As[1] = {X}; const double* const Bs[1] = {C}; double* const Gs[1] = {GC};
+            grams<PT, 1>(As, Bs, Gs, P.n, P.p);
+        }
         __syncthreads();
-        for (int o = threadIdx.x; o < pp; o += ST_THREADS) w[0] = fma(-0.5 * GC[o], GC[o], w[0]);
+        for (int oo = threadIdx.x; oo < pp; oo += ST_THREADS) { const double q = GC[(oo / P.p) * ld + (oo % P.p)]; w[0] = fma(-0.5 * q, q, w[0]); }
         __syncthreads();
     }
     double o1[1];

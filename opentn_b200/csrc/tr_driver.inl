@@ -25,13 +25,52 @@ static int tr_alloc(otn_problem* h) {
     return 0;
 }
 
+static bool tr_use_mma(const otn_problem* h) { return (h->p == 16 || h->p == 8) && h->n % 8 == 0; }
+
 static int cdot_launch(otn_problem* h, const double* x, const double* a, const double* b, int batch, double* out) {
-    const size_t sm = (3 * (size_t)h->np + 2 * (size_t)h->p * h->p) * 8;
-    OTN_TRY(set_smem(cdot_kernel, sm));
     ProfScope ps(&h->prof, h->stream, CAT_TR, 0.0);
-    cdot_kernel<<<batch, ST_THREADS, sm, h->stream>>>(x, a, b, out, h->n, h->p, h->m, nullptr);
+    if (tr_use_mma(h)) {
+        const size_t ld = h->p + 4, sm = (3 * (size_t)h->n * ld + 2 * h->p * ld) * 8;
+        if (h->p == 16) { OTN_TRY(set_smem(cdot_mma_kernel<16>, sm)); cdot_mma_kernel<16><<<batch, ST_THREADS, sm, h->stream>>>(x, a, b, out, h->n, h->m, nullptr); }
+        else { OTN_TRY(set_smem(cdot_mma_kernel<8>, sm)); cdot_mma_kernel<8><<<batch, ST_THREADS, sm, h->stream>>>(x, a, b, out, h->n, h->m, nullptr); }
+    } else {
+        const size_t sm = (3 * (size_t)h->np + 2 * (size_t)h->p * h->p) * 8;
+        OTN_TRY(set_smem(cdot_kernel, sm));
+        cdot_kernel<<<batch, ST_THREADS, sm, h->stream>>>(x, a, b, out, h->n, h->p, h->m, nullptr);
+    }
     CUDA_TRY(cudaGetLastError());
     return 0;
+}
+
+static int retract_launch(otn_problem* h, const double* x, const double* z, double* xn, int batch, int* status) {
+    ProfScope ps(&h->prof, h->stream, CAT_TR, 0.0);
+    const size_t pp = (size_t)h->p * h->p;
+    if (tr_use_mma(h)) {
+        const size_t ld = h->p + 4, sm = (2 * (size_t)h->n * ld + 2 * h->p * ld + 5 * pp) * 8;
+        if (h->p == 16) { OTN_TRY(set_smem(retract_mma_kernel<16>, sm)); retract_mma_kernel<16><<<batch * h->m, ST_THREADS, sm, h->stream>>>(x, z, xn, h->n, h->m, nullptr, status); }
+        else { OTN_TRY(set_smem(retract_mma_kernel<8>, sm)); retract_mma_kernel<8><<<batch * h->m, ST_THREADS, sm, h->stream>>>(x, z, xn, h->n, h->m, nullptr, status); }
+    } else {
+        const size_t sm = ((size_t)h->np + 5 * pp) * 8;
+        OTN_TRY(set_smem(retract_kernel, sm));
+        retract_kernel<<<batch * h->m, ST_THREADS, sm, h->stream>>>(x, z, xn, h->n, h->p, h->m, nullptr, status);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+template <int PT>
+static int tcg_launch(otn_problem* h, const TcgParams& tp, int batch, bool init) {
+    const size_t ld = PT ? PT + 4 : h->p;
+    const size_t sm_init = (2 * (size_t)h->n * ld + h->p * ld) * 8, sm_step = (4 * (size_t)h->n * ld + 3 * h->p * ld) * 8;
+    ProfScope ps(&h->prof, h->stream, CAT_TR, 0.0);
+    if (init) { OTN_TRY(set_smem(tcg_init_kernel<PT>, sm_init)); tcg_init_kernel<PT><<<batch, ST_THREADS, sm_init, h->stream>>>(tp); }
+    else { OTN_TRY(set_smem(tcg_step_kernel<PT>, sm_step)); tcg_step_kernel<PT><<<batch, ST_THREADS, sm_step, h->stream>>>(tp); }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+static int tcg_dispatch(otn_problem* h, const TcgParams& tp, int batch, bool init) {
+    if (tr_use_mma(h)) return h->p == 16 ? tcg_launch<16>(h, tp, batch, init) : tcg_launch<8>(h, tp, batch, init);
+    return tcg_launch<0>(h, tp, batch, init);
 }
 
 extern "C" int otn_tr_run(otn_problem* h, double* x, int batch, const otn_tr_params* prm_in, otn_tr_report* rep) {
@@ -71,27 +110,19 @@ extern "C" int otn_tr_run(otn_problem* h, double* x, int batch, const otn_tr_par
     tp.x = h->x; tp.r = t.r; tp.z = t.z; tp.d = t.d; tp.Hd = t.Hd; tp.g = t.g; tp.radius = t.radius; tp.rsq = t.rsq;
     tp.stoptol = t.stoptol; tp.tcg_active = t.tcg_active; tp.on_boundary = t.on_boundary; tp.n_cg = t.n_cg; tp.status = t.status;
     tp.n_active = t.n_active; tp.n = h->n; tp.p = h->p; tp.m = h->m; tp.maxiter = maxiter; tp.abstol = prm.tcg_abstol; tp.reltol = prm.tcg_reltol;
-    const size_t pp = (size_t)h->p * h->p;
-    const size_t sm_init = (2 * (size_t)h->np + pp) * 8, sm_step = (4 * (size_t)h->np + 3 * pp) * 8;
-    OTN_TRY(set_smem(tcg_init_kernel, sm_init));
-    OTN_TRY(set_smem(tcg_step_kernel, sm_step));
-    const size_t sm_ret = ((size_t)h->np + 3 * pp) * 8;
-    OTN_TRY(set_smem(retract_kernel, sm_ret));
 
     for (int k = 0; k < prm.niter; ++k) {
         // grad = gradfunc(x) ; fx = f(x)  (same primal pass)                                       (:59, :63)
         OTN_TRY(otn_dev_cost_grad(h, h->x, batch, nullptr, t.fx, t.g, nullptr));
         if (rep && rep->f_iter) CUDA_TRY(cudaMemcpyAsync(hist_d(rep->f_iter, k), t.fx, (size_t)batch * 8, cudaMemcpyDefault, st));
         // eta, on_boundary = truncated_cg(grad, hess, radius)                                      (:61)
-        { ProfScope ps(&h->prof, st, CAT_TR, 0.0); tcg_init_kernel<<<batch, ST_THREADS, sm_init, st>>>(tp); }
-        CUDA_TRY(cudaGetLastError());
+        OTN_TRY(tcg_dispatch(h, tp, batch, true));
         int n_active = batch;
         for (int j = 0; j < maxiter && n_active > 0; ++j) {
             OTN_TRY(otn_dev_hvp(h, h->x, t.d, batch, t.tcg_active, t.Hd));
             hvps += n_active;
             CUDA_TRY(cudaMemsetAsync(t.n_active, 0, 4, st));
-            { ProfScope ps(&h->prof, st, CAT_TR, 0.0); tcg_step_kernel<<<batch, ST_THREADS, sm_step, st>>>(tp); }
-            CUDA_TRY(cudaGetLastError());
+            OTN_TRY(tcg_dispatch(h, tp, batch, false));
             CUDA_TRY(cudaMemcpyAsync(&n_active, t.n_active, 4, cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
         }
@@ -101,8 +132,7 @@ extern "C" int otn_tr_run(otn_problem* h, double* x, int batch, const otn_tr_par
         OTN_TRY(cdot_launch(h, h->x, t.g, t.z, batch, t.gz));
         OTN_TRY(cdot_launch(h, h->x, t.z, t.Hd, batch, t.zHz));
         // x_next = retract(x, eta) ; f(x_next)                                                     (:62, :67)
-        { ProfScope ps(&h->prof, st, CAT_TR, 0.0); retract_kernel<<<batch * h->m, ST_THREADS, sm_ret, st>>>(h->x, t.z, t.xn, h->n, h->p, h->m, nullptr, t.status); }
-        CUDA_TRY(cudaGetLastError());
+        OTN_TRY(retract_launch(h, h->x, t.z, t.xn, batch, t.status));
         OTN_TRY(otn_dev_cost(h, t.xn, batch, nullptr, t.fn));
         TrUpdateParams up{};
         up.radius = t.radius; up.rho = t.rho; up.fx = t.fx; up.fn = t.fn; up.gz = t.gz; up.zHz = t.zHz; up.on_boundary = t.on_boundary;

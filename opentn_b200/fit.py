@@ -34,13 +34,13 @@ def _is_cuda_tensor(a) -> bool:
 class _Handle:
     """Owns one otn_problem."""
 
-    def __init__(self, N, d, m, K, model, metric, max_batch, targets_re, targets_im, device):
+    def __init__(self, N, d, m, K, model, metric, max_batch, targets_re, targets_im, device, flags=0):
         lib = _lib.load()
         self._lib = lib
         self.h = C.c_void_p()
         n_targets = targets_re.shape[0]
-        check(lib.otn_create(C.byref(self.h), N, d, m, K, model, metric, max_batch, n_targets, ptr(targets_re),
-                             ptr(targets_im), device))
+        check(lib.otn_create_ex(C.byref(self.h), N, d, m, K, model, metric, max_batch, n_targets, ptr(targets_re),
+                                ptr(targets_im), device, flags))
         n, p, D, mm = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         ws = C.c_longlong()
         check(lib.otn_query(self.h, C.byref(n), C.byref(p), C.byref(D), C.byref(mm), C.byref(ws)))
@@ -68,7 +68,7 @@ class StiefelFit:
     batch selects its own through `target_index`.
     """
 
-    def __init__(self, target, model="local", N=None, d=2, metric="canonical", max_batch=1, device=0):
+    def __init__(self, target, model="local", N=None, d=2, metric="canonical", max_batch=1, device=0, dense=False):
         if model not in ("local", "full"):
             raise ValueError("model must be 'local' or 'full'")
         t = np.asarray(target)
@@ -86,6 +86,7 @@ class StiefelFit:
         self.metric = metric
         metric_id(metric)
         self.device = device
+        self.dense = bool(dense)   # force the dense D x D chain (default: block-diagonal evaluation where available)
         self.max_batch = max_batch
         self._t_re = np.ascontiguousarray(t.real, dtype=np.float64)
         self._t_im = np.ascontiguousarray(t.imag, dtype=np.float64) if np.iscomplexobj(t) and np.any(t.imag) else None
@@ -106,7 +107,7 @@ class StiefelFit:
                 h.close()
             cap = max(batch, self.max_batch)
             h = _Handle(self.N, self.d, m, K, MODEL_LOCAL if self.model == "local" else MODEL_FULL, metric_id(self.metric),
-                        cap, self._t_re, self._t_im, self.device)
+                        cap, self._t_re, self._t_im, self.device, _lib.FLAG_DENSE if self.dense else 0)
             h.tindex_ver = 0
             self._handles[key] = h
         return h

@@ -1,0 +1,109 @@
+"""GPU parity of the stateless representation / manifold entry points (otn_ortho2super, otn_embed_local, otn_compose,
+otn_project, otn_rgrad_map, otn_retract, otn_canonical_dot) against the reference's golden vectors and the oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("tag", ["loc3", "loc10", "full4"])
+def test_ortho2super(goldens, tag):
+    from opentn_b200 import transformations as T
+    np.testing.assert_allclose(T.ortho2super(goldens[f"in/x_{tag}"]), goldens[f"ref/ortho2super_{tag}"], rtol=0, atol=1e-15)
+
+
+def test_kraus2superop_definition(goldens, oracle):
+    from opentn_b200 import transformations as T
+    x = goldens["in/x_loc3"]
+    got = T.kraus2superop(oracle.kraus_from_ortho(x))
+    assert got.dtype == complex
+    np.testing.assert_allclose(got, goldens["ref/kraus2superop_loc3"], atol=1e-15)
+    with pytest.raises(NotImplementedError):
+        T.kraus2superop([np.eye(4) * 1j])
+
+
+@pytest.mark.parametrize("shift", [False, True])
+def test_embed_local_n4(goldens, shift):
+    from opentn_b200 import transformations as T
+    np.testing.assert_array_equal(T.local2full(goldens["in/yloc"], 4, 2, shift_pbc=shift), goldens[f"ref/embed_N4_shift{int(shift)}"])
+
+
+@pytest.mark.parametrize("shift", [False, True])
+def test_embed_local_n6(goldens, shift):
+    from opentn_b200 import transformations as T
+    full = T.local2full(goldens["in/yloc"], 6, 2, shift_pbc=shift)
+    assert full.shape == (4096, 4096)
+    np.testing.assert_array_equal(full[::61, ::67], goldens[f"ref/embed_N6_shift{int(shift)}"])
+
+
+def test_compose_and_models(goldens):
+    from opentn_b200 import optimization as O
+    from opentn_b200 import transformations as T
+    ops = [goldens["ref/ortho2super_full4"], goldens["ref/model_full_m3"], goldens["ref/model_local_m5"]]
+    np.testing.assert_allclose(T.compose_superops_list(ops), goldens["ref/compose3"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(O.model_stiefel_local(list(goldens["in/xs_loc5"]), 4, 2), goldens["ref/model_local_m5"], atol=1e-14)
+    np.testing.assert_allclose(O.model_Ys_stiefel(list(goldens["in/xs_full3"])), goldens["ref/model_full_m3"], atol=1e-13)
+    assert O.frobenius_norm(np.eye(3), np.zeros((3, 3))) == pytest.approx(np.sqrt(3))
+    assert O.frobenius_norm(np.eye(3), np.zeros((3, 3)), squared=True) == pytest.approx(3.0)
+
+
+@pytest.mark.parametrize("tag", ["s40", "s64", "sq"])
+def test_manifold_primitives(goldens, tag):
+    from opentn_b200 import stiefel as S
+    x, z, e = goldens[f"in/st_x_{tag}"], goldens[f"in/st_z_{tag}"], goldens[f"in/st_eta_{tag}"]
+    np.testing.assert_allclose(S.project(x, z), goldens[f"ref/project_{tag}"], atol=1e-14)
+    np.testing.assert_allclose(S.gradient_ambient2riemannian(x, z, 1, 1), goldens[f"ref/rgrad_euc_{tag}"], atol=1e-14)
+    np.testing.assert_allclose(S.gradient_ambient2riemannian(x, z, 1, 0.5), goldens[f"ref/rgrad_can_{tag}"], atol=1e-14)
+    nu = goldens[f"ref/rgrad_can_{tag}"]
+    np.testing.assert_allclose(S.riemannian_connection(z, nu, e, x, 1, 0.5), goldens[f"ref/conn_can_{tag}"], atol=1e-13)
+    assert S.canonical_metric(e, nu, x) == pytest.approx(float(goldens[f"ref/canonical_metric_{tag}"]), rel=1e-12)
+    assert S.euclidean_metric(e, nu) == pytest.approx(float(goldens[f"ref/euclidean_metric_{tag}"]), rel=1e-12)
+    # polar retraction: small tangent step (Newton-Schulz branch) and a large non-tangent one (Jacobi branch)
+    np.testing.assert_allclose(S.polar_decomposition_rectangular(x, 0.3 * e), goldens[f"ref/polar_{tag}"], atol=1e-13)
+    import scipy.linalg
+    big = 3.0 * z
+    np.testing.assert_allclose(S.polar_decomposition_rectangular(x, big), scipy.linalg.polar(x + big)[0], atol=1e-12)
+    y = S.polar_decomposition_rectangular(x, 0.05 * e)
+    assert S.is_isometry_2(y)
+    assert S.is_in_tangent_space(x, S.project(x, z))
+
+
+def test_retract_stiefel_coefficients(goldens):
+    from opentn_b200 import stiefel as S
+    xs, et = list(goldens["in/retract_xs"]), list(goldens["in/retract_etas"])
+    vec = np.hstack([S.parametrization_from_tangent(x, e) for x, e in zip(xs, et)])   # our own X_perp basis
+    np.testing.assert_allclose(np.array(S.retract_stiefel(xs, vec)), goldens["ref/retract_out"], atol=1e-13)
+    assert all(S.check_isometries(S.retract_stiefel(xs, vec)))
+
+
+def test_batched_stack_inputs(oracle):
+    from opentn_b200 import stiefel as S
+    rng = np.random.default_rng(0)
+    X = np.array([oracle.random_stiefel(64, 16, rng) for _ in range(5)])
+    Z = rng.standard_normal(X.shape)
+    out = S.project(X, Z)
+    for b in range(5):
+        np.testing.assert_allclose(out[b], oracle.project(X[b], Z[b]), atol=1e-13)
+
+
+def test_hessian_operator_dense_matches_oracle(oracle):
+    """riemannian_hessian_vec(...).to_dense() == the matrix stiefel.py:498-544 builds column by column (small case)."""
+    from opentn_b200 import StiefelFit
+    from opentn_b200 import stiefel as S
+    P = oracle
+    rng = np.random.default_rng(4)
+    T = P.exp_operator_dt(P.lindbladian2super([P.get_kitaev_nn_linbladian(1.0)]), 1.0)      # N = 2, D = 16
+    xs = [P.random_stiefel(8, 4, rng) for _ in range(2)]
+    fit = StiefelFit(T, model="full", N=2, d=2, metric="canonical")
+    op = S.riemannian_hessian_vec(xs, fit, metric="canonical")
+    H = op.to_dense()
+    assert H.shape == (2 * 22, 2 * 22)
+    # our coefficient basis (QR complement) differs from the oracle's (SVD complement) by an orthogonal map: compare the
+    # basis-independent quantities -- symmetry and spectrum
+    Ho = P.riemannian_hessian_vec(xs, P.CostSpec(T, "full"), "canonical")
+    np.testing.assert_allclose(H, H.T, atol=1e-10)
+    np.testing.assert_allclose(np.linalg.eigvalsh(0.5 * (H + H.T)), np.linalg.eigvalsh(0.5 * (Ho + Ho.T)), atol=1e-9)
+    g = S.gradient_stiefel_vec(xs, fit, metric="canonical")
+    go = P.gradient_stiefel_vec(xs, P.CostSpec(T, "full"), "canonical")
+    assert abs(np.linalg.norm(g) - np.linalg.norm(go)) < 1e-12
+    fit.close()

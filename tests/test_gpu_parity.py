@@ -169,3 +169,48 @@ def test_pipelined_host_path_equals_device_path(P, targets):
         fo, go, ho = P.triple(spec, list(xs[b]), list(et[b]), "canonical")
         assert abs(f_h[b] - fo) / fo < 1e-12 and rel(h_h[b], np.array(ho)) < 1e-10
     fit.close()
+
+
+@pytest.mark.parametrize("metric", ["canonical", "euclidean"])
+@pytest.mark.parametrize("m,K", [(3, 16), (2, 3), (1, 5)])
+def test_dense_formulation_full_model(P, targets, metric, m, K):
+    """OTN_FLAG_DENSE: the dense D x D chain (what the reference executes) against the oracle and against the default
+    block-diagonal evaluation."""
+    from opentn_b200 import StiefelFit
+    T = targets["kitaev_obc_tau4"]
+    B = 2
+    xs, et = _random_batch(P, B, m, 16 * K, 16, 40 + K)
+    dense = StiefelFit(T, model="full", N=N, d=d, metric=metric, max_batch=B, dense=True)
+    blocks = StiefelFit(T, model="full", N=N, d=d, metric=metric, max_batch=B)
+    fd, gd, hd = dense.triple(xs, et)
+    fb, gb, hb = blocks.triple(xs, et)
+    np.testing.assert_allclose(fd, fb, rtol=1e-13)
+    assert rel(gd, gb) < 1e-11 and rel(hd, hb) < 1e-11
+    spec = P.CostSpec(T, "full")
+    for b in range(B):
+        fo, go, ho = P.triple(spec, list(xs[b]), list(et[b]), metric)
+        assert abs(fd[b] - fo) / fo < 1e-12
+        assert rel(gd[b], np.array(go)) < 1e-10 and rel(hd[b], np.array(ho)) < 1e-10
+    Md, Mb = dense.model_matrix(xs), blocks.model_matrix(xs)
+    for b in range(B):
+        Mo = P.model_Ys_stiefel(list(xs[b]))
+        np.testing.assert_allclose(Md[b], Mo, atol=1e-13)
+        np.testing.assert_allclose(Mb[b], Mo, atol=1e-13)
+    dense.close(); blocks.close()
+
+
+def test_full_model_n3_dim8(P):
+    """dim = 8 (N = 3 qubits, D = 64): exercises the DIM = 8 instantiations (blocks 36 -> 48 and 28 -> 64)."""
+    from opentn_b200 import StiefelFit
+    rng = np.random.default_rng(8)
+    T = rng.standard_normal((64, 64))
+    xs, et = _random_batch(P, 2, 3, 8 * 5, 8, 77)
+    spec = P.CostSpec(T, "full")
+    for dense in (False, True):
+        fit = StiefelFit(T, model="full", N=3, d=2, metric="canonical", max_batch=2, dense=dense)
+        f, g, h = fit.triple(xs, et)
+        for b in range(2):
+            fo, go, ho = P.triple(spec, list(xs[b]), list(et[b]), "canonical")
+            assert abs(f[b] - fo) / fo < 1e-12
+            assert rel(g[b], np.array(go)) < 1e-10 and rel(h[b], np.array(ho)) < 1e-10
+        fit.close()
