@@ -204,7 +204,6 @@ def measure_fp64_peak(torch):
 def run_gpu(args):
     import ctypes as C
 
-    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -236,17 +235,8 @@ def run_gpu(args):
     g_pin = torch.empty_like(x_pin).pin_memory()
     h_pin = torch.empty_like(x_pin).pin_memory()
     torch.cuda.synchronize()
-
-    fit = StiefelFit(target, model="full", N=N_SITES, d=D_LOC, metric="canonical", max_batch=BATCH, device=local_rank)
-    handle = fit._handle(M_LAYERS, K_RANK, BATCH)
     stream = torch.cuda.current_stream()
-    _lib.check(lib.otn_set_stream(handle.h, C.c_void_p(stream.cuda_stream)))   # so that torch.cuda.Event brackets our kernels
-
-    def step_device():
-        _lib.check(lib.otn_triple(handle.h, x_dev.data_ptr(), e_dev.data_ptr(), BATCH, f_dev.data_ptr(), g_dev.data_ptr(), h_dev.data_ptr()))
-
-    def step_e2e():
-        _lib.check(lib.otn_triple(handle.h, x_pin.data_ptr(), e_pin.data_ptr(), BATCH, f_pin.data_ptr(), g_pin.data_ptr(), h_pin.data_ptr()))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def barrier():
         if world > 1:
@@ -260,37 +250,54 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def make_fit(dense):
+        fit_ = StiefelFit(target, model="full", N=N_SITES, d=D_LOC, metric="canonical", max_batch=BATCH, device=local_rank, dense=dense)
+        handle_ = fit_._handle(M_LAYERS, K_RANK, BATCH)
+        _lib.check(lib.otn_set_stream(handle_.h, C.c_void_p(stream.cuda_stream)))   # torch.cuda.Event then brackets our kernels
+        return fit_, handle_
+
+    def timed_device_steps(handle_, steps, min_warm_s):
+        """>= W warm-up steps (and >= min_warm_s under load), then `steps` timed steps of otn_triple on device-resident
+        inputs, every kernel launch bracketed by a CUDA-event pair on its stream (otn_profile_*)."""
+        def step():
+            _lib.check(lib.otn_triple(handle_.h, x_dev.data_ptr(), e_dev.data_ptr(), BATCH, f_dev.data_ptr(), g_dev.data_ptr(), h_dev.data_ptr()))
+        t_warm = time.perf_counter()
+        n_warm_ = 0
+        while n_warm_ < max(args.warmup, 3) or time.perf_counter() - t_warm < min_warm_s:
+            step()
+            n_warm_ += 1
+        barrier()
+        lib.otn_profile_enable(handle_.h, 1)
+        launches0 = lib.otn_launch_count()
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        barrier()
+        ms_total_ = max_over_ranks(e0.elapsed_time(e1))
+        launches_ = lib.otn_launch_count() - launches0
+        pms_ = (C.c_double * 6)(); pln_ = (C.c_longlong * 6)(); pfl_ = (C.c_double * 6)()
+        _lib.check(lib.otn_profile_read(handle_.h, pms_, pln_, pfl_))
+        lib.otn_profile_enable(handle_.h, 0)
+        return ms_total_, launches_, list(pms_), list(pln_), list(pfl_), n_warm_
+
     peak_tf = measure_fp64_peak(torch) if rank == 0 else None
 
-    # ---- device-resident timing (`value`) ----------------------------------------------------------------------------
+    # ---- device-resident timing (`value`): default (block-diagonal) evaluation ------------------------------------------
+    fit, handle = make_fit(dense=False)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()          # nvidia-smi samples every 100 ms; "under load" samples are selected by power draw
-    t_warm = time.perf_counter()
-    n_warm = 0
-    while n_warm < max(args.warmup, 3) or time.perf_counter() - t_warm < 0.5:   # >= W steps and >= 0.5 s under load
-        step_device()
-        n_warm += 1
-    barrier()
-    lib.otn_profile_enable(handle.h, 1)
-    launches0 = lib.otn_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step_device()
-    e1.record(stream)
-    barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = lib.otn_launch_count() - launches0
+    ms_total, launches, pms, pln, pfl, n_warm = timed_device_steps(handle, args.steps, 0.5)
     clocks = sampler.stop() if rank == 0 else None
-    pms = (C.c_double * 6)(); pln = (C.c_longlong * 6)(); pfl = (C.c_double * 6)()
-    _lib.check(lib.otn_profile_read(handle.h, pms, pln, pfl))
-    lib.otn_profile_enable(handle.h, 0)
     ms_per_step = ms_total / args.steps
     value = world * BATCH * args.steps / (ms_total * 1e-3)
 
     # ---- end-to-end timing: pinned host buffers through the C ABI, H2D + D2H inside the timed region -----------------
-    for _ in range(2):
+    def step_e2e():
+        _lib.check(lib.otn_triple(handle.h, x_pin.data_ptr(), e_pin.data_ptr(), BATCH, f_pin.data_ptr(), g_pin.data_ptr(), h_pin.data_ptr()))
+
+    for _ in range(3):
         step_e2e()
     barrier()
     e0.record(stream)
@@ -329,6 +336,16 @@ def run_gpu(args):
         tr = {"iters_per_sec": world * BATCH * niter / (ms_tr * 1e-3), "unit": "TR iterations/s (all instances)", "niter": niter,
               "n_cg_mean": float(rep["n_cg"].mean()), "hvp_total_rank0": int(rep["hvp_total"]), "ms_per_iter_batch": ms_tr / niter,
               "accept_rate": float(rep["accepted"].mean())}
+    fit.close()
+
+    # ---- same workload through the dense D x D formulation (what the reference executes; SURVEY 8d flop count) -----------
+    dense_raw = None
+    if not args.no_dense:
+        torch.cuda.empty_cache()
+        fit_d, handle_d = make_fit(dense=True)
+        d_steps = max(3, args.steps // 2)
+        dense_raw = timed_device_steps(handle_d, d_steps, 0.2) + (d_steps,)
+        fit_d.close()
 
     if rank != 0:
         if world > 1:
@@ -336,24 +353,43 @@ def run_gpu(args):
         return 0
 
     # ---- roofline of the dominant kernel (chain GEMM on the FP64 tensor pipe) -------------------------------------------
-    gemm_ms, gemm_n, gemm_fl = pms[0], pln[0], pfl[0]
-    achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+    def roofline_of(pms_, pln_, pfl_, ms_total_, steps_):
+        gemm_ms, gemm_n, gemm_fl = pms_[0], pln_[0], pfl_[0]
+        ach = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+        return {"achieved": ach, "frac": (ach / peak_tf) if ach and peak_tf else None, "launches_timed": int(gemm_n),
+                "avg_launch_ms": gemm_ms / gemm_n if gemm_n else None,
+                "executed_flops_per_launch": gemm_fl / gemm_n if gemm_n else None,
+                "kernel_share_of_step": gemm_ms / ms_total_,
+                "other_kernels_ms_per_step": {"assembly": pms_[1] / steps_, "back_assembly": pms_[2] / steps_,
+                                              "riemannian_epilogue": pms_[3] / steps_, "other": pms_[5] / steps_}}
+
     peak_file = None
     try:
         peak_file = json.load(open(os.path.join(ROOT, "profiles", "fp64_peaks_r01.json")))["dgemm_8192"] / 1e3
     except Exception:
         pass
-    roofline = {"bound": "tensor", "kernel": "gemm_dmma_kernel (FP64 DMMA.8x8x4)", "achieved": achieved, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved and peak_tf else None, "traffic": None,
-                "peak_source": "cuBLAS DGEMM 8192^3 via torch.matmul, best of 3, measured in this run (MEASURED_PEAKS.json has no "
-                               "FP64 figure; DMMA issue-rate ceiling 148 SM x 128 flop/clk x 1.965 GHz = 37.2 TFLOP/s)",
-                "peak_committed_r01": peak_file,
-                "launches_timed": int(gemm_n), "avg_launch_ms": gemm_ms / gemm_n if gemm_n else None,
-                "algorithmic_flops_per_launch": gemm_fl / gemm_n if gemm_n else None,
-                "kernel_share_of_step": gemm_ms / ms_total,
-                "other_kernels_ms_per_step": {"assembly": pms[1] / args.steps, "back_assembly": pms[2] / args.steps,
-                                              "riemannian_epilogue": pms[3] / args.steps, "other": pms[5] / args.steps},
-                "step_tflops_algorithmic": FLOPS_PER_TRIPLE * BATCH / (ms_per_step * 1e-3) / 1e12}
+    peak_source = ("cuBLAS DGEMM 8192^3 via torch.matmul, best of 3, measured in this run (MEASURED_PEAKS.json has no FP64 figure; "
+                   "DMMA issue-rate ceiling 148 SM x 128 flop/clk x 1.965 GHz = 37.2 TFLOP/s)")
+    roofline = {"bound": "tensor", "kernel": "gemm_dmma_kernel (FP64 DMMA.8x8x4), block-diagonal chain: one 144^3 (48x48 tiles) and one "
+                                             "128^3 (64x64 tiles) product per chain product",
+                "peak": peak_tf, "unit": "TFLOP/s", "traffic": None, "peak_source": peak_source, "peak_committed_r01": peak_file}
+    roofline.update(roofline_of(pms, pln, pfl, ms_total, args.steps))
+    roofline["note"] = ("`achieved` counts EXECUTED flops of the block-diagonal evaluation (2*(144^3+128^3) per product incl. zero "
+                        "padding; 2*(136^3+120^3) useful). Dense-equivalent rate (SURVEY 8d algorithmic count, 2*256^3 per product) is "
+                        "`step_tflops_dense_equivalent`; the dense formulation itself is measured in `dense_formulation`.")
+    roofline["step_tflops_dense_equivalent"] = FLOPS_PER_TRIPLE * BATCH / (ms_per_step * 1e-3) / 1e12
+
+    dense_leg = None
+    if dense_raw is not None:
+        ms_d, launches_d, pms_d, pln_d, pfl_d, _, d_steps = dense_raw
+        rf = {"bound": "tensor", "kernel": "gemm_dmma_kernel<64,64,16,32,32,3> (FP64 DMMA.8x8x4), 2*256^3 per product",
+              "peak": peak_tf, "unit": "TFLOP/s", "traffic": 1.59e9,
+              "traffic_note": "dram read+write per launch of a single-product GEMM over 1024 instances from ncu --set full "
+                              "(profiles/ncu_gemm_dense_r01.txt); algorithmic 3*D^2*8*1024 = 1.61e9 B"}
+        rf.update(roofline_of(pms_d, pln_d, pfl_d, ms_d, d_steps))
+        dense_leg = {"value": world * BATCH * d_steps / (ms_d * 1e-3), "unit": UNIT, "ms_per_step": ms_d / d_steps, "steps": d_steps,
+                     "gpu_launches": int(launches_d), "roofline": rf,
+                     "step_tflops_algorithmic": FLOPS_PER_TRIPLE * BATCH / (ms_d / d_steps * 1e-3) / 1e12}
 
     cpu = None
     if not args.no_cpu:
@@ -369,7 +405,7 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu, "tr": tr, "final_gather_ms": gather_ms}
+            "roofline": roofline, "dense_formulation": dense_leg, "cpu_baseline": cpu, "tr": tr, "final_gather_ms": gather_ms}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -384,6 +420,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-tr", action="store_true", help="skip the TR iterations/s leg")
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense-formulation comparison leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
