@@ -288,7 +288,7 @@ def run_gpu(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()          # nvidia-smi samples every 100 ms; "under load" samples are selected by power draw
-    ms_total, launches, pms, pln, pfl, n_warm = timed_device_steps(handle, args.steps, 0.5)
+    ms_total, launches, pms, pln, pfl, n_warm = timed_device_steps(handle, args.steps, args.min_warm_s)
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms_total / args.steps
     value = world * BATCH * args.steps / (ms_total * 1e-3)
@@ -344,7 +344,7 @@ def run_gpu(args):
         torch.cuda.empty_cache()
         fit_d, handle_d = make_fit(dense=True)
         d_steps = max(3, args.steps // 2)
-        dense_raw = timed_device_steps(handle_d, d_steps, 0.2) + (d_steps,)
+        dense_raw = timed_device_steps(handle_d, d_steps, min(0.2, args.min_warm_s)) + (d_steps,)
         fit_d.close()
 
     if rank != 0:
@@ -421,6 +421,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-tr", action="store_true", help="skip the TR iterations/s leg")
     ap.add_argument("--no-dense", action="store_true", help="skip the dense-formulation comparison leg")
+    ap.add_argument("--min-warm-s", type=float, default=0.5,
+                    help="keep warming up until this many seconds under load have passed (0 = exactly --warmup steps, for profilers)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
