@@ -192,7 +192,7 @@ struct otn_problem {
     double* T_re = nullptr;      // [n_targets][SZ]
     double* im2 = nullptr;       // [n_targets]
     int* tindex = nullptr;       // [max_batch]
-    unsigned* tab = nullptr; int* inv = nullptr;
+    unsigned* tab = nullptr; int* inv = nullptr; unsigned* symtab = nullptr; int* t2f = nullptr;
     // work matrices, per instance [m][SZ] unless noted
     double *Y = nullptr, *P = nullptr, *G = nullptr, *W = nullptr, *Yd = nullptr, *Pd = nullptr;
     double *Gd = nullptr;        // [2][SZ]
@@ -228,7 +228,7 @@ extern "C" void otn_destroy(otn_problem* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (void* ptr : {(void*)h->T_re, (void*)h->im2, (void*)h->tindex, (void*)h->tab, (void*)h->inv, (void*)h->Y, (void*)h->P,
+    for (void* ptr : {(void*)h->T_re, (void*)h->im2, (void*)h->tindex, (void*)h->tab, (void*)h->inv, (void*)h->symtab, (void*)h->t2f, (void*)h->Y, (void*)h->P,
                       (void*)h->G, (void*)h->W, (void*)h->Yd, (void*)h->Pd, (void*)h->Gd, (void*)h->Wd, (void*)h->Yl, (void*)h->Yld,
                       (void*)h->Wl, (void*)h->Wld, (void*)h->x, (void*)h->eta, (void*)h->zraw, (void*)h->zdraw, (void*)h->part_f,
                       (void*)h->part_s})
@@ -276,10 +276,12 @@ extern "C" int otn_create_ex(otn_problem** out, int N, int d, int m, int K, int 
     h->nf = N / 2;
     h->dim = (model == OTN_MODEL_FULL) ? ipow(d, N) : d * d;
     h->nblk = 1; h->blkD[0] = h->D; h->blkOff[0] = 0;
-    h->structured = (model == OTN_MODEL_FULL) && (h->dim == 16 || h->dim == 8) && !(flags & OTN_FLAG_DENSE);
+    const int sdim = ipow(d, N);   // side of the doubled index (a,b): D = sdim^2
+    h->structured = !(flags & OTN_FLAG_DENSE) &&
+                    ((model == OTN_MODEL_FULL && (h->dim == 16 || h->dim == 8)) || (model == OTN_MODEL_LOCAL && sdim >= 8 && sdim <= 64));
     if (h->structured) {
         SymLayout& L = h->sym;
-        L.dim = h->dim; L.NS = h->dim * (h->dim + 1) / 2; L.NA = h->dim * (h->dim - 1) / 2;
+        L.dim = sdim; L.NS = sdim * (sdim + 1) / 2; L.NA = sdim * (sdim - 1) / 2;
         auto pad = [](int n) { const int p48 = (n + 47) / 48 * 48, p64 = (n + 63) / 64 * 64; return p48 < p64 ? p48 : p64; };
         L.Ds = pad(L.NS); L.Da = pad(L.NA);
         L.off_a = (long long)L.Ds * L.Ds; L.slot = L.off_a + (long long)L.Da * L.Da;
@@ -360,6 +362,22 @@ extern "C" int otn_create_ex(otn_problem** out, int N, int d, int m, int K, int 
         CREATE_TRY(cudaMemcpy(h->tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
         CREATE_TRY(cudaMalloc(&h->inv, inv.size() * 4));
         CREATE_TRY(cudaMemcpy(h->inv, inv.data(), inv.size() * 4, cudaMemcpyHostToDevice));
+        if (h->structured) {
+            std::vector<unsigned> st(h->D);
+            for (int r = 0; r < h->D; ++r) st[r] = sym_pack(r / sdim, r % sdim, sdim);
+            CREATE_TRY(cudaMalloc(&h->symtab, st.size() * 4));
+            CREATE_TRY(cudaMemcpy(h->symtab, st.data(), st.size() * 4, cudaMemcpyHostToDevice));
+            // tensored index (loc_0, loc_1, ...) -> full index, per shift
+            std::vector<int> t2f(2 * (size_t)h->D);
+            for (int sh = 0; sh < 2; ++sh)
+                for (int r = 0; r < h->D; ++r) {
+                    int rt = 0;
+                    for (int f = 0; f < h->nf; ++f) rt = rt * h->q + (int)((tab[(size_t)sh * h->D + r] >> (8 * f)) & 0xff);
+                    t2f[(size_t)sh * h->D + rt] = r;
+                }
+            CREATE_TRY(cudaMalloc(&h->t2f, t2f.size() * 4));
+            CREATE_TRY(cudaMemcpy(h->t2f, t2f.data(), t2f.size() * 4, cudaMemcpyHostToDevice));
+        }
         const size_t q2 = (size_t)h->q * h->q;
         CREATE_TRY(cudaMalloc(&h->Yl, B * M * q2 * 8));
         CREATE_TRY(cudaMalloc(&h->Yld, B * M * q2 * 8));
@@ -481,7 +499,7 @@ static int build_layers(otn_problem* h, const double* x, const double* eta, int 
     double* Ydout = (h->model == OTN_MODEL_FULL) ? h->Yd : h->Yld;
     const long long ostride = (h->model == OTN_MODEL_FULL) ? h->SZ : (long long)h->q * h->q;
     dim3 grid(h->dim, items);
-    if (h->structured) {
+    if (h->structured && h->model == OTN_MODEL_FULL) {
         const int Kp = (h->K + 3) & ~3;
         const size_t sm = ((size_t)h->dim * Kp * (h->dim + 4) * (tangent ? 2 : 1) + (size_t)8 * 2 * h->dim * (h->dim + 1)) * 8;
 #define ASM_SYM(DIMV, TG, PR)                                                                                        \
@@ -514,7 +532,14 @@ static int build_layers(otn_problem* h, const double* x, const double* eta, int 
         assemble_kernel<false, true><<<grid, ASM_THREADS, smem, h->stream>>>(x, eta, Yout, Ydout, ostride, h->dim, h->K, active, h->m);
     }
     CUDA_TRY(cudaGetLastError());
-    if (h->model == OTN_MODEL_LOCAL) {
+    if (h->model == OTN_MODEL_LOCAL && h->structured) {
+        dim3 g2((h->sym.NS + EMB_ROWS - 1) / EMB_ROWS, items);
+        const size_t sm2 = (size_t)h->q * h->q * 8 * 2;
+        if (tangent && primal) embed_sym_kernel<true, true><<<g2, EMB_THREADS, sm2, h->stream>>>(h->Yl, h->Yld, h->Y, h->Yd, h->tables(), h->sym, active, h->m);
+        else if (tangent) embed_sym_kernel<true, false><<<g2, EMB_THREADS, sm2, h->stream>>>(h->Yl, h->Yld, h->Y, h->Yd, h->tables(), h->sym, active, h->m);
+        else embed_sym_kernel<false, true><<<g2, EMB_THREADS, sm2, h->stream>>>(h->Yl, h->Yld, h->Y, h->Yd, h->tables(), h->sym, active, h->m);
+        CUDA_TRY(cudaGetLastError());
+    } else if (h->model == OTN_MODEL_LOCAL) {
         dim3 g2((h->D + EMB_ROWS - 1) / EMB_ROWS, items);
         const size_t sm2 = (size_t)h->q * h->q * 8 * 2;
         if (tangent && primal) embed_kernel<true, true><<<g2, EMB_THREADS, sm2, h->stream>>>(h->Yl, h->Yld, h->Y, h->Yd, h->tables(), active, h->m);
@@ -610,7 +635,16 @@ static int back_layer(otn_problem* h, int batch, const int* active, int l, const
         const int q2 = h->q * h->q;
         dim3 g((h->nf * q2 + 7) / 8, batch);
         const size_t sm = (size_t)q2 * 8 * 2;
-        if (!tangent) back_embed_kernel<false><<<g, BEM_THREADS, sm, h->stream>>>(Wfull, nullptr, S, 0, h->Yl, h->Yld, h->Wl, h->Wld, h->tables(), active, h->m, l);
+        if (h->structured && h->nf == 2 && h->q == 16) {
+            const size_t sm2 = (size_t)(16 * 256 * (tangent ? 2 : 1) + 16 * 16 * 17) * 8;
+            OTN_TRY(set_smem(back_embed2_sym_kernel<false>, sm2));
+            OTN_TRY(set_smem(back_embed2_sym_kernel<true>, sm2));
+            if (!tangent) back_embed2_sym_kernel<false><<<batch, 256, sm2, h->stream>>>(Wfull, nullptr, S, 0, h->Yl, h->Yld, h->Wl, h->Wld, h->sym, h->symtab, h->t2f, active, h->m, l);
+            else back_embed2_sym_kernel<true><<<batch, 256, sm2, h->stream>>>(Wfull, Wdfull, S, sWd, h->Yl, h->Yld, h->Wl, h->Wld, h->sym, h->symtab, h->t2f, active, h->m, l);
+        } else if (h->structured) {
+            if (!tangent) back_embed_sym_kernel<false><<<g, BEM_THREADS, sm, h->stream>>>(Wfull, nullptr, S, 0, h->Yl, h->Yld, h->Wl, h->Wld, h->tables(), h->sym, h->symtab, active, h->m, l);
+            else back_embed_sym_kernel<true><<<g, BEM_THREADS, sm, h->stream>>>(Wfull, Wdfull, S, sWd, h->Yl, h->Yld, h->Wl, h->Wld, h->tables(), h->sym, h->symtab, active, h->m, l);
+        } else if (!tangent) back_embed_kernel<false><<<g, BEM_THREADS, sm, h->stream>>>(Wfull, nullptr, S, 0, h->Yl, h->Yld, h->Wl, h->Wld, h->tables(), active, h->m, l);
         else back_embed_kernel<true><<<g, BEM_THREADS, sm, h->stream>>>(Wfull, Wdfull, S, sWd, h->Yl, h->Yld, h->Wl, h->Wld, h->tables(), active, h->m, l);
         CUDA_TRY(cudaGetLastError());
         const long long ls = (long long)h->nf * q2;
@@ -620,7 +654,7 @@ static int back_layer(otn_problem* h, int batch, const int* active, int l, const
     }
     const int dim = h->dim;
     dim3 grid(dim, batch);
-    if (h->structured) {
+    if (h->structured && h->model == OTN_MODEL_FULL) {
 #define BAS_SYM(DIMV, ASV)                                                                                                       \
     do {                                                                                                                         \
         const size_t sm = BasSymCfg<DIMV, ASV>::smem_bytes(h->K);                                                                \

@@ -14,6 +14,7 @@
 //     Z[(a,k),c] = sum_{b,d} ( nu_ab nu_cd Ws[{ab},{cd}] + sg_ab sg_cd Wa[{ab},{cd}] ) x[(b,k),d]
 // with nu_ab = sqrt2 if a == b else 1, sg_ab = +1 (a<b), -1 (a>b), 0 (a == b).
 #pragma once
+#include "assemble.cuh"
 #include "otn_common.cuh"
 
 namespace otn {
@@ -249,6 +250,253 @@ __global__ void unblock_kernel(const double* __restrict__ blocks, long long in_s
             v += ((a < b) == (cc < dd)) ? w : -w;
         }
         M[i] = v;
+    }
+}
+
+// ---- 2-site model in the block basis ------------------------------------------------------------------------------------
+// element (r, c) of the swap-symmetric matrix represented by the blocks (same formula as unblock_kernel)
+__device__ __forceinline__ double sym_at(const double* __restrict__ Bs, const SymLayout& L, int r, int c) {
+    const int a = r / L.dim, b = r - a * L.dim, cc = c / L.dim, dd = c - cc * L.dim;
+    const int rlo = a < b ? a : b, rhi = a < b ? b : a, clo = cc < dd ? cc : dd, chi = cc < dd ? dd : cc;
+    const double h = 0.70710678118654752440;
+    double v = ((a == b) ? 1.0 : h) * ((cc == dd) ? 1.0 : h) * Bs[(long long)pair_s(rlo, rhi, L.dim) * L.Ds + pair_s(clo, chi, L.dim)];
+    if (a != b && cc != dd) {
+        const double w = 0.5 * Bs[L.off_a + (long long)pair_a(rlo, rhi, L.dim) * L.Da + pair_a(clo, chi, L.dim)];
+        v += ((a < b) == (cc < dd)) ? w : -w;
+    }
+    return v;
+}
+
+// embed_sym: blocks of Y_full = perm(Y_loc^{(x) N/2}) without materialising Y_full:
+//   Ys[{ab},{cd}] = n_ab n_cd (Y[(a,b),(c,d)] + Y[(a,b),(d,c)]),   Ya[{ab},{cd}] = Y[(a,b),(c,d)] - Y[(a,b),(d,c)]
+// (Y is swap symmetric).  grid = (ceil(NS / EMB_ROWS), items); thread = one column pair {cd}.
+template <bool TANGENT, bool PRIMAL>
+__global__ void __launch_bounds__(EMB_THREADS) embed_sym_kernel(const double* __restrict__ Yl, const double* __restrict__ Yld,
+                                                                double* __restrict__ Y, double* __restrict__ Yd, EmbedTables T,
+                                                                SymLayout L, const int* active, int m) {
+    extern __shared__ __align__(16) double sm[];
+    const int item = blockIdx.y;
+    if (active != nullptr && active[item / m] == 0) return;
+    const int layer = item % m, shift = layer & 1;
+    const int q2 = T.q * T.q;
+    double* yl = sm;
+    double* yld = sm + q2;
+    for (int i = threadIdx.x; i < q2; i += EMB_THREADS) {
+        yl[i] = Yl[(long long)item * q2 + i];
+        if (TANGENT) yld[i] = Yld[(long long)item * q2 + i];
+    }
+    __syncthreads();
+    const unsigned* tab = T.tab + (size_t)shift * T.D;
+    const int dim = L.dim;
+    auto emb = [&](unsigned pr, unsigned pc, double& prim, double& tang) {
+        double prod = 1.0, dsum = 0.0;
+        for (int f = 0; f < T.nf; ++f) {
+            const int e = loc_idx(pr, f) * T.q + loc_idx(pc, f);
+            const double v = yl[e];
+            if (TANGENT) dsum = dsum * v + prod * yld[e];
+            prod *= v;
+        }
+        prim = prod; tang = dsum;
+    };
+    double* Ys = Y + (long long)item * L.slot;
+    double* Ya = Ys + L.off_a;
+    double* Yds = Yd + (long long)item * L.slot;
+    double* Yda = Yds + L.off_a;
+    const double rs2 = 0.70710678118654752440;
+    for (int ci = threadIdx.x; ci < L.NS; ci += EMB_THREADS) {
+        int c = 0, rem = ci;
+        while (rem >= dim - c) { rem -= dim - c; ++c; }
+        const int dd = c + rem;
+        const unsigned p1 = tab[c * dim + dd], p2 = tab[dd * dim + c];
+        for (int rr = 0; rr < EMB_ROWS; ++rr) {
+            const int ri = blockIdx.x * EMB_ROWS + rr;
+            if (ri >= L.NS) break;
+            int a = 0, rm = ri;
+            while (rm >= dim - a) { rm -= dim - a; ++a; }
+            const int b = a + rm;
+            const unsigned pr = tab[a * dim + b];
+            double v1, t1, v2, t2;
+            emb(pr, p1, v1, t1);
+            emb(pr, p2, v2, t2);
+            const double w = ((a == b) ? rs2 : 1.0) * ((c == dd) ? rs2 : 1.0);
+            if (PRIMAL) Ys[(long long)ri * L.Ds + ci] = w * (v1 + v2);
+            if (TANGENT) Yds[(long long)ri * L.Ds + ci] = w * (t1 + t2);
+            if (a < b && c < dd) {
+                const long long o = (long long)pair_a(a, b, dim) * L.Da + pair_a(c, dd, dim);
+                if (PRIMAL) Ya[o] = v1 - v2;
+                if (TANGENT) Yda[o] = t1 - t2;
+            }
+        }
+    }
+}
+
+// Packed per-full-index lookup for sym_at: bits 0-11 pair_s, 12-23 pair_a, 24 diag (a == b), 25 lt (a < b); built on the host.
+__host__ __device__ __forceinline__ unsigned sym_pack(int a, int b, int dim) {
+    const int lo = a < b ? a : b, hi = a < b ? b : a;
+    return (unsigned)pair_s(lo, hi, dim) | ((unsigned)(a != b ? pair_a(lo, hi, dim) : 0) << 12) | ((unsigned)(a == b) << 24) | ((unsigned)(a < b) << 25);
+}
+__device__ __forceinline__ double sym_at_packed(const double* __restrict__ Bs, const SymLayout& L, unsigned pr, unsigned pc) {
+    const double h = 0.70710678118654752440;
+    const bool dr = (pr >> 24) & 1, dc = (pc >> 24) & 1;
+    double v = (dr ? 1.0 : h) * (dc ? 1.0 : h) * Bs[(long long)(pr & 0xfff) * L.Ds + (pc & 0xfff)];
+    if (!dr && !dc) {
+        const double w = 0.5 * Bs[L.off_a + (long long)((pr >> 12) & 0xfff) * L.Da + ((pc >> 12) & 0xfff)];
+        v += (((pr >> 25) & 1) == ((pc >> 25) & 1)) ? w : -w;
+    }
+    return v;
+}
+
+// back_embed from cotangent blocks: identical to back_embed_kernel (assemble.cuh) with W[r,c] reconstructed from the blocks.
+template <bool TANGENT>
+__global__ void __launch_bounds__(BEM_THREADS) back_embed_sym_kernel(const double* __restrict__ W, const double* __restrict__ Wd,
+                                                                     long long w_stride, long long wd_stride,
+                                                                     const double* __restrict__ Yl, const double* __restrict__ Yld,
+                                                                     double* __restrict__ Wl, double* __restrict__ Wld, EmbedTables T,
+                                                                     SymLayout L, const unsigned* __restrict__ symtab, const int* active,
+                                                                     int m, int layer) {
+    extern __shared__ __align__(16) double sm[];
+    const int inst = blockIdx.y;
+    if (active != nullptr && active[inst] == 0) return;
+    const int item = inst * m + layer;
+    const int shift = layer & 1;
+    const int q = T.q, q2 = q * q, per = T.D / q;
+    double* yl = sm;
+    double* yld = sm + q2;
+    for (int i = threadIdx.x; i < q2; i += BEM_THREADS) {
+        yl[i] = Yl[(long long)item * q2 + i];
+        if (TANGENT) yld[i] = Yld[(long long)item * q2 + i];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int out = blockIdx.x * (BEM_THREADS / 32) + warp;
+    if (out >= T.nf * q2) return;
+    const int f = out / q2, ij = out - f * q2, i = ij / q, j = ij - i * q;
+    const unsigned* tab = T.tab + (size_t)shift * T.D;
+    const int* rows = T.inv + (((size_t)shift * T.nf + f) * q + i) * per;
+    const int* cols = T.inv + (((size_t)shift * T.nf + f) * q + j) * per;
+    const double* Wb = W + (long long)inst * w_stride;
+    const double* Wdb = TANGENT ? Wd + (long long)inst * wd_stride : nullptr;
+    double acc = 0.0, accd = 0.0;
+    const long long terms = (long long)per * per;
+    for (long long tix = lane; tix < terms; tix += 32) {
+        const int r = rows[tix / per], c = cols[tix % per];
+        const unsigned pr = tab[r], pc = tab[c];
+        double prod = 1.0, dsum = 0.0;
+        for (int g = 0; g < T.nf; ++g) {
+            if (g == f) continue;
+            const int e = loc_idx(pr, g) * q + loc_idx(pc, g);
+            const double v = yl[e];
+            if (TANGENT) dsum = dsum * v + prod * yld[e];
+            prod *= v;
+        }
+        const unsigned sr = symtab[r], sc = symtab[c];
+        const double w = sym_at_packed(Wb, L, sr, sc);
+        if (!TANGENT) acc = fma(w, prod, acc);
+        if (TANGENT) { accd = fma(sym_at_packed(Wdb, L, sr, sc), prod, accd); accd = fma(w, dsum, accd); }
+    }
+    acc = warp_sum(acc);
+    accd = warp_sum(accd);
+    if (lane == 0) {
+        if (!TANGENT) Wl[((long long)item * T.nf + f) * q2 + ij] = acc;
+        else Wld[((long long)item * T.nf + f) * q2 + ij] = accd;
+    }
+}
+
+// Fast back-embed for two Kronecker factors (N = 4) from cotangent blocks: one CTA per instance, thread = tensored column
+// (j0, j1).  With T[i0][i1][j0][j1] = W[r(i0,i1)][c(j0,j1)]:
+//   O_0[i0][j0] = sum_{i1,j1} T * Y[i1][j1]      (half-warp shuffle reduction over j1)
+//   O_1[i1][j1] = sum_{i0,j0} T * Y[i0][j0]      (register accumulation over i0, one shared-memory reduction over j0 at the end)
+// Each (row r, all columns) access stays inside one 1 KB row of Ws / Wa, so the gathers are sector-efficient.
+template <bool TANGENT>
+__global__ void __launch_bounds__(256) back_embed2_sym_kernel(const double* __restrict__ W, const double* __restrict__ Wd,
+                                                              long long w_stride, long long wd_stride,
+                                                              const double* __restrict__ Yl, const double* __restrict__ Yld,
+                                                              double* __restrict__ Wl, double* __restrict__ Wld, SymLayout L,
+                                                              const unsigned* __restrict__ symtab, const int* __restrict__ t2f,
+                                                              const int* active, int m, int layer) {
+    constexpr int Q = 16, NS = 136;             // q = d^4 = 16 (d = 2); D = 256; NS + NA = 256
+    extern __shared__ __align__(16) double sm[];
+    double* raw = sm;                           // [i1][256]: row r(i0,i1) of Ws (NS entries) followed by the row of Wa
+    double* rawd = raw + Q * 256;               // same for Wd (TANGENT)
+    double* red = rawd + (TANGENT ? Q * 256 : 0);   // [j0][i1][Q+1]
+    __shared__ double yl[Q * Q], yld[Q * Q];
+    __shared__ unsigned srow[Q * Q];
+    const int inst = blockIdx.x;
+    if (active != nullptr && active[inst] == 0) return;
+    const int item = inst * m + layer, shift = layer & 1;
+    const int t = threadIdx.x, j0 = t >> 4, j1 = t & 15;
+    const int* map = t2f + shift * 256;
+    yl[t] = Yl[(long long)item * 256 + t];
+    if (TANGENT) yld[t] = Yld[(long long)item * 256 + t];
+    srow[t] = symtab[map[t]];                   // packed pair info of the full index of tensored index t
+    __syncthreads();
+    const unsigned sc = srow[t];
+    const int psc = sc & 0xfff, pac = (sc >> 12) & 0xfff;
+    const bool dc = (sc >> 24) & 1, ltc = (sc >> 25) & 1;
+    const double* Ws = W + (long long)inst * w_stride;
+    const double* Wa = Ws + L.off_a;
+    const double* Wds = TANGENT ? Wd + (long long)inst * wd_stride : nullptr;
+    const double* Wda = TANGENT ? Wds + L.off_a : nullptr;
+    const double h = 0.70710678118654752440;
+    double o1[Q];
+#pragma unroll
+    for (int i = 0; i < Q; ++i) o1[i] = 0.0;
+    double* out0 = (TANGENT ? Wld : Wl) + ((long long)item * 2 + 0) * 256;
+    double* out1 = (TANGENT ? Wld : Wl) + ((long long)item * 2 + 1) * 256;
+    for (int i0 = 0; i0 < Q; ++i0) {
+        // stage the 16 rows r(i0, i1): coalesced, each global row read exactly once per CTA
+        double v[Q], vd[Q];
+#pragma unroll
+        for (int i1 = 0; i1 < Q; ++i1) {
+            const unsigned sr = srow[i0 * Q + i1];
+            const bool dr = (sr >> 24) & 1;
+            if (t < NS) {
+                v[i1] = Ws[(long long)(sr & 0xfff) * L.Ds + t];
+                if (TANGENT) vd[i1] = Wds[(long long)(sr & 0xfff) * L.Ds + t];
+            } else {
+                v[i1] = dr ? 0.0 : Wa[(long long)((sr >> 12) & 0xfff) * L.Da + (t - NS)];
+                if (TANGENT) vd[i1] = dr ? 0.0 : Wda[(long long)((sr >> 12) & 0xfff) * L.Da + (t - NS)];
+            }
+        }
+        __syncthreads();                        // previous chunk fully consumed
+#pragma unroll
+        for (int i1 = 0; i1 < Q; ++i1) { raw[i1 * 256 + t] = v[i1]; if (TANGENT) rawd[i1 * 256 + t] = vd[i1]; }
+        __syncthreads();
+        const double y00 = yl[i0 * Q + j0], yd00 = TANGENT ? yld[i0 * Q + j0] : 0.0;
+        double p = 0.0;
+#pragma unroll
+        for (int i1 = 0; i1 < Q; ++i1) {
+            const unsigned sr = srow[i0 * Q + i1];
+            const bool dr = (sr >> 24) & 1;
+            const double cf = (dr ? 1.0 : h) * (dc ? 1.0 : h);
+            double w = cf * raw[i1 * 256 + psc], wd = 0.0;
+            if (TANGENT) wd = cf * rawd[i1 * 256 + psc];
+            if (!dr && !dc) {
+                const double sg = ((((sr >> 25) & 1) != 0) == ltc) ? 0.5 : -0.5;
+                w = fma(sg, raw[i1 * 256 + NS + pac], w);
+                if (TANGENT) wd = fma(sg, rawd[i1 * 256 + NS + pac], wd);
+            }
+            if (!TANGENT) {
+                p = fma(w, yl[i1 * Q + j1], p);
+                o1[i1] = fma(w, y00, o1[i1]);
+            } else {
+                p = fma(wd, yl[i1 * Q + j1], p); p = fma(w, yld[i1 * Q + j1], p);
+                o1[i1] = fma(wd, y00, o1[i1]); o1[i1] = fma(w, yd00, o1[i1]);
+            }
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o, 16);
+        if (j1 == 0) out0[i0 * Q + j0] = p;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i1 = 0; i1 < Q; ++i1) red[(j0 * Q + i1) * (Q + 1) + j1] = o1[i1];
+    __syncthreads();
+    {
+        const int i1 = t >> 4, jj = t & 15;
+        double s = 0.0;
+        for (int a = 0; a < Q; ++a) s += red[(a * Q + i1) * (Q + 1) + jj];
+        out1[i1 * Q + jj] = s;
     }
 }
 

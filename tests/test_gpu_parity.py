@@ -62,14 +62,15 @@ def test_full_model_triple(P, targets, metric, m, K):
     fit.close()
 
 
+@pytest.mark.parametrize("dense", [False, True])
 @pytest.mark.parametrize("metric", ["canonical", "euclidean"])
 @pytest.mark.parametrize("m,K,tname", [(3, 10, "pspl_tau1"), (9, 16, "kitaev_pbc_tau05"), (5, 2, "pspl_tau05")])
-def test_local_model_triple(P, targets, metric, m, K, tname):
+def test_local_model_triple(P, targets, metric, m, K, tname, dense):
     from opentn_b200 import StiefelFit
     T = targets[tname]
     B = 2
     xs, et = _random_batch(P, B, m, 4 * K, 4, 11 + m)
-    fit = StiefelFit(T, model="local", N=N, d=d, metric=metric, max_batch=B)
+    fit = StiefelFit(T, model="local", N=N, d=d, metric=metric, max_batch=B, dense=dense)
     f, g, h = fit.triple(xs, et)
     spec = P.CostSpec(T, "local", N, d)
     for b in range(B):
