@@ -98,6 +98,11 @@ int otn_hvp_cached(otn_problem* p, const double* eta, int batch, double* heta);
 int otn_ortho2super(const double* x, int count, int dim, int K, double* Y, int device);
 int otn_embed_local(const double* Yloc, int count, int N, int d, int shift_pbc, double* Yfull, int device);
 int otn_compose(const double* Ys, int count, int m, int D, double* M, int device);
+/* otn_gemm_rows : rows [row0, row0+rows) of  op(A1) op(B1) [+ op(A2) op(B2)]  (D x D, device pointers, asynchronous on `stream`).
+ *                 One step of compose_superops_list (transformations.py:850, `jnp.dot(op, composition)`) restricted to a row
+ *                 block -- the unit of the row-sharded N = 6 composition; a complex product is two dual launches. */
+int otn_gemm_rows(const double* A1, const double* B1, const double* A2, const double* B2, double* C, int D, int row0, int rows,
+                  int transA, int transB, int device, void* stream);
 
 /* ---- manifold layer (stateless) ---------------------------------------------------------------------------------------
  * otn_project       : Z - X sym(X^T Z)                                   project (stiefel.py:23-30)

@@ -57,6 +57,7 @@ SIGNATURES = {
     "otn_ortho2super": (C.c_int, [_dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int]),
     "otn_embed_local": (C.c_int, [_dp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int]),
     "otn_compose": (C.c_int, [_dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int]),
+    "otn_gemm_rows": (C.c_int, [_dp, _dp, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "otn_project": (C.c_int, [_dp, _dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int]),
     "otn_rgrad_map": (C.c_int, [_dp, _dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _dp, C.c_int]),
     "otn_retract": (C.c_int, [_dp, _dp, C.c_int, C.c_int, C.c_int, _dp, _ip, C.c_int]),

@@ -44,6 +44,16 @@ static int fail(const char* fmt, ...) {
 extern "C" const char* otn_last_error(void) { return g_err.c_str(); }
 extern "C" int otn_version(void) { return 100; }
 
+// Every entry point runs on its own device but must leave the caller's current device untouched (a host framework such as
+// torch tracks the current device per thread; changing it behind its back misplaces the caller's next allocation).
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; if (prev != dev) cudaSetDevice(dev); }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 static bool is_device_ptr(const void* p) {
     if (p == nullptr) return false;
     cudaPointerAttributes a;
@@ -220,13 +230,12 @@ struct otn_problem {
 static int check_batch(otn_problem* h, int batch) {
     if (h == nullptr) return fail("null handle");
     if (batch < 1 || batch > h->max_batch) return fail("batch %d outside [1, max_batch=%d]", batch, h->max_batch);
-    CUDA_TRY(cudaSetDevice(h->device));
     return 0;
 }
 
 extern "C" void otn_destroy(otn_problem* h) {
     if (!h) return;
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard__(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (void* ptr : {(void*)h->T_re, (void*)h->im2, (void*)h->tindex, (void*)h->tab, (void*)h->inv, (void*)h->symtab, (void*)h->t2f, (void*)h->Y, (void*)h->P,
                       (void*)h->G, (void*)h->W, (void*)h->Yd, (void*)h->Pd, (void*)h->Gd, (void*)h->Wd, (void*)h->Yl, (void*)h->Yld,
@@ -261,7 +270,7 @@ extern "C" int otn_create_ex(otn_problem** out, int N, int d, int m, int K, int 
     int ndev = 0;
     CUDA_TRY(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail("device %d not available (%d CUDA devices)", device, ndev);
-    CUDA_TRY(cudaSetDevice(device));
+    DeviceGuard dev_guard__(device);
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail("libotn is built for sm_100a (B200); device %d is sm_%d%d", device, prop.major, prop.minor);
@@ -409,6 +418,7 @@ extern "C" int otn_set_metric(otn_problem* h, int metric) {
 
 extern "C" int otn_set_target_index(otn_problem* h, const int* index, int batch) {
     OTN_TRY(check_batch(h, batch));
+    DeviceGuard dev_guard__(h->device);
     std::vector<int> host(batch);
     CUDA_TRY(cudaMemcpy(host.data(), index, batch * 4, cudaMemcpyDefault));
     for (int b = 0; b < batch; ++b)
@@ -431,7 +441,7 @@ extern "C" void* otn_stream(const otn_problem* h) { return h ? (void*)h->stream 
 
 extern "C" int otn_set_stream(otn_problem* h, void* stream) {
     if (!h) return fail("null handle");
-    CUDA_TRY(cudaSetDevice(h->device));
+    DeviceGuard dev_guard__(h->device);
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     if (h->own_stream && h->stream) CUDA_TRY(cudaStreamDestroy(h->stream));
     h->stream = (cudaStream_t)stream;
@@ -448,7 +458,7 @@ extern "C" int otn_profile_enable(otn_problem* h, int on) {
 // sums (and clears) the per-category event timings recorded since the last read: ms[6], launches[6], flops[6]
 extern "C" int otn_profile_read(otn_problem* h, double* ms, long long* launches, double* flops) {
     if (!h) return fail("null handle");
-    CUDA_TRY(cudaSetDevice(h->device));
+    DeviceGuard dev_guard__(h->device);
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     for (int c = 0; c < CAT_COUNT; ++c) { if (ms) ms[c] = 0; if (launches) launches[c] = 0; if (flops) flops[c] = 0; }
     for (auto& r : h->prof.recs) {
@@ -838,6 +848,7 @@ static int keep_x(otn_problem* h, const double* xdev, int batch) {
 
 extern "C" int otn_model(otn_problem* h, const double* x, int batch, double* M) {
     OTN_TRY(check_batch(h, batch));
+    DeviceGuard dev_guard__(h->device);
     if (!x || !M) return fail("null argument");
     const void* xd; void* Md; int tiles;
     OTN_TRY(stage_in(x, xbytes(h, batch), h->in_x, h->stream, &xd));
@@ -854,6 +865,7 @@ extern "C" int otn_model(otn_problem* h, const double* x, int batch, double* M) 
 
 extern "C" int otn_cost(otn_problem* h, const double* x, int batch, double* f) {
     OTN_TRY(check_batch(h, batch));
+    DeviceGuard dev_guard__(h->device);
     if (!x || !f) return fail("null argument");
     const void* xd; void* fd;
     OTN_TRY(stage_in(x, xbytes(h, batch), h->in_x, h->stream, &xd));
@@ -866,6 +878,7 @@ extern "C" int otn_cost(otn_problem* h, const double* x, int batch, double* f) {
 
 extern "C" int otn_cost_grad(otn_problem* h, const double* x, int batch, double* f, double* rgrad, double* egrad) {
     OTN_TRY(check_batch(h, batch));
+    DeviceGuard dev_guard__(h->device);
     if (!x) return fail("null argument");
     const void* xd; void *fd, *gd, *ed;
     OTN_TRY(stage_in(x, xbytes(h, batch), h->in_x, h->stream, &xd));
@@ -941,6 +954,7 @@ static int triple_pipelined(otn_problem* h, const double* x, const double* eta, 
 
 extern "C" int otn_triple(otn_problem* h, const double* x, const double* eta, int batch, double* f, double* rgrad, double* heta) {
     OTN_TRY(check_batch(h, batch));
+    DeviceGuard dev_guard__(h->device);
     if (!x || !eta) return fail("null argument");
     const bool all_host = !is_device_ptr(x) && !is_device_ptr(eta) && (!f || !is_device_ptr(f)) && (!rgrad || !is_device_ptr(rgrad)) &&
                           (!heta || !is_device_ptr(heta));
@@ -963,6 +977,7 @@ extern "C" int otn_triple(otn_problem* h, const double* x, const double* eta, in
 
 extern "C" int otn_hvp_cached(otn_problem* h, const double* eta, int batch, double* heta) {
     OTN_TRY(check_batch(h, batch));
+    DeviceGuard dev_guard__(h->device);
     if (!eta || !heta) return fail("null argument");
     if (h->cached_batch < batch) return fail("no primal cache for %d instances: call otn_cost_grad or otn_triple first", batch);
     const void* ed; void* hd;
@@ -984,7 +999,6 @@ static int use_device(int device) {
     int ndev = 0;
     CUDA_TRY(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev || device >= 16) return fail("device %d not available", device);
-    CUDA_TRY(cudaSetDevice(device));
     return 0;
 }
 
@@ -992,6 +1006,7 @@ extern "C" int otn_ortho2super(const double* x, int count, int dim, int K, doubl
     if (!x || !Y || count < 1 || dim < 1 || K < 1) return fail("bad argument");
     if (K > ASM_MAXK) return fail("Kraus rank %d > %d not supported", K, ASM_MAXK);
     OTN_TRY(use_device(device));
+    DeviceGuard dev_guard__(device);
     Scratch& S = g_scratch[device];
     const size_t np = (size_t)dim * K * dim, d4 = (size_t)dim * dim * dim * dim;
     const void* xd; void* Yd;
@@ -1014,6 +1029,7 @@ extern "C" int otn_embed_local(const double* Yloc, int count, int N, int d, int 
     if (N % 2 != 0) return fail("Only even number of sites allowed");
     if (N / 2 > 4 || ipow(d, 4) > 255) return fail("embedding supports N <= 8 and d <= 3");
     OTN_TRY(use_device(device));
+    DeviceGuard dev_guard__(device);
     Scratch& S = g_scratch[device];
     std::vector<unsigned> tab; std::vector<int> inv;
     build_embed_tables(N, d, tab, inv);
@@ -1042,6 +1058,7 @@ extern "C" int otn_embed_local(const double* Yloc, int count, int N, int d, int 
 extern "C" int otn_compose(const double* Ys, int count, int m, int D, double* M, int device) {
     if (!Ys || !M || count < 1 || m < 1 || D < 1) return fail("bad argument");
     OTN_TRY(use_device(device));
+    DeviceGuard dev_guard__(device);
     Scratch& S = g_scratch[device];
     const size_t SZ = (size_t)D * D;
     const void* yd; void* Md;
@@ -1069,6 +1086,7 @@ static int project_like(const double* x, const double* z, int count, int n, int 
     if (!x || !z || !out || count < 1 || n < p || p < 1) return fail("bad argument");
     if (p > ST_MAXP) return fail("p = %d > %d not supported", p, ST_MAXP);
     OTN_TRY(use_device(device));
+    DeviceGuard dev_guard__(device);
     Scratch& S = g_scratch[device];
     const size_t np = (size_t)n * p;
     const void *xd, *zd; void* od;
@@ -1095,6 +1113,7 @@ extern "C" int otn_retract(const double* x, const double* eta, int count, int n,
     if (!x || !out || count < 1 || n < p || p < 1) return fail("bad argument");
     if (p > ST_MAXP) return fail("p = %d > %d not supported", p, ST_MAXP);
     OTN_TRY(use_device(device));
+    DeviceGuard dev_guard__(device);
     Scratch& S = g_scratch[device];
     const size_t np = (size_t)n * p;
     const void *xd, *ed; void *od, *sd;
@@ -1117,6 +1136,7 @@ extern "C" int otn_canonical_dot(const double* x, const double* a, const double*
     if (!x || !a || !b || !out || batch < 1 || m < 1 || n < p || p < 1) return fail("bad argument");
     if (p > ST_MAXP) return fail("p = %d > %d not supported", p, ST_MAXP);
     OTN_TRY(use_device(device));
+    DeviceGuard dev_guard__(device);
     Scratch& S = g_scratch[device];
     const size_t bytes = (size_t)batch * m * n * p * 8;
     const void *xd, *ad, *bd; void* od;
@@ -1130,6 +1150,25 @@ extern "C" int otn_canonical_dot(const double* x, const double* a, const double*
     CUDA_TRY(cudaGetLastError());
     OTN_TRY(finish_out(out, od, (size_t)batch * 8, 0));
     CUDA_TRY(cudaDeviceSynchronize());
+    return 0;
+}
+
+// Row-window product on device arrays: C[row0:row0+rows, :] = op(A1) op(B1) [+ op(A2) op(B2)] restricted to those rows of the
+// result (all operands D x D row-major, device pointers, `stream` = a cudaStream_t or NULL).  Building block of the row-sharded
+// single-instance N = 6 composition: rank g owns a row block and all-gathers it after every chain step.
+extern "C" int otn_gemm_rows(const double* A1, const double* B1, const double* A2, const double* B2, double* C, int D, int row0,
+                             int rows, int transA, int transB, int device, void* stream) {
+    if (!A1 || !B1 || !C || D < 1 || rows < 1 || row0 < 0 || row0 + rows > D) return fail("bad argument");
+    if ((A2 == nullptr) != (B2 == nullptr)) return fail("A2 and B2 must be given together");
+    if (transA && transB) return fail("A^T B^T is not supported");
+    OTN_TRY(use_device(device));
+    DeviceGuard dev_guard__(device);
+    for (const void* ptr : {(const void*)A1, (const void*)B1, (const void*)C})
+        if (!is_device_ptr(ptr)) return fail("otn_gemm_rows takes device pointers");
+    GemmParams p{};
+    p.A1 = A1; p.B1 = B1; p.A2 = A2; p.B2 = B2; p.C = C; p.D = D; p.row0 = row0; p.rows = rows; p.batch = 1; p.epi = EPI_NONE;
+    ++g_launches;
+    CUDA_TRY(gemm_launch(p, transA != 0, transB != 0, (cudaStream_t)stream));
     return 0;
 }
 

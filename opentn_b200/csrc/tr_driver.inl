@@ -75,6 +75,7 @@ static int tcg_dispatch(otn_problem* h, const TcgParams& tp, int batch, bool ini
 
 extern "C" int otn_tr_run(otn_problem* h, double* x, int batch, const otn_tr_params* prm_in, otn_tr_report* rep) {
     OTN_TRY(check_batch(h, batch));
+    DeviceGuard dev_guard__(h->device);
     if (!x) return fail("null argument");
     otn_tr_params prm;
     if (prm_in) prm = *prm_in; else otn_tr_default_params(&prm);

@@ -1,0 +1,38 @@
+"""N = 6 sites (D = 4096) through the CUDA path: the reference's only N=6 anchors (trust_region_higher_sites.ipynb cells 4, 16:
+cost 0.53944709 and ||Riemannian gradient coefficient vector|| = 15.82062161395626 at the Trotter point, K = 2, canonical)."""
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu, pytest.mark.slow]
+
+
+@pytest.fixture(scope="module")
+def n6(oracle):
+    P = oracle
+    Lnn = P.get_kitaev_nn_linbladian(1.0)
+    T6 = P.exp_operator_dt(P.create_2local_liouvillians(Lnn, 6, 2, pbc=True)[0], 4.0)     # ~15 s of host expm
+    xs = [P.super2ortho(x.real, rank=2) for x in P.get_general_trotter_local_ansatz([Lnn], 4, n=1)]
+    return T6, xs
+
+
+@pytest.mark.parametrize("dense", [False, True])
+def test_n6_cost_and_gradient_norm(n6, goldens, dense):
+    from opentn_b200 import StiefelFit
+    from opentn_b200 import stiefel as S
+    T6, xs = n6
+    fit = StiefelFit(T6, model="local", N=6, d=2, metric="canonical", dense=dense)
+    f, g = fit.cost_grad(xs)
+    assert abs(f - goldens["known/n6_cost0"]) < 5e-9
+    assert abs(f - 0.5394470932876375) < 1e-12                       # SURVEY 8c (reference cost code under the shim)
+    # coefficient-vector norm == canonical norm of the tangent matrices (basis independent)
+    gn = np.sqrt(sum(S.canonical_metric(gl, gl, x) for gl, x in zip(g, xs)))
+    assert abs(gn - goldens["known/n6_gradnorm"]) / goldens["known/n6_gradnorm"] < 1e-11
+    # one HVP: self-adjointness <w, H v> = <v, H w> in the canonical metric
+    rng = np.random.default_rng(0)
+    v = np.array([S.project(x, rng.standard_normal(x.shape)) for x in xs])
+    w = np.array([S.project(x, rng.standard_normal(x.shape)) for x in xs])
+    Hv, Hw = fit.hvp_cached(v), fit.hvp_cached(w)
+    a = sum(S.canonical_metric(w[l], Hv[l], xs[l]) for l in range(3))
+    b = sum(S.canonical_metric(v[l], Hw[l], xs[l]) for l in range(3))
+    assert abs(a - b) < 1e-9 * abs(a)
+    fit.close()

@@ -107,3 +107,23 @@ def test_hessian_operator_dense_matches_oracle(oracle):
     go = P.gradient_stiefel_vec(xs, P.CostSpec(T, "full"), "canonical")
     assert abs(np.linalg.norm(g) - np.linalg.norm(go)) < 1e-12
     fit.close()
+
+
+def test_library_preserves_current_device():
+    """Entry points run on their own device but must not change the caller's current CUDA device."""
+    import torch
+    from opentn_b200 import StiefelFit
+    from opentn_b200 import transformations as T
+    if torch.cuda.device_count() < 2:
+        dev = torch.cuda.current_device()
+        T.ortho2super(np.linalg.qr(np.random.default_rng(0).standard_normal((8, 4)))[0])
+        assert torch.cuda.current_device() == dev
+        return
+    torch.cuda.set_device(1)
+    T.ortho2super(np.linalg.qr(np.random.default_rng(0).standard_normal((8, 4)))[0])      # runs on device 0
+    fit = StiefelFit(np.eye(16), model="full", N=2, d=2, device=0)
+    fit.cost(np.linalg.qr(np.random.default_rng(1).standard_normal((1, 8, 4)))[0])
+    assert torch.cuda.current_device() == 1
+    assert torch.zeros(1, device="cuda").device.index == 1
+    fit.close()
+    torch.cuda.set_device(0)
