@@ -103,6 +103,16 @@ int otn_compose(const double* Ys, int count, int m, int D, double* M, int device
  *                 block -- the unit of the row-sharded N = 6 composition; a complex product is two dual launches. */
 int otn_gemm_rows(const double* A1, const double* B1, const double* A2, const double* B2, double* C, int D, int row0, int rows,
                   int transA, int transB, int device, void* stream);
+/* otn_gemm_rows_bcast : the same product fused with its all-gather -- every output tile is also stored into peers[0..npeer)
+ *                 (the result buffer of the other ranks, mapped over NVLink through CUDA IPC), so the exchange overlaps the
+ *                 math tile by tile and no NCCL collective follows.  Steps of a chain are ordered by the caller's barrier.
+ * otn_ipc_*     : allocate an IPC-shareable device buffer / export its 64-byte handle / map a peer's buffer / release. */
+int otn_gemm_rows_bcast(const double* A1, const double* B1, const double* A2, const double* B2, double* C, double* const* peers,
+                        int npeer, int D, int row0, int rows, int transA, int transB, int device, void* stream);
+int otn_ipc_alloc(long long bytes, int device, void** ptr, unsigned char* handle64);
+int otn_ipc_open(const unsigned char* handle64, int device, void** ptr);
+int otn_ipc_close(void* ptr, int device);
+int otn_ipc_free(void* ptr, int device);
 
 /* ---- manifold layer (stateless) ---------------------------------------------------------------------------------------
  * otn_project       : Z - X sym(X^T Z)                                   project (stiefel.py:23-30)

@@ -11,6 +11,8 @@
 //   EPI_DOT   : C = acc          and  partial[b][tile] = sum acc * R           (d/dt of the norm)
 // Partials are reduced later in a fixed order => bitwise reproducible costs.
 #pragma once
+#include <cstdlib>
+
 #include "otn_common.cuh"
 
 namespace otn {
@@ -33,6 +35,10 @@ struct GemmParams {
     const int* e_index;                      // EPI_RESID: target id per instance (nullptr = 0)
     double* partial;                         // partial sums: partial[b * partial_stride + tile]
     int partial_stride;                      // >= tiles of this launch (several launches may share one row per instance)
+    // fused all-gather of a row-sharded product: every output tile is also stored into the same position of the peers'
+    // result matrices (NVLink peer-mapped pointers, batch == 1)
+    double* Cpeer[7];
+    int npeer;
 };
 
 template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool TA, bool TB>
@@ -177,6 +183,7 @@ gemm_dmma_kernel(const GemmParams p) {
                 part = fma(v.x, e.x, part); part = fma(v.y, e.y, part);
             }
             *reinterpret_cast<double2*>(C + row * D + col) = v;
+            for (int q = 0; q < p.npeer; ++q) *reinterpret_cast<double2*>(p.Cpeer[q] + row * D + col) = v;
         }
     }
     if (p.epi != EPI_NONE) {
@@ -278,9 +285,10 @@ struct GemmPlan {
 
 inline GemmPlan gemm_plan(int D, int rows, int batch) {
     GemmPlan pl;
+    static const int big_tile_min_d = [] { const char* e = getenv("OTN_GEMM_BIG_TILE_MIN_D"); return e ? atoi(e) : (1 << 30); }();   // 64x64 tiles measured faster even at D = 4096 (32.7 vs 30.0 TFLOP/s)
     // 64x64 CTA tiles (4 warps of 32x32, 3 CTAs/SM) measured faster than 128x128 at D = 256 (32.4 vs 28.2 TFLOP/s); the
     // larger tile only pays for big single-instance products where L2 traffic matters (D >= 2048).
-    if (D % 128 == 0 && rows % 128 == 0 && D >= 2048) {
+    if (D % 128 == 0 && rows % 128 == 0 && D >= big_tile_min_d) {
         pl.kind = 1; pl.tiles = (rows / 128) * (D / 128);
     } else if (D % 64 == 0 && rows % 64 == 0) {
         pl.kind = 2; pl.tiles = (rows / 64) * (D / 64);

@@ -1172,6 +1172,61 @@ extern "C" int otn_gemm_rows(const double* A1, const double* B1, const double* A
     return 0;
 }
 
+// Fused product + all-gather: like otn_gemm_rows, and every tile of the row block is also stored into `peers[q]` (the same
+// D x D result buffer on the other GPUs, mapped through CUDA IPC / NVLink peer access), so that no separate collective runs
+// after the product.  The caller orders the steps of a chain with its own barrier.
+extern "C" int otn_gemm_rows_bcast(const double* A1, const double* B1, const double* A2, const double* B2, double* C,
+                                   double* const* peers, int npeer, int D, int row0, int rows, int transA, int transB, int device,
+                                   void* stream) {
+    if (!A1 || !B1 || !C || D < 1 || rows < 1 || row0 < 0 || row0 + rows > D) return fail("bad argument");
+    if ((A2 == nullptr) != (B2 == nullptr)) return fail("A2 and B2 must be given together");
+    if (transA && transB) return fail("A^T B^T is not supported");
+    if (npeer < 0 || npeer > 7 || (npeer > 0 && peers == nullptr)) return fail("npeer must be in [0, 7]");
+    OTN_TRY(use_device(device));
+    DeviceGuard dev_guard__(device);
+    GemmParams p{};
+    p.A1 = A1; p.B1 = B1; p.A2 = A2; p.B2 = B2; p.C = C; p.D = D; p.row0 = row0; p.rows = rows; p.batch = 1; p.epi = EPI_NONE;
+    p.npeer = npeer;
+    for (int q = 0; q < npeer; ++q) p.Cpeer[q] = peers[q];
+    ++g_launches;
+    CUDA_TRY(gemm_launch(p, transA != 0, transB != 0, (cudaStream_t)stream));
+    return 0;
+}
+
+// IPC-shareable device buffers for the peer stores above
+extern "C" int otn_ipc_alloc(long long bytes, int device, void** ptr, unsigned char* handle64) {
+    if (!ptr || !handle64 || bytes <= 0) return fail("bad argument");
+    OTN_TRY(use_device(device));
+    DeviceGuard dev_guard__(device);
+    CUDA_TRY(cudaMalloc(ptr, (size_t)bytes));
+    cudaIpcMemHandle_t hd;
+    CUDA_TRY(cudaIpcGetMemHandle(&hd, *ptr));
+    static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(handle64, &hd, 64);
+    return 0;
+}
+extern "C" int otn_ipc_open(const unsigned char* handle64, int device, void** ptr) {
+    if (!ptr || !handle64) return fail("bad argument");
+    OTN_TRY(use_device(device));
+    DeviceGuard dev_guard__(device);
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, handle64, 64);
+    CUDA_TRY(cudaIpcOpenMemHandle(ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+extern "C" int otn_ipc_close(void* ptr, int device) {
+    OTN_TRY(use_device(device));
+    DeviceGuard dev_guard__(device);
+    CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+    return 0;
+}
+extern "C" int otn_ipc_free(void* ptr, int device) {
+    OTN_TRY(use_device(device));
+    DeviceGuard dev_guard__(device);
+    CUDA_TRY(cudaFree(ptr));
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // trust region
 // ---------------------------------------------------------------------------------------------------------------------

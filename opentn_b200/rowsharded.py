@@ -17,8 +17,22 @@ from . import _lib
 from ._lib import check
 
 
+class _IpcMatrix:
+    """A D x D float64 device buffer allocated by libotn (IPC-shareable), viewable as a torch tensor."""
+
+    def __init__(self, lib, D, device):
+        self.lib, self.D, self.device = lib, D, device
+        self.ptr = C.c_void_p()
+        self.handle = C.create_string_buffer(64)
+        check(lib.otn_ipc_alloc(D * D * 8, device, C.byref(self.ptr), self.handle))
+        self.__cuda_array_interface__ = {"shape": (D, D), "typestr": "<f8", "data": (self.ptr.value, False), "version": 3, "strides": None}
+
+    def tensor(self, torch):
+        return torch.as_tensor(self, device=torch.device("cuda", self.device))
+
+
 class RowShardedChain:
-    def __init__(self, D: int, device=None, group=None):
+    def __init__(self, D: int, device=None, group=None, p2p: bool = False, nbuf: int = 4):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -35,6 +49,59 @@ class RowShardedChain:
         self.device = torch.cuda.current_device() if device is None else device
         self.lib = _lib.load()
         self.products = 0
+        self.p2p = bool(p2p) and self.world > 1
+        if self.p2p:
+            self._setup_p2p(nbuf)
+
+    # ---- fused product + all-gather over NVLink peer memory -----------------------------------------------------------------
+    def _setup_p2p(self, nbuf):
+        """Ring of `nbuf` IPC-shared result buffers per rank; every rank maps the buffers of all the others."""
+        torch, dist = self.torch, self.dist
+        self._bufs = [_IpcMatrix(self.lib, self.D, self.device) for _ in range(nbuf)]
+        self._views = [b.tensor(torch) for b in self._bufs]
+        mine = [bytes(b.handle.raw) for b in self._bufs]
+        allh = [None] * self.world
+        dist.all_gather_object(allh, mine, group=self.group)
+        self._peer_ptrs = []          # per buffer: ctypes array of the other ranks' pointers
+        self._opened = []
+        for i in range(nbuf):
+            arr = (C.c_void_p * 7)()
+            k = 0
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                p = C.c_void_p()
+                check(self.lib.otn_ipc_open(allh[r][i], self.device, C.byref(p)))
+                self._opened.append(p)
+                arr[k] = p.value
+                k += 1
+            self._peer_ptrs.append(arr)
+        self._next = 0
+        dist.barrier(group=self.group)
+
+    def _matmul_p2p(self, A, B, ta, tb, A2=None, B2=None):
+        torch, dist = self.torch, self.dist
+        i = self._next
+        self._next = (self._next + 1) % len(self._bufs)
+        out = self._views[i]
+        st = torch.cuda.current_stream().cuda_stream
+        check(self.lib.otn_gemm_rows_bcast(A.data_ptr(), B.data_ptr(), None if A2 is None else A2.data_ptr(),
+                                           None if B2 is None else B2.data_ptr(), out.data_ptr(), self._peer_ptrs[i], self.world - 1,
+                                           self.D, self.row0, self.rows, int(ta), int(tb), self.device, C.c_void_p(st)))
+        self.products += 1 if A2 is None else 2
+        torch.cuda.current_stream().synchronize()     # my tiles have landed in every peer ...
+        dist.barrier(group=self.group)                # ... and so have everybody else's in mine
+        return out
+
+    def close(self):
+        if getattr(self, "p2p", False):
+            self.dist.barrier(group=self.group)
+            for p in self._opened:
+                self.lib.otn_ipc_close(p, self.device)
+            self._views = []
+            for b in self._bufs:
+                self.lib.otn_ipc_free(b.ptr, self.device)
+            self.p2p = False
 
     # ---- one row-sharded product ------------------------------------------------------------------------------------------
     def _rows(self, A1, B1, C_full, ta=False, tb=False, A2=None, B2=None):
@@ -51,7 +118,11 @@ class RowShardedChain:
         return C_full
 
     def matmul(self, A, B, ta=False, tb=False, gather=True):
-        """op(A) @ op(B): this rank computes its row block; `gather` assembles the full matrix on every rank."""
+        """op(A) @ op(B): this rank computes its row block; `gather` assembles the full matrix on every rank.
+        With p2p=True the gather is fused into the product (peer stores) and the result lives in a ring buffer that is
+        overwritten after `nbuf` further products."""
+        if self.p2p and gather:
+            return self._matmul_p2p(A, B, ta, tb)
         out = self.torch.empty((self.D, self.D), dtype=self.torch.float64, device=A.device)
         self._rows(A, B, out, ta, tb)
         return self._gather(out) if gather else out

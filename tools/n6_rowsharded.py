@@ -27,7 +27,8 @@ for l in range(m):
     yl = T.ortho2super(q)
     Ys.append(torch.from_numpy(T.local2full(yl, 6, 2, shift_pbc=bool(l % 2))).cuda())
 Tre = torch.randn(D, D, dtype=torch.float64, device="cuda") * 0.01
-ch = RowShardedChain(D)
+P2P = os.environ.get('OTN_P2P', '0') == '1'
+ch = RowShardedChain(D, p2p=P2P, nbuf=8)
 def timeit(fn, n=3):
     fn(); torch.cuda.synchronize()
     if world > 1: dist.barrier()
@@ -47,8 +48,9 @@ if rank == 0:
     ref = Ys[2] @ (Ys[1] @ Ys[0])
     err = float((M - ref).abs().max())
     fl = 2 * D ** 3
-    print(f"world={world}: compose (2 products) {ms_c:.2f} ms = {2*fl/ms_c/1e9:.1f} TFLOP/s aggregate, max err vs torch {err:.2e}")
+    print(f"world={world} p2p={P2P}: compose (2 products) {ms_c:.2f} ms = {2*fl/ms_c/1e9:.1f} TFLOP/s aggregate, max err vs torch {err:.2e}")
     print(f"          cost (2 products, last sharded) {ms_f:.2f} ms ; cost + layer cotangents (6 products) {ms_g:.2f} ms = {6*fl/ms_g/1e9:.1f} TFLOP/s")
     print(f"          complex compose (2 complex = 8 real products) {ms_z:.2f} ms = {8*fl/ms_z/1e9:.1f} TFLOP/s ; f = {f:.6f}")
+ch.close()
 if world > 1:
     dist.destroy_process_group()
