@@ -632,7 +632,8 @@ static int export_model(otn_problem* h, int batch, double* Mout) {
 }
 
 // reverse chain on the unscaled residual: G_{l-1} = Y_l^T G_l ; W_l = G_l P_{l-1}^T ; zraw_l = back_assemble(W_l)
-static int back_layer(otn_problem* h, int batch, const int* active, int l, const double* x, bool tangent, const double* eta) {
+static int back_layer(otn_problem* h, int batch, const int* active, int l, const double* x, bool tangent, const double* eta,
+                      bool primal_with_eta = false) {
     // pulls the cotangent of layer l (W_l, and for the tangent pass Wd) back to the isometry
     ProfScope ps(&h->prof, h->stream, CAT_BACK, 4.0 * h->K * (double)h->dim * h->dim * h->dim * h->dim * batch * (tangent ? 2 : 1),
                  (h->model == OTN_MODEL_LOCAL ? 2 : 1) + ((tangent && h->dim >= 8) ? 1 : 0));
@@ -665,18 +666,30 @@ static int back_layer(otn_problem* h, int batch, const int* active, int l, const
     const int dim = h->dim;
     dim3 grid(dim, batch);
     if (h->structured && h->model == OTN_MODEL_FULL) {
-#define BAS_SYM(DIMV, ASV)                                                                                                       \
+#define BAS_SYM(DIMV, ASV, KPV)                                                                                                  \
     do {                                                                                                                         \
-        const size_t sm = BasSymCfg<DIMV, ASV>::smem_bytes(h->K);                                                                \
-        OTN_TRY(set_smem(back_assemble_sym_kernel<DIMV, ASV>, sm));                                                              \
-        if (!tangent) {                                                                                                          \
-            back_assemble_sym_kernel<DIMV, ASV><<<batch * ASV, 256, sm, h->stream>>>(Wsup, sW, x, h->zraw, h->sym, h->K, 0, active, h->m, l);   \
+        const size_t sm1 = BasSym2Cfg<DIMV, ASV, 1, KPV>::SMEM_BYTES, sm2 = BasSym2Cfg<DIMV, ASV, 2, KPV>::SMEM_BYTES;           \
+        OTN_TRY(set_smem(back_assemble_sym2_kernel<DIMV, ASV, 1, KPV>, sm1));                                                    \
+        OTN_TRY(set_smem(back_assemble_sym2_kernel<DIMV, ASV, 2, KPV>, sm2));                                                    \
+        if (!tangent && primal_with_eta) {      /* zraw = A(W) x  and  zdraw = A(W) eta  in one pass over W */                   \
+            back_assemble_sym2_kernel<DIMV, ASV, 2, KPV><<<batch * ASV, 256, sm2, h->stream>>>(Wsup, sW, x, eta, h->zraw, h->zdraw, 0, 0, h->sym, h->K, active, h->m, l); \
+        } else if (!tangent) {                                                                                                   \
+            back_assemble_sym2_kernel<DIMV, ASV, 1, KPV><<<batch * ASV, 256, sm1, h->stream>>>(Wsup, sW, x, nullptr, h->zraw, nullptr, 0, 0, h->sym, h->K, active, h->m, l); \
+        } else if (primal_with_eta) {           /* the W eta part is already in zdraw: only += A(Wd) x */                        \
+            back_assemble_sym2_kernel<DIMV, ASV, 1, KPV><<<batch * ASV, 256, sm1, h->stream>>>(Wdsup, sWds, x, nullptr, h->zdraw, nullptr, 1, 0, h->sym, h->K, active, h->m, l); \
         } else {                                                                                                                 \
-            back_assemble_sym_kernel<DIMV, ASV><<<batch * ASV, 256, sm, h->stream>>>(Wdsup, sWds, x, h->zdraw, h->sym, h->K, 0, active, h->m, l); \
-            back_assemble_sym_kernel<DIMV, ASV><<<batch * ASV, 256, sm, h->stream>>>(Wsup, sW, eta, h->zdraw, h->sym, h->K, 1, active, h->m, l);  \
+            back_assemble_sym2_kernel<DIMV, ASV, 1, KPV><<<batch * ASV, 256, sm1, h->stream>>>(Wdsup, sWds, x, nullptr, h->zdraw, nullptr, 0, 0, h->sym, h->K, active, h->m, l); \
+            back_assemble_sym2_kernel<DIMV, ASV, 1, KPV><<<batch * ASV, 256, sm1, h->stream>>>(Wsup, sW, eta, nullptr, h->zdraw, nullptr, 1, 0, h->sym, h->K, active, h->m, l); \
         }                                                                                                                        \
     } while (0)
-        if (dim == 16) BAS_SYM(16, 2); else BAS_SYM(8, 1);
+#define BAS_SYM_K(DIMV, ASV)                                                                        \
+    do {                                                                                            \
+        const int kp = (h->K + 7) & ~7;                                                             \
+        if (kp == 8) BAS_SYM(DIMV, ASV, 8); else if (kp == 16) BAS_SYM(DIMV, ASV, 16);              \
+        else if (kp == 24) BAS_SYM(DIMV, ASV, 24); else BAS_SYM(DIMV, ASV, 32);                     \
+    } while (0)
+        if (dim == 16) BAS_SYM_K(16, 2); else BAS_SYM_K(8, 1);
+#undef BAS_SYM_K
 #undef BAS_SYM
     } else if (dim == 16 || dim == 8) {
         // streaming kernel, one CTA per instance; tangent = Wd*x then += W*eta
@@ -709,7 +722,7 @@ static int back_layer(otn_problem* h, int batch, const int* active, int l, const
     return 0;
 }
 
-static int reverse_chain(otn_problem* h, int batch, const int* active, const double* x) {
+static int reverse_chain(otn_problem* h, int batch, const int* active, const double* x, const double* eta_joint = nullptr) {
     const long long SZ = h->SZ, S = (long long)h->m * SZ;
     for (int l = h->m - 1; l >= 1; --l) {
         GemmParams p = gp(h, batch, active);                       // W_l = G_l P_{l-1}^T
@@ -722,14 +735,15 @@ static int reverse_chain(otn_problem* h, int batch, const int* active, const dou
         r.B1 = layer_ptr(h->G, l, SZ); r.sB1 = S;
         r.C = layer_ptr(h->G, l - 1, SZ); r.sC = S;
         CUDA_TRY(hgemm(h, r, true, false));
-        OTN_TRY(back_layer(h, batch, active, l, x, false, nullptr));
+        OTN_TRY(back_layer(h, batch, active, l, x, false, eta_joint, eta_joint != nullptr));
     }
-    OTN_TRY(back_layer(h, batch, active, 0, x, false, nullptr));
+    OTN_TRY(back_layer(h, batch, active, 0, x, false, eta_joint, eta_joint != nullptr));
     return 0;
 }
 
 // tangent pass: needs the primal cache (Y, P, G, W, zraw, part_f) of the same x
-static int tangent_pass(otn_problem* h, int batch, const int* active, const double* x, const double* eta, bool layers_built) {
+static int tangent_pass(otn_problem* h, int batch, const int* active, const double* x, const double* eta, bool layers_built,
+                        bool joint = false) {
     const long long SZ = h->SZ, S = (long long)h->m * SZ;
     const int m = h->m;
     if (!layers_built) OTN_TRY(build_layers(h, x, eta, batch, active, false));
@@ -769,11 +783,11 @@ static int tangent_pass(otn_problem* h, int batch, const int* active, const doub
         r.A2 = layer_ptr(h->Y, l, SZ); r.sA2 = S; r.B2 = Ghat; r.sB2 = 2 * SZ;
         r.C = h->Gd + (long long)(1 - cur) * SZ; r.sC = 2 * SZ;
         CUDA_TRY(hgemm(h, r, true, false));
-        OTN_TRY(back_layer(h, batch, active, l, x, true, eta));
+        OTN_TRY(back_layer(h, batch, active, l, x, true, eta, joint));
         cur = 1 - cur;
     }
     h->tr.gd_final = cur;
-    OTN_TRY(back_layer(h, batch, active, 0, x, true, eta));
+    OTN_TRY(back_layer(h, batch, active, 0, x, true, eta, joint));
     return 0;
 }
 
@@ -902,8 +916,9 @@ static int triple_device(otn_problem* h, const double* x, const double* eta, int
     OTN_TRY(build_layers(h, x, eta, batch, nullptr, true));
     OTN_TRY(forward_chain(h, batch, nullptr, false, &tiles));
     h->tr.tiles = tiles;
-    OTN_TRY(reverse_chain(h, batch, nullptr, x));
-    OTN_TRY(tangent_pass(h, batch, nullptr, x, eta, true));
+    const bool joint = h->structured && h->model == OTN_MODEL_FULL;   // W_l is pulled back against x and eta in one pass
+    OTN_TRY(reverse_chain(h, batch, nullptr, x, joint ? eta : nullptr));
+    OTN_TRY(tangent_pass(h, batch, nullptr, x, eta, true, joint));
     OTN_TRY(riem_launch(h, batch, nullptr, tiles, x, eta, true, f, rgrad, nullptr, heta));
     return 0;
 }
@@ -926,9 +941,13 @@ static int triple_pipelined(otn_problem* h, const double* x, const double* eta, 
     const size_t slot_doubles = 4 * (size_t)C * per + C;
     OTN_TRY(h->pipe_buf.ensure(2 * slot_doubles * 8));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    // (copies are not the bottleneck: PCIe moves the 403 MB of a step in 4.2 ms, both directions overlapped; a ramped chunk
+    // schedule with short first/last chunks was measured and did not help -- what remains is the lower kernel efficiency of
+    // 256-instance launches)
     const int nchunks = (batch + C - 1) / C;
+    int b0 = 0;
     for (int c = 0; c < nchunks; ++c) {
-        const int slot = c & 1, b0 = c * C, nb = std::min(C, batch - b0);
+        const int slot = c & 1, nb = std::min(C, batch - b0);
         double* base = h->pipe_buf.as<double>() + slot * slot_doubles;
         double *dx = base, *de = dx + (size_t)C * per, *dg = de + (size_t)C * per, *dh = dg + (size_t)C * per, *df = dh + (size_t)C * per;
         if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_done[slot], 0));          // kernels of chunk c-2 finished reading dx/de
@@ -944,6 +963,7 @@ static int triple_pipelined(otn_problem* h, const double* x, const double* eta, 
         if (rgrad) CUDA_TRY(cudaMemcpyAsync(rgrad + (size_t)b0 * per, dg, nb * per * 8, cudaMemcpyDeviceToHost, h->s_out));
         if (heta) CUDA_TRY(cudaMemcpyAsync(heta + (size_t)b0 * per, dh, nb * per * 8, cudaMemcpyDeviceToHost, h->s_out));
         CUDA_TRY(cudaEventRecord(h->ev_out[slot], h->s_out));
+        b0 += nb;
     }
     CUDA_TRY(cudaStreamSynchronize(h->s_in));
     CUDA_TRY(cudaStreamSynchronize(h->stream));

@@ -232,6 +232,139 @@ __global__ void __launch_bounds__(256) back_assemble_sym_kernel(const double* __
     }
 }
 
+// ---- adjoint of the assembly from cotangent blocks, second version ------------------------------------------------------
+// Differences to back_assemble_sym_kernel: (i) the A fragments are decoded straight from the staged block rows into registers
+// (no dense tile, one barrier per stage instead of two); (ii) up to two right-hand sides share one pass over W
+// (out1 (+)= A u1, out2 (+)= A u2): in a joint (f, rgrad, H eta) evaluation the primal cotangent W is needed against both x
+// (gradient) and eta (tangent of the adjoint), so 9 streaming passes per step become 6; (iii) the right-hand sides live
+// unpadded in shared memory behind an XOR swizzle, which lets two CTAs share an SM.
+template <int DIM, int AS, int NRHS, int KP>
+struct BasSym2Cfg {
+    static constexpr int STAGES = 3, D2 = DIM * DIM, DA = DIM / AS;
+    static constexpr int RAW = DA * D2;
+    static constexpr size_t SMEM_BYTES = (size_t)(STAGES * RAW + NRHS * DIM * KP * DIM) * 8;
+};
+
+// KP = Kraus rank rounded up to a multiple of 8 (compile time, so that every shared-memory offset of the inner loop folds into
+// an immediate; the first version recomputed the swizzled addresses per DMMA and spent 2/3 of its instructions on integer math).
+template <int DIM, int AS, int NRHS, int KP>
+__global__ void __launch_bounds__(256) back_assemble_sym2_kernel(const double* __restrict__ W, long long w_stride,
+                                                                 const double* __restrict__ u1, const double* __restrict__ u2,
+                                                                 double* __restrict__ out1, double* __restrict__ out2, int acc1, int acc2,
+                                                                 SymLayout L, int K, const int* active, int m, int layer) {
+    using Cfg = BasSym2Cfg<DIM, AS, NRHS, KP>;
+    constexpr int D2 = Cfg::D2, ST = Cfg::STAGES, DA = Cfg::DA, NS = DIM * (DIM + 1) / 2, NA = DIM * (DIM - 1) / 2;
+    constexpr int MI = DIM / 8, DQ = DIM / 4, SWZ = DIM / 4 - 1, NI = KP / 8, NJ = NRHS * NI;
+    constexpr int USB = NRHS * KP * DIM;                 // doubles of the right-hand sides per b
+    static_assert(DA == 8, "one a value per warp");
+    extern __shared__ __align__(16) double sm[];
+    const int inst = blockIdx.x / AS, a_lo = (blockIdx.x - inst * AS) * DA;
+    if (active != nullptr && active[inst] == 0) return;
+    const int item = inst * m + layer;
+    double* raw = sm;
+    double* us = raw + ST * Cfg::RAW;           // [b][rhs][k][DIM], 4-column groups XOR-swizzled by (k & SWZ)
+    const long long np = (long long)DIM * K * DIM;
+    const double* Ws = W + (long long)inst * w_stride;
+    const double* Wa = Ws + L.off_a;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+
+    // right-hand sides: asynchronous 16-byte copies (a swizzled 4-column group keeps its two halves contiguous)
+    for (int i = tid; i < DIM * NRHS * KP * (DIM / 2); i += 256) {
+        const int rr = i / (DIM / 2), ch = i - rr * (DIM / 2);          // rr = (b * NRHS + rhs) * KP + k
+        const int k = rr % KP, br = rr / KP, rhs = br % NRHS, bb = br / NRHS;
+        const int c = 2 * ch;
+        double* dst = us + rr * DIM + (c ^ ((k & SWZ) << 2));
+        if (k < K) {
+            const double* u = (NRHS == 2 && rhs == 1) ? u2 : u1;
+            cp_async16(dst, u + (long long)item * np + (bb * K + k) * DIM + c);
+        } else { dst[0] = 0.0; dst[1] = 0.0; }
+    }
+    auto load_stage = [&](int b, int s) {
+        double* dst = raw + s * Cfg::RAW;
+        constexpr int CS = NS / 2, CA = NA / 2;
+        for (int id = tid; id < DA * (CS + CA); id += 256) {
+            const int al = id / (CS + CA), ch = id - al * (CS + CA), a = a_lo + al;
+            const int lo = a < b ? a : b, hi = a < b ? b : a;
+            if (ch < CS) cp_async16(dst + al * D2 + 2 * ch, Ws + (long long)pair_s(lo, hi, DIM) * L.Ds + 2 * ch);
+            else if (a != b) cp_async16(dst + al * D2 + NS + 2 * (ch - CS), Wa + (long long)pair_a(lo, hi, DIM) * L.Da + 2 * (ch - CS));
+        }
+    };
+    load_stage(0, 0);
+    cp_async_commit();                                   // group 0: right-hand sides + stage 0
+#pragma unroll
+    for (int s = 1; s < ST - 1; ++s) { load_stage(s, s); cp_async_commit(); }
+
+    // per-lane decode constants: fragment element (row c_i = i*8+g, column d = dq*4+t)
+    int ixs[MI][DQ], ixa[MI][DQ];
+    double cfd[MI][DQ], scd[MI][DQ];
+    const double s2 = 1.41421356237309504880;
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int dq = 0; dq < DQ; ++dq) {
+            const int c = i * 8 + g, dd = dq * 4 + t, lo = c < dd ? c : dd, hi = c < dd ? dd : c;
+            ixs[i][dq] = pair_s(lo, hi, DIM);
+            ixa[i][dq] = (c == dd) ? NS : NS + pair_a(lo, hi, DIM);
+            cfd[i][dq] = (c == dd) ? s2 : 1.0;
+            scd[i][dq] = (c == dd) ? 0.0 : ((c < dd) ? 1.0 : -1.0);
+        }
+    // swizzled column offset of this lane inside a right-hand-side row: ((dq*4 + t) ^ ((g & SWZ) << 2))
+    int dsw[DQ];
+#pragma unroll
+    for (int dq = 0; dq < DQ; ++dq) dsw[dq] = g * DIM + (((dq ^ (g & SWZ)) << 2) + t);
+    double acc[MI][NJ][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int a = a_lo + warp;
+
+    for (int b = 0; b < DIM; ++b) {
+        cp_async_wait<ST - 2>();
+        __syncthreads();                                   // stage b landed; stage b-1 fully consumed by every warp
+        if (b + ST - 1 < DIM) load_stage(b + ST - 1, (b + ST - 1) % ST);
+        cp_async_commit();
+        const double* R = raw + (b % ST) * Cfg::RAW + warp * D2;
+        const double* ub = us + b * USB;
+        const double nab = (a == b) ? s2 : 1.0;
+        const double sgo = (a == b) ? 0.0 : ((a < b) ? 1.0 : -1.0);   // sign of the antisymmetric part (0 on the diagonal: no Wa row staged)
+#pragma unroll
+        for (int dq = 0; dq < DQ; ++dq) {
+            double wa[MI];
+#pragma unroll
+            for (int i = 0; i < MI; ++i) {
+                const double ra = (a == b) ? 0.0 : R[ixa[i][dq]];
+                wa[i] = fma(sgo * scd[i][dq], ra, nab * cfd[i][dq] * R[ixs[i][dq]]);
+            }
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const double uv = ub[((j / NI) * KP + (j % NI) * 8) * DIM + dsw[dq]];
+#pragma unroll
+                for (int i = 0; i < MI; ++i) dmma884(acc[i][j][0], acc[i][j][1], wa[i], uv);
+            }
+        }
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+        const int c = i * 8 + g;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int rhs = j / NI;
+            double* out = (NRHS == 2 && rhs == 1) ? out2 : out1;
+            const int accm = (NRHS == 2 && rhs == 1) ? acc2 : acc1;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int k = (j % NI) * 8 + 2 * t + e;
+                if (k < K) {
+                    const long long og = (long long)item * np + (a * K + k) * DIM + c;
+                    out[og] = accm ? out[og] + acc[i][j][e] : acc[i][j][e];
+                }
+            }
+        }
+    }
+}
+
 // ---- blocks -> dense superoperator (otn_model in structured mode) ------------------------------------------------------
 //   M[(a,b),(c,d)] = cs_ab cs_cd Ms[{ab},{cd}] + ca_ab ca_cd Ma[{ab},{cd}],  cs = 1 (a==b) else 1/sqrt2,  ca = +-1/sqrt2, 0 on a==b
 __global__ void unblock_kernel(const double* __restrict__ blocks, long long in_stride, double* __restrict__ M, SymLayout L, int batch) {
