@@ -511,7 +511,7 @@ static int build_layers(otn_problem* h, const double* x, const double* eta, int 
     dim3 grid(h->dim, items);
     if (h->structured && h->model == OTN_MODEL_FULL) {
         const int Kp = (h->K + 3) & ~3;
-        const size_t sm = ((size_t)h->dim * Kp * (h->dim + 4) * (tangent ? 2 : 1) + (size_t)8 * 2 * h->dim * (h->dim + 1)) * 8;
+        const size_t sm = ((size_t)h->dim * Kp * h->dim * (tangent ? 2 : 1) + (size_t)8 * 2 * h->dim * (h->dim + 1)) * 8;
 #define ASM_SYM(DIMV, TG, PR)                                                                                        \
     do {                                                                                                             \
         OTN_TRY(set_smem(assemble_sym_kernel<DIMV, TG, PR>, sm));                                                    \

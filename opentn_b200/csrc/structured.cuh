@@ -35,7 +35,9 @@ __global__ void __launch_bounds__(256) assemble_sym_kernel(const double* __restr
                                                            double* __restrict__ Y, double* __restrict__ Yd, SymLayout L, int K,
                                                            const int* active, int m) {
     extern __shared__ __align__(16) double sm[];
-    constexpr int LD = DIM + 4, MI = DIM / 8, LS = DIM + 1, NS = DIM * (DIM + 1) / 2;
+    // x / eta live unpadded in shared memory, 4-column groups XOR-swizzled by (row & SWZ): conflict-free fragment loads at
+    // 64 KB instead of 80 KB, which lets two CTAs share an SM
+    constexpr int LD = DIM, SWZ = DIM / 4 - 1, MI = DIM / 8, LS = DIM + 1, NS = DIM * (DIM + 1) / 2;
     const int item = blockIdx.x;
     if (active != nullptr && active[item / m] == 0) return;
     const int Kp = (K + 3) & ~3, rows = DIM * Kp;
@@ -47,8 +49,9 @@ __global__ void __launch_bounds__(256) assemble_sym_kernel(const double* __restr
     for (int i = threadIdx.x; i < rows * DIM; i += 256) {
         const int r = i / DIM, c = i - r * DIM, aa = r / Kp, k = r - aa * Kp;
         const bool ok = k < K;
-        xs[r * LD + c] = ok ? x[(long long)item * np + (aa * K + k) * DIM + c] : 0.0;
-        if (TANGENT) es[r * LD + c] = ok ? eta[(long long)item * np + (aa * K + k) * DIM + c] : 0.0;
+        const int o = r * LD + (c ^ ((r & SWZ) << 2));
+        xs[o] = ok ? x[(long long)item * np + (aa * K + k) * DIM + c] : 0.0;
+        if (TANGENT) es[o] = ok ? eta[(long long)item * np + (aa * K + k) * DIM + c] : 0.0;
     }
     for (int i = threadIdx.x; i < DIM * DIM; i += 256) {
         const int c = i / DIM, dd = i - c * DIM;
@@ -76,9 +79,11 @@ __global__ void __launch_bounds__(256) assemble_sym_kernel(const double* __restr
             double xa[MI], xb[MI], ea[MI], eb[MI];
 #pragma unroll
             for (int i = 0; i < MI; ++i) {
-                xa[i] = xs[(a * Kp + kk + t) * LD + i * 8 + g];
-                xb[i] = xs[(b * Kp + kk + t) * LD + i * 8 + g];
-                if (TANGENT) { ea[i] = es[(a * Kp + kk + t) * LD + i * 8 + g]; eb[i] = es[(b * Kp + kk + t) * LD + i * 8 + g]; }
+                // rows a*Kp+kk+t and b*Kp+kk+t: Kp and kk are multiples of 4, so (row & SWZ) == t (SWZ <= 3)
+                const int col = (i * 8 + g) ^ ((t & SWZ) << 2);
+                xa[i] = xs[(a * Kp + kk + t) * LD + col];
+                xb[i] = xs[(b * Kp + kk + t) * LD + col];
+                if (TANGENT) { ea[i] = es[(a * Kp + kk + t) * LD + col]; eb[i] = es[(b * Kp + kk + t) * LD + col]; }
             }
 #pragma unroll
             for (int i = 0; i < MI; ++i)
