@@ -92,38 +92,60 @@ def _cpu_worker(args):
     return time.perf_counter() - t0, acc
 
 
-def cpu_triples_per_sec(sample_per_core=16, cores=None):
-    """Throughput of the oracle port: one instance per process, min(B, cores) processes, 1 BLAS thread each
-    (BASELINE.md section 3 protocol)."""
-    import multiprocessing as mp
-    cores = cores or os.cpu_count() or 1
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, [(0, 1)] * cores)  # spawn + import warm-up
+class CpuPool:
+    """Worker pool for the oracle port: one instance per process, min(B, cores) processes, 1 BLAS thread each
+    (BASELINE.md section 3 protocol).  Spawned once; every `run` is one bounded sample."""
+
+    def __init__(self, cores=None):
+        import multiprocessing as mp
+        self.cores = cores or os.cpu_count() or 1
+        self.pool = mp.get_context("spawn").Pool(self.cores)
+        self.pool.map(_cpu_worker, [(0, 1)] * self.cores)  # spawn + import + BLAS warm-up
+        self.offset = 0
+
+    def run(self, sample_per_core):
         t0 = time.perf_counter()
-        res = pool.map(_cpu_worker, [(c * sample_per_core, sample_per_core) for c in range(cores)])
+        res = self.pool.map(_cpu_worker, [(self.offset + c * sample_per_core, sample_per_core) for c in range(self.cores)])
         wall = time.perf_counter() - t0
-    inner = max(r[0] for r in res)
-    total = cores * sample_per_core
-    return total / inner, cores, total, wall
+        self.offset = (self.offset + self.cores * sample_per_core) % 4096
+        inner = max(r[0] for r in res)
+        total = self.cores * sample_per_core
+        return total / inner, total, wall
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_triples_per_sec(sample_per_core=16, cores=None):
+    pool = CpuPool(cores)
+    try:
+        v, total, wall = pool.run(sample_per_core)
+    finally:
+        pool.close()
+    return v, pool.cores, total, wall
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
-    per_core = 32
-    values = []
-    for _ in range(min(args.warmup, 1)):
-        cpu_triples_per_sec(2, cores)
-    t_ms = []
-    for _ in range(args.steps):
-        v, c, total, wall = cpu_triples_per_sec(per_core, cores)
-        values.append(v)
-        t_ms.append(1e3 * total / v)
+    per_core = 16
+    pool = CpuPool()
+    cores = pool.cores
+    try:
+        for _ in range(args.warmup):
+            pool.run(2)
+        values, t_ms = [], []
+        for _ in range(args.steps):
+            v, total, wall = pool.run(per_core)
+            values.append(v)
+            t_ms.append(1e3 * total / v)
+    finally:
+        pool.close()
     v = statistics.median(values)
-    sample = f"{cores * per_core} instances of C3 per step ({per_core} per process x {cores} processes, 1 BLAS thread each)"
+    sample = (f"{cores * per_core} instances of C3 per step ({per_core} per process x {cores} processes, 1 BLAS thread each); "
+              f"value = median over {args.steps} steps")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": statistics.median(t_ms), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -131,7 +153,7 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference = opentn's algorithm restated in NumPy (oracle/port.py; JAX is not installable here), "
-                    "matrix-free HVP (BASELINE.md baseline (ii))"}
+                    "matrix-free HVP (BASELINE.md baseline (ii)); CPU work does not scale with --gpus"}
     print(json.dumps(line))
     return 0
 

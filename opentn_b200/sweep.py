@@ -1,0 +1,64 @@
+"""tau x Kraus-rank x seed sweeps of 2-site trust-region fits (BASELINE config 4), sharded by instance.
+
+An instance = (model Lindbladian, tau, K, seed).  Instances are grouped by K (a batch must share the isometry shape), every
+group is one `StiefelFit` with one target per tau and a per-instance target index, each rank runs `b mod world == rank`
+of every group on its GPU with the batched device solver, and the only collective is the final all-gather of costs, status
+flags and isometries (`opentn_b200.sharding`)."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import transformations as T
+from .fit import StiefelFit
+from .optimization import get_general_trotter_local_ansatz
+from .stiefel import polar_decomposition_rectangular, project
+
+
+def kicked_start(xs0, seed, kick=1e-2):
+    """Trotter starting point retracted after a random tangent kick of canonical norm `kick` (default_rng(seed))."""
+    rng = np.random.default_rng(seed)
+    eta = np.stack([rng.standard_normal(x.shape) for x in xs0])
+    xs0 = np.stack(xs0)
+    eta = project(xs0, eta)
+    xte = np.swapaxes(xs0, -1, -2) @ eta
+    nrm = np.sqrt(np.sum(eta * eta) - 0.5 * np.sum(xte * xte))
+    return polar_decomposition_rectangular(xs0, eta * (kick / nrm))
+
+
+def run_sweep(lindbladians, N, d, taus, ranks, seeds, n_steps=4, niter=10, device=0, rank=0, world=1, pbc=True, max_batch=1024,
+              gather=None):
+    """Returns {K: dict(tau_index, seed, f0, f_final, x_final, status)} for the instances owned by `rank` (or, with
+    `gather` = a function like sharding.gather_instances, for all instances on every rank)."""
+    import torch
+    Lvec = T.create_2local_liouvillians(lindbladians, N, d, pbc=pbc)[0]
+    targets = np.stack([T.exp_operator_dt(Lvec, tau) for tau in taus])
+    out = {}
+    for K in ranks:
+        starts = [np.stack([T.super2ortho(x.real, rank=K) for x in get_general_trotter_local_ansatz(lindbladians, tau, n_steps)])
+                  for tau in taus]
+        inst = [(ti, s) for ti in range(len(taus)) for s in seeds]
+        mine = inst[rank::world]
+        if not mine:
+            continue
+        xs = np.stack([kicked_start(list(starts[ti]), s) for ti, s in mine])
+        tindex = np.array([ti for ti, _ in mine], dtype=np.int32)
+        xf = np.empty_like(xs)
+        f0 = np.empty(len(mine)); ff = np.empty(len(mine)); status = np.zeros(len(mine), dtype=np.int32)
+        for c0 in range(0, len(mine), max_batch):
+            sl = slice(c0, min(c0 + max_batch, len(mine)))
+            fit = StiefelFit(targets, model="local", N=N, d=d, metric="canonical", max_batch=sl.stop - sl.start, device=device)
+            fit.set_target_index(tindex[sl])
+            xd = torch.from_numpy(xs[sl]).to(torch.device("cuda", device))
+            xe, rep = fit.tr_run(xd, niter=niter)
+            ff[sl] = fit.cost(xe).cpu().numpy()
+            f0[sl] = rep["f_iter"][0]
+            status[sl] = rep["status"]
+            xf[sl] = xe.cpu().numpy()
+            fit.close()
+        res = dict(tau_index=tindex, seed=np.array([s for _, s in mine]), f0=f0, f_final=ff, x_final=xf, status=status)
+        if gather is not None:
+            total = len(inst)
+            dev = torch.device("cuda", device)
+            res = {k: gather(torch.from_numpy(np.ascontiguousarray(v)).to(dev), total).cpu().numpy() for k, v in res.items()}
+        out[K] = res
+    return out

@@ -93,3 +93,24 @@ def test_host_loop_mirror(P, c1, goldens):
     assert radius == 0.1 or radius == 0.08 or radius > 0
     assert len(xs) == 5
     f_stiefel.close()
+
+
+def test_sweep_driver_small(P):
+    """Reduced config-4 sweep (2 taus x 2 ranks x 3 seeds, 2 TR iterations): runs through the sharding-aware driver and every
+    instance's first cost equals the oracle's cost at its kicked starting point."""
+    from opentn_b200 import sweep
+    from opentn_b200 import transformations as T
+    Lnn = [T.get_kitaev_nn_linbladian(1.0)]
+    taus, ranks, seeds = [0.5, 1.0], [2, 4], [0, 1, 2]
+    res = sweep.run_sweep(Lnn, N, d, taus, ranks, seeds, n_steps=1, niter=2)
+    Lvec = P.create_2local_liouvillians(P.get_kitaev_nn_linbladian(1.0), N, d, pbc=True)[0]
+    for K in ranks:
+        r = res[K]
+        assert len(r["f0"]) == 6 and (r["status"] == 0).all()
+        assert (r["f_final"] <= r["f0"] * (1 + 1e-12)).all()
+        for i in (0, 5):
+            tau = taus[r["tau_index"][i]]
+            xs0 = [P.super2ortho(x.real, rank=K) for x in P.get_general_trotter_local_ansatz([P.get_kitaev_nn_linbladian(1.0)], tau, 1)]
+            x0 = sweep.kicked_start(xs0, int(r["seed"][i]))
+            f = P.CostSpec(P.exp_operator_dt(Lvec, tau), "local", N, d)(list(x0))
+            assert abs(f - r["f0"][i]) / f < 1e-10
