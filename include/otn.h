@@ -125,6 +125,13 @@ int otn_project(const double* x, const double* z, int count, int n, int p, doubl
 int otn_rgrad_map(const double* x, const double* z, int count, int n, int p, double alpha0, double alpha1, double* out, int device);
 int otn_retract(const double* x, const double* eta, int count, int n, int p, double* out, int* status, int device);
 int otn_canonical_dot(const double* x, const double* a, const double* b, int batch, int m, int n, int p, double* out, int device);
+/* otn_connection : D_nu + X (eta^T nu + nu^T eta)/2 + ((a0-a1)/a0)(I - X X^T)(eta nu^T + nu eta^T) X   riemannian_connection
+ *                  (stiefel.py:468-475), `count` isometries at once
+ * otn_frobenius  : out[c] = || A_c - (B_re_c + i B_im_c) ||_F  (squared if asked; B_im may be NULL)   frobenius_norm
+ *                  (optimization.py:56-61) for `count` pairs of n-element arrays */
+int otn_connection(const double* dnu, const double* nu, const double* eta, const double* x, int count, int n, int p, double alpha0,
+                   double alpha1, double* out, int device);
+int otn_frobenius(const double* A, const double* B_re, const double* B_im, int count, long long n, int squared, double* out, int device);
 
 /* ---- optimiser layer --------------------------------------------------------------------------------------------------
  * Batched Riemannian trust region (Absil Alg. 10) with Steihaug truncated CG (Alg. 11), one independent run per instance,

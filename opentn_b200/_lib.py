@@ -68,6 +68,8 @@ SIGNATURES = {
     "otn_rgrad_map": (C.c_int, [_dp, _dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _dp, C.c_int]),
     "otn_retract": (C.c_int, [_dp, _dp, C.c_int, C.c_int, C.c_int, _dp, _ip, C.c_int]),
     "otn_canonical_dot": (C.c_int, [_dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int]),
+    "otn_connection": (C.c_int, [_dp, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _dp, C.c_int]),
+    "otn_frobenius": (C.c_int, [_dp, _dp, _dp, C.c_int, C.c_longlong, C.c_int, _dp, C.c_int]),
     "otn_tr_default_params": (None, [C.POINTER(TrParams)]),
     "otn_tr_run": (C.c_int, [C.c_void_p, _dp, C.c_int, C.POINTER(TrParams), C.POINTER(TrReport)]),
 }

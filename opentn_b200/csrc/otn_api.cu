@@ -1152,6 +1152,51 @@ extern "C" int otn_retract(const double* x, const double* eta, int count, int n,
     return 0;
 }
 
+extern "C" int otn_connection(const double* dnu, const double* nu, const double* eta, const double* x, int count, int n, int p,
+                              double alpha0, double alpha1, double* out, int device) {
+    if (!dnu || !nu || !eta || !x || !out || count < 1 || n < p || p < 1) return fail("bad argument");
+    if (p > ST_MAXP) return fail("p = %d > %d not supported", p, ST_MAXP);
+    if (!(alpha0 > 0.0)) return fail("alpha0 must be positive");
+    OTN_TRY(use_device(device));
+    DeviceGuard dev_guard__(device);
+    Scratch& S = g_scratch[device];
+    const size_t bytes = (size_t)count * n * p * 8;
+    const void *dd, *nd, *ed, *xd; void* od;
+    static thread_local DevBuf extra;
+    OTN_TRY(stage_in(dnu, bytes, S.a, 0, &dd));
+    OTN_TRY(stage_in(nu, bytes, S.b, 0, &nd));
+    OTN_TRY(stage_in(eta, bytes, S.c, 0, &ed));
+    OTN_TRY(stage_in(x, bytes, extra, 0, &xd));
+    OTN_TRY(stage_out(out, bytes, S.o, &od));
+    const size_t sm = (4 * (size_t)n * p + 5 * (size_t)p * p) * 8;
+    OTN_TRY(set_smem(connection_kernel, sm));
+    connection_kernel<<<count, ST_THREADS, sm>>>((const double*)dd, (const double*)nd, (const double*)ed, (const double*)xd, (double*)od,
+                                                 n, p, (alpha0 - alpha1) / alpha0);
+    CUDA_TRY(cudaGetLastError());
+    OTN_TRY(finish_out(out, od, bytes, 0));
+    CUDA_TRY(cudaDeviceSynchronize());
+    return 0;
+}
+
+extern "C" int otn_frobenius(const double* A, const double* B_re, const double* B_im, int count, long long n, int squared, double* out,
+                             int device) {
+    if (!A || !B_re || !out || count < 1 || n < 1) return fail("bad argument");
+    OTN_TRY(use_device(device));
+    DeviceGuard dev_guard__(device);
+    Scratch& S = g_scratch[device];
+    const size_t bytes = (size_t)count * n * 8;
+    const void *ad, *brd, *bid; void* od;
+    OTN_TRY(stage_in(A, bytes, S.a, 0, &ad));
+    OTN_TRY(stage_in(B_re, bytes, S.b, 0, &brd));
+    OTN_TRY(stage_in(B_im, bytes, S.c, 0, &bid));
+    OTN_TRY(stage_out(out, (size_t)count * 8, S.o, &od));
+    frobenius_kernel<<<count, 256>>>((const double*)ad, (const double*)brd, (const double*)bid, n, squared, (double*)od);
+    CUDA_TRY(cudaGetLastError());
+    OTN_TRY(finish_out(out, od, (size_t)count * 8, 0));
+    CUDA_TRY(cudaDeviceSynchronize());
+    return 0;
+}
+
 extern "C" int otn_canonical_dot(const double* x, const double* a, const double* b, int batch, int m, int n, int p, double* out, int device) {
     if (!x || !a || !b || !out || batch < 1 || m < 1 || n < p || p < 1) return fail("bad argument");
     if (p > ST_MAXP) return fail("p = %d > %d not supported", p, ST_MAXP);

@@ -696,3 +696,67 @@ __global__ void __launch_bounds__(ST_THREADS) retract_mma_kernel(const double* _
 }
 
 }  // namespace otn
+
+namespace otn {
+
+// riemannian_connection (stiefel.py:468-475):  D_nu + X (eta^T nu + nu^T eta)/2 + kap (I - X X^T)(eta nu^T + nu eta^T) X
+// one CTA per isometry, any p <= ST_MAXP (CUDA cores; the fused HVP epilogue riem_*_kernel is the hot-path version)
+__global__ void __launch_bounds__(ST_THREADS) connection_kernel(const double* __restrict__ dnu, const double* __restrict__ nu,
+                                                                const double* __restrict__ eta, const double* __restrict__ x,
+                                                                double* __restrict__ out, int n, int p, double kap) {
+    extern __shared__ __align__(16) double sm[];
+    const int np = n * p, pp = p * p;
+    double* X = sm;
+    double* E = X + np;
+    double* Nu = E + np;
+    double* Z = Nu + np;
+    double* EN = Z + np;
+    double* XN = EN + pp;
+    double* XE = XN + pp;
+    double* T0 = XE + pp;
+    double* T1 = T0 + pp;
+    const long long base = (long long)blockIdx.x * np;
+    for (int i = threadIdx.x; i < np; i += ST_THREADS) { X[i] = x[base + i]; E[i] = eta[base + i]; Nu[i] = nu[base + i]; Z[i] = dnu[base + i]; }
+    __syncthreads();
+    gram(E, Nu, EN, n, p); gram(X, Nu, XN, n, p); gram(X, E, XE, n, p);
+    __syncthreads();
+    for (int o = threadIdx.x; o < pp; o += ST_THREADS) {
+        const int i = o / p, j = o - i * p;
+        double s = 0.0;
+        for (int k = 0; k < p; ++k) s += XE[i * p + k] * XN[j * p + k] + XN[i * p + k] * XE[j * p + k];
+        T0[o] = 0.5 * (EN[o] + EN[j * p + i]) - kap * s;
+    }
+    __syncthreads();
+    addmul<false>(Z, 1.0, X, T0, n, p);
+    __syncthreads();
+    for (int o = threadIdx.x; o < pp; o += ST_THREADS) { T0[o] = kap * XN[o]; T1[o] = kap * XE[o]; }
+    __syncthreads();
+    addmul<true>(Z, 1.0, E, T0, n, p);
+    __syncthreads();
+    addmul<true>(Z, 1.0, Nu, T1, n, p);
+    __syncthreads();
+    for (int i = threadIdx.x; i < np; i += ST_THREADS) out[base + i] = Z[i];
+}
+
+// || A - (B_re + i B_im) ||_F (squared if asked) for `count` pairs of length-n arrays; A real (frobenius_norm, optimization.py:56-61)
+__global__ void __launch_bounds__(256) frobenius_kernel(const double* __restrict__ A, const double* __restrict__ Bre,
+                                                        const double* __restrict__ Bim, long long n, int squared, double* __restrict__ out) {
+    __shared__ double red[8];
+    const long long base = (long long)blockIdx.x * n;
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < n; i += 256) {
+        const double r = A[base + i] - Bre[base + i];
+        s = fma(r, r, s);
+        if (Bim != nullptr) { const double im = Bim[base + i]; s = fma(im, im, s); }
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        out[blockIdx.x] = squared ? t : sqrt(t);
+    }
+}
+
+}  // namespace otn

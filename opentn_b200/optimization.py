@@ -39,11 +39,25 @@ def model_Ys_stiefel(xs) -> np.ndarray:
 
 
 def frobenius_norm(A, B, squared: bool = False):
-    """|| A - B ||_F (squared if asked), optimization.py:56-61.  A plain host reduction: inside a fit the residual norm is
-    fused into the last chain GEMM on the device (StiefelFit.cost)."""
-    r = np.asarray(A) - np.asarray(B)
-    s = float(np.sum(r.real ** 2) + (np.sum(r.imag ** 2) if np.iscomplexobj(r) else 0.0))
-    return s if squared else float(np.sqrt(s))
+    """|| A - B ||_F (squared if asked), optimization.py:56-61: A real (a model matrix), B real or complex (a target).  GPU
+    reduction; inside a fit the residual norm is fused into the last chain GEMM instead (StiefelFit.cost)."""
+    from . import _lib
+    from . import transformations as _T
+    A = np.asarray(A)
+    B = np.asarray(B)
+    if np.iscomplexobj(A):
+        if np.abs(A.imag).max() > 0:
+            raise NotImplementedError("frobenius_norm: the first argument (model) must be real on the accelerated path")
+        A = A.real
+    a = _lib.as_f64(A).reshape(-1)
+    bre = _lib.as_f64(B.real).reshape(-1)
+    bim = _lib.as_f64(B.imag).reshape(-1) if np.iscomplexobj(B) else None
+    if a.shape != bre.shape:
+        raise ValueError("operands could not be broadcast together")
+    out = np.empty(1)
+    _lib.check(_lib.load().otn_frobenius(_lib.ptr(a), _lib.ptr(bre), _lib.ptr(bim), 1, a.size, int(bool(squared)), _lib.ptr(out),
+                                         _T._DEVICE))
+    return float(out[0])
 
 
 def get_general_trotter_local_ansatz(lindbladians, tau, n: int):

@@ -160,12 +160,14 @@ polar_decomposition_stiefel = polar_decomposition_rectangular  # stiefel.py:312-
 
 
 def riemannian_connection(D_nu, nu, eta, x, alpha0=1, alpha1=1):
-    """stiefel.py:468-475.  Thin host expression over small (n,p) arrays, kept for signature compatibility; inside the
-    accelerated HVP the connection is fused into `riem_kernel` (csrc/stiefel.cuh)."""
-    x = np.asarray(x)
-    sym = eta.T @ nu + nu.T @ eta
-    M = (eta @ (nu.T @ x) + nu @ (eta.T @ x))
-    return D_nu + 0.5 * x @ sym + ((alpha0 - alpha1) / alpha0) * (M - x @ (x.T @ M))
+    """stiefel.py:468-475 (GPU; accepts stacks).  Inside the accelerated HVP the connection is fused into the epilogue
+    kernel (csrc/stiefel.cuh: riem_mma_kernel)."""
+    xb, lead, n, p = _batched(x)
+    out = np.empty_like(xb)
+    check(_lib.load().otn_connection(ptr(as_f64(D_nu).reshape(xb.shape)), ptr(as_f64(nu).reshape(xb.shape)),
+                                     ptr(as_f64(eta).reshape(xb.shape)), ptr(xb), xb.shape[0], n, p, float(alpha0), float(alpha1),
+                                     ptr(out), _dev()))
+    return out.reshape(lead + (n, p))
 
 
 # ---- coefficient basis (host glue) --------------------------------------------------------------------------------------
