@@ -103,7 +103,9 @@ static int finish_out(void* dst, const void* dev, size_t bytes, cudaStream_t st)
 
 template <class K>
 static int set_smem(K kern, size_t bytes) {
-    if (bytes > 227 * 1024) return fail("kernel needs %zu bytes of shared memory (> 227 KB): isometry too large for the fused path", bytes);
+    if (bytes > 227 * 1024)
+        return fail("kernel needs %zu bytes of shared memory (> 227 KB): isometry too large for the fused Stiefel kernels "
+                    "(gradient / HVP / trust region need n*p <= 6144, i.e. Kraus rank <= 24 for the full-sites N = 4 model)", bytes);
     if (bytes > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     return 0;
 }
@@ -799,9 +801,11 @@ static int riem_launch(otn_problem* h, int batch, const int* active, int tiles, 
     P.tindex = h->tindex; P.tiles = tiles; P.f_out = f; P.rgrad = rgrad; P.egrad = egrad; P.heta = heta;
     P.n = h->n; P.p = h->p; P.m = h->m; P.alpha0 = h->alpha0; P.alpha1 = h->alpha1; P.active = active;
     const size_t pp = (size_t)h->p * h->p;
-    if ((h->p == 16 || h->p == 8) && h->n % 8 == 0) {
+    const size_t sm_mma = ((hvp ? 4 : 2) * (size_t)h->n * (h->p + 4) + 8 * h->p * (h->p + 4)) * 8;
+    // large Kraus ranks (K > 20 at p = 16): the padded DMMA layout no longer fits 227 KB; the unpadded CUDA-core kernel does up to K = 24
+    if ((h->p == 16 || h->p == 8) && h->n % 8 == 0 && sm_mma <= 227 * 1024) {
         const size_t ld = h->p + 4;
-        const size_t sm = ((hvp ? 4 : 2) * (size_t)h->n * ld + 8 * h->p * ld) * 8;
+        const size_t sm = sm_mma;
 #define RIEM_MMA(PV)                                                                               \
     do {                                                                                           \
         if (!hvp) { OTN_TRY(set_smem(riem_mma_kernel<PV, false>, sm)); riem_mma_kernel<PV, false><<<batch * h->m, ST_THREADS, sm, h->stream>>>(P); } \

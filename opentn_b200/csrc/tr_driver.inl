@@ -25,7 +25,10 @@ static int tr_alloc(otn_problem* h) {
     return 0;
 }
 
-static bool tr_use_mma(const otn_problem* h) { return (h->p == 16 || h->p == 8) && h->n % 8 == 0; }
+static bool tr_use_mma(const otn_problem* h) {
+    // the padded layout of tcg_step (4 arrays of n x (p+4)) must fit 227 KB; otherwise the unpadded CUDA-core kernels are used
+    return (h->p == 16 || h->p == 8) && h->n % 8 == 0 && (4 * (size_t)h->n * (h->p + 4) + 3 * h->p * (h->p + 4)) * 8 <= 227 * 1024;
+}
 
 static int cdot_launch(otn_problem* h, const double* x, const double* a, const double* b, int batch, double* out) {
     ProfScope ps(&h->prof, h->stream, CAT_TR, 0.0);
