@@ -277,6 +277,10 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p) {
     }
 }
 
+// (A persistent variant -- one CTA per resident slot walking a static tile list with the cp.async ring running across tile
+// boundaries -- was measured in round 1: 22.8 vs 28.6 TFLOP/s at D = 144.  The hardware CTA scheduler with 4-5 co-resident CTAs
+// per SM already hides the per-tile prologue; the extra index arithmetic and register pressure cost more than they saved.)
+
 // ---- host-side dispatch -------------------------------------------------------------------------------------------
 struct GemmPlan {
     int kind;      // 0 = simt fallback, 1 = dmma 128x128, 2 = dmma 64x64, 3 = dmma 48x48
