@@ -158,7 +158,8 @@ typedef struct {
     double* x_iter;      /* [niter+1][batch][m][n][p] iterate history (save_x=True) ; nullable */
     double* radius_inout;/* [batch] initial radii in, final radii out (warm restart, :37) ; nullable */
     int* status;         /* [batch] OTN_STATUS_* bits ; nullable */
-    long long hvp_total; /* out: Hessian-vector products evaluated over all instances (incl. the model-value one, :67) */
+    long long hvp_total; /* out: Hessian-vector products evaluated over all instances (tCG only: the model-value product `hess @ eta`
+                            of :67 is accumulated from the tCG products, H eta = sum_j alpha_j H d_j, not recomputed) */
 } otn_tr_report;
 
 void otn_tr_default_params(otn_tr_params* prm);

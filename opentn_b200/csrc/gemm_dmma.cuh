@@ -24,7 +24,9 @@ struct GemmParams {
     const double* A2; const double* B2;      // optional second product accumulated into the same tile (nullptr = none)
     double* C;
     long long sA1, sB1, sA2, sB2, sC;        // per-instance strides in doubles (0 = shared operand)
-    int D;                                   // matrix side
+    int D;                                   // matrix side (leading dimension)
+    int kvalid;                              // contraction extent actually populated (0 = D); rows/columns beyond it are zero
+                                             // padding of the block-diagonal evaluation and are skipped (multiple of 4)
     int row0, rows;                          // row window of C computed by this launch (row sharding); rows % BM == 0
     int batch;
     const int* active;                       // optional per-instance mask (nullptr = all active)
@@ -76,7 +78,8 @@ gemm_dmma_kernel(const GemmParams p) {
     const int g = lane >> 2, t = lane & 3;
 
     const int nprod = (p.A2 != nullptr) ? 2 : 1;
-    const int ktiles_one = D / BK;
+    const int kvalid = p.kvalid > 0 ? p.kvalid : D;
+    const int ktiles_one = (kvalid + BK - 1) / BK;
     const int ktiles = ktiles_one * nprod;
 
     const double* A1 = p.A1 + (long long)b * p.sA1;
@@ -140,8 +143,8 @@ gemm_dmma_kernel(const GemmParams p) {
         }
         const double* As = smem + (kt % STAGES) * Cfg::STAGE_ELEMS;
         const double* Bs = As + Cfg::A_ELEMS;
-#pragma unroll
-        for (int kk = 0; kk < BK; kk += 4) {
+        const int kend = kvalid - (kt < ktiles_one ? kt : kt - ktiles_one) * BK;   // < BK only in the last k-tile of a padded block
+        auto kstep = [&](int kk) {
             double a[MI], bf[NI];
 #pragma unroll
             for (int i = 0; i < MI; ++i) {
@@ -157,6 +160,13 @@ gemm_dmma_kernel(const GemmParams p) {
             for (int i = 0; i < MI; ++i)
 #pragma unroll
                 for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bf[j]);
+        };
+        if (kend >= BK) {
+#pragma unroll
+            for (int kk = 0; kk < BK; kk += 4) kstep(kk);
+        } else {
+#pragma unroll 1
+            for (int kk = 0; kk < kend; kk += 4) kstep(kk);
         }
     }
     cp_async_wait<0>();

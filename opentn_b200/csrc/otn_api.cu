@@ -106,7 +106,8 @@ static int set_smem(K kern, size_t bytes) {
     if (bytes > 227 * 1024)
         return fail("kernel needs %zu bytes of shared memory (> 227 KB): isometry too large for the fused Stiefel kernels "
                     "(gradient / HVP / trust region need n*p <= 6144, i.e. Kraus rank <= 24 for the full-sites N = 4 model)", bytes);
-    if (bytes > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    // opt in early: the 48 KB default limit covers static + dynamic shared memory together
+    if (bytes > 40 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     return 0;
 }
 
@@ -484,6 +485,7 @@ static cudaError_t hgemm(otn_problem* h, const GemmParams& p0, bool ta, bool tb)
         GemmParams p = p0;
         const long long o = h->blkOff[i];
         p.D = h->blkD[i]; p.row0 = 0; p.rows = h->blkD[i];
+        p.kvalid = h->structured ? (i == 0 ? h->sym.NS : h->sym.NA) : 0;
         p.A1 += o; p.B1 += o; p.C += o;
         if (p.A2) { p.A2 += o; p.B2 += o; }
         if (p.epi != EPI_NONE) { p.E += o; p.partial += h->blkTileOff[i]; p.partial_stride = h->tiles; }

@@ -15,7 +15,8 @@
 
 namespace otn {
 
-constexpr int ST_THREADS = 256;
+constexpr int ST_THREADS = 512;   // 16 warps per isometry: these kernels keep one CTA per SM (shared memory), so latency hiding must come from within
+constexpr int ST_WARPS = ST_THREADS / 32;
 constexpr int ST_MAXP = 16;  // p <= 16 (dim = d^N <= 16 or d^2 = 4)
 
 // G[i][j] = sum_r A[r][i] * B[r][j]   (p x p), fixed summation order => deterministic
@@ -278,16 +279,16 @@ __device__ inline void jacobi_eig_warp(double* S, double* V, int p, double* cs /
 //   * otherwise: symmetric eigendecomposition by the one-warp Jacobi solver above.
 // Work arrays Y, Z, T: p*p doubles each.  Returns (in every thread) 0 = ok, 2 = G not positive definite.
 __device__ inline int inv_sqrt_spd(const double* G, double* Q, double* Y, double* Z, double* T, int p, double* cs, int* pairs,
-                                   double* red /* >= 9 doubles */) {
+                                   double* red /* >= ST_WARPS + 1 doubles */) {
     const int pp = p * p;
     double dev = 0.0;
     for (int o = threadIdx.x; o < pp; o += ST_THREADS) { const double e = G[o] - ((o / p == o % p) ? 1.0 : 0.0); dev = fma(e, e, dev); }
     dev = warp_sum(dev);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dev;
     __syncthreads();
-    if (threadIdx.x == 0) { double t = 0.0; for (int w = 0; w < ST_THREADS / 32; ++w) t += red[w]; red[8] = t; }
+    if (threadIdx.x == 0) { double t = 0.0; for (int w = 0; w < ST_THREADS / 32; ++w) t += red[w]; red[ST_WARPS] = t; }
     __syncthreads();
-    const bool newton = red[8] < 0.25;
+    const bool newton = red[ST_WARPS] < 0.25;
     __syncthreads();
     if (newton) {
         for (int o = threadIdx.x; o < pp; o += ST_THREADS) { Y[o] = G[o]; Z[o] = (o / p == o % p) ? 1.0 : 0.0; }
@@ -308,7 +309,7 @@ __device__ inline int inv_sqrt_spd(const double* G, double* Q, double* Y, double
             double tot = 0.0;
             for (int w = 0; w < ST_THREADS / 32; ++w) tot += red[w];
             if (tot < 1e-30) break;                                        // uniform: every thread sees the same sum
-            double yn[4], zn[4];                                           // pp <= 4 * ST_THREADS is not needed: pp <= 256
+            double yn[4], zn[4];                                           // pp <= 256 <= ST_THREADS: at most one element per thread
             int cnt = 0;
             for (int o = threadIdx.x; o < pp; o += ST_THREADS, ++cnt) {
                 const int i = o / p, j = o - i * p;
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(ST_THREADS) retract_kernel(const double* __res
     double* Tw = Yw + pp;
     __shared__ double cs[2 * ST_MAXP];
     __shared__ int pairs[2 * ST_MAXP];
-    __shared__ double red[9];
+    __shared__ double red[ST_WARPS + 1];
     const long long base = (long long)item * np;
     for (int i = threadIdx.x; i < np; i += ST_THREADS) A[i] = x[base + i] + (eta ? eta[base + i] : 0.0);
     __syncthreads();
@@ -668,7 +669,7 @@ __global__ void __launch_bounds__(ST_THREADS) retract_mma_kernel(const double* _
     double* Tw = Yw + P * P;
     __shared__ double cs[2 * ST_MAXP];
     __shared__ int pairs[2 * ST_MAXP];
-    __shared__ double red[9];
+    __shared__ double red[ST_WARPS + 1];
     const long long base = (long long)item * np;
     for (int i = threadIdx.x; i < np; i += ST_THREADS) {
         const int o = (i / P) * LD + (i % P);

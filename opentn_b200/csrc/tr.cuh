@@ -13,7 +13,7 @@ struct TrState {
     int gd_final = 0;   // which half of the Gd ping-pong buffer holds Ghat_0 after the tangent reverse sweep
     int tiles = 1;      // partial-sum tiles of the cached forward pass
     // device arrays (allocated by the driver)
-    double *g = nullptr, *r = nullptr, *z = nullptr, *d = nullptr, *Hd = nullptr, *xn = nullptr;   // [B][m][np]
+    double *g = nullptr, *r = nullptr, *z = nullptr, *d = nullptr, *Hd = nullptr, *xn = nullptr, *Hz = nullptr;   // [B][m][np]
     double *radius = nullptr, *fx = nullptr, *fn = nullptr, *rsq = nullptr, *stoptol = nullptr, *gz = nullptr, *zHz = nullptr;
     int *tcg_active = nullptr, *on_boundary = nullptr, *n_cg = nullptr, *status = nullptr, *accepted = nullptr, *n_active = nullptr;
     double* rho = nullptr;
@@ -23,6 +23,8 @@ struct TrState {
 struct TcgParams {
     const double* x;
     double *r, *z, *d;
+    double* Hz;            // H z, accumulated alongside z (z = sum_j alpha_j d_j  =>  H z = sum_j alpha_j H d_j): saves the extra
+                           // `hess @ eta` product of trust_region_rcopt.py:67
     const double* Hd;
     const double* g;
     double *radius, *rsq, *stoptol;
@@ -33,18 +35,18 @@ struct TcgParams {
 
 // block-wide sum of `nv` per-thread values, fixed order (warp shuffle tree, then warps in index order)
 template <int NV>
-__device__ __forceinline__ void block_sum(double (&v)[NV], double* red /* [NV][8] */, double (&out)[NV]) {
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* red /* [NV][ST_WARPS] */, double (&out)[NV]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         double s = warp_sum(v[i]);
-        if (lane == 0) red[i * 8 + warp] = s;
+        if (lane == 0) red[i * ST_WARPS + warp] = s;
     }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         double s = 0.0;
-        for (int w = 0; w < ST_THREADS / 32; ++w) s += red[i * 8 + w];
+        for (int w = 0; w < ST_THREADS / 32; ++w) s += red[i * ST_WARPS + w];
         out[i] = s;
     }
     __syncthreads();
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(ST_THREADS) tcg_init_kernel(const TcgParams P)
     double* X = sm;
     double* A = X + nl;
     double* GA = A + nl;
-    __shared__ double red[8];
+    __shared__ double red[ST_WARPS];
     double v[1] = {0.0};
     for (int l = 0; l < P.m; ++l) {
         const long long base = ((long long)inst * P.m + l) * np;
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(ST_THREADS) tcg_init_kernel(const TcgParams P)
             const double gv = P.g[base + i];
             const int o = (i / P.p) * ld + (i % P.p);
             X[o] = P.x[base + i]; A[o] = gv;
-            P.r[base + i] = gv; P.z[base + i] = 0.0; P.d[base + i] = -gv;
+            P.r[base + i] = gv; P.z[base + i] = 0.0; P.d[base + i] = -gv; P.Hz[base + i] = 0.0;
             v[0] = fma(gv, gv, v[0]);
         }
         __syncthreads();
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(ST_THREADS) tcg_step_kernel(const TcgParams P)
     double* GA = C + nl;
     double* GB = GA + pl;
     double* GC = GB + pl;
-    __shared__ double red[4 * 8];
+    __shared__ double red[4 * ST_WARPS];
     __shared__ double sc[4];
     __shared__ int flag;
     // ---- pass A: dHd, dsq, zd, zz
@@ -183,7 +185,10 @@ __global__ void __launch_bounds__(ST_THREADS) tcg_step_kernel(const TcgParams P)
         const double t = sc[0];
         for (int l = 0; l < P.m; ++l) {
             const long long base = ((long long)inst * P.m + l) * np;
-            for (int i = threadIdx.x; i < np; i += ST_THREADS) P.z[base + i] = fma(t, P.d[base + i], P.z[base + i]);
+            for (int i = threadIdx.x; i < np; i += ST_THREADS) {
+                P.z[base + i] = fma(t, P.d[base + i], P.z[base + i]);
+                P.Hz[base + i] = fma(t, P.Hd[base + i], P.Hz[base + i]);
+            }
         }
         if (threadIdx.x == 0) { P.tcg_active[inst] = 0; P.on_boundary[inst] = 1; }
         return;
@@ -194,8 +199,10 @@ __global__ void __launch_bounds__(ST_THREADS) tcg_step_kernel(const TcgParams P)
     for (int l = 0; l < P.m; ++l) {
         const long long base = ((long long)inst * P.m + l) * np;
         for (int i = threadIdx.x; i < np; i += ST_THREADS) {
-            const double rv = fma(alpha, P.Hd[base + i], P.r[base + i]);
+            const double hv = P.Hd[base + i];
+            const double rv = fma(alpha, hv, P.r[base + i]);
             P.r[base + i] = rv;
+            P.Hz[base + i] = fma(alpha, hv, P.Hz[base + i]);
             P.z[base + i] = fma(alpha, P.d[base + i], P.z[base + i]);
             const int o = (i / P.p) * ld + (i % P.p);
             X[o] = P.x[base + i]; C[o] = rv;

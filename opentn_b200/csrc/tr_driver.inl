@@ -11,12 +11,12 @@ static int tr_alloc(otn_problem* h) {
     TrState& t = h->tr;
     if (t.cap_batch >= h->max_batch) return 0;
     const size_t B = (size_t)h->max_batch, V = B * h->m * h->np;
-    const size_t bytes = 6 * (V * 8 + 16) + 8 * (B * 8 + 16) + 6 * (B * 4 + 16) + 64;   // every slice is rounded up to 16 B
+    const size_t bytes = 7 * (V * 8 + 16) + 8 * (B * 8 + 16) + 6 * (B * 4 + 16) + 64;   // every slice is rounded up to 16 B
     OTN_TRY(h->tr_buf.ensure(bytes));
     char* base = h->tr_buf.as<char>();
     auto take = [&](size_t nbytes) { char* r = base; base += (nbytes + 15) / 16 * 16; return r; };
     t.g = (double*)take(V * 8); t.r = (double*)take(V * 8); t.z = (double*)take(V * 8); t.d = (double*)take(V * 8);
-    t.Hd = (double*)take(V * 8); t.xn = (double*)take(V * 8);
+    t.Hd = (double*)take(V * 8); t.xn = (double*)take(V * 8); t.Hz = (double*)take(V * 8);
     t.radius = (double*)take(B * 8); t.fx = (double*)take(B * 8); t.fn = (double*)take(B * 8); t.rsq = (double*)take(B * 8);
     t.stoptol = (double*)take(B * 8); t.gz = (double*)take(B * 8); t.zHz = (double*)take(B * 8); t.rho = (double*)take(B * 8);
     t.tcg_active = (int*)take(B * 4); t.on_boundary = (int*)take(B * 4); t.n_cg = (int*)take(B * 4); t.status = (int*)take(B * 4);
@@ -111,7 +111,7 @@ extern "C" int otn_tr_run(otn_problem* h, double* x, int batch, const otn_tr_par
     if (rep && rep->x_iter) CUDA_TRY(cudaMemcpyAsync(rep->x_iter, h->x, V, cudaMemcpyDefault, st));     // x_iter = [x] (:52)
 
     TcgParams tp{};
-    tp.x = h->x; tp.r = t.r; tp.z = t.z; tp.d = t.d; tp.Hd = t.Hd; tp.g = t.g; tp.radius = t.radius; tp.rsq = t.rsq;
+    tp.x = h->x; tp.r = t.r; tp.z = t.z; tp.d = t.d; tp.Hd = t.Hd; tp.Hz = t.Hz; tp.g = t.g; tp.radius = t.radius; tp.rsq = t.rsq;
     tp.stoptol = t.stoptol; tp.tcg_active = t.tcg_active; tp.on_boundary = t.on_boundary; tp.n_cg = t.n_cg; tp.status = t.status;
     tp.n_active = t.n_active; tp.n = h->n; tp.p = h->p; tp.m = h->m; tp.maxiter = maxiter; tp.abstol = prm.tcg_abstol; tp.reltol = prm.tcg_reltol;
 
@@ -130,11 +130,10 @@ extern "C" int otn_tr_run(otn_problem* h, double* x, int batch, const otn_tr_par
             CUDA_TRY(cudaMemcpyAsync(&n_active, t.n_active, 4, cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
         }
-        // model decrease  <grad, eta> + 1/2 <eta, hess @ eta>                                       (:67)
-        OTN_TRY(otn_dev_hvp(h, h->x, t.z, batch, nullptr, t.Hd));
-        hvps += batch;
+        // model decrease  <grad, eta> + 1/2 <eta, hess @ eta>  (:67).  hess @ eta is not recomputed: eta = sum_j alpha_j d_j,
+        // so H eta = sum_j alpha_j (H d_j) was accumulated by tcg_step_kernel from the products tCG already paid for.
         OTN_TRY(cdot_launch(h, h->x, t.g, t.z, batch, t.gz));
-        OTN_TRY(cdot_launch(h, h->x, t.z, t.Hd, batch, t.zHz));
+        OTN_TRY(cdot_launch(h, h->x, t.z, t.Hz, batch, t.zHz));
         // x_next = retract(x, eta) ; f(x_next)                                                     (:62, :67)
         OTN_TRY(retract_launch(h, h->x, t.z, t.xn, batch, t.status));
         OTN_TRY(otn_dev_cost(h, t.xn, batch, nullptr, t.fn));

@@ -38,8 +38,10 @@ def test_tr_c1_trajectory(P, c1, goldens):
     np.testing.assert_array_equal(rep["radius_iter"][:k, 0], [l["radius"] for l in log_[:k]])
     np.testing.assert_array_equal(rep["on_boundary"][:k, 0], [int(l["on_boundary"]) for l in log_[:k]])
     np.testing.assert_array_equal(rep["accepted"][:k, 0], [int(l["accepted"]) for l in log_[:k]])
-    # n_matvec of the oracle operator counts tCG products + the model-value product
+    # n_matvec of the oracle operator counts tCG products + the model-value product (which the device solver accumulates
+    # from the tCG products instead of recomputing)
     np.testing.assert_array_equal(rep["n_cg"][:k, 0] + 1, [l["n_matvec"] for l in log_[:k]])
+    assert rep["hvp_total"] == rep["n_cg"].sum()
     np.testing.assert_allclose(rep["x_iter"][k, 0], np.array(xs_it[k]), atol=1e-8)
     assert rep["status"][0] == 0
     assert x.shape == (3, 40, 4) and np.allclose(x, rep["x_iter"][-1, 0])
