@@ -11,6 +11,7 @@
 //   EPI_DOT   : C = acc          and  partial[b][tile] = sum acc * R           (d/dt of the norm)
 // Partials are reduced later in a fixed order => bitwise reproducible costs.
 #pragma once
+#include <atomic>
 #include <cstdlib>
 
 #include "otn_common.cuh"
@@ -318,11 +319,15 @@ template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool TA, bool TB>
 inline cudaError_t launch_dmma(const GemmParams& p, int tiles, cudaStream_t st) {
     using Cfg = GemmCfg<BM, BN, BK, WM, WN, STAGES, TA, TB>;
     auto kern = gemm_dmma_kernel<BM, BN, BK, WM, WN, STAGES, TA, TB>;
-    static bool configured = false;
-    if (!configured) {
+    // opt in to > 48 KB of dynamic shared memory once per device (function attributes are per device context)
+    static std::atomic<unsigned long long> configured{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ULL << (dev & 63);
+    if (!(configured.load(std::memory_order_acquire) & bit)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured.fetch_or(bit, std::memory_order_release);
     }
     kern<<<(unsigned)((long long)p.batch * tiles), Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(p);
     return cudaGetLastError();

@@ -3,6 +3,7 @@
 #include "../../include/otn.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
@@ -115,7 +116,7 @@ static int set_smem(K kern, size_t bytes) {
 // launch accounting + optional per-kernel CUDA-event timing (bench.py's live roofline measurement)
 // ---------------------------------------------------------------------------------------------------------------------
 enum { CAT_GEMM = 0, CAT_ASSEMBLE = 1, CAT_BACK = 2, CAT_RIEM = 3, CAT_TR = 4, CAT_OTHER = 5, CAT_COUNT = 6 };
-static long long g_launches = 0;
+static std::atomic<long long> g_launches{0};
 struct ProfRec { int cat; cudaEvent_t e0, e1; double flops; };
 struct Profiler {
     bool on = false;
@@ -134,7 +135,7 @@ struct ProfScope {
     }
     ~ProfScope() { if (live) { cudaEventRecord(rec.e1, st); pr->recs.push_back(rec); } }
 };
-extern "C" long long otn_launch_count(void) { return g_launches; }
+extern "C" long long otn_launch_count(void) { return g_launches.load(); }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // embedding index tables (transformations.py:431-444, 473-482)

@@ -127,3 +127,21 @@ def test_library_preserves_current_device():
     assert torch.zeros(1, device="cuda").device.index == 1
     fit.close()
     torch.cuda.set_device(0)
+
+
+def test_two_devices_in_one_process(oracle):
+    """Handles on two GPUs of one process (per-device kernel attributes, per-device scratch)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from opentn_b200 import StiefelFit
+    P = oracle
+    T = P.kitaev_fullsites_target()
+    rng = np.random.default_rng(0)
+    xs = np.array([[P.random_stiefel(256, 16, rng) for _ in range(3)]])
+    f = []
+    for dev in (0, 1):
+        fit = StiefelFit(T, model="full", N=4, d=2, device=dev)
+        f.append(fit.cost_grad(xs)[0])
+        fit.close()
+    assert f[0][0] == f[1][0]
