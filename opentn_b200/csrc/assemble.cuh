@@ -330,112 +330,11 @@ __global__ void __launch_bounds__(256) assemble_mma_kernel(const double* __restr
     }
 }
 
-// Z[(a,k),c] = 2 sum_{b,d} W[(a,b),(c,d)] x[(b,k),d]   (+ tangent: Wd * x + W * eta); W is swap-symmetric (see below).
-// 8 warps split the b range; per-warp partial tiles are summed in warp order (deterministic).
-template <int DIM, bool TANGENT>
-__global__ void __launch_bounds__(256) back_assemble_mma_kernel(const double* __restrict__ W, const double* __restrict__ Wd,
-                                                                long long w_stride, long long wd_stride, int nslices,
-                                                                const double* __restrict__ x, const double* __restrict__ eta,
-                                                                double* __restrict__ Z, double* __restrict__ Zd, int K,
-                                                                const int* active, int m, int layer) {
-    extern __shared__ __align__(16) double sm[];
-    constexpr int LD = DIM + 4, MI = DIM / 8, D2 = DIM * DIM, WSZ = DIM * DIM * LD;
-    const int inst = blockIdx.y, a = blockIdx.x;
-    if (active != nullptr && active[inst] == 0) return;
-    const int item = inst * m + layer;
-    const int Kp = (K + 7) & ~7, NI = Kp / 8;
-    const int xrows = DIM * Kp;
-    double* wds = sm;                          // cotangent to contract with x   (W in primal mode, Wd in tangent mode)
-    double* ws = wds + WSZ;                    // tangent mode only: W, contracted with eta
-    double* xs = ws + (TANGENT ? WSZ : 0);
-    double* es = xs + xrows * LD;
-    double* part = es + (TANGENT ? xrows * LD : 0);   // [8][DIM][Kp]
-    const long long np = (long long)DIM * K * DIM;
-    for (int i = threadIdx.x; i < xrows * DIM; i += 256) {
-        const int r = i / DIM, c = i - r * DIM, bb = r / Kp, k = r - bb * Kp;
-        const bool ok = k < K;
-        xs[r * LD + c] = ok ? x[(long long)item * np + (bb * K + k) * DIM + c] : 0.0;
-        if (TANGENT) es[r * LD + c] = ok ? eta[(long long)item * np + (bb * K + k) * DIM + c] : 0.0;
-    }
-    const double* Wb = W + (long long)inst * w_stride;
-    const double* Wdb = TANGENT ? Wd + (long long)inst * wd_stride : nullptr;
-    (void)nslices;
-    // nslices == 1 on this path (the per-factor slices only exist for the local model, which has dim = 4).
-    // Loads are issued in fully unrolled batches so that each thread keeps NU (x2) requests in flight (the first version
-    // looped load->store and was latency bound at ~1 CTA/SM).
-    constexpr int NU = DIM * D2 / 256;
-    {   // pass 1: rows (a,b), columns (c,d): coalesced along (c,d)
-        double v[NU], vd[NU];
-#pragma unroll
-        for (int u = 0; u < NU; ++u) {
-            const int idx = threadIdx.x + u * 256;
-            const long long gi = (long long)a * DIM * D2 + idx;   // (a*DIM + b)*D2 + cd with idx = b*D2 + cd
-            v[u] = Wb[gi];
-            if (TANGENT) vd[u] = Wdb[gi];
-        }
-#pragma unroll
-        for (int u = 0; u < NU; ++u) {
-            const int idx = threadIdx.x + u * 256;
-            const int b = idx / D2, cd = idx - b * D2, c = cd / DIM, dd = cd - c * DIM;
-            if (TANGENT) { ws[(b * DIM + c) * LD + dd] = v[u]; wds[(b * DIM + c) * LD + dd] = vd[u]; }
-            else wds[(b * DIM + c) * LD + dd] = v[u];
-        }
-    }
-    __syncthreads();
-    // No second (transposed) pass: the reverse chain runs on the swap-symmetric residual (see otn_create), so
-    // W[(b,a),(d,c)] == W[(a,b),(c,d)] and W + swap(W) = 2 W; the factor 2 is applied at the output.
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-    double acc[MI][4][2];                       // NI <= 4  (K <= 32)
-#pragma unroll
-    for (int i = 0; i < MI; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-    for (int b = warp; b < DIM; b += 8) {
-#pragma unroll
-        for (int d0 = 0; d0 < DIM; d0 += 4) {
-            double wa[MI], w0[MI];
-#pragma unroll
-            for (int i = 0; i < MI; ++i) {
-                wa[i] = wds[(b * DIM + i * 8 + g) * LD + d0 + t];
-                if (TANGENT) w0[i] = ws[(b * DIM + i * 8 + g) * LD + d0 + t];
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (j < NI) {
-                    const double xb = xs[(b * Kp + j * 8 + g) * LD + d0 + t];
-                    const double eb = TANGENT ? es[(b * Kp + j * 8 + g) * LD + d0 + t] : 0.0;
-#pragma unroll
-                    for (int i = 0; i < MI; ++i) {
-                        dmma884(acc[i][j][0], acc[i][j][1], wa[i], xb);
-                        if (TANGENT) dmma884(acc[i][j][0], acc[i][j][1], w0[i], eb);
-                    }
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < MI; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (j < NI) {
-                const int c = i * 8 + g, k = j * 8 + 2 * t;
-                part[(warp * DIM + c) * Kp + k] = acc[i][j][0];
-                part[(warp * DIM + c) * Kp + k + 1] = acc[i][j][1];
-            }
-    __syncthreads();
-    for (int o = threadIdx.x; o < K * DIM; o += 256) {
-        const int k = o / DIM, c = o - k * DIM;
-        double s = 0.0;
-        for (int w = 0; w < 8; ++w) s += part[(w * DIM + c) * Kp + k];
-        const long long og = (long long)item * np + (a * K + k) * DIM + c;
-        if (TANGENT) Zd[og] = 2.0 * s; else Z[og] = 2.0 * s;
-    }
-}
-
 }  // namespace otn
 
 // ==================================================================================================================
-// Streaming back-assembly (third version; replaces back_assemble_mma_kernel on the hot path).
+// Streaming back-assembly for the dense formulation (an earlier one-CTA-per-(a, instance) kernel that re-read W with a
+// transposed gather ran 3-7x slower; see git history).
 //   out[(a,k),c]  (+)=  2 * sum_{b,d} W[(a,b),(c,d)] * u[(b,k),d]          u = x or eta, W swap-symmetric
 // One CTA per (instance, layer) streams the whole D x D cotangent once through a 3-stage cp.async ring (one stage = the
 // DIM rows {(a,b)}_a of a fixed b, 32 KB at DIM = 16), so ~64 KB per SM are in flight while the previous stage is consumed

@@ -123,122 +123,10 @@ __global__ void __launch_bounds__(256) assemble_sym_kernel(const double* __restr
     }
 }
 
-// ---- adjoint of the assembly from cotangent blocks --------------------------------------------------------------------
-// AS CTAs per instance, each owning DIM/AS values of the output index a (so that 2 CTAs fit one SM: the first version with one
-// CTA per instance ran at 12 % warp occupancy and was latency bound); every CTA streams the rows {(a,b)}_a of Ws and Wa for
-// b = 0..DIM-1 through a 3-stage cp.async ring, expands them to the dense tile [a][c][d] in shared memory and feeds DMMA.
-template <int DIM, int AS>
-struct BasSymCfg {
-    static constexpr int LD = DIM + 4, STAGES = 3, D2 = DIM * DIM, DA = DIM / AS;
-    static constexpr int RAW = DA * D2;                // [a][NS + NA] doubles per stage (NS + NA == DIM*DIM)
-    static constexpr int DENSE = DA * DIM * LD;        // [a][c][LD]
-    static size_t smem_bytes(int K) { return (size_t)(STAGES * RAW + DENSE + DIM * ((K + 7) & ~7) * LD) * 8; }
-};
-
-template <int DIM, int AS>
-__global__ void __launch_bounds__(256) back_assemble_sym_kernel(const double* __restrict__ W, long long w_stride,
-                                                                const double* __restrict__ u, double* __restrict__ out, SymLayout L,
-                                                                int K, int accumulate, const int* active, int m, int layer) {
-    using Cfg = BasSymCfg<DIM, AS>;
-    constexpr int LD = Cfg::LD, D2 = Cfg::D2, ST = Cfg::STAGES, DA = Cfg::DA, NS = DIM * (DIM + 1) / 2, NA = DIM * (DIM - 1) / 2;
-    constexpr int MI = DA * DIM / 64;                  // 8-row blocks per warp
-    static_assert(MI >= 1 && (DA * D2) % 256 == 0, "unsupported split");
-    extern __shared__ __align__(16) double sm[];
-    const int inst = blockIdx.x / AS, a_lo = (blockIdx.x - inst * AS) * DA;
-    if (active != nullptr && active[inst] == 0) return;
-    const int item = inst * m + layer;
-    const int Kp = (K + 7) & ~7, NI = Kp / 8;
-    double* raw = sm;
-    double* dense = raw + ST * Cfg::RAW;
-    double* us = dense + Cfg::DENSE;
-    const long long np = (long long)DIM * K * DIM;
-    const double* Ws = W + (long long)inst * w_stride;
-    const double* Wa = Ws + L.off_a;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-
-    auto load_stage = [&](int b, int s) {
-        double* dst = raw + s * Cfg::RAW;
-        constexpr int CS = NS / 2, CA = NA / 2;        // 16-byte chunks per row
-        for (int id = tid; id < DA * (CS + CA); id += 256) {
-            const int al = id / (CS + CA), ch = id - al * (CS + CA), a = a_lo + al;
-            const int lo = a < b ? a : b, hi = a < b ? b : a;
-            if (ch < CS) cp_async16(dst + al * D2 + 2 * ch, Ws + (long long)pair_s(lo, hi, DIM) * L.Ds + 2 * ch);
-            else if (a != b) cp_async16(dst + al * D2 + NS + 2 * (ch - CS), Wa + (long long)pair_a(lo, hi, DIM) * L.Da + 2 * (ch - CS));
-        }
-    };
-#pragma unroll
-    for (int s = 0; s < ST - 1; ++s) { load_stage(s, s); cp_async_commit(); }
-    for (int i = tid; i < DIM * Kp * DIM; i += 256) {
-        const int r = i / DIM, c = i - r * DIM, bb = r / Kp, k = r - bb * Kp;
-        us[r * LD + c] = (k < K) ? u[(long long)item * np + (bb * K + k) * DIM + c] : 0.0;
-    }
-    double acc[MI][4][2];
-#pragma unroll
-    for (int i = 0; i < MI; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-    const double s2 = 1.41421356237309504880;
-    // per-thread constants of the decode step: this thread always expands column pair (c, dd) = tid % D2
-    const int dc_cd = tid % D2, dc_c = dc_cd / DIM, dc_dd = dc_cd - dc_c * DIM, dc_a0 = tid / D2;
-    const int dc_lo = dc_c < dc_dd ? dc_c : dc_dd, dc_hi = dc_c < dc_dd ? dc_dd : dc_c;
-    const int dc_ps = pair_s(dc_lo, dc_hi, DIM), dc_pa = (dc_c != dc_dd) ? pair_a(dc_lo, dc_hi, DIM) : 0;
-    const bool dc_has_a = dc_c != dc_dd, dc_lt = dc_c < dc_dd;
-    const double dc_nu = (dc_c == dc_dd) ? s2 : 1.0;
-    const int dc_off = dc_c * LD + dc_dd;
-
-    for (int b = 0; b < DIM; ++b) {
-        cp_async_wait<ST - 2>();
-        __syncthreads();                                   // stage b landed; every warp is done with the previous dense tile
-        if (b + ST - 1 < DIM) load_stage(b + ST - 1, (b + ST - 1) % ST);
-        cp_async_commit();
-        const double* R = raw + (b % ST) * Cfg::RAW;
-        // decode: dense[a][c][d] = nu_ab nu_cd Ws[{ab},{cd}] + sg_ab sg_cd Wa[{ab},{cd}]   (thread-invariant parts hoisted: dc_*)
-#pragma unroll
-        for (int uu = 0; uu < DA * D2 / 256; ++uu) {
-            const int al = dc_a0 + uu * (256 / D2), a = a_lo + al;
-            double v = ((a == b) ? s2 : 1.0) * dc_nu * R[al * D2 + dc_ps];
-            if (dc_has_a && a != b) {
-                const double w = R[al * D2 + NS + dc_pa];
-                v += ((a < b) == dc_lt) ? w : -w;
-            }
-            dense[al * DIM * LD + dc_off] = v;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int d0 = 0; d0 < DIM; d0 += 4) {
-            double wa[MI];
-#pragma unroll
-            for (int i = 0; i < MI; ++i) wa[i] = dense[(warp * (MI * 8) + i * 8 + g) * LD + d0 + t];
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (j < NI) {
-                    const double ub = us[(b * Kp + j * 8 + g) * LD + d0 + t];
-#pragma unroll
-                    for (int i = 0; i < MI; ++i) dmma884(acc[i][j][0], acc[i][j][1], wa[i], ub);
-                }
-        }
-    }
-    cp_async_wait<0>();
-#pragma unroll
-    for (int i = 0; i < MI; ++i) {
-        const int Rw = warp * (MI * 8) + i * 8 + g, a = a_lo + Rw / DIM, c = Rw % DIM;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (j < NI) {
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int k = j * 8 + 2 * t + e;
-                    if (k < K) {
-                        const long long og = (long long)item * np + (a * K + k) * DIM + c;
-                        out[og] = accumulate ? out[og] + acc[i][j][e] : acc[i][j][e];
-                    }
-                }
-            }
-    }
-}
-
-// ---- adjoint of the assembly from cotangent blocks, second version ------------------------------------------------------
-// Differences to back_assemble_sym_kernel: (i) the A fragments are decoded straight from the staged block rows into registers
+// ---- adjoint of the assembly from cotangent blocks -----------------------------------------------------------------------
+// AS CTAs per instance, each owning DIM/AS values of the output index a; every CTA streams the rows {(a,b)}_a of Ws and Wa for
+// b = 0..DIM-1 through a 3-stage cp.async ring and feeds DMMA.  Versus the first version (dense tile decoded into shared
+// memory, 4.7 ms per step): (i) the A fragments are decoded straight from the staged block rows into registers
 // (no dense tile, one barrier per stage instead of two); (ii) up to two right-hand sides share one pass over W
 // (out1 (+)= A u1, out2 (+)= A u2): in a joint (f, rgrad, H eta) evaluation the primal cotangent W is needed against both x
 // (gradient) and eta (tangent of the adjoint), so 9 streaming passes per step become 6; (iii) the right-hand sides live
