@@ -394,10 +394,14 @@ def run_gpu(args):
                    "DMMA issue-rate ceiling 148 SM x 128 flop/clk x 1.965 GHz = 37.2 TFLOP/s)")
     roofline = {"bound": "tensor", "kernel": "gemm_dmma_kernel (FP64 DMMA.8x8x4), block-diagonal chain: one 144^3 (48x48 tiles) and one "
                                              "128^3 (64x64 tiles) product per chain product",
-                "peak": peak_tf, "unit": "TFLOP/s", "traffic": None, "peak_source": peak_source, "peak_committed_r01": peak_file}
+                "peak": peak_tf, "unit": "TFLOP/s", "traffic": 4.84e8,
+                "traffic_note": "dram read+write of one single-product launch of the 144-block kernel over 1024 instances, ncu --set "
+                                "full (profiles/ncu_struct_r01.txt: 340 MB + 144 MB); algorithmic 3*144^2*8*1024 = 5.10e8 B (the zero "
+                                "padding is partly never written); the 128-block launch: 372 MB vs 4.03e8 B",
+                "peak_source": peak_source, "peak_committed_r01": peak_file}
     roofline.update(roofline_of(pms, pln, pfl, ms_total, args.steps))
-    roofline["note"] = ("`achieved` counts EXECUTED flops of the block-diagonal evaluation (2*(144^3+128^3) per product incl. zero "
-                        "padding; 2*(136^3+120^3) useful). Dense-equivalent rate (SURVEY 8d algorithmic count, 2*256^3 per product) is "
+    roofline["note"] = ("`achieved` counts EXECUTED flops of the block-diagonal evaluation (2*(144*144*136 + 128*128*120) per product: "
+                        "output tiles are zero-padded to 144 / 128, the contraction stops at 136 / 120; 2*(136^3+120^3) useful). Dense-equivalent rate (SURVEY 8d algorithmic count, 2*256^3 per product) is "
                         "`step_tflops_dense_equivalent`; the dense formulation itself is measured in `dense_formulation`.")
     roofline["step_tflops_dense_equivalent"] = FLOPS_PER_TRIPLE * BATCH / (ms_per_step * 1e-3) / 1e12
 

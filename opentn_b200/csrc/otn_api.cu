@@ -490,7 +490,8 @@ static cudaError_t hgemm(otn_problem* h, const GemmParams& p0, bool ta, bool tb)
         p.A1 += o; p.B1 += o; p.C += o;
         if (p.A2) { p.A2 += o; p.B2 += o; }
         if (p.epi != EPI_NONE) { p.E += o; p.partial += h->blkTileOff[i]; p.partial_stride = h->tiles; }
-        ProfScope ps(&h->prof, h->stream, CAT_GEMM, 2.0 * p.D * (double)p.rows * p.D * p.batch * (p.A2 ? 2 : 1));
+        // executed flops: zero-padded k-steps beyond kvalid are skipped by the kernel
+        ProfScope ps(&h->prof, h->stream, CAT_GEMM, 2.0 * p.D * (double)p.rows * (p.kvalid > 0 ? p.kvalid : p.D) * p.batch * (p.A2 ? 2 : 1));
         cudaError_t e = gemm_launch(p, ta, tb, h->stream);
         if (e != cudaSuccess) return e;
     }
