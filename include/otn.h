@@ -114,6 +114,12 @@ int otn_ipc_open(const unsigned char* handle64, int device, void** ptr);
 int otn_ipc_close(void* ptr, int device);
 int otn_ipc_free(void* ptr, int device);
 
+/* ---- target construction (SURVEY 8f "next" #1) -----------------------------------------------------------------------------
+ * otn_expm : out = exp(tau * A), A a D x D real matrix (A_im == out_im == NULL) or complex as (re, im) pairs.
+ *            exp_operator_dt (transformations.py:24-32; scipy / jax `expm`): scaling and squaring with a degree-16 Taylor
+ *            polynomial (Paterson-Stockmeyer), every product on the chain's DMMA GEMM kernel. */
+int otn_expm(const double* A_re, const double* A_im, int D, double tau, double* out_re, double* out_im, int device);
+
 /* ---- manifold layer (stateless) ---------------------------------------------------------------------------------------
  * otn_project       : Z - X sym(X^T Z)                                   project (stiefel.py:23-30)
  * otn_rgrad_map     : Z/a0 + (1/a1 - 2/a0)/2 X X^T Z - 1/(2 a1) X Z^T X   gradient_ambient2riemannian (stiefel.py:398-409)

@@ -1301,6 +1301,11 @@ extern "C" int otn_ipc_free(void* ptr, int device) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// target construction (section 8f "next")
+// ---------------------------------------------------------------------------------------------------------------------
+#include "expm.inl"
+
+// ---------------------------------------------------------------------------------------------------------------------
 // trust region
 // ---------------------------------------------------------------------------------------------------------------------
 #include "tr_driver.inl"

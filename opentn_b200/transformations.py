@@ -20,6 +20,8 @@ import scipy.linalg
 from . import _lib
 from ._lib import as_f64, check, ptr
 
+_DEVICE = 0
+
 # ---------------------------------------------------------------------------------------------------------------------
 # set-up layer (host)
 # ---------------------------------------------------------------------------------------------------------------------
@@ -39,7 +41,23 @@ def get_ladder_operator(num_levels: int = 2, adjoint: bool = False) -> np.ndarra
 
 
 def exp_operator_dt(op: np.ndarray, tau: float = 1, backend: str = "jax") -> np.ndarray:
-    """exp(tau * op), transformations.py:24-32.  Both reference backends are Pade scaling-and-squaring; SciPy's is used."""
+    """exp(tau * op), transformations.py:24-32.  backend 'scipy' / 'jax' (the reference's two names; both are Pade scaling-and-
+    squaring, evaluated with SciPy on the host) or 'cuda' (otn_expm: Taylor scaling-and-squaring on the FP64 tensor pipe; the
+    4096 x 4096 Liouvillian of N = 6 takes well under a second instead of ~15-90 s)."""
+    if backend == "cuda":
+        a = np.asarray(op)
+        D = a.shape[0]
+        assert a.ndim == 2 and a.shape[1] == D, "square matrix expected"
+        lib = _lib.load()
+        re = as_f64(a.real)
+        out_re = np.empty((D, D))
+        if np.iscomplexobj(a) and np.any(a.imag):
+            im = as_f64(a.imag)
+            out_im = np.empty((D, D))
+            check(lib.otn_expm(ptr(re), ptr(im), D, float(tau), ptr(out_re), ptr(out_im), _DEVICE))
+            return out_re + 1j * out_im
+        check(lib.otn_expm(ptr(re), None, D, float(tau), ptr(out_re), None, _DEVICE))
+        return out_re.astype(a.dtype) if np.iscomplexobj(a) else out_re
     if backend not in ("scipy", "jax"):
         raise ValueError(f"{backend} is not a valid backend string")
     return scipy.linalg.expm(np.asarray(op) * tau)
@@ -262,9 +280,6 @@ def super2ortho(x: np.ndarray, rank: int = None) -> np.ndarray:
 # ---------------------------------------------------------------------------------------------------------------------
 # hot-path arithmetic (GPU through libotn)
 # ---------------------------------------------------------------------------------------------------------------------
-_DEVICE = 0
-
-
 def set_device(device: int):
     global _DEVICE
     _DEVICE = int(device)

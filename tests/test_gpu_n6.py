@@ -36,3 +36,17 @@ def test_n6_cost_and_gradient_norm(n6, goldens, dense):
     b = sum(S.canonical_metric(v[l], Hw[l], xs[l]) for l in range(3))
     assert abs(a - b) < 1e-9 * abs(a)
     fit.close()
+
+
+def test_n6_expm_on_device(n6, oracle):
+    """The 4096 x 4096 Liouvillian propagator (scipy: ~15 s here, 1m28 on the reference author's machine,
+    experiments/gradient.ipynb cell 15) through otn_expm."""
+    import time
+    from opentn_b200 import transformations as T
+    T6, _ = n6
+    L = oracle.create_2local_liouvillians(oracle.get_kitaev_nn_linbladian(1.0), 6, 2, pbc=True)[0]
+    t0 = time.perf_counter()
+    got = T.exp_operator_dt(L, 4.0, backend="cuda")
+    dt = time.perf_counter() - t0
+    assert np.abs(got - T6).max() / np.abs(T6).max() < 1e-12
+    print(f"otn_expm 4096^2: {dt:.2f} s incl. host<->device copies")
