@@ -290,8 +290,12 @@ extern "C" int otn_create_ex(otn_problem** out, int N, int d, int m, int K, int 
     h->dim = (model == OTN_MODEL_FULL) ? ipow(d, N) : d * d;
     h->nblk = 1; h->blkD[0] = h->D; h->blkOff[0] = 0;
     const int sdim = ipow(d, N);   // side of the doubled index (a,b): D = sdim^2
-    h->structured = !(flags & OTN_FLAG_DENSE) &&
-                    ((model == OTN_MODEL_FULL && (h->dim == 16 || h->dim == 8)) || (model == OTN_MODEL_LOCAL && sdim >= 8 && sdim <= 64));
+    // block-diagonal evaluation: 3.3x fewer chain flops, but two launches per product with fewer CTAs each -- for a handful of
+    // small instances the path is launch/latency bound and the dense chain is faster (measured at D = 256, batch 1: 2.1 vs 3.2 ms
+    // per U1), so AUTO picks blocks only when there is enough work to fill the GPU
+    const bool blocks_possible = (model == OTN_MODEL_FULL && (h->dim == 16 || h->dim == 8)) || (model == OTN_MODEL_LOCAL && sdim >= 8 && sdim <= 64);
+    const bool enough_work = (long long)max_batch * h->D >= 4096;
+    h->structured = blocks_possible && !(flags & OTN_FLAG_DENSE) && ((flags & OTN_FLAG_BLOCKS) || enough_work);
     if (h->structured) {
         SymLayout& L = h->sym;
         L.dim = sdim; L.NS = sdim * (sdim + 1) / 2; L.NA = sdim * (sdim - 1) / 2;

@@ -68,7 +68,7 @@ class StiefelFit:
     batch selects its own through `target_index`.
     """
 
-    def __init__(self, target, model="local", N=None, d=2, metric="canonical", max_batch=1, device=0, dense=False):
+    def __init__(self, target, model="local", N=None, d=2, metric="canonical", max_batch=1, device=0, dense=None):
         if model not in ("local", "full"):
             raise ValueError("model must be 'local' or 'full'")
         t = np.asarray(target)
@@ -86,7 +86,9 @@ class StiefelFit:
         self.metric = metric
         metric_id(metric)
         self.device = device
-        self.dense = bool(dense)   # force the dense D x D chain (default: block-diagonal evaluation where available)
+        # dense=True: force the dense D x D chain; False: force the block-diagonal evaluation; None: let the library choose
+        # (blocks when the batch is large enough to fill the GPU)
+        self.dense = dense
         self.max_batch = max_batch
         self._t_re = np.ascontiguousarray(t.real, dtype=np.float64)
         self._t_im = np.ascontiguousarray(t.imag, dtype=np.float64) if np.iscomplexobj(t) and np.any(t.imag) else None
@@ -107,7 +109,8 @@ class StiefelFit:
                 h.close()
             cap = max(batch, self.max_batch)
             h = _Handle(self.N, self.d, m, K, MODEL_LOCAL if self.model == "local" else MODEL_FULL, metric_id(self.metric),
-                        cap, self._t_re, self._t_im, self.device, _lib.FLAG_DENSE if self.dense else 0)
+                        cap, self._t_re, self._t_im, self.device,
+                        0 if self.dense is None else (_lib.FLAG_DENSE if self.dense else _lib.FLAG_BLOCKS))
             h.tindex_ver = 0
             self._handles[key] = h
         return h

@@ -34,14 +34,15 @@ def _random_batch(P, B, m, n, p, seed):
     return xs, et
 
 
+@pytest.mark.parametrize("dense", [False, True])
 @pytest.mark.parametrize("metric", ["canonical", "euclidean"])
 @pytest.mark.parametrize("m,K", [(3, 16), (3, 4), (1, 2), (2, 5)])
-def test_full_model_triple(P, targets, metric, m, K):
+def test_full_model_triple(P, targets, metric, m, K, dense):
     from opentn_b200 import StiefelFit
     T = targets["kitaev_obc_tau4"]
     B = 3
     xs, et = _random_batch(P, B, m, 16 * K, 16, 7 + K)
-    fit = StiefelFit(T, model="full", N=N, d=d, metric=metric, max_batch=B)
+    fit = StiefelFit(T, model="full", N=N, d=d, metric=metric, max_batch=B, dense=dense)
     f, g, h = fit.triple(xs, et)
     spec = P.CostSpec(T, "full")
     for b in range(B):
@@ -118,7 +119,7 @@ def test_generic_complex_target(P, model, m, K):
     T = 0.1 * (rng.standard_normal((256, 256)) + 1j * rng.standard_normal((256, 256)))
     p = 16 if model == "full" else 4
     xs, et = _random_batch(P, 2, m, p * K, p, 3)
-    fit = StiefelFit(T, model=model, N=N, d=d, metric="canonical", max_batch=2)
+    fit = StiefelFit(T, model=model, N=N, d=d, metric="canonical", max_batch=2, dense=False)
     f, g, h = fit.triple(xs, et)
     spec = P.CostSpec(T, model, N, d)
     for b in range(2):
@@ -134,7 +135,7 @@ def test_multiple_targets(P, targets):
     from opentn_b200 import StiefelFit
     Ts = np.stack([targets["pspl_tau1"], targets["pspl_tau05"], targets["kitaev_pbc_tau05"]])
     xs, et = _random_batch(P, 4, 3, 8, 4, 21)
-    fit = StiefelFit(Ts, model="local", N=N, d=d, metric="canonical", max_batch=4)
+    fit = StiefelFit(Ts, model="local", N=N, d=d, metric="canonical", max_batch=4, dense=False)
     index = [2, 0, 1, 0]
     fit.set_target_index(index)
     f, g, h = fit.triple(xs, et)
@@ -182,7 +183,7 @@ def test_dense_formulation_full_model(P, targets, metric, m, K):
     B = 2
     xs, et = _random_batch(P, B, m, 16 * K, 16, 40 + K)
     dense = StiefelFit(T, model="full", N=N, d=d, metric=metric, max_batch=B, dense=True)
-    blocks = StiefelFit(T, model="full", N=N, d=d, metric=metric, max_batch=B)
+    blocks = StiefelFit(T, model="full", N=N, d=d, metric=metric, max_batch=B, dense=False)
     fd, gd, hd = dense.triple(xs, et)
     fb, gb, hb = blocks.triple(xs, et)
     np.testing.assert_allclose(fd, fb, rtol=1e-13)

@@ -26,7 +26,7 @@ def test_tr_c1_trajectory(P, c1, goldens):
     cost trajectory for the iterations over which tCG exit decisions coincide (0-4), and the oracle's per-step log."""
     from opentn_b200 import StiefelFit
     T, xs0 = c1
-    fit = StiefelFit(T, model="local", N=N, d=d, metric="canonical")
+    fit = StiefelFit(T, model="local", N=N, d=d, metric="canonical", dense=False)    # block-diagonal path; the host-loop test below takes the dense one
     x, rep = fit.tr_run(np.array(xs0), niter=5, save_x=True)
     np.testing.assert_allclose(rep["f_iter"][:, 0], goldens["art/f_pauli_n1_tau1_rank10"][:5], rtol=1e-10)
     xs_it, f_it, radius, log_ = P.trust_region_fit(P.CostSpec(T, "local", N, d), xs0, "canonical", niter=5, save_x=True)
@@ -61,14 +61,15 @@ def test_tr_single_steps_from_stored_iterates(c1, goldens):
     fit.close()
 
 
-def test_tr_batch_matches_oracle_fullsites(P):
+@pytest.mark.parametrize("dense", [False, True])
+def test_tr_batch_matches_oracle_fullsites(P, dense):
     """Full-sites ansatz, random starts (headline workload shape, K=4 to keep the oracle fast): per-step parity for a batch."""
     from opentn_b200 import StiefelFit
     T = P.kitaev_fullsites_target()
     B, K = 3, 4
     rng = np.random.default_rng(5)
     xs = np.array([[P.random_stiefel(16 * K, 16, rng) for _ in range(3)] for _ in range(B)])
-    fit = StiefelFit(T, model="full", N=N, d=d, metric="canonical", max_batch=B)
+    fit = StiefelFit(T, model="full", N=N, d=d, metric="canonical", max_batch=B, dense=dense)
     x, rep = fit.tr_run(xs, niter=2)
     spec = P.CostSpec(T, "full")
     for b in range(B):
