@@ -92,6 +92,25 @@ def _cpu_worker(args):
     return time.perf_counter() - t0, acc
 
 
+def _cpu_tr_worker(args):
+    """One trust-region iteration (matrix-free Hessian operator, BASELINE.md baseline (ii)) per instance on the CPU oracle."""
+    first, count = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    from oracle import port as P
+    T = P.kitaev_fullsites_target(N_SITES, D_LOC, 1.0, 4.0, False)
+    spec = P.CostSpec(T, "full")
+    xs, _ = make_inputs(first, count)
+    t0 = time.perf_counter()
+    for i in range(count):
+        P.trust_region_fit(spec, list(xs[i]), "canonical", niter=1)
+    return time.perf_counter() - t0, 0.0
+
+
 class CpuPool:
     """Worker pool for the oracle port: one instance per process, min(B, cores) processes, 1 BLAS thread each
     (BASELINE.md section 3 protocol).  Spawned once; every `run` is one bounded sample."""
@@ -111,6 +130,10 @@ class CpuPool:
         inner = max(r[0] for r in res)
         total = self.cores * sample_per_core
         return total / inner, total, wall
+
+    def run_tr(self, sample_per_core):
+        res = self.pool.map(_cpu_tr_worker, [(c * sample_per_core, sample_per_core) for c in range(self.cores)])
+        return self.cores * sample_per_core / max(r[0] for r in res)
 
     def close(self):
         self.pool.close()
@@ -419,10 +442,19 @@ def run_gpu(args):
 
     cpu = None
     if not args.no_cpu:
-        v, cores, total, wall = cpu_triples_per_sec(32)
+        pool = CpuPool()
+        try:
+            v, total, wall = pool.run(32)
+            tr_cpu = pool.run_tr(2)
+        finally:
+            pool.close()
+        cores = pool.cores
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{total} instances of the same workload ({total // cores} per process x {cores} processes, 1 BLAS thread each, "
-                         f"{wall:.1f} s wall)"}
+                         f"{wall:.1f} s wall)",
+               "tr_iters_per_sec": tr_cpu,
+               "tr_note": "one TR iteration per instance with the matrix-free Hessian operator (BASELINE.md baseline (ii)); the "
+                          "reference's own dense Hessian (stiefel.py:498-529) needs 11 880 jvp(grad) evaluations per iteration at this size"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",

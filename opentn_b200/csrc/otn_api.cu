@@ -950,18 +950,40 @@ static int triple_pipelined(otn_problem* h, const double* x, const double* eta, 
         }
     }
     // staging: per slot  x | eta | rgrad | heta | f
-    const size_t slot_doubles = 4 * (size_t)C * per + C;
+    const int CMAX = 3 * C;
+    const size_t slot_doubles = 4 * (size_t)CMAX * per + CMAX;
     OTN_TRY(h->pipe_buf.ensure(2 * slot_doubles * 8));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     // (copies are not the bottleneck: PCIe moves the 403 MB of a step in 4.2 ms, both directions overlapped; a ramped chunk
     // schedule with short first/last chunks was measured and did not help -- what remains is the lower kernel efficiency of
     // 256-instance launches)
-    const int nchunks = (batch + C - 1) / C;
+    // chunk schedule: C/2 first and last (short exposed head H2D / tail D2H), 1.5 C in between (kernel efficiency)
+    std::vector<int> sizes;
+    if (const char* env = getenv("OTN_PIPE_SCHEDULE")) {          // experiment hook: comma-separated chunk sizes
+        int left = batch;
+        for (const char* q = env; *q && left > 0;) {
+            int n = atoi(q);
+            if (n <= 0) break;
+            n = std::min(std::min(n, CMAX), left);
+            sizes.push_back(n); left -= n;
+            while (*q && *q != ',') ++q;
+            if (*q == ',') ++q;
+        }
+        while (left > 0) { const int n = std::min(C, left); sizes.push_back(n); left -= n; }
+    } else if (batch >= 4 * C) {
+        int left = batch - C;
+        sizes.push_back(C / 2);
+        while (left > 0) { const int n = std::min(C + C / 2, left); sizes.push_back(n); left -= n; }
+        sizes.push_back(C / 2);
+    } else {
+        for (int left = batch; left > 0; left -= C) sizes.push_back(std::min(C, left));
+    }
+    const int nchunks = (int)sizes.size();
     int b0 = 0;
     for (int c = 0; c < nchunks; ++c) {
-        const int slot = c & 1, nb = std::min(C, batch - b0);
+        const int slot = c & 1, nb = sizes[c];
         double* base = h->pipe_buf.as<double>() + slot * slot_doubles;
-        double *dx = base, *de = dx + (size_t)C * per, *dg = de + (size_t)C * per, *dh = dg + (size_t)C * per, *df = dh + (size_t)C * per;
+        double *dx = base, *de = dx + (size_t)CMAX * per, *dg = de + (size_t)CMAX * per, *dh = dg + (size_t)CMAX * per, *df = dh + (size_t)CMAX * per;
         if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_done[slot], 0));          // kernels of chunk c-2 finished reading dx/de
         CUDA_TRY(cudaMemcpyAsync(dx, x + (size_t)b0 * per, nb * per * 8, cudaMemcpyHostToDevice, h->s_in));
         CUDA_TRY(cudaMemcpyAsync(de, eta + (size_t)b0 * per, nb * per * 8, cudaMemcpyHostToDevice, h->s_in));
