@@ -444,7 +444,7 @@ def run_gpu(args):
     if not args.no_cpu:
         pool = CpuPool()
         try:
-            v, total, wall = pool.run(32)
+            v, total, wall = pool.run(64)
             tr_cpu = pool.run_tr(2)
         finally:
             pool.close()
