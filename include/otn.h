@@ -119,6 +119,18 @@ int otn_ipc_free(void* ptr, int device);
  *            exp_operator_dt (transformations.py:24-32; scipy / jax `expm`): scaling and squaring with a degree-16 Taylor
  *            polynomial (Paterson-Stockmeyer), every product on the chain's DMMA GEMM kernel. */
 int otn_expm(const double* A_re, const double* A_im, int D, double tau, double* out_re, double* out_im, int device);
+/* otn_expm_batch : out[b] = exp(taus[b] * A) for b < count (tau sweeps of one generator: the Trotter layers exp(tau L),
+ *                  exp(tau/2 L_odd), exp(tau L_even) of create_trotter_layers, transformations.py:387-402, for every tau of a
+ *                  study in one batched launch sequence).  `taus` is a HOST array; out is [count][D][D] per plane. */
+int otn_expm_batch(const double* A_re, const double* A_im, int D, const double* taus, int count, double* out_re, double* out_im,
+                   int device);
+/* otn_liouvillian : out = sum_t D[L_{term_op[t]} acting on the sites (term_site0[t], term_site1[t]) of an N-site register],
+ *                   D[L] = L (x) conj(L) - (L^+L (x) 1)/2 - (1 (x) (L^+L)^T)/2  (vectorize_dissipative transformations.py:243-250
+ *                   of op2fullspace :252-260; the odd / even / periodic sums of local_lindbladian_to_full_liouvillians :337-369
+ *                   are term lists).  L: [n_ops][d^2][d^2] as (re, im) planes (L_im nullable); term arrays are HOST arrays;
+ *                   out: D x D planes, D = d^(2N); n_terms <= 64, d^N <= 4096. */
+int otn_liouvillian(const double* L_re, const double* L_im, int n_ops, int N, int d, const int* term_op, const int* term_site0,
+                    const int* term_site1, int n_terms, double* out_re, double* out_im, int device);
 
 /* ---- manifold layer (stateless) ---------------------------------------------------------------------------------------
  * otn_project       : Z - X sym(X^T Z)                                   project (stiefel.py:23-30)

@@ -19,27 +19,32 @@ __global__ void col_abs_sum_kernel(const double* __restrict__ re, const double* 
     out[j] = s;
 }
 
-// out = c0 I + c1 X1 + c2 X2 + c3 X3 + c4 X4 (null pointers skipped; `diag` = coefficient of the identity, real part only)
-__global__ void lincomb_kernel(double* __restrict__ out, long long n, int D, double diag, double c1, const double* __restrict__ X1,
-                               double c2, const double* __restrict__ X2, double c3, const double* __restrict__ X3, double c4,
+// out_b = diag I + c1 X1_b + c2 X2_b + c3 X3_b + c4 X4_b for every instance b (null pointers skipped; `diag` = coefficient
+// of the identity; `c1b`, when given, multiplies c1 per instance; s1 = instance stride of X1, `sb` of everything else)
+__global__ void lincomb_kernel(double* __restrict__ out, long long n, int D, int count, long long sb, double diag, double c1,
+                               const double* __restrict__ c1b, const double* __restrict__ X1, long long s1, double c2,
+                               const double* __restrict__ X2, double c3, const double* __restrict__ X3, double c4,
                                const double* __restrict__ X4) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long total = n * count;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long b = t / n, i = t - b * n, o = b * sb + i;
         double v = ((i / D) == (i % D)) ? diag : 0.0;
-        if (X1) v = fma(c1, X1[i], v);
-        if (X2) v = fma(c2, X2[i], v);
-        if (X3) v = fma(c3, X3[i], v);
-        if (X4) v = fma(c4, X4[i], v);
-        out[i] = v;
+        if (X1) v = fma(c1b ? c1 * c1b[b] : c1, X1[b * s1 + i], v);
+        if (X2) v = fma(c2, X2[o], v);
+        if (X3) v = fma(c3, X3[o], v);
+        if (X4) v = fma(c4, X4[o], v);
+        out[o] = v;
     }
 }
 
-struct CMat { double* re; double* im; };   // im == nullptr for a real matrix
+struct CMat { double* re; double* im; };   // im == nullptr for a real matrix; instance b at re + b * stride
 
 struct ExpmCtx {
-    int D; long long n; bool cplx; cudaStream_t st; double* neg;   // neg: scratch for -Im
+    int D; long long n; bool cplx; int count; long long sb; cudaStream_t st; double* neg;   // neg: scratch for -Im
     int launch(const double* A1, const double* B1, const double* A2, const double* B2, double* C) {
         GemmParams p{};
-        p.A1 = A1; p.B1 = B1; p.A2 = A2; p.B2 = B2; p.C = C; p.D = D; p.row0 = 0; p.rows = D; p.batch = 1; p.epi = EPI_NONE;
+        p.A1 = A1; p.B1 = B1; p.A2 = A2; p.B2 = B2; p.C = C; p.D = D; p.row0 = 0; p.rows = D; p.batch = count; p.epi = EPI_NONE;
+        p.sA1 = p.sB1 = p.sA2 = p.sB2 = p.sC = sb;
         ++g_launches;
         CUDA_TRY(gemm_launch(p, false, false, st));
         return 0;
@@ -47,7 +52,7 @@ struct ExpmCtx {
     // C = A * B
     int mul(CMat A, CMat B, CMat C) {
         if (!cplx) return launch(A.re, B.re, nullptr, nullptr, C.re);
-        lincomb_kernel<<<1024, 256, 0, st>>>(neg, n, D, 0.0, -1.0, A.im, 0.0, nullptr, 0.0, nullptr, 0.0, nullptr);
+        lincomb_kernel<<<1024, 256, 0, st>>>(neg, n, D, count, sb, 0.0, -1.0, nullptr, A.im, sb, 0.0, nullptr, 0.0, nullptr, 0.0, nullptr);
         CUDA_TRY(cudaGetLastError());
         OTN_TRY(launch(A.re, B.re, neg, B.im, C.re));     // Re = Ar Br - Ai Bi
         OTN_TRY(launch(A.re, B.im, A.im, B.re, C.im));    // Im = Ar Bi + Ai Br
@@ -55,8 +60,8 @@ struct ExpmCtx {
     }
     // out = diag I + c1 X1 + c2 X2 + c3 X3 + c4 X4
     int comb(CMat out, double diag, double c1, CMat X1, double c2, CMat X2, double c3, CMat X3, double c4, CMat X4) {
-        lincomb_kernel<<<1024, 256, 0, st>>>(out.re, n, D, diag, c1, X1.re, c2, X2.re, c3, X3.re, c4, X4.re);
-        if (cplx) lincomb_kernel<<<1024, 256, 0, st>>>(out.im, n, D, 0.0, c1, X1.im, c2, X2.im, c3, X3.im, c4, X4.im);
+        lincomb_kernel<<<1024, 256, 0, st>>>(out.re, n, D, count, sb, diag, c1, nullptr, X1.re, sb, c2, X2.re, c3, X3.re, c4, X4.re);
+        if (cplx) lincomb_kernel<<<1024, 256, 0, st>>>(out.im, n, D, count, sb, 0.0, c1, nullptr, X1.im, sb, c2, X2.im, c3, X3.im, c4, X4.im);
         CUDA_TRY(cudaGetLastError());
         return 0;
     }
@@ -64,8 +69,9 @@ struct ExpmCtx {
 
 }  // namespace
 
-extern "C" int otn_expm(const double* A_re, const double* A_im, int D, double tau, double* out_re, double* out_im, int device) {
-    if (!A_re || !out_re || D < 1) return fail("bad argument");
+extern "C" int otn_expm_batch(const double* A_re, const double* A_im, int D, const double* taus, int count, double* out_re,
+                              double* out_im, int device) {
+    if (!A_re || !out_re || !taus || D < 1 || count < 1) return fail("bad argument");
     if ((A_im != nullptr) != (out_im != nullptr)) return fail("A_im and out_im must be given together");
     OTN_TRY(use_device(device));
     DeviceGuard dev_guard__(device);
@@ -76,34 +82,44 @@ extern "C" int otn_expm(const double* A_re, const double* A_im, int D, double ta
     const void *are, *aim; void *ore, *oim;
     OTN_TRY(stage_in(A_re, bytes, in_re, 0, &are));
     OTN_TRY(stage_in(A_im, bytes, in_im, 0, &aim));
-    OTN_TRY(stage_out(out_re, bytes, o_re, &ore));
-    OTN_TRY(stage_out(out_im, bytes, o_im, &oim));
-    // ||tau A||_1 and the scaling power
+    OTN_TRY(stage_out(out_re, bytes * count, o_re, &ore));
+    OTN_TRY(stage_out(out_im, bytes * count, o_im, &oim));
+    // ||A||_1; one scaling power for the whole sweep, from the largest |tau| (over-scaling the smaller ones is harmless)
     const int nmat = 8;                                             // X, X2, X3, X4, B, P, Q, neg
-    OTN_TRY(ws.ensure((size_t)nmat * (cplx ? 2 : 1) * bytes + (size_t)D * 8));
+    const long long sb = (cplx ? 2 : 1) * n;                        // instance stride inside one work matrix
+    OTN_TRY(ws.ensure((size_t)nmat * count * sb * 8 + (size_t)(D + count) * 8));
     double* base = ws.as<double>();
-    double* colsum = base + (size_t)nmat * (cplx ? 2 : 1) * n;
+    double* colsum = base + (size_t)nmat * count * sb;
+    double* scales = colsum + D;
     col_abs_sum_kernel<<<(D + 127) / 128, 128>>>((const double*)are, (const double*)aim, D, colsum);
     CUDA_TRY(cudaGetLastError());
     std::vector<double> hs(D);
     CUDA_TRY(cudaMemcpy(hs.data(), colsum, (size_t)D * 8, cudaMemcpyDeviceToHost));
-    double nrm = 0.0;
+    double nrm = 0.0, tmax = 0.0;
     for (double v : hs) nrm = std::max(nrm, v);
-    nrm *= std::fabs(tau);
+    for (int b = 0; b < count; ++b) {
+        if (!(taus[b] == taus[b]) || std::isinf(taus[b])) return fail("otn_expm: tau is not finite");
+        tmax = std::max(tmax, std::fabs(taus[b]));
+    }
+    nrm *= tmax;
     if (!(nrm == nrm) || std::isinf(nrm)) return fail("otn_expm: matrix norm is not finite");
     int s = 0;
     while (std::ldexp(nrm, -s) > 0.5 && s < 60) ++s;
-    const double scale = std::ldexp(tau, -s);
+    std::vector<double> hscale(count);
+    for (int b = 0; b < count; ++b) hscale[b] = std::ldexp(taus[b], -s);
+    CUDA_TRY(cudaMemcpy(scales, hscale.data(), (size_t)count * 8, cudaMemcpyHostToDevice));
 
-    auto mat = [&](int k) { CMat m; m.re = base + (size_t)k * (cplx ? 2 : 1) * n; m.im = cplx ? m.re + n : nullptr; return m; };
+    auto mat = [&](int k) { CMat m; m.re = base + (size_t)k * count * sb; m.im = cplx ? m.re + n : nullptr; return m; };
     CMat X = mat(0), X2 = mat(1), X3 = mat(2), X4 = mat(3), B = mat(4), P = mat(5), Q = mat(6);
-    ExpmCtx cx{D, n, cplx, 0, mat(7).re};
+    ExpmCtx cx{D, n, cplx, count, sb, 0, mat(7).re};
     const CMat none{nullptr, nullptr};
-    CMat A{(double*)are, (double*)aim};
     double c[17];
     c[0] = 1.0;
     for (int k = 1; k <= 16; ++k) c[k] = c[k - 1] / k;
-    OTN_TRY(cx.comb(X, 0.0, scale, A, 0.0, none, 0.0, none, 0.0, none));
+    // X_b = tau_b A / 2^s (A shared by the sweep: instance stride 0)
+    lincomb_kernel<<<1024, 256>>>(X.re, n, D, count, sb, 0.0, 1.0, scales, (const double*)are, 0, 0.0, nullptr, 0.0, nullptr, 0.0, nullptr);
+    if (cplx) lincomb_kernel<<<1024, 256>>>(X.im, n, D, count, sb, 0.0, 1.0, scales, (const double*)aim, 0, 0.0, nullptr, 0.0, nullptr, 0.0, nullptr);
+    CUDA_TRY(cudaGetLastError());
     OTN_TRY(cx.mul(X, X, X2));
     OTN_TRY(cx.mul(X2, X, X3));
     OTN_TRY(cx.mul(X2, X2, X4));
@@ -115,10 +131,14 @@ extern "C" int otn_expm(const double* A_re, const double* A_im, int D, double ta
         std::swap(P, B);
     }
     for (int k = 0; k < s; ++k) { OTN_TRY(cx.mul(P, P, Q)); std::swap(P, Q); }
-    CUDA_TRY(cudaMemcpyAsync(ore, P.re, bytes, cudaMemcpyDeviceToDevice, 0));
-    if (cplx) CUDA_TRY(cudaMemcpyAsync(oim, P.im, bytes, cudaMemcpyDeviceToDevice, 0));
-    OTN_TRY(finish_out(out_re, ore, bytes, 0));
-    OTN_TRY(finish_out(out_im, oim, bytes, 0));
+    CUDA_TRY(cudaMemcpy2DAsync(ore, bytes, P.re, (size_t)sb * 8, bytes, count, cudaMemcpyDeviceToDevice, 0));
+    if (cplx) CUDA_TRY(cudaMemcpy2DAsync(oim, bytes, P.im, (size_t)sb * 8, bytes, count, cudaMemcpyDeviceToDevice, 0));
+    OTN_TRY(finish_out(out_re, ore, bytes * count, 0));
+    OTN_TRY(finish_out(out_im, oim, bytes * count, 0));
     CUDA_TRY(cudaDeviceSynchronize());
     return 0;
+}
+
+extern "C" int otn_expm(const double* A_re, const double* A_im, int D, double tau, double* out_re, double* out_im, int device) {
+    return otn_expm_batch(A_re, A_im, D, &tau, 1, out_re, out_im, device);
 }

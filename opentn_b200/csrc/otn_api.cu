@@ -1330,6 +1330,7 @@ extern "C" int otn_ipc_free(void* ptr, int device) {
 // target construction (section 8f "next")
 // ---------------------------------------------------------------------------------------------------------------------
 #include "expm.inl"
+#include "liouville.inl"
 
 // ---------------------------------------------------------------------------------------------------------------------
 // trust region

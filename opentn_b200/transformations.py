@@ -63,6 +63,52 @@ def exp_operator_dt(op: np.ndarray, tau: float = 1, backend: str = "jax") -> np.
     return scipy.linalg.expm(np.asarray(op) * tau)
 
 
+def exp_operator_sweep(op: np.ndarray, taus) -> np.ndarray:
+    """[exp(tau * op) for tau in taus] as one array (len(taus), D, D): the tau sweep of one generator in one batched sequence of
+    launches (otn_expm_batch).  No counterpart in the reference, which loops `exp_operator_dt` (transformations.py:24-32) over
+    tau on the host; used by `create_trotter_layers_sweep`."""
+    a = np.asarray(op)
+    D = a.shape[0]
+    assert a.ndim == 2 and a.shape[1] == D, "square matrix expected"
+    t = as_f64(np.atleast_1d(np.asarray(taus, dtype=np.float64)))
+    lib = _lib.load()
+    re = as_f64(a.real)
+    out_re = np.empty((t.size, D, D))
+    if np.iscomplexobj(a) and np.any(a.imag):
+        im = as_f64(a.imag)
+        out_im = np.empty((t.size, D, D))
+        check(lib.otn_expm_batch(ptr(re), ptr(im), D, ptr(t), t.size, ptr(out_re), ptr(out_im), _DEVICE))
+        return out_re + 1j * out_im
+    check(lib.otn_expm_batch(ptr(re), None, D, ptr(t), t.size, ptr(out_re), None, _DEVICE))
+    return out_re.astype(a.dtype) if np.iscomplexobj(a) else out_re
+
+
+def create_trotter_layers_sweep(liouvillians: list, taus, order: int = 2, half_idx: int = 1) -> list:
+    """`create_trotter_layers` (transformations.py:387-402) for every tau of a sweep: returns one list per tau, each
+    [exp(tau L), exp(tau/2 L_odd), exp(tau L_even)]; three batched device `expm` sweeps in total."""
+    if order != 2:
+        raise ValueError("ATM only order 2 is implemented")
+    taus = np.atleast_1d(np.asarray(taus, dtype=np.float64))
+    per_op = [exp_operator_sweep(op, taus / 2 if i == half_idx else taus) for i, op in enumerate(liouvillians)]
+    return [[per_op[i][k] for i in range(len(liouvillians))] for k in range(taus.size)]
+
+
+def _liouvillian_terms_device(ops, terms, N: int, d: int) -> np.ndarray:
+    """sum of dissipators of two-site jump operators placed on site pairs (otn_liouvillian).  terms: (op index, site0, site1)."""
+    ops = np.stack([np.asarray(o, dtype=complex) for o in ops])
+    q = d * d
+    assert ops.shape[1:] == (q, q), "two-site jump operators expected"
+    D = d ** (2 * N)
+    re, im = as_f64(ops.real), as_f64(ops.imag)
+    t = np.asarray(terms, dtype=np.int32).reshape(-1, 3)
+    t_op, t_s0, t_s1 = (np.ascontiguousarray(t[:, i]) for i in range(3))
+    out_re, out_im = np.empty((D, D)), np.empty((D, D))
+    lib = _lib.load()
+    check(lib.otn_liouvillian(ptr(re), ptr(im), ops.shape[0], N, d, ptr(t_op), ptr(t_s0), ptr(t_s1), t.shape[0], ptr(out_re),
+                              ptr(out_im), _DEVICE))
+    return out_re + 1j * out_im
+
+
 def vectorize(matrix: np.ndarray) -> np.ndarray:
     """Row-major vectorisation to a column vector, transformations.py:221-223."""
     return np.reshape(matrix, (-1, 1))
@@ -166,10 +212,26 @@ def local_lindbladian_to_full_liouvillians(Lnn: np.ndarray, N: int, d: int, pbc:
     return even + odd, odd, even
 
 
-def create_2local_liouvillians(Li, N: int, d: int, pbc: bool = False):
-    """transformations.py:324-335"""
+def create_2local_liouvillians(Li, N: int, d: int, pbc: bool = False, backend: str = "numpy"):
+    """transformations.py:324-335.  backend='cuda' assembles the odd and even sums entry by entry on the device
+    (otn_liouvillian) instead of through D x D Kronecker products on the host."""
     if not isinstance(Li, list):
         Li = [Li]
+    if backend == "cuda":
+        if N % 2:
+            raise ValueError("two-site odd/even layers need an even number of sites (the reference's loop "
+                             "`range(0, N, 2)`, transformations.py:351, runs off the chain for odd N)")
+        use_pbc = pbc and N > 2                         # transformations.py:347-348: pbc is dropped when N == num_sites
+        odd_t = [(j, i, i + 1) for j in range(len(Li)) for i in range(0, N - 1, 2)]
+        even_t = [(j, i, i + 1) for j in range(len(Li)) for i in range(1, N - 1, 2)]
+        if use_pbc:
+            even_t += [(j, N - 1, 0) for j in range(len(Li))]   # permute_operator_pbc(direction='right'): first factor on N-1
+        D = d ** (2 * N)
+        odd = _liouvillian_terms_device(Li, odd_t, N, d)
+        even = _liouvillian_terms_device(Li, even_t, N, d) if even_t else np.zeros((D, D), dtype=complex)
+        return odd + even, odd, even
+    if backend != "numpy":
+        raise ValueError(f"{backend} is not a valid backend string")
     D = d ** (2 * N)
     odd = np.zeros((D, D), dtype=complex)
     even = np.zeros((D, D), dtype=complex)
@@ -188,10 +250,10 @@ def get_kitaev_nn_linbladian(gamma: float):
     return np.sqrt(gamma) * plus @ minus / 4
 
 
-def create_kitaev_liouvillians(N: int, d: int, gamma: float, pbc: bool = False):
+def create_kitaev_liouvillians(N: int, d: int, gamma: float, pbc: bool = False, backend: str = "numpy"):
     """transformations.py:379-384"""
     Lnn = get_kitaev_nn_linbladian(gamma)
-    full, odd, even = create_2local_liouvillians(Lnn, N, d, pbc)
+    full, odd, even = create_2local_liouvillians(Lnn, N, d, pbc, backend=backend)
     return full, odd, even, Lnn
 
 
