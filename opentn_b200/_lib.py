@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libotn.so")
 MODEL_FULL, MODEL_LOCAL = 0, 1
 METRIC_EUCLIDEAN, METRIC_CANONICAL = 0, 1
 STATUS_NAN, STATUS_NOT_SPD, STATUS_NEG_DISCRIMINANT = 1, 2, 4
-FLAG_DENSE, FLAG_BLOCKS = 1, 2
+FLAG_DENSE, FLAG_BLOCKS, FLAG_FACTORED = 1, 2, 4
 
 _dp = C.c_void_p  # double* (host or device)
 _ip = C.c_void_p  # int*

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "assemble.cuh"
+#include "factored.cuh"
 #include "gemm_dmma.cuh"
 #include "stiefel.cuh"
 #include "structured.cuh"
@@ -228,6 +229,11 @@ struct otn_problem {
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     DevBuf pipe_buf;
     DevBuf tr_buf;
+    // factored evaluation of the 2-site model (factored.cuh)
+    bool factored = false;
+    int f_ncols = 0, f_tiles = 0;
+    double *f_Tt = nullptr, *f_Pst = nullptr, *f_Wp = nullptr, *f_colw = nullptr;
+    int *f_jrow = nullptr, *f_restrow = nullptr, *f_colidx = nullptr, *f_swaprow = nullptr;
     EmbedTables tables() const { return EmbedTables{tab, inv, D, q, nf}; }
 };
 
@@ -244,7 +250,8 @@ extern "C" void otn_destroy(otn_problem* h) {
     for (void* ptr : {(void*)h->T_re, (void*)h->im2, (void*)h->tindex, (void*)h->tab, (void*)h->inv, (void*)h->symtab, (void*)h->t2f, (void*)h->Y, (void*)h->P,
                       (void*)h->G, (void*)h->W, (void*)h->Yd, (void*)h->Pd, (void*)h->Gd, (void*)h->Wd, (void*)h->Yl, (void*)h->Yld,
                       (void*)h->Wl, (void*)h->Wld, (void*)h->x, (void*)h->eta, (void*)h->zraw, (void*)h->zdraw, (void*)h->part_f,
-                      (void*)h->part_s})
+                      (void*)h->part_s, (void*)h->f_Tt, (void*)h->f_Pst, (void*)h->f_Wp, (void*)h->f_colw, (void*)h->f_jrow,
+                      (void*)h->f_restrow, (void*)h->f_colidx, (void*)h->f_swaprow})
         if (ptr) cudaFree(ptr);
     for (DevBuf* b : {&h->in_x, &h->in_eta, &h->out_a, &h->out_b, &h->out_c, &h->out_f, &h->out_M, &h->tr_buf}) b->release();
     for (auto& r : h->prof.recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
@@ -296,6 +303,17 @@ extern "C" int otn_create_ex(otn_problem** out, int N, int d, int m, int K, int 
     const bool blocks_possible = (model == OTN_MODEL_FULL && (h->dim == 16 || h->dim == 8)) || (model == OTN_MODEL_LOCAL && sdim >= 8 && sdim <= 64);
     const bool enough_work = (long long)max_batch * h->D >= 4096;
     h->structured = blocks_possible && !(flags & OTN_FLAG_DENSE) && ((flags & OTN_FLAG_BLOCKS) || enough_work);
+    if (flags & OTN_FLAG_FACTORED) {
+        if (model != OTN_MODEL_LOCAL || d != 2 || (N != 4 && N != 6)) {
+            delete h;
+            return fail("OTN_FLAG_FACTORED needs the 2-site model with d = 2 and N = 4 or 6");
+        }
+        if (flags & (OTN_FLAG_DENSE | OTN_FLAG_BLOCKS)) { delete h; return fail("OTN_FLAG_FACTORED excludes OTN_FLAG_DENSE / OTN_FLAG_BLOCKS"); }
+        h->factored = true;
+        h->structured = false;
+        h->f_ncols = (N == 4) ? 8 : 1;
+        h->f_tiles = (sdim * (sdim + 1) / 2 + h->f_ncols - 1) / h->f_ncols;
+    }
     if (h->structured) {
         SymLayout& L = h->sym;
         L.dim = sdim; L.NS = sdim * (sdim + 1) / 2; L.NA = sdim * (sdim - 1) / 2;
@@ -311,6 +329,7 @@ extern "C" int otn_create_ex(otn_problem** out, int N, int d, int m, int K, int 
         h->blkTileOff[i] = h->tiles;
         h->tiles += h->blkTiles[i];
     }
+    if (h->factored) h->tiles = h->f_tiles;
     h->p = h->dim; h->n = h->dim * K; h->np = h->n * h->p;
     if (h->p > ST_MAXP) { delete h; return fail("isometry with p = %d columns > %d not supported", h->dim, ST_MAXP); }
     if (model == OTN_MODEL_LOCAL && (h->nf > 4 || h->q > 255)) { delete h; return fail("local model supports N <= 8 and d <= 3"); }
@@ -342,6 +361,19 @@ extern "C" int otn_create_ex(otn_problem** out, int N, int d, int m, int K, int 
                     tsym[(size_t)r * Dn + c] = v;
                     s += a * a;
                 }
+            }
+            if (h->factored) {
+                // tile-column layout of the columns (c1 <= c2): Tt[t][tile][r][c]
+                const int nc = h->f_ncols, tiles = h->f_tiles;
+                if (t == 0) CREATE_TRY(cudaMalloc(&h->f_Tt, (size_t)n_targets * tiles * Dn * nc * 8));
+                std::vector<double> tt((size_t)tiles * Dn * nc, 0.0);
+                int k = 0;
+                for (int c1 = 0; c1 < dm; ++c1)
+                    for (int c2 = c1; c2 < dm; ++c2, ++k) {
+                        const int col = c1 * dm + c2, tile = k / nc, c = k % nc;
+                        for (int r = 0; r < Dn; ++r) tt[((size_t)tile * Dn + r) * nc + c] = tsym[(size_t)r * Dn + col];
+                    }
+                CREATE_TRY(cudaMemcpy(h->f_Tt + (size_t)t * tt.size(), tt.data(), tt.size() * 8, cudaMemcpyHostToDevice));
             }
             if (!h->structured) {
                 CREATE_TRY(cudaMemcpy(h->T_re + (size_t)t * SZ, tsym.data(), SZ * 8, cudaMemcpyHostToDevice));
@@ -395,18 +427,62 @@ extern "C" int otn_create_ex(otn_problem** out, int N, int d, int m, int K, int 
             CREATE_TRY(cudaMalloc(&h->t2f, t2f.size() * 4));
             CREATE_TRY(cudaMemcpy(h->t2f, t2f.data(), t2f.size() * 4, cudaMemcpyHostToDevice));
         }
+        if (h->factored) {
+            const int NF = h->nf, Dn = h->D, REST = Dn / 16, nc = h->f_ncols;
+            std::vector<int> jrow(2 * NF * 16, -1), restrow((size_t)2 * NF * REST, 0);
+            for (int sh = 0; sh < 2; ++sh)
+                for (int f = 0; f < NF; ++f) {
+                    auto loc = [&](int r, int g) { return (int)((tab[(size_t)sh * Dn + r] >> (8 * g)) & 0xff); };
+                    int k = 0;
+                    for (int r = 0; r < Dn; ++r) {
+                        bool others0 = true;
+                        for (int g = 0; g < NF; ++g) if (g != f && loc(r, g) != 0) others0 = false;
+                        if (others0) jrow[(sh * NF + f) * 16 + loc(r, f)] = r;
+                        if (loc(r, f) == 0) restrow[(size_t)(sh * NF + f) * REST + k++] = r;
+                    }
+                    // the gather tables rely on the index map being a digit permutation: row = rest row + local-digit offset
+                    for (int kk = 0; kk < REST; ++kk)
+                        for (int j = 0; j < 16; ++j) {
+                            const int r0 = restrow[(size_t)(sh * NF + f) * REST + kk], r = r0 + jrow[(sh * NF + f) * 16 + j];
+                            bool ok = r >= 0 && r < Dn && loc(r, f) == j;
+                            for (int g = 0; ok && g < NF; ++g) if (g != f && loc(r, g) != loc(r0, g)) ok = false;
+                            if (!ok) { fail("factored evaluation: embedding is not a digit permutation"); return bail(-1); }
+                        }
+                }
+            std::vector<int> colidx((size_t)h->f_tiles * nc, 0), swaprow(Dn);
+            std::vector<double> colw((size_t)h->f_tiles * nc, 0.0);
+            int k = 0;
+            for (int c1 = 0; c1 < sdim; ++c1)
+                for (int c2 = c1; c2 < sdim; ++c2, ++k) { colidx[k] = c1 * sdim + c2; colw[k] = (c1 == c2) ? 0.5 : 1.0; }
+            for (int r = 0; r < Dn; ++r) swaprow[r] = (r % sdim) * sdim + r / sdim;
+            CREATE_TRY(cudaMalloc(&h->f_jrow, jrow.size() * 4));
+            CREATE_TRY(cudaMemcpy(h->f_jrow, jrow.data(), jrow.size() * 4, cudaMemcpyHostToDevice));
+            CREATE_TRY(cudaMalloc(&h->f_restrow, restrow.size() * 4));
+            CREATE_TRY(cudaMemcpy(h->f_restrow, restrow.data(), restrow.size() * 4, cudaMemcpyHostToDevice));
+            CREATE_TRY(cudaMalloc(&h->f_colidx, colidx.size() * 4));
+            CREATE_TRY(cudaMemcpy(h->f_colidx, colidx.data(), colidx.size() * 4, cudaMemcpyHostToDevice));
+            CREATE_TRY(cudaMalloc(&h->f_swaprow, swaprow.size() * 4));
+            CREATE_TRY(cudaMemcpy(h->f_swaprow, swaprow.data(), swaprow.size() * 4, cudaMemcpyHostToDevice));
+            CREATE_TRY(cudaMalloc(&h->f_colw, colw.size() * 8));
+            CREATE_TRY(cudaMemcpy(h->f_colw, colw.data(), colw.size() * 8, cudaMemcpyHostToDevice));
+            const size_t SBs = (size_t)Dn * nc;
+            if (m > 1) CREATE_TRY(cudaMalloc(&h->f_Pst, B * h->f_tiles * (M - 1) * 2 * SBs * 8));
+            CREATE_TRY(cudaMalloc(&h->f_Wp, B * h->f_tiles * M * NF * 512 * 8));
+        }
         const size_t q2 = (size_t)h->q * h->q;
         CREATE_TRY(cudaMalloc(&h->Yl, B * M * q2 * 8));
         CREATE_TRY(cudaMalloc(&h->Yld, B * M * q2 * 8));
         CREATE_TRY(cudaMalloc(&h->Wl, B * M * h->nf * q2 * 8));
         CREATE_TRY(cudaMalloc(&h->Wld, B * M * h->nf * q2 * 8));
     }
-    for (double** ptr : {&h->Y, &h->P, &h->G, &h->W, &h->Yd, &h->Pd}) {
-        CREATE_TRY(cudaMalloc(ptr, B * M * SZ * 8));
-        if (h->structured) CREATE_TRY(cudaMemset(*ptr, 0, B * M * SZ * 8));   // zero padding of the blocks is an invariant
+    if (!h->factored) {        // the factored evaluation never materialises a D x D work matrix
+        for (double** ptr : {&h->Y, &h->P, &h->G, &h->W, &h->Yd, &h->Pd}) {
+            CREATE_TRY(cudaMalloc(ptr, B * M * SZ * 8));
+            if (h->structured) CREATE_TRY(cudaMemset(*ptr, 0, B * M * SZ * 8));   // zero padding of the blocks is an invariant
+        }
+        CREATE_TRY(cudaMalloc(&h->Gd, B * 2 * SZ * 8));
+        CREATE_TRY(cudaMalloc(&h->Wd, B * SZ * 8));
     }
-    CREATE_TRY(cudaMalloc(&h->Gd, B * 2 * SZ * 8));
-    CREATE_TRY(cudaMalloc(&h->Wd, B * SZ * 8));
     if (h->structured) { CREATE_TRY(cudaMemset(h->Gd, 0, B * 2 * SZ * 8)); CREATE_TRY(cudaMemset(h->Wd, 0, B * SZ * 8)); }
     for (double** ptr : {&h->x, &h->eta, &h->zraw, &h->zdraw}) CREATE_TRY(cudaMalloc(ptr, B * M * h->np * 8));
     CREATE_TRY(cudaMalloc(&h->part_f, B * h->tiles * 8));
@@ -441,7 +517,8 @@ extern "C" int otn_query(const otn_problem* h, int* n, int* pp, int* D, int* m, 
     if (pp) *pp = h->p;
     if (D) *D = h->D;
     if (m) *m = h->m;
-    if (ws) *ws = (6LL * h->m + 3) * h->SZ * 8 + 4LL * h->m * h->np * 8;
+    if (ws) *ws = h->factored ? ((long long)h->f_tiles * (2LL * (h->m - 1) * h->D * h->f_ncols + (long long)h->m * h->nf * 512)) * 8 + 4LL * h->m * h->np * 8
+                              : (6LL * h->m + 3) * h->SZ * 8 + 4LL * h->m * h->np * 8;
     return 0;
 }
 
@@ -552,6 +629,7 @@ static int build_layers(otn_problem* h, const double* x, const double* eta, int 
         assemble_kernel<false, true><<<grid, ASM_THREADS, smem, h->stream>>>(x, eta, Yout, Ydout, ostride, h->dim, h->K, active, h->m);
     }
     CUDA_TRY(cudaGetLastError());
+    if (h->factored) return 0;                 // layers stay local (16 x 16): factored.cuh applies them factor by factor
     if (h->model == OTN_MODEL_LOCAL && h->structured) {
         dim3 g2((h->sym.NS + EMB_ROWS - 1) / EMB_ROWS, items);
         const size_t sm2 = (size_t)h->q * h->q * 8 * 2;
@@ -656,7 +734,9 @@ static int back_layer(otn_problem* h, int batch, const int* active, int l, const
         const int q2 = h->q * h->q;
         dim3 g((h->nf * q2 + 7) / 8, batch);
         const size_t sm = (size_t)q2 * 8 * 2;
-        if (h->structured && h->nf == 2 && h->q == 16) {
+        if (h->factored) {
+            // Wl / Wld already hold the per-factor local cotangents (fact_reduce_kernel)
+        } else if (h->structured && h->nf == 2 && h->q == 16) {
             const size_t sm2 = (size_t)(16 * 256 * (tangent ? 2 : 1) + 16 * 16 * 17) * 8;
             OTN_TRY(set_smem(back_embed2_sym_kernel<false>, sm2));
             OTN_TRY(set_smem(back_embed2_sym_kernel<true>, sm2));
@@ -834,11 +914,48 @@ static int riem_launch(otn_problem* h, int batch, const int* active, int tiles, 
     return 0;
 }
 
+// factored evaluation (factored.cuh): one launch does forward / residual / reverse / tangent for every column tile
+static int fact_eval(otn_problem* h, int batch, const int* active, int mode, double* Mout) {
+    FactParams p{};
+    p.Yl = h->Yl; p.Yld = h->Yld; p.Tt = h->f_Tt; p.tindex = h->tindex; p.active = active; p.jrow = h->f_jrow; p.restrow = h->f_restrow;
+    p.colidx = h->f_colidx; p.colw = h->f_colw; p.Pst = h->f_Pst; p.Wp = h->f_Wp; p.part_f = h->part_f; p.part_s = h->part_s;
+    p.part_stride = h->f_tiles; p.Mout = Mout; p.swaprow = h->f_swaprow; p.m = h->m; p.tiles = h->f_tiles;
+    const double cols = 0.5 * std::sqrt((double)h->D) * (std::sqrt((double)h->D) + 1.0);
+    // applications + contractions of 2*16*16 flops per 16-vector: forward nf (x3 dual), reverse nf(nf-1)/2 + nf + nf (x3 dual)
+    const double units = (mode == FACT_COST || mode == FACT_MODEL) ? h->nf : (h->nf + 0.5 * h->nf * (h->nf - 1) + 2.0 * h->nf) * (mode == FACT_HVP ? 3.0 : 1.0);
+    ProfScope ps(&h->prof, h->stream, CAT_GEMM, units * h->m * 2.0 * 16.0 * h->D * cols * batch);
+    dim3 grid(h->f_tiles, batch);
+#define FACT_LAUNCH(NFV, NCV, MODEV)                                                                     \
+    do {                                                                                                 \
+        const size_t sm = FactCfg<NFV, NCV, MODEV>::SMEM_BYTES;                                          \
+        OTN_TRY(set_smem(fact_kernel<NFV, NCV, MODEV>, sm));                                             \
+        fact_kernel<NFV, NCV, MODEV><<<grid, FACT_THREADS, sm, h->stream>>>(p);                          \
+    } while (0)
+#define FACT_MODE(NFV, NCV)                                                                              \
+    do {                                                                                                 \
+        if (mode == FACT_COST) FACT_LAUNCH(NFV, NCV, FACT_COST);                                         \
+        else if (mode == FACT_GRAD) FACT_LAUNCH(NFV, NCV, FACT_GRAD);                                    \
+        else if (mode == FACT_HVP) FACT_LAUNCH(NFV, NCV, FACT_HVP);                                      \
+        else FACT_LAUNCH(NFV, NCV, FACT_MODEL);                                                          \
+    } while (0)
+    if (h->nf == 2) FACT_MODE(2, 8); else FACT_MODE(3, 1);
+#undef FACT_MODE
+#undef FACT_LAUNCH
+    CUDA_TRY(cudaGetLastError());
+    if (mode == FACT_GRAD || mode == FACT_HVP) {
+        dim3 g2(h->m * h->nf, batch);
+        fact_reduce_kernel<<<g2, 256, 0, h->stream>>>(h->f_Wp, h->Wl, h->Wld, h->f_tiles, h->m, h->nf, mode == FACT_HVP, active);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return 0;
+}
+
 // device-level building blocks shared with the trust-region driver
 int otn_dev_cost(otn_problem* h, const double* x, int batch, const int* active, double* f) {
     int tiles;
     OTN_TRY(build_layers(h, x, nullptr, batch, active, true));
-    OTN_TRY(forward_chain(h, batch, active, false, &tiles));
+    if (h->factored) { OTN_TRY(fact_eval(h, batch, active, FACT_COST, nullptr)); tiles = h->f_tiles; }
+    else OTN_TRY(forward_chain(h, batch, active, false, &tiles));
     ProfScope ps(&h->prof, h->stream, CAT_OTHER, 0.0);
     cost_from_partials_kernel<<<(batch + 127) / 128, 128, 0, h->stream>>>(h->part_f, tiles, h->im2, h->tindex, f, batch, active);
     CUDA_TRY(cudaGetLastError());
@@ -848,14 +965,26 @@ int otn_dev_cost(otn_problem* h, const double* x, int batch, const int* active, 
 int otn_dev_cost_grad(otn_problem* h, const double* x, int batch, const int* active, double* f, double* rgrad, double* egrad) {
     int tiles;
     OTN_TRY(build_layers(h, x, nullptr, batch, active, true));
-    OTN_TRY(forward_chain(h, batch, active, false, &tiles));
-    OTN_TRY(reverse_chain(h, batch, active, x));
+    if (h->factored) {
+        OTN_TRY(fact_eval(h, batch, active, FACT_GRAD, nullptr));
+        tiles = h->f_tiles;
+        for (int l = h->m - 1; l >= 0; --l) OTN_TRY(back_layer(h, batch, active, l, x, false, nullptr));
+    } else {
+        OTN_TRY(forward_chain(h, batch, active, false, &tiles));
+        OTN_TRY(reverse_chain(h, batch, active, x));
+    }
     OTN_TRY(riem_launch(h, batch, active, tiles, x, nullptr, false, f, rgrad, egrad, nullptr));
     h->tr.tiles = tiles;
     return 0;
 }
 int otn_dev_hvp(otn_problem* h, const double* x, const double* eta, int batch, const int* active, double* heta) {
-    OTN_TRY(tangent_pass(h, batch, active, x, eta, false));
+    if (h->factored) {          // primal recomputed alongside the tangent (dual numbers); zraw is the cached primal pull-back
+        OTN_TRY(build_layers(h, x, eta, batch, active, true));
+        OTN_TRY(fact_eval(h, batch, active, FACT_HVP, nullptr));
+        for (int l = h->m - 1; l >= 0; --l) OTN_TRY(back_layer(h, batch, active, l, x, true, eta));
+    } else {
+        OTN_TRY(tangent_pass(h, batch, active, x, eta, false));
+    }
     OTN_TRY(riem_launch(h, batch, active, h->tr.tiles, x, eta, true, nullptr, nullptr, nullptr, heta));
     return 0;
 }
@@ -881,8 +1010,12 @@ extern "C" int otn_model(otn_problem* h, const double* x, int batch, double* M) 
     const size_t mbytes = (size_t)batch * h->D * h->D * 8;
     OTN_TRY(stage_out(M, mbytes, h->out_M, &Md));
     OTN_TRY(build_layers(h, (const double*)xd, nullptr, batch, nullptr, true));
-    OTN_TRY(forward_chain(h, batch, nullptr, true, &tiles));
-    OTN_TRY(export_model(h, batch, (double*)Md));
+    if (h->factored) {
+        OTN_TRY(fact_eval(h, batch, nullptr, FACT_MODEL, (double*)Md));
+    } else {
+        OTN_TRY(forward_chain(h, batch, nullptr, true, &tiles));
+        OTN_TRY(export_model(h, batch, (double*)Md));
+    }
     OTN_TRY(finish_out(M, Md, mbytes, h->stream));
     h->cached_batch = 0;
     CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -926,6 +1059,16 @@ static int triple_device(otn_problem* h, const double* x, const double* eta, int
     int tiles;
     // primal + tangent layers in one assembly pass, then forward / reverse / tangent chains
     OTN_TRY(build_layers(h, x, eta, batch, nullptr, true));
+    if (h->factored) {
+        OTN_TRY(fact_eval(h, batch, nullptr, FACT_HVP, nullptr));
+        h->tr.tiles = tiles = h->f_tiles;
+        for (int l = h->m - 1; l >= 0; --l) {
+            OTN_TRY(back_layer(h, batch, nullptr, l, x, false, nullptr));
+            OTN_TRY(back_layer(h, batch, nullptr, l, x, true, eta));
+        }
+        OTN_TRY(riem_launch(h, batch, nullptr, tiles, x, eta, true, f, rgrad, nullptr, heta));
+        return 0;
+    }
     OTN_TRY(forward_chain(h, batch, nullptr, false, &tiles));
     h->tr.tiles = tiles;
     const bool joint = h->structured && h->model == OTN_MODEL_FULL;   // W_l is pulled back against x and eta in one pass

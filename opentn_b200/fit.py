@@ -68,7 +68,7 @@ class StiefelFit:
     batch selects its own through `target_index`.
     """
 
-    def __init__(self, target, model="local", N=None, d=2, metric="canonical", max_batch=1, device=0, dense=None):
+    def __init__(self, target, model="local", N=None, d=2, metric="canonical", max_batch=1, device=0, dense=None, factored=False):
         if model not in ("local", "full"):
             raise ValueError("model must be 'local' or 'full'")
         t = np.asarray(target)
@@ -89,6 +89,9 @@ class StiefelFit:
         # dense=True: force the dense D x D chain; False: force the block-diagonal evaluation; None: let the library choose
         # (blocks when the batch is large enough to fill the GPU)
         self.dense = dense
+        # factored=True (2-site model, d = 2, N = 4 or 6): never form a D x D layer or chain product; every 16 x 16 local
+        # superoperator is applied to the columns of the running product one factor at a time (csrc/factored.cuh)
+        self.factored = bool(factored)
         self.max_batch = max_batch
         self._t_re = np.ascontiguousarray(t.real, dtype=np.float64)
         self._t_im = np.ascontiguousarray(t.imag, dtype=np.float64) if np.iscomplexobj(t) and np.any(t.imag) else None
@@ -110,7 +113,8 @@ class StiefelFit:
             cap = max(batch, self.max_batch)
             h = _Handle(self.N, self.d, m, K, MODEL_LOCAL if self.model == "local" else MODEL_FULL, metric_id(self.metric),
                         cap, self._t_re, self._t_im, self.device,
-                        0 if self.dense is None else (_lib.FLAG_DENSE if self.dense else _lib.FLAG_BLOCKS))
+                        _lib.FLAG_FACTORED if self.factored else
+                        (0 if self.dense is None else (_lib.FLAG_DENSE if self.dense else _lib.FLAG_BLOCKS)))
             h.tindex_ver = 0
             self._handles[key] = h
         return h
