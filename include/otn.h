@@ -52,7 +52,8 @@ int otn_create(otn_problem** out, int N, int d, int m, int K, int model, int met
  * superoperators are applied factor by factor to the columns of the running product, each CTA owning a tile of columns for the
  * whole forward / reverse / tangent evaluation (opentn_b200/csrc/factored.cuh): 2*16*D instead of 2*D^2 flops per column and
  * factor, and O(D * columns) instead of O(m D^2) memory per instance. */
-enum { OTN_FLAG_DENSE = 1, OTN_FLAG_BLOCKS = 2, OTN_FLAG_FACTORED = 4 };   /* neither: blocks when max_batch * D >= 4096 (enough work to fill the GPU) */
+enum { OTN_FLAG_DENSE = 1, OTN_FLAG_BLOCKS = 2, OTN_FLAG_FACTORED = 4 };   /* none: factored where it applies, else blocks when
+                                                                            * max_batch * D >= 4096 (enough work to fill the GPU) */
 int otn_create_ex(otn_problem** out, int N, int d, int m, int K, int model, int metric, int max_batch, int n_targets,
                   const double* target_re, const double* target_im, int device, int flags);
 void otn_destroy(otn_problem* p);
