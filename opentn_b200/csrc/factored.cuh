@@ -46,55 +46,99 @@ struct FactParams {
 
 template <int NF> struct FactDims { static constexpr int D = (NF == 2) ? 256 : 4096; static constexpr int REST = D / 16; };
 
-// dst = A src (and dstd = Ad src + A srcd) on factor `f`; A = Y or Y^T (16 x 16 in shared memory).  May run in place.
-template <int NF, int NCOLS, bool DUAL>
-__device__ __forceinline__ void fact_apply(const double* src, const double* srcd, double* dst, double* dstd,
-                                           const double* __restrict__ Ysm, const double* __restrict__ Ydsm, bool trans,
-                                           const int* __restrict__ jrow, const int* __restrict__ restrow) {
-    constexpr int NV = FactDims<NF>::REST * NCOLS;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, lr = lane >> 2, lc = lane & 3;
-    double a[2][4], ad[2][4];
+// Shared-memory layout of a state: element (row r, column c) lives at (r * NCOLS + c) ^ fact_swz(r).  The XOR mask is linear in
+// the bits of r and chosen so that the 16 addresses a half-warp touches in every fragment load -- 4 rows that differ in the two
+// low bits of a factor's local index (bra bits of the pair's sites, wherever the permutation puts them) x 4 consecutive columns /
+// rest indices -- fall into 16 different 8-byte banks (ncu before the swizzle: 5-way conflicts, L1 pipe 84 % busy).
+template <int NF, int NCOLS>
+__device__ __forceinline__ int fact_swz(int r) {
+    if (NF == 2) return ((((r >> 1) ^ (r >> 2) ^ (r >> 3)) & 1) << 3) | ((((r >> 1) ^ (r >> 3)) & 1) << 2);   // NCOLS == 8
+    return ((r >> 4) & 3) << 2;                                                                             // NCOLS == 1
+}
+
+constexpr int FACT_YLD = 20;   // row pitch of the staged 16 x 16 local superoperators (+4: conflict-free fragment reads)
+
+// A-operand fragments of the local superoperator (or its transpose), and of its tangent: lane holds A[8 mt + l/4][4 ks + l%4]
+template <bool DUAL>
+__device__ __forceinline__ void fact_frags(const double* __restrict__ Ysm, const double* __restrict__ Ydsm, bool trans,
+                                           double (&a)[2][4], double (&ad)[2][4]) {
+    const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
             const int r = 8 * mt + lr, c = 4 * ks + lc;
-            const int idx = trans ? c * 16 + r : r * 16 + c;
+            const int idx = trans ? c * FACT_YLD + r : r * FACT_YLD + c;
             a[mt][ks] = Ysm[idx];
-            if (DUAL) ad[mt][ks] = Ydsm[idx];
+            ad[mt][ks] = DUAL ? Ydsm[idx] : 0.0;
         }
-    int jb[4], jc[2];
+}
+
+// dst = A src (and dstd = Ad src + A srcd) on one factor; A given as fragments.  May run in place: a warp reads all 16 entries
+// of its vectors before it writes them.  Two n-tiles (16 vectors) per step for instruction-level parallelism.
+template <int NF, int NCOLS, bool DUAL>
+__device__ __forceinline__ void fact_apply(const double* src, const double* srcd, double* dst, double* dstd,
+                                           const double (&a)[2][4], const double (&ad)[2][4],
+                                           const int* __restrict__ jrow, const int* __restrict__ restrow) {
+    constexpr int NV = FactDims<NF>::REST * NCOLS, NT = NV / 8, U = 2;
+    static_assert(NT % (FACT_WARPS * U) == 0, "n-tiles must split evenly over the warps");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, lr = lane >> 2, lc = lane & 3;
+    int jb[4], sb[4], jc[2], sc[2];
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) jb[ks] = jrow[4 * ks + lc] * NCOLS;
+    for (int ks = 0; ks < 4; ++ks) { const int j = jrow[4 * ks + lc]; jb[ks] = j * NCOLS; sb[ks] = fact_swz<NF, NCOLS>(j); }
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) jc[mt] = jrow[8 * mt + lr] * NCOLS;
-    for (int nt = warp; nt < NV / 8; nt += FACT_WARPS) {
-        const int v = 8 * nt + lr;
-        const int base = restrow[v / NCOLS] * NCOLS + (v % NCOLS);
-        double b[4], bd[4];
+    for (int mt = 0; mt < 2; ++mt) { const int j = jrow[8 * mt + lr]; jc[mt] = j * NCOLS; sc[mt] = fact_swz<NF, NCOLS>(j); }
+#pragma unroll 1
+    for (int nt0 = warp * U; nt0 < NT; nt0 += FACT_WARPS * U) {
+        double b[U][4], bd[U][4];
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-            b[ks] = src[base + jb[ks]];
-            if (DUAL) bd[ks] = srcd[base + jb[ks]];
+        for (int u = 0; u < U; ++u) {
+            const int v = 8 * (nt0 + u) + lr;
+            const int rr = restrow[v / NCOLS];
+            const int base = rr * NCOLS + (v % NCOLS), sr = fact_swz<NF, NCOLS>(rr);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const int a_ = (base + jb[ks]) ^ sr ^ sb[ks];
+                b[u][ks] = src[a_];
+                if (DUAL) bd[u][ks] = srcd[a_];
+            }
         }
-        double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, cd[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        double c[U][2][2], cd[U][2][2], ce[U][2][2];      // cd: Ad b, ce: A bd (separate dependency chains)
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) { c[u][mt][0] = c[u][mt][1] = 0.0; cd[u][mt][0] = cd[u][mt][1] = 0.0; ce[u][mt][0] = ce[u][mt][1] = 0.0; }
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
 #pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    dmma884(c[u][mt][0], c[u][mt][1], a[mt][ks], b[u][ks]);
+                    if (DUAL) {
+                        dmma884(cd[u][mt][0], cd[u][mt][1], ad[mt][ks], b[u][ks]);
+                        dmma884(ce[u][mt][0], ce[u][mt][1], a[mt][ks], bd[u][ks]);
+                    }
+                }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int v0 = 8 * (nt0 + u) + 2 * lc, v1 = v0 + 1;
+            const int r0 = restrow[v0 / NCOLS], r1 = restrow[v1 / NCOLS];
+            const int b0 = r0 * NCOLS + (v0 % NCOLS), b1 = r1 * NCOLS + (v1 % NCOLS);
+            const int s0 = fact_swz<NF, NCOLS>(r0), s1 = fact_swz<NF, NCOLS>(r1);
+#pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
-                dmma884(c[mt][0], c[mt][1], a[mt][ks], b[ks]);
-                if (DUAL) {
-                    dmma884(cd[mt][0], cd[mt][1], ad[mt][ks], b[ks]);
-                    dmma884(cd[mt][0], cd[mt][1], a[mt][ks], bd[ks]);
+                if (NCOLS % 2 == 0) {               // both columns of the fragment sit in the same row: one 16-byte store
+                    const int a_ = (b0 + jc[mt]) ^ s0 ^ sc[mt];
+                    *reinterpret_cast<double2*>(dst + a_) = make_double2(c[u][mt][0], c[u][mt][1]);
+                    if (DUAL) *reinterpret_cast<double2*>(dstd + a_) = make_double2(cd[u][mt][0] + ce[u][mt][0], cd[u][mt][1] + ce[u][mt][1]);
+                } else {
+                    const int a0 = (b0 + jc[mt]) ^ s0 ^ sc[mt], a1 = (b1 + jc[mt]) ^ s1 ^ sc[mt];
+                    dst[a0] = c[u][mt][0];
+                    dst[a1] = c[u][mt][1];
+                    if (DUAL) { dstd[a0] = cd[u][mt][0] + ce[u][mt][0]; dstd[a1] = cd[u][mt][1] + ce[u][mt][1]; }
                 }
             }
-        const int v0 = 8 * nt + 2 * lc, v1 = v0 + 1;
-        const int b0 = restrow[v0 / NCOLS] * NCOLS + (v0 % NCOLS), b1 = restrow[v1 / NCOLS] * NCOLS + (v1 % NCOLS);
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-            dst[b0 + jc[mt]] = c[mt][0];
-            dst[b1 + jc[mt]] = c[mt][1];
-            if (DUAL) { dstd[b0 + jc[mt]] = cd[mt][0]; dstd[b1 + jc[mt]] = cd[mt][1]; }
         }
     }
 }
@@ -106,20 +150,23 @@ __device__ __forceinline__ void fact_contract(const double* X, const double* Xd,
                                               double (&acc)[2][2][2], double (&accd)[2][2][2]) {
     constexpr int NV = FactDims<NF>::REST * NCOLS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, lr = lane >> 2, lc = lane & 3;
-    const int ro[2] = {jrow[lr] * NCOLS, jrow[8 + lr] * NCOLS};
+    const int j0 = jrow[lr], j1 = jrow[8 + lr];
+    const int ro[2] = {j0 * NCOLS, j1 * NCOLS}, so[2] = {fact_swz<NF, NCOLS>(j0), fact_swz<NF, NCOLS>(j1)};
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) { acc[mt][nt][0] = acc[mt][nt][1] = 0.0; accd[mt][nt][0] = accd[mt][nt][1] = 0.0; }
     for (int kv = warp; kv < NV / 4; kv += FACT_WARPS) {
         const int v = 4 * kv + lc;
-        const int base = restrow[v / NCOLS] * NCOLS + (v % NCOLS);
+        const int rr = restrow[v / NCOLS];
+        const int base = rr * NCOLS + (v % NCOLS), sr = fact_swz<NF, NCOLS>(rr);
         double x[2], z[2], xd[2], zd[2];
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
-            x[t] = X[base + ro[t]];
-            z[t] = Z[base + ro[t]];
-            if (DUAL) { xd[t] = Xd[base + ro[t]]; zd[t] = Zd[base + ro[t]]; }
+            const int a_ = (base + ro[t]) ^ sr ^ so[t];
+            x[t] = X[a_];
+            z[t] = Z[a_];
+            if (DUAL) { xd[t] = Xd[a_]; zd[t] = Zd[a_]; }
         }
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
@@ -140,11 +187,11 @@ struct FactCfg {
     static constexpr int SB = D * NCOLS;                                   // doubles per state buffer
     static constexpr int NBUF = (MODE == FACT_HVP) ? 6 : (MODE == FACT_GRAD ? 3 : 1);
     static constexpr int TAB_INTS = 2 * NF * 16 + 2 * NF * (D / 16);
-    static constexpr size_t SMEM_BYTES = (size_t)NBUF * SB * 8 + 2 * 256 * 8 + (size_t)TAB_INTS * 4 + 64 * 8;
+    static constexpr size_t SMEM_BYTES = (size_t)NBUF * SB * 8 + 2 * 16 * FACT_YLD * 8 + (size_t)TAB_INTS * 4 + 64 * 8;
 };
 
 template <int NF, int NCOLS, int MODE>
-__global__ void __launch_bounds__(FACT_THREADS) fact_kernel(const FactParams p) {
+__global__ void __launch_bounds__(FACT_THREADS, (NF == 2 ? 2 : 1)) fact_kernel(const FactParams p) {
     using Cfg = FactCfg<NF, NCOLS, MODE>;
     constexpr int D = Cfg::D, SB = Cfg::SB, REST = D / 16;
     constexpr bool DUAL = MODE == FACT_HVP;
@@ -160,8 +207,8 @@ __global__ void __launch_bounds__(FACT_THREADS) fact_kernel(const FactParams p) 
     double* tmp = REV ? P + (DUAL ? 2 : 1) * SB : nullptr;
     double* tmpd = DUAL ? tmp + SB : nullptr;
     double* Ysm = fsm + (size_t)Cfg::NBUF * SB;
-    double* Ydsm = Ysm + 256;
-    double* red = Ydsm + 256;                       // 64 doubles
+    double* Ydsm = Ysm + 16 * FACT_YLD;
+    double* red = Ydsm + 16 * FACT_YLD;             // 64 doubles
     int* jrow_s = reinterpret_cast<int*>(red + 64); // [2][NF][16]
     int* rest_s = jrow_s + 2 * NF * 16;             // [2][NF][REST]
     for (int i = tid; i < 2 * NF * 16; i += FACT_THREADS) jrow_s[i] = p.jrow[i];
@@ -171,7 +218,7 @@ __global__ void __launch_bounds__(FACT_THREADS) fact_kernel(const FactParams p) 
     // identity columns
     for (int i = tid; i < SB; i += FACT_THREADS) {
         const int r = i / NCOLS, c = i % NCOLS;
-        G[i] = (r == cidx[c]) ? 1.0 : 0.0;
+        G[i ^ fact_swz<NF, NCOLS>(r)] = (r == cidx[c]) ? 1.0 : 0.0;
         if (DUAL) Gd[i] = 0.0;
     }
     const double* Yb = p.Yl + (size_t)b * p.m * 256;
@@ -181,8 +228,8 @@ __global__ void __launch_bounds__(FACT_THREADS) fact_kernel(const FactParams p) 
     // ---- forward ----------------------------------------------------------------------------------------------------
     for (int l = 0; l < p.m; ++l) {
         __syncthreads();                            // previous layer done with Ysm; state complete
-        Ysm[tid] = Yb[(size_t)l * 256 + tid];
-        if (DUAL) Ydsm[tid] = Ydb[(size_t)l * 256 + tid];
+        Ysm[(tid >> 4) * FACT_YLD + (tid & 15)] = Yb[(size_t)l * 256 + tid];
+        if (DUAL) Ydsm[(tid >> 4) * FACT_YLD + (tid & 15)] = Ydb[(size_t)l * 256 + tid];
         if (REV && l >= 1) {                        // state entering layer l
             double* dstp = scratch + (size_t)(l - 1) * 2 * SB;
             for (int i = tid * 2; i < SB; i += FACT_THREADS * 2) {
@@ -192,9 +239,11 @@ __global__ void __launch_bounds__(FACT_THREADS) fact_kernel(const FactParams p) 
         }
         __syncthreads();
         const int sh = l & 1;
+        double a[2][4], ad[2][4];
+        fact_frags<DUAL>(Ysm, Ydsm, false, a, ad);
 #pragma unroll 1
         for (int g = NF - 1; g >= 0; --g) {
-            fact_apply<NF, NCOLS, DUAL>(G, Gd, G, Gd, Ysm, Ydsm, false, jrow_s + (sh * NF + g) * 16, rest_s + (sh * NF + g) * REST);
+            fact_apply<NF, NCOLS, DUAL>(G, Gd, G, Gd, a, ad, jrow_s + (sh * NF + g) * 16, rest_s + (sh * NF + g) * REST);
             __syncthreads();
         }
     }
@@ -204,8 +253,9 @@ __global__ void __launch_bounds__(FACT_THREADS) fact_kernel(const FactParams p) 
             const int r = i / NCOLS, c = i % NCOLS;
             if (cw[c] == 0.0) continue;
             const int col = cidx[c];
-            Mb[(size_t)r * D + col] = G[i];
-            Mb[(size_t)p.swaprow[r] * D + p.swaprow[col]] = G[i];
+            const double val = G[i ^ fact_swz<NF, NCOLS>(r)];
+            Mb[(size_t)r * D + col] = val;
+            Mb[(size_t)p.swaprow[r] * D + p.swaprow[col]] = val;
         }
         return;
     }
@@ -215,10 +265,11 @@ __global__ void __launch_bounds__(FACT_THREADS) fact_kernel(const FactParams p) 
         double sf = 0.0, ss = 0.0;
         for (int i = tid; i < SB; i += FACT_THREADS) {
             const double w = cw[i % NCOLS];
-            const double r = G[i] - Tt[i];
+            const int ip = i ^ fact_swz<NF, NCOLS>(i / NCOLS);
+            const double r = G[ip] - Tt[i];
             sf = fma(2.0 * w * r, r, sf);
-            if (REV) G[i] = w * r;
-            if (DUAL) { const double sd = Gd[i]; ss = fma(2.0 * w * r, sd, ss); Gd[i] = w * sd; }
+            if (REV) G[ip] = w * r;
+            if (DUAL) { const double sd = Gd[ip]; ss = fma(2.0 * w * r, sd, ss); Gd[ip] = w * sd; }
         }
         sf = warp_sum(sf);
         if (DUAL) ss = warp_sum(ss);
@@ -238,8 +289,8 @@ __global__ void __launch_bounds__(FACT_THREADS) fact_kernel(const FactParams p) 
 #pragma unroll 1
     for (int l = p.m - 1; l >= 0; --l) {
         __syncthreads();
-        Ysm[tid] = Yb[(size_t)l * 256 + tid];
-        if (DUAL) Ydsm[tid] = Ydb[(size_t)l * 256 + tid];
+        Ysm[(tid >> 4) * FACT_YLD + (tid & 15)] = Yb[(size_t)l * 256 + tid];
+        if (DUAL) Ydsm[(tid >> 4) * FACT_YLD + (tid & 15)] = Ydb[(size_t)l * 256 + tid];
         if (l >= 1) {
             const double* srcp = scratch + (size_t)(l - 1) * 2 * SB;
             for (int i = tid * 2; i < SB; i += FACT_THREADS * 2) {
@@ -248,7 +299,7 @@ __global__ void __launch_bounds__(FACT_THREADS) fact_kernel(const FactParams p) 
             }
         } else {
             for (int i = tid; i < SB; i += FACT_THREADS) {
-                P[i] = ((i / NCOLS) == cidx[i % NCOLS]) ? 1.0 : 0.0;
+                P[i ^ fact_swz<NF, NCOLS>(i / NCOLS)] = ((i / NCOLS) == cidx[i % NCOLS]) ? 1.0 : 0.0;
                 if (DUAL) Pd[i] = 0.0;
             }
         }
@@ -258,10 +309,12 @@ __global__ void __launch_bounds__(FACT_THREADS) fact_kernel(const FactParams p) 
         for (int f = 0; f < NF; ++f) {
             const double* Fs = P; const double* Fds = Pd;
             if (f < NF - 1) {                       // tmp = (factors NF-1 .. f+1) applied to P
+                double a[2][4], ad[2][4];
+                fact_frags<DUAL>(Ysm, Ydsm, false, a, ad);
 #pragma unroll 1
                 for (int g = NF - 1; g > f; --g) {
                     const bool first = (g == NF - 1);
-                    fact_apply<NF, NCOLS, DUAL>(first ? P : tmp, first ? Pd : tmpd, tmp, tmpd, Ysm, Ydsm, false,
+                    fact_apply<NF, NCOLS, DUAL>(first ? P : tmp, first ? Pd : tmpd, tmp, tmpd, a, ad,
                                                 jrow_s + (sh * NF + g) * 16, rest_s + (sh * NF + g) * REST);
                     __syncthreads();
                 }
@@ -295,7 +348,9 @@ __global__ void __launch_bounds__(FACT_THREADS) fact_kernel(const FactParams p) 
             }
             __syncthreads();
             if (!(l == 0 && f == NF - 1)) {         // B_{f+1} = A_f^T B_f
-                fact_apply<NF, NCOLS, DUAL>(G, Gd, G, Gd, Ysm, Ydsm, true, jrow_s + (sh * NF + f) * 16, rest_s + (sh * NF + f) * REST);
+                double at[2][4], adt[2][4];
+                fact_frags<DUAL>(Ysm, Ydsm, true, at, adt);
+                fact_apply<NF, NCOLS, DUAL>(G, Gd, G, Gd, at, adt, jrow_s + (sh * NF + f) * 16, rest_s + (sh * NF + f) * REST);
                 __syncthreads();
             }
         }
