@@ -246,6 +246,55 @@ def measure_fp64_peak(torch):
     return 2 * n ** 3 / best / 1e9  # TFLOP/s
 
 
+def two_site_leg(torch, lib, C, _lib, StiefelFit, T, stream, device, peak_tf, steps):
+    """U1 throughput of the 2-site model on a config-4-shaped batch (1024 instances of 9 layers (64, 4)): the factored evaluation
+    (csrc/factored.cuh, default) against the block-diagonal D x D chain, device-resident inputs, CUDA events."""
+    import numpy as np
+    from opentn_b200 import optimization as O
+    from opentn_b200 import stiefel as S
+    B, K, m, tau = 1024, 16, 9, 0.5
+    target = T.exp_operator_dt(T.create_kitaev_liouvillians(N_SITES, D_LOC, 1.0, pbc=True)[0], tau)
+    xs0 = np.array([T.super2ortho(x.real, rank=K) for x in O.get_kitaev_trotter_local_ansatz(1.0, tau, (m - 1) // 2)])
+    xs = np.empty((B,) + xs0.shape)
+    et = np.empty_like(xs)
+    for b in range(B):                     # start = Trotter point retracted after a random tangent kick of norm 1e-2 (SURVEY C4)
+        rng = np.random.default_rng(b)
+        kick = np.array([S.project(x, rng.standard_normal(x.shape)) for x in xs0])
+        kick *= 1e-2 / np.sqrt(sum(S.canonical_metric(k, k, x) for k, x in zip(kick, xs0)))
+        u, _, vt = np.linalg.svd(xs0 + kick, full_matrices=False)
+        xs[b] = u @ vt
+        et[b] = np.array([S.project(x, rng.standard_normal(x.shape)) for x in xs[b]])
+    x = torch.from_numpy(xs).cuda(); e = torch.from_numpy(et).cuda()
+    f = torch.empty(B, dtype=torch.float64, device="cuda"); g = torch.empty_like(x); h = torch.empty_like(x)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    out = {"workload": f"Kitaev gamma=1 N=4 tau={tau} pbc, 2-site ansatz m={m} K={K}, x[B,{m},{4 * K},4], B={B}", "unit": UNIT, "steps": steps}
+    for name, kw in (("factored", dict(factored=True)), ("block_diagonal", dict(dense=False))):
+        fit = StiefelFit(target, model="local", N=N_SITES, d=D_LOC, metric="canonical", max_batch=B, device=device, **kw)
+        hd = fit._handle(m, K, B)
+        _lib.check(lib.otn_set_stream(hd.h, C.c_void_p(stream.cuda_stream)))
+        step = lambda: _lib.check(lib.otn_triple(hd.h, x.data_ptr(), e.data_ptr(), B, f.data_ptr(), g.data_ptr(), h.data_ptr()))
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        lib.otn_profile_enable(hd.h, 1)
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        pms = (C.c_double * 6)(); pln = (C.c_longlong * 6)(); pfl = (C.c_double * 6)()
+        _lib.check(lib.otn_profile_read(hd.h, pms, pln, pfl))
+        lib.otn_profile_enable(hd.h, 0)
+        ach = pfl[0] / (pms[0] * 1e-3) / 1e12
+        out[name] = {"value": B / (ms * 1e-3), "ms_per_step": ms, "dominant_kernel_ms_per_step": pms[0] / steps,
+                     "dominant_kernel_tflops_executed": ach, "frac_of_fp64_peak": ach / peak_tf if peak_tf else None,
+                     "dense_equivalent_tflops": (9 * (m - 1) * 2 * 256.0 ** 3) * B / (ms * 1e-3) / 1e12}
+        fit.close()
+    out["speedup_factored_vs_block_diagonal"] = out["factored"]["value"] / out["block_diagonal"]["value"]
+    return out
+
+
 def run_gpu(args):
     import ctypes as C
 
@@ -392,6 +441,12 @@ def run_gpu(args):
         dense_raw = timed_device_steps(handle_d, d_steps, min(0.2, args.min_warm_s)) + (d_steps,)
         fit_d.close()
 
+    # ---- 2-site model (BASELINE config 4 shape: Kitaev pbc, tau = 0.5, m = 9, K = 16): factored vs block-diagonal chain ------
+    two_site = None
+    if not args.no_local and rank == 0 and world == 1:
+        torch.cuda.empty_cache()
+        two_site = two_site_leg(torch, lib, C, _lib, StiefelFit, T, stream, local_rank, peak_tf, max(5, args.steps // 5))
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -463,7 +518,8 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
-            "roofline": roofline, "dense_formulation": dense_leg, "cpu_baseline": cpu, "tr": tr, "final_gather_ms": gather_ms}
+            "roofline": roofline, "dense_formulation": dense_leg, "cpu_baseline": cpu, "tr": tr, "final_gather_ms": gather_ms,
+            "two_site_model": two_site}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -479,6 +535,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-tr", action="store_true", help="skip the TR iterations/s leg")
     ap.add_argument("--no-dense", action="store_true", help="skip the dense-formulation comparison leg")
+    ap.add_argument("--no-local", action="store_true", help="skip the 2-site-model (factored evaluation) leg")
     ap.add_argument("--min-warm-s", type=float, default=0.5,
                     help="keep warming up until this many seconds under load have passed (0 = exactly --warmup steps, for profilers)")
     args = ap.parse_args()
