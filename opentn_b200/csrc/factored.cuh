@@ -25,7 +25,7 @@
 
 namespace otn {
 
-enum { FACT_COST = 0, FACT_GRAD = 1, FACT_HVP = 2, FACT_MODEL = 3 };
+enum { FACT_COST = 0, FACT_GRAD = 1, FACT_HVP = 2, FACT_MODEL = 3, FACT_HVPONLY = 4 };   // HVPONLY: tangent cotangents only (tCG)
 constexpr int FACT_THREADS = 256;
 constexpr int FACT_WARPS = FACT_THREADS / 32;
 
@@ -144,7 +144,7 @@ __device__ __forceinline__ void fact_apply(const double* src, const double* srcd
 }
 
 // acc[i][j] += sum_v X[i, v] Z[j, v]   (and accd += Xd Z + X Zd) over the vectors of factor `f` handled by this warp
-template <int NF, int NCOLS, bool DUAL>
+template <int NF, int NCOLS, bool DUAL, bool PRIMAL>
 __device__ __forceinline__ void fact_contract(const double* X, const double* Xd, const double* Z, const double* Zd,
                                               const int* __restrict__ jrow, const int* __restrict__ restrow,
                                               double (&acc)[2][2][2], double (&accd)[2][2][2]) {
@@ -172,7 +172,7 @@ __device__ __forceinline__ void fact_contract(const double* X, const double* Xd,
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
-                dmma884(acc[mt][nt][0], acc[mt][nt][1], x[mt], z[nt]);
+                if (PRIMAL) dmma884(acc[mt][nt][0], acc[mt][nt][1], x[mt], z[nt]);
                 if (DUAL) {
                     dmma884(accd[mt][nt][0], accd[mt][nt][1], xd[mt], z[nt]);
                     dmma884(accd[mt][nt][0], accd[mt][nt][1], x[mt], zd[nt]);
@@ -185,7 +185,7 @@ template <int NF, int NCOLS, int MODE>
 struct FactCfg {
     static constexpr int D = FactDims<NF>::D;
     static constexpr int SB = D * NCOLS;                                   // doubles per state buffer
-    static constexpr int NBUF = (MODE == FACT_HVP) ? 6 : (MODE == FACT_GRAD ? 3 : 1);
+    static constexpr int NBUF = (MODE == FACT_HVP || MODE == FACT_HVPONLY) ? 6 : (MODE == FACT_GRAD ? 3 : 1);
     static constexpr int TAB_INTS = 2 * NF * 16 + 2 * NF * (D / 16);
     static constexpr size_t SMEM_BYTES = (size_t)NBUF * SB * 8 + 2 * 16 * FACT_YLD * 8 + (size_t)TAB_INTS * 4 + 64 * 8;
 };
@@ -194,8 +194,9 @@ template <int NF, int NCOLS, int MODE>
 __global__ void __launch_bounds__(FACT_THREADS, (NF == 2 ? 2 : 1)) fact_kernel(const FactParams p) {
     using Cfg = FactCfg<NF, NCOLS, MODE>;
     constexpr int D = Cfg::D, SB = Cfg::SB, REST = D / 16;
-    constexpr bool DUAL = MODE == FACT_HVP;
-    constexpr bool REV = MODE == FACT_GRAD || MODE == FACT_HVP;
+    constexpr bool DUAL = MODE == FACT_HVP || MODE == FACT_HVPONLY;
+    constexpr bool REV = MODE == FACT_GRAD || DUAL;
+    constexpr bool PRIMALW = MODE != FACT_HVPONLY;
     const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     if (p.active != nullptr && p.active[b] == 0) return;
     extern __shared__ __align__(16) double fsm[];
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(FACT_THREADS, (NF == 2 ? 2 : 1)) fact_kernel(c
                 Fs = tmp; Fds = tmpd;
             }
             double acc[2][2][2], accd[2][2][2];
-            fact_contract<NF, NCOLS, DUAL>(G, Gd, Fs, Fds, jrow_s + (sh * NF + f) * 16, rest_s + (sh * NF + f) * REST, acc, accd);
+            fact_contract<NF, NCOLS, DUAL, PRIMALW>(G, Gd, Fs, Fds, jrow_s + (sh * NF + f) * 16, rest_s + (sh * NF + f) * REST, acc, accd);
             __syncthreads();                        // tmp no longer read: reuse it for the per-warp partials
             double* part = tmp + (size_t)warp * (DUAL ? 512 : 256);
 #pragma unroll
@@ -330,20 +331,22 @@ __global__ void __launch_bounds__(FACT_THREADS, (NF == 2 ? 2 : 1)) fact_kernel(c
                 for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        const int idx = (8 * mt + lr) * 16 + 8 * nt + 2 * lc + e;
-                        part[idx] = acc[mt][nt][e];
+                        // column XOR-swizzled by the row so that the 8 rows of a fragment store hit different banks
+                        const int idx = (8 * mt + lr) * 16 + ((8 * nt + 2 * lc + e) ^ ((lr & 1) | ((lr & 2) << 2)));
+                        if (PRIMALW) part[idx] = acc[mt][nt][e];
                         if (DUAL) part[256 + idx] = accd[mt][nt][e];
                     }
             __syncthreads();
             {
                 double s = 0.0, sd = 0.0;
+                const int row = tid >> 4, ti = (tid & ~15) | ((tid & 15) ^ ((row & 1) | ((row & 2) << 2)));
 #pragma unroll
                 for (int w = 0; w < FACT_WARPS; ++w) {
-                    s += tmp[(size_t)w * (DUAL ? 512 : 256) + tid];
-                    if (DUAL) sd += tmp[(size_t)w * 512 + 256 + tid];
+                    if (PRIMALW) s += tmp[(size_t)w * (DUAL ? 512 : 256) + ti];
+                    if (DUAL) sd += tmp[(size_t)w * 512 + 256 + ti];
                 }
                 double* o = wp + ((size_t)l * NF + f) * 512;
-                o[tid] = s;
+                if (PRIMALW) o[tid] = s;
                 if (DUAL) o[256 + tid] = sd;
             }
             __syncthreads();
@@ -359,14 +362,14 @@ __global__ void __launch_bounds__(FACT_THREADS, (NF == 2 ? 2 : 1)) fact_kernel(c
 
 // Wl[b][l][f] = H + swap(H), H = sum over tiles of the per-tile partials; swap: local index (a,b) -> (b,a) on rows and columns
 __global__ void fact_reduce_kernel(const double* __restrict__ Wp, double* __restrict__ Wl, double* __restrict__ Wld, int tiles, int m,
-                                   int nf, bool dual, const int* active) {
+                                   int nf, bool primal, bool dual, const int* active) {
     const int lf = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
     if (active != nullptr && active[b] == 0) return;
     __shared__ double H[512];
     double s = 0.0, sd = 0.0;
     for (int tile = 0; tile < tiles; ++tile) {
         const double* src = Wp + (((size_t)b * tiles + tile) * m * nf + lf) * 512;
-        s += src[t];
+        if (primal) s += src[t];
         if (dual) sd += src[256 + t];
     }
     H[t] = s; H[256 + t] = sd;
@@ -374,7 +377,7 @@ __global__ void fact_reduce_kernel(const double* __restrict__ Wp, double* __rest
     const int i = t >> 4, j = t & 15;
     const int ts = (((i & 3) << 2) | (i >> 2)) * 16 + (((j & 3) << 2) | (j >> 2));
     const size_t o = ((size_t)b * m * nf + lf) * 256 + t;
-    Wl[o] = H[t] + H[ts];
+    if (primal) Wl[o] = H[t] + H[ts];
     if (dual) Wld[o] = H[256 + t] + H[256 + ts];
 }
 

@@ -928,7 +928,8 @@ static int fact_eval(otn_problem* h, int batch, const int* active, int mode, dou
     p.part_stride = h->f_tiles; p.Mout = Mout; p.swaprow = h->f_swaprow; p.m = h->m; p.tiles = h->f_tiles;
     const double cols = 0.5 * std::sqrt((double)h->D) * (std::sqrt((double)h->D) + 1.0);
     // applications + contractions of 2*16*16 flops per 16-vector: forward nf (x3 dual), reverse nf(nf-1)/2 + nf + nf (x3 dual)
-    const double units = (mode == FACT_COST || mode == FACT_MODEL) ? h->nf : (h->nf + 0.5 * h->nf * (h->nf - 1) + 2.0 * h->nf) * (mode == FACT_HVP ? 3.0 : 1.0);
+    const double units = (mode == FACT_COST || mode == FACT_MODEL) ? h->nf
+                         : (h->nf + 0.5 * h->nf * (h->nf - 1) + 2.0 * h->nf) * (mode == FACT_GRAD ? 1.0 : 3.0) - (mode == FACT_HVPONLY ? h->nf : 0.0);
     ProfScope ps(&h->prof, h->stream, CAT_GEMM, units * h->m * 2.0 * 16.0 * h->D * cols * batch);
     dim3 grid(h->f_tiles, batch);
 #define FACT_LAUNCH(NFV, NCV, MODEV)                                                                     \
@@ -942,15 +943,17 @@ static int fact_eval(otn_problem* h, int batch, const int* active, int mode, dou
         if (mode == FACT_COST) FACT_LAUNCH(NFV, NCV, FACT_COST);                                         \
         else if (mode == FACT_GRAD) FACT_LAUNCH(NFV, NCV, FACT_GRAD);                                    \
         else if (mode == FACT_HVP) FACT_LAUNCH(NFV, NCV, FACT_HVP);                                      \
+        else if (mode == FACT_HVPONLY) FACT_LAUNCH(NFV, NCV, FACT_HVPONLY);                              \
         else FACT_LAUNCH(NFV, NCV, FACT_MODEL);                                                          \
     } while (0)
     if (h->nf == 2) FACT_MODE(2, 8); else FACT_MODE(3, 1);
 #undef FACT_MODE
 #undef FACT_LAUNCH
     CUDA_TRY(cudaGetLastError());
-    if (mode == FACT_GRAD || mode == FACT_HVP) {
+    if (mode == FACT_GRAD || mode == FACT_HVP || mode == FACT_HVPONLY) {
         dim3 g2(h->m * h->nf, batch);
-        fact_reduce_kernel<<<g2, 256, 0, h->stream>>>(h->f_Wp, h->Wl, h->Wld, h->f_tiles, h->m, h->nf, mode == FACT_HVP, active);
+        fact_reduce_kernel<<<g2, 256, 0, h->stream>>>(h->f_Wp, h->Wl, h->Wld, h->f_tiles, h->m, h->nf, mode != FACT_HVPONLY,
+                                                       mode != FACT_GRAD, active);
         CUDA_TRY(cudaGetLastError());
     }
     return 0;
@@ -986,7 +989,7 @@ int otn_dev_cost_grad(otn_problem* h, const double* x, int batch, const int* act
 int otn_dev_hvp(otn_problem* h, const double* x, const double* eta, int batch, const int* active, double* heta) {
     if (h->factored) {          // primal recomputed alongside the tangent (dual numbers); zraw is the cached primal pull-back
         OTN_TRY(build_layers(h, x, eta, batch, active, true));
-        OTN_TRY(fact_eval(h, batch, active, FACT_HVP, nullptr));
+        OTN_TRY(fact_eval(h, batch, active, FACT_HVPONLY, nullptr));   // Wl (primal cotangents) stays as cached by cost_grad
         for (int l = h->m - 1; l >= 0; --l) OTN_TRY(back_layer(h, batch, active, l, x, true, eta));
     } else {
         OTN_TRY(tangent_pass(h, batch, active, x, eta, false));
