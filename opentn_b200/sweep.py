@@ -30,8 +30,10 @@ def run_sweep(lindbladians, N, d, taus, ranks, seeds, n_steps=4, niter=10, devic
     """Returns {K: dict(tau_index, seed, f0, f_final, x_final, status)} for the instances owned by `rank` (or, with
     `gather` = a function like sharding.gather_instances, for all instances on every rank)."""
     import torch
-    Lvec = T.create_2local_liouvillians(lindbladians, N, d, pbc=pbc)[0]
-    targets = np.stack([T.exp_operator_dt(Lvec, tau) for tau in taus])
+    # set-up on the device: Liouvillian assembly (otn_liouvillian) and one batched expm over the tau grid (otn_expm_batch)
+    T.set_device(device)
+    Lvec = T.create_2local_liouvillians(lindbladians, N, d, pbc=pbc, backend="cuda")[0]
+    targets = T.exp_operator_sweep(Lvec, taus)
     out = {}
     for K in ranks:
         starts = [np.stack([T.super2ortho(x.real, rank=K) for x in get_general_trotter_local_ansatz(lindbladians, tau, n_steps)])
