@@ -124,6 +124,12 @@ int otn_ipc_free(void* ptr, int device);
  *            exp_operator_dt (transformations.py:24-32; scipy / jax `expm`): scaling and squaring with a degree-16 Taylor
  *            polynomial (Paterson-Stockmeyer), every product on the chain's DMMA GEMM kernel. */
 int otn_expm(const double* A_re, const double* A_im, int D, double tau, double* out_re, double* out_im, int device);
+/* otn_super2ortho : x[i] = super2ortho(superop[i], rank=K) (transformations.py:728-741: super2choi :68-94, rank-truncated PSD
+ *                   factor :793-802, choi2ortho :701-714) for `count` real dim^2 x dim^2 superoperators; dim^2 <= 16 (the 2-site
+ *                   model).  Columns of the factor carry a sign convention (largest component positive) where the reference's
+ *                   SVD leaves the sign open: ortho2super(x) and every cost are identical, x itself only up to those signs.
+ *                   x: [count][dim*K][dim]. */
+int otn_super2ortho(const double* superop, int count, int dim, int K, double* x, int device);
 /* otn_expm_batch : out[b] = exp(taus[b] * A) for b < count (tau sweeps of one generator: the Trotter layers exp(tau L),
  *                  exp(tau/2 L_odd), exp(tau L_even) of create_trotter_layers, transformations.py:387-402, for every tau of a
  *                  study in one batched launch sequence).  `taus` is a HOST array; out is [count][D][D] per plane. */

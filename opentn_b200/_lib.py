@@ -65,6 +65,7 @@ SIGNATURES = {
     "otn_ipc_close": (C.c_int, [C.c_void_p, C.c_int]),
     "otn_ipc_free": (C.c_int, [C.c_void_p, C.c_int]),
     "otn_expm": (C.c_int, [_dp, _dp, C.c_int, C.c_double, _dp, _dp, C.c_int]),
+    "otn_super2ortho": (C.c_int, [_dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int]),
     "otn_expm_batch": (C.c_int, [_dp, _dp, C.c_int, _dp, C.c_int, _dp, _dp, C.c_int]),
     "otn_liouvillian": (C.c_int, [_dp, _dp, C.c_int, C.c_int, C.c_int, _ip, _ip, _ip, C.c_int, _dp, _dp, C.c_int]),
     "otn_project": (C.c_int, [_dp, _dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int]),

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libotn.so")
 SOURCES = ["otn_api.cu"]
-DEPS = ["otn_api.cu", "otn_common.cuh", "gemm_dmma.cuh", "assemble.cuh", "stiefel.cuh", "tr.cuh", "tr_driver.inl", "structured.cuh", "expm.inl", "liouville.inl", "factored.cuh",
+DEPS = ["otn_api.cu", "otn_common.cuh", "gemm_dmma.cuh", "assemble.cuh", "stiefel.cuh", "tr.cuh", "tr_driver.inl", "structured.cuh", "expm.inl", "liouville.inl", "factory.inl", "factored.cuh",
         os.path.join("..", "..", "include", "otn.h")]
 
 

@@ -1483,6 +1483,7 @@ extern "C" int otn_ipc_free(void* ptr, int device) {
 // ---------------------------------------------------------------------------------------------------------------------
 #include "expm.inl"
 #include "liouville.inl"
+#include "factory.inl"
 
 // ---------------------------------------------------------------------------------------------------------------------
 // trust region

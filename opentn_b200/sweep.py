@@ -36,8 +36,11 @@ def run_sweep(lindbladians, N, d, taus, ranks, seeds, n_steps=4, niter=10, devic
     targets = T.exp_operator_sweep(Lvec, taus)
     out = {}
     for K in ranks:
-        starts = [np.stack([T.super2ortho(x.real, rank=K) for x in get_general_trotter_local_ansatz(lindbladians, tau, n_steps)])
-                  for tau in taus]
+        # starting points: one batched device super2ortho over the Trotter layers of every tau (otn_super2ortho)
+        layers = [np.stack([np.asarray(x).real for x in get_general_trotter_local_ansatz(lindbladians, tau, n_steps)]) for tau in taus]
+        m_layers = layers[0].shape[0]
+        flat = T.super2ortho_batch(np.concatenate(layers), K)
+        starts = [flat[i * m_layers:(i + 1) * m_layers] for i in range(len(taus))]
         inst = [(ti, s) for ti in range(len(taus)) for s in seeds]
         mine = inst[rank::world]
         if not mine:

@@ -331,8 +331,30 @@ def unfactorize_psd(x: np.ndarray) -> np.ndarray:
     return x @ x.conj().T
 
 
-def super2ortho(x: np.ndarray, rank: int = None) -> np.ndarray:
+def super2ortho_batch(superops, rank: int) -> np.ndarray:
+    """super2ortho (transformations.py:728-741) of a stack of real 2-site superoperators (count, 16, 16) on the device
+    (otn_super2ortho: Jacobi eigen-decomposition of the Choi matrices, one warp each) -> (count, 4 rank, 4).  Kraus operators come
+    out with a fixed sign convention; ortho2super(x) equals the host route's."""
+    a = np.asarray(superops)
+    if np.iscomplexobj(a):
+        if np.abs(a.imag).max() > 0:
+            raise NotImplementedError("super2ortho_batch: real superoperators only (the reference passes `.real`)")
+        a = a.real
+    a = as_f64(a)
+    assert a.ndim == 3 and a.shape[1] == a.shape[2], "stack of square superoperators expected"
+    dim = int(round(np.sqrt(a.shape[1])))
+    assert dim * dim == a.shape[1]
+    out = np.empty((a.shape[0], dim * rank, dim))
+    check(_lib.load().otn_super2ortho(ptr(a), a.shape[0], dim, int(rank), ptr(out), _DEVICE))
+    return out
+
+
+def super2ortho(x: np.ndarray, rank: int = None, backend: str = "numpy") -> np.ndarray:
     """superop -> Choi -> rank-truncated factor -> isometry, transformations.py:728-741."""
+    if backend == "cuda":
+        if not rank:
+            rank = np.linalg.matrix_rank(super2choi(np.asarray(x)))
+        return super2ortho_batch(np.asarray(x)[None], rank)[0]
     c = super2choi(x)
     if not rank:
         rank = np.linalg.matrix_rank(c)

@@ -145,3 +145,45 @@ def test_two_devices_in_one_process(oracle):
         f.append(fit.cost_grad(xs)[0])
         fit.close()
     assert f[0][0] == f[1][0]
+
+
+# ---- initial-point factory ---------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("K", [2, 4, 10, 16])
+def test_super2ortho_device_matches_host_route(oracle, K):
+    """otn_super2ortho against the reference route (oracle.super2ortho, bitwise-pinned to the reference): the isometry is
+    defined up to the sign of each Kraus operator (SVD sign ambiguity), so compare what the path consumes -- the truncated
+    Choi matrix X X^T and ortho2super(x) -- plus isometry-ness of trace-preserving inputs."""
+    from opentn_b200 import transformations as T
+    P = oracle
+    layers = [np.asarray(x).real for x in P.get_general_trotter_local_ansatz(P.pspl_lindbladians(1.0), 1.0, n=2)]
+    rng = np.random.default_rng(K)
+    A = rng.standard_normal((16, 16)); psd = A @ A.T / 16                     # generic PSD Choi, distinct eigenvalues
+    stack = np.stack(layers + [T.choi2super(psd)])
+    got = T.super2ortho_batch(stack, K)
+    assert got.shape == (len(stack), 4 * K, 4)
+    for s, x in zip(stack, got):
+        want = P.super2ortho(s, rank=K)
+        cw, cg = T.ortho2choi(want), T.ortho2choi(x)
+        ev = np.sort(np.abs(np.linalg.eigvalsh(T.super2choi(s))))[::-1]
+        if K == 16 or ev[K - 1] - ev[K] > 1e-8 * ev[0]:                        # truncation well defined
+            np.testing.assert_allclose(cg @ cg.T, cw @ cw.T, rtol=0, atol=1e-13)
+            np.testing.assert_allclose(T.ortho2super(x), T.ortho2super(want), rtol=0, atol=1e-13)
+        # kept spectrum is the same either way
+        np.testing.assert_allclose(np.sort(np.linalg.norm(cg, axis=0) ** 2)[::-1], ev[:K], rtol=0, atol=1e-13)
+    one = T.super2ortho(stack[0], rank=K, backend="cuda")
+    np.testing.assert_array_equal(one, got[0])
+    if K == 16:                                                              # full rank of a CPTP map: an exact isometry
+        for x in got[:-1]:
+            np.testing.assert_allclose(x.T @ x, np.eye(4), rtol=0, atol=1e-13)
+
+
+def test_super2ortho_device_argument_checks():
+    from opentn_b200 import transformations as T
+    from opentn_b200._lib import OtnError
+    with pytest.raises(OtnError):
+        T.super2ortho_batch(np.zeros((1, 256, 256)), 4)                       # full-sites Choi (256 x 256) stays on the host
+    with pytest.raises(OtnError):
+        T.super2ortho_batch(np.eye(16)[None], 17)
+    with pytest.raises(NotImplementedError):
+        T.super2ortho_batch(np.eye(16)[None] * 1j, 2)
