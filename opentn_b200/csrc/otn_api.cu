@@ -225,7 +225,7 @@ struct otn_problem {
     Profiler prof;
     bool own_stream = true;
     // host-pointer pipeline (otn_triple): chunked H2D / compute / D2H overlap
-    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_comp[2] = {nullptr, nullptr};
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     DevBuf pipe_buf;
     DevBuf tr_buf;
@@ -259,6 +259,7 @@ extern "C" void otn_destroy(otn_problem* h) {
     for (int i = 0; i < 2; ++i) for (cudaEvent_t e : {h->ev_in[i], h->ev_done[i], h->ev_out[i]}) if (e) cudaEventDestroy(e);
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
+    for (int i = 0; i < 2; ++i) if (h->s_comp[i]) cudaStreamDestroy(h->s_comp[i]);
     h->pipe_buf.release();
     if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -1087,8 +1088,26 @@ static int triple_device(otn_problem* h, const double* x, const double* eta, int
     return 0;
 }
 
-// Host arrays in, host arrays out: the batch is cut into chunks and pipelined over three streams so that the PCIe copies of
-// chunk c+1 (H2D) and chunk c-1 (D2H) overlap the kernels of chunk c.  Double-buffered staging, ordering by events.
+// Move every per-instance array of the handle by `db` instances: a chunk of the host-staged pipeline then works on its own slice
+// of the workspaces (and on its own target indices), so the kernels of neighbouring chunks may overlap.
+static void shift_instance_views(otn_problem* h, long long db) {
+    const long long SZ = h->SZ, m = h->m, q2 = (long long)h->q * h->q;
+    auto mv = [&](double*& ptr, long long stride) { if (ptr) ptr += db * stride; };
+    for (double** ptr : {&h->Y, &h->P, &h->G, &h->W, &h->Yd, &h->Pd}) mv(*ptr, m * SZ);
+    mv(h->Gd, 2 * SZ); mv(h->Wd, SZ);
+    mv(h->Yl, m * q2); mv(h->Yld, m * q2); mv(h->Wl, m * h->nf * q2); mv(h->Wld, m * h->nf * q2);
+    for (double** ptr : {&h->x, &h->eta, &h->zraw, &h->zdraw}) mv(*ptr, m * h->np);
+    mv(h->part_f, h->tiles); mv(h->part_s, h->tiles);
+    if (h->factored) {
+        mv(h->f_Pst, (long long)h->f_tiles * (m - 1) * 2 * h->D * h->f_ncols);
+        mv(h->f_Wp, (long long)h->f_tiles * m * h->nf * 512);
+    }
+    h->tindex += db;
+}
+
+// Host arrays in, host arrays out: the batch is cut into chunks and pipelined so that the PCIe copies of chunk c+1 (H2D) and
+// chunk c-1 (D2H) overlap the kernels of chunk c; chunks alternate between two compute streams and work on disjoint slices of
+// the workspaces, so the tail of one chunk's kernels overlaps the head of the next.  Double-buffered staging, ordering by events.
 static int triple_pipelined(otn_problem* h, const double* x, const double* eta, int batch, double* f, double* rgrad, double* heta) {
     const int C = 256;
     const size_t per = (size_t)h->m * h->np;
@@ -1096,6 +1115,7 @@ static int triple_pipelined(otn_problem* h, const double* x, const double* eta, 
         CUDA_TRY(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
         for (int i = 0; i < 2; ++i) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&h->s_comp[i], cudaStreamNonBlocking));
             CUDA_TRY(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
@@ -1106,9 +1126,7 @@ static int triple_pipelined(otn_problem* h, const double* x, const double* eta, 
     const size_t slot_doubles = 4 * (size_t)CMAX * per + CMAX;
     OTN_TRY(h->pipe_buf.ensure(2 * slot_doubles * 8));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    // (copies are not the bottleneck: PCIe moves the 403 MB of a step in 4.2 ms, both directions overlapped; a ramped chunk
-    // schedule with short first/last chunks was measured and did not help -- what remains is the lower kernel efficiency of
-    // 256-instance launches)
+    // (copies are not the bottleneck: PCIe moves the 403 MB of a step in 4.2 ms, both directions overlapped)
     // chunk schedule: C/2 first and last (short exposed head H2D / tail D2H), 1.5 C in between (kernel efficiency)
     std::vector<int> sizes;
     if (const char* env = getenv("OTN_PIPE_SCHEDULE")) {          // experiment hook: comma-separated chunk sizes
@@ -1140,10 +1158,17 @@ static int triple_pipelined(otn_problem* h, const double* x, const double* eta, 
         CUDA_TRY(cudaMemcpyAsync(dx, x + (size_t)b0 * per, nb * per * 8, cudaMemcpyHostToDevice, h->s_in));
         CUDA_TRY(cudaMemcpyAsync(de, eta + (size_t)b0 * per, nb * per * 8, cudaMemcpyHostToDevice, h->s_in));
         CUDA_TRY(cudaEventRecord(h->ev_in[slot], h->s_in));
-        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_in[slot], 0));
-        if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_out[slot], 0));         // D2H of chunk c-2 drained dg/dh/df
-        OTN_TRY(triple_device(h, dx, de, nb, df, dg, dh));
-        CUDA_TRY(cudaEventRecord(h->ev_done[slot], h->stream));
+        cudaStream_t comp = h->s_comp[slot];
+        CUDA_TRY(cudaStreamWaitEvent(comp, h->ev_in[slot], 0));
+        if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(comp, h->ev_out[slot], 0));              // D2H of chunk c-2 drained dg/dh/df
+        cudaStream_t user_stream = h->stream;
+        h->stream = comp;
+        shift_instance_views(h, b0);
+        const int rc = triple_device(h, dx, de, nb, df, dg, dh);
+        shift_instance_views(h, -(long long)b0);
+        h->stream = user_stream;
+        if (rc != 0) return rc;
+        CUDA_TRY(cudaEventRecord(h->ev_done[slot], comp));
         CUDA_TRY(cudaStreamWaitEvent(h->s_out, h->ev_done[slot], 0));
         if (f) CUDA_TRY(cudaMemcpyAsync(f + b0, df, (size_t)nb * 8, cudaMemcpyDeviceToHost, h->s_out));
         if (rgrad) CUDA_TRY(cudaMemcpyAsync(rgrad + (size_t)b0 * per, dg, nb * per * 8, cudaMemcpyDeviceToHost, h->s_out));
@@ -1152,7 +1177,7 @@ static int triple_pipelined(otn_problem* h, const double* x, const double* eta, 
         b0 += nb;
     }
     CUDA_TRY(cudaStreamSynchronize(h->s_in));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < 2; ++i) CUDA_TRY(cudaStreamSynchronize(h->s_comp[i]));
     CUDA_TRY(cudaStreamSynchronize(h->s_out));
     h->cached_batch = 0;   // the work matrices hold the last chunk only
     return 0;

@@ -173,6 +173,35 @@ def test_pipelined_host_path_equals_device_path(P, targets):
     fit.close()
 
 
+@pytest.mark.parametrize("model", ["local", "full"])
+def test_pipelined_host_path_with_per_instance_targets(P, targets, model):
+    """The chunked host pipeline must use each chunk's own slice of the target indices and of the workspaces (chunks overlap on
+    two compute streams): per-instance targets, batch >= 512, both models (the 2-site model takes the factored evaluation)."""
+    import torch
+    from opentn_b200 import StiefelFit
+    B, K = 640, 2
+    p = 4 if model == "local" else 16
+    rng = np.random.default_rng(2)
+    xs = np.linalg.qr(rng.standard_normal((B, 3, p * K, p)))[0]
+    z = rng.standard_normal(xs.shape)
+    xtz = np.swapaxes(xs, -1, -2) @ z
+    et = z - xs @ (0.5 * (xtz + np.swapaxes(xtz, -1, -2)))
+    both = np.stack([targets["pspl_tau1"], targets["kitaev_pbc_tau05"]])
+    idx = rng.integers(0, 2, B).astype(np.int32)
+    fit = StiefelFit(both, model=model, N=N, d=d, metric="canonical", max_batch=B)
+    fit.set_target_index(idx)
+    f_h, g_h, h_h = fit.triple(xs, et)
+    f_d, g_d, h_d = fit.triple(torch.from_numpy(xs).cuda(), torch.from_numpy(et).cuda())
+    np.testing.assert_array_equal(f_h, f_d.cpu().numpy())
+    np.testing.assert_array_equal(g_h, g_d.cpu().numpy())
+    np.testing.assert_array_equal(h_h, h_d.cpu().numpy())
+    for b in (0, 127, 128, 511, 512, 639):
+        spec = P.CostSpec(both[idx[b]], model, N, d)
+        fo, go, ho = P.triple(spec, list(xs[b]), list(et[b]), "canonical")
+        assert abs(f_h[b] - fo) / fo < 1e-12 and rel(g_h[b], np.array(go)) < 1e-10 and rel(h_h[b], np.array(ho)) < 1e-10
+    fit.close()
+
+
 @pytest.mark.parametrize("metric", ["canonical", "euclidean"])
 @pytest.mark.parametrize("m,K", [(3, 16), (2, 3), (1, 5)])
 def test_dense_formulation_full_model(P, targets, metric, m, K):
