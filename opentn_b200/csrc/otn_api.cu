@@ -1127,7 +1127,7 @@ static int triple_pipelined(otn_problem* h, const double* x, const double* eta, 
     OTN_TRY(h->pipe_buf.ensure(2 * slot_doubles * 8));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     // (copies are not the bottleneck: PCIe moves the 403 MB of a step in 4.2 ms, both directions overlapped)
-    // chunk schedule: C/2 first and last (short exposed head H2D / tail D2H), 1.5 C in between (kernel efficiency)
+    // chunk schedule: short first and last chunks (exposed head H2D / tail D2H), longer ones in between (kernel efficiency)
     std::vector<int> sizes;
     if (const char* env = getenv("OTN_PIPE_SCHEDULE")) {          // experiment hook: comma-separated chunk sizes
         int left = batch;
@@ -1141,10 +1141,13 @@ static int triple_pipelined(otn_problem* h, const double* x, const double* eta, 
         }
         while (left > 0) { const int n = std::min(C, left); sizes.push_back(n); left -= n; }
     } else if (batch >= 4 * C) {
-        int left = batch - C;
-        sizes.push_back(C / 2);
-        while (left > 0) { const int n = std::min(C + C / 2, left); sizes.push_back(n); left -= n; }
-        sizes.push_back(C / 2);
+        // measured at 1024 instances (ms per step): 96/288/288/256/96 10.37, 64/192/256/256/192/64 10.44, 128/384/384/128 10.68,
+        // 8 x 128 10.83
+        const int edge = 3 * C / 8, mid = 9 * C / 8;
+        int left = batch - 2 * edge;
+        sizes.push_back(edge);
+        while (left > 0) { const int n = std::min(mid, left); sizes.push_back(n); left -= n; }
+        sizes.push_back(edge);
     } else {
         for (int left = batch; left > 0; left -= C) sizes.push_back(std::min(C, left));
     }
