@@ -232,10 +232,17 @@ __global__ void __launch_bounds__(FACT_THREADS, (NF == 2 ? 2 : 1)) fact_kernel(c
         Ysm[(tid >> 4) * FACT_YLD + (tid & 15)] = Yb[(size_t)l * 256 + tid];
         if (DUAL) Ydsm[(tid >> 4) * FACT_YLD + (tid & 15)] = Ydb[(size_t)l * 256 + tid];
         if (REV && l >= 1) {                        // state entering layer l
-            double* dstp = scratch + (size_t)(l - 1) * 2 * SB;
-            for (int i = tid * 2; i < SB; i += FACT_THREADS * 2) {
-                *reinterpret_cast<double2*>(dstp + i) = *reinterpret_cast<const double2*>(G + i);
-                if (DUAL) *reinterpret_cast<double2*>(dstp + SB + i) = *reinterpret_cast<const double2*>(Gd + i);
+            if (l == p.m - 1) {                     // the reverse sweep starts here: keep it in shared memory
+                for (int i = tid * 2; i < SB; i += FACT_THREADS * 2) {
+                    *reinterpret_cast<double2*>(P + i) = *reinterpret_cast<const double2*>(G + i);
+                    if (DUAL) *reinterpret_cast<double2*>(Pd + i) = *reinterpret_cast<const double2*>(Gd + i);
+                }
+            } else {
+                double* dstp = scratch + (size_t)(l - 1) * 2 * SB;
+                for (int i = tid * 2; i < SB; i += FACT_THREADS * 2) {
+                    *reinterpret_cast<double2*>(dstp + i) = *reinterpret_cast<const double2*>(G + i);
+                    if (DUAL) *reinterpret_cast<double2*>(dstp + SB + i) = *reinterpret_cast<const double2*>(Gd + i);
+                }
             }
         }
         __syncthreads();
@@ -293,11 +300,9 @@ __global__ void __launch_bounds__(FACT_THREADS, (NF == 2 ? 2 : 1)) fact_kernel(c
         Ysm[(tid >> 4) * FACT_YLD + (tid & 15)] = Yb[(size_t)l * 256 + tid];
         if (DUAL) Ydsm[(tid >> 4) * FACT_YLD + (tid & 15)] = Ydb[(size_t)l * 256 + tid];
         if (l >= 1) {
-            const double* srcp = scratch + (size_t)(l - 1) * 2 * SB;
-            for (int i = tid * 2; i < SB; i += FACT_THREADS * 2) {
-                *reinterpret_cast<double2*>(P + i) = *reinterpret_cast<const double2*>(srcp + i);
-                if (DUAL) *reinterpret_cast<double2*>(Pd + i) = *reinterpret_cast<const double2*>(srcp + SB + i);
-            }
+            // P / Pd already hold the state entering layer l: left there by the forward pass (l = m-1) or prefetched with
+            // cp.async during the tail of layer l+1
+            cp_async_wait<0>();
         } else {
             for (int i = tid; i < SB; i += FACT_THREADS) {
                 P[i ^ fact_swz<NF, NCOLS>(i / NCOLS)] = ((i / NCOLS) == cidx[i % NCOLS]) ? 1.0 : 0.0;
@@ -324,6 +329,14 @@ __global__ void __launch_bounds__(FACT_THREADS, (NF == 2 ? 2 : 1)) fact_kernel(c
             double acc[2][2][2], accd[2][2][2];
             fact_contract<NF, NCOLS, DUAL, PRIMALW>(G, Gd, Fs, Fds, jrow_s + (sh * NF + f) * 16, rest_s + (sh * NF + f) * REST, acc, accd);
             __syncthreads();                        // tmp no longer read: reuse it for the per-warp partials
+            if (f == NF - 1 && l >= 2) {            // P / Pd are free now: prefetch the state entering layer l-1
+                const double* srcp = scratch + (size_t)(l - 2) * 2 * SB;
+                for (int i = tid * 2; i < SB; i += FACT_THREADS * 2) {
+                    cp_async16(P + i, srcp + i);
+                    if (DUAL) cp_async16(Pd + i, srcp + SB + i);
+                }
+                cp_async_commit();
+            }
             double* part = tmp + (size_t)warp * (DUAL ? 512 : 256);
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
