@@ -101,6 +101,7 @@ def _cpu_tr_worker(args):
         threadpool_limits(1)
     except Exception:
         pass
+    import numpy as np
     from oracle import port as P
     T = P.kitaev_fullsites_target(N_SITES, D_LOC, 1.0, 4.0, False)
     spec = P.CostSpec(T, "full")
@@ -108,7 +109,17 @@ def _cpu_tr_worker(args):
     t0 = time.perf_counter()
     for i in range(count):
         P.trust_region_fit(spec, list(xs[i]), "canonical", niter=1)
-    return time.perf_counter() - t0, 0.0
+    t_tr = time.perf_counter() - t0
+    # baseline (i): the reference builds the dense Hessian one column per tangent degree of freedom (stiefel.py:498-529);
+    # time a few columns of exactly that construction and let the caller extrapolate to all of them
+    op = P.HessianOperator(spec, list(xs[0]), "canonical")
+    size = sum(P.stiefel_tangent_dof(*x.shape) for x in xs[0])
+    ncol = 4
+    t1 = time.perf_counter()
+    for k in range(ncol):
+        e = np.zeros(size); e[k * (size // ncol)] = 1.0
+        op @ e
+    return t_tr, (time.perf_counter() - t1) / ncol * size
 
 
 class CpuPool:
@@ -133,7 +144,8 @@ class CpuPool:
 
     def run_tr(self, sample_per_core):
         res = self.pool.map(_cpu_tr_worker, [(c * sample_per_core, sample_per_core) for c in range(self.cores)])
-        return self.cores * sample_per_core / max(r[0] for r in res)
+        dense_iter_s = statistics.median(r[1] for r in res)      # seconds per TR iteration spent building the dense Hessian
+        return self.cores * sample_per_core / max(r[0] for r in res), self.cores / dense_iter_s
 
     def close(self):
         self.pool.close()
@@ -500,16 +512,17 @@ def run_gpu(args):
         pool = CpuPool()
         try:
             v, total, wall = pool.run(64)
-            tr_cpu = pool.run_tr(2)
+            tr_cpu, tr_cpu_dense = pool.run_tr(2)
         finally:
             pool.close()
         cores = pool.cores
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{total} instances of the same workload ({total // cores} per process x {cores} processes, 1 BLAS thread each, "
                          f"{wall:.1f} s wall)",
-               "tr_iters_per_sec": tr_cpu,
-               "tr_note": "one TR iteration per instance with the matrix-free Hessian operator (BASELINE.md baseline (ii)); the "
-                          "reference's own dense Hessian (stiefel.py:498-529) needs 11 880 jvp(grad) evaluations per iteration at this size"}
+               "tr_iters_per_sec": tr_cpu, "tr_iters_per_sec_dense_hessian": tr_cpu_dense,
+               "tr_note": "tr_iters_per_sec: one TR iteration per instance with the matrix-free Hessian operator (SURVEY 8d baseline "
+                          "(ii)); tr_iters_per_sec_dense_hessian: baseline (i), the reference's own dense Hessian (stiefel.py:498-529, "
+                          "11 880 jvp(grad) columns per iteration at this size), extrapolated from 4 timed columns per process"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
