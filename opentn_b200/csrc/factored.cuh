@@ -26,8 +26,8 @@
 namespace otn {
 
 enum { FACT_COST = 0, FACT_GRAD = 1, FACT_HVP = 2, FACT_MODEL = 3, FACT_HVPONLY = 4 };   // HVPONLY: tangent cotangents only (tCG)
-constexpr int FACT_THREADS = 256;
-constexpr int FACT_WARPS = FACT_THREADS / 32;
+// threads per CTA: 8 warps at N = 4 (two CTAs per SM), 16 warps at N = 6 (one CTA per SM: 192 KB of states)
+template <int NF> struct FactThreads { static constexpr int THREADS = (NF == 2) ? 256 : 512; static constexpr int WARPS = THREADS / 32; };
 
 struct FactParams {
     const double* Yl; const double* Yld;   // [B][m][256] local superoperators and tangents
@@ -81,6 +81,7 @@ __device__ __forceinline__ void fact_apply(const double* src, const double* srcd
                                            const double (&a)[2][4], const double (&ad)[2][4],
                                            const int* __restrict__ jrow, const int* __restrict__ restrow) {
     constexpr int NV = FactDims<NF>::REST * NCOLS, NT = NV / 8, U = 2;
+    constexpr int FACT_WARPS = FactThreads<NF>::WARPS;
     static_assert(NT % (FACT_WARPS * U) == 0, "n-tiles must split evenly over the warps");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, lr = lane >> 2, lc = lane & 3;
     int jb[4], sb[4], jc[2], sc[2];
@@ -148,7 +149,7 @@ template <int NF, int NCOLS, bool DUAL, bool PRIMAL>
 __device__ __forceinline__ void fact_contract(const double* X, const double* Xd, const double* Z, const double* Zd,
                                               const int* __restrict__ jrow, const int* __restrict__ restrow,
                                               double (&acc)[2][2][2], double (&accd)[2][2][2]) {
-    constexpr int NV = FactDims<NF>::REST * NCOLS;
+    constexpr int NV = FactDims<NF>::REST * NCOLS, FACT_WARPS = FactThreads<NF>::WARPS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, lr = lane >> 2, lc = lane & 3;
     const int j0 = jrow[lr], j1 = jrow[8 + lr];
     const int ro[2] = {j0 * NCOLS, j1 * NCOLS}, so[2] = {fact_swz<NF, NCOLS>(j0), fact_swz<NF, NCOLS>(j1)};
@@ -191,8 +192,9 @@ struct FactCfg {
 };
 
 template <int NF, int NCOLS, int MODE>
-__global__ void __launch_bounds__(FACT_THREADS, (NF == 2 ? 2 : 1)) fact_kernel(const FactParams p) {
+__global__ void __launch_bounds__(FactThreads<NF>::THREADS, (NF == 2 ? 2 : 1)) fact_kernel(const FactParams p) {
     using Cfg = FactCfg<NF, NCOLS, MODE>;
+    constexpr int FACT_THREADS = FactThreads<NF>::THREADS, FACT_WARPS = FactThreads<NF>::WARPS;
     constexpr int D = Cfg::D, SB = Cfg::SB, REST = D / 16;
     constexpr bool DUAL = MODE == FACT_HVP || MODE == FACT_HVPONLY;
     constexpr bool REV = MODE == FACT_GRAD || DUAL;
@@ -229,8 +231,10 @@ __global__ void __launch_bounds__(FACT_THREADS, (NF == 2 ? 2 : 1)) fact_kernel(c
     // ---- forward ----------------------------------------------------------------------------------------------------
     for (int l = 0; l < p.m; ++l) {
         __syncthreads();                            // previous layer done with Ysm; state complete
-        Ysm[(tid >> 4) * FACT_YLD + (tid & 15)] = Yb[(size_t)l * 256 + tid];
-        if (DUAL) Ydsm[(tid >> 4) * FACT_YLD + (tid & 15)] = Ydb[(size_t)l * 256 + tid];
+        if (tid < 256) {
+            Ysm[(tid >> 4) * FACT_YLD + (tid & 15)] = Yb[(size_t)l * 256 + tid];
+            if (DUAL) Ydsm[(tid >> 4) * FACT_YLD + (tid & 15)] = Ydb[(size_t)l * 256 + tid];
+        }
         if (REV && l >= 1) {                        // state entering layer l
             if (l == p.m - 1) {                     // the reverse sweep starts here: keep it in shared memory
                 for (int i = tid * 2; i < SB; i += FACT_THREADS * 2) {
@@ -281,11 +285,11 @@ __global__ void __launch_bounds__(FACT_THREADS, (NF == 2 ? 2 : 1)) fact_kernel(c
         }
         sf = warp_sum(sf);
         if (DUAL) ss = warp_sum(ss);
-        if ((tid & 31) == 0) { red[tid >> 5] = sf; red[8 + (tid >> 5)] = ss; }
+        if ((tid & 31) == 0) { red[tid >> 5] = sf; red[16 + (tid >> 5)] = ss; }
         __syncthreads();
         if (tid == 0) {
             double tf = 0.0, ts = 0.0;
-            for (int w = 0; w < FACT_WARPS; ++w) { tf += red[w]; ts += red[8 + w]; }
+            for (int w = 0; w < FACT_WARPS; ++w) { tf += red[w]; ts += red[16 + w]; }
             p.part_f[(size_t)b * p.part_stride + tile] = tf;
             if (DUAL) p.part_s[(size_t)b * p.part_stride + tile] = ts;
         }
@@ -297,8 +301,10 @@ __global__ void __launch_bounds__(FACT_THREADS, (NF == 2 ? 2 : 1)) fact_kernel(c
 #pragma unroll 1
     for (int l = p.m - 1; l >= 0; --l) {
         __syncthreads();
-        Ysm[(tid >> 4) * FACT_YLD + (tid & 15)] = Yb[(size_t)l * 256 + tid];
-        if (DUAL) Ydsm[(tid >> 4) * FACT_YLD + (tid & 15)] = Ydb[(size_t)l * 256 + tid];
+        if (tid < 256) {
+            Ysm[(tid >> 4) * FACT_YLD + (tid & 15)] = Yb[(size_t)l * 256 + tid];
+            if (DUAL) Ydsm[(tid >> 4) * FACT_YLD + (tid & 15)] = Ydb[(size_t)l * 256 + tid];
+        }
         if (l >= 1) {
             // P / Pd already hold the state entering layer l: left there by the forward pass (l = m-1) or prefetched with
             // cp.async during the tail of layer l+1
@@ -350,7 +356,7 @@ __global__ void __launch_bounds__(FACT_THREADS, (NF == 2 ? 2 : 1)) fact_kernel(c
                         if (DUAL) part[256 + idx] = accd[mt][nt][e];
                     }
             __syncthreads();
-            {
+            if (tid < 256) {
                 double s = 0.0, sd = 0.0;
                 const int row = tid >> 4, ti = (tid & ~15) | ((tid & 15) ^ ((row & 1) | ((row & 2) << 2)));
 #pragma unroll
@@ -371,6 +377,23 @@ __global__ void __launch_bounds__(FACT_THREADS, (NF == 2 ? 2 : 1)) fact_kernel(c
             }
         }
     }
+}
+
+// first stage of the tile reduction when there are many tiles (N = 6: 2080): out[b][z][lf] = sum of the tiles of chunk z
+__global__ void fact_partial_reduce_kernel(const double* __restrict__ Wp, double* __restrict__ out, int tiles, int chunk, int mnf,
+                                           bool primal, bool dual, const int* active) {
+    const int lf = blockIdx.x, b = blockIdx.y, z = blockIdx.z, t = threadIdx.x, nsplit = gridDim.z;
+    if (active != nullptr && active[b] == 0) return;
+    const int t0 = z * chunk, t1 = min(tiles, t0 + chunk);
+    double s = 0.0, sd = 0.0;
+    for (int tile = t0; tile < t1; ++tile) {
+        const double* src = Wp + (((size_t)b * tiles + tile) * mnf + lf) * 512;
+        if (primal) s += src[t];
+        if (dual) sd += src[256 + t];
+    }
+    double* o = out + (((size_t)b * nsplit + z) * mnf + lf) * 512;
+    o[t] = s;
+    o[256 + t] = sd;
 }
 
 // Wl[b][l][f] = H + swap(H), H = sum over tiles of the per-tile partials; swap: local index (a,b) -> (b,a) on rows and columns

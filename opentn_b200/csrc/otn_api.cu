@@ -232,7 +232,8 @@ struct otn_problem {
     // factored evaluation of the 2-site model (factored.cuh)
     bool factored = false;
     int f_ncols = 0, f_tiles = 0;
-    double *f_Tt = nullptr, *f_Pst = nullptr, *f_Wp = nullptr, *f_colw = nullptr;
+    double *f_Tt = nullptr, *f_Pst = nullptr, *f_Wp = nullptr, *f_Wp2 = nullptr, *f_colw = nullptr;
+    int f_nsplit = 1;            // two-stage tile reduction when there are many tiles
     int *f_jrow = nullptr, *f_restrow = nullptr, *f_colidx = nullptr, *f_swaprow = nullptr;
     EmbedTables tables() const { return EmbedTables{tab, inv, D, q, nf}; }
 };
@@ -250,7 +251,7 @@ extern "C" void otn_destroy(otn_problem* h) {
     for (void* ptr : {(void*)h->T_re, (void*)h->im2, (void*)h->tindex, (void*)h->tab, (void*)h->inv, (void*)h->symtab, (void*)h->t2f, (void*)h->Y, (void*)h->P,
                       (void*)h->G, (void*)h->W, (void*)h->Yd, (void*)h->Pd, (void*)h->Gd, (void*)h->Wd, (void*)h->Yl, (void*)h->Yld,
                       (void*)h->Wl, (void*)h->Wld, (void*)h->x, (void*)h->eta, (void*)h->zraw, (void*)h->zdraw, (void*)h->part_f,
-                      (void*)h->part_s, (void*)h->f_Tt, (void*)h->f_Pst, (void*)h->f_Wp, (void*)h->f_colw, (void*)h->f_jrow,
+                      (void*)h->part_s, (void*)h->f_Tt, (void*)h->f_Pst, (void*)h->f_Wp, (void*)h->f_Wp2, (void*)h->f_colw, (void*)h->f_jrow,
                       (void*)h->f_restrow, (void*)h->f_colidx, (void*)h->f_swaprow})
         if (ptr) cudaFree(ptr);
     for (DevBuf* b : {&h->in_x, &h->in_eta, &h->out_a, &h->out_b, &h->out_c, &h->out_f, &h->out_M, &h->tr_buf}) b->release();
@@ -475,6 +476,10 @@ extern "C" int otn_create_ex(otn_problem** out, int N, int d, int m, int K, int 
             const size_t SBs = (size_t)Dn * nc;
             if (m > 1) CREATE_TRY(cudaMalloc(&h->f_Pst, B * h->f_tiles * (M - 1) * 2 * SBs * 8));
             CREATE_TRY(cudaMalloc(&h->f_Wp, B * h->f_tiles * M * NF * 512 * 8));
+            if (h->f_tiles > 64) {
+                h->f_nsplit = (h->f_tiles + 31) / 32;
+                CREATE_TRY(cudaMalloc(&h->f_Wp2, B * h->f_nsplit * M * NF * 512 * 8));
+            }
         }
         const size_t q2 = (size_t)h->q * h->q;
         CREATE_TRY(cudaMalloc(&h->Yl, B * M * q2 * 8));
@@ -937,7 +942,7 @@ static int fact_eval(otn_problem* h, int batch, const int* active, int mode, dou
     do {                                                                                                 \
         const size_t sm = FactCfg<NFV, NCV, MODEV>::SMEM_BYTES;                                          \
         OTN_TRY(set_smem(fact_kernel<NFV, NCV, MODEV>, sm));                                             \
-        fact_kernel<NFV, NCV, MODEV><<<grid, FACT_THREADS, sm, h->stream>>>(p);                          \
+        fact_kernel<NFV, NCV, MODEV><<<grid, FactThreads<NFV>::THREADS, sm, h->stream>>>(p);            \
     } while (0)
 #define FACT_MODE(NFV, NCV)                                                                              \
     do {                                                                                                 \
@@ -953,8 +958,14 @@ static int fact_eval(otn_problem* h, int batch, const int* active, int mode, dou
     CUDA_TRY(cudaGetLastError());
     if (mode == FACT_GRAD || mode == FACT_HVP || mode == FACT_HVPONLY) {
         dim3 g2(h->m * h->nf, batch);
-        fact_reduce_kernel<<<g2, 256, 0, h->stream>>>(h->f_Wp, h->Wl, h->Wld, h->f_tiles, h->m, h->nf, mode != FACT_HVPONLY,
-                                                       mode != FACT_GRAD, active);
+        const bool primal = mode != FACT_HVPONLY, dual = mode != FACT_GRAD;
+        if (h->f_nsplit > 1) {
+            dim3 g1(h->m * h->nf, batch, h->f_nsplit);
+            fact_partial_reduce_kernel<<<g1, 256, 0, h->stream>>>(h->f_Wp, h->f_Wp2, h->f_tiles, 32, h->m * h->nf, primal, dual, active);
+            fact_reduce_kernel<<<g2, 256, 0, h->stream>>>(h->f_Wp2, h->Wl, h->Wld, h->f_nsplit, h->m, h->nf, primal, dual, active);
+        } else {
+            fact_reduce_kernel<<<g2, 256, 0, h->stream>>>(h->f_Wp, h->Wl, h->Wld, h->f_tiles, h->m, h->nf, primal, dual, active);
+        }
         CUDA_TRY(cudaGetLastError());
     }
     return 0;
@@ -1101,6 +1112,7 @@ static void shift_instance_views(otn_problem* h, long long db) {
     if (h->factored) {
         mv(h->f_Pst, (long long)h->f_tiles * (m - 1) * 2 * h->D * h->f_ncols);
         mv(h->f_Wp, (long long)h->f_tiles * m * h->nf * 512);
+        mv(h->f_Wp2, (long long)h->f_nsplit * m * h->nf * 512);
     }
     h->tindex += db;
 }

@@ -30,3 +30,18 @@ for mode, kw in (("blocks", dict(dense=False)), ("factored", dict(factored=True)
         torch.cuda.synchronize()
         print(f"N=6 K={K} {mode:9s} {what:12s} {(time.perf_counter() - t0) / reps * 1e3:9.2f} ms")
     fit.close()
+
+# per-category device time of one factored triple
+import ctypes as C
+from opentn_b200 import _lib
+fit = StiefelFit(T6, model="local", N=6, d=2, factored=True)
+fit.triple(x, e); torch.cuda.synchronize()
+h = fit._handle(3, K, 1)
+lib = _lib.load()
+lib.otn_profile_enable(h.h, 1)
+fit.triple(x, e); torch.cuda.synchronize()
+ms = (C.c_double * 6)(); n = (C.c_longlong * 6)(); fl = (C.c_double * 6)()
+lib.otn_profile_read(h.h, ms, n, fl); lib.otn_profile_enable(h.h, 0)
+for k, nm in enumerate(["factored kernel", "assembly", "back_assembly", "riem", "tr", "other"]):
+    if n[k]:
+        print(f"  {nm:16s} {ms[k]:7.3f} ms {n[k]:3d} launches" + (f"  {fl[k] / ms[k] / 1e9:.1f} TFLOP/s" if k == 0 else ""))
