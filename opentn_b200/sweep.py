@@ -27,7 +27,7 @@ def kicked_start(xs0, seed, kick=1e-2):
 
 def run_sweep(lindbladians, N, d, taus, ranks, seeds, n_steps=4, niter=10, device=0, rank=0, world=1, pbc=True, max_batch=1024,
               gather=None):
-    """Returns {K: dict(tau_index, seed, f0, f_final, x_final, status)} for the instances owned by `rank` (or, with
+    """Returns {K: dict(tau_index, seed, f0, f_final, x0, x_final, status)} for the instances owned by `rank` (or, with
     `gather` = a function like sharding.gather_instances, for all instances on every rank)."""
     import torch
     # set-up on the device: Liouvillian assembly (otn_liouvillian) and one batched expm over the tau grid (otn_expm_batch)
@@ -60,7 +60,7 @@ def run_sweep(lindbladians, N, d, taus, ranks, seeds, n_steps=4, niter=10, devic
             status[sl] = rep["status"]
             xf[sl] = xe.cpu().numpy()
             fit.close()
-        res = dict(tau_index=tindex, seed=np.array([s for _, s in mine]), f0=f0, f_final=ff, x_final=xf, status=status)
+        res = dict(tau_index=tindex, seed=np.array([s for _, s in mine]), f0=f0, f_final=ff, x0=xs, x_final=xf, status=status)
         if gather is not None:
             total = len(inst)
             dev = torch.device("cuda", device)

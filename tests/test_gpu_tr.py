@@ -113,7 +113,14 @@ def test_sweep_driver_small(P):
         assert (r["f_final"] <= r["f0"] * (1 + 1e-12)).all()
         for i in (0, 5):
             tau = taus[r["tau_index"][i]]
-            xs0 = [P.super2ortho(x.real, rank=K) for x in P.get_general_trotter_local_ansatz([P.get_kitaev_nn_linbladian(1.0)], tau, 1)]
-            x0 = sweep.kicked_start(xs0, int(r["seed"][i]))
+            # starting points come from the device factory (otn_super2ortho: Kraus operators up to sign) + a 1e-2 kick
+            x0 = r["x0"][i]
+            np.testing.assert_allclose(np.swapaxes(x0, -1, -2) @ x0, np.broadcast_to(np.eye(4), (x0.shape[0], 4, 4)), atol=1e-13)
             f = P.CostSpec(P.exp_operator_dt(Lvec, tau), "local", N, d)(list(x0))
             assert abs(f - r["f0"][i]) / f < 1e-10
+            # the un-kicked device start reproduces the host-built Trotter start's cost (same superoperators, Kraus signs aside)
+            layers = np.stack([np.asarray(x).real for x in P.get_general_trotter_local_ansatz([P.get_kitaev_nn_linbladian(1.0)], tau, 1)])
+            xs_dev = T.super2ortho_batch(layers, K)
+            xs_host = [P.super2ortho(x, rank=K) for x in layers]
+            spec = P.CostSpec(P.exp_operator_dt(Lvec, tau), "local", N, d)
+            assert abs(spec(list(xs_dev)) - spec(xs_host)) < 1e-9
