@@ -199,13 +199,19 @@ __global__ void __launch_bounds__(BAS_THREADS) back_assemble_kernel(const double
                                                                     long long w_stride, long long wd_stride, int nslices,
                                                                     const double* __restrict__ x, const double* __restrict__ eta,
                                                                     double* __restrict__ Z, double* __restrict__ Zd, int dim, int K,
-                                                                    const int* active, int m, int layer) {
-    // launched once per layer: W / Wd point at that layer's matrix of instance 0, strides are per instance
+                                                                    const int* active, int m, int layer_arg) {
+    // launched once per layer: W / Wd point at that layer's matrix of instance 0, strides are per instance;
+    // or once for all layers (layer_arg < 0, grid.z = m): W / Wd point at layer 0 and layers are nslices * d^4 apart
     extern __shared__ __align__(16) double sm[];
     const int inst = blockIdx.y, a = blockIdx.x;
     if (active != nullptr && active[inst] == 0) return;
+    const int layer = layer_arg >= 0 ? layer_arg : (int)blockIdx.z;
     const int item = inst * m + layer;
     const int d2 = dim * dim, np = dim * K * dim, ldc = dim + 1, wsz = dim * dim * ldc;
+    if (layer_arg < 0) {
+        W += (long long)layer * nslices * d2 * d2;
+        if (TANGENT) Wd += (long long)layer * nslices * d2 * d2;
+    }
     double* ws = sm;
     double* wds = ws + (TANGENT ? wsz : 0);
     double* xs = wds + wsz;

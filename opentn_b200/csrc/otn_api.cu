@@ -926,6 +926,26 @@ static int riem_launch(otn_problem* h, int batch, const int* active, int tiles, 
     return 0;
 }
 
+// factored evaluation: pull the local cotangents Wl (and Wld) of ALL layers back to the isometries in one launch
+static int fact_back_layers(otn_problem* h, int batch, const int* active, const double* x, bool tangent, const double* eta) {
+    ProfScope ps(&h->prof, h->stream, CAT_BACK, 4.0 * h->K * (double)h->dim * h->dim * h->dim * h->dim * batch * h->m * (tangent ? 2 : 1));
+    const int dim = h->dim;
+    const long long ls = (long long)h->nf * h->q * h->q, sW = (long long)h->m * ls;
+    const size_t wsz = (size_t)dim * dim * (dim + 1);
+    dim3 grid(dim, batch, h->m);
+    if (!tangent) {
+        const size_t sm = (wsz + h->np) * 8;
+        OTN_TRY(set_smem(back_assemble_kernel<false>, sm));
+        back_assemble_kernel<false><<<grid, BAS_THREADS, sm, h->stream>>>(h->Wl, nullptr, sW, 0, h->nf, x, nullptr, h->zraw, nullptr, dim, h->K, active, h->m, -1);
+    } else {
+        const size_t sm = (2 * wsz + 2 * h->np) * 8;
+        OTN_TRY(set_smem(back_assemble_kernel<true>, sm));
+        back_assemble_kernel<true><<<grid, BAS_THREADS, sm, h->stream>>>(h->Wl, h->Wld, sW, sW, h->nf, x, eta, nullptr, h->zdraw, dim, h->K, active, h->m, -1);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 // factored evaluation (factored.cuh): one launch does forward / residual / reverse / tangent for every column tile
 static int fact_eval(otn_problem* h, int batch, const int* active, int mode, double* Mout) {
     FactParams p{};
@@ -989,7 +1009,7 @@ int otn_dev_cost_grad(otn_problem* h, const double* x, int batch, const int* act
     if (h->factored) {
         OTN_TRY(fact_eval(h, batch, active, FACT_GRAD, nullptr));
         tiles = h->f_tiles;
-        for (int l = h->m - 1; l >= 0; --l) OTN_TRY(back_layer(h, batch, active, l, x, false, nullptr));
+        OTN_TRY(fact_back_layers(h, batch, active, x, false, nullptr));
     } else {
         OTN_TRY(forward_chain(h, batch, active, false, &tiles));
         OTN_TRY(reverse_chain(h, batch, active, x));
@@ -1002,7 +1022,7 @@ int otn_dev_hvp(otn_problem* h, const double* x, const double* eta, int batch, c
     if (h->factored) {          // primal recomputed alongside the tangent (dual numbers); zraw is the cached primal pull-back
         OTN_TRY(build_layers(h, x, eta, batch, active, true));
         OTN_TRY(fact_eval(h, batch, active, FACT_HVPONLY, nullptr));   // Wl (primal cotangents) stays as cached by cost_grad
-        for (int l = h->m - 1; l >= 0; --l) OTN_TRY(back_layer(h, batch, active, l, x, true, eta));
+        OTN_TRY(fact_back_layers(h, batch, active, x, true, eta));
     } else {
         OTN_TRY(tangent_pass(h, batch, active, x, eta, false));
     }
@@ -1083,10 +1103,8 @@ static int triple_device(otn_problem* h, const double* x, const double* eta, int
     if (h->factored) {
         OTN_TRY(fact_eval(h, batch, nullptr, FACT_HVP, nullptr));
         h->tr.tiles = tiles = h->f_tiles;
-        for (int l = h->m - 1; l >= 0; --l) {
-            OTN_TRY(back_layer(h, batch, nullptr, l, x, false, nullptr));
-            OTN_TRY(back_layer(h, batch, nullptr, l, x, true, eta));
-        }
+        OTN_TRY(fact_back_layers(h, batch, nullptr, x, false, nullptr));
+        OTN_TRY(fact_back_layers(h, batch, nullptr, x, true, eta));
         OTN_TRY(riem_launch(h, batch, nullptr, tiles, x, eta, true, f, rgrad, nullptr, heta));
         return 0;
     }
