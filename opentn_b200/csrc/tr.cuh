@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(ST_THREADS) tcg_step_kernel(const TcgParams P)
     extern __shared__ __align__(16) double sm[];
     const int inst = blockIdx.x;
     if (P.tcg_active[inst] == 0) return;
+    if (threadIdx.x == 0) atomicAdd(P.n_active + 1, 1);   // Hessian-vector products consumed (one per active instance and step)
     const int ld = TrLay<PT>::ld(P.p);
     const int np = P.n * P.p, nl = P.n * ld, pl = P.p * ld, pp = P.p * P.p;
     double* X = sm;

@@ -121,15 +121,25 @@ extern "C" int otn_tr_run(otn_problem* h, double* x, int batch, const otn_tr_par
         if (rep && rep->f_iter) CUDA_TRY(cudaMemcpyAsync(hist_d(rep->f_iter, k), t.fx, (size_t)batch * 8, cudaMemcpyDefault, st));
         // eta, on_boundary = truncated_cg(grad, hess, radius)                                      (:61)
         OTN_TRY(tcg_dispatch(h, tp, batch, true));
-        int n_active = batch;
-        for (int j = 0; j < maxiter && n_active > 0; ++j) {
+        // The host only needs to know when every instance has left tCG.  Finished instances are masked on the device
+        // (their CTAs exit at once), so the count of still-active instances is read back -- a stream synchronisation -- only
+        // every `check` steps when the batch is small enough for launch/sync latency to matter; the Hessian-vector products
+        // actually consumed are counted on the device.
+        const int check = ((long long)batch * h->D <= 16384) ? 4 : 1;
+        int counters[2] = {batch, 0};
+        CUDA_TRY(cudaMemsetAsync(t.n_active, 0, 8, st));
+        for (int j = 0; j < maxiter && counters[0] > 0; ++j) {
             OTN_TRY(otn_dev_hvp(h, h->x, t.d, batch, t.tcg_active, t.Hd));
-            hvps += n_active;
             CUDA_TRY(cudaMemsetAsync(t.n_active, 0, 4, st));
             OTN_TRY(tcg_dispatch(h, tp, batch, false));
-            CUDA_TRY(cudaMemcpyAsync(&n_active, t.n_active, 4, cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaStreamSynchronize(st));
+            if ((j + 1) % check == 0 || j + 1 == maxiter) {
+                CUDA_TRY(cudaMemcpyAsync(counters, t.n_active, 8, cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaStreamSynchronize(st));
+            }
         }
+        CUDA_TRY(cudaMemcpyAsync(counters, t.n_active, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        hvps += counters[1];
         // model decrease  <grad, eta> + 1/2 <eta, hess @ eta>  (:67).  hess @ eta is not recomputed: eta = sum_j alpha_j d_j,
         // so H eta = sum_j alpha_j (H d_j) was accumulated by tcg_step_kernel from the products tCG already paid for.
         OTN_TRY(cdot_launch(h, h->x, t.g, t.z, batch, t.gz));
