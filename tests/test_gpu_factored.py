@@ -136,3 +136,51 @@ def test_factored_n6(oracle, goldens):
     assert rel(h2, h1) < 1e-10
     ref.close()
     fit.close()
+
+
+@pytest.mark.parametrize("m,K", [(2, 1), (17, 2), (6, 7)])
+def test_factored_edge_shapes(P, targets, m, K):
+    """Square isometries (K = 1), an even / long layer stack, an odd Kraus rank: factored == oracle and == block-diagonal."""
+    from opentn_b200 import StiefelFit
+    T = targets["pspl_tau1"]
+    B = 2
+    xs, et = _random_batch(P, B, m, 4 * K, 4, 100 + m)
+    fit = StiefelFit(T, model="local", N=N, d=d, max_batch=B, factored=True)
+    ref = StiefelFit(T, model="local", N=N, d=d, max_batch=B, dense=False)
+    f, g, h = fit.triple(xs, et)
+    f2, g2, h2 = ref.triple(xs, et)
+    np.testing.assert_allclose(f, f2, rtol=1e-13)
+    assert rel(g, g2) < 1e-11 and rel(h, h2) < 1e-11
+    fo, go, ho = P.triple(P.CostSpec(T, "local", N, d), list(xs[0]), list(et[0]), "canonical")
+    assert abs(f[0] - fo) / fo < 1e-12 and rel(g[0], np.array(go)) < 1e-10 and rel(h[0], np.array(ho)) < 1e-10
+    fit.close(); ref.close()
+
+
+def test_factored_flag_validation(targets):
+    """OTN_FLAG_FACTORED is refused where it does not apply (full-sites model, d = 3, N = 2) and cannot be combined with the
+    other formulations; the default picks it only for the 2-site model with d = 2 and N in {4, 6}."""
+    import ctypes as C
+    from opentn_b200 import _lib
+    lib = _lib.load()
+    T = np.ascontiguousarray(targets["pspl_tau1"].real)
+    h = C.c_void_p()
+    # (N, d, model, flags) -> expected failure
+    for Nn, dd, model, flags in [(4, 2, _lib.MODEL_FULL, 4), (4, 2, _lib.MODEL_LOCAL, 4 | 1), (4, 2, _lib.MODEL_LOCAL, 4 | 2)]:
+        rc = lib.otn_create_ex(C.byref(h), Nn, dd, 3, 2, model, 1, 1, 1, T.ctypes.data, None, 0, flags)
+        assert rc != 0 and b"FACTORED" in lib.otn_last_error()
+
+
+def test_factored_batched_tr_vs_oracle(P, targets):
+    """Batched device TR on the factored evaluation against the oracle's TR loop, instance by instance (tCG lengths differ per
+    instance, so the per-instance masks of the lock-step solver are exercised)."""
+    from opentn_b200 import StiefelFit
+    T = targets["kitaev_pbc_tau05"]
+    B, m, K = 3, 3, 4
+    xs, _ = _random_batch(P, B, m, 4 * K, 4, 77)
+    fit = StiefelFit(T, model="local", N=N, d=d, max_batch=B, factored=True)
+    x, rep = fit.tr_run(xs, niter=3)
+    spec = P.CostSpec(T, "local", N, d)
+    for b in range(B):
+        _, f_it, _, _ = P.trust_region_fit(spec, list(xs[b]), "canonical", niter=3)
+        np.testing.assert_allclose(rep["f_iter"][:, b], f_it, rtol=1e-9)
+    fit.close()
