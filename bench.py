@@ -508,7 +508,7 @@ def run_gpu(args):
                      "step_tflops_algorithmic": FLOPS_PER_TRIPLE * BATCH / (ms_d / d_steps * 1e-3) / 1e12}
 
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:     # the host-core baseline is timed at N = 1 only (rank 0 would compete with N-1 ranks)
         pool = CpuPool()
         try:
             v, total, wall = pool.run(64)
