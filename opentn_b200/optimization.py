@@ -45,9 +45,11 @@ def frobenius_norm(A, B, squared: bool = False):
     from . import transformations as _T
     A = np.asarray(A)
     B = np.asarray(B)
+    if np.iscomplexobj(A) and np.abs(A.imag).max() > 0 and not (np.iscomplexobj(B) and np.abs(B.imag).max() > 0):
+        A, B = B, A                                     # the norm is symmetric: compute_loss passes (exact, prediction)
     if np.iscomplexobj(A):
         if np.abs(A.imag).max() > 0:
-            raise NotImplementedError("frobenius_norm: the first argument (model) must be real on the accelerated path")
+            raise NotImplementedError("frobenius_norm: one argument (the model matrix) must be real on the accelerated path")
         A = A.real
     a = _lib.as_f64(A).reshape(-1)
     bre = _lib.as_f64(B.real).reshape(-1)
@@ -58,6 +60,15 @@ def frobenius_norm(A, B, squared: bool = False):
     _lib.check(_lib.load().otn_frobenius(_lib.ptr(a), _lib.ptr(bre), _lib.ptr(bim), 1, a.size, int(bool(squared)), _lib.ptr(out),
                                          _T._DEVICE))
     return float(out[0])
+
+
+def compute_loss(xi, loss_fn, model, exact, **kwargs):
+    """loss_fn(exact, model(xi, **kwargs)), optimization.py:153-159 (the reference wraps loss_fn in `jit`; here `model` and
+    `loss_fn` are the device-backed functions of this module)."""
+    prediction = model(xi, **kwargs)
+    exact = np.asarray(exact)
+    assert exact.ndim == np.ndim(prediction) == 2, "not a matrix"
+    return loss_fn(exact, prediction)
 
 
 def get_general_trotter_local_ansatz(lindbladians, tau, n: int):

@@ -45,6 +45,12 @@ def test_compose_and_models(goldens):
     np.testing.assert_allclose(O.model_Ys_stiefel(list(goldens["in/xs_full3"])), goldens["ref/model_full_m3"], atol=1e-13)
     assert O.frobenius_norm(np.eye(3), np.zeros((3, 3))) == pytest.approx(np.sqrt(3))
     assert O.frobenius_norm(np.eye(3), np.zeros((3, 3)), squared=True) == pytest.approx(3.0)
+    # compute_loss(xi, loss_fn, model, exact) = loss_fn(exact, model(xi)) (optimization.py:153-159): complex target first
+    rng = np.random.default_rng(3)
+    tgt = rng.standard_normal((256, 256)) + 1j * rng.standard_normal((256, 256))
+    xs = [np.linalg.qr(rng.standard_normal((8, 4)))[0] for _ in range(3)]
+    want = np.linalg.norm(O.model_stiefel_local(xs, 4, 2) - tgt)
+    assert O.compute_loss(xs, O.frobenius_norm, O.model_stiefel_local, tgt, N=4, d=2) == pytest.approx(want, rel=1e-13)
 
 
 @pytest.mark.parametrize("tag", ["s40", "s64", "sq"])
