@@ -259,6 +259,77 @@ def tangent_from_parametrization(X, A, B):
     return X @ A + get_orthogonal_complement(X) @ B
 
 
+def parametrization_from_tangent_square(x, z, vectorized=True):
+    """A with z = x A on the orthogonal group (n == p), stiefel.py:252-264."""
+    A = get_antisymmetric(np.asarray(x), np.asarray(z))
+    return square_to_upper_triangular(A) if vectorized else A
+
+
+# ---- elementary tangent directions (the columns of the reference's dense Hessian are indexed by them) ------------------
+def get_unit_matrices(ops):
+    """One E_00 unit matrix per operator shape, stiefel.py:112-121."""
+    return [get_ij_unit_matrix(*np.shape(op)) for op in ops]
+
+
+def get_elementary_antisymmetric(k, x):
+    """x (E_ij - E_ji), (i < j) the k-th upper-triangle position, stiefel.py:123-136."""
+    x = np.asarray(x)
+    upper = np.zeros(antisymmetric_dof(x))
+    upper[k] = 1.0
+    return x @ upper_triangular_to_antisymmetric(upper, p=x.shape[1])
+
+
+def get_elementary_arbitrary(k, x):
+    """x_perp E_k with E_k the k-th (n-p) x p unit matrix, stiefel.py:139-148."""
+    x = np.asarray(x)
+    n, p = x.shape
+    return get_orthogonal_complement(x) @ get_k_unit_matrix(n - p, p, k)
+
+
+def get_elementary_tangent_direction(k, x):
+    """k-th basis direction of T_x St(n,p): antisymmetric block first, then the complement block, stiefel.py:150-173."""
+    x = np.asarray(x)
+    assert 0 <= k < stiefel_tangent_dof(x), "k it is out of range"
+    na = antisymmetric_dof(x)
+    return get_elementary_antisymmetric(k, x) if k < na else get_elementary_arbitrary(k - na, x)
+
+
+# ---- predicates and small utilities ---------------------------------------------------------------------------------------
+def is_hermitian(H):
+    """True, or (False, ||H - H^+||) when it is not (atol 1e-8), stiefel.py:376-382."""
+    H = np.asarray(H)
+    if np.allclose(H.conj().T, H, atol=1e-8):
+        return True
+    return False, np.linalg.norm(H - H.conj().T)
+
+
+def is_antisymmetric(A):
+    """stiefel.py:390-392"""
+    A = np.asarray(A)
+    return bool(np.allclose(A, -A.conj().T))
+
+
+def is_symmetric(C):
+    """stiefel.py:394-396"""
+    C = np.asarray(C)
+    return bool(np.allclose(C, C.conj().T))
+
+
+def random_psd(dim, normalized=True):
+    """Random PSD matrix B B^T from uniform entries (trace 1 if normalised), stiefel.py:15-21."""
+    b = np.random.rand(dim, dim)
+    psd = b @ b.conj().T
+    return psd / np.trace(psd) if normalized else psd
+
+
+def polar_decomposition_stiefel(X, Z):
+    """(X + Z)(1 + Z^T Z)^(-1/2) for a TANGENT Z (Absil eq. 4.7), stiefel.py:312-321.  For a tangent vector X^T Z is skew, so
+    (X+Z)^T (X+Z) = 1 + Z^T Z and this is the polar factor `polar_decomposition_rectangular` computes on the device."""
+    X, Z = np.asarray(X), np.asarray(Z)
+    assert X.shape == Z.shape, "shapes don't match"
+    return polar_decomposition_rectangular(X, Z)
+
+
 def _tangents_from_vector(xi, vec):
     params = parametrizations_from_vector(vec, [np.asarray(x).shape for x in xi])
     return [tangent_from_parametrization(np.asarray(x), A, B) for x, (A, B) in zip(xi, params)]
@@ -381,6 +452,22 @@ class RiemannianHessianOperator:
 
     def __array__(self, dtype=None, copy=None):
         return self.to_dense()
+
+
+def riemannian_hessian(x, func, vector=False, metric="euclidean", check_complex=False, stiefel_elementary=True):
+    """Block form of the dense Hessian, stiefel.py:477-531 with vector=True: a list over source isometries i of lists over
+    target isometries j of (dof_j, dof_i) blocks -- what `riemannian_hessian_vec` stacks.  All columns come from one batched
+    device evaluation (`RiemannianHessianOperator.to_dense`)."""
+    if not vector:
+        raise NotImplementedError("only vector=True (coefficient blocks) is supported; the reference marks the other layout for deprecation")
+    metric_id(metric)
+    if not stiefel_elementary:
+        raise NotImplementedError("only the Stiefel elementary tangent basis is supported")
+    op = RiemannianHessianOperator(x, _need_fit(func), metric)
+    H = op.to_dense()
+    sizes = [stiefel_tangent_dof(a) for a in op.x]
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    return [[H[off[j]:off[j + 1], off[i]:off[i + 1]] for j in range(len(sizes))] for i in range(len(sizes))]
 
 
 def riemannian_hessian_vec(x, func, transpose=False, metric="euclidean", stiefel_elementary=True):

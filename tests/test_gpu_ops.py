@@ -141,6 +141,13 @@ def test_dense_hessian_config1_batched_columns(oracle, goldens):
         np.testing.assert_allclose(H[:, k], op @ e, rtol=0, atol=1e-11)
     v = rng.standard_normal(450)
     np.testing.assert_allclose(H @ v, op @ v, rtol=1e-10, atol=1e-10)
+    # block form (stiefel.py:477-531, vector=True): blocks[i][j] = rows of isometry j, columns of isometry i
+    blocks = S.riemannian_hessian(xs0, fit, vector=True, metric="canonical")
+    assert len(blocks) == 3 and blocks[1][2].shape == (150, 150)
+    np.testing.assert_allclose(blocks[1][2], H[300:450, 150:300], rtol=0, atol=1e-12)
+    # the tangent-only polar formula (stiefel.py:312-321) is the same retraction
+    eta = S._tangents_from_vector(xs0, 1e-2 * rng.standard_normal(450))
+    np.testing.assert_allclose(S.polar_decomposition_stiefel(xs0[0], eta[0]), S.polar_decomposition_rectangular(xs0[0], eta[0]), atol=1e-14)
     # against the oracle without building its dense matrix (76 s on one core): v^T H v == <eta, Hess[eta]> in the canonical
     # metric for the tangent eta our coefficient vector v stands for (basis independent)
     spec = P.CostSpec(T, "local", 4, 2)

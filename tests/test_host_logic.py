@@ -160,3 +160,30 @@ def test_gradient_requires_fit_object():
         gradient_stiefel_vec([np.zeros((8, 4))], lambda x: 0.0)
     with pytest.raises(ValueError, match="not a valid metric value"):
         riemannian_hessian_vec([np.zeros((8, 4))], None, metric="bogus")
+
+
+def test_elementary_tangent_directions_and_predicates():
+    """Host mirrors of the reference's tangent-basis helpers (stiefel.py:112-173, 252-264, 376-396): the k-th elementary direction
+    is the tangent whose coefficient vector is the k-th unit vector -- the convention the dense Hessian's columns follow."""
+    from opentn_b200 import stiefel as S
+    rng = np.random.default_rng(0)
+    x = np.linalg.qr(rng.standard_normal((8, 4)))[0]
+    dof = S.stiefel_tangent_dof(x)
+    assert dof == 6 + 16
+    for k in range(dof):
+        z = S.get_elementary_tangent_direction(k, x)
+        assert S.is_in_tangent_space(x, z)
+        e = np.zeros(dof); e[k] = 1.0
+        np.testing.assert_allclose(S.parametrization_from_tangent(x, z), e, atol=1e-12)
+    with pytest.raises(AssertionError):
+        S.get_elementary_tangent_direction(dof, x)
+    q = np.linalg.qr(rng.standard_normal((4, 4)))[0]
+    a = S.parametrization_from_tangent_square(q, q @ np.array([[0, 1, 0, 0], [-1, 0, 0, 2], [0, 0, 0, 0], [0, -2, 0, 0.]]))
+    np.testing.assert_allclose(a, [1, 0, 0, 0, 2, 0], atol=1e-12)
+    assert S.is_hermitian(np.eye(3)) is True
+    ok, dist = S.is_hermitian(np.array([[0, 1], [0, 0.]]))
+    assert ok is False and dist == pytest.approx(np.sqrt(2))
+    assert S.is_symmetric(np.eye(2)) and S.is_antisymmetric(np.array([[0, 1], [-1, 0.]])) and not S.is_antisymmetric(np.eye(2))
+    assert [u.shape for u in S.get_unit_matrices([x, q])] == [(8, 4), (4, 4)] and S.get_unit_matrices([x])[0][0, 0] == 1
+    p = S.random_psd(5)
+    assert p.trace() == pytest.approx(1.0) and np.linalg.eigvalsh(p).min() > -1e-12
