@@ -156,9 +156,6 @@ def polar_decomposition_rectangular(X, Z):
     return out.reshape(lead + (n, p))
 
 
-polar_decomposition_stiefel = polar_decomposition_rectangular  # stiefel.py:312-321 computes the same factor for tangent Z
-
-
 def riemannian_connection(D_nu, nu, eta, x, alpha0=1, alpha1=1):
     """stiefel.py:468-475 (GPU; accepts stacks).  Inside the accelerated HVP the connection is fused into the epilogue
     kernel (csrc/stiefel.cuh: riem_mma_kernel)."""

@@ -25,6 +25,21 @@ def kicked_start(xs0, seed, kick=1e-2):
     return polar_decomposition_rectangular(xs0, eta * (kick / nrm))
 
 
+def kicked_starts(xs0_stack, seeds, kick=1e-2):
+    """`kicked_start` for many instances at once: xs0_stack (B, m, n, p), one seed per instance.  The random directions are drawn
+    per instance exactly as in `kicked_start`; projection and polar retraction are one batched device call each."""
+    xs0_stack = np.asarray(xs0_stack, dtype=np.float64)
+    eta = np.empty_like(xs0_stack)
+    for b, seed in enumerate(seeds):
+        rng = np.random.default_rng(seed)
+        for l in range(xs0_stack.shape[1]):
+            eta[b, l] = rng.standard_normal(xs0_stack.shape[2:])
+    eta = project(xs0_stack, eta)
+    xte = np.swapaxes(xs0_stack, -1, -2) @ eta
+    nrm = np.sqrt(np.sum(eta * eta, axis=(1, 2, 3)) - 0.5 * np.sum(xte * xte, axis=(1, 2, 3)))
+    return polar_decomposition_rectangular(xs0_stack, eta * (kick / nrm)[:, None, None, None])
+
+
 def run_sweep(lindbladians, N, d, taus, ranks, seeds, n_steps=4, niter=10, device=0, rank=0, world=1, pbc=True, max_batch=1024,
               gather=None):
     """Returns {K: dict(tau_index, seed, f0, f_final, x0, x_final, status)} for the instances owned by `rank` (or, with
@@ -45,7 +60,7 @@ def run_sweep(lindbladians, N, d, taus, ranks, seeds, n_steps=4, niter=10, devic
         mine = inst[rank::world]
         if not mine:
             continue
-        xs = np.stack([kicked_start(list(starts[ti]), s) for ti, s in mine])
+        xs = kicked_starts(np.stack([starts[ti] for ti, _ in mine]), [s for _, s in mine])
         tindex = np.array([ti for ti, _ in mine], dtype=np.int32)
         xf = np.empty_like(xs)
         f0 = np.empty(len(mine)); ff = np.empty(len(mine)); status = np.zeros(len(mine), dtype=np.int32)

@@ -124,3 +124,13 @@ def test_sweep_driver_small(P):
             xs_host = [P.super2ortho(x, rank=K) for x in layers]
             spec = P.CostSpec(P.exp_operator_dt(Lvec, tau), "local", N, d)
             assert abs(spec(list(xs_dev)) - spec(xs_host)) < 1e-9
+
+
+def test_kicked_starts_batched_equals_single(P):
+    from opentn_b200 import sweep
+    rng = np.random.default_rng(0)
+    xs0 = np.stack([np.linalg.qr(rng.standard_normal((16, 4)))[0] for _ in range(5)])
+    many = sweep.kicked_starts(np.stack([xs0, xs0, xs0]), [3, 8, 3])
+    one = sweep.kicked_start(list(xs0), 8)
+    np.testing.assert_allclose(many[1], one, rtol=0, atol=1e-14)
+    np.testing.assert_array_equal(many[0], many[2])
