@@ -115,6 +115,11 @@ extern "C" int otn_tr_run(otn_problem* h, double* x, int batch, const otn_tr_par
     tp.stoptol = t.stoptol; tp.tcg_active = t.tcg_active; tp.on_boundary = t.on_boundary; tp.n_cg = t.n_cg; tp.status = t.status;
     tp.n_active = t.n_active; tp.n = h->n; tp.p = h->p; tp.m = h->m; tp.maxiter = maxiter; tp.abstol = prm.tcg_abstol; tp.reltol = prm.tcg_reltol;
 
+    // launch-bound regime (few small instances): sparser host checks and a CUDA graph for the tCG inner loop
+    const bool small_batch = (long long)batch * h->D <= 16384;
+    const bool use_graph = small_batch && !h->prof.on && getenv("OTN_NO_GRAPH") == nullptr;   // env: A/B switch for measurements
+    struct GraphHolder { cudaGraphExec_t exec = nullptr; bool failed = false; ~GraphHolder() { if (exec) cudaGraphExecDestroy(exec); } } cg_graph;
+
     for (int k = 0; k < prm.niter; ++k) {
         // grad = gradfunc(x) ; fx = f(x)  (same primal pass)                                       (:59, :63)
         OTN_TRY(otn_dev_cost_grad(h, h->x, batch, nullptr, t.fx, t.g, nullptr));
@@ -125,13 +130,37 @@ extern "C" int otn_tr_run(otn_problem* h, double* x, int batch, const otn_tr_par
         // (their CTAs exit at once), so the count of still-active instances is read back -- a stream synchronisation -- only
         // every `check` steps when the batch is small enough for launch/sync latency to matter; the Hessian-vector products
         // actually consumed are counted on the device.
-        const int check = ((long long)batch * h->D <= 16384) ? 4 : 1;
+        const int check = small_batch ? 4 : 1;
         int counters[2] = {batch, 0};
         CUDA_TRY(cudaMemsetAsync(t.n_active, 0, 8, st));
-        for (int j = 0; j < maxiter && counters[0] > 0; ++j) {
+        auto cg_step = [&]() -> int {               // one tCG iteration: H d, then the batched CG update
             OTN_TRY(otn_dev_hvp(h, h->x, t.d, batch, t.tcg_active, t.Hd));
             CUDA_TRY(cudaMemsetAsync(t.n_active, 0, 4, st));
             OTN_TRY(tcg_dispatch(h, tp, batch, false));
+            return 0;
+        };
+        for (int j = 0; j < maxiter && counters[0] > 0; ++j) {
+            if (cg_graph.exec) {
+                CUDA_TRY(cudaGraphLaunch(cg_graph.exec, st));
+            } else if (use_graph && !cg_graph.failed && (k > 0 || j > 0)) {
+                // every pointer of the step is owned by the handle, so the ~8 launches of one iteration are captured once (after
+                // a first plain execution has configured the kernels) and replayed for the rest of this call
+                cudaGraph_t graph = nullptr;
+                CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                const int rc = cg_step();
+                const cudaError_t ec = cudaStreamEndCapture(st, &graph);
+                if (rc == 0 && ec == cudaSuccess && cudaGraphInstantiate(&cg_graph.exec, graph, 0) == cudaSuccess) {
+                    cudaGraphDestroy(graph);
+                    CUDA_TRY(cudaGraphLaunch(cg_graph.exec, st));
+                } else {
+                    if (graph) cudaGraphDestroy(graph);
+                    cudaGetLastError();
+                    cg_graph.exec = nullptr; cg_graph.failed = true;
+                    OTN_TRY(cg_step());
+                }
+            } else {
+                OTN_TRY(cg_step());
+            }
             if ((j + 1) % check == 0 || j + 1 == maxiter) {
                 CUDA_TRY(cudaMemcpyAsync(counters, t.n_active, 8, cudaMemcpyDeviceToHost, st));
                 CUDA_TRY(cudaStreamSynchronize(st));
