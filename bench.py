@@ -258,6 +258,35 @@ def measure_fp64_peak(torch):
     return 2 * n ** 3 / best / 1e9  # TFLOP/s
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (sysfs), so that the pinned host buffers of the end-to-end
+    leg are first-touched there; with 8 ranks streaming 400 MB per step each, remote-node traffic is what limits `e2e`.
+    Returns a description for the JSON line, or None when the topology is not exposed."""
+    if os.environ.get("OTN_BENCH_NO_NUMA"):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(gpu_index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dev = "/sys/bus/pci/devices/" + bus.lower()[-12:]
+        node = int(open(dev + "/numa_node").read())
+        if node < 0:
+            return None
+        cpulist = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "cpus": cpulist}
+    except Exception:
+        return None
+
+
 def two_site_leg(torch, lib, C, _lib, StiefelFit, T, stream, device, peak_tf, steps):
     """U1 throughput of the 2-site model on a config-4-shaped batch (1024 instances of 9 layers (64, 4)): the factored evaluation
     (csrc/factored.cuh, default) against the block-diagonal D x D chain, device-resident inputs, CUDA events."""
@@ -322,6 +351,8 @@ def run_gpu(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local_rank)      # before any pinned allocation: host staging buffers land next to the GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = _lib.load()
@@ -509,6 +540,7 @@ def run_gpu(args):
 
     cpu = None
     if not args.no_cpu and world == 1:     # the host-core baseline is timed at N = 1 only (rank 0 would compete with N-1 ranks)
+        os.sched_setaffinity(0, all_cpus)  # the CPU baseline gets every core of the box, not just the GPU's NUMA node
         pool = CpuPool()
         try:
             v, total, wall = pool.run(64)
@@ -526,7 +558,7 @@ def run_gpu(args):
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(),
+            "data": "synthetic", "config": workload_config({"host_numa_binding": numa} if numa else None),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
