@@ -26,8 +26,12 @@
 namespace otn {
 
 enum { FACT_COST = 0, FACT_GRAD = 1, FACT_HVP = 2, FACT_MODEL = 3, FACT_HVPONLY = 4 };   // HVPONLY: tangent cotangents only (tCG)
-// threads per CTA: 8 warps at N = 4 (two CTAs per SM), 16 warps at N = 6 (one CTA per SM: 192 KB of states)
-template <int NF> struct FactThreads { static constexpr int THREADS = (NF == 2) ? 256 : 512; static constexpr int WARPS = THREADS / 32; };
+// threads per CTA: one warp per two n-tiles of a state -- 8 warps at N = 4 with 8 columns (two CTAs per SM), 2 warps with the
+// 2-column tiles used for a handful of instances (4x more CTAs), 16 warps at N = 6 (one CTA per SM: 192 KB of states)
+template <int NF, int NCOLS> struct FactThreads {
+    static constexpr int THREADS = (NF == 3) ? 512 : 32 * NCOLS;
+    static constexpr int WARPS = THREADS / 32;
+};
 
 struct FactParams {
     const double* Yl; const double* Yld;   // [B][m][256] local superoperators and tangents
@@ -52,8 +56,9 @@ template <int NF> struct FactDims { static constexpr int D = (NF == 2) ? 256 : 4
 // rest indices -- fall into 16 different 8-byte banks (ncu before the swizzle: 5-way conflicts, L1 pipe 84 % busy).
 template <int NF, int NCOLS>
 __device__ __forceinline__ int fact_swz(int r) {
-    if (NF == 2) return ((((r >> 1) ^ (r >> 2) ^ (r >> 3)) & 1) << 3) | ((((r >> 1) ^ (r >> 3)) & 1) << 2);   // NCOLS == 8
-    return ((r >> 4) & 3) << 2;                                                                             // NCOLS == 1
+    if (NF == 2 && NCOLS == 8) return ((((r >> 1) ^ (r >> 2) ^ (r >> 3)) & 1) << 3) | ((((r >> 1) ^ (r >> 3)) & 1) << 2);
+    if (NF == 3) return ((r >> 4) & 3) << 2;                                                               // NCOLS == 1
+    return 0;   // narrow tiles (latency regime, not shared-memory bound): plain layout
 }
 
 constexpr int FACT_YLD = 20;   // row pitch of the staged 16 x 16 local superoperators (+4: conflict-free fragment reads)
@@ -81,7 +86,7 @@ __device__ __forceinline__ void fact_apply(const double* src, const double* srcd
                                            const double (&a)[2][4], const double (&ad)[2][4],
                                            const int* __restrict__ jrow, const int* __restrict__ restrow) {
     constexpr int NV = FactDims<NF>::REST * NCOLS, NT = NV / 8, U = 2;
-    constexpr int FACT_WARPS = FactThreads<NF>::WARPS;
+    constexpr int FACT_WARPS = FactThreads<NF, NCOLS>::WARPS;
     static_assert(NT % (FACT_WARPS * U) == 0, "n-tiles must split evenly over the warps");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, lr = lane >> 2, lc = lane & 3;
     int jb[4], sb[4], jc[2], sc[2];
@@ -149,7 +154,7 @@ template <int NF, int NCOLS, bool DUAL, bool PRIMAL>
 __device__ __forceinline__ void fact_contract(const double* X, const double* Xd, const double* Z, const double* Zd,
                                               const int* __restrict__ jrow, const int* __restrict__ restrow,
                                               double (&acc)[2][2][2], double (&accd)[2][2][2]) {
-    constexpr int NV = FactDims<NF>::REST * NCOLS, FACT_WARPS = FactThreads<NF>::WARPS;
+    constexpr int NV = FactDims<NF>::REST * NCOLS, FACT_WARPS = FactThreads<NF, NCOLS>::WARPS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, lr = lane >> 2, lc = lane & 3;
     const int j0 = jrow[lr], j1 = jrow[8 + lr];
     const int ro[2] = {j0 * NCOLS, j1 * NCOLS}, so[2] = {fact_swz<NF, NCOLS>(j0), fact_swz<NF, NCOLS>(j1)};
@@ -192,9 +197,9 @@ struct FactCfg {
 };
 
 template <int NF, int NCOLS, int MODE>
-__global__ void __launch_bounds__(FactThreads<NF>::THREADS, (NF == 2 ? 2 : 1)) fact_kernel(const FactParams p) {
+__global__ void __launch_bounds__(FactThreads<NF, NCOLS>::THREADS, (NF == 2 ? 2 : 1)) fact_kernel(const FactParams p) {
     using Cfg = FactCfg<NF, NCOLS, MODE>;
-    constexpr int FACT_THREADS = FactThreads<NF>::THREADS, FACT_WARPS = FactThreads<NF>::WARPS;
+    constexpr int FACT_THREADS = FactThreads<NF, NCOLS>::THREADS, FACT_WARPS = FactThreads<NF, NCOLS>::WARPS;
     constexpr int D = Cfg::D, SB = Cfg::SB, REST = D / 16;
     constexpr bool DUAL = MODE == FACT_HVP || MODE == FACT_HVPONLY;
     constexpr bool REV = MODE == FACT_GRAD || DUAL;
@@ -231,9 +236,9 @@ __global__ void __launch_bounds__(FactThreads<NF>::THREADS, (NF == 2 ? 2 : 1)) f
     // ---- forward ----------------------------------------------------------------------------------------------------
     for (int l = 0; l < p.m; ++l) {
         __syncthreads();                            // previous layer done with Ysm; state complete
-        if (tid < 256) {
-            Ysm[(tid >> 4) * FACT_YLD + (tid & 15)] = Yb[(size_t)l * 256 + tid];
-            if (DUAL) Ydsm[(tid >> 4) * FACT_YLD + (tid & 15)] = Ydb[(size_t)l * 256 + tid];
+        for (int t = tid; t < 256; t += FACT_THREADS) {
+            Ysm[(t >> 4) * FACT_YLD + (t & 15)] = Yb[(size_t)l * 256 + t];
+            if (DUAL) Ydsm[(t >> 4) * FACT_YLD + (t & 15)] = Ydb[(size_t)l * 256 + t];
         }
         if (REV && l >= 1) {                        // state entering layer l
             if (l == p.m - 1) {                     // the reverse sweep starts here: keep it in shared memory
@@ -301,9 +306,9 @@ __global__ void __launch_bounds__(FactThreads<NF>::THREADS, (NF == 2 ? 2 : 1)) f
 #pragma unroll 1
     for (int l = p.m - 1; l >= 0; --l) {
         __syncthreads();
-        if (tid < 256) {
-            Ysm[(tid >> 4) * FACT_YLD + (tid & 15)] = Yb[(size_t)l * 256 + tid];
-            if (DUAL) Ydsm[(tid >> 4) * FACT_YLD + (tid & 15)] = Ydb[(size_t)l * 256 + tid];
+        for (int t = tid; t < 256; t += FACT_THREADS) {
+            Ysm[(t >> 4) * FACT_YLD + (t & 15)] = Yb[(size_t)l * 256 + t];
+            if (DUAL) Ydsm[(t >> 4) * FACT_YLD + (t & 15)] = Ydb[(size_t)l * 256 + t];
         }
         if (l >= 1) {
             // P / Pd already hold the state entering layer l: left there by the forward pass (l = m-1) or prefetched with
@@ -356,17 +361,17 @@ __global__ void __launch_bounds__(FactThreads<NF>::THREADS, (NF == 2 ? 2 : 1)) f
                         if (DUAL) part[256 + idx] = accd[mt][nt][e];
                     }
             __syncthreads();
-            if (tid < 256) {
+            for (int t = tid; t < 256; t += FACT_THREADS) {
                 double s = 0.0, sd = 0.0;
-                const int row = tid >> 4, ti = (tid & ~15) | ((tid & 15) ^ ((row & 1) | ((row & 2) << 2)));
+                const int row = t >> 4, ti = (t & ~15) | ((t & 15) ^ ((row & 1) | ((row & 2) << 2)));
 #pragma unroll
                 for (int w = 0; w < FACT_WARPS; ++w) {
                     if (PRIMALW) s += tmp[(size_t)w * (DUAL ? 512 : 256) + ti];
                     if (DUAL) sd += tmp[(size_t)w * 512 + 256 + ti];
                 }
                 double* o = wp + ((size_t)l * NF + f) * 512;
-                if (PRIMALW) o[tid] = s;
-                if (DUAL) o[256 + tid] = sd;
+                if (PRIMALW) o[t] = s;
+                if (DUAL) o[256 + t] = sd;
             }
             __syncthreads();
             if (!(l == 0 && f == NF - 1)) {         // B_{f+1} = A_f^T B_f

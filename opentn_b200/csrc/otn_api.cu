@@ -319,7 +319,8 @@ extern "C" int otn_create_ex(otn_problem** out, int N, int d, int m, int K, int 
     if ((flags & OTN_FLAG_FACTORED) || (fact_possible && !(flags & (OTN_FLAG_DENSE | OTN_FLAG_BLOCKS)))) {
         h->factored = true;
         h->structured = false;
-        h->f_ncols = (N == 4) ? 8 : 1;
+        // N = 4: 8-column tiles (17 per instance); with only a handful of instances 2-column tiles give 4x more, smaller CTAs
+        h->f_ncols = (N == 4) ? (max_batch <= 4 ? 2 : 8) : 1;
         h->f_tiles = (sdim * (sdim + 1) / 2 + h->f_ncols - 1) / h->f_ncols;
     }
     if (h->structured) {
@@ -962,7 +963,7 @@ static int fact_eval(otn_problem* h, int batch, const int* active, int mode, dou
     do {                                                                                                 \
         const size_t sm = FactCfg<NFV, NCV, MODEV>::SMEM_BYTES;                                          \
         OTN_TRY(set_smem(fact_kernel<NFV, NCV, MODEV>, sm));                                             \
-        fact_kernel<NFV, NCV, MODEV><<<grid, FactThreads<NFV>::THREADS, sm, h->stream>>>(p);            \
+        fact_kernel<NFV, NCV, MODEV><<<grid, FactThreads<NFV, NCV>::THREADS, sm, h->stream>>>(p);       \
     } while (0)
 #define FACT_MODE(NFV, NCV)                                                                              \
     do {                                                                                                 \
@@ -972,7 +973,7 @@ static int fact_eval(otn_problem* h, int batch, const int* active, int mode, dou
         else if (mode == FACT_HVPONLY) FACT_LAUNCH(NFV, NCV, FACT_HVPONLY);                              \
         else FACT_LAUNCH(NFV, NCV, FACT_MODEL);                                                          \
     } while (0)
-    if (h->nf == 2) FACT_MODE(2, 8); else FACT_MODE(3, 1);
+    if (h->nf == 2 && h->f_ncols == 8) FACT_MODE(2, 8); else if (h->nf == 2) FACT_MODE(2, 2); else FACT_MODE(3, 1);
 #undef FACT_MODE
 #undef FACT_LAUNCH
     CUDA_TRY(cudaGetLastError());

@@ -34,14 +34,15 @@ def _random_batch(P, B, m, n, p, seed):
     return xs, et
 
 
+@pytest.mark.parametrize("max_batch", [3, 64])      # <= 4 instances: 2-column tiles; more: 8-column tiles (two kernel variants)
 @pytest.mark.parametrize("metric", ["canonical", "euclidean"])
 @pytest.mark.parametrize("m,K,tname", [(3, 10, "pspl_tau1"), (9, 16, "kitaev_pbc_tau05"), (1, 3, "pspl_tau1"), (4, 2, "pspl_tau1")])
-def test_factored_triple_vs_oracle(P, targets, metric, m, K, tname):
+def test_factored_triple_vs_oracle(P, targets, metric, m, K, tname, max_batch):
     from opentn_b200 import StiefelFit
     T = targets[tname]
     B = 3
     xs, et = _random_batch(P, B, m, 4 * K, 4, 21 + m)
-    fit = StiefelFit(T, model="local", N=N, d=d, metric=metric, max_batch=B, factored=True)
+    fit = StiefelFit(T, model="local", N=N, d=d, metric=metric, max_batch=max_batch, factored=True)
     M = fit.model_matrix(xs)
     for b in range(B):
         np.testing.assert_allclose(M[b], P.model_stiefel_local(list(xs[b]), N, d), rtol=0, atol=1e-13)
@@ -145,7 +146,7 @@ def test_factored_edge_shapes(P, targets, m, K):
     T = targets["pspl_tau1"]
     B = 2
     xs, et = _random_batch(P, B, m, 4 * K, 4, 100 + m)
-    fit = StiefelFit(T, model="local", N=N, d=d, max_batch=B, factored=True)
+    fit = StiefelFit(T, model="local", N=N, d=d, max_batch=16, factored=True)
     ref = StiefelFit(T, model="local", N=N, d=d, max_batch=B, dense=False)
     f, g, h = fit.triple(xs, et)
     f2, g2, h2 = ref.triple(xs, et)
@@ -177,7 +178,7 @@ def test_factored_batched_tr_vs_oracle(P, targets):
     T = targets["kitaev_pbc_tau05"]
     B, m, K = 3, 3, 4
     xs, _ = _random_batch(P, B, m, 4 * K, 4, 77)
-    fit = StiefelFit(T, model="local", N=N, d=d, max_batch=B, factored=True)
+    fit = StiefelFit(T, model="local", N=N, d=d, max_batch=8, factored=True)
     x, rep = fit.tr_run(xs, niter=3)
     spec = P.CostSpec(T, "local", N, d)
     for b in range(B):
