@@ -187,3 +187,35 @@ def test_elementary_tangent_directions_and_predicates():
     assert [u.shape for u in S.get_unit_matrices([x, q])] == [(8, 4), (4, 4)] and S.get_unit_matrices([x])[0][0, 0] == 1
     p = S.random_psd(5)
     assert p.trace() == pytest.approx(1.0) and np.linalg.eigvalsh(p).min() > -1e-12
+
+
+def test_liouvillian_term_lists_match_kron_route(monkeypatch):
+    """The (operator, site0, site1) term lists `create_2local_liouvillians(backend='cuda')` hands to otn_liouvillian, evaluated
+    here by a NumPy stand-in for the kernel, reproduce the reference's kron / permute route (odd, even and periodic sums)."""
+    from opentn_b200 import transformations as T
+
+    def place(op, s0, s1, N, d):
+        # two-site operator with its first factor on site s0 and its second on s1, identity elsewhere
+        full = np.kron(op, np.eye(d ** (N - 2)))                       # factors on sites (0, 1), rest in order
+        rest = [s for s in range(N) if s not in (s0, s1)]
+        perm = [0] * N                                                  # new axis j <- old axis perm[j]
+        for old, new in enumerate([s0, s1] + rest):
+            perm[new] = old
+        return T.permute_operator(full, perm, d)
+
+    def numpy_terms(ops, terms, N, d):
+        out = np.zeros((d ** (2 * N), d ** (2 * N)), dtype=complex)
+        for j, s0, s1 in terms:
+            out += T.vectorize_dissipative(place(np.asarray(ops[j], dtype=complex), s0, s1, N, d))
+        return out
+
+    monkeypatch.setattr(T, "_liouvillian_terms_device", numpy_terms)
+    rng = np.random.default_rng(0)
+    Li = [rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4)), T.get_kitaev_nn_linbladian(0.5)]
+    for N, pbc in ((2, True), (4, False), (4, True)):
+        want = T.create_2local_liouvillians(Li, N, 2, pbc=pbc)
+        got = T.create_2local_liouvillians(Li, N, 2, pbc=pbc, backend="cuda")
+        for g, w in zip(got, want):
+            np.testing.assert_allclose(g, w, rtol=0, atol=1e-13)
+    with pytest.raises(ValueError):
+        T.create_2local_liouvillians(Li, 3, 2, backend="cuda")
