@@ -76,3 +76,47 @@ def test_argument_validation_messages():
         fit._prep(np.zeros((3, 40, 5)))
     with pytest.raises(NotImplementedError, match="complex isometries"):
         fit._prep(np.zeros((3, 40, 4)) + 1j)
+
+
+def _compile_c_demo(tmp_path):
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    from opentn_b200 import build
+    lib = build.build(force=False)
+    exe = str(tmp_path / "c_abi_demo")
+    libdir = os.path.dirname(lib)
+    cmd = ["gcc", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "c_abi_demo.c"),
+           "-L", libdir, "-lotn", f"-Wl,-rpath,{libdir}", "-lm", "-o", exe]
+    subprocess.run(cmd, check=True, capture_output=True)
+    return exe
+
+
+def test_c_host_compiles_against_header(tmp_path):
+    """include/otn.h is plain C (no torch / C++ types): a C host compiles and links against libotn.so with gcc."""
+    exe = _compile_c_demo(tmp_path)
+    assert os.path.exists(exe)
+
+
+@pytest.mark.gpu
+def test_c_host_runs_and_matches_golden(tmp_path, goldens, oracle):
+    """The C host of examples/c_abi_demo.c on config 1: cost = the reference's printed 0.11294517951068227, gradient norm and
+    <g, H g> equal the oracle's, three TR iterations reproduce the golden history."""
+    import subprocess
+    P = oracle
+    exe = _compile_c_demo(tmp_path)
+    Li = P.pspl_lindbladians(1.0)
+    T = P.exp_operator_dt(P.create_2local_liouvillians(Li, 4, 2, pbc=True)[0], 1.0)
+    xs0 = [np.asarray(x) for x in goldens["ref/xs0_pspl_n1_K10"]]
+    np.ascontiguousarray(T.real).tofile(tmp_path / "t.bin")
+    np.ascontiguousarray(np.stack(xs0)).tofile(tmp_path / "x.bin")
+    out = subprocess.run([exe, str(tmp_path / "t.bin"), str(tmp_path / "x.bin"), "4", "3", "10"], check=True, capture_output=True, text=True)
+    f, gnorm, ghg, f_after = (float(v) for v in out.stdout.split())
+    assert abs(f - goldens["known/pspl_n1_tau1_K10_cost0"]) < 1e-13
+    spec = P.CostSpec(T, "local", 4, 2)
+    _, g = P.cost_rgrad(spec, xs0, "canonical")
+    assert abs(gnorm - np.sqrt(sum((a * a).sum() for a in g))) < 1e-10
+    want = P.canonical_dot(xs0, g, P.hvp(spec, xs0, g, "canonical"))
+    assert abs(ghg - want) < 1e-9 * abs(want)
+    assert abs(f_after - goldens["art/f_pauli_n1_tau1_rank10"][3]) < 1e-8
