@@ -94,6 +94,19 @@ int otn_cost_grad(otn_problem* p, const double* x, int batch, double* f, double*
 int otn_triple(otn_problem* p, const double* x, const double* eta, int batch, double* f, double* rgrad, double* heta);
 int otn_hvp_cached(otn_problem* p, const double* eta, int batch, double* heta);
 
+/* ---- streamed form of otn_triple for host arrays ("_async variant") ---------------------------------------
+ * otn_triple_submit : enqueues the chunked H2D / kernels / D2H pipeline of one otn_triple call and returns at once with a
+ *                     ticket; the caller may submit the next batch (other host arrays) before waiting, so the copies of one
+ *                     batch overlap the kernels of its neighbours.  The host arrays (pinned memory for real overlap) must stay
+ *                     valid and untouched until the ticket has been waited for.  At most 4 tickets are outstanding: a 5th
+ *                     submit first waits for the oldest.  Replaces a loop of cost / gradient / `hess @ d` evaluations over
+ *                     many parameter sets (the tau x rank x seed sweeps of the reference's notebooks), stiefel.py:411-544.
+ * otn_triple_wait   : blocks until the outputs of `ticket` are in the caller's host arrays (ticket < 0: all of them).
+ *                     Any other call on the handle waits for all outstanding submissions first. */
+int otn_triple_submit(otn_problem* p, const double* x, const double* eta, int batch, double* f, double* rgrad, double* heta,
+                      long long* ticket);
+int otn_triple_wait(otn_problem* p, long long ticket);
+
 /* ---- representation layer (stateless; `device` selects the GPU) -----------------------------------------------------
  * otn_ortho2super : Y[count][dim^2][dim^2] = sum_k E_k (x) E_k      ortho2super (transformations.py:743-749),
  *                   == kraus2superop of E_k = x[k::K,:] (transformations.py:170-180)

@@ -54,6 +54,8 @@ SIGNATURES = {
     "otn_cost_grad": (C.c_int, [C.c_void_p, _dp, C.c_int, _dp, _dp, _dp]),
     "otn_triple": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int, _dp, _dp, _dp]),
     "otn_hvp_cached": (C.c_int, [C.c_void_p, _dp, C.c_int, _dp]),
+    "otn_triple_submit": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int, _dp, _dp, _dp, C.POINTER(C.c_longlong)]),
+    "otn_triple_wait": (C.c_int, [C.c_void_p, C.c_longlong]),
     "otn_ortho2super": (C.c_int, [_dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int]),
     "otn_embed_local": (C.c_int, [_dp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int]),
     "otn_compose": (C.c_int, [_dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int]),

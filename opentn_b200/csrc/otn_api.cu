@@ -227,6 +227,13 @@ struct otn_problem {
     // host-pointer pipeline (otn_triple): chunked H2D / compute / D2H overlap
     cudaStream_t s_in = nullptr, s_out = nullptr, s_comp[2] = {nullptr, nullptr};
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    long long pipe_seq = 0;      // chunks enqueued so far (staging slot = pipe_seq & 1; slot reuse is ordered across calls)
+    // streamed submissions (otn_triple_submit / otn_triple_wait): ticket t completes when ev_ticket[t % 4] has fired
+    enum { TICKETS = 4 };
+    cudaEvent_t ev_ticket[TICKETS] = {nullptr, nullptr, nullptr, nullptr};
+    long long next_ticket = 0;
+    bool pipe_inflight = false;
+    int pipe_prev_b0 = 0, pipe_prev_nb = 0;   // workspace slice of the most recently enqueued chunk
     DevBuf pipe_buf;
     DevBuf tr_buf;
     // factored evaluation of the 2-site model (factored.cuh)
@@ -238,9 +245,22 @@ struct otn_problem {
     EmbedTables tables() const { return EmbedTables{tab, inv, D, q, nf}; }
 };
 
-static int check_batch(otn_problem* h, int batch) {
+// Streamed submissions (otn_triple_submit) leave work in flight on the pipeline streams; every other entry point of the handle
+// shares the workspaces with it and therefore drains the pipeline first.
+static int drain_pipeline(otn_problem* h) {
+    if (!h->pipe_inflight) return 0;
+    DeviceGuard dev_guard__(h->device);
+    CUDA_TRY(cudaStreamSynchronize(h->s_in));
+    for (int i = 0; i < 2; ++i) CUDA_TRY(cudaStreamSynchronize(h->s_comp[i]));
+    CUDA_TRY(cudaStreamSynchronize(h->s_out));
+    h->pipe_inflight = false;
+    return 0;
+}
+
+static int check_batch(otn_problem* h, int batch, bool drain = true) {
     if (h == nullptr) return fail("null handle");
     if (batch < 1 || batch > h->max_batch) return fail("batch %d outside [1, max_batch=%d]", batch, h->max_batch);
+    if (drain) return drain_pipeline(h);
     return 0;
 }
 
@@ -258,6 +278,10 @@ extern "C" void otn_destroy(otn_problem* h) {
     for (auto& r : h->prof.recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (auto e : h->prof.pool) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) for (cudaEvent_t e : {h->ev_in[i], h->ev_done[i], h->ev_out[i]}) if (e) cudaEventDestroy(e);
+    if (h->s_in) cudaStreamSynchronize(h->s_in);
+    for (int i = 0; i < 2; ++i) if (h->s_comp[i]) cudaStreamSynchronize(h->s_comp[i]);
+    if (h->s_out) cudaStreamSynchronize(h->s_out);
+    for (cudaEvent_t e : h->ev_ticket) if (e) cudaEventDestroy(e);
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
     for (int i = 0; i < 2; ++i) if (h->s_comp[i]) cudaStreamDestroy(h->s_comp[i]);
@@ -1139,7 +1163,11 @@ static void shift_instance_views(otn_problem* h, long long db) {
 // Host arrays in, host arrays out: the batch is cut into chunks and pipelined so that the PCIe copies of chunk c+1 (H2D) and
 // chunk c-1 (D2H) overlap the kernels of chunk c; chunks alternate between two compute streams and work on disjoint slices of
 // the workspaces, so the tail of one chunk's kernels overlaps the head of the next.  Double-buffered staging, ordering by events.
-static int triple_pipelined(otn_problem* h, const double* x, const double* eta, int batch, double* f, double* rgrad, double* heta) {
+// `ticket` == nullptr: synchronous (returns when the host arrays are filled).  Otherwise the call only enqueues: the slot-reuse
+// events order its chunks behind those of earlier submissions, so the head H2D of this call overlaps the kernels of the previous
+// one and the tail D2H of the previous call overlaps the kernels of this one; *ticket identifies the completion event.
+static int triple_pipelined(otn_problem* h, const double* x, const double* eta, int batch, double* f, double* rgrad, double* heta,
+                            long long* ticket = nullptr) {
     const int C = 256;
     const size_t per = (size_t)h->m * h->np;
     if (!h->s_in) {
@@ -1151,6 +1179,7 @@ static int triple_pipelined(otn_problem* h, const double* x, const double* eta, 
             CUDA_TRY(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
         }
+        for (cudaEvent_t& e : h->ev_ticket) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     // staging: per slot  x | eta | rgrad | heta | f
     const int CMAX = 3 * C;
@@ -1171,6 +1200,10 @@ static int triple_pipelined(otn_problem* h, const double* x, const double* eta, 
             if (*q == ',') ++q;
         }
         while (left > 0) { const int n = std::min(C, left); sizes.push_back(n); left -= n; }
+    } else if (ticket != nullptr) {
+        // streamed: head and tail copies hide behind the neighbouring submissions, so few large chunks (kernel efficiency) win;
+        // measured at 1024 instances (ms per step): 512/512 8.81, 4 x 256 9.07, 128/256/256/256/128 9.66, 96/288/288/256/96 9.69
+        for (int left = batch; left > 0; left -= 2 * C) sizes.push_back(std::min(2 * C, left));
     } else if (batch >= 4 * C) {
         // measured at 1024 instances (ms per step): 96/288/288/256/96 10.37, 64/192/256/256/192/64 10.44, 128/384/384/128 10.68,
         // 8 x 128 10.83
@@ -1184,17 +1217,22 @@ static int triple_pipelined(otn_problem* h, const double* x, const double* eta, 
     }
     const int nchunks = (int)sizes.size();
     int b0 = 0;
-    for (int c = 0; c < nchunks; ++c) {
-        const int slot = c & 1, nb = sizes[c];
+    for (int c = 0; c < nchunks; ++c, ++h->pipe_seq) {
+        const int slot = (int)(h->pipe_seq & 1), nb = sizes[c];
         double* base = h->pipe_buf.as<double>() + slot * slot_doubles;
         double *dx = base, *de = dx + (size_t)CMAX * per, *dg = de + (size_t)CMAX * per, *dh = dg + (size_t)CMAX * per, *df = dh + (size_t)CMAX * per;
-        if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_done[slot], 0));          // kernels of chunk c-2 finished reading dx/de
+        if (h->pipe_seq >= 2) CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_done[slot], 0));   // kernels of chunk c-2 finished reading dx/de
         CUDA_TRY(cudaMemcpyAsync(dx, x + (size_t)b0 * per, nb * per * 8, cudaMemcpyHostToDevice, h->s_in));
         CUDA_TRY(cudaMemcpyAsync(de, eta + (size_t)b0 * per, nb * per * 8, cudaMemcpyHostToDevice, h->s_in));
         CUDA_TRY(cudaEventRecord(h->ev_in[slot], h->s_in));
         cudaStream_t comp = h->s_comp[slot];
         CUDA_TRY(cudaStreamWaitEvent(comp, h->ev_in[slot], 0));
-        if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(comp, h->ev_out[slot], 0));              // D2H of chunk c-2 drained dg/dh/df
+        if (h->pipe_seq >= 2) CUDA_TRY(cudaStreamWaitEvent(comp, h->ev_out[slot], 0));       // D2H of chunk c-2 drained dg/dh/df
+        // neighbouring chunks overlap on the two compute streams and must not share a workspace slice: always true inside one
+        // call, across calls only if the first chunk of this call stays clear of the last chunk of the previous one
+        if (h->pipe_seq >= 1 && b0 < h->pipe_prev_b0 + h->pipe_prev_nb && h->pipe_prev_b0 < b0 + nb)
+            CUDA_TRY(cudaStreamWaitEvent(comp, h->ev_done[slot ^ 1], 0));
+        h->pipe_prev_b0 = b0; h->pipe_prev_nb = nb;
         cudaStream_t user_stream = h->stream;
         h->stream = comp;
         shift_instance_views(h, b0);
@@ -1210,10 +1248,18 @@ static int triple_pipelined(otn_problem* h, const double* x, const double* eta, 
         CUDA_TRY(cudaEventRecord(h->ev_out[slot], h->s_out));
         b0 += nb;
     }
+    h->cached_batch = 0;   // the work matrices hold the last chunk only
+    if (ticket != nullptr) {
+        const long long t = h->next_ticket++;
+        CUDA_TRY(cudaEventRecord(h->ev_ticket[t % otn_problem::TICKETS], h->s_out));   // s_out runs the D2H copies in order
+        h->pipe_inflight = true;
+        *ticket = t;
+        return 0;
+    }
     CUDA_TRY(cudaStreamSynchronize(h->s_in));
     for (int i = 0; i < 2; ++i) CUDA_TRY(cudaStreamSynchronize(h->s_comp[i]));
     CUDA_TRY(cudaStreamSynchronize(h->s_out));
-    h->cached_batch = 0;   // the work matrices hold the last chunk only
+    h->pipe_inflight = false;
     return 0;
 }
 
@@ -1237,6 +1283,33 @@ extern "C" int otn_triple(otn_problem* h, const double* x, const double* eta, in
     OTN_TRY(finish_out(rgrad, gd, xbytes(h, batch), h->stream));
     OTN_TRY(finish_out(heta, hd, xbytes(h, batch), h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int otn_triple_submit(otn_problem* h, const double* x, const double* eta, int batch, double* f, double* rgrad, double* heta,
+                                 long long* ticket) {
+    OTN_TRY(check_batch(h, batch, /*drain=*/false));
+    DeviceGuard dev_guard__(h->device);
+    if (!x || !eta || !ticket) return fail("null argument");
+    if (is_device_ptr(x) || is_device_ptr(eta) || (f && is_device_ptr(f)) || (rgrad && is_device_ptr(rgrad)) || (heta && is_device_ptr(heta)))
+        return fail("otn_triple_submit takes host arrays (device-resident data: otn_triple on the handle's stream)");
+    // the completion event of ticket t - TICKETS is about to be re-recorded: that submission must have finished
+    if (h->next_ticket >= otn_problem::TICKETS && h->ev_ticket[0] != nullptr)
+        CUDA_TRY(cudaEventSynchronize(h->ev_ticket[h->next_ticket % otn_problem::TICKETS]));
+    return triple_pipelined(h, x, eta, batch, f, rgrad, heta, ticket);
+}
+
+extern "C" int otn_triple_wait(otn_problem* h, long long ticket) {
+    if (h == nullptr) return fail("null handle");
+    if (ticket < 0) return drain_pipeline(h);
+    if (ticket >= h->next_ticket) return fail("ticket %lld was never issued (next is %lld)", ticket, h->next_ticket);
+    if (ticket + otn_problem::TICKETS < h->next_ticket) return 0;   // its event was re-used: submit waited for it already
+    DeviceGuard dev_guard__(h->device);
+    CUDA_TRY(cudaEventSynchronize(h->ev_ticket[ticket % otn_problem::TICKETS]));
+    if (ticket + 1 == h->next_ticket) {   // the newest submission is done, hence all of them: nothing left in flight
+        CUDA_TRY(cudaStreamSynchronize(h->s_out));
+        h->pipe_inflight = false;
+    }
     return 0;
 }
 

@@ -243,6 +243,40 @@ class StiefelFit:
             return float(f[0]), g[0], hv[0]
         return f, g, hv
 
+    def triple_submit(self, xs, etas, out):
+        """Streamed form of `triple` for host arrays [B,m,n,p] (pinned torch tensors or numpy): enqueues the copies and kernels
+        of this batch and returns a ticket at once; `out = (f, rgrad, heta)` are host arrays that `triple_wait(ticket)` fills.
+        Submitting the next batch before waiting overlaps its copies with this batch's kernels (otn_triple_submit)."""
+        x, B, m, K, single, cuda = self._prep(xs)
+        e, B2, m2, K2, _, cuda2 = self._prep(etas)
+        if (B, m, K) != (B2, m2, K2):
+            raise ValueError("xs and etas must have the same shape")
+        if cuda or cuda2 or any(getattr(o, "is_cuda", False) for o in out):
+            raise ValueError("triple_submit takes host arrays; device-resident data goes through triple()")
+        h = self._handle(m, K, B)
+        self._bind(h, B)
+        f, g, hv = out
+        ticket = C.c_longlong(-1)
+        check(h._lib.otn_triple_submit(h.h, ptr(x), ptr(e), B, ptr(f), ptr(g), ptr(hv), C.byref(ticket)))
+        self._cached = None
+        self._inflight = getattr(self, "_inflight", {})
+        key = (id(h), ticket.value)                        # tickets are per handle (one handle per (m, K, max_batch))
+        self._inflight[key] = (h, x, e, out)               # keep the host arrays alive until the wait
+        return key
+
+    def triple_wait(self, ticket=None):
+        """Block until the outputs of `ticket` (default: every outstanding submission) are in their host arrays."""
+        inflight = getattr(self, "_inflight", {})
+        if ticket is None:
+            for t in sorted(inflight):
+                self.triple_wait(t)
+            return
+        if ticket not in inflight:
+            raise OtnError(f"ticket {ticket} is not outstanding")
+        h = inflight[ticket][0]
+        check(h._lib.otn_triple_wait(h.h, ticket[1]))
+        del inflight[ticket]
+
     def hvp_cached(self, etas):
         """H eta at the x of the latest cost_grad / triple call."""
         cached = getattr(self, "_cached", None)

@@ -1,0 +1,122 @@
+"""Streamed submissions (otn_triple_submit / otn_triple_wait): results identical to the synchronous call and to the oracle,
+with several batches in flight, batches of one chunk (workspace slices of neighbouring calls coincide) and of several chunks."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+N, d = 4, 2
+
+
+def rel(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300)
+
+
+def _pinned(shape):
+    import torch
+    return torch.empty(shape, dtype=torch.float64).pin_memory()
+
+
+def _batch(P, B, K, seed, local=False):
+    rng = np.random.default_rng(seed)
+    n, p = (4 * K, 4) if local else (16 * K, 16)
+    m = 3
+    g = rng.standard_normal((B, m, n, p))
+    q, r = np.linalg.qr(g)
+    x = q * np.sign(np.diagonal(r, axis1=-2, axis2=-1))[..., None, :]
+    z = rng.standard_normal(x.shape)
+    s = np.swapaxes(x, -1, -2) @ z
+    eta = z - x @ (0.5 * (s + np.swapaxes(s, -1, -2)))
+    return np.ascontiguousarray(x), np.ascontiguousarray(eta)
+
+
+@pytest.mark.parametrize("B", [3, 300, 700])
+def test_streamed_equals_synchronous_and_oracle(oracle, B):
+    """6 submissions over 3 rotating sets of pinned host arrays, never more than 3 in flight; every result is compared with the
+    synchronous otn_triple on the same inputs (bitwise) and instance 0 / B-1 of each with the oracle."""
+    import torch
+    from opentn_b200 import StiefelFit
+    P = oracle
+    K = 4
+    T = P.kitaev_fullsites_target()
+    spec = P.CostSpec(T, "full")
+    fit = StiefelFit(T, model="full", N=N, d=d, metric="canonical", max_batch=B)
+    nset, nsub = 3, 6
+    shape = (B, 3, 16 * K, 16)
+    xs = [_pinned(shape) for _ in range(nset)]
+    es = [_pinned(shape) for _ in range(nset)]
+    outs = [(_pinned((B,)), _pinned(shape), _pinned(shape)) for _ in range(nset)]
+    inputs = [_batch(P, B, K, 100 + i) for i in range(nsub)]
+    results = [None] * nsub
+    tickets = [None] * nsub
+
+    def harvest(i):
+        fit.triple_wait(tickets[i])
+        results[i] = tuple(o.numpy().copy() for o in outs[i % nset])
+
+    for i in range(nsub):
+        if i >= nset:
+            harvest(i - nset)               # frees host set i % nset
+        xs[i % nset].copy_(torch.from_numpy(inputs[i][0]))
+        es[i % nset].copy_(torch.from_numpy(inputs[i][1]))
+        for o in outs[i % nset]:
+            o.fill_(float("nan"))
+        tickets[i] = fit.triple_submit(xs[i % nset], es[i % nset], outs[i % nset])
+    for i in range(nsub - nset, nsub):
+        harvest(i)
+
+    for i in range(nsub):
+        f, g, h = fit.triple(inputs[i][0], inputs[i][1])          # synchronous host path
+        fs, gs, hs = results[i]
+        assert np.array_equal(fs, f) and np.array_equal(gs, g) and np.array_equal(hs, h), f"submission {i}"
+        for b in (0, B - 1):
+            fo, go, ho = P.triple(spec, list(inputs[i][0][b]), list(inputs[i][1][b]), "canonical")
+            assert abs(fs[b] - fo) / fo < 1e-12
+            assert rel(gs[b], np.array(go)) < 1e-10 and rel(hs[b], np.array(ho)) < 1e-10
+    fit.close()
+
+
+def test_other_calls_drain_outstanding_submissions(oracle):
+    """A synchronous call on the same fit while a submission is in flight waits for it (shared workspaces) and both results
+    are right; numpy (pageable) host arrays are accepted too; waiting twice for a ticket is an error."""
+    from opentn_b200 import OtnError, StiefelFit
+    P = oracle
+    K, B = 2, 600
+    T = P.kitaev_fullsites_target()
+    fit = StiefelFit(T, model="full", N=N, d=d, metric="euclidean", max_batch=B)
+    x, e = _batch(P, B, K, 7)
+    x2, _ = _batch(P, B, K, 8)
+    out = (np.full(B, np.nan), np.full(x.shape, np.nan), np.full(x.shape, np.nan))
+    t = fit.triple_submit(x, e, out)
+    f2 = fit.cost(x2)                        # drains the pipeline first
+    fit.triple_wait(t)
+    with pytest.raises(OtnError):
+        fit.triple_wait(t)
+    f, g, h = fit.triple(x, e)
+    assert np.array_equal(out[0], f) and np.array_equal(out[1], g) and np.array_equal(out[2], h)
+    assert np.array_equal(f2, fit.cost(x2))
+    with pytest.raises(ValueError):
+        import torch
+        fit.triple_submit(torch.from_numpy(x).cuda(), torch.from_numpy(e).cuda(), out)
+    fit.close()
+
+
+def test_streamed_two_site_model(oracle):
+    """2-site (factored) model through the streamed path."""
+    from opentn_b200 import StiefelFit
+    P = oracle
+    K, B = 4, 520
+    Lk = P.create_2local_liouvillians(P.get_kitaev_nn_linbladian(1.0), N, d, pbc=True)[0]
+    T = P.exp_operator_dt(Lk, 0.5)
+    fit = StiefelFit(T, model="local", N=N, d=d, metric="canonical", max_batch=B)
+    x, e = _batch(P, B, K, 21, local=True)
+    outs = [(np.empty(B), np.empty(x.shape), np.empty(x.shape)) for _ in range(2)]
+    t0 = fit.triple_submit(x, e, outs[0])
+    t1 = fit.triple_submit(x, e, outs[1])
+    fit.triple_wait()                        # all outstanding
+    f, g, h = fit.triple(x, e)
+    for o in outs:
+        assert np.array_equal(o[0], f) and np.array_equal(o[1], g) and np.array_equal(o[2], h)
+    spec = P.CostSpec(T, "local", N, d)
+    fo, go, ho = P.triple(spec, list(x[5]), list(e[5]), "canonical")
+    assert abs(f[5] - fo) / fo < 1e-12 and rel(g[5], np.array(go)) < 1e-10 and rel(h[5], np.array(ho)) < 1e-10
+    fit.close()
