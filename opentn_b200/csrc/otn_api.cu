@@ -1043,6 +1043,18 @@ int otn_dev_cost_grad(otn_problem* h, const double* x, int batch, const int* act
     h->tr.tiles = tiles;
     return 0;
 }
+// cost + gradient when the forward state (layers Y, products P, residual, cost partials) of the instances with stale[b] == 0 is
+// already in the work matrices (left there by otn_dev_cost at the same x): forward pass for the stale instances only, reverse
+// pass and Riemannian epilogue for all.  Chain (non-factored) evaluations only.
+int otn_dev_cost_grad_cached_forward(otn_problem* h, const double* x, int batch, const int* stale, double* f, double* rgrad) {
+    int tiles;
+    OTN_TRY(build_layers(h, x, nullptr, batch, stale, true));
+    OTN_TRY(forward_chain(h, batch, stale, false, &tiles));
+    OTN_TRY(reverse_chain(h, batch, nullptr, x));
+    OTN_TRY(riem_launch(h, batch, nullptr, tiles, x, nullptr, false, f, rgrad, nullptr, nullptr));
+    h->tr.tiles = tiles;
+    return 0;
+}
 int otn_dev_hvp(otn_problem* h, const double* x, const double* eta, int batch, const int* active, double* heta) {
     if (h->factored) {          // primal recomputed alongside the tangent (dual numbers); zraw is the cached primal pull-back
         OTN_TRY(build_layers(h, x, eta, batch, active, true));

@@ -16,6 +16,7 @@ struct TrState {
     double *g = nullptr, *r = nullptr, *z = nullptr, *d = nullptr, *Hd = nullptr, *xn = nullptr, *Hz = nullptr;   // [B][m][np]
     double *radius = nullptr, *fx = nullptr, *fn = nullptr, *rsq = nullptr, *stoptol = nullptr, *gz = nullptr, *zHz = nullptr;
     int *tcg_active = nullptr, *on_boundary = nullptr, *n_cg = nullptr, *status = nullptr, *accepted = nullptr, *n_active = nullptr;
+    int* rejected = nullptr;   // 1 - accepted: instances whose cached forward pass (of x_next) does not belong to their x
     double* rho = nullptr;
     int cap_batch = 0;
 };
@@ -244,6 +245,7 @@ struct TrUpdateParams {
     const double *fx, *fn, *gz, *zHz;
     const int* on_boundary;
     int *accepted, *status;
+    int* rejected;
     double rho_trust, maxradius;
     int batch;
     // history rows for this iteration (nullable)
@@ -260,7 +262,7 @@ __global__ void tr_update_kernel(const TrUpdateParams P) {
     else if (rho > 0.75 && P.on_boundary[b]) radius = fmin(2.0 * radius, P.maxradius);
     const int acc = rho > P.rho_trust ? 1 : 0;
     if (!(rho == rho)) atomicOr(&P.status[b], 1);
-    P.radius[b] = radius; P.rho[b] = rho; P.accepted[b] = acc;
+    P.radius[b] = radius; P.rho[b] = rho; P.accepted[b] = acc; P.rejected[b] = 1 - acc;
     if (P.h_rho) P.h_rho[b] = rho;
     if (P.h_radius) P.h_radius[b] = radius;
     if (P.h_ncg) P.h_ncg[b] = P.n_cg[b];

@@ -11,7 +11,7 @@ static int tr_alloc(otn_problem* h) {
     TrState& t = h->tr;
     if (t.cap_batch >= h->max_batch) return 0;
     const size_t B = (size_t)h->max_batch, V = B * h->m * h->np;
-    const size_t bytes = 7 * (V * 8 + 16) + 8 * (B * 8 + 16) + 6 * (B * 4 + 16) + 64;   // every slice is rounded up to 16 B
+    const size_t bytes = 7 * (V * 8 + 16) + 8 * (B * 8 + 16) + 7 * (B * 4 + 16) + 64;   // every slice is rounded up to 16 B
     OTN_TRY(h->tr_buf.ensure(bytes));
     char* base = h->tr_buf.as<char>();
     auto take = [&](size_t nbytes) { char* r = base; base += (nbytes + 15) / 16 * 16; return r; };
@@ -20,7 +20,7 @@ static int tr_alloc(otn_problem* h) {
     t.radius = (double*)take(B * 8); t.fx = (double*)take(B * 8); t.fn = (double*)take(B * 8); t.rsq = (double*)take(B * 8);
     t.stoptol = (double*)take(B * 8); t.gz = (double*)take(B * 8); t.zHz = (double*)take(B * 8); t.rho = (double*)take(B * 8);
     t.tcg_active = (int*)take(B * 4); t.on_boundary = (int*)take(B * 4); t.n_cg = (int*)take(B * 4); t.status = (int*)take(B * 4);
-    t.accepted = (int*)take(B * 4); t.n_active = (int*)take(16);
+    t.accepted = (int*)take(B * 4); t.rejected = (int*)take(B * 4); t.n_active = (int*)take(16);
     t.cap_batch = h->max_batch;
     return 0;
 }
@@ -122,7 +122,11 @@ extern "C" int otn_tr_run(otn_problem* h, double* x, int batch, const otn_tr_par
 
     for (int k = 0; k < prm.niter; ++k) {
         // grad = gradfunc(x) ; fx = f(x)  (same primal pass)                                       (:59, :63)
-        OTN_TRY(otn_dev_cost_grad(h, h->x, batch, nullptr, t.fx, t.g, nullptr));
+        // From the second iteration on, the layers, the forward chain and the residual of every ACCEPTED instance are still in
+        // the work matrices: f(x_next) of the previous iteration computed them, and x = x_next now.  Only rejected instances
+        // (x unchanged, forward state overwritten by the trial point) redo the forward pass.
+        if (k > 0 && !h->factored) OTN_TRY(otn_dev_cost_grad_cached_forward(h, h->x, batch, t.rejected, t.fx, t.g));
+        else OTN_TRY(otn_dev_cost_grad(h, h->x, batch, nullptr, t.fx, t.g, nullptr));
         if (rep && rep->f_iter) CUDA_TRY(cudaMemcpyAsync(hist_d(rep->f_iter, k), t.fx, (size_t)batch * 8, cudaMemcpyDefault, st));
         // eta, on_boundary = truncated_cg(grad, hess, radius)                                      (:61)
         OTN_TRY(tcg_dispatch(h, tp, batch, true));
@@ -178,7 +182,7 @@ extern "C" int otn_tr_run(otn_problem* h, double* x, int batch, const otn_tr_par
         OTN_TRY(otn_dev_cost(h, t.xn, batch, nullptr, t.fn));
         TrUpdateParams up{};
         up.radius = t.radius; up.rho = t.rho; up.fx = t.fx; up.fn = t.fn; up.gz = t.gz; up.zHz = t.zHz; up.on_boundary = t.on_boundary;
-        up.accepted = t.accepted; up.status = t.status; up.rho_trust = prm.rho_trust; up.maxradius = prm.maxradius; up.batch = batch;
+        up.accepted = t.accepted; up.rejected = t.rejected; up.status = t.status; up.rho_trust = prm.rho_trust; up.maxradius = prm.maxradius; up.batch = batch;
         up.h_rho = d_hrho; up.h_radius = d_hrad; up.h_ncg = d_hncg; up.h_onb = d_honb; up.h_acc = d_hacc; up.n_cg = t.n_cg;
         { ProfScope ps(&h->prof, st, CAT_TR, 0.0, 2); tr_update_kernel<<<(batch + 127) / 128, 128, 0, st>>>(up); }
         CUDA_TRY(cudaGetLastError());

@@ -80,6 +80,32 @@ def test_tr_batch_matches_oracle_fullsites(P, dense):
     fit.close()
 
 
+@pytest.mark.parametrize("dense", [False, True])
+def test_tr_rejected_steps_in_a_batch(P, dense):
+    """Oversized trust region: two of the three instances reject their second step, the third accepts every step.  From the
+    second iteration on the solver reuses the forward pass of f(x_next) for accepted instances and redoes it for rejected ones
+    (otn_dev_cost_grad_cached_forward); costs, decisions and iterates must follow the oracle through and after the rejection."""
+    from opentn_b200 import StiefelFit
+    T = P.kitaev_fullsites_target()
+    B, K, niter = 3, 2, 4
+    rng = np.random.default_rng(6)
+    xs = np.array([[P.random_stiefel(16 * K, 16, rng) for _ in range(3)] for _ in range(B)])
+    fit = StiefelFit(T, model="full", N=N, d=d, metric="canonical", max_batch=B, dense=dense)
+    x, rep = fit.tr_run(xs, niter=niter, radius_init=3.0, maxradius=6.0)
+    spec = P.CostSpec(T, "full")
+    acc = []
+    for b in range(B):
+        xs_it, f_it, radius, log_ = P.trust_region_fit(spec, list(xs[b]), "canonical", niter=niter, radius_init=3.0, maxradius=6.0)
+        np.testing.assert_allclose(rep["f_iter"][:, b], f_it, rtol=1e-10)
+        np.testing.assert_array_equal(rep["accepted"][:, b], [int(l["accepted"]) for l in log_])
+        np.testing.assert_allclose(rep["rho"][:, b], [l["rho"] for l in log_], rtol=1e-6)
+        np.testing.assert_allclose(x[b], np.array(xs_it[-1]), atol=1e-8)
+        acc.append([int(l["accepted"]) for l in log_])
+    acc = np.array(acc)
+    assert (acc == 0).any() and (acc[:, 1:] == 1).all(axis=1).any(), "the case must mix rejected and accepted steps"
+    fit.close()
+
+
 def test_host_loop_mirror(P, c1, goldens):
     """The reference-signature host loop (riemannian_trust_region_optimize with gradient_stiefel_vec /
     riemannian_hessian_vec / retract_stiefel closures) over the GPU callables."""
