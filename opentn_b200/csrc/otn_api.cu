@@ -118,21 +118,56 @@ static int set_smem(K kern, size_t bytes) {
 // ---------------------------------------------------------------------------------------------------------------------
 enum { CAT_GEMM = 0, CAT_ASSEMBLE = 1, CAT_BACK = 2, CAT_RIEM = 3, CAT_TR = 4, CAT_OTHER = 5, CAT_COUNT = 6 };
 static std::atomic<long long> g_launches{0};
-struct ProfRec { int cat; cudaEvent_t e0, e1; double flops; };
+struct ProfRec { int cat; cudaEvent_t e0, e1; double flops; int n; };
+// Side stream of the block-diagonal chain: the antisymmetric block of every chain product is launched on `st`, the symmetric one
+// on the handle's stream, so CTAs of one block fill the drain phase of the other (between two non-GEMM kernels the two chains are
+// independent).  fork = the side stream waits for everything enqueued on the main stream so far; join = the main stream waits for
+// the side stream.  Every non-GEMM launch site opens a ProfScope, which joins first: a non-GEMM kernel is a barrier for both chains.
+struct SideStream {
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool enabled = false;      // structured evaluation with two diagonal blocks
+    bool suspended = false;    // pipelined chunks (already overlapped on two compute streams), graph-captured tCG steps
+    bool busy = false;         // side work enqueued since the last join
+    // live profiling of a fork..join group: overlapping launches have no additive individual durations, so the group is timed
+    ProfRec grp{}; bool grp_live = false;
+    bool active() const { return enabled && !suspended && st != nullptr; }
+};
 struct Profiler {
     bool on = false;
     std::vector<ProfRec> recs;
     std::vector<cudaEvent_t> pool;
+    SideStream side;
     cudaEvent_t get() {
         if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
         cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    // called with the main stream before anything that is not a chain GEMM is enqueued on it
+    void join(cudaStream_t main) {
+        if (!side.busy) return;
+        cudaEventRecord(side.ev_join, side.st);
+        cudaStreamWaitEvent(main, side.ev_join, 0);
+        side.busy = false;
+        if (side.grp_live) { cudaEventRecord(side.grp.e1, main); recs.push_back(side.grp); side.grp_live = false; }
+    }
+    // called before a chain GEMM goes to the side stream
+    void fork(cudaStream_t main) {
+        if (side.busy) return;
+        if (on) { side.grp = ProfRec{CAT_GEMM, get(), get(), 0.0, 0}; cudaEventRecord(side.grp.e0, main); side.grp_live = true; }
+        cudaEventRecord(side.ev_fork, main);
+        cudaStreamWaitEvent(side.st, side.ev_fork, 0);
+        side.busy = true;
     }
 };
 struct ProfScope {
     Profiler* pr; cudaStream_t st; ProfRec rec; bool live;
     ProfScope(Profiler* p, cudaStream_t s, int cat, double flops, int nkernels = 1) : pr(p), st(s), live(p && p->on) {
         g_launches += nkernels;
-        if (live) { rec.cat = cat; rec.flops = flops; rec.e0 = pr->get(); rec.e1 = pr->get(); cudaEventRecord(rec.e0, st); }
+        if (p && cat != CAT_GEMM) p->join(s);
+        if (p && cat == CAT_GEMM && p->side.grp_live) {   // part of a timed fork..join group
+            p->side.grp.flops += flops; p->side.grp.n += nkernels; live = false;
+        }
+        if (live) { rec.cat = cat; rec.flops = flops; rec.n = nkernels; rec.e0 = pr->get(); rec.e1 = pr->get(); cudaEventRecord(rec.e0, st); }
     }
     ~ProfScope() { if (live) { cudaEventRecord(rec.e1, st); pr->recs.push_back(rec); } }
 };
@@ -225,7 +260,7 @@ struct otn_problem {
     Profiler prof;
     bool own_stream = true;
     // host-pointer pipeline (otn_triple): chunked H2D / compute / D2H overlap
-    cudaStream_t s_in = nullptr, s_out = nullptr, s_comp[2] = {nullptr, nullptr};
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_comp[2] = {nullptr, nullptr}, s_side[2] = {nullptr, nullptr};
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     long long pipe_seq = 0;      // chunks enqueued so far (staging slot = pipe_seq & 1; slot reuse is ordered across calls)
     // streamed submissions (otn_triple_submit / otn_triple_wait): ticket t completes when ev_ticket[t % 4] has fired
@@ -268,6 +303,8 @@ extern "C" void otn_destroy(otn_problem* h) {
     if (!h) return;
     DeviceGuard dev_guard__(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->prof.side.st) { cudaStreamSynchronize(h->prof.side.st); cudaStreamDestroy(h->prof.side.st); }
+    for (cudaEvent_t e : {h->prof.side.ev_fork, h->prof.side.ev_join}) if (e) cudaEventDestroy(e);
     for (void* ptr : {(void*)h->T_re, (void*)h->im2, (void*)h->tindex, (void*)h->tab, (void*)h->inv, (void*)h->symtab, (void*)h->t2f, (void*)h->Y, (void*)h->P,
                       (void*)h->G, (void*)h->W, (void*)h->Yd, (void*)h->Pd, (void*)h->Gd, (void*)h->Wd, (void*)h->Yl, (void*)h->Yld,
                       (void*)h->Wl, (void*)h->Wld, (void*)h->x, (void*)h->eta, (void*)h->zraw, (void*)h->zdraw, (void*)h->part_f,
@@ -285,6 +322,7 @@ extern "C" void otn_destroy(otn_problem* h) {
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
     for (int i = 0; i < 2; ++i) if (h->s_comp[i]) cudaStreamDestroy(h->s_comp[i]);
+    for (int i = 0; i < 2; ++i) if (h->s_side[i]) { cudaStreamSynchronize(h->s_side[i]); cudaStreamDestroy(h->s_side[i]); }
     h->pipe_buf.release();
     if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -372,6 +410,13 @@ extern "C" int otn_create_ex(otn_problem** out, int N, int d, int m, int K, int 
 #define CREATE_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { fail("%s failed: %s", #expr, cudaGetErrorString(e__)); return bail(-1); } } while (0)
     if (otn_set_metric(h, metric) != 0) return bail(-1);
     CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    if (h->nblk == 2 && getenv("OTN_NO_SIDE_STREAM") == nullptr) {     // env: A/B switch for measurements
+        SideStream& sd = h->prof.side;
+        CREATE_TRY(cudaStreamCreateWithFlags(&sd.st, cudaStreamNonBlocking));
+        CREATE_TRY(cudaEventCreateWithFlags(&sd.ev_fork, cudaEventDisableTiming));
+        CREATE_TRY(cudaEventCreateWithFlags(&sd.ev_join, cudaEventDisableTiming));
+        sd.enabled = true;
+    }
     const size_t B = (size_t)max_batch, SZ = (size_t)h->SZ, M = (size_t)m;
     // targets.  Every layer superoperator Y = sum_k E_k (x) E_k (and hence every chain product and tangent) is invariant under
     // the swap S: (a,b) <-> (b,a) applied to rows and columns, so only the swap-symmetric part Ts = (T + S T S)/2 of Re T
@@ -587,7 +632,7 @@ extern "C" int otn_profile_read(otn_problem* h, double* ms, long long* launches,
         float t = 0.f;
         CUDA_TRY(cudaEventElapsedTime(&t, r.e0, r.e1));
         if (ms) ms[r.cat] += t;
-        if (launches) launches[r.cat] += 1;
+        if (launches) launches[r.cat] += r.n;
         if (flops) flops[r.cat] += r.flops;
         h->prof.pool.push_back(r.e0); h->prof.pool.push_back(r.e1);
     }
@@ -609,8 +654,13 @@ static cudaError_t hgemm(otn_problem* h, const GemmParams& p0, bool ta, bool tb)
         if (p.A2) { p.A2 += o; p.B2 += o; }
         if (p.epi != EPI_NONE) { p.E += o; p.partial += h->blkTileOff[i]; p.partial_stride = h->tiles; }
         // executed flops: zero-padded k-steps beyond kvalid are skipped by the kernel
-        ProfScope ps(&h->prof, h->stream, CAT_GEMM, 2.0 * p.D * (double)p.rows * (p.kvalid > 0 ? p.kvalid : p.D) * p.batch * (p.A2 ? 2 : 1));
-        cudaError_t e = gemm_launch(p, ta, tb, h->stream);
+        cudaStream_t st = h->stream;
+        if (h->nblk == 2 && h->prof.side.active()) {
+            h->prof.fork(h->stream);                  // (first product after a join; no-op while the side stream is busy)
+            if (i == 1) st = h->prof.side.st;
+        }
+        ProfScope ps(&h->prof, st, CAT_GEMM, 2.0 * p.D * (double)p.rows * (p.kvalid > 0 ? p.kvalid : p.D) * p.batch * (p.A2 ? 2 : 1));
+        cudaError_t e = gemm_launch(p, ta, tb, st);
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
@@ -1187,6 +1237,7 @@ static int triple_pipelined(otn_problem* h, const double* x, const double* eta, 
         CUDA_TRY(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
         for (int i = 0; i < 2; ++i) {
             CUDA_TRY(cudaStreamCreateWithFlags(&h->s_comp[i], cudaStreamNonBlocking));
+            CUDA_TRY(cudaStreamCreateWithFlags(&h->s_side[i], cudaStreamNonBlocking));
             CUDA_TRY(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
@@ -1247,9 +1298,12 @@ static int triple_pipelined(otn_problem* h, const double* x, const double* eta, 
         h->pipe_prev_b0 = b0; h->pipe_prev_nb = nb;
         cudaStream_t user_stream = h->stream;
         h->stream = comp;
+        cudaStream_t user_side = h->prof.side.st;
+        if (h->prof.side.enabled) h->prof.side.st = h->s_side[slot];   // each compute stream forks to its own side stream
         shift_instance_views(h, b0);
         const int rc = triple_device(h, dx, de, nb, df, dg, dh);
         shift_instance_views(h, -(long long)b0);
+        h->prof.side.st = user_side;
         h->stream = user_stream;
         if (rc != 0) return rc;
         CUDA_TRY(cudaEventRecord(h->ev_done[slot], comp));

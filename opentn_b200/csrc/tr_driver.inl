@@ -118,6 +118,11 @@ extern "C" int otn_tr_run(otn_problem* h, double* x, int batch, const otn_tr_par
     // launch-bound regime (few small instances): sparser host checks and a CUDA graph for the tCG inner loop
     const bool small_batch = (long long)batch * h->D <= 16384;
     const bool use_graph = small_batch && !h->prof.on && getenv("OTN_NO_GRAPH") == nullptr;   // env: A/B switch for measurements
+    struct SideSuspend {       // the captured tCG step stays on one stream
+        SideStream& s; bool prev;
+        SideSuspend(SideStream& s_, bool on) : s(s_), prev(s_.suspended) { if (on) s.suspended = true; }
+        ~SideSuspend() { s.suspended = prev; }
+    } side_suspend(h->prof.side, use_graph);
     struct GraphHolder { cudaGraphExec_t exec = nullptr; bool failed = false; ~GraphHolder() { if (exec) cudaGraphExecDestroy(exec); } } cg_graph;
 
     for (int k = 0; k < prm.niter; ++k) {

@@ -120,3 +120,26 @@ def test_streamed_two_site_model(oracle):
     fo, go, ho = P.triple(spec, list(x[5]), list(e[5]), "canonical")
     assert abs(f[5] - fo) / fo < 1e-12 and rel(g[5], np.array(go)) < 1e-10 and rel(h[5], np.array(ho)) < 1e-10
     fit.close()
+
+
+def test_side_stream_is_bitwise_neutral(oracle, monkeypatch):
+    """The antisymmetric block of every chain product runs on a side stream (fork / join around the non-GEMM kernels).  Same
+    kernels, same data: U1 and a 3-iteration batched trust region must be bitwise identical with the side stream switched off."""
+    from opentn_b200 import StiefelFit
+    P = oracle
+    K, B = 4, 40
+    T = P.kitaev_fullsites_target()
+    x, e = _batch(P, B, K, 33)
+    res = []
+    for off in (False, True):
+        if off:
+            monkeypatch.setenv("OTN_NO_SIDE_STREAM", "1")
+        fit = StiefelFit(T, model="full", N=N, d=d, metric="canonical", max_batch=B, dense=False)
+        f, g, h = fit.triple(x, e)
+        xt, rep = fit.tr_run(x, niter=3)
+        res.append((f, g, h, xt, rep["f_iter"], rep["rho"]))
+        fit.close()
+    for a, b in zip(*res):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+    fo, go, ho = P.triple(P.CostSpec(T, "full"), list(x[7]), list(e[7]), "canonical")
+    assert abs(res[0][0][7] - fo) / fo < 1e-12 and rel(res[0][1][7], np.array(go)) < 1e-10 and rel(res[0][2][7], np.array(ho)) < 1e-10
