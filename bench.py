@@ -394,8 +394,10 @@ def run_gpu(args):
         return fit_, handle_
 
     def timed_device_steps(handle_, steps, min_warm_s):
-        """>= W warm-up steps (and >= min_warm_s under load), then `steps` timed steps of otn_triple on device-resident
-        inputs, every kernel launch bracketed by a CUDA-event pair on its stream (otn_profile_*)."""
+        """>= W warm-up steps (and >= min_warm_s under load), then two timed regions of `steps` steps of otn_triple on
+        device-resident inputs: (1) the plain one (`value`); (2) the same steps with every kernel launch bracketed by a CUDA-event
+        pair on its stream (otn_profile_*; the roofline numbers).  Per-launch timing needs launches that do not overlap, so in (2)
+        the library keeps the cotangent pull-backs on the main stream instead of its back stream: (2) is slightly slower."""
         def step():
             _lib.check(lib.otn_triple(handle_.h, x_dev.data_ptr(), e_dev.data_ptr(), BATCH, f_dev.data_ptr(), g_dev.data_ptr(), h_dev.data_ptr()))
         t_warm = time.perf_counter()
@@ -404,7 +406,6 @@ def run_gpu(args):
             step()
             n_warm_ += 1
         barrier()
-        lib.otn_profile_enable(handle_.h, 1)
         launches0 = lib.otn_launch_count()
         e0.record(stream)
         for _ in range(steps):
@@ -413,10 +414,20 @@ def run_gpu(args):
         barrier()
         ms_total_ = max_over_ranks(e0.elapsed_time(e1))
         launches_ = lib.otn_launch_count() - launches0
+        lib.otn_profile_enable(handle_.h, 1)
+        step()
+        barrier()
         pms_ = (C.c_double * 6)(); pln_ = (C.c_longlong * 6)(); pfl_ = (C.c_double * 6)()
+        _lib.check(lib.otn_profile_read(handle_.h, pms_, pln_, pfl_))     # discard the records of the untimed step
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        barrier()
+        ms_prof_ = max_over_ranks(e0.elapsed_time(e1))
         _lib.check(lib.otn_profile_read(handle_.h, pms_, pln_, pfl_))
         lib.otn_profile_enable(handle_.h, 0)
-        return ms_total_, launches_, list(pms_), list(pln_), list(pfl_), n_warm_
+        return ms_total_, launches_, list(pms_), list(pln_), list(pfl_), n_warm_, ms_prof_
 
     peak_tf = measure_fp64_peak(torch) if rank == 0 else None
 
@@ -425,7 +436,7 @@ def run_gpu(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()          # nvidia-smi samples every 100 ms; "under load" samples are selected by power draw
-    ms_total, launches, pms, pln, pfl, n_warm = timed_device_steps(handle, args.steps, args.min_warm_s)
+    ms_total, launches, pms, pln, pfl, n_warm, ms_prof = timed_device_steps(handle, args.steps, args.min_warm_s)
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms_total / args.steps
     value = world * BATCH * args.steps / (ms_total * 1e-3)
@@ -540,7 +551,7 @@ def run_gpu(args):
         return {"achieved": ach, "frac": (ach / peak_tf) if ach and peak_tf else None, "launches_timed": int(gemm_n),
                 "avg_launch_ms": gemm_ms / gemm_n if gemm_n else None,
                 "executed_flops_per_launch": gemm_fl / gemm_n if gemm_n else None,
-                "kernel_share_of_step": gemm_ms / ms_total_,
+                "profiled_ms_per_step": ms_total_ / steps_, "kernel_share_of_step": gemm_ms / ms_total_,
                 "other_kernels_ms_per_step": {"assembly": pms_[1] / steps_, "back_assembly": pms_[2] / steps_,
                                               "riemannian_epilogue": pms_[3] / steps_, "other": pms_[5] / steps_}}
 
@@ -558,7 +569,7 @@ def run_gpu(args):
                                 "full (profiles/ncu_struct_r01.txt: 340 MB + 144 MB); algorithmic 3*144^2*8*1024 = 5.10e8 B (the zero "
                                 "padding is partly never written); the 128-block launch: 372 MB vs 4.03e8 B",
                 "peak_source": peak_source, "peak_committed_r01": peak_file}
-    roofline.update(roofline_of(pms, pln, pfl, ms_total, args.steps))
+    roofline.update(roofline_of(pms, pln, pfl, ms_prof, args.steps))
     roofline["note"] = ("`achieved` counts EXECUTED flops of the block-diagonal evaluation (2*(144*144*136 + 128*128*120) per product: "
                         "output tiles are zero-padded to 144 / 128, the contraction stops at 136 / 120; 2*(136^3+120^3) useful). Dense-equivalent rate (SURVEY 8d algorithmic count, 2*256^3 per product) is "
                         "`step_tflops_dense_equivalent`; the dense formulation itself is measured in `dense_formulation`.")
@@ -566,12 +577,12 @@ def run_gpu(args):
 
     dense_leg = None
     if dense_raw is not None:
-        ms_d, launches_d, pms_d, pln_d, pfl_d, _, d_steps = dense_raw
+        ms_d, launches_d, pms_d, pln_d, pfl_d, _, ms_prof_d, d_steps = dense_raw
         rf = {"bound": "tensor", "kernel": "gemm_dmma_kernel<64,64,16,32,32,3> (FP64 DMMA.8x8x4), 2*256^3 per product",
               "peak": peak_tf, "unit": "TFLOP/s", "traffic": 1.59e9,
               "traffic_note": "dram read+write per launch of a single-product GEMM over 1024 instances from ncu --set full "
                               "(profiles/ncu_gemm_dense_r01.txt); algorithmic 3*D^2*8*1024 = 1.61e9 B"}
-        rf.update(roofline_of(pms_d, pln_d, pfl_d, ms_d, d_steps))
+        rf.update(roofline_of(pms_d, pln_d, pfl_d, ms_prof_d, d_steps))
         dense_leg = {"value": world * BATCH * d_steps / (ms_d * 1e-3), "unit": UNIT, "ms_per_step": ms_d / d_steps, "steps": d_steps,
                      "gpu_launches": int(launches_d), "roofline": rf,
                      "step_tflops_algorithmic": FLOPS_PER_TRIPLE * BATCH / (ms_d / d_steps * 1e-3) / 1e12}

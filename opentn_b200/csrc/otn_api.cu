@@ -161,9 +161,9 @@ struct Profiler {
 };
 struct ProfScope {
     Profiler* pr; cudaStream_t st; ProfRec rec; bool live;
-    ProfScope(Profiler* p, cudaStream_t s, int cat, double flops, int nkernels = 1) : pr(p), st(s), live(p && p->on) {
+    ProfScope(Profiler* p, cudaStream_t s, int cat, double flops, int nkernels = 1, bool nojoin = false) : pr(p), st(s), live(p && p->on) {
         g_launches += nkernels;
-        if (p && cat != CAT_GEMM) p->join(s);
+        if (p && cat != CAT_GEMM && !nojoin) p->join(s);
         if (p && cat == CAT_GEMM && p->side.grp_live) {   // part of a timed fork..join group
             p->side.grp.flops += flops; p->side.grp.n += nkernels; live = false;
         }
@@ -260,7 +260,14 @@ struct otn_problem {
     Profiler prof;
     bool own_stream = true;
     // host-pointer pipeline (otn_triple): chunked H2D / compute / D2H overlap
-    cudaStream_t s_in = nullptr, s_out = nullptr, s_comp[2] = {nullptr, nullptr}, s_side[2] = {nullptr, nullptr};
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_comp[2] = {nullptr, nullptr}, s_side[2] = {nullptr, nullptr}, s_backp[2] = {nullptr, nullptr};
+    // Back stream: the pull-backs of the layer cotangents to the isometries (back_layer) only feed the Riemannian epilogue, so they
+    // run on their own stream behind the GEMM that produced their input while the chain continues (back_begin / back_sync).
+    // Off while per-launch profiling is on (overlapping launches have no additive durations) and inside graph capture.
+    cudaStream_t s_back = nullptr, s_back_own = nullptr;
+    cudaEvent_t ev_bk_main = nullptr, ev_bk_side = nullptr, ev_bk_done = nullptr;
+    bool back_busy = false;
+    bool back_wd_pending = false;              // a pull-back reading the (single) Wd buffer is out on the back stream
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     long long pipe_seq = 0;      // chunks enqueued so far (staging slot = pipe_seq & 1; slot reuse is ordered across calls)
     // streamed submissions (otn_triple_submit / otn_triple_wait): ticket t completes when ev_ticket[t % 4] has fired
@@ -304,6 +311,9 @@ extern "C" void otn_destroy(otn_problem* h) {
     DeviceGuard dev_guard__(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->prof.side.st) { cudaStreamSynchronize(h->prof.side.st); cudaStreamDestroy(h->prof.side.st); }
+    if (h->s_back_own) { cudaStreamSynchronize(h->s_back_own); cudaStreamDestroy(h->s_back_own); }
+    for (int i = 0; i < 2; ++i) if (h->s_backp[i]) { cudaStreamSynchronize(h->s_backp[i]); cudaStreamDestroy(h->s_backp[i]); }
+    for (cudaEvent_t e : {h->ev_bk_main, h->ev_bk_side, h->ev_bk_done}) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : {h->prof.side.ev_fork, h->prof.side.ev_join}) if (e) cudaEventDestroy(e);
     for (void* ptr : {(void*)h->T_re, (void*)h->im2, (void*)h->tindex, (void*)h->tab, (void*)h->inv, (void*)h->symtab, (void*)h->t2f, (void*)h->Y, (void*)h->P,
                       (void*)h->G, (void*)h->W, (void*)h->Yd, (void*)h->Pd, (void*)h->Gd, (void*)h->Wd, (void*)h->Yl, (void*)h->Yld,
@@ -416,6 +426,13 @@ extern "C" int otn_create_ex(otn_problem** out, int N, int d, int m, int K, int 
         CREATE_TRY(cudaEventCreateWithFlags(&sd.ev_fork, cudaEventDisableTiming));
         CREATE_TRY(cudaEventCreateWithFlags(&sd.ev_join, cudaEventDisableTiming));
         sd.enabled = true;
+    }
+    if (getenv("OTN_NO_BACK_STREAM") == nullptr) {                      // env: A/B switch for measurements
+        CREATE_TRY(cudaStreamCreateWithFlags(&h->s_back_own, cudaStreamNonBlocking));
+        CREATE_TRY(cudaEventCreateWithFlags(&h->ev_bk_main, cudaEventDisableTiming));
+        CREATE_TRY(cudaEventCreateWithFlags(&h->ev_bk_side, cudaEventDisableTiming));
+        CREATE_TRY(cudaEventCreateWithFlags(&h->ev_bk_done, cudaEventDisableTiming));
+        h->s_back = h->s_back_own;
     }
     const size_t B = (size_t)max_batch, SZ = (size_t)h->SZ, M = (size_t)m;
     // targets.  Every layer superoperator Y = sum_k E_k (x) E_k (and hence every chain product and tangent) is invariant under
@@ -643,6 +660,29 @@ extern "C" int otn_profile_read(otn_problem* h, double* ms, long long* launches,
 // ---------------------------------------------------------------------------------------------------------------------
 // pipeline pieces (all enqueue on h->stream; x / eta are device pointers [batch][m][np])
 // ---------------------------------------------------------------------------------------------------------------------
+// back stream (see otn_problem::s_back)
+static bool back_overlap(const otn_problem* h) { return h->s_back != nullptr && !h->prof.on && !h->prof.side.suspended && !h->factored; }
+// the back stream waits for everything enqueued so far on the main stream and, if the antisymmetric chain is out on it, the side stream
+static cudaStream_t back_begin(otn_problem* h) {
+    cudaEventRecord(h->ev_bk_main, h->stream);
+    cudaStreamWaitEvent(h->s_back, h->ev_bk_main, 0);
+    if (h->prof.side.busy) {
+        cudaEventRecord(h->ev_bk_side, h->prof.side.st);
+        cudaStreamWaitEvent(h->s_back, h->ev_bk_side, 0);
+    }
+    h->back_busy = true;
+    return h->s_back;
+}
+// the main stream (and a busy side stream) wait for the pull-backs enqueued so far
+static void back_sync(otn_problem* h) {
+    if (!h->back_busy) return;
+    cudaEventRecord(h->ev_bk_done, h->s_back);
+    cudaStreamWaitEvent(h->stream, h->ev_bk_done, 0);
+    if (h->prof.side.busy) cudaStreamWaitEvent(h->prof.side.st, h->ev_bk_done, 0);
+    h->back_busy = false;
+    h->back_wd_pending = false;
+}
+
 // one chain product = one launch per diagonal block (1 block in the dense formulation, 2 in the structured one)
 static cudaError_t hgemm(otn_problem* h, const GemmParams& p0, bool ta, bool tb) {
     for (int i = 0; i < h->nblk; ++i) {
@@ -676,6 +716,7 @@ static inline double* layer_ptr(double* base, int l, long long SZ) { return base
 static int build_layers(otn_problem* h, const double* x, const double* eta, int batch, const int* active, bool primal) {
     const int items = batch * h->m;
     const bool tangent = eta != nullptr;
+    back_sync(h);
     ProfScope ps(&h->prof, h->stream, CAT_ASSEMBLE, 2.0 * h->K * (double)h->dim * h->dim * h->dim * h->dim * items * ((primal ? 1 : 0) + (tangent ? 2 : 0)),
                  h->model == OTN_MODEL_LOCAL ? 2 : 1);
     const size_t smem = (size_t)h->np * 8 * (tangent ? 2 : 1);
@@ -810,8 +851,11 @@ static int export_model(otn_problem* h, int batch, double* Mout) {
 static int back_layer(otn_problem* h, int batch, const int* active, int l, const double* x, bool tangent, const double* eta,
                       bool primal_with_eta = false) {
     // pulls the cotangent of layer l (W_l, and for the tangent pass Wd) back to the isometry
-    ProfScope ps(&h->prof, h->stream, CAT_BACK, 4.0 * h->K * (double)h->dim * h->dim * h->dim * h->dim * batch * (tangent ? 2 : 1),
-                 (h->model == OTN_MODEL_LOCAL ? 2 : 1) + ((tangent && h->dim >= 8) ? 1 : 0));
+    const bool ovl = back_overlap(h);
+    const cudaStream_t bst = ovl ? back_begin(h) : h->stream;
+    ProfScope ps(&h->prof, bst, CAT_BACK, 4.0 * h->K * (double)h->dim * h->dim * h->dim * h->dim * batch * (tangent ? 2 : 1),
+                 (h->model == OTN_MODEL_LOCAL ? 2 : 1) + ((tangent && h->dim >= 8) ? 1 : 0), ovl);
+    if (ovl && tangent) h->back_wd_pending = true;
     const long long SZ = h->SZ, S = (long long)h->m * SZ;
     const double* Wfull = (l == 0) ? h->G : layer_ptr(h->W, l, SZ);                  // W_0 = G_0
     const double* Wdfull = nullptr; long long sWd = 0;
@@ -827,13 +871,13 @@ static int back_layer(otn_problem* h, int batch, const int* active, int l, const
             const size_t sm2 = (size_t)(16 * 256 * (tangent ? 2 : 1) + 16 * 16 * 17) * 8;
             OTN_TRY(set_smem(back_embed2_sym_kernel<false>, sm2));
             OTN_TRY(set_smem(back_embed2_sym_kernel<true>, sm2));
-            if (!tangent) back_embed2_sym_kernel<false><<<batch, 256, sm2, h->stream>>>(Wfull, nullptr, S, 0, h->Yl, h->Yld, h->Wl, h->Wld, h->sym, h->symtab, h->t2f, active, h->m, l);
-            else back_embed2_sym_kernel<true><<<batch, 256, sm2, h->stream>>>(Wfull, Wdfull, S, sWd, h->Yl, h->Yld, h->Wl, h->Wld, h->sym, h->symtab, h->t2f, active, h->m, l);
+            if (!tangent) back_embed2_sym_kernel<false><<<batch, 256, sm2, bst>>>(Wfull, nullptr, S, 0, h->Yl, h->Yld, h->Wl, h->Wld, h->sym, h->symtab, h->t2f, active, h->m, l);
+            else back_embed2_sym_kernel<true><<<batch, 256, sm2, bst>>>(Wfull, Wdfull, S, sWd, h->Yl, h->Yld, h->Wl, h->Wld, h->sym, h->symtab, h->t2f, active, h->m, l);
         } else if (h->structured) {
-            if (!tangent) back_embed_sym_kernel<false><<<g, BEM_THREADS, sm, h->stream>>>(Wfull, nullptr, S, 0, h->Yl, h->Yld, h->Wl, h->Wld, h->tables(), h->sym, h->symtab, active, h->m, l);
-            else back_embed_sym_kernel<true><<<g, BEM_THREADS, sm, h->stream>>>(Wfull, Wdfull, S, sWd, h->Yl, h->Yld, h->Wl, h->Wld, h->tables(), h->sym, h->symtab, active, h->m, l);
-        } else if (!tangent) back_embed_kernel<false><<<g, BEM_THREADS, sm, h->stream>>>(Wfull, nullptr, S, 0, h->Yl, h->Yld, h->Wl, h->Wld, h->tables(), active, h->m, l);
-        else back_embed_kernel<true><<<g, BEM_THREADS, sm, h->stream>>>(Wfull, Wdfull, S, sWd, h->Yl, h->Yld, h->Wl, h->Wld, h->tables(), active, h->m, l);
+            if (!tangent) back_embed_sym_kernel<false><<<g, BEM_THREADS, sm, bst>>>(Wfull, nullptr, S, 0, h->Yl, h->Yld, h->Wl, h->Wld, h->tables(), h->sym, h->symtab, active, h->m, l);
+            else back_embed_sym_kernel<true><<<g, BEM_THREADS, sm, bst>>>(Wfull, Wdfull, S, sWd, h->Yl, h->Yld, h->Wl, h->Wld, h->tables(), h->sym, h->symtab, active, h->m, l);
+        } else if (!tangent) back_embed_kernel<false><<<g, BEM_THREADS, sm, bst>>>(Wfull, nullptr, S, 0, h->Yl, h->Yld, h->Wl, h->Wld, h->tables(), active, h->m, l);
+        else back_embed_kernel<true><<<g, BEM_THREADS, sm, bst>>>(Wfull, Wdfull, S, sWd, h->Yl, h->Yld, h->Wl, h->Wld, h->tables(), active, h->m, l);
         CUDA_TRY(cudaGetLastError());
         const long long ls = (long long)h->nf * q2;
         Wsup = h->Wl + (long long)l * ls; sW = (long long)h->m * ls;
@@ -849,14 +893,14 @@ static int back_layer(otn_problem* h, int batch, const int* active, int l, const
         OTN_TRY(set_smem(back_assemble_sym2_kernel<DIMV, ASV, 1, KPV>, sm1));                                                    \
         OTN_TRY(set_smem(back_assemble_sym2_kernel<DIMV, ASV, 2, KPV>, sm2));                                                    \
         if (!tangent && primal_with_eta) {      /* zraw = A(W) x  and  zdraw = A(W) eta  in one pass over W */                   \
-            back_assemble_sym2_kernel<DIMV, ASV, 2, KPV><<<batch * ASV, 256, sm2, h->stream>>>(Wsup, sW, x, eta, h->zraw, h->zdraw, 0, 0, h->sym, h->K, active, h->m, l); \
+            back_assemble_sym2_kernel<DIMV, ASV, 2, KPV><<<batch * ASV, 256, sm2, bst>>>(Wsup, sW, x, eta, h->zraw, h->zdraw, 0, 0, h->sym, h->K, active, h->m, l); \
         } else if (!tangent) {                                                                                                   \
-            back_assemble_sym2_kernel<DIMV, ASV, 1, KPV><<<batch * ASV, 256, sm1, h->stream>>>(Wsup, sW, x, nullptr, h->zraw, nullptr, 0, 0, h->sym, h->K, active, h->m, l); \
+            back_assemble_sym2_kernel<DIMV, ASV, 1, KPV><<<batch * ASV, 256, sm1, bst>>>(Wsup, sW, x, nullptr, h->zraw, nullptr, 0, 0, h->sym, h->K, active, h->m, l); \
         } else if (primal_with_eta) {           /* the W eta part is already in zdraw: only += A(Wd) x */                        \
-            back_assemble_sym2_kernel<DIMV, ASV, 1, KPV><<<batch * ASV, 256, sm1, h->stream>>>(Wdsup, sWds, x, nullptr, h->zdraw, nullptr, 1, 0, h->sym, h->K, active, h->m, l); \
+            back_assemble_sym2_kernel<DIMV, ASV, 1, KPV><<<batch * ASV, 256, sm1, bst>>>(Wdsup, sWds, x, nullptr, h->zdraw, nullptr, 1, 0, h->sym, h->K, active, h->m, l); \
         } else {                                                                                                                 \
-            back_assemble_sym2_kernel<DIMV, ASV, 1, KPV><<<batch * ASV, 256, sm1, h->stream>>>(Wdsup, sWds, x, nullptr, h->zdraw, nullptr, 0, 0, h->sym, h->K, active, h->m, l); \
-            back_assemble_sym2_kernel<DIMV, ASV, 1, KPV><<<batch * ASV, 256, sm1, h->stream>>>(Wsup, sW, eta, nullptr, h->zdraw, nullptr, 1, 0, h->sym, h->K, active, h->m, l); \
+            back_assemble_sym2_kernel<DIMV, ASV, 1, KPV><<<batch * ASV, 256, sm1, bst>>>(Wdsup, sWds, x, nullptr, h->zdraw, nullptr, 0, 0, h->sym, h->K, active, h->m, l); \
+            back_assemble_sym2_kernel<DIMV, ASV, 1, KPV><<<batch * ASV, 256, sm1, bst>>>(Wsup, sW, eta, nullptr, h->zdraw, nullptr, 1, 0, h->sym, h->K, active, h->m, l); \
         }                                                                                                                        \
     } while (0)
 #define BAS_SYM_K(DIMV, ASV)                                                                        \
@@ -875,10 +919,10 @@ static int back_layer(otn_problem* h, int batch, const int* active, int l, const
         const size_t sm = BasCfg<DIMV>::smem_bytes(h->K);                                                                       \
         OTN_TRY(set_smem(back_assemble_stream_kernel<DIMV>, sm));                                                               \
         if (!tangent) {                                                                                                         \
-            back_assemble_stream_kernel<DIMV><<<batch, 256, sm, h->stream>>>(Wsup, sW, x, h->zraw, h->K, 0, active, h->m, l);   \
+            back_assemble_stream_kernel<DIMV><<<batch, 256, sm, bst>>>(Wsup, sW, x, h->zraw, h->K, 0, active, h->m, l);   \
         } else {                                                                                                                \
-            back_assemble_stream_kernel<DIMV><<<batch, 256, sm, h->stream>>>(Wdsup, sWds, x, h->zdraw, h->K, 0, active, h->m, l); \
-            back_assemble_stream_kernel<DIMV><<<batch, 256, sm, h->stream>>>(Wsup, sW, eta, h->zdraw, h->K, 1, active, h->m, l);  \
+            back_assemble_stream_kernel<DIMV><<<batch, 256, sm, bst>>>(Wdsup, sWds, x, h->zdraw, h->K, 0, active, h->m, l); \
+            back_assemble_stream_kernel<DIMV><<<batch, 256, sm, bst>>>(Wsup, sW, eta, h->zdraw, h->K, 1, active, h->m, l);  \
         }                                                                                                                       \
     } while (0)
         if (dim == 16) BAS_STREAM(16); else BAS_STREAM(8);
@@ -888,11 +932,11 @@ static int back_layer(otn_problem* h, int batch, const int* active, int l, const
         if (!tangent) {
             const size_t sm = (wsz + h->np) * 8;
             OTN_TRY(set_smem(back_assemble_kernel<false>, sm));
-            back_assemble_kernel<false><<<grid, BAS_THREADS, sm, h->stream>>>(Wsup, nullptr, sW, 0, nslices, x, nullptr, h->zraw, nullptr, dim, h->K, active, h->m, l);
+            back_assemble_kernel<false><<<grid, BAS_THREADS, sm, bst>>>(Wsup, nullptr, sW, 0, nslices, x, nullptr, h->zraw, nullptr, dim, h->K, active, h->m, l);
         } else {
             const size_t sm = (2 * wsz + 2 * h->np) * 8;
             OTN_TRY(set_smem(back_assemble_kernel<true>, sm));
-            back_assemble_kernel<true><<<grid, BAS_THREADS, sm, h->stream>>>(Wsup, Wdsup, sW, sWds, nslices, x, eta, nullptr, h->zdraw, dim, h->K, active, h->m, l);
+            back_assemble_kernel<true><<<grid, BAS_THREADS, sm, bst>>>(Wsup, Wdsup, sW, sWds, nslices, x, eta, nullptr, h->zdraw, dim, h->K, active, h->m, l);
         }
     }
     CUDA_TRY(cudaGetLastError());
@@ -907,12 +951,14 @@ static int reverse_chain(otn_problem* h, int batch, const int* active, const dou
         p.B1 = (l == 1) ? h->Y : layer_ptr(h->P, l - 1, SZ); p.sB1 = S;
         p.C = layer_ptr(h->W, l, SZ); p.sC = S;
         CUDA_TRY(hgemm(h, p, false, true));
+        const bool ovl = back_overlap(h);      // W_l goes to the back stream at once; the chain carries on underneath
+        if (ovl) OTN_TRY(back_layer(h, batch, active, l, x, false, eta_joint, eta_joint != nullptr));
         GemmParams r = gp(h, batch, active);                       // G_{l-1} = Y_l^T G_l
         r.A1 = layer_ptr(h->Y, l, SZ); r.sA1 = S;
         r.B1 = layer_ptr(h->G, l, SZ); r.sB1 = S;
         r.C = layer_ptr(h->G, l - 1, SZ); r.sC = S;
         CUDA_TRY(hgemm(h, r, true, false));
-        OTN_TRY(back_layer(h, batch, active, l, x, false, eta_joint, eta_joint != nullptr));
+        if (!ovl) OTN_TRY(back_layer(h, batch, active, l, x, false, eta_joint, eta_joint != nullptr));
     }
     OTN_TRY(back_layer(h, batch, active, 0, x, false, eta_joint, eta_joint != nullptr));
     return 0;
@@ -954,13 +1000,16 @@ static int tangent_pass(otn_problem* h, int batch, const int* active, const doub
         p.A1 = Ghat; p.sA1 = 2 * SZ; p.B1 = Pprev; p.sB1 = S;
         p.A2 = layer_ptr(h->G, l, SZ); p.sA2 = S; p.B2 = Pdprev; p.sB2 = S;
         p.C = h->Wd; p.sC = SZ;
+        if (h->back_wd_pending) back_sync(h);  // Wd is one buffer: the pull-back of the previous layer's Wd must have read it
         CUDA_TRY(hgemm(h, p, false, true));
+        const bool ovl = back_overlap(h);
+        if (ovl) OTN_TRY(back_layer(h, batch, active, l, x, true, eta, joint));
         GemmParams r = gp(h, batch, active);                       // Ghat_{l-1} = Yd_l^T G_l + Y_l^T Ghat_l
         r.A1 = layer_ptr(h->Yd, l, SZ); r.sA1 = S; r.B1 = layer_ptr(h->G, l, SZ); r.sB1 = S;
         r.A2 = layer_ptr(h->Y, l, SZ); r.sA2 = S; r.B2 = Ghat; r.sB2 = 2 * SZ;
         r.C = h->Gd + (long long)(1 - cur) * SZ; r.sC = 2 * SZ;
         CUDA_TRY(hgemm(h, r, true, false));
-        OTN_TRY(back_layer(h, batch, active, l, x, true, eta, joint));
+        if (!ovl) OTN_TRY(back_layer(h, batch, active, l, x, true, eta, joint));
         cur = 1 - cur;
     }
     h->tr.gd_final = cur;
@@ -970,6 +1019,7 @@ static int tangent_pass(otn_problem* h, int batch, const int* active, const doub
 
 static int riem_launch(otn_problem* h, int batch, const int* active, int tiles, const double* x, const double* eta, bool hvp,
                        double* f, double* rgrad, double* egrad, double* heta) {
+    back_sync(h);                              // zraw / zdraw come from the back stream
     ProfScope ps(&h->prof, h->stream, CAT_RIEM, 0.0);
     RiemParams P{};
     P.x = x; P.zraw = h->zraw; P.eta = eta; P.zdraw = h->zdraw; P.part_f = h->part_f; P.part_s = h->part_s; P.im2 = h->im2;
@@ -1238,6 +1288,7 @@ static int triple_pipelined(otn_problem* h, const double* x, const double* eta, 
         for (int i = 0; i < 2; ++i) {
             CUDA_TRY(cudaStreamCreateWithFlags(&h->s_comp[i], cudaStreamNonBlocking));
             CUDA_TRY(cudaStreamCreateWithFlags(&h->s_side[i], cudaStreamNonBlocking));
+            CUDA_TRY(cudaStreamCreateWithFlags(&h->s_backp[i], cudaStreamNonBlocking));
             CUDA_TRY(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
@@ -1300,9 +1351,12 @@ static int triple_pipelined(otn_problem* h, const double* x, const double* eta, 
         h->stream = comp;
         cudaStream_t user_side = h->prof.side.st;
         if (h->prof.side.enabled) h->prof.side.st = h->s_side[slot];   // each compute stream forks to its own side stream
+        cudaStream_t user_back = h->s_back;
+        if (h->s_back) h->s_back = h->s_backp[slot];                   // ... and has its own back stream
         shift_instance_views(h, b0);
         const int rc = triple_device(h, dx, de, nb, df, dg, dh);
         shift_instance_views(h, -(long long)b0);
+        h->s_back = user_back;
         h->prof.side.st = user_side;
         h->stream = user_stream;
         if (rc != 0) return rc;

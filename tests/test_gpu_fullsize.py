@@ -174,6 +174,7 @@ def test_c3_euclidean_metric_full_batch(P, c3):
     edot = lambda a, b: np.einsum("blnp,blnp->b", a, b)
     # the Hessian is symmetric in the euclidean inner product
     et2 = stiefel.project(xs, np.random.default_rng(8).standard_normal(xs.shape))
+    fit.cost_grad(xs)                                  # primal cache for hvp_cached (the chunked host path of triple keeps none)
     h2 = fit.hvp_cached(et2)
     assert (np.abs(edot(et2, h) - edot(et, h2)) / np.sqrt(edot(h, h) * edot(et2, et2))).max() < 1e-10
     # the polar retraction is a second-order retraction for the embedded (euclidean) metric (stiefel.py:323-355), so

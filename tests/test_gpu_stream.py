@@ -143,3 +143,49 @@ def test_side_stream_is_bitwise_neutral(oracle, monkeypatch):
         assert np.array_equal(np.asarray(a), np.asarray(b))
     fo, go, ho = P.triple(P.CostSpec(T, "full"), list(x[7]), list(e[7]), "canonical")
     assert abs(res[0][0][7] - fo) / fo < 1e-12 and rel(res[0][1][7], np.array(go)) < 1e-10 and rel(res[0][2][7], np.array(ho)) < 1e-10
+
+
+@pytest.mark.parametrize("model,dense,m,K,B", [("full", False, 3, 16, 300), ("full", False, 5, 4, 64), ("full", True, 3, 4, 40),
+                                               ("local", False, 4, 4, 64), ("local", True, 3, 2, 8)])
+def test_back_stream_is_bitwise_neutral(oracle, monkeypatch, model, dense, m, K, B):
+    """The cotangent pull-backs (back_layer) run on a back stream behind the GEMM that produced their input while the chain
+    carries on (otn_problem::s_back).  Same kernels, same data, ordered by events: U1, cost+grad, cached HVPs and a batched
+    trust region must be bitwise identical with the back stream switched off, several times in a row (races show up as flicker)."""
+    import torch
+    from opentn_b200 import StiefelFit
+    P = oracle
+    if model == "full":
+        T = P.kitaev_fullsites_target()
+        n, p = 16 * K, 16
+    else:
+        T = P.exp_operator_dt(P.create_2local_liouvillians(P.get_kitaev_nn_linbladian(1.0), N, d, pbc=True)[0], 0.5)
+        n, p = 4 * K, 4
+    rng = np.random.default_rng(77)
+    x = np.array([[P.random_stiefel(n, p, rng) for _ in range(m)] for _ in range(B)])
+    e = np.array([[P.project(a, rng.standard_normal((n, p))) for a in xb] for xb in x])
+    res = []
+    for off in (False, True):
+        if off:
+            monkeypatch.setenv("OTN_NO_BACK_STREAM", "1")
+        fit = StiefelFit(T, model=model, N=N, d=d, metric="canonical", max_batch=B, dense=dense)
+        runs = []
+        for _ in range(1 if off else 4):
+            f, g, h = fit.triple(x, e)
+            f2, g2 = fit.cost_grad(x)
+            h2 = fit.hvp_cached(e)
+            # device-resident inputs: one otn_triple on the handle's own streams (host arrays go through the chunk pipeline)
+            fd, gd, hd = fit.triple(torch.from_numpy(x).cuda(), torch.from_numpy(e).cuda())
+            runs.append((f, g, h, f2, g2, h2, fd.cpu().numpy(), gd.cpu().numpy(), hd.cpu().numpy()))
+        np.testing.assert_allclose(runs[0][6], runs[0][0], rtol=1e-13)
+        np.testing.assert_allclose(runs[0][8], runs[0][2], rtol=0, atol=1e-13 * np.abs(runs[0][2]).max())
+        for r in runs[1:]:
+            for a, b in zip(runs[0], r):
+                assert np.array_equal(a, b)
+        xt, rep = fit.tr_run(x, niter=2)
+        res.append(runs[0] + (xt, rep["f_iter"], rep["rho"]))
+        fit.close()
+    for a, b in zip(*res):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+    spec = P.CostSpec(T, "full") if model == "full" else P.CostSpec(T, "local", N, d)
+    fo, go, ho = P.triple(spec, list(x[3]), list(e[3]), "canonical")
+    assert abs(res[0][0][3] - fo) / fo < 1e-12 and rel(res[0][1][3], np.array(go)) < 1e-10 and rel(res[0][2][3], np.array(ho)) < 1e-10
