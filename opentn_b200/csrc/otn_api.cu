@@ -1027,8 +1027,19 @@ static int riem_launch(otn_problem* h, int batch, const int* active, int tiles, 
     P.n = h->n; P.p = h->p; P.m = h->m; P.alpha0 = h->alpha0; P.alpha1 = h->alpha1; P.active = active;
     const size_t pp = (size_t)h->p * h->p;
     const size_t sm_mma = ((hvp ? 4 : 2) * (size_t)h->n * (h->p + 4) + 8 * h->p * (h->p + 4)) * 8;
+    // p = 16 (full-sites model at N = 4): streaming kernel, nothing n x p staged in shared memory (4 CTAs per SM, any Kraus rank)
+    const bool staged_only = getenv("OTN_RIEM_STAGED") != nullptr;             // env: A/B switch for measurements and tests
+    if (h->p == 16 && h->n % 8 == 0 && !staged_only) {
+        if (!hvp) {
+            OTN_TRY(set_smem(riem_stream_kernel<false>, RiemStreamCfg<false>::SMEM_BYTES));
+            riem_stream_kernel<false><<<batch * h->m, RS_THREADS, RiemStreamCfg<false>::SMEM_BYTES, h->stream>>>(P);
+        } else {
+            OTN_TRY(set_smem(riem_stream_kernel<true>, RiemStreamCfg<true>::SMEM_BYTES));
+            riem_stream_kernel<true><<<batch * h->m, RS_THREADS, RiemStreamCfg<true>::SMEM_BYTES, h->stream>>>(P);
+        }
+    }
     // large Kraus ranks (K > 20 at p = 16): the padded DMMA layout no longer fits 227 KB; the unpadded CUDA-core kernel does up to K = 24
-    if ((h->p == 16 || h->p == 8) && h->n % 8 == 0 && sm_mma <= 227 * 1024) {
+    else if ((h->p == 16 || h->p == 8) && h->n % 8 == 0 && sm_mma <= 227 * 1024) {
         const size_t ld = h->p + 4;
         const size_t sm = sm_mma;
 #define RIEM_MMA(PV)                                                                               \

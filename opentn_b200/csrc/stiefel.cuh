@@ -604,6 +604,226 @@ __global__ void __launch_bounds__(ST_THREADS) riem_mma_kernel(const RiemParams P
 
 
 // ==================================================================================================================
+// Streaming version of the Riemannian epilogue for p = 16 (full-sites model at N = 4).  riem_mma_kernel above stages x, eta,
+// zraw, zdraw of one isometry in shared memory (184 KB at K = 16: one CTA per SM, every phase latency-exposed, K <= 20).  Here
+// nothing n x p is staged.  Every output is a combination of the four inputs with p x p coefficient matrices,
+//     rgrad = zraw * (1/(f a0)) + x Gn
+//     H eta = zdraw * (1/(f a0)) + zraw Cz' + eta Ce + x Cx
+// (derivation pinned on the CPU by tests/test_riem_coefficient_form.py against the oracle's step-by-step form of
+// stiefel.py:398-409, :468-475, :23-30), and the coefficients only need the five Grams x^T x, x^T zraw, x^T zdraw, x^T eta,
+// eta^T zraw.  Stage 1: DMMA Grams with fragments loaded straight from global memory (a fragment row is 64 contiguous bytes),
+// rows dealt round-robin to 4 warp groups, the two column halves to 2; partial Grams meet in shared memory and are summed in a
+// fixed order.  Stage 2: the 16 x 16 algebra, one thread per entry.  Stage 3: the outputs, 8 rows per warp and step, inputs
+// re-read (L2 hits) as DMMA A fragments, coefficient matrices from shared memory.  53 KB of shared memory -> 4 CTAs per SM,
+// whose stages overlap; no limit on the Kraus rank.
+// ==================================================================================================================
+namespace otn {
+
+constexpr int RS_THREADS = 256;
+template <bool HVP>
+struct RiemStreamCfg {
+    static constexpr int P = 16, LD = 20, NQ = HVP ? 5 : 1, KS = 4;
+    static constexpr int GRAMS = NQ * P * LD;            // reduced Grams (padded rows)
+    static constexpr int PART = KS * NQ * P * P;         // partial Grams; the derived matrices reuse this space afterwards
+    static constexpr size_t SMEM_BYTES = (size_t)(GRAMS + PART) * sizeof(double);
+};
+
+template <bool HVP>
+__global__ void __launch_bounds__(RS_THREADS) riem_stream_kernel(const RiemParams Pm) {
+    using Cfg = RiemStreamCfg<HVP>;
+    constexpr int P = Cfg::P, LD = Cfg::LD, NQ = Cfg::NQ, GS = P * LD;
+    enum { QXZ = 0, QXX = 1, QXZD = 2, QXE = 3, QEZ = 4 };
+    extern __shared__ __align__(16) double sm[];
+    const int item = blockIdx.x, inst = item / Pm.m, layer = item - inst * Pm.m;
+    if (Pm.active != nullptr && Pm.active[inst] == 0) return;
+    const int n = Pm.n, np = n * P;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    double* Gm = sm;                       // [NQ][P][LD]
+    double* part = sm + Cfg::GRAMS;        // [KS][NQ][P][P]
+    __shared__ double sc[2];
+    if (tid == 0) {
+        double s = 0.0;
+        for (int tt = 0; tt < Pm.tiles; ++tt) s += Pm.part_f[(long long)inst * Pm.tiles + tt];
+        s += Pm.im2[Pm.tindex ? Pm.tindex[inst] : 0];
+        const double f = sqrt(s);
+        sc[0] = f;
+        if (HVP) {
+            double dsum = 0.0;
+            for (int tt = 0; tt < Pm.tiles; ++tt) dsum += Pm.part_s[(long long)inst * Pm.tiles + tt];
+            sc[1] = dsum;
+        }
+        if (layer == 0 && Pm.f_out != nullptr) Pm.f_out[inst] = f;
+    }
+    const long long base = (long long)item * np;
+    const double* __restrict__ xg = Pm.x + base;
+    const double* __restrict__ zg = Pm.zraw + base;
+    const double* __restrict__ eg = HVP ? Pm.eta + base : nullptr;
+    const double* __restrict__ zdg = HVP ? Pm.zdraw + base : nullptr;
+
+    // ---- stage 1: partial Grams -----------------------------------------------------------------------------------------
+    {
+        const int ks = warp & 3, jh = warp >> 2;
+        double acc[NQ][2][2];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) acc[q][i][0] = acc[q][i][1] = 0.0;
+        const int ksteps = n >> 2;
+#pragma unroll 4
+        for (int s = ks; s < ksteps; s += Cfg::KS) {
+            const int ro = (s * 4 + t) * P;
+            const double xa0 = xg[ro + g], xa1 = xg[ro + 8 + g];
+            const double zb = zg[ro + jh * 8 + g];
+            dmma884(acc[QXZ][0][0], acc[QXZ][0][1], xa0, zb);
+            dmma884(acc[QXZ][1][0], acc[QXZ][1][1], xa1, zb);
+            if (HVP) {
+                const double ea0 = eg[ro + g], ea1 = eg[ro + 8 + g];
+                const double zdb = zdg[ro + jh * 8 + g];
+                const double xb = jh ? xa1 : xa0, eb = jh ? ea1 : ea0;
+                dmma884(acc[QXX][0][0], acc[QXX][0][1], xa0, xb);
+                dmma884(acc[QXX][1][0], acc[QXX][1][1], xa1, xb);
+                dmma884(acc[QXZD][0][0], acc[QXZD][0][1], xa0, zdb);
+                dmma884(acc[QXZD][1][0], acc[QXZD][1][1], xa1, zdb);
+                dmma884(acc[QXE][0][0], acc[QXE][0][1], xa0, eb);
+                dmma884(acc[QXE][1][0], acc[QXE][1][1], xa1, eb);
+                dmma884(acc[QEZ][0][0], acc[QEZ][0][1], ea0, zb);
+                dmma884(acc[QEZ][1][0], acc[QEZ][1][1], ea1, zb);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                double* o = part + ((ks * NQ + q) * P + i * 8 + g) * P + jh * 8 + 2 * t;
+                o[0] = acc[q][i][0]; o[1] = acc[q][i][1];
+            }
+    }
+    __syncthreads();
+    for (int o = tid; o < NQ * P * P; o += RS_THREADS) {
+        const int q = o / (P * P), rc = o - q * P * P, r = rc / P, c = rc - r * P;
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < Cfg::KS; ++k) s += part[(k * NQ + q) * P * P + rc];
+        Gm[q * GS + r * LD + c] = s;
+    }
+    __syncthreads();
+
+    // ---- stage 2: coefficient matrices (thread = entry (i, j)); derived matrices live where the partials were ---------------
+    const double f = sc[0], inv_f = 1.0 / f;
+    const double a0 = Pm.alpha0, a1 = Pm.alpha1;
+    const double c1 = 0.5 * ((1.0 / a1) - (2.0 / a0)), c2 = 0.5 * (1.0 / a1), kap = (a0 - a1) / a0;
+    const int i = tid / P, j = tid - i * P, ij = i * LD + j, ji = j * LD + i;
+    double* XZ = Gm + QXZ * GS;
+    double* Gn = part;
+    double *Cx = nullptr, *Czp = nullptr, *Ce = nullptr;
+    double kappa = 0.0;
+    if (!HVP) {
+        XZ[ij] *= inv_f;
+        __syncthreads();
+        Gn[ij] = c1 * XZ[ij] - c2 * XZ[ji];
+    } else {
+        double *XX = Gm + QXX * GS, *XZd = Gm + QXZD * GS, *XE = Gm + QXE * GS, *EZ = Gm + QEZ * GS;
+        double *Gd = part + GS, *XN = part + 2 * GS, *EN = part + 3 * GS, *Cz = part + 4 * GS, *Cx0 = part + 6 * GS, *T0 = part + 7 * GS;
+        Ce = part + 5 * GS; Cx = Cx0; Czp = Cz;
+        kappa = sc[1] * inv_f * inv_f * inv_f;
+        {
+            const double xzr = XZ[ij];
+            XZ[ij] = inv_f * xzr;
+            XZd[ij] = inv_f * XZd[ij] - kappa * xzr;
+            EZ[ij] *= inv_f;
+        }
+        __syncthreads();
+        Gn[ij] = c1 * XZ[ij] - c2 * XZ[ji];
+        Gd[ij] = c1 * (EZ[ij] + XZd[ij]) - c2 * (XZd[ji] + EZ[ji]);
+        __syncthreads();
+        {   // XN = X^T nu = XZ/a0 + XX Gn ;  EN = eta^T nu = EZ/a0 + XE^T Gn
+            double sx = 0.0, se = 0.0;
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                const double gk = Gn[k * LD + j];
+                sx = fma(XX[i * LD + k], gk, sx);
+                se = fma(XE[k * LD + i], gk, se);
+            }
+            XN[ij] = XZ[ij] / a0 + sx;
+            EN[ij] = EZ[ij] / a0 + se;
+        }
+        __syncthreads();
+        {   // Gz = sym(EN) - kap (XE XN^T + XN XE^T);  Ce = Gn + kap XN^T;  Cz = (kap/a0) XE^T;  Cx0 = Gd + Gz + kap Gn XE^T
+            double s = 0.0, w = 0.0;
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                s += XE[i * LD + k] * XN[j * LD + k] + XN[i * LD + k] * XE[j * LD + k];
+                w = fma(Gn[i * LD + k], XE[j * LD + k], w);
+            }
+            const double gz = 0.5 * (EN[ij] + EN[ji]) - kap * s;
+            Ce[ij] = Gn[ij] + kap * XN[ji];
+            Cz[ij] = (kap / a0) * XE[ji];
+            Cx0[ij] = Gd[ij] + gz + kap * w;
+        }
+        __syncthreads();
+        {   // T0 = X^T z = XZd/a0 + XZ Cz + XE Ce + XX Cx0
+            double s = XZd[ij] / a0;
+#pragma unroll
+            for (int k = 0; k < P; ++k)
+                s += XZ[i * LD + k] * Cz[k * LD + j] + XE[i * LD + k] * Ce[k * LD + j] + XX[i * LD + k] * Cx0[k * LD + j];
+            T0[ij] = s;
+        }
+        __syncthreads();
+        {   // H eta = z - X sym(X^T z);  zraw enters as Z = zraw/f and through Zd = zdraw/f - kappa zraw
+            const double cx = Cx0[ij] - 0.5 * (T0[ij] + T0[ji]);
+            const double cz = inv_f * Cz[ij] - ((i == j) ? kappa / a0 : 0.0);
+            Cx[ij] = cx;
+            Czp[ij] = cz;
+        }
+    }
+    __syncthreads();
+
+    // ---- stage 3: outputs, 8 rows per warp and step ---------------------------------------------------------------------------
+    const double sz = inv_f / a0;
+    for (int rb = warp; rb < (n >> 3); rb += RS_THREADS / 32) {
+        const int row = rb * 8 + g;
+        double accN[2][2], accH[2][2];
+        double2 zr2[2];
+#pragma unroll
+        for (int jb = 0; jb < 2; ++jb) {
+            const int col = jb * 8 + 2 * t;
+            zr2[jb] = *reinterpret_cast<const double2*>(zg + row * P + col);
+            accN[jb][0] = sz * zr2[jb].x; accN[jb][1] = sz * zr2[jb].y;
+            if (HVP) {
+                const double2 zd2 = *reinterpret_cast<const double2*>(zdg + row * P + col);
+                accH[jb][0] = sz * zd2.x; accH[jb][1] = sz * zd2.y;
+            }
+        }
+#pragma unroll
+        for (int i0 = 0; i0 < P; i0 += 4) {
+            const double xr = xg[row * P + i0 + t];
+            double zra = 0.0, ea = 0.0;
+            if (HVP) { zra = zg[row * P + i0 + t]; ea = eg[row * P + i0 + t]; }
+#pragma unroll
+            for (int jb = 0; jb < 2; ++jb) {
+                const int bo = (i0 + t) * LD + jb * 8 + g;
+                dmma884(accN[jb][0], accN[jb][1], xr, Gn[bo]);
+                if (HVP) {
+                    dmma884(accH[jb][0], accH[jb][1], xr, Cx[bo]);
+                    dmma884(accH[jb][0], accH[jb][1], zra, Czp[bo]);
+                    dmma884(accH[jb][0], accH[jb][1], ea, Ce[bo]);
+                }
+            }
+        }
+#pragma unroll
+        for (int jb = 0; jb < 2; ++jb) {
+            const long long og = base + row * P + jb * 8 + 2 * t;
+            if (Pm.rgrad != nullptr) *reinterpret_cast<double2*>(Pm.rgrad + og) = make_double2(accN[jb][0], accN[jb][1]);
+            if (!HVP && Pm.egrad != nullptr) *reinterpret_cast<double2*>(Pm.egrad + og) = make_double2(inv_f * zr2[jb].x, inv_f * zr2[jb].y);
+            if (HVP) *reinterpret_cast<double2*>(Pm.heta + og) = make_double2(accH[jb][0], accH[jb][1]);
+        }
+    }
+}
+
+}  // namespace otn
+
+
+// ==================================================================================================================
 // DMMA-Gram versions of the canonical dot product and of the polar retraction for p in {8, 16} (padded rows, LD = p + 4)
 // ==================================================================================================================
 namespace otn {

@@ -29,20 +29,28 @@ def test_ragged_and_large_kraus_rank(oracle, K):
         fit.close()
 
 
-def test_kraus_rank_32_cost_only_and_clear_error(oracle):
-    """K = 32 (the assembly limit): cost and gradient work; the HVP epilogue (four n x p arrays resident in shared memory)
-    exceeds the 227 KB budget and must say so (no silent fallback)."""
+def test_kraus_rank_32(oracle, monkeypatch):
+    """K = 32 (the assembly limit): cost, gradient and -- with the streaming Riemannian epilogue, which stages nothing n x p in
+    shared memory -- the HVP work.  The staged epilogue (OTN_RIEM_STAGED=1: four n x p arrays resident in shared memory) exceeds
+    the 227 KB budget there and must say so (no silent fallback)."""
     from opentn_b200 import OtnError, StiefelFit
     P = oracle
     T = P.kitaev_fullsites_target()
     rng = np.random.default_rng(32)
     xs = np.array([[P.random_stiefel(16 * 32, 16, rng) for _ in range(2)]])
+    spec = P.CostSpec(T, "full")
     fit = StiefelFit(T, model="full", N=N, d=d)
     f = fit.cost(xs)
-    assert abs(f[0] - P.CostSpec(T, "full")(list(xs[0]))) / f[0] < 1e-12
+    assert abs(f[0] - spec(list(xs[0]))) / f[0] < 1e-12
     f2, g = fit.cost_grad(xs)
-    go = P.rgrad(P.CostSpec(T, "full"), list(xs[0]), "canonical")
+    go = P.rgrad(spec, list(xs[0]), "canonical")
     assert rel(g[0], np.array(go)) < 1e-10
+    f3, g3, h3 = fit.triple(xs, g)
+    fo, go, ho = P.triple(spec, list(xs[0]), list(g[0]), "canonical")
+    assert abs(f3[0] - fo) / fo < 1e-12 and rel(g3[0], np.array(go)) < 1e-10 and rel(h3[0], np.array(ho)) < 1e-10
+    fit.close()
+    monkeypatch.setenv("OTN_RIEM_STAGED", "1")
+    fit = StiefelFit(T, model="full", N=N, d=d)
     with pytest.raises(OtnError, match="Kraus rank <= 24"):
         fit.triple(xs, g)
     fit.close()

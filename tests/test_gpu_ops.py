@@ -237,3 +237,44 @@ def test_super2ortho_device_argument_checks():
         T.super2ortho_batch(np.eye(16)[None], 17)
     with pytest.raises(NotImplementedError):
         T.super2ortho_batch(np.eye(16)[None] * 1j, 2)
+
+
+@pytest.mark.parametrize("metric", ["canonical", "euclidean"])
+@pytest.mark.parametrize("m,K,B", [(3, 16, 20), (2, 5, 7), (3, 24, 3), (1, 1, 4)])
+def test_streaming_riemannian_epilogue_vs_staged_and_oracle(oracle, monkeypatch, metric, m, K, B):
+    """riem_stream_kernel (coefficient form, nothing staged in shared memory) against riem_mma_kernel (step-by-step form on staged
+    operands, OTN_RIEM_STAGED=1) and against the oracle; K = 24 is beyond what the staged DMMA kernel can hold."""
+    from opentn_b200 import StiefelFit
+    P = oracle
+    T = P.kitaev_fullsites_target()
+    rng = np.random.default_rng(100 + K)
+    n, p = 16 * K, 16
+    x = np.array([[P.random_stiefel(n, p, rng) for _ in range(m)] for _ in range(B)])
+    e = np.array([[P.project(a, rng.standard_normal((n, p))) for a in xb] for xb in x])
+    res = []
+    for staged in (False, True):
+        if staged:
+            monkeypatch.setenv("OTN_RIEM_STAGED", "1")
+        fit = StiefelFit(T, model="full", N=4, d=2, metric=metric, max_batch=B)
+        f, g, h = fit.triple(x, e)
+        f2, g2, e2 = fit.cost_grad(x, want_egrad=True)
+        np.testing.assert_allclose(f2, f, rtol=1e-14)
+        np.testing.assert_allclose(g2, g, rtol=0, atol=1e-13 * max(1.0, np.abs(g).max()))
+        res.append((f, g, h, e2))
+        fit.close()
+    scale = max(1.0, np.abs(res[1][2]).max())
+    assert np.array_equal(res[0][0], res[1][0])                      # f: same partial sums, same order
+    for a, b in zip(res[0][1:], res[1][1:]):
+        assert np.abs(a - b).max() <= 1e-12 * scale
+    spec = P.CostSpec(T, "full")
+    for b in range(min(B, 3)):
+        fo, go, ho = P.triple(spec, list(x[b]), list(e[b]), metric)
+        assert abs(res[0][0][b] - fo) / fo < 1e-12
+        assert np.abs(res[0][1][b] - np.array(go)).max() / np.abs(np.array(go)).max() < 1e-10
+        assert np.abs(res[0][2][b] - np.array(ho)).max() / np.abs(np.array(ho)).max() < 1e-10
+        assert np.abs(res[0][3][b] - np.array(P.egrad(spec, list(x[b])))).max() / np.abs(res[0][3][b]).max() < 1e-10
+    # tangency of the streamed outputs
+    xt = np.swapaxes(x, -1, -2)
+    for z in (res[0][1], res[0][2]):
+        s = xt @ z
+        assert np.abs(s + np.swapaxes(s, -1, -2)).max() <= 1e-12 * max(1.0, np.abs(z).max())
