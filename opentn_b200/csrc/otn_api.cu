@@ -853,8 +853,11 @@ static int back_layer(otn_problem* h, int batch, const int* active, int l, const
     // pulls the cotangent of layer l (W_l, and for the tangent pass Wd) back to the isometry
     const bool ovl = back_overlap(h);
     const cudaStream_t bst = ovl ? back_begin(h) : h->stream;
+    // kernels launched below: the back-embedding of the 2-site model, then one pull-back, or two when the tangent pass pulls Wd
+    // back against x and W against eta separately (dense streaming kernel; block kernel outside the joint x / eta pass)
+    const bool two_pullbacks = tangent && ((h->structured && h->model == OTN_MODEL_FULL) ? !primal_with_eta : (h->dim == 16 || h->dim == 8));
     ProfScope ps(&h->prof, bst, CAT_BACK, 4.0 * h->K * (double)h->dim * h->dim * h->dim * h->dim * batch * (tangent ? 2 : 1),
-                 (h->model == OTN_MODEL_LOCAL ? 2 : 1) + ((tangent && h->dim >= 8) ? 1 : 0), ovl);
+                 ((h->model == OTN_MODEL_LOCAL && !h->factored) ? 1 : 0) + (two_pullbacks ? 2 : 1), ovl);
     if (ovl && tangent) h->back_wd_pending = true;
     const long long SZ = h->SZ, S = (long long)h->m * SZ;
     const double* Wfull = (l == 0) ? h->G : layer_ptr(h->W, l, SZ);                  // W_0 = G_0

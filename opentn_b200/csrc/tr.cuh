@@ -240,6 +240,207 @@ __global__ void __launch_bounds__(ST_THREADS) tcg_step_kernel(const TcgParams P)
     }
 }
 
+// ---- streaming versions for p = 16 (full-sites model at N = 4) -----------------------------------------------------------
+// Same arithmetic as tcg_init_kernel / tcg_step_kernel; the Grams x^T v come from DMMA fragments loaded straight from global
+// memory (scheme of riem_stream_kernel: warp = (row group ks of 4, column half jh of 2), partial Grams summed in a fixed order),
+// so no n x p array is staged: 24 KB of shared memory instead of 164 KB, several CTAs per SM.  The B-fragment element of a warp
+// lane, (row 4 s + t, column 8 jh + g), visits every entry of an n x 16 array exactly once over the CTA: the Frobenius parts of the
+// inner products and the element-wise updates ride on those loads.
+template <int NQ>
+__device__ __forceinline__ void rs_store_partials(double* part, const double (&acc)[NQ][2][2], int ks, int jh, int g, int t) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            double* o = part + ((ks * NQ + q) * 16 + i * 8 + g) * 16 + jh * 8 + 2 * t;
+            o[0] = acc[q][i][0]; o[1] = acc[q][i][1];
+        }
+}
+template <int NQ>
+__device__ __forceinline__ double rs_gram_entry(const double* part, int q, int entry) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s += part[(k * NQ + q) * 256 + entry];
+    return s;
+}
+template <int NV>
+__device__ __forceinline__ void rs_block_sum(double (&v)[NV], double* red /* [NV][RS_THREADS / 32] */, double (&out)[NV]) {
+    constexpr int NW = RS_THREADS / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const double s = warp_sum(v[i]);
+        if (lane == 0) red[i * NW + warp] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double s = 0.0;
+        for (int w = 0; w < NW; ++w) s += red[i * NW + w];
+        out[i] = s;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(RS_THREADS) tcg_init_stream_kernel(const TcgParams P) {
+    __shared__ double part[4 * 256];
+    __shared__ double red[RS_THREADS / 32];
+    const int inst = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int ks = warp & 3, jh = warp >> 2, np = P.n * 16, ksteps = P.n >> 2;
+    double v[1] = {0.0};
+    for (int l = 0; l < P.m; ++l) {
+        const long long base = ((long long)inst * P.m + l) * np;
+        const double* __restrict__ xg = P.x + base;
+        double acc[1][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}};
+#pragma unroll 4
+        for (int s = ks; s < ksteps; s += 4) {
+            const int ro = (s * 4 + t) * 16;
+            const long long e = base + ro + jh * 8 + g;
+            const double xa0 = xg[ro + g], xa1 = xg[ro + 8 + g];
+            const double gv = P.g[e];
+            P.r[e] = gv; P.z[e] = 0.0; P.d[e] = -gv; P.Hz[e] = 0.0;
+            v[0] = fma(gv, gv, v[0]);
+            dmma884(acc[0][0][0], acc[0][0][1], xa0, gv);
+            dmma884(acc[0][1][0], acc[0][1][1], xa1, gv);
+        }
+        rs_store_partials<1>(part, acc, ks, jh, g, t);
+        __syncthreads();
+        { const double q = rs_gram_entry<1>(part, 0, tid); v[0] = fma(-0.5 * q, q, v[0]); }
+        __syncthreads();
+    }
+    double out[1];
+    rs_block_sum<1>(v, red, out);
+    if (tid == 0) {
+        P.rsq[inst] = out[0];
+        P.stoptol[inst] = fmax(P.abstol, P.reltol * sqrt(out[0]));
+        P.tcg_active[inst] = 1;
+        P.on_boundary[inst] = 0;
+        P.n_cg[inst] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS) tcg_step_stream_kernel(const TcgParams P) {
+    __shared__ double part[4 * 3 * 256];
+    __shared__ double red[4 * (RS_THREADS / 32)];
+    __shared__ double sc[4];
+    __shared__ int flag;
+    const int inst = blockIdx.x;
+    if (P.tcg_active[inst] == 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    if (tid == 0) atomicAdd(P.n_active + 1, 1);   // Hessian-vector products consumed (one per active instance and step)
+    const int ks = warp & 3, jh = warp >> 2, np = P.n * 16, ksteps = P.n >> 2;
+    // ---- pass A: dHd, dsq, zd, zz
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int l = 0; l < P.m; ++l) {
+        const long long base = ((long long)inst * P.m + l) * np;
+        const double* __restrict__ xg = P.x + base;
+        double acc[3][2][2];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { acc[q][0][0] = acc[q][0][1] = acc[q][1][0] = acc[q][1][1] = 0.0; }
+#pragma unroll 4
+        for (int s = ks; s < ksteps; s += 4) {
+            const int ro = (s * 4 + t) * 16;
+            const long long e = base + ro + jh * 8 + g;
+            const double xa0 = xg[ro + g], xa1 = xg[ro + 8 + g];
+            const double dv = P.d[e], hv = P.Hd[e], zv = P.z[e];
+            v[0] = fma(dv, hv, v[0]); v[1] = fma(dv, dv, v[1]); v[2] = fma(zv, dv, v[2]); v[3] = fma(zv, zv, v[3]);
+            dmma884(acc[0][0][0], acc[0][0][1], xa0, dv); dmma884(acc[0][1][0], acc[0][1][1], xa1, dv);
+            dmma884(acc[1][0][0], acc[1][0][1], xa0, hv); dmma884(acc[1][1][0], acc[1][1][1], xa1, hv);
+            dmma884(acc[2][0][0], acc[2][0][1], xa0, zv); dmma884(acc[2][1][0], acc[2][1][1], xa1, zv);
+        }
+        rs_store_partials<3>(part, acc, ks, jh, g, t);
+        __syncthreads();
+        {
+            const double ga = rs_gram_entry<3>(part, 0, tid), gb = rs_gram_entry<3>(part, 1, tid), gc = rs_gram_entry<3>(part, 2, tid);
+            v[0] = fma(-0.5 * ga, gb, v[0]); v[1] = fma(-0.5 * ga, ga, v[1]);
+            v[2] = fma(-0.5 * gc, ga, v[2]); v[3] = fma(-0.5 * gc, gc, v[3]);
+        }
+        __syncthreads();
+    }
+    double o4[4];
+    rs_block_sum<4>(v, red, o4);
+    if (tid == 0) {
+        const double dHd = o4[0], dsq = o4[1], zd = o4[2], zz = o4[3];
+        const double radius = P.radius[inst], rsq = P.rsq[inst];
+        double tt = 0.0;
+        int fl = 0;  // 0 = interior CG update, 1 = move to boundary and stop, 2 = failed
+        if (dsq != 0.0) {  // _move_to_boundary (:137-152); dsq == 0 leaves z unchanged
+            const double pq = zd / dsq, q = (zz - radius * radius) / dsq;
+            const double disc = pq * pq - q;
+            if (disc < 0.0) { fl = 2; atomicOr(&P.status[inst], 4); }      // solve_quadratic_equation raises (:159-160)
+            else if (pq == 0.0) tt = sqrt(-q);
+            else {
+                const double x1 = -(pq + (pq > 0.0 ? 1.0 : -1.0) * sqrt(disc));
+                const double x2 = q / x1;
+                tt = fmax(x1, x2);
+            }
+        }
+        const double alpha = rsq / dHd;
+        if (fl == 0 && (dHd <= 0.0 || alpha > tt)) fl = 1;
+        if (fl == 0 && !(alpha == alpha)) { fl = 2; atomicOr(&P.status[inst], 1); }
+        sc[0] = tt; sc[1] = alpha;
+        flag = fl;
+        P.n_cg[inst] += 1;
+    }
+    __syncthreads();
+    const int fl = flag;
+    if (fl == 2) { if (tid == 0) P.tcg_active[inst] = 0; return; }
+    const long long ibase = (long long)inst * P.m * np;
+    const int tot = P.m * np;
+    if (fl == 1) {  // z += t d ; on_boundary                                    (:120-122)
+        const double tt = sc[0];
+        for (int i = tid; i < tot; i += RS_THREADS) {
+            P.z[ibase + i] = fma(tt, P.d[ibase + i], P.z[ibase + i]);
+            P.Hz[ibase + i] = fma(tt, P.Hd[ibase + i], P.Hz[ibase + i]);
+        }
+        if (tid == 0) { P.tcg_active[inst] = 0; P.on_boundary[inst] = 1; }
+        return;
+    }
+    // ---- pass B: r += alpha Hd ; z += alpha d ; rsq_next                        (:124-126)
+    const double alpha = sc[1];
+    double w[1] = {0.0};
+    for (int l = 0; l < P.m; ++l) {
+        const long long base = ((long long)inst * P.m + l) * np;
+        const double* __restrict__ xg = P.x + base;
+        double acc[1][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}};
+#pragma unroll 4
+        for (int s = ks; s < ksteps; s += 4) {
+            const int ro = (s * 4 + t) * 16;
+            const long long e = base + ro + jh * 8 + g;
+            const double xa0 = xg[ro + g], xa1 = xg[ro + 8 + g];
+            const double hv = P.Hd[e];
+            const double rv = fma(alpha, hv, P.r[e]);
+            P.r[e] = rv;
+            P.Hz[e] = fma(alpha, hv, P.Hz[e]);
+            P.z[e] = fma(alpha, P.d[e], P.z[e]);
+            w[0] = fma(rv, rv, w[0]);
+            dmma884(acc[0][0][0], acc[0][0][1], xa0, rv);
+            dmma884(acc[0][1][0], acc[0][1][1], xa1, rv);
+        }
+        rs_store_partials<1>(part, acc, ks, jh, g, t);
+        __syncthreads();
+        { const double q = rs_gram_entry<1>(part, 0, tid); w[0] = fma(-0.5 * q, q, w[0]); }
+        __syncthreads();
+    }
+    double o1[1];
+    rs_block_sum<1>(w, red, o1);
+    if (tid == 0) {
+        const double rsq_next = o1[0];
+        int stop = 0;
+        if (sqrt(rsq_next) <= P.stoptol[inst]) stop = 1;                          // (:127-129)
+        if (P.n_cg[inst] >= P.maxiter) stop = 1;                                  // (:115, 133-134)
+        sc[2] = rsq_next / P.rsq[inst];                                           // beta (:130)
+        P.rsq[inst] = rsq_next;
+        flag = stop;
+        if (stop) P.tcg_active[inst] = 0; else atomicAdd(P.n_active, 1);
+    }
+    __syncthreads();
+    if (flag) return;
+    const double beta = sc[2];
+    for (int i = tid; i < tot; i += RS_THREADS) P.d[ibase + i] = fma(beta, P.d[ibase + i], -P.r[ibase + i]);   // d = -r + beta d (:131)
+}
+
 struct TrUpdateParams {
     double *radius, *rho;
     const double *fx, *fn, *gz, *zHz;

@@ -32,7 +32,9 @@ static bool tr_use_mma(const otn_problem* h) {
 
 static int cdot_launch(otn_problem* h, const double* x, const double* a, const double* b, int batch, double* out) {
     ProfScope ps(&h->prof, h->stream, CAT_TR, 0.0);
-    if (tr_use_mma(h)) {
+    if (h->p == 16 && h->n % 4 == 0 && getenv("OTN_RIEM_STAGED") == nullptr) {
+        cdot_stream_kernel<<<batch, RS_THREADS, 0, h->stream>>>(x, a, b, out, h->n, h->m, nullptr);
+    } else if (tr_use_mma(h)) {
         const size_t ld = h->p + 4, sm = (3 * (size_t)h->n * ld + 2 * h->p * ld) * 8;
         if (h->p == 16) { OTN_TRY(set_smem(cdot_mma_kernel<16>, sm)); cdot_mma_kernel<16><<<batch, ST_THREADS, sm, h->stream>>>(x, a, b, out, h->n, h->m, nullptr); }
         else { OTN_TRY(set_smem(cdot_mma_kernel<8>, sm)); cdot_mma_kernel<8><<<batch, ST_THREADS, sm, h->stream>>>(x, a, b, out, h->n, h->m, nullptr); }
@@ -72,6 +74,13 @@ static int tcg_launch(otn_problem* h, const TcgParams& tp, int batch, bool init)
     return 0;
 }
 static int tcg_dispatch(otn_problem* h, const TcgParams& tp, int batch, bool init) {
+    if (h->p == 16 && h->n % 4 == 0 && getenv("OTN_RIEM_STAGED") == nullptr) {      // streaming kernels (nothing n x p staged)
+        ProfScope ps(&h->prof, h->stream, CAT_TR, 0.0);
+        if (init) tcg_init_stream_kernel<<<batch, RS_THREADS, 0, h->stream>>>(tp);
+        else tcg_step_stream_kernel<<<batch, RS_THREADS, 0, h->stream>>>(tp);
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     if (tr_use_mma(h)) return h->p == 16 ? tcg_launch<16>(h, tp, batch, init) : tcg_launch<8>(h, tp, batch, init);
     return tcg_launch<0>(h, tp, batch, init);
 }
