@@ -101,7 +101,11 @@ int otn_hvp_cached(otn_problem* p, const double* eta, int batch, double* heta);
  *                     valid and untouched until the ticket has been waited for.  At most 4 tickets are outstanding: a 5th
  *                     submit first waits for the oldest.  Replaces a loop of cost / gradient / `hess @ d` evaluations over
  *                     many parameter sets (the tau x rank x seed sweeps of the reference's notebooks), stiefel.py:411-544.
- * otn_triple_wait   : blocks until the outputs of `ticket` are in the caller's host arrays (ticket < 0: all of them).
+ *                     Device arrays (all of x, eta, f, rgrad, heta device resident): no copies; the submission is ordered behind
+ *                     the handle's stream and computes in place in the caller's arrays, without the host synchronisation that
+ *                     ends otn_triple, so consecutive submissions overlap across their boundary.  Outputs are valid after
+ *                     otn_triple_wait (they are not ordered into the handle's stream).
+ * otn_triple_wait   : blocks until the outputs of `ticket` are in the caller's arrays (ticket < 0: all of them).
  *                     Any other call on the handle waits for all outstanding submissions first. */
 int otn_triple_submit(otn_problem* p, const double* x, const double* eta, int batch, double* f, double* rgrad, double* heta,
                       long long* ticket);

@@ -1293,7 +1293,7 @@ static void shift_instance_views(otn_problem* h, long long db) {
 // events order its chunks behind those of earlier submissions, so the head H2D of this call overlaps the kernels of the previous
 // one and the tail D2H of the previous call overlaps the kernels of this one; *ticket identifies the completion event.
 static int triple_pipelined(otn_problem* h, const double* x, const double* eta, int batch, double* f, double* rgrad, double* heta,
-                            long long* ticket = nullptr) {
+                            long long* ticket = nullptr, bool dev = false) {
     const int C = 256;
     const size_t per = (size_t)h->m * h->np;
     if (!h->s_in) {
@@ -1312,8 +1312,12 @@ static int triple_pipelined(otn_problem* h, const double* x, const double* eta, 
     // staging: per slot  x | eta | rgrad | heta | f
     const int CMAX = 3 * C;
     const size_t slot_doubles = 4 * (size_t)CMAX * per + CMAX;
-    OTN_TRY(h->pipe_buf.ensure(2 * slot_doubles * 8));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    // dev: every array is device resident (otn_triple_submit with device pointers): no staging and no copies, the chunks read and
+    // write the caller's arrays in place; what remains is the schedule -- chunks alternating between the two compute streams on
+    // disjoint workspace slices, no host synchronisation between submissions -- so that the first kernels of one submission run
+    // under the last kernels of the previous one.  Ordered behind the handle's stream at submission time.
+    if (!dev) OTN_TRY(h->pipe_buf.ensure(2 * slot_doubles * 8));
+    if (!dev) CUDA_TRY(cudaStreamSynchronize(h->stream));
     // (copies are not the bottleneck: PCIe moves the 403 MB of a step in 4.2 ms, both directions overlapped)
     // chunk schedule: short first and last chunks (exposed head H2D / tail D2H), longer ones in between (kernel efficiency)
     std::vector<int> sizes;
@@ -1347,15 +1351,22 @@ static int triple_pipelined(otn_problem* h, const double* x, const double* eta, 
     int b0 = 0;
     for (int c = 0; c < nchunks; ++c, ++h->pipe_seq) {
         const int slot = (int)(h->pipe_seq & 1), nb = sizes[c];
-        double* base = h->pipe_buf.as<double>() + slot * slot_doubles;
+        double* base = dev ? nullptr : h->pipe_buf.as<double>() + slot * slot_doubles;
         double *dx = base, *de = dx + (size_t)CMAX * per, *dg = de + (size_t)CMAX * per, *dh = dg + (size_t)CMAX * per, *df = dh + (size_t)CMAX * per;
-        if (h->pipe_seq >= 2) CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_done[slot], 0));   // kernels of chunk c-2 finished reading dx/de
-        CUDA_TRY(cudaMemcpyAsync(dx, x + (size_t)b0 * per, nb * per * 8, cudaMemcpyHostToDevice, h->s_in));
-        CUDA_TRY(cudaMemcpyAsync(de, eta + (size_t)b0 * per, nb * per * 8, cudaMemcpyHostToDevice, h->s_in));
-        CUDA_TRY(cudaEventRecord(h->ev_in[slot], h->s_in));
         cudaStream_t comp = h->s_comp[slot];
-        CUDA_TRY(cudaStreamWaitEvent(comp, h->ev_in[slot], 0));
-        if (h->pipe_seq >= 2) CUDA_TRY(cudaStreamWaitEvent(comp, h->ev_out[slot], 0));       // D2H of chunk c-2 drained dg/dh/df
+        if (dev) {
+            dx = const_cast<double*>(x) + (size_t)b0 * per; de = const_cast<double*>(eta) + (size_t)b0 * per;
+            dg = rgrad + (size_t)b0 * per; dh = heta + (size_t)b0 * per; df = f + b0;
+            CUDA_TRY(cudaEventRecord(h->ev_in[slot], h->stream));                            // inputs are ready in the handle's stream order
+            CUDA_TRY(cudaStreamWaitEvent(comp, h->ev_in[slot], 0));
+        } else {
+            if (h->pipe_seq >= 2) CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_done[slot], 0));   // kernels of chunk c-2 finished reading dx/de
+            CUDA_TRY(cudaMemcpyAsync(dx, x + (size_t)b0 * per, nb * per * 8, cudaMemcpyHostToDevice, h->s_in));
+            CUDA_TRY(cudaMemcpyAsync(de, eta + (size_t)b0 * per, nb * per * 8, cudaMemcpyHostToDevice, h->s_in));
+            CUDA_TRY(cudaEventRecord(h->ev_in[slot], h->s_in));
+            CUDA_TRY(cudaStreamWaitEvent(comp, h->ev_in[slot], 0));
+            if (h->pipe_seq >= 2) CUDA_TRY(cudaStreamWaitEvent(comp, h->ev_out[slot], 0));   // D2H of chunk c-2 drained dg/dh/df
+        }
         // neighbouring chunks overlap on the two compute streams and must not share a workspace slice: always true inside one
         // call, across calls only if the first chunk of this call stays clear of the last chunk of the previous one
         if (h->pipe_seq >= 1 && b0 < h->pipe_prev_b0 + h->pipe_prev_nb && h->pipe_prev_b0 < b0 + nb)
@@ -1376,9 +1387,11 @@ static int triple_pipelined(otn_problem* h, const double* x, const double* eta, 
         if (rc != 0) return rc;
         CUDA_TRY(cudaEventRecord(h->ev_done[slot], comp));
         CUDA_TRY(cudaStreamWaitEvent(h->s_out, h->ev_done[slot], 0));
-        if (f) CUDA_TRY(cudaMemcpyAsync(f + b0, df, (size_t)nb * 8, cudaMemcpyDeviceToHost, h->s_out));
-        if (rgrad) CUDA_TRY(cudaMemcpyAsync(rgrad + (size_t)b0 * per, dg, nb * per * 8, cudaMemcpyDeviceToHost, h->s_out));
-        if (heta) CUDA_TRY(cudaMemcpyAsync(heta + (size_t)b0 * per, dh, nb * per * 8, cudaMemcpyDeviceToHost, h->s_out));
+        if (!dev) {
+            if (f) CUDA_TRY(cudaMemcpyAsync(f + b0, df, (size_t)nb * 8, cudaMemcpyDeviceToHost, h->s_out));
+            if (rgrad) CUDA_TRY(cudaMemcpyAsync(rgrad + (size_t)b0 * per, dg, nb * per * 8, cudaMemcpyDeviceToHost, h->s_out));
+            if (heta) CUDA_TRY(cudaMemcpyAsync(heta + (size_t)b0 * per, dh, nb * per * 8, cudaMemcpyDeviceToHost, h->s_out));
+        }
         CUDA_TRY(cudaEventRecord(h->ev_out[slot], h->s_out));
         b0 += nb;
     }
@@ -1425,12 +1438,18 @@ extern "C" int otn_triple_submit(otn_problem* h, const double* x, const double* 
     OTN_TRY(check_batch(h, batch, /*drain=*/false));
     DeviceGuard dev_guard__(h->device);
     if (!x || !eta || !ticket) return fail("null argument");
-    if (is_device_ptr(x) || is_device_ptr(eta) || (f && is_device_ptr(f)) || (rgrad && is_device_ptr(rgrad)) || (heta && is_device_ptr(heta)))
-        return fail("otn_triple_submit takes host arrays (device-resident data: otn_triple on the handle's stream)");
+    const bool dx = is_device_ptr(x);
+    if (dx) {
+        if (!f || !rgrad || !heta) return fail("otn_triple_submit with device arrays needs f, rgrad and heta");
+        if (!is_device_ptr(eta) || !is_device_ptr(f) || !is_device_ptr(rgrad) || !is_device_ptr(heta))
+            return fail("otn_triple_submit: the arrays of one submission must be all host or all device resident");
+    } else if (is_device_ptr(eta) || (f && is_device_ptr(f)) || (rgrad && is_device_ptr(rgrad)) || (heta && is_device_ptr(heta))) {
+        return fail("otn_triple_submit: the arrays of one submission must be all host or all device resident");
+    }
     // the completion event of ticket t - TICKETS is about to be re-recorded: that submission must have finished
     if (h->next_ticket >= otn_problem::TICKETS && h->ev_ticket[0] != nullptr)
         CUDA_TRY(cudaEventSynchronize(h->ev_ticket[h->next_ticket % otn_problem::TICKETS]));
-    return triple_pipelined(h, x, eta, batch, f, rgrad, heta, ticket);
+    return triple_pipelined(h, x, eta, batch, f, rgrad, heta, ticket, dx);
 }
 
 extern "C" int otn_triple_wait(otn_problem* h, long long ticket) {

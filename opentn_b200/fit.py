@@ -246,13 +246,16 @@ class StiefelFit:
     def triple_submit(self, xs, etas, out):
         """Streamed form of `triple` for host arrays [B,m,n,p] (pinned torch tensors or numpy): enqueues the copies and kernels
         of this batch and returns a ticket at once; `out = (f, rgrad, heta)` are host arrays that `triple_wait(ticket)` fills.
-        Submitting the next batch before waiting overlaps its copies with this batch's kernels (otn_triple_submit)."""
+        Submitting the next batch before waiting overlaps its copies with this batch's kernels (otn_triple_submit).
+        With CUDA tensors throughout (inputs and outputs) nothing is copied: the submission only skips the host synchronisation
+        of `triple`, so consecutive batches overlap across their boundary; results are valid after `triple_wait`."""
         x, B, m, K, single, cuda = self._prep(xs)
         e, B2, m2, K2, _, cuda2 = self._prep(etas)
         if (B, m, K) != (B2, m2, K2):
             raise ValueError("xs and etas must have the same shape")
-        if cuda or cuda2 or any(getattr(o, "is_cuda", False) for o in out):
-            raise ValueError("triple_submit takes host arrays; device-resident data goes through triple()")
+        outs_cuda = [bool(getattr(o, "is_cuda", False)) for o in out]
+        if len({cuda, cuda2, *outs_cuda}) != 1:
+            raise ValueError("triple_submit: the arrays of one submission must be all host or all device resident")
         h = self._handle(m, K, B)
         self._bind(h, B)
         f, g, hv = out

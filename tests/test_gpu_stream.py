@@ -189,3 +189,39 @@ def test_back_stream_is_bitwise_neutral(oracle, monkeypatch, model, dense, m, K,
     spec = P.CostSpec(T, "full") if model == "full" else P.CostSpec(T, "local", N, d)
     fo, go, ho = P.triple(spec, list(x[3]), list(e[3]), "canonical")
     assert abs(res[0][0][3] - fo) / fo < 1e-12 and rel(res[0][1][3], np.array(go)) < 1e-10 and rel(res[0][2][3], np.array(ho)) < 1e-10
+
+
+def test_streamed_device_arrays(oracle):
+    """otn_triple_submit with device-resident arrays: no copies, chunks on the two compute streams, several submissions in flight
+    on rotating output sets; bitwise equal to the blocking call, and mixed host / device arrays are refused."""
+    import torch
+    from opentn_b200 import StiefelFit
+    P = oracle
+    K, B = 4, 1024
+    T = P.kitaev_fullsites_target()
+    x, e = _batch(P, B, K, 91)
+    xd, ed = torch.from_numpy(x).cuda(), torch.from_numpy(e).cuda()
+    xr, er = torch.flip(xd, dims=[0]).contiguous(), torch.flip(ed, dims=[0]).contiguous()
+    fit = StiefelFit(T, model="full", N=N, d=d, metric="canonical", max_batch=B)
+    f, g, h = fit.triple(xd, ed)
+    outs = [tuple(torch.zeros_like(t) for t in (f, g, h)) for _ in range(2)]
+    torch.cuda.synchronize()                         # torch's stream is not the handle's: its kernels must have finished
+    tickets = []
+    for i in range(6):                               # 6 submissions, at most 2 in flight, inputs alternate between x and flipped x
+        if i >= 2:
+            fit.triple_wait(tickets[i - 2])
+            ref = (f, g, h) if i % 2 == 0 else tuple(torch.flip(t, dims=[0]) for t in (f, g, h))
+            for a, b in zip(outs[i % 2], ref):
+                assert torch.equal(a, b)
+            for a in outs[i % 2]:
+                a.zero_()
+            torch.cuda.synchronize()
+        tickets.append(fit.triple_submit(xd if i % 2 == 0 else xr, ed if i % 2 == 0 else er, outs[i % 2]))
+    fit.triple_wait()
+    assert torch.equal(outs[0][0], f) and torch.equal(outs[0][1], g) and torch.equal(outs[0][2], h)
+    assert torch.equal(torch.flip(outs[1][1], dims=[0]), g) and torch.equal(torch.flip(outs[1][2], dims=[0]), h)
+    fo, go, ho = P.triple(P.CostSpec(T, "full"), list(x[600]), list(e[600]), "canonical")
+    assert abs(float(f[600]) - fo) / fo < 1e-12 and rel(g[600].cpu().numpy(), np.array(go)) < 1e-10 and rel(h[600].cpu().numpy(), np.array(ho)) < 1e-10
+    with pytest.raises(ValueError, match="all host or all device"):
+        fit.triple_submit(xd, ed, (np.empty(B), np.empty(x.shape), np.empty(x.shape)))
+    fit.close()
