@@ -112,7 +112,6 @@ extern "C" int otn_expm_batch(const double* A_re, const double* A_im, int D, con
     auto mat = [&](int k) { CMat m; m.re = base + (size_t)k * count * sb; m.im = cplx ? m.re + n : nullptr; return m; };
     CMat X = mat(0), X2 = mat(1), X3 = mat(2), X4 = mat(3), B = mat(4), P = mat(5), Q = mat(6);
     ExpmCtx cx{D, n, cplx, count, sb, 0, mat(7).re};
-    const CMat none{nullptr, nullptr};
     double c[17];
     c[0] = 1.0;
     for (int k = 1; k <= 16; ++k) c[k] = c[k - 1] / k;

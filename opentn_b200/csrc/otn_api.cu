@@ -412,7 +412,7 @@ extern "C" int otn_create_ex(otn_problem** out, int N, int d, int m, int K, int 
     }
     if (h->factored) h->tiles = h->f_tiles;
     h->p = h->dim; h->n = h->dim * K; h->np = h->n * h->p;
-    if (h->p > ST_MAXP) { delete h; return fail("isometry with p = %d columns > %d not supported", h->dim, ST_MAXP); }
+    if (h->p > ST_MAXP) { const int pcols = h->p; delete h; return fail("isometry with p = %d columns > %d not supported", pcols, ST_MAXP); }
     if (model == OTN_MODEL_LOCAL && (h->nf > 4 || h->q > 255)) { delete h; return fail("local model supports N <= 8 and d <= 3"); }
     if ((long long)max_batch * m > 65535) { delete h; return fail("max_batch * m must be <= 65535 (split the batch)"); }
     *out = h;  // from here on failures go through otn_destroy by the caller? no: clean up ourselves
@@ -1043,7 +1043,6 @@ static int riem_launch(otn_problem* h, int batch, const int* active, int tiles, 
     }
     // large Kraus ranks (K > 20 at p = 16): the padded DMMA layout no longer fits 227 KB; the unpadded CUDA-core kernel does up to K = 24
     else if ((h->p == 16 || h->p == 8) && h->n % 8 == 0 && sm_mma <= 227 * 1024) {
-        const size_t ld = h->p + 4;
         const size_t sm = sm_mma;
 #define RIEM_MMA(PV)                                                                               \
     do {                                                                                           \
