@@ -35,6 +35,9 @@ enum { OTN_STATUS_OK = 0, OTN_STATUS_NAN = 1, OTN_STATUS_NOT_SPD = 2, OTN_STATUS
 
 const char* otn_last_error(void);
 int otn_version(void);
+/* hash (sha256, hex) of the CUDA / header sources this binary was compiled from; opentn_b200/build.py rebuilds when it differs from
+ * the sources on disk, so a shipped binary can always be tied to its source */
+const char* otn_build_id(void);
 
 /* ---- problem handle ------------------------------------------------------------------------------------------------
  * A handle owns: the targets exp(tau L) (n_targets of them, real parts [n_targets][D][D]; imaginary parts may be NULL
@@ -61,6 +64,9 @@ void otn_destroy(otn_problem* p);
 int otn_set_target_index(otn_problem* p, const int* index, int batch);
 /* metric of the Riemannian gradient / connection: (alpha0, alpha1) of stiefel.py:398-409; OTN_METRIC_* presets */
 int otn_set_metric(otn_problem* p, int metric);
+/* any (alpha0, alpha1) > 0 of the two-parameter family gradient_stiefel_general takes (stiefel.py:411-426); gradient, connection
+ * and Hessian-vector products follow it, the trust region's inner product stays the coefficient-vector dot of the reference */
+int otn_set_metric_general(otn_problem* p, double alpha0, double alpha1);
 /* n, p, D, m, per-instance workspace bytes */
 int otn_query(const otn_problem* p, int* n, int* pp, int* D, int* m, long long* workspace_bytes);
 /* the handle's cudaStream_t (as void*) so a host framework can order its own work after ours */
@@ -118,6 +124,12 @@ int otn_triple_wait(otn_problem* p, long long ticket);
  *                   (transformations.py:405-429) + convert_supertensored2liouvillianfull(shift_pbc) (:484-490)
  * otn_compose     : M[count][D][D] = Ys[count][m-1] @ ... @ Ys[count][0]   compose_superops_list (transformations.py:841-851) */
 int otn_ortho2super(const double* x, int count, int dim, int K, double* Y, int device);
+/* otn_kraus2superop : out[count][dim^2][dim^2] = sum_k E_k (x) conj(E_k) for explicit, possibly COMPLEX Kraus operators
+ *                   E[count][K][dim][dim] given as (re, im) planes (E_im == NULL: real; then out_im may be NULL)
+ *                   kraus2superop (transformations.py:170-180, `np.kron(kraus, kraus.conj())`) */
+int otn_kraus2superop(const double* E_re, const double* E_im, int count, int K, int dim, double* out_re, double* out_im, int device);
+/* frees the calling thread's grow-only staging buffers of the stateless entry points on `device` (< 0: every device) */
+int otn_release_scratch(int device);
 int otn_embed_local(const double* Yloc, int count, int N, int d, int shift_pbc, double* Yfull, int device);
 int otn_compose(const double* Ys, int count, int m, int D, double* M, int device);
 /* otn_gemm_rows : rows [row0, row0+rows) of  op(A1) op(B1) [+ op(A2) op(B2)]  (D x D, device pointers, asynchronous on `stream`).
@@ -211,6 +223,22 @@ typedef struct {
 void otn_tr_default_params(otn_tr_params* prm);
 /* x [batch][m][n][p] in/out: on return the iterate after the last step (x_iter[-1] of the reference) */
 int otn_tr_run(otn_problem* p, double* x, int batch, const otn_tr_params* prm, otn_tr_report* rep);
+
+/* ---- the one collective of the data-parallel path: final all-gather of costs and isometries -------------------------
+ * Instances are sharded over GPUs with no exchange during the fit; when every shard has finished (otn_tr_run, or any call that
+ * leaves the iterates in the handle), the costs f(x) at and the isometries x of ALL shards are gathered with one ncclAllGather
+ * (NCCL is bound at run time: dlopen of libnccl.so.2).  The reference has no counterpart (single process); this replaces the
+ * np.save / np.load round trips of its notebooks (experiments/trust_region_pauli_noise.ipynb cells 60-61) for a sharded sweep.
+ * otn_gather       : ONE process driving `nshards` GPUs, one handle per device, `batch` instances each; f_all [nshards*batch],
+ *                    x_all [nshards*batch][m][n][p] (host or device, nullable), shard-major.
+ * otn_comm_*       : ONE PROCESS PER GPU: rank 0 creates the 128-byte id (otn_comm_unique_id) and hands it to the other ranks by any
+ *                    means, every rank calls otn_comm_init, then otn_comm_gather with its own handle (same `batch` on every rank). */
+typedef struct otn_comm otn_comm;
+int otn_gather(otn_problem* const* shards, int nshards, int batch, double* f_all, double* x_all);
+int otn_comm_unique_id(unsigned char* id128);
+int otn_comm_init(otn_comm** out, int rank, int nranks, const unsigned char* id128, int device);
+int otn_comm_gather(otn_comm* c, otn_problem* p, int batch, double* f_all, double* x_all);
+void otn_comm_destroy(otn_comm* c);
 
 #ifdef __cplusplus
 }

@@ -35,6 +35,7 @@ class TrReport(C.Structure):
 SIGNATURES = {
     "otn_last_error": (C.c_char_p, []),
     "otn_version": (C.c_int, []),
+    "otn_build_id": (C.c_char_p, []),
     "otn_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                              _dp, _dp, C.c_int]),
     "otn_create_ex": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -42,6 +43,7 @@ SIGNATURES = {
     "otn_destroy": (None, [C.c_void_p]),
     "otn_set_target_index": (C.c_int, [C.c_void_p, _ip, C.c_int]),
     "otn_set_metric": (C.c_int, [C.c_void_p, C.c_int]),
+    "otn_set_metric_general": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "otn_query": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                             C.POINTER(C.c_longlong)]),
     "otn_stream": (C.c_void_p, [C.c_void_p]),
@@ -57,6 +59,8 @@ SIGNATURES = {
     "otn_triple_submit": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int, _dp, _dp, _dp, C.POINTER(C.c_longlong)]),
     "otn_triple_wait": (C.c_int, [C.c_void_p, C.c_longlong]),
     "otn_ortho2super": (C.c_int, [_dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int]),
+    "otn_kraus2superop": (C.c_int, [_dp, _dp, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int]),
+    "otn_release_scratch": (C.c_int, [C.c_int]),
     "otn_embed_local": (C.c_int, [_dp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int]),
     "otn_compose": (C.c_int, [_dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int]),
     "otn_gemm_rows": (C.c_int, [_dp, _dp, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
@@ -78,6 +82,11 @@ SIGNATURES = {
     "otn_frobenius": (C.c_int, [_dp, _dp, _dp, C.c_int, C.c_longlong, C.c_int, _dp, C.c_int]),
     "otn_tr_default_params": (None, [C.POINTER(TrParams)]),
     "otn_tr_run": (C.c_int, [C.c_void_p, _dp, C.c_int, C.POINTER(TrParams), C.POINTER(TrReport)]),
+    "otn_gather": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, _dp, _dp]),
+    "otn_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "otn_comm_init": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_char_p, C.c_int]),
+    "otn_comm_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _dp, _dp]),
+    "otn_comm_destroy": (None, [C.c_void_p]),
 }
 
 _lib = None

@@ -78,7 +78,8 @@ extern "C" int otn_expm_batch(const double* A_re, const double* A_im, int D, con
     const bool cplx = A_im != nullptr;
     const long long n = (long long)D * D;
     const size_t bytes = (size_t)n * 8;
-    static thread_local DevBuf in_re, in_im, ws, o_re, o_im;
+    Scratch& S = g_scratch[device];                 // per device: a buffer cached for one GPU must never be handed to another
+    DevBuf &in_re = S.a, &in_im = S.b, &ws = S.x1, &o_re = S.o, &o_im = S.x2;
     const void *are, *aim; void *ore, *oim;
     OTN_TRY(stage_in(A_re, bytes, in_re, 0, &are));
     OTN_TRY(stage_in(A_im, bytes, in_im, 0, &aim));

@@ -93,7 +93,8 @@ extern "C" int otn_liouvillian(const double* L_re, const double* L_im, int n_ops
     }
     OTN_TRY(use_device(device));
     DeviceGuard dev_guard__(device);
-    static thread_local DevBuf in_re, in_im, gram, o_re, o_im;
+    Scratch& S = g_scratch[device];                 // per device (see otn_expm_batch)
+    DevBuf &in_re = S.a, &in_im = S.b, &gram = S.c, &o_re = S.o, &o_im = S.x2;
     const size_t lbytes = (size_t)n_ops * q * q * 8, obytes = (size_t)dim * dim * dim * dim * 8;
     const void *lre, *lim; void *ore, *oim;
     OTN_TRY(stage_in(L_re, lbytes, in_re, 0, &lre));

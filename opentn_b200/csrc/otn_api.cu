@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only; a no-op unless a profiler (nsys / ncu --nvtx) is attached
+
 #include "assemble.cuh"
 #include "factored.cuh"
 #include "gemm_dmma.cuh"
@@ -159,9 +161,13 @@ struct Profiler {
         side.busy = true;
     }
 };
+// NVTX ranges: every launch site of the handle sits inside one of these, named by the stage of the path
+static const char* const kNvtxNames[CAT_COUNT] = {"otn:chain_gemm", "otn:kraus_assembly", "otn:back_assembly", "otn:riemannian_epilogue",
+                                                  "otn:trust_region", "otn:other"};
 struct ProfScope {
     Profiler* pr; cudaStream_t st; ProfRec rec; bool live;
     ProfScope(Profiler* p, cudaStream_t s, int cat, double flops, int nkernels = 1, bool nojoin = false) : pr(p), st(s), live(p && p->on) {
+        nvtxRangePushA(kNvtxNames[cat]);
         g_launches += nkernels;
         if (p && cat != CAT_GEMM && !nojoin) p->join(s);
         if (p && cat == CAT_GEMM && p->side.grp_live) {   // part of a timed fork..join group
@@ -169,7 +175,7 @@ struct ProfScope {
         }
         if (live) { rec.cat = cat; rec.flops = flops; rec.n = nkernels; rec.e0 = pr->get(); rec.e1 = pr->get(); cudaEventRecord(rec.e0, st); }
     }
-    ~ProfScope() { if (live) { cudaEventRecord(rec.e1, st); pr->recs.push_back(rec); } }
+    ~ProfScope() { if (live) { cudaEventRecord(rec.e1, st); pr->recs.push_back(rec); } nvtxRangePop(); }
 };
 extern "C" long long otn_launch_count(void) { return g_launches.load(); }
 
@@ -275,7 +281,8 @@ struct otn_problem {
     cudaEvent_t ev_ticket[TICKETS] = {nullptr, nullptr, nullptr, nullptr};
     long long next_ticket = 0;
     bool pipe_inflight = false;
-    int pipe_prev_b0 = 0, pipe_prev_nb = 0;   // workspace slice of the most recently enqueued chunk
+    std::vector<std::pair<int, int>> pipe_unsynced[2];   // [s]: workspace slices (first instance, count) enqueued on compute stream 1-s
+                                                         // since stream s last waited for it (triple_pipelined)
     DevBuf pipe_buf;
     DevBuf tr_buf;
     // factored evaluation of the 2-site model (factored.cuh)
@@ -296,6 +303,7 @@ static int drain_pipeline(otn_problem* h) {
     for (int i = 0; i < 2; ++i) CUDA_TRY(cudaStreamSynchronize(h->s_comp[i]));
     CUDA_TRY(cudaStreamSynchronize(h->s_out));
     h->pipe_inflight = false;
+    for (auto& v : h->pipe_unsynced) v.clear();
     return 0;
 }
 
@@ -596,6 +604,17 @@ extern "C" int otn_set_metric(otn_problem* h, int metric) {
     else if (metric == OTN_METRIC_CANONICAL) { h->alpha0 = 1.0; h->alpha1 = 0.5; }    // stiefel.py:458-459
     else return fail("%d is not a valid metric value", metric);
     h->metric = metric;
+    return 0;
+}
+
+// general two-parameter family of metrics g(D1, D2) = tr(D1^T (alpha0 (I - X X^T) + alpha1 X X^T) D2) (stiefel.py:398-426): every
+// kernel of the Riemannian epilogue carries (alpha0, alpha1), the presets above are two points of the family
+extern "C" int otn_set_metric_general(otn_problem* h, double alpha0, double alpha1) {
+    if (!h) return fail("null handle");
+    if (!(alpha0 > 0.0) || !(alpha1 > 0.0) || std::isinf(alpha0) || std::isinf(alpha1)) return fail("alpha0 and alpha1 must be positive and finite");
+    OTN_TRY(drain_pipeline(h));
+    h->alpha0 = alpha0; h->alpha1 = alpha1;
+    h->metric = (alpha0 == 1.0 && alpha1 == 1.0) ? OTN_METRIC_EUCLIDEAN : (alpha0 == 1.0 && alpha1 == 0.5) ? OTN_METRIC_CANONICAL : -1;
     return 0;
 }
 
@@ -1366,11 +1385,24 @@ static int triple_pipelined(otn_problem* h, const double* x, const double* eta, 
             CUDA_TRY(cudaStreamWaitEvent(comp, h->ev_in[slot], 0));
             if (h->pipe_seq >= 2) CUDA_TRY(cudaStreamWaitEvent(comp, h->ev_out[slot], 0));   // D2H of chunk c-2 drained dg/dh/df
         }
-        // neighbouring chunks overlap on the two compute streams and must not share a workspace slice: always true inside one
-        // call, across calls only if the first chunk of this call stays clear of the last chunk of the previous one
-        if (h->pipe_seq >= 1 && b0 < h->pipe_prev_b0 + h->pipe_prev_nb && h->pipe_prev_b0 < b0 + nb)
-            CUDA_TRY(cudaStreamWaitEvent(comp, h->ev_done[slot ^ 1], 0));
-        h->pipe_prev_b0 = b0; h->pipe_prev_nb = nb;
+        // Chunks on the two compute streams overlap in time and must not share a workspace slice.  Inside one call the slices
+        // are disjoint; across calls a chunk may meet the slice of an EARLIER chunk that ran on the other stream (any earlier
+        // chunk, not only the most recent one: an odd chunk count flips the slot parity between calls).  pipe_unsynced[s] holds
+        // the slices enqueued on the other stream since stream s last waited for it; a chunk that overlaps one of them waits for
+        // the other stream's newest chunk (stream order covers the older ones) and clears the list.
+        {
+            auto& mine = h->pipe_unsynced[slot];
+            bool clash = mine.size() > 16;                      // bound the list: an occasional extra wait is harmless
+            for (const auto& r : mine) if (b0 < r.first + r.second && r.first < b0 + nb) { clash = true; break; }
+            if (clash) {
+                CUDA_TRY(cudaStreamWaitEvent(comp, h->ev_done[slot ^ 1], 0));
+                mine.clear();
+            }
+            auto& theirs = h->pipe_unsynced[slot ^ 1];
+            bool known = false;
+            for (const auto& r : theirs) if (r.first == b0 && r.second == nb) { known = true; break; }
+            if (!known) theirs.push_back({b0, nb});
+        }
         cudaStream_t user_stream = h->stream;
         h->stream = comp;
         cudaStream_t user_side = h->prof.side.st;
@@ -1406,6 +1438,7 @@ static int triple_pipelined(otn_problem* h, const double* x, const double* eta, 
     for (int i = 0; i < 2; ++i) CUDA_TRY(cudaStreamSynchronize(h->s_comp[i]));
     CUDA_TRY(cudaStreamSynchronize(h->s_out));
     h->pipe_inflight = false;
+    for (auto& v : h->pipe_unsynced) v.clear();
     return 0;
 }
 
@@ -1482,13 +1515,30 @@ extern "C" int otn_hvp_cached(otn_problem* h, const double* eta, int batch, doub
 // ---------------------------------------------------------------------------------------------------------------------
 // stateless representation / manifold entry points: per-thread scratch + the legacy default stream of `device`
 // ---------------------------------------------------------------------------------------------------------------------
-struct Scratch { DevBuf a, b, c, o, s; };
+struct Scratch {
+    DevBuf a, b, c, o, s, x1, x2;                   // inputs a/b/c, output o, small/int s, extras x1/x2 (work space, second output)
+    void release() { for (DevBuf* d : {&a, &b, &c, &o, &s, &x1, &x2}) d->release(); }
+};
 static thread_local Scratch g_scratch[16];
 
 static int use_device(int device) {
     int ndev = 0;
     CUDA_TRY(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev || device >= 16) return fail("device %d not available", device);
+    return 0;
+}
+
+// Frees the calling thread's staging / work buffers of the stateless entry points on `device` (they are grow-only: an N = 6
+// complex expm leaves ~2 GB behind); device < 0: all devices.
+extern "C" int otn_release_scratch(int device) {
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    for (int dv = 0; dv < ndev && dv < 16; ++dv) {
+        if (device >= 0 && dv != device) continue;
+        DeviceGuard dev_guard__(dv);
+        cudaDeviceSynchronize();
+        g_scratch[dv].release();
+    }
     return 0;
 }
 
@@ -1632,11 +1682,10 @@ extern "C" int otn_connection(const double* dnu, const double* nu, const double*
     Scratch& S = g_scratch[device];
     const size_t bytes = (size_t)count * n * p * 8;
     const void *dd, *nd, *ed, *xd; void* od;
-    static thread_local DevBuf extra;
     OTN_TRY(stage_in(dnu, bytes, S.a, 0, &dd));
     OTN_TRY(stage_in(nu, bytes, S.b, 0, &nd));
     OTN_TRY(stage_in(eta, bytes, S.c, 0, &ed));
-    OTN_TRY(stage_in(x, bytes, extra, 0, &xd));
+    OTN_TRY(stage_in(x, bytes, S.x1, 0, &xd));
     OTN_TRY(stage_out(out, bytes, S.o, &od));
     const size_t sm = (4 * (size_t)n * p + 5 * (size_t)p * p) * 8;
     OTN_TRY(set_smem(connection_kernel, sm));
@@ -1768,6 +1817,7 @@ extern "C" int otn_ipc_free(void* ptr, int device) {
 #include "expm.inl"
 #include "liouville.inl"
 #include "factory.inl"
+#include "extras.inl"
 
 // ---------------------------------------------------------------------------------------------------------------------
 // trust region

@@ -126,7 +126,10 @@ extern "C" int otn_tr_run(otn_problem* h, double* x, int batch, const otn_tr_par
 
     // launch-bound regime (few small instances): sparser host checks and a CUDA graph for the tCG inner loop
     const bool small_batch = (long long)batch * h->D <= 16384;
-    const bool use_graph = small_batch && !h->prof.on && getenv("OTN_NO_GRAPH") == nullptr;   // env: A/B switch for measurements
+    // (stream capture cannot begin on the legacy default stream -- which is what otn_set_stream(h, 0) selects, e.g. torch's default
+    // stream handle -- nor is it worth it on the per-thread default stream: plain launches there)
+    const bool capturable = st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
+    const bool use_graph = small_batch && capturable && !h->prof.on && getenv("OTN_NO_GRAPH") == nullptr;   // env: A/B switch for measurements
     struct SideSuspend {       // the captured tCG step stays on one stream
         SideStream& s; bool prev;
         SideSuspend(SideStream& s_, bool on) : s(s_), prev(s_.suspended) { if (on) s.suspended = true; }
@@ -164,7 +167,12 @@ extern "C" int otn_tr_run(otn_problem* h, double* x, int batch, const otn_tr_par
                 // every pointer of the step is owned by the handle, so the ~8 launches of one iteration are captured once (after
                 // a first plain execution has configured the kernels) and replayed for the rest of this call
                 cudaGraph_t graph = nullptr;
-                CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+                    cudaGetLastError();                       // a stream that cannot be captured: same fallback as a failed instantiate
+                    cg_graph.failed = true;
+                    OTN_TRY(cg_step());
+                    goto step_done;
+                }
                 const int rc = cg_step();
                 const cudaError_t ec = cudaStreamEndCapture(st, &graph);
                 if (rc == 0 && ec == cudaSuccess && cudaGraphInstantiate(&cg_graph.exec, graph, 0) == cudaSuccess) {
@@ -179,6 +187,7 @@ extern "C" int otn_tr_run(otn_problem* h, double* x, int batch, const otn_tr_par
             } else {
                 OTN_TRY(cg_step());
             }
+        step_done:
             if ((j + 1) % check == 0 || j + 1 == maxiter) {
                 CUDA_TRY(cudaMemcpyAsync(counters, t.n_active, 8, cudaMemcpyDeviceToHost, st));
                 CUDA_TRY(cudaStreamSynchronize(st));

@@ -21,10 +21,28 @@ from ._lib import MODEL_FULL, MODEL_LOCAL, METRIC_CANONICAL, METRIC_EUCLIDEAN, O
 _METRICS = {"euclidean": METRIC_EUCLIDEAN, "canonical": METRIC_CANONICAL}
 
 
-def metric_id(metric: str) -> int:
-    if metric not in _METRICS:
-        raise ValueError(f"{metric} is not a valid metric value")  # same message as stiefel.py:461
-    return _METRICS[metric]
+def metric_id(metric) -> int:
+    """Preset id of a metric name; -1 for a general (alpha0, alpha1) pair (`metric_alphas` validates it)."""
+    if isinstance(metric, str):
+        if metric not in _METRICS:
+            raise ValueError(f"{metric} is not a valid metric value")  # same message as stiefel.py:461
+        return _METRICS[metric]
+    metric_alphas(metric)
+    return -1
+
+
+def metric_alphas(metric):
+    """(alpha0, alpha1) of a metric: 'euclidean' = (1, 1), 'canonical' = (1, 1/2) (stiefel.py:456-459), or any positive pair
+    of the family `gradient_stiefel_general` takes (stiefel.py:411-426)."""
+    if isinstance(metric, str):
+        return (1.0, 1.0) if metric_id(metric) == METRIC_EUCLIDEAN else (1.0, 0.5)
+    try:
+        a0, a1 = (float(v) for v in metric)
+    except (TypeError, ValueError):
+        raise ValueError(f"{metric} is not a valid metric value") from None
+    if not (a0 > 0 and a1 > 0 and np.isfinite(a0) and np.isfinite(a1)):
+        raise ValueError("alpha0 and alpha1 must be positive and finite")
+    return a0, a1
 
 
 def _is_cuda_tensor(a) -> bool:
@@ -83,7 +101,7 @@ class StiefelFit:
             raise ValueError(f"target side {D} != d^(2N) = {d ** (2 * N)}")
         self.N, self.d, self.D = N, d, D
         self.model = model
-        self.metric = metric
+        self.metric = metric if isinstance(metric, str) else metric_alphas(metric)
         metric_id(metric)
         self.device = device
         # dense=True: force the dense D x D chain; False: force the block-diagonal evaluation; None: let the library choose
@@ -111,11 +129,15 @@ class StiefelFit:
             if h is not None:
                 h.close()
             cap = max(batch, self.max_batch)
-            h = _Handle(self.N, self.d, m, K, MODEL_LOCAL if self.model == "local" else MODEL_FULL, metric_id(self.metric),
+            mid = metric_id(self.metric)
+            h = _Handle(self.N, self.d, m, K, MODEL_LOCAL if self.model == "local" else MODEL_FULL, max(mid, 0),
                         cap, self._t_re, self._t_im, self.device,
                         _lib.FLAG_FACTORED if self.factored else
                         (0 if self.dense is None else (_lib.FLAG_DENSE if self.dense else _lib.FLAG_BLOCKS)))
+            if mid < 0:
+                check(h._lib.otn_set_metric_general(h.h, *metric_alphas(self.metric)))
             h.tindex_ver = 0
+            h.tindex_len = cap
             self._handles[key] = h
         return h
 
@@ -161,16 +183,34 @@ class StiefelFit:
         return x, B, m, n // p, single, cuda
 
     def _bind(self, h: _Handle, B):
-        if h.tindex_ver == self._tindex_ver:
+        """Make the handle's per-instance target ids those of `set_target_index` for the first B instances.  The length that
+        was bound is remembered on the handle: a later, larger batch re-validates instead of silently running instances
+        beyond it on stale ids."""
+        if self._tindex is not None and len(self._tindex) < B:
+            raise ValueError(f"target_index has {len(self._tindex)} entries but the batch has {B} instances")
+        if h.tindex_ver == self._tindex_ver and B <= h.tindex_len:
             return
-        if self._tindex is None:
-            idx = np.zeros(h.max_batch, dtype=np.int32)
-        else:
-            if len(self._tindex) < B:
-                raise ValueError("target_index shorter than the batch")
-            idx = self._tindex
-        check(h._lib.otn_set_target_index(h.h, ptr(idx), min(len(idx), h.max_batch)))
+        idx = np.zeros(h.max_batch, dtype=np.int32) if self._tindex is None else self._tindex
+        nbind = min(len(idx), h.max_batch)
+        check(h._lib.otn_set_target_index(h.h, ptr(idx), nbind))
         h.tindex_ver = self._tindex_ver
+        h.tindex_len = h.max_batch if self._tindex is None else nbind
+
+    @staticmethod
+    def _check_out(arr, shape, cuda, name):
+        """User-supplied output arrays go straight to the C ABI as raw addresses: refuse anything that is not a C-contiguous
+        float64 array of exactly the expected shape and residency."""
+        if _is_cuda_tensor(arr) != cuda:
+            raise ValueError(f"{name}: outputs must live where the inputs live ({'device' if cuda else 'host'})")
+        if tuple(arr.shape) != tuple(shape):
+            raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(arr.shape)}")
+        if cuda or hasattr(arr, "is_contiguous"):
+            import torch
+            if arr.dtype != torch.float64 or not arr.is_contiguous():
+                raise TypeError(f"{name}: need a contiguous float64 tensor")
+        else:
+            if not isinstance(arr, np.ndarray) or arr.dtype != np.float64 or not arr.flags.c_contiguous or not arr.flags.writeable:
+                raise TypeError(f"{name}: need a writeable C-contiguous float64 numpy array")
 
     @staticmethod
     def _empty_like(x, shape, cuda, dtype=np.float64):
@@ -180,11 +220,38 @@ class StiefelFit:
         return np.empty(shape, dtype=dtype)
 
     def set_metric(self, metric):
+        """`metric`: 'euclidean', 'canonical' or a pair (alpha0, alpha1) (stiefel.py:411-426)."""
+        a0, a1 = metric_alphas(metric)
         self._cached = None
-        self.metric = metric
-        mid = metric_id(metric)
+        self.metric = metric if isinstance(metric, str) else (a0, a1)
         for h in self._handles.values():
-            check(h._lib.otn_set_metric(h.h, mid))
+            check(h._lib.otn_set_metric_general(h.h, a0, a1))
+
+    def closures(self, metric=None):
+        """`(f, retract, gradfunc, hessfunc)` with the signatures `riemannian_trust_region_optimize` expects -- the four
+        lambdas a reference notebook builds around its cost closure (experiments/trust_region_pauli_noise.ipynb cell 21).
+        Each one is usable on its own and runs on the GPU; they also carry the fit they belong to, so that
+        `opentn_b200.trust_region_rcopt.riemannian_trust_region_optimize` recognises the quadruple and runs every
+        trust-region step on the device (`otn_tr_run`) instead of driving the four callables from the host."""
+        from . import stiefel as _S
+        metric = self.metric if metric is None else metric
+        metric_id(metric)
+
+        def f(xi):
+            return self(xi)
+
+        def retract(xi, eta):
+            return _S.retract_stiefel(xi, eta)
+
+        def gradfunc(xi):
+            return _S.gradient_stiefel_vec(xi, self, metric=metric)
+
+        def hessfunc(xi):
+            return _S.riemannian_hessian_vec(xi, self, metric=metric)
+
+        for fn in (f, retract, gradfunc, hessfunc):
+            fn._otn_fit = (self, metric)
+        return f, retract, gradfunc, hessfunc
 
     # ------------------------------------------------------------------ evaluations
     def __call__(self, xs):
@@ -237,6 +304,9 @@ class StiefelFit:
             hv = self._empty_like(x, tuple(x.shape), cuda)
         else:
             f, g, hv = out
+            self._check_out(f, (B,), cuda, "out[0] (f)")
+            self._check_out(g, tuple(x.shape), cuda, "out[1] (rgrad)")
+            self._check_out(hv, tuple(x.shape), cuda, "out[2] (heta)")
         check(h._lib.otn_triple(h.h, ptr(x), ptr(e), B, ptr(f), ptr(g), ptr(hv)))
         self._cached = (h, B, object())
         if single:
@@ -259,6 +329,9 @@ class StiefelFit:
         h = self._handle(m, K, B)
         self._bind(h, B)
         f, g, hv = out
+        self._check_out(f, (B,), cuda, "out[0] (f)")
+        self._check_out(g, tuple(x.shape), cuda, "out[1] (rgrad)")
+        self._check_out(hv, tuple(x.shape), cuda, "out[2] (heta)")
         ticket = C.c_longlong(-1)
         check(h._lib.otn_triple_submit(h.h, ptr(x), ptr(e), B, ptr(f), ptr(g), ptr(hv), C.byref(ticket)))
         self._cached = None

@@ -15,7 +15,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import as_f64, check, ptr
-from .fit import StiefelFit, metric_id
+from .fit import StiefelFit, metric_alphas, metric_id
 from . import transformations as _T
 
 
@@ -350,25 +350,18 @@ def _need_fit(func) -> StiefelFit:
     return func
 
 
-def _alphas_to_metric(alpha0, alpha1):
-    if (alpha0, alpha1) == (1, 1):
-        return "euclidean"
-    if (alpha0, alpha1) == (1, 0.5):
-        return "canonical"
-    raise NotImplementedError("only the euclidean (1,1) and canonical (1,1/2) metrics are wired into StiefelFit")
-
-
 def gradient_stiefel_general(xi, func, alpha0=1, alpha1=1):
-    """Riemannian gradient list, stiefel.py:411-426."""
+    """Riemannian gradient list for ANY metric (alpha0, alpha1) > 0 of the family, stiefel.py:411-426."""
     fit = _need_fit(func)
-    metric = _alphas_to_metric(alpha0, alpha1)
+    metric = (float(alpha0), float(alpha1))
     old = fit.metric
-    if old != metric:
+    same = metric_alphas(old) == metric
+    if not same:
         fit.set_metric(metric)
     try:
         _, g = fit.cost_grad(xi)
     finally:
-        if old != metric:
+        if not same:
             fit.set_metric(old)
     return list(g)
 
@@ -385,8 +378,7 @@ def gradient_canonical(xi, func):
 
 def gradient_stiefel_vec(xi, func, metric="euclidean"):
     """Coefficient vector of the Riemannian gradient, stiefel.py:453-466."""
-    metric_id(metric)
-    a0, a1 = (1, 1) if metric == "euclidean" else (1, 0.5)
+    a0, a1 = metric_alphas(metric)
     return _vector_from_tangents(xi, gradient_stiefel_general(xi, func, a0, a1))
 
 
@@ -408,9 +400,9 @@ class RiemannianHessianOperator:
         """(Re)build the device-side primal cache if another evaluation used the handle since ours."""
         fit = self.fit
         cached = fit._cached
-        if cached is not None and cached[2] is self._token and fit.metric == self.metric:
+        if cached is not None and cached[2] is self._token and metric_alphas(fit.metric) == metric_alphas(self.metric):
             return
-        if fit.metric != self.metric:
+        if metric_alphas(fit.metric) != metric_alphas(self.metric):
             fit.set_metric(self.metric)
         fit.cost_grad(self.x)
         self._token = fit._cached[2]
@@ -431,7 +423,7 @@ class RiemannianHessianOperator:
         go through one batched cost+grad+HVP evaluation at the replicated point."""
         xs = np.stack(self.x)
         out = np.empty((self.size, self.size))
-        if self.fit.metric != self.metric:
+        if metric_alphas(self.fit.metric) != metric_alphas(self.metric):
             self.fit.set_metric(self.metric)
         e = np.zeros(self.size)
         for c0 in range(0, self.size, chunk):

@@ -394,15 +394,22 @@ def ortho2super(x: np.ndarray) -> np.ndarray:
 
 
 def kraus2superop(kraus_list) -> np.ndarray:
-    """sum_k E_k (x) E_k^*, transformations.py:170-180 (real Kraus operators; returned complex like the reference)."""
+    """sum_k E_k (x) E_k^*, transformations.py:170-180 (`np.kron(kraus, kraus.conj())` summed over the list).  Real or complex
+    square Kraus operators; returned complex like the reference.  One fused kernel (`otn_kraus2superop`): the Kronecker
+    products are never formed one by one."""
     if not isinstance(kraus_list, list):
         kraus_list = [kraus_list]
-    E = np.stack([_real_input(k, "kraus2superop") for k in kraus_list])  # (K, rows, cols)
+    E = np.stack([np.asarray(k) for k in kraus_list])  # (K, rows, cols)
     K, rows, cols = E.shape
     if rows != cols:
         raise NotImplementedError("kraus2superop: only square Kraus operators on the accelerated path")
-    x = np.ascontiguousarray(E.transpose(1, 0, 2)).reshape(rows * K, cols)  # row a*K + k
-    return ortho2super(x).astype(complex)
+    cplx = np.iscomplexobj(E)
+    e_re = as_f64(E.real)[None]
+    e_im = as_f64(E.imag)[None] if cplx else None
+    o_re = np.empty((1, rows * rows, rows * rows))
+    o_im = np.empty_like(o_re) if cplx else None
+    check(_lib.load().otn_kraus2superop(ptr(e_re), ptr(e_im), 1, K, rows, ptr(o_re), ptr(o_im), _DEVICE))
+    return (o_re[0] + 1j * o_im[0]) if cplx else o_re[0].astype(complex)
 
 
 def compose_superops_list(superops) -> np.ndarray:

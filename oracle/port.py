@@ -615,6 +615,8 @@ def metric_alphas(metric):
         return 1.0, 1.0
     if metric == "canonical":
         return 1.0, 0.5
+    if isinstance(metric, (tuple, list)) and len(metric) == 2:   # general (alpha0, alpha1), gradient_stiefel_general :411-426
+        return float(metric[0]), float(metric[1])
     raise ValueError(f"{metric} is not a valid metric value")
 
 
