@@ -1,0 +1,229 @@
+"""GPU tests of the round-2 additions: general (alpha0, alpha1) metric, complex kraus2superop, the device fast path of the
+host trust-region loop, the NCCL gather of the C ABI, and regressions for the advisor's findings (cross-call workspace race of
+the streamed pipeline, graph capture on the default stream, stale target ids)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+N, d = 4, 2
+
+
+@pytest.fixture(scope="module")
+def P():
+    from oracle import port
+    return port
+
+
+def _rand_local(P, m, K, seed):
+    rng = np.random.default_rng(seed)
+    xs = [P.random_stiefel(4 * K, 4, rng) for _ in range(m)]
+    etas = [P.project(x, rng.standard_normal(x.shape)) for x in xs]
+    return xs, etas
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# general metric (stiefel.py:411-426: gradient_stiefel_general takes any alpha0, alpha1)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("alphas", [(2.0, 0.7), (0.5, 0.5), (1.0, 3.0)])
+@pytest.mark.parametrize("model", ["local", "full"])
+def test_general_metric(P, alphas, model):
+    from opentn_b200 import StiefelFit
+    from opentn_b200.stiefel import gradient_stiefel_general
+    rng = np.random.default_rng(3)
+    if model == "local":
+        xs, etas = _rand_local(P, 3, 3, 11)
+        T = P.model_stiefel_local(_rand_local(P, 3, 3, 12)[0], N, d) + 0.01 * rng.standard_normal((256, 256))
+        spec = P.CostSpec(T, "local", N, d)
+    else:
+        xs = [P.random_stiefel(32, 16, rng) for _ in range(2)]
+        etas = [P.project(x, rng.standard_normal(x.shape)) for x in xs]
+        T = P.kitaev_fullsites_target()
+        spec = P.CostSpec(T, "full")
+    fit = StiefelFit(T, model=model, N=N, d=d, metric=alphas)
+    f, g, h = fit.triple(np.array(xs), np.array(etas))
+    fo, go, ho = P.triple(spec, xs, etas, alphas)
+    assert abs(f - fo) / fo < 1e-12
+    go, ho = np.array(go), np.array(ho)
+    assert np.abs(g - go).max() / np.abs(go).max() < 1e-10
+    assert np.abs(h - ho).max() / np.abs(ho).max() < 1e-10
+    # the reference-named entry point: temporary metric switch on a canonical fit, restored afterwards
+    fit2 = StiefelFit(T, model=model, N=N, d=d, metric="canonical")
+    g2 = np.array(gradient_stiefel_general(xs, fit2, *alphas))
+    assert np.abs(g2 - go).max() / np.abs(go).max() < 1e-10
+    assert fit2.metric == "canonical"
+    # the presets are two points of the family
+    fit.set_metric((1, 0.5))
+    _, gc, hc = fit.triple(np.array(xs), np.array(etas))
+    _, gc2, hc2 = fit2.triple(np.array(xs), np.array(etas))
+    np.testing.assert_array_equal(gc, gc2)
+    np.testing.assert_array_equal(hc, hc2)
+    with pytest.raises(ValueError):
+        fit.set_metric((1.0, -1.0))
+    fit.close(); fit2.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# complex kraus2superop (transformations.py:170-180)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim,K", [(4, 3), (2, 1), (16, 5)])
+def test_kraus2superop_complex(P, goldens, dim, K):
+    from opentn_b200 import transformations as T
+    rng = np.random.default_rng(dim * 10 + K)
+    E = [rng.standard_normal((dim, dim)) + 1j * rng.standard_normal((dim, dim)) for _ in range(K)]
+    want = sum(np.kron(e, e.conj()) for e in E)                     # the reference's definition, line 179
+    got = T.kraus2superop(E)
+    assert got.dtype == np.complex128
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-13 * np.abs(want).max())
+    # real operators: same kernel, imaginary plane absent; equals ortho2super of the stacked isometry layout
+    Er = [e.real for e in E]
+    np.testing.assert_allclose(T.kraus2superop(Er), sum(np.kron(e, e) for e in Er), rtol=0, atol=1e-13 * np.abs(want).max())
+    assert np.iscomplexobj(T.kraus2superop(Er))
+
+
+def test_kraus2superop_golden(goldens):
+    from opentn_b200 import transformations as T
+    x = goldens["in/x_loc3"]                                         # (12, 4): K = 3, rows a*K + k
+    E = [np.ascontiguousarray(x[k::3]) for k in range(3)]
+    np.testing.assert_allclose(T.kraus2superop(E), goldens["ref/kraus2superop_loc3"], atol=1e-14)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# host loop with the reference's signature: device fast path == callable path == oracle
+# ---------------------------------------------------------------------------------------------------------------------
+def test_closures_device_path(P, goldens):
+    from opentn_b200 import StiefelFit
+    from opentn_b200.trust_region_rcopt import riemannian_trust_region_optimize
+    Li = P.pspl_lindbladians(1.0)
+    T = P.exp_operator_dt(P.create_2local_liouvillians(Li, N, d, pbc=True)[0], 1.0)
+    xs0 = [P.super2ortho(x.real, rank=10) for x in P.get_general_trotter_local_ansatz(Li, 1, n=1)]
+    fit = StiefelFit(T, model="local", N=N, d=d, metric="canonical")
+    f, retract, gradfunc, hessfunc = fit.closures()
+    xs, fs, radius = riemannian_trust_region_optimize(f, retract, gradfunc, hessfunc, xs0, save_x=True, niter=4, verbose=False)
+    np.testing.assert_allclose(fs, goldens["art/f_pauli_n1_tau1_rank10"][:4], rtol=1e-10)
+    assert len(xs) == 5 and radius == 0.1
+    # the same closures are plain callables too: drive them from the host loop (untagged copies) and compare
+    plain = [lambda *a, fn=fn: fn(*a) for fn in (f, retract, gradfunc, hessfunc)]
+    xs2, fs2, radius2 = riemannian_trust_region_optimize(*plain, xs0, save_x=True, niter=4, verbose=False)
+    np.testing.assert_allclose(fs2, fs, rtol=1e-10)
+    np.testing.assert_allclose(np.array(xs2[-1]), np.array(xs[-1]), atol=1e-8)
+    assert radius2 == radius
+    # save_x=False keeps the first and the last iterate only; check_convergence stops early on a stalled cost
+    xs3, fs3, _ = riemannian_trust_region_optimize(f, retract, gradfunc, hessfunc, xs0, niter=3, verbose=False)
+    assert len(xs3) == 2 and len(fs3) == 3
+    fit.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# advisor regressions
+# ---------------------------------------------------------------------------------------------------------------------
+def test_streamed_pipeline_odd_chunk_count(P):
+    """Back-to-back streamed submissions whose chunk count is odd (3 chunks of <= 512 instances) flip the slot parity between
+    calls; every chunk must still see its own workspace slice untouched by chunks of the previous submission."""
+    import torch
+    from opentn_b200 import StiefelFit
+    B, m, K = 1100, 2, 2
+    rng = np.random.default_rng(0)
+    T = P.kitaev_fullsites_target()
+    fit = StiefelFit(T, model="full", N=N, d=d, metric="canonical", max_batch=B)
+    base = np.stack([np.stack([P.random_stiefel(16 * K, 16, rng) for _ in range(m)]) for _ in range(8)])
+    sets = []
+    for s in range(3):
+        x = base[rng.integers(0, 8, B)].copy()
+        z = rng.standard_normal(x.shape)
+        xtz = np.swapaxes(x, -1, -2) @ z
+        e = z - x @ (0.5 * (xtz + np.swapaxes(xtz, -1, -2)))          # project(x, z), batched
+        sets.append((torch.from_numpy(x).pin_memory(), torch.from_numpy(np.ascontiguousarray(e)).pin_memory()))
+    ref = [fit.triple(x.numpy(), e.numpy()) for x, e in sets]
+    for rep in range(2):
+        outs, tickets = [], []
+        for x, e in sets:                       # all three in flight: chunks of neighbouring submissions overlap
+            o = (torch.empty(B, dtype=torch.float64).pin_memory(), torch.empty_like(x).pin_memory(), torch.empty_like(x).pin_memory())
+            tickets.append(fit.triple_submit(x, e, o)); outs.append(o)
+        fit.triple_wait()
+        for o, r in zip(outs, ref):
+            for got, want in zip(o, r):
+                np.testing.assert_array_equal(got.numpy(), want)
+    fit.close()
+
+
+def test_tr_run_on_legacy_default_stream(P):
+    """otn_set_stream(h, 0) (torch's default stream handle) + a small batch: the tCG step cannot be captured into a CUDA graph
+    there; the solver must fall back to plain launches and give the same trajectory."""
+    from opentn_b200 import StiefelFit
+    xs, _ = _rand_local(P, 3, 2, 21)
+    T = P.model_stiefel_local(_rand_local(P, 3, 2, 22)[0], N, d)
+    fit = StiefelFit(T, model="local", N=N, d=d, metric="canonical")
+    x1, rep1 = fit.tr_run(np.array(xs), niter=3)
+    h = fit._handle(3, 2, 1)
+    from opentn_b200._lib import check
+    check(h._lib.otn_set_stream(h.h, None))
+    x2, rep2 = fit.tr_run(np.array(xs), niter=3)
+    np.testing.assert_array_equal(rep1["f_iter"], rep2["f_iter"])
+    np.testing.assert_array_equal(x1, x2)
+    fit.close()
+
+
+def test_target_index_rebind_and_out_validation(P):
+    from opentn_b200 import StiefelFit
+    xs, etas = _rand_local(P, 2, 2, 31)
+    T0 = P.model_stiefel_local(_rand_local(P, 2, 2, 32)[0], N, d)
+    T1 = P.model_stiefel_local(_rand_local(P, 2, 2, 33)[0], N, d)
+    fit = StiefelFit(np.stack([T0, T1]), model="local", N=N, d=d, metric="canonical", max_batch=4)
+    x4 = np.stack([np.array(xs)] * 4)
+    fit.set_target_index([1, 1])
+    f2 = fit.cost(x4[:2])
+    with pytest.raises(ValueError, match="target_index"):
+        fit.cost(x4)                                                 # 4 instances, 2 ids: refused, not run on stale ids
+    fit.set_target_index([1, 0, 0, 1])
+    f4 = fit.cost(x4)
+    f_t0, f_t1 = P.CostSpec(T0, "local", N, d)(xs), P.CostSpec(T1, "local", N, d)(xs)
+    np.testing.assert_allclose(f2, [f_t1, f_t1], rtol=1e-12)
+    np.testing.assert_allclose(f4, [f_t1, f_t0, f_t0, f_t1], rtol=1e-12)
+    e4 = np.stack([np.array(etas)] * 4)
+    good = (np.empty(4), np.empty_like(x4), np.empty_like(x4))
+    fit.triple(x4, e4, out=good)
+    for bad in [(np.empty(4, dtype=np.float32), good[1], good[2]), (good[0], np.empty(x4.shape[:-1]), good[2]),
+                (good[0], good[1], np.empty(x4.shape + (2,))[..., 0])]:
+        with pytest.raises((TypeError, ValueError)):
+            fit.triple(x4, e4, out=bad)
+    fit.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the one collective of the data-parallel path through the C ABI
+# ---------------------------------------------------------------------------------------------------------------------
+def _gather_case(P, ndev):
+    import torch
+    from opentn_b200 import StiefelFit
+    from opentn_b200._lib import check, load
+    lib = load()
+    B = 3
+    T = P.model_stiefel_local(_rand_local(P, 2, 2, 41)[0], N, d)
+    fits, xs_all = [], []
+    for dev in range(ndev):
+        xs = np.stack([np.array(_rand_local(P, 2, 2, 50 + 10 * dev + b)[0]) for b in range(B)])
+        fit = StiefelFit(T, model="local", N=N, d=d, metric="canonical", max_batch=B, device=dev)
+        fit.tr_run(xs, niter=1)                                       # leaves the iterates in the handle
+        fits.append(fit); xs_all.append(xs)
+    handles = (C.c_void_p * ndev)(*[f._handle(2, 2, B).h for f in fits])
+    f_all = np.empty(ndev * B); x_all = np.empty((ndev * B, 2, 8, 4))
+    check(lib.otn_gather(handles, ndev, B, f_all.ctypes.data, x_all.ctypes.data))
+    for dev in range(ndev):
+        x_fin, _ = fits[dev].tr_run(xs_all[dev], niter=1)
+        np.testing.assert_array_equal(x_all[dev * B:(dev + 1) * B], x_fin)
+        np.testing.assert_allclose(f_all[dev * B:(dev + 1) * B], fits[dev].cost(x_fin), rtol=1e-13)
+    for f in fits:
+        f.close()
+
+
+def test_gather_one_gpu(P):
+    _gather_case(P, 1)
+
+
+def test_gather_two_gpus(P):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _gather_case(P, 2)
