@@ -13,6 +13,7 @@
 #include <nvtx3/nvToolsExt.h>   // header-only; a no-op unless a profiler (nsys / ncu --nvtx) is attached
 
 #include "assemble.cuh"
+#include "chain_fused.cuh"
 #include "factored.cuh"
 #include "gemm_dmma.cuh"
 #include "stiefel.cuh"
@@ -252,7 +253,9 @@ struct otn_problem {
     // work matrices, per instance [m][SZ] unless noted
     double *Y = nullptr, *P = nullptr, *G = nullptr, *W = nullptr, *Yd = nullptr, *Pd = nullptr;
     double *Gd = nullptr;        // [2][SZ]
-    double *Wd = nullptr;        // [SZ]
+    double *Wd = nullptr;        // [SZ]; [m][SZ] with the fused chain (all tangent cotangents are formed before the pull-backs run)
+    bool fused = false;          // per-instance fused chain kernel (chain_fused.cuh) instead of one batched GEMM launch per product
+    long long wd_stride = 0;     // per-instance stride of Wd
     // local model: [m][q*q] and per-factor partials [m][nf][q*q]
     double *Yl = nullptr, *Yld = nullptr, *Wl = nullptr, *Wld = nullptr;
     // small per-instance state
@@ -274,8 +277,13 @@ struct otn_problem {
     cudaEvent_t ev_bk_main = nullptr, ev_bk_side = nullptr, ev_bk_done = nullptr;
     bool back_busy = false;
     bool back_wd_pending = false;              // a pull-back reading the (single) Wd buffer is out on the back stream
-    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
-    long long pipe_seq = 0;      // chunks enqueued so far (staging slot = pipe_seq & 1; slot reuse is ordered across calls)
+    // staging slots of the host-array pipeline (inputs + outputs of one chunk each): more slots than compute streams, so that the
+    // H2D copy of chunk c+2 does not have to wait for the kernels of chunk c (with the fused chain a 512-instance chunk computes in
+    // 3.6 ms and copies in 1.8 ms: two slots left the copy engine and the SMs waiting for each other)
+    enum { NSLOT = 4 };
+    cudaEvent_t ev_in[NSLOT] = {}, ev_done[NSLOT] = {}, ev_out[NSLOT] = {};
+    cudaEvent_t ev_cs_done[2] = {nullptr, nullptr};   // newest chunk of each compute stream
+    long long pipe_seq = 0;      // chunks enqueued so far (staging slot = pipe_seq % NSLOT, compute stream = pipe_seq & 1; reuse is ordered across calls)
     // streamed submissions (otn_triple_submit / otn_triple_wait): ticket t completes when ev_ticket[t % 4] has fired
     enum { TICKETS = 4 };
     cudaEvent_t ev_ticket[TICKETS] = {nullptr, nullptr, nullptr, nullptr};
@@ -332,7 +340,8 @@ extern "C" void otn_destroy(otn_problem* h) {
     for (DevBuf* b : {&h->in_x, &h->in_eta, &h->out_a, &h->out_b, &h->out_c, &h->out_f, &h->out_M, &h->tr_buf}) b->release();
     for (auto& r : h->prof.recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (auto e : h->prof.pool) cudaEventDestroy(e);
-    for (int i = 0; i < 2; ++i) for (cudaEvent_t e : {h->ev_in[i], h->ev_done[i], h->ev_out[i]}) if (e) cudaEventDestroy(e);
+    for (int i = 0; i < otn_problem::NSLOT; ++i) for (cudaEvent_t e : {h->ev_in[i], h->ev_done[i], h->ev_out[i]}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_cs_done) if (e) cudaEventDestroy(e);
     if (h->s_in) cudaStreamSynchronize(h->s_in);
     for (int i = 0; i < 2; ++i) if (h->s_comp[i]) cudaStreamSynchronize(h->s_comp[i]);
     if (h->s_out) cudaStreamSynchronize(h->s_out);
@@ -412,9 +421,16 @@ extern "C" int otn_create_ex(otn_problem** out, int N, int d, int m, int K, int 
         h->SZ = L.slot;
         h->nblk = 2; h->blkD[0] = L.Ds; h->blkD[1] = L.Da; h->blkOff[0] = 0; h->blkOff[1] = L.off_a;
     }
+    // fused per-instance chain: block-diagonal evaluation with blocks the fused kernel is instantiated for (144 + 128: N = 4),
+    // m >= 2, and enough instances to give every SM a CTA (below that the tiled kernels spread one product over more SMs)
+    {
+        const char* env = getenv("OTN_FUSED_CHAIN");     // A/B switch for measurements and tests: "0" = never, "1" = always
+        const bool want = env ? (env[0] != '0') : max_batch >= 64;
+        h->fused = want && h->structured && m >= 2 && m <= 15 && chain_fused_supports(h->blkD[0]) && chain_fused_supports(h->blkD[1]);
+    }
     h->tiles = 0;
     for (int i = 0; i < h->nblk; ++i) {
-        h->blkTiles[i] = gemm_plan(h->blkD[i], h->blkD[i], 1).tiles;
+        h->blkTiles[i] = h->fused ? chain_fused_partials(h->blkD[i]) : gemm_plan(h->blkD[i], h->blkD[i], 1).tiles;
         h->blkTileOff[i] = h->tiles;
         h->tiles += h->blkTiles[i];
     }
@@ -588,9 +604,10 @@ extern "C" int otn_create_ex(otn_problem** out, int N, int d, int m, int K, int 
             if (h->structured) CREATE_TRY(cudaMemset(*ptr, 0, B * M * SZ * 8));   // zero padding of the blocks is an invariant
         }
         CREATE_TRY(cudaMalloc(&h->Gd, B * 2 * SZ * 8));
-        CREATE_TRY(cudaMalloc(&h->Wd, B * SZ * 8));
+        h->wd_stride = (h->fused ? (long long)m : 1LL) * h->SZ;
+        CREATE_TRY(cudaMalloc(&h->Wd, B * (size_t)h->wd_stride * 8));
     }
-    if (h->structured) { CREATE_TRY(cudaMemset(h->Gd, 0, B * 2 * SZ * 8)); CREATE_TRY(cudaMemset(h->Wd, 0, B * SZ * 8)); }
+    if (h->structured) { CREATE_TRY(cudaMemset(h->Gd, 0, B * 2 * SZ * 8)); CREATE_TRY(cudaMemset(h->Wd, 0, B * (size_t)h->wd_stride * 8)); }
     for (double** ptr : {&h->x, &h->eta, &h->zraw, &h->zdraw}) CREATE_TRY(cudaMalloc(ptr, B * M * h->np * 8));
     CREATE_TRY(cudaMalloc(&h->part_f, B * h->tiles * 8));
     CREATE_TRY(cudaMalloc(&h->part_s, B * h->tiles * 8));
@@ -731,6 +748,36 @@ static GemmParams gp(const otn_problem* h, int batch, const int* active) {
 }
 static inline double* layer_ptr(double* base, int l, long long SZ) { return base + (long long)l * SZ; }
 
+// fused chain (chain_fused.cuh): the whole product sequence of `mode` for every instance, one launch per diagonal block
+// (symmetric block on the handle's stream, antisymmetric one on the side stream, like hgemm)
+static int hchain(otn_problem* h, int batch, const int* active, int mode) {
+    ChainProgram prog;
+    int gd_final = 0;
+    if (!chain_build(mode, h->m, prog, &gd_final)) return fail("fused chain: cannot build the op list for m = %d", h->m);
+    if (mode == CHAIN_TANGENT || mode == CHAIN_TRIPLE) h->tr.gd_final = gd_final;
+    const long long SZ = h->SZ, S = (long long)h->m * SZ;
+    for (int i = 0; i < h->nblk; ++i) {
+        ChainParams p{};
+        const long long o = h->blkOff[i];
+        double* bases[CH_NARR] = {h->Y, h->P, h->G, h->W, h->Yd, h->Pd, h->Gd, h->Wd};
+        const long long strides[CH_NARR] = {S, S, S, S, S, S, 2 * SZ, h->wd_stride};
+        for (int a = 0; a < CH_NARR; ++a) { p.base[a] = bases[a] + o; p.stride[a] = strides[a]; p.lstride[a] = SZ; }
+        p.D = h->blkD[i]; p.kvalid = (i == 0 ? h->sym.NS : h->sym.NA);
+        p.T = h->T_re + o; p.sT = SZ; p.tindex = h->tindex;
+        p.part_f = h->part_f + h->blkTileOff[i]; p.part_s = h->part_s + h->blkTileOff[i]; p.part_stride = h->tiles;
+        p.active = active; p.nops = prog.nops;
+        std::memcpy(p.ops, prog.ops, sizeof(ChainOp) * prog.nops);
+        cudaStream_t st = h->stream;
+        if (h->prof.side.active()) {
+            h->prof.fork(h->stream);
+            if (i == 1) st = h->prof.side.st;
+        }
+        ProfScope ps(&h->prof, st, CAT_GEMM, 2.0 * p.D * (double)p.D * p.kvalid * batch * prog.products);
+        CUDA_TRY(chain_launch(p, batch, st));
+    }
+    return 0;
+}
+
 // layer superoperators Y_l (and tangents Yd_l) for all instances
 static int build_layers(otn_problem* h, const double* x, const double* eta, int batch, const int* active, bool primal) {
     const int items = batch * h->m;
@@ -837,6 +884,7 @@ static int forward_chain(otn_problem* h, int batch, const int* active, bool mode
         CUDA_TRY(cudaGetLastError());
         return 0;
     }
+    if (h->fused) return hchain(h, batch, active, model_only ? CHAIN_FWD_MODEL : CHAIN_FWD);
     for (int l = 1; l < m; ++l) {
         GemmParams p = gp(h, batch, active);
         p.A1 = layer_ptr(h->Y, l, SZ); p.sA1 = S;
@@ -881,7 +929,10 @@ static int back_layer(otn_problem* h, int batch, const int* active, int l, const
     const long long SZ = h->SZ, S = (long long)h->m * SZ;
     const double* Wfull = (l == 0) ? h->G : layer_ptr(h->W, l, SZ);                  // W_0 = G_0
     const double* Wdfull = nullptr; long long sWd = 0;
-    if (tangent) { Wdfull = (l == 0) ? h->Gd + (long long)h->tr.gd_final * SZ : h->Wd; sWd = (l == 0) ? 2 * SZ : SZ; }
+    if (tangent) {
+        if (l == 0) { Wdfull = h->Gd + (long long)h->tr.gd_final * SZ; sWd = 2 * SZ; }
+        else { Wdfull = h->fused ? h->Wd + (long long)l * SZ : h->Wd; sWd = h->wd_stride; }
+    }
     const double* Wsup = Wfull; long long sW = S; const double* Wdsup = Wdfull; long long sWds = sWd; int nslices = 1;
     if (h->model == OTN_MODEL_LOCAL) {
         const int q2 = h->q * h->q;
@@ -967,6 +1018,11 @@ static int back_layer(otn_problem* h, int batch, const int* active, int l, const
 
 static int reverse_chain(otn_problem* h, int batch, const int* active, const double* x, const double* eta_joint = nullptr) {
     const long long SZ = h->SZ, S = (long long)h->m * SZ;
+    if (h->fused && h->m >= 2) {
+        OTN_TRY(hchain(h, batch, active, CHAIN_REV));
+        for (int l = h->m - 1; l >= 0; --l) OTN_TRY(back_layer(h, batch, active, l, x, false, eta_joint, eta_joint != nullptr));
+        return 0;
+    }
     for (int l = h->m - 1; l >= 1; --l) {
         GemmParams p = gp(h, batch, active);                       // W_l = G_l P_{l-1}^T
         p.A1 = layer_ptr(h->G, l, SZ); p.sA1 = S;
@@ -992,6 +1048,11 @@ static int tangent_pass(otn_problem* h, int batch, const int* active, const doub
     const long long SZ = h->SZ, S = (long long)h->m * SZ;
     const int m = h->m;
     if (!layers_built) OTN_TRY(build_layers(h, x, eta, batch, active, false));
+    if (h->fused && m >= 2) {
+        OTN_TRY(hchain(h, batch, active, CHAIN_TANGENT));
+        for (int l = m - 1; l >= 0; --l) OTN_TRY(back_layer(h, batch, active, l, x, true, eta, joint));
+        return 0;
+    }
     // forward tangent: Pd_l = Yd_l P_{l-1} + Y_l Pd_{l-1};  last one is Mdot -> Gd[0], with <R, Mdot> partials
     int cur = 0;
     if (m == 1) {
@@ -1277,9 +1338,18 @@ static int triple_device(otn_problem* h, const double* x, const double* eta, int
         OTN_TRY(riem_launch(h, batch, nullptr, tiles, x, eta, true, f, rgrad, nullptr, heta));
         return 0;
     }
+    const bool joint = h->structured && h->model == OTN_MODEL_FULL;   // W_l is pulled back against x and eta in one pass
+    if (h->fused && h->m >= 2) {
+        // forward, residual, reverse and tangent sweeps of every instance in ONE launch per diagonal block, then the pull-backs
+        h->tr.tiles = tiles = h->tiles;
+        OTN_TRY(hchain(h, batch, nullptr, CHAIN_TRIPLE));
+        for (int l = h->m - 1; l >= 0; --l) OTN_TRY(back_layer(h, batch, nullptr, l, x, false, joint ? eta : nullptr, joint));
+        for (int l = h->m - 1; l >= 0; --l) OTN_TRY(back_layer(h, batch, nullptr, l, x, true, eta, joint));
+        OTN_TRY(riem_launch(h, batch, nullptr, tiles, x, eta, true, f, rgrad, nullptr, heta));
+        return 0;
+    }
     OTN_TRY(forward_chain(h, batch, nullptr, false, &tiles));
     h->tr.tiles = tiles;
-    const bool joint = h->structured && h->model == OTN_MODEL_FULL;   // W_l is pulled back against x and eta in one pass
     OTN_TRY(reverse_chain(h, batch, nullptr, x, joint ? eta : nullptr));
     OTN_TRY(tangent_pass(h, batch, nullptr, x, eta, true, joint));
     OTN_TRY(riem_launch(h, batch, nullptr, tiles, x, eta, true, f, rgrad, nullptr, heta));
@@ -1292,7 +1362,7 @@ static void shift_instance_views(otn_problem* h, long long db) {
     const long long SZ = h->SZ, m = h->m, q2 = (long long)h->q * h->q;
     auto mv = [&](double*& ptr, long long stride) { if (ptr) ptr += db * stride; };
     for (double** ptr : {&h->Y, &h->P, &h->G, &h->W, &h->Yd, &h->Pd}) mv(*ptr, m * SZ);
-    mv(h->Gd, 2 * SZ); mv(h->Wd, SZ);
+    mv(h->Gd, 2 * SZ); mv(h->Wd, h->wd_stride);
     mv(h->Yl, m * q2); mv(h->Yld, m * q2); mv(h->Wl, m * h->nf * q2); mv(h->Wld, m * h->nf * q2);
     for (double** ptr : {&h->x, &h->eta, &h->zraw, &h->zdraw}) mv(*ptr, m * h->np);
     mv(h->part_f, h->tiles); mv(h->part_s, h->tiles);
@@ -1321,6 +1391,9 @@ static int triple_pipelined(otn_problem* h, const double* x, const double* eta, 
             CUDA_TRY(cudaStreamCreateWithFlags(&h->s_comp[i], cudaStreamNonBlocking));
             CUDA_TRY(cudaStreamCreateWithFlags(&h->s_side[i], cudaStreamNonBlocking));
             CUDA_TRY(cudaStreamCreateWithFlags(&h->s_backp[i], cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&h->ev_cs_done[i], cudaEventDisableTiming));
+        }
+        for (int i = 0; i < otn_problem::NSLOT; ++i) {
             CUDA_TRY(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
@@ -1334,7 +1407,8 @@ static int triple_pipelined(otn_problem* h, const double* x, const double* eta, 
     // write the caller's arrays in place; what remains is the schedule -- chunks alternating between the two compute streams on
     // disjoint workspace slices, no host synchronisation between submissions -- so that the first kernels of one submission run
     // under the last kernels of the previous one.  Ordered behind the handle's stream at submission time.
-    if (!dev) OTN_TRY(h->pipe_buf.ensure(2 * slot_doubles * 8));
+    constexpr int NSLOT = otn_problem::NSLOT;
+    if (!dev) OTN_TRY(h->pipe_buf.ensure(NSLOT * slot_doubles * 8));
     if (!dev) CUDA_TRY(cudaStreamSynchronize(h->stream));
     // (copies are not the bottleneck: PCIe moves the 403 MB of a step in 4.2 ms, both directions overlapped)
     // chunk schedule: short first and last chunks (exposed head H2D / tail D2H), longer ones in between (kernel efficiency)
@@ -1368,22 +1442,22 @@ static int triple_pipelined(otn_problem* h, const double* x, const double* eta, 
     const int nchunks = (int)sizes.size();
     int b0 = 0;
     for (int c = 0; c < nchunks; ++c, ++h->pipe_seq) {
-        const int slot = (int)(h->pipe_seq & 1), nb = sizes[c];
+        const int slot = (int)(h->pipe_seq % NSLOT), cs = (int)(h->pipe_seq & 1), nb = sizes[c];   // staging slot, compute stream
         double* base = dev ? nullptr : h->pipe_buf.as<double>() + slot * slot_doubles;
         double *dx = base, *de = dx + (size_t)CMAX * per, *dg = de + (size_t)CMAX * per, *dh = dg + (size_t)CMAX * per, *df = dh + (size_t)CMAX * per;
-        cudaStream_t comp = h->s_comp[slot];
+        cudaStream_t comp = h->s_comp[cs];
         if (dev) {
             dx = const_cast<double*>(x) + (size_t)b0 * per; de = const_cast<double*>(eta) + (size_t)b0 * per;
             dg = rgrad + (size_t)b0 * per; dh = heta + (size_t)b0 * per; df = f + b0;
             CUDA_TRY(cudaEventRecord(h->ev_in[slot], h->stream));                            // inputs are ready in the handle's stream order
             CUDA_TRY(cudaStreamWaitEvent(comp, h->ev_in[slot], 0));
         } else {
-            if (h->pipe_seq >= 2) CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_done[slot], 0));   // kernels of chunk c-2 finished reading dx/de
+            if (h->pipe_seq >= NSLOT) CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_done[slot], 0));   // kernels of chunk c-NSLOT finished reading dx/de
             CUDA_TRY(cudaMemcpyAsync(dx, x + (size_t)b0 * per, nb * per * 8, cudaMemcpyHostToDevice, h->s_in));
             CUDA_TRY(cudaMemcpyAsync(de, eta + (size_t)b0 * per, nb * per * 8, cudaMemcpyHostToDevice, h->s_in));
             CUDA_TRY(cudaEventRecord(h->ev_in[slot], h->s_in));
             CUDA_TRY(cudaStreamWaitEvent(comp, h->ev_in[slot], 0));
-            if (h->pipe_seq >= 2) CUDA_TRY(cudaStreamWaitEvent(comp, h->ev_out[slot], 0));   // D2H of chunk c-2 drained dg/dh/df
+            if (h->pipe_seq >= NSLOT) CUDA_TRY(cudaStreamWaitEvent(comp, h->ev_out[slot], 0));   // D2H of chunk c-NSLOT drained dg/dh/df
         }
         // Chunks on the two compute streams overlap in time and must not share a workspace slice.  Inside one call the slices
         // are disjoint; across calls a chunk may meet the slice of an EARLIER chunk that ran on the other stream (any earlier
@@ -1391,14 +1465,14 @@ static int triple_pipelined(otn_problem* h, const double* x, const double* eta, 
         // the slices enqueued on the other stream since stream s last waited for it; a chunk that overlaps one of them waits for
         // the other stream's newest chunk (stream order covers the older ones) and clears the list.
         {
-            auto& mine = h->pipe_unsynced[slot];
+            auto& mine = h->pipe_unsynced[cs];
             bool clash = mine.size() > 16;                      // bound the list: an occasional extra wait is harmless
             for (const auto& r : mine) if (b0 < r.first + r.second && r.first < b0 + nb) { clash = true; break; }
             if (clash) {
-                CUDA_TRY(cudaStreamWaitEvent(comp, h->ev_done[slot ^ 1], 0));
+                CUDA_TRY(cudaStreamWaitEvent(comp, h->ev_cs_done[cs ^ 1], 0));
                 mine.clear();
             }
-            auto& theirs = h->pipe_unsynced[slot ^ 1];
+            auto& theirs = h->pipe_unsynced[cs ^ 1];
             bool known = false;
             for (const auto& r : theirs) if (r.first == b0 && r.second == nb) { known = true; break; }
             if (!known) theirs.push_back({b0, nb});
@@ -1406,9 +1480,9 @@ static int triple_pipelined(otn_problem* h, const double* x, const double* eta, 
         cudaStream_t user_stream = h->stream;
         h->stream = comp;
         cudaStream_t user_side = h->prof.side.st;
-        if (h->prof.side.enabled) h->prof.side.st = h->s_side[slot];   // each compute stream forks to its own side stream
+        if (h->prof.side.enabled) h->prof.side.st = h->s_side[cs];   // each compute stream forks to its own side stream
         cudaStream_t user_back = h->s_back;
-        if (h->s_back) h->s_back = h->s_backp[slot];                   // ... and has its own back stream
+        if (h->s_back) h->s_back = h->s_backp[cs];                   // ... and has its own back stream
         shift_instance_views(h, b0);
         const int rc = triple_device(h, dx, de, nb, df, dg, dh);
         shift_instance_views(h, -(long long)b0);
@@ -1417,6 +1491,7 @@ static int triple_pipelined(otn_problem* h, const double* x, const double* eta, 
         h->stream = user_stream;
         if (rc != 0) return rc;
         CUDA_TRY(cudaEventRecord(h->ev_done[slot], comp));
+        CUDA_TRY(cudaEventRecord(h->ev_cs_done[cs], comp));
         CUDA_TRY(cudaStreamWaitEvent(h->s_out, h->ev_done[slot], 0));
         if (!dev) {
             if (f) CUDA_TRY(cudaMemcpyAsync(f + b0, df, (size_t)nb * 8, cudaMemcpyDeviceToHost, h->s_out));
