@@ -18,8 +18,10 @@ def test_kraus2superop_definition(goldens, oracle):
     got = T.kraus2superop(oracle.kraus_from_ortho(x))
     assert got.dtype == complex
     np.testing.assert_allclose(got, goldens["ref/kraus2superop_loc3"], atol=1e-15)
+    # complex Kraus operators (the reference's definition is complex: np.kron(E, E.conj()), transformations.py:179)
+    np.testing.assert_allclose(T.kraus2superop([np.eye(4) * 1j]), np.eye(16), atol=1e-15)
     with pytest.raises(NotImplementedError):
-        T.kraus2superop([np.eye(4) * 1j])
+        T.kraus2superop([np.ones((4, 2))])         # rectangular Kraus operators are not on the accelerated path
 
 
 @pytest.mark.parametrize("shift", [False, True])
