@@ -184,7 +184,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": statistics.median(t_ms), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config({"sample": sample}),
+            "config": workload_config(),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference = opentn's algorithm restated in NumPy (oracle/port.py; JAX is not installable here), "
@@ -336,6 +336,344 @@ def two_site_leg(torch, lib, C, _lib, StiefelFit, T, stream, device, peak_tf, st
     return out
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# additional legs (all bounded; each returns a dict that becomes a key of the JSON line)
+# ---------------------------------------------------------------------------------------------------------------------
+TR_KICK = 1e-2
+
+
+def c3_tr_start():
+    """Trotter (Strang) starting point of the C3 workload at Kraus rank 16: [exp(tau/2 L_odd), exp(tau L_even), exp(tau/2 L_odd)] of
+    the Kitaev chain (experiments/trust_region_fullsites_ansatz.ipynb cell 1: tau = 4, pbc = False), each layer factorised by
+    super2ortho(rank=16) (transformations.py:728-741).  Host NumPy, set-up only."""
+    import numpy as np
+    from opentn_b200 import transformations as T
+    layers = T.create_trotter_layers(list(T.create_kitaev_liouvillians(N_SITES, D_LOC, 1.0, pbc=False)), tau=4.0)[1:]
+    xs = [T.super2ortho(np.asarray(x).real, rank=K_RANK) for x in layers]
+    return np.stack([xs[0], xs[1], xs[0]])
+
+
+def _cpu_tr_c3_worker(args):
+    """TR iterations of the oracle (matrix-free Hessian operator) on the SAME instances the device TR leg runs: the kicked Trotter
+    starts are handed over as arrays (Kraus-operator signs of a rank-deficient Choi factor are a convention of the factorisation,
+    so rebuilding the start on the host would give a different instance)."""
+    xs_list, niter = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    from oracle import port as P
+    T = P.kitaev_fullsites_target(N_SITES, D_LOC, 1.0, 4.0, False)
+    spec = P.CostSpec(T, "full")
+    t0 = time.perf_counter()
+    ncg, fs = 0, []
+    for xs in xs_list:
+        _, f_it, _, log_ = P.trust_region_fit(spec, list(xs), "canonical", niter=niter)
+        ncg += sum(l["n_matvec"] - 1 for l in log_)
+        fs.append(f_it)
+    return time.perf_counter() - t0, ncg, fs
+
+
+def _cpu_latency_worker(args):
+    """Single-instance trust-region latency of the oracle on configs 1 / 2 (one process, one BLAS thread)."""
+    which, niter = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    from oracle import port as P
+    Li = P.pspl_lindbladians(1.0)
+    tau, n = (1.0, 1) if which == "c1" else (0.5, 4)
+    T = P.exp_operator_dt(P.create_2local_liouvillians(Li, N_SITES, D_LOC, pbc=True)[0], tau)
+    xs0 = [P.super2ortho(x.real, rank=10) for x in P.get_general_trotter_local_ansatz(Li, tau, n=n)]
+    spec = P.CostSpec(T, "local", N_SITES, D_LOC)
+    t0 = time.perf_counter()
+    _, f_it, _, log_ = P.trust_region_fit(spec, xs0, "canonical", niter=niter)
+    dt = time.perf_counter() - t0
+    return dt / niter, sum(l["n_matvec"] - 1 for l in log_) / niter, list(f_it)
+
+
+def latency_leg(torch, StiefelFit, device, cpu):
+    """Configs 1 and 2 of BASELINE.json: ONE instance (PSPL N=4, K=10; tau=1 n=1 m=3 / tau=0.5 n=4 m=9), Trotter start, canonical
+    metric: milliseconds per trust-region iteration of the device solver (otn_tr_run, host arrays in and out) next to the oracle's
+    loop on one host core (same start, same iteration count; matrix-free Hessian operator = baseline (ii))."""
+    import numpy as np
+    from opentn_b200 import optimization as O
+    from opentn_b200 import transformations as T
+    out = {"unit": "ms per TR iteration (single instance)", "note": "device: StiefelFit.tr_run with host arrays, wall clock incl. "
+           "H2D/D2H of x and the report; cpu: oracle/port.py trust_region_fit, 1 process, 1 BLAS thread"}
+    Li = [np.kron(T.X, T.I) - np.kron(T.I, T.X), np.kron(T.Z, T.I) - np.kron(T.I, T.Z)]          # PSPL, gamma = 1
+    for which, tau, n, niter_dev, niter_cpu in (("c1", 1.0, 1, 5, 5), ("c2", 0.5, 4, 3, 3)):
+        target = T.exp_operator_dt(T.create_2local_liouvillians(Li, N_SITES, D_LOC, pbc=True)[0], tau)
+        xs0 = np.stack([T.super2ortho(np.asarray(x).real, rank=10) for x in O.get_general_trotter_local_ansatz(Li, tau, n)])
+        fit = StiefelFit(target, model="local", N=N_SITES, d=D_LOC, metric="canonical", device=device)
+        fit.tr_run(xs0, niter=2)                                   # warm-up: handle, kernel attributes, graph
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _, rep = fit.tr_run(xs0, niter=niter_dev)
+        torch.cuda.synchronize()
+        ms_dev = 1e3 * (time.perf_counter() - t0) / niter_dev
+        leg = {"workload": f"PSPL N=4 tau={tau} n={n} (m={2 * n + 1}) K=10, 2-site ansatz, Trotter start, B=1",
+               "device_ms_per_iter": ms_dev, "device_niter": niter_dev, "device_n_cg_mean": float(rep["n_cg"].mean()),
+               "device_f_first_last": [float(rep["f_iter"][0, 0]), float(rep["f_iter"][-1, 0])]}
+        fit.close()
+        if cpu is not None:
+            s_it, ncg, f_it = cpu.pool.apply(_cpu_latency_worker, ((which, niter_cpu),))
+            leg.update({"cpu_ms_per_iter": 1e3 * s_it, "cpu_niter": niter_cpu, "cpu_n_cg_mean": ncg, "cpu_cores": 1,
+                        "cpu_f_first_last": [f_it[0], f_it[-1]], "speedup": 1e3 * s_it / ms_dev,
+                        "cost_history_max_rel_diff": float(np.max(np.abs(np.array(f_it) - rep["f_iter"][:, 0]) / np.array(f_it)))})
+        out[which] = leg
+    return out
+
+
+def host_ceiling_leg(torch, dist, world, x_pin, g_pin, barrier, max_over_ranks, steps):
+    """What the host side of the box can move: every rank copies one step's worth of inputs H2D and outputs D2H concurrently
+    (two streams, pinned buffers, NO kernels).  The end-to-end U1 rate cannot exceed batch / this time, whatever the GPUs do."""
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    d_in = torch.empty((2,) + tuple(x_pin.shape), dtype=torch.float64, device="cuda")
+    d_out = torch.empty_like(d_in)
+    h_in = [x_pin, x_pin]; h_out = [g_pin, g_pin]
+
+    def one():
+        with torch.cuda.stream(s_in):
+            for k in range(2):
+                d_in[k].copy_(h_in[k], non_blocking=True)
+        with torch.cuda.stream(s_out):
+            for k in range(2):
+                h_out[k].copy_(d_out[k], non_blocking=True)
+    for _ in range(2):
+        one()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+    barrier()
+    nbytes = 4 * x_pin.numel() * 8
+    return {"ms_per_step": ms / steps, "gb_per_s_per_rank_both_directions": nbytes * steps / (ms * 1e-3) / 1e9,
+            "u1_per_s_ceiling": world * BATCH * steps / (ms * 1e-3),
+            "note": "concurrent pinned H2D (x, eta) + D2H (rgrad, heta) of one step per rank, no kernels; wall clock, max over ranks"}
+
+
+def tr_leg(torch, C, lib, _lib, fit, handle, stream, rank, world, barrier, max_over_ranks, e0, e1, cpu, niter):
+    """Unit U2: trust-region iterations/s of the batched device solver on the C3 batch with REALISTIC starts -- the
+    Trotter point at Kraus rank 16 retracted after a random tangent kick of canonical norm 1e-2 (seed = global instance index) --
+    (a) device-resident x, (b) end to end: pinned host x in, otn_tr_run, host x and report out.  With a CpuPool: the oracle's loop on
+    the same instances (first `cores` seeds), same iteration count."""
+    import numpy as np
+    from opentn_b200 import sweep
+    x0 = c3_tr_start()
+    seeds = np.arange(rank * BATCH, (rank + 1) * BATCH, dtype=np.uint64)
+    xs_dev = sweep.kicked_starts_device(torch.from_numpy(np.broadcast_to(x0, (BATCH,) + x0.shape).copy()).cuda(), seeds, TR_KICK)
+    fit.tr_run(xs_dev, niter=1)                                     # warm-up
+    barrier()
+    e0.record(stream)
+    _, rep = fit.tr_run(xs_dev, niter=niter)
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    out = {"iters_per_sec": world * BATCH * niter / (ms * 1e-3), "unit": "TR iterations/s (all instances)", "niter": niter,
+           "starts": f"Trotter point (K=16) + tangent kick of canonical norm {TR_KICK}, seed = global instance index (otn_kicked_starts)",
+           "n_cg_mean": float(rep["n_cg"].mean()), "n_cg_max": int(rep["n_cg"].max()), "hvp_total_rank0": int(rep["hvp_total"]),
+           "ms_per_iter_batch": ms / niter, "accept_rate": float(rep["accepted"].mean()),
+           "f_median_first_last": [float(np.median(rep["f_iter"][0])), float(np.median(rep["f_iter"][-1]))],
+           "status_nonzero": int((rep["status"] != 0).sum())}
+    # (b) end to end through the C ABI with host arrays: x in (pinned), x out, per-iteration report arrays out
+    x_pin = xs_dev.cpu().pin_memory()
+    xw = torch.empty_like(x_pin).pin_memory()
+    f_it = torch.empty((niter, BATCH), dtype=torch.float64).pin_memory()
+    ncg = torch.empty((niter, BATCH), dtype=torch.int32).pin_memory()
+    status = torch.zeros(BATCH, dtype=torch.int32).pin_memory()
+    prm = _lib.TrParams(0.125, 0.01, 0.1, niter, 0, 1e-8, 1e-6)
+
+    def run_e2e():
+        xw.copy_(x_pin)
+        rp = _lib.TrReport(f_it.data_ptr(), None, None, ncg.data_ptr(), None, None, None, None, status.data_ptr(), 0)
+        _lib.check(lib.otn_tr_run(handle.h, xw.data_ptr(), BATCH, C.byref(prm), C.byref(rp)))
+    run_e2e()
+    barrier()
+    reps = 2
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        run_e2e()
+    torch.cuda.synchronize()
+    ms_e2e = max_over_ranks(1e3 * (time.perf_counter() - t0)) / reps
+    barrier()
+    per = x_pin.numel() * 8
+    out["e2e"] = {"iters_per_sec": world * BATCH * niter / (ms_e2e * 1e-3), "ms_per_call": ms_e2e, "niter_per_call": niter,
+                  "h2d_bytes_per_call": per, "d2h_bytes_per_call": per + niter * BATCH * 12 + BATCH * 4,
+                  "mode": "otn_tr_run with host arrays: x in, x + f_iter + n_cg + status out; wall clock incl. the host-side copy of x",
+                  "matches_device_resident": bool(np.allclose(f_it.numpy(), rep["f_iter"], rtol=1e-12))}
+    if cpu is not None:
+        n_cpu = cpu.cores
+        xs_host = x_pin.numpy()
+        res = cpu.pool.map(_cpu_tr_c3_worker, [([xs_host[c]], niter) for c in range(n_cpu)])
+        wall = max(r[0] for r in res)
+        f_cpu = np.array([r[2][0] for r in res]).T                     # [niter][n_cpu]
+        out["cpu"] = {"iters_per_sec": n_cpu * niter / wall, "cores": n_cpu, "kind": "port",
+                      "sample": f"{n_cpu} of the same instances (1 per process, 1 BLAS thread), {niter} TR iterations each, {wall:.1f} s",
+                      "n_cg_mean": sum(r[1] for r in res) / (n_cpu * niter),
+                      "cost_history_max_rel_diff_vs_device": float(np.max(np.abs(f_cpu - rep["f_iter"][:, :n_cpu]) / f_cpu))}
+        out["speedup_vs_cpu"] = out["iters_per_sec"] / out["cpu"]["iters_per_sec"]
+    return out
+
+
+C4_TAUS, C4_RANKS, C4_STEPS = [0.25, 0.5, 1.0, 2.0], [2, 4, 8, 16], 4
+
+
+def _cpu_c4_worker(args):
+    """One fit of config 4 on the oracle, from the kicked start the device run used (handed over as an array): seconds for
+    `niter` TR iterations and the first cost."""
+    xs, ti, niter = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    from oracle import port as P
+    Lk = P.get_kitaev_nn_linbladian(1.0)
+    T = P.exp_operator_dt(P.create_2local_liouvillians(Lk, N_SITES, D_LOC, pbc=True)[0], C4_TAUS[ti])
+    spec = P.CostSpec(T, "local", N_SITES, D_LOC)
+    t0 = time.perf_counter()
+    _, f_it, _, _ = P.trust_region_fit(spec, list(xs), "canonical", niter=niter)
+    return time.perf_counter() - t0, f_it[0]
+
+
+def c4_leg(torch, dist, rank, world, device, barrier, max_over_ranks, cpu, seeds_per_cell=256, niter=5):
+    """BASELINE config 4: tau x rank x seed sweep, 4 taus x ranks {2,4,8,16} x `seeds_per_cell` seeds = 4096 instances of the 2-site
+    model (N=4, m=9), `niter` TR iterations each, STRONG scaling: the 16 (K, tau) cells are split over the ranks
+    (sweep.plan_cells), one final all-gather.  Reported: fits/s over the whole job, set-up (device Liouvillian, expm sweep, Choi
+    factorisation, kicked starts) and solve separately."""
+    import numpy as np
+    from opentn_b200 import sweep
+    from opentn_b200 import transformations as T
+    Lnn = [T.get_kitaev_nn_linbladian(1.0)]
+    sweep.run_sweep(Lnn, N_SITES, D_LOC, C4_TAUS, C4_RANKS, list(range(2)), n_steps=C4_STEPS, niter=1, device=device, rank=rank,
+                    world=world, gather=world > 1)                                   # warm-up: contexts, kernel attributes
+    barrier()
+    tm = {}
+    t0 = time.perf_counter()
+    res = sweep.run_sweep(Lnn, N_SITES, D_LOC, C4_TAUS, C4_RANKS, list(range(seeds_per_cell)), n_steps=C4_STEPS, niter=niter,
+                          device=device, rank=rank, world=world, gather=world > 1, timings=tm)
+    torch.cuda.synchronize()
+    wall = max_over_ranks(time.perf_counter() - t0)
+    setup_s, solve_s = max_over_ranks(tm["setup_s"]), max_over_ranks(tm["solve_s"])
+    barrier()
+    n_inst = len(C4_TAUS) * len(C4_RANKS) * seeds_per_cell
+    got = sum(len(r["f0"]) for r in res.values())
+    improved = float(np.mean(np.concatenate([r["f_final"] < r["f0"] for r in res.values()])))
+    out = {"workload": f"Kitaev gamma=1 N=4 pbc, 2-site ansatz n=4 (m=9): taus {C4_TAUS} x K {C4_RANKS} x {seeds_per_cell} seeds = {n_inst} fits, "
+                       f"{niter} TR iterations each, Trotter start + 1e-2 kick",
+           "scaling": "strong", "fits_per_sec": n_inst / wall, "tr_iters_per_sec": n_inst * niter / wall, "wall_s": wall,
+           "setup_s": setup_s, "solve_s": solve_s, "gather_s": max(wall - setup_s - solve_s, 0.0),
+           "instances_returned_rank0": got, "improved_fraction": improved,
+           "status_nonzero": int(sum((r["status"] != 0).sum() for r in res.values())),
+           "partition": "contiguous pieces of the K-major (K, tau) cell list per rank; one all-gather per K group at the end"}
+    if cpu is not None and world == 1:
+        picks = [(C4_RANKS[c % 4], (c // 4) % 4, c % seeds_per_cell) for c in range(cpu.cores)]     # (K, tau index, seed) cycling
+        jobs, dev_f0 = [], []
+        for K, ti, sd in picks:
+            r = res[K]
+            i = int(np.where((r["tau_index"] == ti) & (r["seed"] == sd))[0][0])
+            jobs.append((r["x0"][i], ti, 1))
+            dev_f0.append(r["f0"][i])
+        resc = cpu.pool.map(_cpu_c4_worker, jobs)
+        wall_c = max(r[0] for r in resc)
+        chk = [abs(d - c[1]) / c[1] for d, c in zip(dev_f0, resc)]       # same instance: first costs agree to rounding
+        out["cpu"] = {"tr_iters_per_sec": cpu.cores / wall_c, "cores": cpu.cores, "kind": "port",
+                      "sample": f"{cpu.cores} instances of the sweep (K and tau cycling), 1 TR iteration each, {wall_c:.1f} s",
+                      "first_cost_max_rel_diff_vs_device": float(max(chk)) if chk else None}
+        out["speedup_vs_cpu"] = out["tr_iters_per_sec"] / out["cpu"]["tr_iters_per_sec"]
+    return out
+
+
+
+def _cpu_zgemm_worker(D):
+    """The reference's composition step on the host: one complex128 D x D product with every core (numpy / BLAS threads), the
+    operation timed in experiments/gradient.ipynb cells 195-197 (9.4-15 s on the author's machine)."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((D, D)) + 1j * rng.standard_normal((D, D))
+    B = rng.standard_normal((D, D)) + 1j * rng.standard_normal((D, D))
+    t0 = time.perf_counter()
+    A @ B
+    return time.perf_counter() - t0
+
+
+def c5_leg(torch, dist, rank, world, device, barrier, max_over_ranks, with_cpu):
+    """BASELINE config 5: one synthetic N=6 instance (D = 4096), three complex layer superoperators (rank-16 two-site layers embedded
+    to 4096 x 4096, complex128 as (re, im) planes), the composition Y3 Y2 Y1 = 2 complex = 8 real D^3 products on FP64 DMMA, rows of
+    every product sharded over the ranks; exchange fused into the GEMM epilogue (NVLink peer stores + device-side flags) and, for
+    comparison, by NCCL all-gather.  STRONG scaling: the efficiency is measured inside the run against rank 0 computing the same
+    products alone."""
+    import numpy as np
+    from opentn_b200 import transformations as T
+    from opentn_b200.rowsharded import RowShardedChain
+    T.set_device(device)
+    D, m, K = 4096, 3, 16
+    rng = np.random.default_rng(5)
+    planes = []
+    for l in range(m):                      # same layers on every rank
+        pair = []
+        for part in range(2):
+            q, _ = np.linalg.qr(rng.standard_normal((4 * K, 4)))
+            pair.append(torch.from_numpy(T.local2full(T.ortho2super(q), 6, 2, shift_pbc=bool(l % 2))).cuda() * (1.0 if part == 0 else 0.1))
+        planes.append(tuple(pair))
+    flops = 8 * (m - 1) * 2.0 * D ** 3
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(chain, reps=3):
+        chain.compose_complex(planes)
+        barrier()
+        e0.record()
+        for _ in range(reps):
+            out = chain.compose_complex(planes)
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / reps, out
+
+    # single-GPU time of the same products (every rank computes everything: world = 1 view of the chain)
+    solo = RowShardedChain(D, device=device, single=True)
+    ms_solo, M_solo = timed(solo)
+    out = {"workload": f"synthetic N=6 (D={D}) complex layers, m={m}, composition Y3 Y2 Y1 = {8 * (m - 1)} real D^3 products (4M complex), "
+                       f"rows sharded over {world} GPU(s)",
+           "scaling": "strong", "unit": "TFLOP/s (real flops, aggregate)", "flops_per_composition": flops,
+           "single_gpu": {"ms": ms_solo, "tflops": flops / ms_solo / 1e9}}
+    if world > 1:
+        for name, p2p in (("fused_peer_store", True), ("nccl_allgather", False)):
+            ch = RowShardedChain(D, p2p=p2p, nbuf=8)
+            ms, M = timed(ch)
+            same = bool(torch.equal(M[0], M_solo[0]) and torch.equal(M[1], M_solo[1]))
+            out[name] = {"ms": ms, "tflops": flops / ms / 1e9, "efficiency_vs_single_gpu": ms_solo / (world * ms),
+                         "bitwise_equal_to_single_gpu": same}
+            ch.close()
+        out["value_tflops"] = out["fused_peer_store"]["tflops"]
+    else:
+        out["value_tflops"] = out["single_gpu"]["tflops"]
+    # parity spot check against NumPy on 4 columns of the result (the full product on the host takes ~10 s per product)
+    if rank == 0:
+        cols = [0, 1023, 2048, 4095]
+        Yc = [(pr[0].cpu().numpy() + 1j * pr[1].cpu().numpy()) for pr in planes]
+        v = Yc[0][:, cols]
+        for Y in Yc[1:]:
+            v = Y @ v
+        got = M_solo[0][:, cols].cpu().numpy() + 1j * M_solo[1][:, cols].cpu().numpy()
+        out["max_rel_err_vs_numpy_4_columns"] = float(np.abs(got - v).max() / np.abs(v).max())
+        if with_cpu:
+            t = _cpu_zgemm_worker(D)
+            out["cpu"] = {"seconds_per_complex_product": t, "tflops_real_equivalent": 8.0 * D ** 3 / t / 1e12, "cores": os.cpu_count(),
+                          "kind": "port", "sample": "one complex128 4096^3 product, numpy @ with all BLAS threads (transformations.py:850 on the host)"}
+            out["speedup_vs_cpu"] = out["value_tflops"] / out["cpu"]["tflops_real_equivalent"]
+    return out
+
+
+
 def run_gpu(args):
     import ctypes as C
 
@@ -482,7 +820,7 @@ def run_gpu(args):
 
     for t_ in (f_pin, g_pin, h_pin):
         t_.zero_()
-    stream_steps(4)
+    stream_steps(max(args.warmup, 3))
     barrier()
     e0.record(stream)
     stream_steps(args.steps)
@@ -516,7 +854,7 @@ def run_gpu(args):
 
     g_blocking = g_dev.clone()
     h_blocking = h_dev.clone()
-    dev_stream_steps(4)
+    dev_stream_steps(max(args.warmup, 3))
     barrier()
     launches0 = lib.otn_launch_count()
     e0.record(stream)
@@ -541,21 +879,33 @@ def run_gpu(args):
         barrier()
         gather_ms = max_over_ranks(e0.elapsed_time(e1))
 
-    # ---- TR iterations / s (unit U2) on the same batch ------------------------------------------------------------------
+    # ---- host-side ceiling of the end-to-end path: concurrent H2D + D2H of one step per rank, no kernels ---------------------
+    host_ceiling = host_ceiling_leg(torch, dist, world, x_pin, g_pin, barrier, max_over_ranks, max(5, args.steps // 5))
+
+    # ---- CPU pool for the legs that time the oracle beside the device (N = 1 only: rank 0 would compete with N-1 ranks) ---------
+    cpu_pool = None
+    if not args.no_cpu and world == 1:
+        os.sched_setaffinity(0, all_cpus)  # the CPU baseline gets every core of the box, not just the GPU's NUMA node
+        cpu_pool = CpuPool()
+
+    # ---- TR iterations / s (unit U2): kicked Trotter starts, device-resident and end to end, oracle on the same instances -------
     tr = None
     if not args.no_tr:
-        niter = 3
-        fit.tr_run(x_dev, niter=1)  # warm-up
-        barrier()
-        e0.record(stream)
-        _, rep = fit.tr_run(x_dev, niter=niter)
-        e1.record(stream)
-        barrier()
-        ms_tr = max_over_ranks(e0.elapsed_time(e1))
-        tr = {"iters_per_sec": world * BATCH * niter / (ms_tr * 1e-3), "unit": "TR iterations/s (all instances)", "niter": niter,
-              "n_cg_mean": float(rep["n_cg"].mean()), "hvp_total_rank0": int(rep["hvp_total"]), "ms_per_iter_batch": ms_tr / niter,
-              "accept_rate": float(rep["accepted"].mean())}
+        tr = tr_leg(torch, C, lib, _lib, fit, handle, stream, rank, world, barrier, max_over_ranks, e0, e1, cpu_pool, niter=4)
     fit.close()
+
+    # ---- configs 1 / 2: single-instance latency; config 4: the sharded sweep ------------------------------------------------------
+    latency = None
+    if not args.no_latency and rank == 0 and world == 1:
+        latency = latency_leg(torch, StiefelFit, local_rank, cpu_pool)
+    c4 = None
+    if not args.no_c4:
+        torch.cuda.empty_cache()
+        c4 = c4_leg(torch, dist, rank, world, local_rank, barrier, max_over_ranks, cpu_pool)
+    c5 = None
+    if not args.no_c5:
+        torch.cuda.empty_cache()
+        c5 = c5_leg(torch, dist, rank, world, local_rank, barrier, max_over_ranks, with_cpu=(not args.no_cpu and world == 1))
 
     # ---- same workload through the dense D x D formulation (what the reference executes; SURVEY 8d flop count) -----------
     dense_raw = None
@@ -621,9 +971,8 @@ def run_gpu(args):
                      "step_tflops_algorithmic": FLOPS_PER_TRIPLE * BATCH / (ms_d / d_steps * 1e-3) / 1e12}
 
     cpu = None
-    if not args.no_cpu and world == 1:     # the host-core baseline is timed at N = 1 only (rank 0 would compete with N-1 ranks)
-        os.sched_setaffinity(0, all_cpus)  # the CPU baseline gets every core of the box, not just the GPU's NUMA node
-        pool = CpuPool()
+    if cpu_pool is not None:
+        pool = cpu_pool
         try:
             v, total, wall = pool.run(64)
             tr_cpu, tr_cpu_dense = pool.run_tr(2)
@@ -633,10 +982,11 @@ def run_gpu(args):
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{total} instances of the same workload ({total // cores} per process x {cores} processes, 1 BLAS thread each, "
                          f"{wall:.1f} s wall)",
-               "tr_iters_per_sec": tr_cpu, "tr_iters_per_sec_dense_hessian": tr_cpu_dense,
-               "tr_note": "tr_iters_per_sec: one TR iteration per instance with the matrix-free Hessian operator (SURVEY 8d baseline "
-                          "(ii)); tr_iters_per_sec_dense_hessian: baseline (i), the reference's own dense Hessian (stiefel.py:498-529, "
-                          "11 880 jvp(grad) columns per iteration at this size), extrapolated from 4 timed columns per process"}
+               "tr_iters_per_sec_random_starts": tr_cpu, "tr_iters_per_sec_dense_hessian": tr_cpu_dense,
+               "tr_note": "tr_iters_per_sec_random_starts: one TR iteration per instance from RANDOM starts (tCG leaves after one product), "
+                          "matrix-free Hessian operator; the like-for-like TR comparison on kicked Trotter starts is `tr.cpu`. "
+                          "tr_iters_per_sec_dense_hessian: baseline (i), the reference's own dense Hessian (stiefel.py:498-529, 11 880 "
+                          "jvp(grad) columns per iteration at this size), extrapolated from 4 timed columns per process"}
 
     # `value`: device-resident throughput of the better of the two ways to drive the device path (both timed above over
     # args.steps steps); the other one stays visible in `device_resident`
@@ -645,12 +995,12 @@ def run_gpu(args):
                        "streamed": {"value": value_streamed, "ms_per_step": ms_dev_stream / args.steps, "gpu_launches": int(launches_stream),
                                     "mode": "otn_triple_submit / otn_triple_wait with device arrays (no copies), one step in flight "
                                             "ahead, two rotating output sets"}}
-    best = "streamed" if value_streamed > value else "blocking"
+    best = "streamed"      # the way a device-resident caller drives the path (no host synchronisation between steps); fixed choice
     value, ms_per_step, launches = (device_resident[best][k] for k in ("value", "ms_per_step", "gpu_launches"))
     device_resident["value_is"] = best
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config({"host_numa_binding": numa} if numa else None),
+            "data": "synthetic", "config": workload_config(), "host_numa_binding": numa,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps,
@@ -660,7 +1010,9 @@ def run_gpu(args):
                                     "mode": "one blocking otn_triple call per step"}},
             "gpu_launches": int(launches), "device_resident": device_resident,
             "roofline": roofline, "dense_formulation": dense_leg, "cpu_baseline": cpu, "tr": tr, "final_gather_ms": gather_ms,
-            "two_site_model": two_site}
+            "two_site_model": two_site, "latency": latency, "c4": c4, "c5": c5}
+    line["e2e"]["host_ceiling"] = host_ceiling
+    line["e2e"]["frac_of_host_ceiling"] = e2e_value / host_ceiling["u1_per_s_ceiling"]
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -677,8 +1029,13 @@ def main():
     ap.add_argument("--no-tr", action="store_true", help="skip the TR iterations/s leg")
     ap.add_argument("--no-dense", action="store_true", help="skip the dense-formulation comparison leg")
     ap.add_argument("--no-local", action="store_true", help="skip the 2-site-model (factored evaluation) leg")
-    ap.add_argument("--min-warm-s", type=float, default=0.5,
-                    help="keep warming up until this many seconds under load have passed (0 = exactly --warmup steps, for profilers)")
+    ap.add_argument("--no-latency", action="store_true", help="skip the config-1 / config-2 single-instance latency leg")
+    ap.add_argument("--no-c4", action="store_true", help="skip the config-4 sweep leg")
+    ap.add_argument("--no-c5", action="store_true", help="skip the config-5 row-sharded N=6 composition leg")
+    ap.add_argument("--min-warm-s", type=float, default=0.0,
+                    help="keep warming up until this many seconds under load have passed (default 0 = exactly max(--warmup, 3) steps)")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5"],
+                    help="c3 (default): the headline line with every leg; c4 / c5: only that configuration's leg as the line")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

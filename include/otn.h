@@ -143,6 +143,19 @@ int otn_gemm_rows(const double* A1, const double* B1, const double* A2, const do
  * otn_ipc_*     : allocate an IPC-shareable device buffer / export its 64-byte handle / map a peer's buffer / release. */
 int otn_gemm_rows_bcast(const double* A1, const double* B1, const double* A2, const double* B2, double* C, double* const* peers,
                         int npeer, int D, int row0, int rows, int transA, int transB, int device, void* stream);
+/* otn_gemm_rows_ex  : otn_gemm_rows_bcast with the residual epilogue of the batched path: with T != NULL the row window receives
+ *                     product - T and partial[tile] the squared norm of each output tile (otn_gemm_rows_tiles(D, rows) of them;
+ *                     frobenius_norm, optimization.py:56-61, fused into the last product of a composition).
+ * otn_peer_signal / otn_peer_wait : device-side ordering of a row-sharded product sequence, asynchronous on `stream`: after its
+ *                     product a rank writes `value` into slot `slot` of every peer's flag array (system-scope fence first), before
+ *                     the next product it waits until flags[0..n) (except `skip`, its own slot) are >= value.  Replaces a host
+ *                     synchronise + barrier per product. */
+int otn_gemm_rows_ex(const double* A1, const double* B1, const double* A2, const double* B2, double* C, double* const* peers,
+                     int npeer, int D, int row0, int rows, int transA, int transB, const double* T, double* partial, int device,
+                     void* stream);
+int otn_gemm_rows_tiles(int D, int rows);
+int otn_peer_signal(int* const* peer_flags, int npeer, int slot, int value, int device, void* stream);
+int otn_peer_wait(const int* flags, int n, int skip, int value, int device, void* stream);
 int otn_ipc_alloc(long long bytes, int device, void** ptr, unsigned char* handle64);
 int otn_ipc_open(const unsigned char* handle64, int device, void** ptr);
 int otn_ipc_close(void* ptr, int device);
@@ -159,6 +172,19 @@ int otn_expm(const double* A_re, const double* A_im, int D, double tau, double* 
  *                   SVD leaves the sign open: ortho2super(x) and every cost are identical, x itself only up to those signs.
  *                   x: [count][dim*K][dim]. */
 int otn_super2ortho(const double* superop, int count, int dim, int K, double* x, int device);
+/* ---- initial-point factory, random part (SURVEY 8f "next" #2) ----------------------------------------------------------------------
+ * Counter-based generator (Philox4x32-10; convention in csrc/extras.inl, restated in oracle/port.py): every number depends only
+ * on (seed of the instance, stream, element index), so a sweep draws the same starts however it is sharded.  `seeds` are HOST arrays.
+ * otn_random_normal  : out[count][per] standard normals (stream_id >= 0 selects an independent stream)
+ * otn_random_stiefel : x[count][m][n][p], each isometry the polar factor of a standard-normal matrix (Haar-distributed; the device
+ *                      counterpart of the host-side `qf(G)` starts of the reference-side studies)
+ * otn_kicked_starts  : out = retract(x0, kick * xi / |xi|), xi = project(x0, G) in the canonical norm summed over the m isometries of
+ *                      an instance -- "Trotter start + random tangent kick" (tau x rank x seed sweeps); project = stiefel.py:23-30,
+ *                      retract = polar_decomposition_rectangular, stiefel.py:323-330 */
+int otn_random_normal(const unsigned long long* seeds, int count, long long per, int stream_id, double* out, int device);
+int otn_random_stiefel(const unsigned long long* seeds, int count, int m, int n, int p, double* x, int device);
+int otn_kicked_starts(const double* x0, const unsigned long long* seeds, int count, int m, int n, int p, double kick, double* out,
+                      int device);
 /* otn_expm_batch : out[b] = exp(taus[b] * A) for b < count (tau sweeps of one generator: the Trotter layers exp(tau L),
  *                  exp(tau/2 L_odd), exp(tau L_even) of create_trotter_layers, transformations.py:387-402, for every tau of a
  *                  study in one batched launch sequence).  `taus` is a HOST array; out is [count][D][D] per plane. */

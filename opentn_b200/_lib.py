@@ -66,12 +66,20 @@ SIGNATURES = {
     "otn_gemm_rows": (C.c_int, [_dp, _dp, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "otn_gemm_rows_bcast": (C.c_int, [_dp, _dp, _dp, _dp, _dp, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.c_void_p]),
+    "otn_gemm_rows_ex": (C.c_int, [_dp, _dp, _dp, _dp, _dp, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   _dp, _dp, C.c_int, C.c_void_p]),
+    "otn_gemm_rows_tiles": (C.c_int, [C.c_int, C.c_int]),
+    "otn_peer_signal": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "otn_peer_wait": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "otn_ipc_alloc": (C.c_int, [C.c_longlong, C.c_int, C.POINTER(C.c_void_p), C.c_char_p]),
     "otn_ipc_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
     "otn_ipc_close": (C.c_int, [C.c_void_p, C.c_int]),
     "otn_ipc_free": (C.c_int, [C.c_void_p, C.c_int]),
     "otn_expm": (C.c_int, [_dp, _dp, C.c_int, C.c_double, _dp, _dp, C.c_int]),
     "otn_super2ortho": (C.c_int, [_dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int]),
+    "otn_random_normal": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_int, _dp, C.c_int]),
+    "otn_random_stiefel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int]),
+    "otn_kicked_starts": (C.c_int, [_dp, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _dp, C.c_int]),
     "otn_expm_batch": (C.c_int, [_dp, _dp, C.c_int, _dp, C.c_int, _dp, _dp, C.c_int]),
     "otn_liouvillian": (C.c_int, [_dp, _dp, C.c_int, C.c_int, C.c_int, _ip, _ip, _ip, C.c_int, _dp, _dp, C.c_int]),
     "otn_project": (C.c_int, [_dp, _dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int]),

@@ -82,6 +82,137 @@ extern "C" int otn_kraus2superop(const double* E_re, const double* E_im, int cou
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Initial-point factory, random part (SURVEY 8f "next" #2): counter-based normals, Haar-random isometries, kicked Trotter starts.
+// Seed convention (restated in oracle/port.py: philox_normal): element e of instance i draws
+//     (x0, x1, x2, x3) = Philox4x32-10(counter = (e_lo, e_hi, stream, 0), key = (seed_lo, seed_hi))
+//     u1 = (((x0 << 32 | x1) >> 11) + 0.5) * 2^-53,  u2 likewise from (x2, x3),   z = sqrt(-2 ln u1) cos(2 pi u2)
+// so every entry depends only on (seed, stream, e): any launch shape, any GPU count, any order gives the same numbers.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ void philox_round(unsigned& c0, unsigned& c1, unsigned& c2, unsigned& c3, unsigned k0, unsigned k1) {
+    const unsigned long long p0 = 0xD2511F53ull * c0, p1 = 0xCD9E8D57ull * c2;
+    const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0, n1 = (unsigned)p1, n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1, n3 = (unsigned)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+}
+
+__device__ __forceinline__ double philox_normal(unsigned long long seed, unsigned stream, unsigned long long e) {
+    unsigned c0 = (unsigned)e, c1 = (unsigned)(e >> 32), c2 = stream, c3 = 0u;
+    unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        philox_round(c0, c1, c2, c3, k0, k1);
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    const double u1 = ((double)((((unsigned long long)c0 << 32) | c1) >> 11) + 0.5) * 1.1102230246251565e-16;   // 2^-53
+    const double u2 = ((double)((((unsigned long long)c2 << 32) | c3) >> 11) + 0.5) * 1.1102230246251565e-16;
+    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
+__global__ void rng_normal_kernel(const unsigned long long* __restrict__ seeds, int count, long long per, unsigned stream,
+                                  double* __restrict__ out) {
+    const long long total = (long long)count * per;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long inst = i / per, e = i - inst * per;
+        out[i] = philox_normal(seeds[inst], stream, (unsigned long long)e);
+    }
+}
+
+// eta[inst][...] *= kick / sqrt(nrm2[inst])
+__global__ void scale_instances_kernel(double* __restrict__ eta, const double* __restrict__ nrm2, double kick, long long per, int count) {
+    const long long total = (long long)count * per;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+        eta[i] *= kick / sqrt(nrm2[i / per]);
+}
+
+static int rng_fill(const unsigned long long* seeds_host, int count, long long per, unsigned stream, double* out_dev, DevBuf& seedbuf) {
+    OTN_TRY(seedbuf.ensure((size_t)count * 8));
+    CUDA_TRY(cudaMemcpy(seedbuf.ptr, seeds_host, (size_t)count * 8, cudaMemcpyHostToDevice));
+    const long long total = (long long)count * per;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
+    rng_normal_kernel<<<blocks, 256>>>(seedbuf.as<unsigned long long>(), count, per, stream, out_dev);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+enum { OTN_RNG_STREAM_GENERIC = 0, OTN_RNG_STREAM_STIEFEL = 1, OTN_RNG_STREAM_KICK = 2 };
+
+extern "C" int otn_random_normal(const unsigned long long* seeds, int count, long long per, int stream_id, double* out, int device) {
+    if (!seeds || !out || count < 1 || per < 1 || stream_id < 0) return fail("bad argument");
+    OTN_TRY(use_device(device));
+    DeviceGuard dev_guard__(device);
+    Scratch& S = g_scratch[device];
+    void* od;
+    OTN_TRY(stage_out(out, (size_t)count * per * 8, S.o, &od));
+    OTN_TRY(rng_fill(seeds, count, per, (unsigned)stream_id, (double*)od, S.s));
+    OTN_TRY(finish_out(out, od, (size_t)count * per * 8, 0));
+    CUDA_TRY(cudaDeviceSynchronize());
+    return 0;
+}
+
+// x[count][m][n][p]: every isometry is the polar factor G (G^T G)^{-1/2} of a standard-normal n x p matrix G -- uniformly (Haar)
+// distributed on St(n, p), like the sign-fixed QR factor the reference-side benchmarks draw on the host (numpy qr of a Gaussian).
+extern "C" int otn_random_stiefel(const unsigned long long* seeds, int count, int m, int n, int p, double* x, int device) {
+    if (!seeds || !x || count < 1 || m < 1 || n < p || p < 1) return fail("bad argument");
+    if (p > ST_MAXP) return fail("p = %d > %d not supported", p, ST_MAXP);
+    OTN_TRY(use_device(device));
+    DeviceGuard dev_guard__(device);
+    Scratch& S = g_scratch[device];
+    const size_t np = (size_t)n * p, bytes = (size_t)count * m * np * 8;
+    void* od;
+    OTN_TRY(stage_out(x, bytes, S.o, &od));
+    OTN_TRY(S.a.ensure(bytes));
+    OTN_TRY(rng_fill(seeds, count, (long long)m * np, OTN_RNG_STREAM_STIEFEL, S.a.as<double>(), S.s));
+    const size_t sm = (np + 5 * (size_t)p * p) * 8;
+    OTN_TRY(set_smem(retract_kernel, sm));
+    retract_kernel<<<count * m, ST_THREADS, sm>>>(S.a.as<double>(), nullptr, (double*)od, n, p, 1, nullptr, nullptr);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    OTN_TRY(finish_out(x, od, bytes, 0));
+    CUDA_TRY(cudaDeviceSynchronize());
+    return 0;
+}
+
+// out[i] = retract(x0[i], kick * xi / ||xi||_canonical),  xi = P_{x0[i]}(G_i),  G_i standard normal from seeds[i]  (the kicked Trotter
+// starts of a seed sweep; host counterpart: opentn_b200.sweep.kicked_start).  x0, out: [count][m][n][p], host or device.
+extern "C" int otn_kicked_starts(const double* x0, const unsigned long long* seeds, int count, int m, int n, int p, double kick,
+                                 double* out, int device) {
+    if (!x0 || !seeds || !out || count < 1 || m < 1 || n < p || p < 1) return fail("bad argument");
+    if (p > ST_MAXP) return fail("p = %d > %d not supported", p, ST_MAXP);
+    if ((long long)count * m > 2000000000LL) return fail("too many isometries");
+    OTN_TRY(use_device(device));
+    DeviceGuard dev_guard__(device);
+    Scratch& S = g_scratch[device];
+    const size_t np = (size_t)n * p, pp = (size_t)p * p, per = (size_t)m * np, bytes = (size_t)count * per * 8;
+    const void* xd; void* od;
+    OTN_TRY(stage_in(x0, bytes, S.a, 0, &xd));
+    OTN_TRY(stage_out(out, bytes, S.o, &od));
+    OTN_TRY(S.b.ensure(bytes));                       // G
+    OTN_TRY(S.x1.ensure(bytes));                      // its tangent projection
+    OTN_TRY(S.c.ensure((size_t)count * 8));
+    double* gauss = S.b.as<double>();
+    double* eta = S.x1.as<double>();
+    OTN_TRY(rng_fill(seeds, count, (long long)per, OTN_RNG_STREAM_KICK, gauss, S.s));
+    const size_t sm_p = (2 * np + 2 * pp) * 8, sm_c = (3 * np + 2 * pp) * 8, sm_r = (np + 5 * pp) * 8;
+    OTN_TRY(set_smem(project_kernel, sm_p));
+    project_kernel<<<count * m, ST_THREADS, sm_p>>>((const double*)xd, gauss, eta, n, p, 0, 1.0, 1.0);
+    OTN_TRY(set_smem(cdot_kernel, sm_c));
+    cdot_kernel<<<count, ST_THREADS, sm_c>>>((const double*)xd, eta, eta, S.c.as<double>(), n, p, m, nullptr);
+    const int blocks = (int)std::min<long long>(((long long)count * per + 255) / 256, 148LL * 16);
+    scale_instances_kernel<<<blocks, 256>>>(eta, S.c.as<double>(), kick, (long long)per, count);
+    OTN_TRY(set_smem(retract_kernel, sm_r));
+    retract_kernel<<<count * m, ST_THREADS, sm_r>>>((const double*)xd, eta, (double*)od, n, p, 1, nullptr, nullptr);
+    g_launches += 4;
+    CUDA_TRY(cudaGetLastError());
+    OTN_TRY(finish_out(out, od, bytes, 0));
+    CUDA_TRY(cudaDeviceSynchronize());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // NCCL, bound at run time
 // ---------------------------------------------------------------------------------------------------------------------
 namespace {
@@ -256,6 +387,83 @@ extern "C" int otn_gather(otn_problem* const* shards, int nshards, int batch, do
     }
     return rc;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Row-sharded chain products (BASELINE config 5): device-side ordering between the ranks of a sharded product sequence.
+// Every rank stores the tiles of its row block into the result buffer of every peer (otn_gemm_rows_bcast).  What was a host
+// round trip per product (stream synchronise + barrier) is two tiny kernels on the same stream: after product k a rank raises
+// flag[k] in every peer's flag array (system-scope fence first, so its tiles are visible), and before product k+1 it spins until
+// all peers have raised theirs.  No host involvement between the products of a chain.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct PeerFlagPtrs { int* p[8]; };
+
+__global__ void peer_signal_kernel(PeerFlagPtrs peers, int npeer, int slot, int value) {
+    __threadfence_system();                        // the kernel before this one on the stream wrote the tiles
+    if ((int)threadIdx.x < npeer) {
+        volatile int* f = peers.p[threadIdx.x] + slot;
+        *f = value;
+    }
+    __threadfence_system();
+}
+
+__global__ void peer_wait_kernel(const volatile int* flags, int n, int skip, int value) {
+    if ((int)threadIdx.x < n && (int)threadIdx.x != skip)
+        while (flags[threadIdx.x] < value) __nanosleep(200);
+    __threadfence_system();
+}
+
+}  // namespace
+
+extern "C" int otn_peer_signal(int* const* peer_flags, int npeer, int slot, int value, int device, void* stream) {
+    if (npeer < 0 || npeer > 7 || (npeer > 0 && !peer_flags)) return fail("npeer must be in [0, 7]");
+    OTN_TRY(use_device(device));
+    DeviceGuard dev_guard__(device);
+    PeerFlagPtrs P{};
+    for (int q = 0; q < npeer; ++q) P.p[q] = peer_flags[q];
+    peer_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(P, npeer, slot, value);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int otn_peer_wait(const int* flags, int n, int skip, int value, int device, void* stream) {
+    if (!flags || n < 1 || n > 32) return fail("bad argument");
+    OTN_TRY(use_device(device));
+    DeviceGuard dev_guard__(device);
+    peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags, n, skip, value);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// otn_gemm_rows_bcast with the fused residual epilogue of the batched path: C = op(A1) op(B1) [+ ...] - T on the row window, and
+// partial[tile] = sum over the tile of (C - T)^2 (the caller adds the partials of all ranks in a fixed order: frobenius_norm,
+// optimization.py:56-61, without a separate pass over a D x D matrix).  T == NULL: plain product.
+extern "C" int otn_gemm_rows_ex(const double* A1, const double* B1, const double* A2, const double* B2, double* C,
+                                double* const* peers, int npeer, int D, int row0, int rows, int transA, int transB,
+                                const double* T, double* partial, int device, void* stream) {
+    if (!A1 || !B1 || !C || D < 1 || rows < 1 || row0 < 0 || row0 + rows > D) return fail("bad argument");
+    if ((A2 == nullptr) != (B2 == nullptr)) return fail("A2 and B2 must be given together");
+    if (transA && transB) return fail("A^T B^T is not supported");
+    if (npeer < 0 || npeer > 7 || (npeer > 0 && peers == nullptr)) return fail("npeer must be in [0, 7]");
+    if ((T == nullptr) != (partial == nullptr)) return fail("T and partial must be given together");
+    OTN_TRY(use_device(device));
+    DeviceGuard dev_guard__(device);
+    GemmParams p{};
+    p.A1 = A1; p.B1 = B1; p.A2 = A2; p.B2 = B2; p.C = C; p.D = D; p.row0 = row0; p.rows = rows; p.batch = 1;
+    p.npeer = npeer;
+    for (int q = 0; q < npeer; ++q) p.Cpeer[q] = peers[q];
+    p.epi = T ? EPI_RESID : EPI_NONE;
+    if (T) { p.E = T; p.sE = 0; p.e_index = nullptr; p.partial = partial; p.partial_stride = gemm_plan(D, rows, 1).tiles; }
+    ++g_launches;
+    CUDA_TRY(gemm_launch(p, transA != 0, transB != 0, (cudaStream_t)stream));
+    return 0;
+}
+
+// number of partial sums otn_gemm_rows_ex writes for a row window
+extern "C" int otn_gemm_rows_tiles(int D, int rows) { return gemm_plan(D, rows, 1).tiles; }
 
 // ---------------------------------------------------------------------------------------------------------------------
 #ifndef OTN_SOURCE_HASH

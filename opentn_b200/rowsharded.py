@@ -31,13 +31,21 @@ class _IpcMatrix:
         return torch.as_tensor(self, device=torch.device("cuda", self.device))
 
 
+class _RawBuffer:
+    """CUDA array interface over a raw device pointer."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3, "strides": None}
+
+
 class RowShardedChain:
-    def __init__(self, D: int, device=None, group=None, p2p: bool = False, nbuf: int = 4):
+    def __init__(self, D: int, device=None, group=None, p2p: bool = False, nbuf: int = 8, single: bool = False):
+        """`single=True`: ignore the process group -- this rank computes every row itself (the one-GPU baseline of a scaling run)."""
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
         self.group = group
-        if dist.is_available() and dist.is_initialized():
+        if not single and dist.is_available() and dist.is_initialized():
             self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         else:
             self.rank, self.world = 0, 1
@@ -77,30 +85,67 @@ class RowShardedChain:
                 k += 1
             self._peer_ptrs.append(arr)
         self._next = 0
+        # device-side ordering: one int per rank in an IPC-shared flag array; rank r raises slot r of every peer's array after each
+        # product (otn_peer_signal) and waits for all slots of its own array before the next one (otn_peer_wait)
+        self._flag_ptr = C.c_void_p()
+        fh = C.create_string_buffer(64)
+        check(self.lib.otn_ipc_alloc(256, self.device, C.byref(self._flag_ptr), fh))
+        self._flags_view = torch.as_tensor(_RawBuffer(self._flag_ptr.value, (64,), "<i4"), device=torch.device("cuda", self.device))
+        self._flags_view.zero_()
+        torch.cuda.synchronize()
+        allf = [None] * self.world
+        dist.all_gather_object(allf, bytes(fh.raw), group=self.group)
+        self._peer_flags = (C.c_void_p * 7)()
+        k = 0
+        for r in range(self.world):
+            if r == self.rank:
+                continue
+            p = C.c_void_p()
+            check(self.lib.otn_ipc_open(allf[r], self.device, C.byref(p)))
+            self._opened.append(p)
+            self._peer_flags[k] = p.value
+            k += 1
+        self._epoch = 0
         dist.barrier(group=self.group)
 
-    def _matmul_p2p(self, A, B, ta, tb, A2=None, B2=None):
-        torch, dist = self.torch, self.dist
-        i = self._next
+    def _launch_p2p(self, A, B, ta, tb, A2=None, B2=None):
+        """One product whose tiles are stored into the next ring buffer of every rank (no ordering yet)."""
+        torch = self.torch
+        out_index = self._next
         self._next = (self._next + 1) % len(self._bufs)
-        out = self._views[i]
-        st = torch.cuda.current_stream().cuda_stream
-        check(self.lib.otn_gemm_rows_bcast(A.data_ptr(), B.data_ptr(), None if A2 is None else A2.data_ptr(),
-                                           None if B2 is None else B2.data_ptr(), out.data_ptr(), self._peer_ptrs[i], self.world - 1,
-                                           self.D, self.row0, self.rows, int(ta), int(tb), self.device, C.c_void_p(st)))
+        out = self._views[out_index]
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        check(self.lib.otn_gemm_rows_ex(A.data_ptr(), B.data_ptr(), None if A2 is None else A2.data_ptr(),
+                                        None if B2 is None else B2.data_ptr(), out.data_ptr(), self._peer_ptrs[out_index], self.world - 1,
+                                        self.D, self.row0, self.rows, int(ta), int(tb), None, None, self.device, st))
         self.products += 1 if A2 is None else 2
-        torch.cuda.current_stream().synchronize()     # my tiles have landed in every peer ...
-        dist.barrier(group=self.group)                # ... and so have everybody else's in mine
+        return out
+
+    def _sync_p2p(self):
+        """Device-side hand-shake after one or more `_launch_p2p`: raise my flag in every peer, wait for theirs.  Asynchronous."""
+        st = C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+        self._epoch += 1
+        check(self.lib.otn_peer_signal(self._peer_flags, self.world - 1, self.rank, self._epoch, self.device, st))
+        check(self.lib.otn_peer_wait(self._flag_ptr, self.world, self.rank, self._epoch, self.device, st))
+
+    def _matmul_p2p(self, A, B, ta, tb, A2=None, B2=None):
+        """Product + all-gather in one kernel (peer stores), ordered against the other ranks on the device: nothing here blocks
+        the host.  The result lives in a ring buffer until `nbuf` further products have been issued."""
+        out = self._launch_p2p(A, B, ta, tb, A2, B2)
+        self._sync_p2p()
         return out
 
     def close(self):
         if getattr(self, "p2p", False):
+            self.torch.cuda.synchronize()
             self.dist.barrier(group=self.group)
             for p in self._opened:
                 self.lib.otn_ipc_close(p, self.device)
             self._views = []
             for b in self._bufs:
                 self.lib.otn_ipc_free(b.ptr, self.device)
+            self._flags_view = None
+            self.lib.otn_ipc_free(self._flag_ptr, self.device)
             self.p2p = False
 
     # ---- one row-sharded product ------------------------------------------------------------------------------------------
@@ -132,6 +177,12 @@ class RowShardedChain:
         Ar, Ai = A
         Br, Bi = B
         t = self.torch
+        if self.p2p and gather:
+            nAi = -Ai
+            Cr = self._launch_p2p(Ar, Br, False, False, nAi, Bi)
+            Ci = self._launch_p2p(Ar, Bi, False, False, Ai, Br)
+            self._sync_p2p()                      # one hand-shake for both planes
+            return Cr, Ci
         Cr = t.empty((self.D, self.D), dtype=t.float64, device=Ar.device)
         Ci = t.empty_like(Cr)
         nAi = -Ai
@@ -155,15 +206,31 @@ class RowShardedChain:
             P = self.matmul_complex(Y, P)
         return P
 
+    def _resid_rows(self, A, B, T_re):
+        """Rows of op(A) op(B) - T of this rank (left sharded, no exchange) and the sum of their squares: the residual / norm
+        epilogue fused into the product (EPI_RESID), no extra pass over the matrix."""
+        t = self.torch
+        out = t.empty((self.D, self.D), dtype=t.float64, device=A.device)
+        tiles = self.lib.otn_gemm_rows_tiles(self.D, self.rows)
+        partial = t.empty(tiles, dtype=t.float64, device=A.device)
+        st = C.c_void_p(t.cuda.current_stream().cuda_stream)
+        check(self.lib.otn_gemm_rows_ex(A.data_ptr(), B.data_ptr(), None, None, out.data_ptr(), None, 0, self.D, self.row0, self.rows,
+                                        0, 0, T_re.data_ptr(), partial.data_ptr(), self.device, st))
+        self.products += 1
+        return out, partial.sum()
+
     def cost(self, Ys, T_re, T_im=None):
-        """|| Ys[-1] ... Ys[0] - T ||_F with the last product left sharded: one scalar all-reduce instead of an all-gather."""
+        """|| Ys[-1] ... Ys[0] - T ||_F with the last product left sharded: its residual and squared norm come out of the GEMM
+        epilogue, and one scalar all-reduce replaces the all-gather."""
         t = self.torch
         P = Ys[0]
         for Y in Ys[1:-1]:
             P = self.matmul(Y, P)
-        M = self.matmul(Ys[-1], P, gather=False) if len(Ys) > 1 else P
         sl = slice(self.row0, self.row0 + self.rows)
-        s = t.sum((M[sl] - T_re[sl]) ** 2)
+        if len(Ys) > 1:
+            _, s = self._resid_rows(Ys[-1], P, T_re)
+        else:
+            s = t.sum((P[sl] - T_re[sl]) ** 2)
         if T_im is not None:
             s = s + t.sum(T_im[sl] ** 2)
         if self.world > 1:
@@ -175,6 +242,11 @@ class RowShardedChain:
         G_m = R / f;  W_l = G_l P_{l-1}^T;  G_{l-1} = Y_l^T G_l."""
         t = self.torch
         m = len(Ys)
+        if self.p2p and len(self._bufs) < 3 * (m - 1):
+            # every forward product and every cotangent is kept until the end: 3 (m - 1) ring buffers, or the ring wraps and a later
+            # product silently overwrites an earlier result that is still needed
+            raise ValueError(f"cost_and_layer_cotangents with {m} layers keeps {3 * (m - 1)} products alive: construct "
+                             f"RowShardedChain(..., nbuf={3 * (m - 1)}) or larger (have {len(self._bufs)})")
         P = [Ys[0]]
         for Y in Ys[1:]:
             P.append(self.matmul(Y, P[-1]))

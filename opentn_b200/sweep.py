@@ -40,45 +40,158 @@ def kicked_starts(xs0_stack, seeds, kick=1e-2):
     return polar_decomposition_rectangular(xs0_stack, eta * (kick / nrm)[:, None, None, None])
 
 
-def run_sweep(lindbladians, N, d, taus, ranks, seeds, n_steps=4, niter=10, device=0, rank=0, world=1, pbc=True, max_batch=1024,
-              gather=None):
-    """Returns {K: dict(tau_index, seed, f0, f_final, x0, x_final, status)} for the instances owned by `rank` (or, with
-    `gather` = a function like sharding.gather_instances, for all instances on every rank)."""
+def _seed_array(seeds):
+    return np.ascontiguousarray(np.asarray(seeds, dtype=np.uint64))
+
+
+def kicked_starts_device(xs0_stack, seeds, kick=1e-2, device=None):
+    """The same construction entirely on the device (otn_kicked_starts): the directions come from the counter-based generator of
+    the library (Philox4x32-10, one independent stream per seed; convention in include/otn.h) instead of numpy's PCG64, so nothing
+    is drawn in a host loop.  xs0_stack: numpy array or CUDA tensor (B, m, n, p); returns the same kind."""
+    from . import _lib
+    from ._lib import check, ptr
+    seeds = _seed_array(seeds)
+    cuda = hasattr(xs0_stack, "is_cuda") and xs0_stack.is_cuda
+    if cuda:
+        x0 = xs0_stack.contiguous()
+        import torch
+        out = torch.empty_like(x0)
+        dev = x0.device.index if device is None else device
+    else:
+        x0 = np.ascontiguousarray(xs0_stack, dtype=np.float64)
+        out = np.empty_like(x0)
+        dev = T._DEVICE if device is None else device
+    B, m, n, p = x0.shape
+    assert len(seeds) == B, "one seed per instance"
+    check(_lib.load().otn_kicked_starts(ptr(x0), seeds.ctypes.data, B, m, n, p, float(kick), ptr(out), dev))
+    return out
+
+
+def random_stiefel_device(seeds, m, n, p, device=None):
+    """Haar-random isometries (B, m, n, p) drawn on the device (otn_random_stiefel); numpy array out."""
+    from . import _lib
+    from ._lib import check, ptr
+    seeds = _seed_array(seeds)
+    out = np.empty((len(seeds), m, n, p))
+    check(_lib.load().otn_random_stiefel(seeds.ctypes.data, len(seeds), m, n, p, ptr(out), T._DEVICE if device is None else device))
+    return out
+
+
+def plan_cells(ranks, n_taus, world, rank):
+    """(K, tau index) cells of the sweep owned by `rank`: the K-major cell list cut into `world` contiguous, equally long pieces.
+    A rank therefore works on as few distinct isometry shapes as possible (one handle, one large batch per shape) instead of a
+    1/world slice of every shape -- small batches are launch-latency bound, large ones are not."""
+    cells = [(K, ti) for K in ranks for ti in range(n_taus)]
+    lo, hi = (len(cells) * rank) // world, (len(cells) * (rank + 1)) // world
+    return cells[lo:hi]
+
+
+def instance_seed(K, tau_index, seed):
+    """64-bit generator seed of instance (K, tau, seed): independent of how the sweep is sharded."""
+    return (int(K) << 48) | (int(tau_index) << 32) | (int(seed) & 0xFFFFFFFF)
+
+
+def run_sweep(lindbladians, N, d, taus, ranks, seeds, n_steps=4, niter=10, device=0, rank=0, world=1, pbc=True, max_batch=4096,
+              gather=False, fit=None, timings=None, kick=1e-2):
+    """tau x rank x seed sweep of 2-site trust-region fits (BASELINE config 4).  Returns {K: dict(tau_index, seed, f0, f_final,
+    x0, x_final, status)} for the instances of the cells owned by `rank` (`plan_cells`); with `gather=True` (inside an initialised
+    torch.distributed job) the final all-gather follows and every rank returns all instances of every K.
+
+    Everything between the Lindbladian and the final costs runs on the device: Liouvillian assembly (otn_liouvillian), one batched
+    expm over the tau grid (otn_expm_batch), Choi factorisation of the Trotter layers (otn_super2ortho), kicked starts from the
+    counter-based generator (otn_kicked_starts), the batched trust region (otn_tr_run).  `fit`: a StiefelFit to reuse (its targets
+    must be exp(tau L) for `taus`); `timings`: dict that receives 'setup_s' and 'solve_s' (host wall clock around synchronised
+    device work)."""
+    import time
+
     import torch
-    # set-up on the device: Liouvillian assembly (otn_liouvillian) and one batched expm over the tau grid (otn_expm_batch)
     T.set_device(device)
-    Lvec = T.create_2local_liouvillians(lindbladians, N, d, pbc=pbc, backend="cuda")[0]
-    targets = T.exp_operator_sweep(Lvec, taus)
+    dev = torch.device("cuda", device)
+    t0 = time.perf_counter()
+    own_fit = fit is None
+    if own_fit:
+        Lvec = T.create_2local_liouvillians(lindbladians, N, d, pbc=pbc, backend="cuda")[0]
+        targets = T.exp_operator_sweep(Lvec, taus)
+        fit = StiefelFit(targets, model="local", N=N, d=d, metric="canonical", max_batch=1, device=device)
+    cells = plan_cells(ranks, len(taus), world, rank)
+    # Trotter layers of every tau this rank needs (16 x 16 expm on the host: microseconds), factorised per K on the device
+    need_taus = sorted({ti for _, ti in cells})
+    layers = {ti: np.stack([np.asarray(x).real for x in get_general_trotter_local_ansatz(lindbladians, taus[ti], n_steps)]) for ti in need_taus}
+    groups = {}
+    for K, ti in cells:
+        groups.setdefault(K, []).append(ti)
+    seeds = list(seeds)
+    prepared = {}
+    for K, tis in groups.items():
+        m_layers = layers[tis[0]].shape[0]
+        flat = T.super2ortho_batch(np.concatenate([layers[ti] for ti in tis]), K)            # (len(tis) * m, 4K, 4)
+        starts = torch.from_numpy(flat.reshape(len(tis), m_layers, 4 * K, d * d)).to(dev)
+        tindex = np.repeat(np.asarray(tis, dtype=np.int32), len(seeds))
+        sd = np.array([instance_seed(K, ti, s) for ti in tis for s in seeds], dtype=np.uint64)
+        x0 = starts[torch.arange(len(tis), device=dev).repeat_interleave(len(seeds))].contiguous()
+        prepared[K] = (kicked_starts_device(x0, sd, kick), tindex, np.tile(np.asarray(seeds), len(tis)))
+    torch.cuda.synchronize(dev)
+    t1 = time.perf_counter()
     out = {}
-    for K in ranks:
-        # starting points: one batched device super2ortho over the Trotter layers of every tau (otn_super2ortho)
-        layers = [np.stack([np.asarray(x).real for x in get_general_trotter_local_ansatz(lindbladians, tau, n_steps)]) for tau in taus]
-        m_layers = layers[0].shape[0]
-        flat = T.super2ortho_batch(np.concatenate(layers), K)
-        starts = [flat[i * m_layers:(i + 1) * m_layers] for i in range(len(taus))]
-        inst = [(ti, s) for ti in range(len(taus)) for s in seeds]
-        mine = inst[rank::world]
-        if not mine:
-            continue
-        xs = kicked_starts(np.stack([starts[ti] for ti, _ in mine]), [s for _, s in mine])
-        tindex = np.array([ti for ti, _ in mine], dtype=np.int32)
-        xf = np.empty_like(xs)
-        f0 = np.empty(len(mine)); ff = np.empty(len(mine)); status = np.zeros(len(mine), dtype=np.int32)
-        for c0 in range(0, len(mine), max_batch):
-            sl = slice(c0, min(c0 + max_batch, len(mine)))
-            fit = StiefelFit(targets, model="local", N=N, d=d, metric="canonical", max_batch=sl.stop - sl.start, device=device)
+    for K, (xs, tindex, seed_arr) in prepared.items():
+        B = xs.shape[0]
+        xf = torch.empty_like(xs)
+        f0 = np.empty(B); ff = np.empty(B); status = np.zeros(B, dtype=np.int32)
+        for c0 in range(0, B, max_batch):
+            sl = slice(c0, min(c0 + max_batch, B))
             fit.set_target_index(tindex[sl])
-            xd = torch.from_numpy(xs[sl]).to(torch.device("cuda", device))
-            xe, rep = fit.tr_run(xd, niter=niter)
+            xe, rep = fit.tr_run(xs[sl], niter=niter)
             ff[sl] = fit.cost(xe).cpu().numpy()
             f0[sl] = rep["f_iter"][0]
             status[sl] = rep["status"]
-            xf[sl] = xe.cpu().numpy()
-            fit.close()
-        res = dict(tau_index=tindex, seed=np.array([s for _, s in mine]), f0=f0, f_final=ff, x0=xs, x_final=xf, status=status)
-        if gather is not None:
-            total = len(inst)
-            dev = torch.device("cuda", device)
-            res = {k: gather(torch.from_numpy(np.ascontiguousarray(v)).to(dev), total).cpu().numpy() for k, v in res.items()}
-        out[K] = res
+            xf[sl] = xe
+        out[K] = dict(tau_index=tindex, seed=seed_arr, f0=f0, f_final=ff, x0=xs, x_final=xf, status=status)
+    torch.cuda.synchronize(dev)
+    t2 = time.perf_counter()
+    if timings is not None:
+        timings["setup_s"], timings["solve_s"] = t1 - t0, t2 - t1
+    if own_fit:
+        fit.close()
+    res = {}
+    for K, r in out.items():
+        r = {k: (v if torch.is_tensor(v) else torch.from_numpy(np.ascontiguousarray(v)).to(dev)) for k, v in r.items()}
+        res[K] = r
+    if gather:
+        res = gather_groups(res, list(ranks), len(taus), len(seeds), world)
+    return {K: {k: v.cpu().numpy() for k, v in r.items()} for K, r in res.items()}
+
+
+def gather_groups(res, ranks, n_taus, n_seeds, world):
+    """Final all-gather of a cell-partitioned sweep (the one collective of the path): every rank contributes the K groups it owns;
+    on return every rank holds all instances of every K, ordered by (tau index, seed).  `res`: {K: {name: CUDA tensor}}."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or world == 1:
+        return res
+    some = next(iter(res.values()))
+    dev = some["f0"].device
+    out = {}
+    for K in ranks:
+        # which ranks hold cells of this K, and how many instances each
+        counts = [sum(1 for (kk, _) in plan_cells(ranks, n_taus, world, r) if kk == K) * n_seeds for r in range(world)]
+        cap = max(counts)
+        mine = res.get(K)
+        merged = {}
+        for name, like in some.items():
+            shape_tail = tuple(mine[name].shape[1:]) if mine is not None else tuple(_tail_shape(name, like, K, some))
+            pad = torch.zeros((cap,) + shape_tail, dtype=like.dtype, device=dev)
+            if mine is not None:
+                pad[: mine[name].shape[0]] = mine[name]
+            parts = [torch.empty_like(pad) for _ in range(world)]
+            dist.all_gather(parts, pad)
+            merged[name] = torch.cat([parts[r][: counts[r]] for r in range(world)])
+        out[K] = merged
     return out
+
+
+def _tail_shape(name, like, K, some):
+    """Trailing shape of array `name` for Kraus rank K given an example of another rank (isometries are (m, 4K, 4))."""
+    if like.dim() <= 1:
+        return ()
+    m, _, p = like.shape[1:]
+    return (m, p * K, p)

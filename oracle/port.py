@@ -839,3 +839,47 @@ def c3_instance(b, m=3, n=256, p=16):
     etas = [project(x, rng2.standard_normal((n, p))) for x in xs]
     nrm = np.sqrt(canonical_dot(xs, etas, etas))
     return xs, [e / nrm for e in etas]
+
+
+# --------------------------------------------------------------------------------------------------
+# counter-based random numbers of the device factory (csrc/extras.inl) restated in NumPy
+# --------------------------------------------------------------------------------------------------
+def philox4x32_10(c, k):
+    """Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11; Random123 constants) on arrays of
+    counters c (..., 4) and keys k (..., 2), dtype uint32 -> (..., 4) uint32."""
+    c = [np.asarray(c[..., i], dtype=np.uint64) for i in range(4)]
+    k0, k1 = np.asarray(k[..., 0], dtype=np.uint64), np.asarray(k[..., 1], dtype=np.uint64)
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(0xD2511F53) * c[0]
+        p1 = np.uint64(0xCD9E8D57) * c[2]
+        c = [(p1 >> np.uint64(32)) ^ c[1] ^ k0, p1 & mask, (p0 >> np.uint64(32)) ^ c[3] ^ k1, p0 & mask]
+        k0 = (k0 + np.uint64(0x9E3779B9)) & mask
+        k1 = (k1 + np.uint64(0xBB67AE85)) & mask
+    return np.stack(c, axis=-1).astype(np.uint32)
+
+
+def philox_normal(seed, count, stream=0):
+    """Standard normals e = 0..count-1 of one instance under the device convention: counter (e_lo, e_hi, stream, 0), key
+    (seed_lo, seed_hi); u = ((x_hi << 32 | x_lo) >> 11 + 0.5) 2^-53 from each half of the output; Box-Muller cosine branch."""
+    e = np.arange(count, dtype=np.uint64)
+    ctr = np.stack([e & np.uint64(0xFFFFFFFF), e >> np.uint64(32), np.full(count, stream, dtype=np.uint64),
+                    np.zeros(count, dtype=np.uint64)], axis=-1)
+    seed = np.uint64(seed)
+    key = np.broadcast_to(np.array([seed & np.uint64(0xFFFFFFFF), seed >> np.uint64(32)], dtype=np.uint64), (count, 2))
+    x = philox4x32_10(ctr, key).astype(np.uint64)
+    u1 = (((x[:, 0] << np.uint64(32)) | x[:, 1]) >> np.uint64(11)).astype(np.float64) + 0.5
+    u2 = (((x[:, 2] << np.uint64(32)) | x[:, 3]) >> np.uint64(11)).astype(np.float64) + 0.5
+    u1 *= 2.0 ** -53
+    u2 *= 2.0 ** -53
+    return np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+
+
+def kicked_start(xs0, seed, kick=1e-2, stream=2):
+    """Trotter start + random tangent kick of canonical norm `kick` (what otn_kicked_starts computes on the device)."""
+    xs0 = [np.asarray(x, dtype=np.float64) for x in xs0]
+    n, p = xs0[0].shape
+    g = philox_normal(seed, len(xs0) * n * p, stream).reshape(len(xs0), n, p)
+    etas = [project(x, gi) for x, gi in zip(xs0, g)]
+    nrm = np.sqrt(canonical_dot(xs0, etas, etas))
+    return retract_tangent(xs0, [kick * e / nrm for e in etas])

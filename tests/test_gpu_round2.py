@@ -227,3 +227,44 @@ def test_gather_two_gpus(P):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     _gather_case(P, 2)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# device generator / random starts
+# ---------------------------------------------------------------------------------------------------------------------
+def test_device_rng_matches_oracle(P):
+    from opentn_b200._lib import check, load
+    lib = load()
+    seeds = np.array([0, 1, 2 ** 40 + 17, 2 ** 63 + 5], dtype=np.uint64)
+    per = 1000
+    for stream in (0, 2):
+        out = np.empty((len(seeds), per))
+        check(lib.otn_random_normal(seeds.ctypes.data, len(seeds), per, stream, out.ctypes.data, 0))
+        for i, s in enumerate(seeds):
+            np.testing.assert_allclose(out[i], P.philox_normal(int(s), per, stream), rtol=0, atol=5e-15)
+    # a different launch shape draws the same numbers (counter-based): first 10 of a longer request
+    out2 = np.empty((1, 10))
+    check(lib.otn_random_normal(seeds[2:3].ctypes.data, 1, 10, 2, out2.ctypes.data, 0))
+    np.testing.assert_array_equal(out2[0], out[2, :10])
+
+
+def test_random_stiefel_and_kicked_starts(P):
+    from opentn_b200 import sweep
+    seeds = [11, 12, 13]
+    x = sweep.random_stiefel_device(seeds, 2, 32, 16)
+    assert x.shape == (3, 2, 32, 16)
+    np.testing.assert_allclose(np.swapaxes(x, -1, -2) @ x, np.broadcast_to(np.eye(16), (3, 2, 16, 16)), atol=1e-13)
+    import scipy.linalg
+    g = P.philox_normal(12, 2 * 32 * 16, 1).reshape(2, 32, 16)
+    np.testing.assert_allclose(x[1, 1], scipy.linalg.polar(g[1])[0], atol=1e-12)
+    # kicked starts: numpy in / numpy out and CUDA tensor in / out agree with the oracle's restatement
+    import torch
+    xk = sweep.kicked_starts_device(x, [5, 6, 7], kick=1e-2)
+    xk_t = sweep.kicked_starts_device(torch.from_numpy(x).cuda(), [5, 6, 7], kick=1e-2)
+    np.testing.assert_array_equal(xk, xk_t.cpu().numpy())
+    for b, s in enumerate([5, 6, 7]):
+        np.testing.assert_allclose(xk[b], np.array(P.kicked_start(list(x[b]), s, 1e-2)), rtol=0, atol=1e-12)
+    step = xk - x
+    xts = np.swapaxes(x, -1, -2) @ step
+    nrm = np.sqrt(np.sum(step * step, axis=(1, 2, 3)) - 0.5 * np.sum(xts * xts, axis=(1, 2, 3)))
+    np.testing.assert_allclose(nrm, 1e-2, rtol=1e-3)            # retraction is first-order exact

@@ -139,8 +139,12 @@ def test_sweep_driver_small(P):
         assert (r["f_final"] <= r["f0"] * (1 + 1e-12)).all()
         for i in (0, 5):
             tau = taus[r["tau_index"][i]]
-            # starting points come from the device factory (otn_super2ortho: Kraus operators up to sign) + a 1e-2 kick
+            # starting points come from the device factory (otn_super2ortho: Kraus operators up to sign) + a 1e-2 kick drawn by
+            # the device generator (otn_kicked_starts); the oracle restates both (Philox4x32-10 in NumPy)
             x0 = r["x0"][i]
+            layers_i = np.stack([np.asarray(x).real for x in P.get_general_trotter_local_ansatz([P.get_kitaev_nn_linbladian(1.0)], tau, 1)])
+            want = P.kicked_start(list(T.super2ortho_batch(layers_i, K)), sweep.instance_seed(K, r["tau_index"][i], r["seed"][i]))
+            np.testing.assert_allclose(x0, np.array(want), rtol=0, atol=1e-12)
             np.testing.assert_allclose(np.swapaxes(x0, -1, -2) @ x0, np.broadcast_to(np.eye(4), (x0.shape[0], 4, 4)), atol=1e-13)
             f = P.CostSpec(P.exp_operator_dt(Lvec, tau), "local", N, d)(list(x0))
             assert abs(f - r["f0"][i]) / f < 1e-10

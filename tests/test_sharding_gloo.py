@@ -64,3 +64,49 @@ def test_shard_sizes():
     assert sum(sharding.shard_sizes(1000, 8)) == 1000
     x = torch.arange(5.0)
     assert torch.equal(sharding.gather_instances(x, 5), x)       # no process group: identity
+
+
+# ---- config-4 sweep: cell partition + group-wise final gather (opentn_b200.sweep) ---------------------------------------------
+def _cells_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from opentn_b200 import sweep
+    ranks, n_taus, n_seeds, m = [2, 4, 8], 2, 3, 2                     # 6 cells: 3 per rank, K = 4 is split between the ranks
+    cells = sweep.plan_cells(ranks, n_taus, world, rank)
+    res = {}
+    for K in sorted({k for k, _ in cells}):
+        tis = [ti for k, ti in cells if k == K]
+        B = len(tis) * n_seeds
+        tindex = torch.tensor(np.repeat(tis, n_seeds), dtype=torch.int32)
+        seed = torch.tensor(np.tile(np.arange(n_seeds), len(tis)))
+        f0 = (1000.0 * K + 10.0 * tindex + seed).to(torch.float64)       # a value that identifies the instance
+        res[K] = dict(tau_index=tindex, seed=seed, f0=f0, x0=f0[:, None, None, None] * torch.ones(B, m, 4 * K, 4, dtype=torch.float64))
+    full = sweep.gather_groups(res, ranks, n_taus, n_seeds, world)
+    for K in ranks:
+        r = full[K]
+        want = torch.tensor([1000.0 * K + 10.0 * ti + s for ti in range(n_taus) for s in range(n_seeds)], dtype=torch.float64)
+        assert torch.equal(r["f0"], want), (K, r["f0"], want)
+        assert r["x0"].shape == (n_taus * n_seeds, m, 4 * K, 4) and torch.equal(r["x0"][:, 0, 0, 0], want)
+        assert r["tau_index"].tolist() == [ti for ti in range(n_taus) for _ in range(n_seeds)]
+    dist.barrier()
+    dist.destroy_process_group()
+    open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+
+
+def test_sweep_cells_gather_world2(tmp_path):
+    world = 2
+    mp.spawn(_cells_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
+
+
+def test_plan_cells_partition():
+    from opentn_b200 import sweep
+    ranks, n_taus = [2, 4, 8, 16], 4
+    for world in (1, 2, 4, 8):
+        owned = [sweep.plan_cells(ranks, n_taus, world, r) for r in range(world)]
+        assert sum(owned, []) == [(K, ti) for K in ranks for ti in range(n_taus)]        # a partition, K-major
+        assert {len(o) for o in owned} == {16 // world}
+        assert all(len({K for K, _ in o}) == max(1, 4 // world) for o in owned)           # as few shapes per rank as possible
+    assert sweep.instance_seed(16, 3, 255) != sweep.instance_seed(16, 2, 255)

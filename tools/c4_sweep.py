@@ -25,15 +25,22 @@ if world > 1:
     dist.barrier()
 torch.cuda.synchronize()
 t0 = time.perf_counter()
+sweep.run_sweep(Lnn, 4, 2, taus, ranks, [0, 1], n_steps=4, niter=1, device=lr, rank=rank, world=world, gather=world > 1)   # warm-up
+if world > 1:
+    dist.barrier()
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+tm = {}
 res = sweep.run_sweep(Lnn, 4, 2, taus, ranks, list(range(seeds_per_cell)), n_steps=4, niter=niter, device=lr, rank=rank, world=world,
-                      gather=sharding.gather_instances if world > 1 else None)
+                      gather=world > 1, timings=tm)
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
 wall = time.perf_counter() - t0
 if rank == 0:
     n_inst = sum(len(r["f0"]) for r in res.values())
-    print(f"world={world}: {n_inst} instances x {niter} TR iterations in {wall:.2f} s = {n_inst * niter / wall:.0f} TR iterations/s")
+    print(f"world={world}: {n_inst} instances x {niter} TR iterations in {wall:.3f} s = {n_inst * niter / wall:.0f} TR iterations/s "
+          f"(rank 0: set-up {tm['setup_s']:.3f} s, solve {tm['solve_s']:.3f} s)")
     for K, r in res.items():
         for ti, tau in enumerate(taus):
             sel = r["tau_index"] == ti
