@@ -92,7 +92,8 @@ def instance_seed(K, tau_index, seed):
 
 
 def run_sweep(lindbladians, N, d, taus, ranks, seeds, n_steps=4, niter=10, device=0, rank=0, world=1, pbc=True, max_batch=4096,
-              gather=False, fit=None, timings=None, kick=1e-2):
+              gather=False, fit=None, timings=None, kick=1e-2, to_host=True,
+              gather_names=("tau_index", "seed", "f0", "f_final", "status", "x_final")):
     """tau x rank x seed sweep of 2-site trust-region fits (BASELINE config 4).  Returns {K: dict(tau_index, seed, f0, f_final,
     x0, x_final, status)} for the instances of the cells owned by `rank` (`plan_cells`); with `gather=True` (inside an initialised
     torch.distributed job) the final all-gather follows and every rank returns all instances of every K.
@@ -101,7 +102,8 @@ def run_sweep(lindbladians, N, d, taus, ranks, seeds, n_steps=4, niter=10, devic
     expm over the tau grid (otn_expm_batch), Choi factorisation of the Trotter layers (otn_super2ortho), kicked starts from the
     counter-based generator (otn_kicked_starts), the batched trust region (otn_tr_run).  `fit`: a StiefelFit to reuse (its targets
     must be exp(tau L) for `taus`); `timings`: dict that receives 'setup_s' and 'solve_s' (host wall clock around synchronised
-    device work)."""
+    device work; 'gather_s' with `gather`).  `to_host=False` returns CUDA tensors instead of numpy arrays; `gather_names`: the arrays
+    the final all-gather carries (costs, status and final isometries by default; the starts `x0` stay on the rank that drew them)."""
     import time
 
     import torch
@@ -157,11 +159,17 @@ def run_sweep(lindbladians, N, d, taus, ranks, seeds, n_steps=4, niter=10, devic
         r = {k: (v if torch.is_tensor(v) else torch.from_numpy(np.ascontiguousarray(v)).to(dev)) for k, v in r.items()}
         res[K] = r
     if gather:
-        res = gather_groups(res, list(ranks), len(taus), len(seeds), world)
+        t3 = time.perf_counter()
+        res = gather_groups(res, list(ranks), len(taus), len(seeds), world, names=gather_names)
+        torch.cuda.synchronize(dev)
+        if timings is not None:
+            timings["gather_s"] = time.perf_counter() - t3
+    if not to_host:
+        return res
     return {K: {k: v.cpu().numpy() for k, v in r.items()} for K, r in res.items()}
 
 
-def gather_groups(res, ranks, n_taus, n_seeds, world):
+def gather_groups(res, ranks, n_taus, n_seeds, world, names=None):
     """Final all-gather of a cell-partitioned sweep (the one collective of the path): every rank contributes the K groups it owns;
     on return every rank holds all instances of every K, ordered by (tau index, seed).  `res`: {K: {name: CUDA tensor}}."""
     import torch
@@ -178,6 +186,8 @@ def gather_groups(res, ranks, n_taus, n_seeds, world):
         mine = res.get(K)
         merged = {}
         for name, like in some.items():
+            if names is not None and name not in names:
+                continue
             shape_tail = tuple(mine[name].shape[1:]) if mine is not None else tuple(_tail_shape(name, like, K, some))
             pad = torch.zeros((cap,) + shape_tail, dtype=like.dtype, device=dev)
             if mine is not None:
