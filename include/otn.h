@@ -55,8 +55,14 @@ int otn_create(otn_problem** out, int N, int d, int m, int K, int model, int met
  * superoperators are applied factor by factor to the columns of the running product, each CTA owning a tile of columns for the
  * whole forward / reverse / tangent evaluation (opentn_b200/csrc/factored.cuh): 2*16*D instead of 2*D^2 flops per column and
  * factor, and O(D * columns) instead of O(m D^2) memory per instance. */
-enum { OTN_FLAG_DENSE = 1, OTN_FLAG_BLOCKS = 2, OTN_FLAG_FACTORED = 4 };   /* none: factored where it applies, else blocks when
+enum { OTN_FLAG_DENSE = 1, OTN_FLAG_BLOCKS = 2, OTN_FLAG_FACTORED = 4, OTN_FLAG_COMPLEX = 8 };   /* none: factored where it applies, else blocks when
                                                                             * max_batch * D >= 4096 (enough work to fill the GPU) */
+/* OTN_FLAG_COMPLEX (full-sites model): COMPLEX isometries, x^H x = 1 -- the extension the reference marks "TODO: add back the conj"
+ * (stiefel.py:29,36,44,184,201,214,218,320).  Every isometry / tangent array of the handle's entry points (x, eta, rgrad, egrad,
+ * heta) is then interleaved complex128 [batch][m][n][p][2]; layers are Y = sum_k E_k (x) conj(E_k) (kraus2superop,
+ * transformations.py:170-180), the target is used as given (re and im planes), gradients are in the convention
+ * df = Re tr(Z^H dx), and ^T becomes ^H throughout stiefel.py:23-30, :398-409, :468-475.  otn_cost / otn_cost_grad / otn_triple /
+ * otn_hvp_cached / otn_triple_submit work; otn_model and otn_tr_run do not (host trust-region loop instead). */
 int otn_create_ex(otn_problem** out, int N, int d, int m, int K, int model, int metric, int max_batch, int n_targets,
                   const double* target_re, const double* target_im, int device, int flags);
 void otn_destroy(otn_problem* p);
@@ -209,6 +215,10 @@ int otn_project(const double* x, const double* z, int count, int n, int p, doubl
 int otn_rgrad_map(const double* x, const double* z, int count, int n, int p, double alpha0, double alpha1, double* out, int device);
 int otn_retract(const double* x, const double* eta, int count, int n, int p, double* out, int* status, int device);
 int otn_canonical_dot(const double* x, const double* a, const double* b, int batch, int m, int n, int p, double* out, int device);
+/* otn_retract_complex : polar factor of X + eta for complex isometries (interleaved complex128 [count][n][p][2]): polar retraction of
+ *                       stiefel.py:323-330 on the complex Stiefel manifold; status bit OTN_STATUS_NOT_SPD where the Newton-Schulz
+ *                       inverse square root of (X+eta)^H (X+eta) does not converge (||.. - 1|| >= 1) */
+int otn_retract_complex(const double* x, const double* eta, int count, int n, int p, double* out, int* status, int device);
 /* otn_connection : D_nu + X (eta^T nu + nu^T eta)/2 + ((a0-a1)/a0)(I - X X^T)(eta nu^T + nu eta^T) X   riemannian_connection
  *                  (stiefel.py:468-475), `count` isometries at once
  * otn_frobenius  : out[c] = || A_c - (B_re_c + i B_im_c) ||_F  (squared if asked; B_im may be NULL)   frobenius_norm

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libotn.so")
 MODEL_FULL, MODEL_LOCAL = 0, 1
 METRIC_EUCLIDEAN, METRIC_CANONICAL = 0, 1
 STATUS_NAN, STATUS_NOT_SPD, STATUS_NEG_DISCRIMINANT = 1, 2, 4
-FLAG_DENSE, FLAG_BLOCKS, FLAG_FACTORED = 1, 2, 4
+FLAG_DENSE, FLAG_BLOCKS, FLAG_FACTORED, FLAG_COMPLEX = 1, 2, 4, 8
 
 _dp = C.c_void_p  # double* (host or device)
 _ip = C.c_void_p  # int*
@@ -86,6 +86,7 @@ SIGNATURES = {
     "otn_rgrad_map": (C.c_int, [_dp, _dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _dp, C.c_int]),
     "otn_retract": (C.c_int, [_dp, _dp, C.c_int, C.c_int, C.c_int, _dp, _ip, C.c_int]),
     "otn_canonical_dot": (C.c_int, [_dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int]),
+    "otn_retract_complex": (C.c_int, [_dp, _dp, C.c_int, C.c_int, C.c_int, _dp, _ip, C.c_int]),
     "otn_connection": (C.c_int, [_dp, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _dp, C.c_int]),
     "otn_frobenius": (C.c_int, [_dp, _dp, _dp, C.c_int, C.c_longlong, C.c_int, _dp, C.c_int]),
     "otn_tr_default_params": (None, [C.POINTER(TrParams)]),

@@ -81,6 +81,30 @@ extern "C" int otn_kraus2superop(const double* E_re, const double* E_im, int cou
     return 0;
 }
 
+extern "C" int otn_retract_complex(const double* x, const double* eta, int count, int n, int p, double* out, int* status, int device) {
+    if (!x || !out || count < 1 || n < p || p < 1) return fail("bad argument");
+    if (p > ST_MAXP) return fail("p = %d > %d not supported", p, ST_MAXP);
+    OTN_TRY(use_device(device));
+    DeviceGuard dev_guard__(device);
+    Scratch& S = g_scratch[device];
+    const size_t bytes = (size_t)count * n * p * 16;
+    const void *xd, *ed; void *od, *sd;
+    OTN_TRY(stage_in(x, bytes, S.a, 0, &xd));
+    OTN_TRY(stage_in(eta, bytes, S.b, 0, &ed));
+    OTN_TRY(stage_out(out, bytes, S.o, &od));
+    OTN_TRY(stage_out(status, (size_t)count * 4, S.s, &sd));
+    if (sd) CUDA_TRY(cudaMemset(sd, 0, (size_t)count * 4));
+    const size_t sm = ((size_t)n * p + 3 * (size_t)p * p) * 16;
+    OTN_TRY(set_smem(cretract_kernel, sm));
+    cretract_kernel<<<count, ST_THREADS, sm>>>((const cplx*)xd, (const cplx*)ed, (cplx*)od, n, p, (int*)sd);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    OTN_TRY(finish_out(out, od, bytes, 0));
+    OTN_TRY(finish_out(status, sd, (size_t)count * 4, 0));
+    CUDA_TRY(cudaDeviceSynchronize());
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Initial-point factory, random part (SURVEY 8f "next" #2): counter-based normals, Haar-random isometries, kicked Trotter starts.
 // Seed convention (restated in oracle/port.py: philox_normal): element e of instance i draws

@@ -14,6 +14,7 @@
 
 #include "assemble.cuh"
 #include "chain_fused.cuh"
+#include "complex.cuh"
 #include "factored.cuh"
 #include "gemm_dmma.cuh"
 #include "stiefel.cuh"
@@ -254,6 +255,7 @@ struct otn_problem {
     double *Y = nullptr, *P = nullptr, *G = nullptr, *W = nullptr, *Yd = nullptr, *Pd = nullptr;
     double *Gd = nullptr;        // [2][SZ]
     double *Wd = nullptr;        // [SZ]; [m][SZ] with the fused chain (all tangent cotangents are formed before the pull-backs run)
+    bool cplx = false;           // complex isometries: x is interleaved complex128, the chain runs on the real embedding (complex.cuh)
     bool fused = false;          // per-instance fused chain kernel (chain_fused.cuh) instead of one batched GEMM launch per product
     long long wd_stride = 0;     // per-instance stride of Wd
     // local model: [m][q*q] and per-factor partials [m][nf][q*q]
@@ -382,16 +384,20 @@ extern "C" int otn_create_ex(otn_problem** out, int N, int d, int m, int K, int 
     otn_problem* h = new otn_problem();
     h->N = N; h->d = d; h->m = m; h->K = K; h->model = model; h->max_batch = max_batch; h->n_targets = n_targets; h->device = device;
     h->D = ipow(d, 2 * N);
-    h->SZ = (long long)h->D * h->D;
+    h->cplx = (flags & OTN_FLAG_COMPLEX) != 0;
+    if (h->cplx && model != OTN_MODEL_FULL) { delete h; return fail("complex isometries: full-sites model only (OTN_MODEL_FULL)"); }
+    if (h->cplx && (flags & (OTN_FLAG_BLOCKS | OTN_FLAG_FACTORED))) { delete h; return fail("OTN_FLAG_COMPLEX excludes OTN_FLAG_BLOCKS / OTN_FLAG_FACTORED"); }
+    const int chainD = h->cplx ? 2 * h->D : h->D;      // side of the matrices the chain multiplies (real embedding of complex ones)
+    h->SZ = (long long)chainD * chainD;
     h->q = ipow(d, 4);
     h->nf = N / 2;
     h->dim = (model == OTN_MODEL_FULL) ? ipow(d, N) : d * d;
-    h->nblk = 1; h->blkD[0] = h->D; h->blkOff[0] = 0;
+    h->nblk = 1; h->blkD[0] = chainD; h->blkOff[0] = 0;
     const int sdim = ipow(d, N);   // side of the doubled index (a,b): D = sdim^2
     // block-diagonal evaluation: 3.3x fewer chain flops, but two launches per product with fewer CTAs each -- for a handful of
     // small instances the path is launch/latency bound and the dense chain is faster (measured at D = 256, batch 1: 2.1 vs 3.2 ms
     // per U1), so AUTO picks blocks only when there is enough work to fill the GPU
-    const bool blocks_possible = (model == OTN_MODEL_FULL && (h->dim == 16 || h->dim == 8)) || (model == OTN_MODEL_LOCAL && sdim >= 8 && sdim <= 64);
+    const bool blocks_possible = !h->cplx && ((model == OTN_MODEL_FULL && (h->dim == 16 || h->dim == 8)) || (model == OTN_MODEL_LOCAL && sdim >= 8 && sdim <= 64));
     const bool enough_work = (long long)max_batch * h->D >= 4096;
     h->structured = blocks_possible && !(flags & OTN_FLAG_DENSE) && ((flags & OTN_FLAG_BLOCKS) || enough_work);
     const bool fact_possible = model == OTN_MODEL_LOCAL && d == 2 && (N == 4 || N == 6);
@@ -435,7 +441,7 @@ extern "C" int otn_create_ex(otn_problem** out, int N, int d, int m, int K, int 
         h->tiles += h->blkTiles[i];
     }
     if (h->factored) h->tiles = h->f_tiles;
-    h->p = h->dim; h->n = h->dim * K; h->np = h->n * h->p;
+    h->p = h->dim; h->n = h->dim * K; h->np = h->n * h->p * (h->cplx ? 2 : 1);   // doubles per isometry
     if (h->p > ST_MAXP) { const int pcols = h->p; delete h; return fail("isometry with p = %d columns > %d not supported", pcols, ST_MAXP); }
     if (model == OTN_MODEL_LOCAL && (h->nf > 4 || h->q > 255)) { delete h; return fail("local model supports N <= 8 and d <= 3"); }
     if ((long long)max_batch * m > 65535) { delete h; return fail("max_batch * m must be <= 65535 (split the batch)"); }
@@ -468,7 +474,23 @@ extern "C" int otn_create_ex(otn_problem** out, int N, int d, int m, int K, int 
         const size_t DD = (size_t)h->D * h->D;
         std::vector<double> im2(n_targets, 0.0), tre(DD), tsym(DD), tmp(DD), tblk(SZ);
         const int dm = ipow(d, N), Dn = h->D;
-        for (int t = 0; t < n_targets; ++t) {
+        for (int t = 0; t < n_targets && h->cplx; ++t) {
+            // emb(T) = [[Tr, -Ti], [Ti, Tr]]; no swap symmetrisation (complex layers are swap-Hermitian, not swap-symmetric)
+            std::vector<double> emb(SZ);
+            CREATE_TRY(cudaMemcpy(tre.data(), target_re + (size_t)t * DD, DD * 8, cudaMemcpyDefault));
+            std::fill(tmp.begin(), tmp.end(), 0.0);
+            if (target_im != nullptr) CREATE_TRY(cudaMemcpy(tmp.data(), target_im + (size_t)t * DD, DD * 8, cudaMemcpyDefault));
+            const size_t Dn2 = 2 * (size_t)Dn;
+            for (int r = 0; r < Dn; ++r)
+                for (int c = 0; c < Dn; ++c) {
+                    const double re = tre[(size_t)r * Dn + c], im = tmp[(size_t)r * Dn + c];
+                    emb[(size_t)r * Dn2 + c] = re; emb[(size_t)r * Dn2 + Dn + c] = -im;
+                    emb[((size_t)r + Dn) * Dn2 + c] = im; emb[((size_t)r + Dn) * Dn2 + Dn + c] = re;
+                }
+            CREATE_TRY(cudaMemcpy(h->T_re + (size_t)t * SZ, emb.data(), SZ * 8, cudaMemcpyHostToDevice));
+            im2[t] = 0.0;
+        }
+        for (int t = 0; t < n_targets && !h->cplx; ++t) {
             CREATE_TRY(cudaMemcpy(tre.data(), target_re + (size_t)t * DD, DD * 8, cudaMemcpyDefault));
             double s = 0.0;
             for (int r = 0; r < Dn; ++r) {
@@ -790,6 +812,20 @@ static int build_layers(otn_problem* h, const double* x, const double* eta, int 
     double* Ydout = (h->model == OTN_MODEL_FULL) ? h->Yd : h->Yld;
     const long long ostride = (h->model == OTN_MODEL_FULL) ? h->SZ : (long long)h->q * h->q;
     dim3 grid(h->dim, items);
+    if (h->cplx) {
+        const size_t smc = (size_t)h->np * 8 * (tangent ? 2 : 1);
+        const cplx* xc = reinterpret_cast<const cplx*>(x);
+        const cplx* ec = reinterpret_cast<const cplx*>(eta);
+#define CASM(TG, PR)                                                                                                 \
+    do {                                                                                                             \
+        OTN_TRY(set_smem(cassemble_emb_kernel<TG, PR>, smc));                                                        \
+        cassemble_emb_kernel<TG, PR><<<grid, 256, smc, h->stream>>>(xc, ec, h->Y, h->Yd, h->SZ, h->dim, h->K, active, h->m); \
+    } while (0)
+        if (tangent && primal) CASM(true, true); else if (tangent) CASM(true, false); else CASM(false, true);
+#undef CASM
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     if (h->structured && h->model == OTN_MODEL_FULL) {
         const int Kp = (h->K + 3) & ~3;
         const size_t sm = ((size_t)h->dim * Kp * h->dim * (tangent ? 2 : 1) + (size_t)8 * 2 * h->dim * (h->dim + 1)) * 8;
@@ -932,6 +968,24 @@ static int back_layer(otn_problem* h, int batch, const int* active, int l, const
     if (tangent) {
         if (l == 0) { Wdfull = h->Gd + (long long)h->tr.gd_final * SZ; sWd = 2 * SZ; }
         else { Wdfull = h->fused ? h->Wd + (long long)l * SZ : h->Wd; sWd = h->wd_stride; }
+    }
+    if (h->cplx) {
+        // zraw = A(W) x ;  tangent: zdraw = A(Wd) x + A(W) eta   (A = adjoint of the complex assembly, complex.cuh)
+        const size_t smc = ((size_t)h->np / 2 + 2 * (size_t)h->dim * h->dim) * 16;
+        OTN_TRY(set_smem(cback_assemble_kernel, smc));
+        dim3 gc(h->dim, batch);
+        const cplx* xc = reinterpret_cast<const cplx*>(x);
+        if (!tangent) {
+            cback_assemble_kernel<<<gc, 256, smc, bst>>>(Wfull, S, xc, reinterpret_cast<cplx*>(h->zraw), 0, h->dim, h->K, active, h->m, l);
+            if (primal_with_eta)
+                cback_assemble_kernel<<<gc, 256, smc, bst>>>(Wfull, S, reinterpret_cast<const cplx*>(eta), reinterpret_cast<cplx*>(h->zdraw), 0, h->dim, h->K, active, h->m, l);
+        } else {
+            cback_assemble_kernel<<<gc, 256, smc, bst>>>(Wdfull, sWd, xc, reinterpret_cast<cplx*>(h->zdraw), primal_with_eta ? 1 : 0, h->dim, h->K, active, h->m, l);
+            if (!primal_with_eta)
+                cback_assemble_kernel<<<gc, 256, smc, bst>>>(Wfull, S, reinterpret_cast<const cplx*>(eta), reinterpret_cast<cplx*>(h->zdraw), 1, h->dim, h->K, active, h->m, l);
+        }
+        CUDA_TRY(cudaGetLastError());
+        return 0;
     }
     const double* Wsup = Wfull; long long sW = S; const double* Wdsup = Wdfull; long long sWds = sWd; int nslices = 1;
     if (h->model == OTN_MODEL_LOCAL) {
@@ -1104,6 +1158,19 @@ static int riem_launch(otn_problem* h, int batch, const int* active, int tiles, 
                        double* f, double* rgrad, double* egrad, double* heta) {
     back_sync(h);                              // zraw / zdraw come from the back stream
     ProfScope ps(&h->prof, h->stream, CAT_RIEM, 0.0);
+    if (h->cplx) {
+        CRiemParams Pc{};
+        Pc.x = reinterpret_cast<const cplx*>(x); Pc.zraw = reinterpret_cast<const cplx*>(h->zraw);
+        Pc.eta = reinterpret_cast<const cplx*>(eta); Pc.zdraw = reinterpret_cast<const cplx*>(h->zdraw);
+        Pc.part_f = h->part_f; Pc.part_s = h->part_s; Pc.tiles = tiles; Pc.f_out = f;
+        Pc.rgrad = reinterpret_cast<cplx*>(rgrad); Pc.egrad = reinterpret_cast<cplx*>(egrad); Pc.heta = reinterpret_cast<cplx*>(heta);
+        Pc.n = h->n; Pc.p = h->p; Pc.m = h->m; Pc.alpha0 = h->alpha0; Pc.alpha1 = h->alpha1; Pc.active = active;
+        const size_t smc = ((hvp ? 4 : 2) * (size_t)h->n * h->p + 8 * (size_t)h->p * h->p) * 16;
+        if (!hvp) { OTN_TRY(set_smem(criem_kernel<false>, smc)); criem_kernel<false><<<batch * h->m, ST_THREADS, smc, h->stream>>>(Pc); }
+        else { OTN_TRY(set_smem(criem_kernel<true>, smc)); criem_kernel<true><<<batch * h->m, ST_THREADS, smc, h->stream>>>(Pc); }
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     RiemParams P{};
     P.x = x; P.zraw = h->zraw; P.eta = eta; P.zdraw = h->zdraw; P.part_f = h->part_f; P.part_s = h->part_s; P.im2 = h->im2;
     P.tindex = h->tindex; P.tiles = tiles; P.f_out = f; P.rgrad = rgrad; P.egrad = egrad; P.heta = heta;
@@ -1216,7 +1283,8 @@ int otn_dev_cost(otn_problem* h, const double* x, int batch, const int* active, 
     if (h->factored) { OTN_TRY(fact_eval(h, batch, active, FACT_COST, nullptr)); tiles = h->f_tiles; }
     else OTN_TRY(forward_chain(h, batch, active, false, &tiles));
     ProfScope ps(&h->prof, h->stream, CAT_OTHER, 0.0);
-    cost_from_partials_kernel<<<(batch + 127) / 128, 128, 0, h->stream>>>(h->part_f, tiles, h->im2, h->tindex, f, batch, active);
+    cost_from_partials_kernel<<<(batch + 127) / 128, 128, 0, h->stream>>>(h->part_f, tiles, h->im2, h->tindex, f, batch, active,
+                                                                          h->cplx ? 0.5 : 1.0);   // ||emb(R)||^2 = 2 ||R||^2
     CUDA_TRY(cudaGetLastError());
     h->cached_batch = 0;
     return 0;
@@ -1274,6 +1342,7 @@ static int keep_x(otn_problem* h, const double* xdev, int batch) {
 
 extern "C" int otn_model(otn_problem* h, const double* x, int batch, double* M) {
     OTN_TRY(check_batch(h, batch));
+    if (h->cplx) return fail("otn_model: not available for complex isometries (use otn_kraus2superop + otn_compose on (re, im) planes)");
     DeviceGuard dev_guard__(h->device);
     if (!x || !M) return fail("null argument");
     const void* xd; void* Md; int tiles;

@@ -172,13 +172,13 @@ __global__ void __launch_bounds__(ST_THREADS) riem_kernel(const RiemParams P) {
 
 // cost only: f[b] = sqrt(sum partial + im2)
 __global__ void cost_from_partials_kernel(const double* part_f, int tiles, const double* im2, const int* tindex, double* f,
-                                          int batch, const int* active) {
+                                          int batch, const int* active, double scale = 1.0) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= batch) return;
     if (active != nullptr && active[b] == 0) return;
     double s = 0.0;
     for (int t = 0; t < tiles; ++t) s += part_f[(long long)b * tiles + t];
-    f[b] = sqrt(s + im2[tindex ? tindex[b] : 0]);
+    f[b] = sqrt(scale * s + im2[tindex ? tindex[b] : 0]);
 }
 
 // out = a0inv * Z + c1 X X^T Z - c2 X Z^T X   (general metric; (1,1) => project for tangent-normal split)

@@ -89,6 +89,8 @@ extern "C" int otn_tr_run(otn_problem* h, double* x, int batch, const otn_tr_par
     OTN_TRY(check_batch(h, batch));
     DeviceGuard dev_guard__(h->device);
     if (!x) return fail("null argument");
+    if (h->cplx) return fail("otn_tr_run: the batched device solver is real-only; complex isometries run the host loop "
+                             "(opentn_b200.trust_region_rcopt over otn_cost_grad / otn_hvp_cached / otn_retract_complex)");
     otn_tr_params prm;
     if (prm_in) prm = *prm_in; else otn_tr_default_params(&prm);
     if (!(prm.rho_trust >= 0.0 && prm.rho_trust < 0.25)) return fail("need 0 <= rho_trust < 0.25");   // trust_region_rcopt.py:47

@@ -49,6 +49,25 @@ def _is_cuda_tensor(a) -> bool:
     return hasattr(a, "is_cuda") and bool(a.is_cuda)
 
 
+def _promote_pair(x, e):
+    """Isometries and directions of one call must agree on real vs complex: a real array next to a complex one is promoted."""
+    cx, ce = _is_cplx(x), _is_cplx(e)
+    if cx == ce:
+        return x, e
+    def up(a):
+        if isinstance(a, np.ndarray):
+            return np.ascontiguousarray(a, dtype=np.complex128)
+        import torch
+        return a.to(torch.complex128).contiguous()
+    return (x, up(e)) if cx else (up(x), e)
+
+
+def _is_cplx(a) -> bool:
+    if isinstance(a, np.ndarray):
+        return np.iscomplexobj(a)
+    return bool(getattr(a, "is_complex", lambda: False)())
+
+
 class _Handle:
     """Owns one otn_problem."""
 
@@ -122,8 +141,8 @@ class StiefelFit:
         self.last_report = None
 
     # ------------------------------------------------------------------ plumbing
-    def _handle(self, m, K, batch) -> _Handle:
-        key = (m, K)
+    def _handle(self, m, K, batch, cplx=False) -> _Handle:
+        key = (m, K, bool(cplx))
         h = self._handles.get(key)
         if h is None or h.max_batch < batch:
             if h is not None:
@@ -132,8 +151,9 @@ class StiefelFit:
             mid = metric_id(self.metric)
             h = _Handle(self.N, self.d, m, K, MODEL_LOCAL if self.model == "local" else MODEL_FULL, max(mid, 0),
                         cap, self._t_re, self._t_im, self.device,
-                        _lib.FLAG_FACTORED if self.factored else
-                        (0 if self.dense is None else (_lib.FLAG_DENSE if self.dense else _lib.FLAG_BLOCKS)))
+                        _lib.FLAG_COMPLEX if cplx else
+                        (_lib.FLAG_FACTORED if self.factored else
+                         (0 if self.dense is None else (_lib.FLAG_DENSE if self.dense else _lib.FLAG_BLOCKS))))
             if mid < 0:
                 check(h._lib.otn_set_metric_general(h.h, *metric_alphas(self.metric)))
             h.tindex_ver = 0
@@ -150,8 +170,10 @@ class StiefelFit:
         """-> (array-like [B, m, n, p] float64 contiguous, B, m, K, single, is_cuda)"""
         if _is_cuda_tensor(xs):
             import torch
-            if xs.dtype != torch.float64:
-                raise TypeError("device tensors must be float64")
+            if xs.dtype not in (torch.float64, torch.complex128):
+                raise TypeError("device tensors must be float64 (or complex128 for complex isometries)")
+            if xs.dtype == torch.complex128 and self.model != "full":
+                raise NotImplementedError("complex isometries are supported for the full-sites model only (model='full')")
             x = xs.contiguous()
             single = x.dim() == 3
             if single:
@@ -164,17 +186,23 @@ class StiefelFit:
             if isinstance(xs, (list, tuple)):
                 xs = np.stack([np.asarray(a) for a in xs])
             x = np.asarray(xs)
+            cplx = False
             if np.iscomplexobj(x):
                 if np.abs(x.imag).max() > 0:
-                    raise NotImplementedError("complex isometries are not supported (the reference's Stiefel path is real: "
-                                              "stiefel.py:29-44 'TODO: add back the conj')")
-                x = x.real
+                    # complex isometries (the extension the reference marks "TODO: add back the conj", stiefel.py:29-44): full-sites
+                    # model through the complex handle (OTN_FLAG_COMPLEX); arrays stay complex128
+                    if self.model != "full":
+                        raise NotImplementedError("complex isometries are supported for the full-sites model only (model='full'); "
+                                                  "the 2-site model's Kronecker embedding is real on the accelerated path")
+                    cplx = True
+                else:
+                    x = x.real
             single = x.ndim == 3
             if single:
                 x = x[None]
             if x.ndim != 4:
                 raise ValueError("x must be a list of m (n,p) isometries, or an array [m,n,p] / [B,m,n,p]")
-            x = as_f64(x)
+            x = np.ascontiguousarray(x, dtype=np.complex128) if cplx else as_f64(x)
             shape = x.shape
             cuda = False
         B, m, n, p = shape
@@ -197,7 +225,7 @@ class StiefelFit:
         h.tindex_len = h.max_batch if self._tindex is None else nbind
 
     @staticmethod
-    def _check_out(arr, shape, cuda, name):
+    def _check_out(arr, shape, cuda, name, cplx=False):
         """User-supplied output arrays go straight to the C ABI as raw addresses: refuse anything that is not a C-contiguous
         float64 array of exactly the expected shape and residency."""
         if _is_cuda_tensor(arr) != cuda:
@@ -206,18 +234,22 @@ class StiefelFit:
             raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(arr.shape)}")
         if cuda or hasattr(arr, "is_contiguous"):
             import torch
-            if arr.dtype != torch.float64 or not arr.is_contiguous():
-                raise TypeError(f"{name}: need a contiguous float64 tensor")
+            if arr.dtype != (torch.complex128 if cplx else torch.float64) or not arr.is_contiguous():
+                raise TypeError(f"{name}: need a contiguous {'complex128' if cplx else 'float64'} tensor")
         else:
-            if not isinstance(arr, np.ndarray) or arr.dtype != np.float64 or not arr.flags.c_contiguous or not arr.flags.writeable:
-                raise TypeError(f"{name}: need a writeable C-contiguous float64 numpy array")
+            if (not isinstance(arr, np.ndarray) or arr.dtype != (np.complex128 if cplx else np.float64) or not arr.flags.c_contiguous
+                    or not arr.flags.writeable):
+                raise TypeError(f"{name}: need a writeable C-contiguous {'complex128' if cplx else 'float64'} numpy array")
 
     @staticmethod
     def _empty_like(x, shape, cuda, dtype=np.float64):
+        """Uninitialised array living where `x` lives; dtype: np.float64 / np.int32, or "like" = the dtype of x (float64 or
+        complex128: gradients of complex isometries are complex)."""
         if cuda:
             import torch
-            return torch.empty(shape, dtype=torch.float64 if dtype == np.float64 else torch.int32, device=x.device)
-        return np.empty(shape, dtype=dtype)
+            tdt = x.dtype if dtype == "like" else (torch.float64 if dtype == np.float64 else torch.int32)
+            return torch.empty(shape, dtype=tdt, device=x.device)
+        return np.empty(shape, dtype=x.dtype if dtype == "like" else dtype)
 
     def set_metric(self, metric):
         """`metric`: 'euclidean', 'canonical' or a pair (alpha0, alpha1) (stiefel.py:411-426)."""
@@ -261,7 +293,7 @@ class StiefelFit:
 
     def model_matrix(self, xs):
         x, B, m, K, single, cuda = self._prep(xs)
-        h = self._handle(m, K, B)
+        h = self._handle(m, K, B, _is_cplx(x))
         M = self._empty_like(x, (B, self.D, self.D), cuda)
         self._cached = None
         check(h._lib.otn_model(h.h, ptr(x), B, ptr(M)))
@@ -269,7 +301,7 @@ class StiefelFit:
 
     def cost(self, xs):
         x, B, m, K, single, cuda = self._prep(xs)
-        h = self._handle(m, K, B)
+        h = self._handle(m, K, B, _is_cplx(x))
         self._bind(h, B)
         f = self._empty_like(x, (B,), cuda)
         self._cached = None
@@ -279,13 +311,13 @@ class StiefelFit:
     def cost_grad(self, xs, want_egrad=False):
         """-> (f, rgrad[, egrad]); gradients as (n,p) tangent matrices stacked like the input."""
         x, B, m, K, single, cuda = self._prep(xs)
-        h = self._handle(m, K, B)
+        h = self._handle(m, K, B, _is_cplx(x))
         self._bind(h, B)
         f = self._empty_like(x, (B,), cuda)
-        g = self._empty_like(x, tuple(x.shape), cuda)
-        e = self._empty_like(x, tuple(x.shape), cuda) if want_egrad else None
+        g = self._empty_like(x, tuple(x.shape), cuda, "like")
+        e = self._empty_like(x, tuple(x.shape), cuda, "like") if want_egrad else None
         check(h._lib.otn_cost_grad(h.h, ptr(x), B, ptr(f), ptr(g), ptr(e)))
-        self._cached = (h, B, object())
+        self._cached = (h, B, object(), _is_cplx(x))
         if single:
             return (float(f[0]), g[0], e[0]) if want_egrad else (float(f[0]), g[0])
         return (f, g, e) if want_egrad else (f, g)
@@ -296,19 +328,20 @@ class StiefelFit:
         e, B2, m2, K2, _, cuda2 = self._prep(etas)
         if (B, m, K, cuda) != (B2, m2, K2, cuda2):
             raise ValueError("xs and etas must have the same shape and residency")
-        h = self._handle(m, K, B)
+        x, e = _promote_pair(x, e)
+        h = self._handle(m, K, B, _is_cplx(x))
         self._bind(h, B)
         if out is None:
             f = self._empty_like(x, (B,), cuda)
-            g = self._empty_like(x, tuple(x.shape), cuda)
-            hv = self._empty_like(x, tuple(x.shape), cuda)
+            g = self._empty_like(x, tuple(x.shape), cuda, "like")
+            hv = self._empty_like(x, tuple(x.shape), cuda, "like")
         else:
             f, g, hv = out
             self._check_out(f, (B,), cuda, "out[0] (f)")
-            self._check_out(g, tuple(x.shape), cuda, "out[1] (rgrad)")
-            self._check_out(hv, tuple(x.shape), cuda, "out[2] (heta)")
+            self._check_out(g, tuple(x.shape), cuda, "out[1] (rgrad)", _is_cplx(x))
+            self._check_out(hv, tuple(x.shape), cuda, "out[2] (heta)", _is_cplx(x))
         check(h._lib.otn_triple(h.h, ptr(x), ptr(e), B, ptr(f), ptr(g), ptr(hv)))
-        self._cached = (h, B, object())
+        self._cached = (h, B, object(), _is_cplx(x))
         if single:
             return float(f[0]), g[0], hv[0]
         return f, g, hv
@@ -323,15 +356,16 @@ class StiefelFit:
         e, B2, m2, K2, _, cuda2 = self._prep(etas)
         if (B, m, K) != (B2, m2, K2):
             raise ValueError("xs and etas must have the same shape")
+        x, e = _promote_pair(x, e)
         outs_cuda = [bool(getattr(o, "is_cuda", False)) for o in out]
         if len({cuda, cuda2, *outs_cuda}) != 1:
             raise ValueError("triple_submit: the arrays of one submission must be all host or all device resident")
-        h = self._handle(m, K, B)
+        h = self._handle(m, K, B, _is_cplx(x))
         self._bind(h, B)
         f, g, hv = out
         self._check_out(f, (B,), cuda, "out[0] (f)")
-        self._check_out(g, tuple(x.shape), cuda, "out[1] (rgrad)")
-        self._check_out(hv, tuple(x.shape), cuda, "out[2] (heta)")
+        self._check_out(g, tuple(x.shape), cuda, "out[1] (rgrad)", _is_cplx(x))
+        self._check_out(hv, tuple(x.shape), cuda, "out[2] (heta)", _is_cplx(x))
         ticket = C.c_longlong(-1)
         check(h._lib.otn_triple_submit(h.h, ptr(x), ptr(e), B, ptr(f), ptr(g), ptr(hv), C.byref(ticket)))
         self._cached = None
@@ -358,11 +392,19 @@ class StiefelFit:
         cached = getattr(self, "_cached", None)
         if cached is None:
             raise OtnError("no primal cache: call cost_grad or triple first")
-        h, B, _ = cached
+        h, B = cached[0], cached[1]
         e, B2, m2, K2, single, cuda = self._prep(etas)
         if B2 != B:
             raise ValueError("batch differs from the cached primal pass")
-        hv = self._empty_like(e, tuple(e.shape), cuda)
+        if cached[3] and not _is_cplx(e):                       # primal pass was complex: a real direction is promoted
+            if isinstance(e, np.ndarray):
+                e = np.ascontiguousarray(e, dtype=np.complex128)
+            else:
+                import torch
+                e = e.to(torch.complex128).contiguous()
+        elif _is_cplx(e) and not cached[3]:
+            raise ValueError("complex direction for a real cached primal pass")
+        hv = self._empty_like(e, tuple(e.shape), cuda, "like")
         check(h._lib.otn_hvp_cached(h.h, ptr(e), B, ptr(hv)))
         return hv[0] if single else hv
 
@@ -374,7 +416,11 @@ class StiefelFit:
                tcg_reltol=1e-6, save_x=False, radius=None):
         """Batched device-side trust region.  Returns (x_final, report dict).  `xs` [B,m,n,p] (or one instance)."""
         x, B, m, K, single, cuda = self._prep(xs)
-        h = self._handle(m, K, B)
+        if _is_cplx(x):
+            raise NotImplementedError("the batched device solver is real-only; for complex isometries run "
+                                      "opentn_b200.trust_region_rcopt.riemannian_trust_region_optimize over "
+                                      "opentn_b200.complex_stiefel.closures(fit)")
+        h = self._handle(m, K, B, _is_cplx(x))
         self._bind(h, B)
         if cuda:
             xw = x.clone()
