@@ -268,3 +268,32 @@ def test_random_stiefel_and_kicked_starts(P):
     xts = np.swapaxes(x, -1, -2) @ step
     nrm = np.sqrt(np.sum(step * step, axis=(1, 2, 3)) - 0.5 * np.sum(xts * xts, axis=(1, 2, 3)))
     np.testing.assert_allclose(nrm, 1e-2, rtol=1e-3)            # retraction is first-order exact
+
+
+def test_super2ortho_fullsites_on_device(P, goldens):
+    """super2ortho (transformations.py:728-741) of the 256 x 256 full-sites Trotter layers on the device (block power iteration
+    for the dominant Choi eigenpairs): same superoperator and same cost as the host SVD route, isometry to rounding."""
+    from opentn_b200 import transformations as T
+    Lnn = P.get_kitaev_nn_linbladian(1.0)
+    layers = [np.asarray(x).real for x in P.create_trotter_layers(list(P.create_2local_liouvillians(Lnn, N, d, pbc=False)), tau=4)[1:]]
+    spec = P.CostSpec(P.kitaev_fullsites_target(), "full")
+    for K in (4, 16):
+        xs_dev = T.super2ortho_batch(np.stack(layers), K)
+        assert xs_dev.shape == (2, 16 * K, 16)
+        for l in range(2):
+            x_host = P.super2ortho(layers[l], rank=K)
+            np.testing.assert_allclose(xs_dev[l].T @ xs_dev[l], np.eye(16), atol=1e-12)
+            np.testing.assert_allclose(P.ortho2super(xs_dev[l]), P.ortho2super(x_host), atol=1e-12)
+            np.testing.assert_allclose(P.ortho2super(xs_dev[l]), layers[l], atol=1e-12)        # rank 4 is exact for these layers
+        f0 = spec([xs_dev[0], xs_dev[1], xs_dev[0]])
+        assert abs(f0 - float(goldens["known/fullsites_cost0"])) < 1e-11                       # notebook cell 6: 0.0959176702323516
+    # a genuinely truncated factorisation (random PSD Choi of full rank, keep 8): dominant eigenpairs vs numpy
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((256, 40))
+    C = A @ np.diag(np.logspace(0, -3, 40)) @ A.T
+    S = C.reshape(16, 16, 16, 16).transpose(0, 2, 1, 3).reshape(256, 256)                     # choi2super (an involution)
+    x = T.super2ortho_batch(S[None], 8)[0]
+    X = x.reshape(16, 8, 16).transpose(0, 2, 1).reshape(256, 8)                               # ortho2choi: factor with C ~ X X^T
+    w, v = np.linalg.eigh(C)
+    top = v[:, ::-1][:, :8] * np.sqrt(w[::-1][:8])
+    np.testing.assert_allclose(X @ X.T, top @ top.T, atol=1e-9 * w[-1])
