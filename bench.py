@@ -348,7 +348,7 @@ def c3_tr_start():
     super2ortho(rank=16) (transformations.py:728-741) on the device (otn_super2ortho).  Set-up, not timed."""
     import numpy as np
     from opentn_b200 import transformations as T
-    layers = T.create_trotter_layers(list(T.create_kitaev_liouvillians(N_SITES, D_LOC, 1.0, pbc=False)), tau=4.0)[1:]
+    layers = T.create_trotter_layers(list(T.create_kitaev_liouvillians(N_SITES, D_LOC, 1.0, pbc=False)[:3]), tau=4.0)[1:]
     xs = T.super2ortho_batch(np.stack([np.asarray(x).real for x in layers]), K_RANK)      # device factory (256 x 256 Choi matrices)
     return np.stack([xs[0], xs[1], xs[0]])
 
