@@ -673,14 +673,21 @@ __global__ void __launch_bounds__(RS_THREADS, 3) riem_stream_kernel(const RiemPa
 #pragma unroll 4
         for (int s = ks; s < ksteps; s += Cfg::KS) {
             const int ro = (s * 4 + t) * P;
-            const double xa0 = xg[ro + g], xa1 = xg[ro + 8 + g];
+            // The row index of an MMA output can be permuted freely: A-fragment row g of block i stands for Gram row 2g+i (not
+            // 8i+g), so both blocks come from ONE 16-byte load (ncu of the 8-byte version: L1/TEX 88 % busy, one wavefront per
+            // 128-byte line touched by every load instruction).
+            const double2 xa = *reinterpret_cast<const double2*>(xg + ro + 2 * g);
+            const double xa0 = xa.x, xa1 = xa.y;
             const double zb = zg[ro + jh * 8 + g];
             dmma884(acc[QXZ][0][0], acc[QXZ][0][1], xa0, zb);
             dmma884(acc[QXZ][1][0], acc[QXZ][1][1], xa1, zb);
             if (HVP) {
-                const double ea0 = eg[ro + g], ea1 = eg[ro + 8 + g];
+                const double2 ea = *reinterpret_cast<const double2*>(eg + ro + 2 * g);
+                const double ea0 = ea.x, ea1 = ea.y;
                 const double zdb = zdg[ro + jh * 8 + g];
-                const double xb = jh ? xa1 : xa0, eb = jh ? ea1 : ea0;
+                // B fragments of the x^T x / x^T eta Grams: column jh*8+g of the same row (separate 8-byte loads: the column
+                // index of the B operand is not permuted)
+                const double xb = xg[ro + jh * 8 + g], eb = eg[ro + jh * 8 + g];
                 dmma884(acc[QXX][0][0], acc[QXX][0][1], xa0, xb);
                 dmma884(acc[QXX][1][0], acc[QXX][1][1], xa1, xb);
                 dmma884(acc[QXZD][0][0], acc[QXZD][0][1], xa0, zdb);
@@ -695,7 +702,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) riem_stream_kernel(const RiemPa
         for (int q = 0; q < NQ; ++q)
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-                double* o = part + ((ks * NQ + q) * P + i * 8 + g) * P + jh * 8 + 2 * t;
+                double* o = part + ((ks * NQ + q) * P + 2 * g + i) * P + jh * 8 + 2 * t;
                 o[0] = acc[q][i][0]; o[1] = acc[q][i][1];
             }
     }
@@ -778,6 +785,20 @@ __global__ void __launch_bounds__(RS_THREADS, 3) riem_stream_kernel(const RiemPa
         }
     }
     __syncthreads();
+    // Stage 3 contracts over k = 4t + s in step s (vector loads of the inputs, below).  The coefficient matrices are its B operands:
+    // row k is re-filed at row (k & 3) * 4 + (k >> 2), so that step s reads row 4s + t -- the same conflict-free bank pattern
+    // (4t + g) as before the permutation.
+    {
+        const int pi = ((i & 3) << 2) + (i >> 2), pij = pi * LD + j;
+        double* perm = part + (HVP ? 8 : 1) * GS;            // free part of the partial-Gram area
+        const double v0 = Gn[ij];
+        double v1 = 0.0, v2 = 0.0, v3 = 0.0;
+        if (HVP) { v1 = Cx[ij]; v2 = Czp[ij]; v3 = Ce[ij]; }
+        __syncthreads();
+        perm[pij] = v0; Gn = perm;
+        if (HVP) { perm[GS + pij] = v1; perm[2 * GS + pij] = v2; perm[3 * GS + pij] = v3; Cx = perm + GS; Czp = perm + 2 * GS; Ce = perm + 3 * GS; }
+        __syncthreads();
+    }
 
     // ---- stage 3: outputs, 8 rows per warp and step ---------------------------------------------------------------------------
     const double sz = inv_f / a0;
@@ -795,19 +816,29 @@ __global__ void __launch_bounds__(RS_THREADS, 3) riem_stream_kernel(const RiemPa
                 accH[jb][0] = sz * zd2.x; accH[jb][1] = sz * zd2.y;
             }
         }
+        // The contraction index of an MMA can be permuted as long as A and B agree: in step s lane t takes k = 4t + s (not 4s + t),
+        // so the four steps read x[row][4t .. 4t+3] -- two 16-byte loads per array and row instead of four 8-byte ones.
+        double xr4[4], zr4[4], er4[4];
+        {
+            const double2 a0 = *reinterpret_cast<const double2*>(xg + row * P + 4 * t), a1 = *reinterpret_cast<const double2*>(xg + row * P + 4 * t + 2);
+            xr4[0] = a0.x; xr4[1] = a0.y; xr4[2] = a1.x; xr4[3] = a1.y;
+            if (HVP) {
+                const double2 b0 = *reinterpret_cast<const double2*>(zg + row * P + 4 * t), b1 = *reinterpret_cast<const double2*>(zg + row * P + 4 * t + 2);
+                const double2 c0 = *reinterpret_cast<const double2*>(eg + row * P + 4 * t), c1 = *reinterpret_cast<const double2*>(eg + row * P + 4 * t + 2);
+                zr4[0] = b0.x; zr4[1] = b0.y; zr4[2] = b1.x; zr4[3] = b1.y;
+                er4[0] = c0.x; er4[1] = c0.y; er4[2] = c1.x; er4[3] = c1.y;
+            }
+        }
 #pragma unroll
-        for (int i0 = 0; i0 < P; i0 += 4) {
-            const double xr = xg[row * P + i0 + t];
-            double zra = 0.0, ea = 0.0;
-            if (HVP) { zra = zg[row * P + i0 + t]; ea = eg[row * P + i0 + t]; }
+        for (int s = 0; s < 4; ++s) {
 #pragma unroll
             for (int jb = 0; jb < 2; ++jb) {
-                const int bo = (i0 + t) * LD + jb * 8 + g;
-                dmma884(accN[jb][0], accN[jb][1], xr, Gn[bo]);
+                const int bo = (4 * s + t) * LD + jb * 8 + g;          // row 4t + s of the matrix, re-filed (see above)
+                dmma884(accN[jb][0], accN[jb][1], xr4[s], Gn[bo]);
                 if (HVP) {
-                    dmma884(accH[jb][0], accH[jb][1], xr, Cx[bo]);
-                    dmma884(accH[jb][0], accH[jb][1], zra, Czp[bo]);
-                    dmma884(accH[jb][0], accH[jb][1], ea, Ce[bo]);
+                    dmma884(accH[jb][0], accH[jb][1], xr4[s], Cx[bo]);
+                    dmma884(accH[jb][0], accH[jb][1], zr4[s], Czp[bo]);
+                    dmma884(accH[jb][0], accH[jb][1], er4[s], Ce[bo]);
                 }
             }
         }

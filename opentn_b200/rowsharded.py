@@ -57,6 +57,7 @@ class RowShardedChain:
         self.device = torch.cuda.current_device() if device is None else device
         self.lib = _lib.load()
         self.products = 0
+        self._side = None
         self.p2p = bool(p2p) and self.world > 1
         if self.p2p:
             self._setup_p2p(nbuf)
@@ -178,16 +179,31 @@ class RowShardedChain:
         Br, Bi = B
         t = self.torch
         if self.p2p and gather:
+            # The two planes are independent launches: on two streams their tiles fill the SMs together.  One plane alone is
+            # rows/64 * D/64 tiles -- 512 at D = 4096 on 8 GPUs, 3.46 per SM, so a quarter of the SMs would run a 4th tile while
+            # the others idle (measured: 0.71 -> see profiles/README.md); both planes together are 6.9 per SM.
             nAi = -Ai
+            cur = t.cuda.current_stream()
+            if self._side is None:
+                self._side = t.cuda.Stream()
+            self._side.wait_stream(cur)
             Cr = self._launch_p2p(Ar, Br, False, False, nAi, Bi)
-            Ci = self._launch_p2p(Ar, Bi, False, False, Ai, Br)
+            with t.cuda.stream(self._side):
+                Ci = self._launch_p2p(Ar, Bi, False, False, Ai, Br)
+            cur.wait_stream(self._side)
             self._sync_p2p()                      # one hand-shake for both planes
             return Cr, Ci
         Cr = t.empty((self.D, self.D), dtype=t.float64, device=Ar.device)
         Ci = t.empty_like(Cr)
         nAi = -Ai
+        cur = t.cuda.current_stream()
+        if self._side is None:
+            self._side = t.cuda.Stream()
+        self._side.wait_stream(cur)
         self._rows(Ar, Br, Cr, A2=nAi, B2=Bi)
-        self._rows(Ar, Bi, Ci, A2=Ai, B2=Br)
+        with t.cuda.stream(self._side):
+            self._rows(Ar, Bi, Ci, A2=Ai, B2=Br)
+        cur.wait_stream(self._side)
         if gather:
             self._gather(Cr); self._gather(Ci)
         return Cr, Ci

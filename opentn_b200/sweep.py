@@ -184,17 +184,24 @@ def gather_groups(res, ranks, n_taus, n_seeds, world, names=None):
         counts = [sum(1 for (kk, _) in plan_cells(ranks, n_taus, world, r) if kk == K) * n_seeds for r in range(world)]
         cap = max(counts)
         mine = res.get(K)
-        merged = {}
-        for name, like in some.items():
-            if names is not None and name not in names:
-                continue
-            shape_tail = tuple(mine[name].shape[1:]) if mine is not None else tuple(_tail_shape(name, like, K, some))
-            pad = torch.zeros((cap,) + shape_tail, dtype=like.dtype, device=dev)
-            if mine is not None:
-                pad[: mine[name].shape[0]] = mine[name]
-            parts = [torch.empty_like(pad) for _ in range(world)]
-            dist.all_gather(parts, pad)
-            merged[name] = torch.cat([parts[r][: counts[r]] for r in range(world)])
+        # ONE collective per K group: every array of the group is packed, instance by instance, into a float64 row (integers are
+        # exactly representable: indices, 32-bit seeds, status bits)
+        fields = [(name, tuple(mine[name].shape[1:]) if mine is not None else tuple(_tail_shape(name, like, K, some)), like.dtype)
+                  for name, like in some.items() if names is None or name in names]
+        widths = [int(np.prod(shape)) if shape else 1 for _, shape, _ in fields]
+        pad = torch.zeros((cap, sum(widths)), dtype=torch.float64, device=dev)
+        if mine is not None:
+            o = 0
+            for (name, shape, _), w in zip(fields, widths):
+                pad[: mine[name].shape[0], o:o + w] = mine[name].reshape(mine[name].shape[0], w).to(torch.float64)
+                o += w
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad)                      # (list form: also available on gloo, which the CPU tests use)
+        full = torch.cat([parts[r][: counts[r]] for r in range(world)])
+        merged, o = {}, 0
+        for (name, shape, dtype), w in zip(fields, widths):
+            merged[name] = full[:, o:o + w].reshape((full.shape[0],) + shape).to(dtype).contiguous()
+            o += w
         out[K] = merged
     return out
 
