@@ -61,7 +61,7 @@ def test_argument_errors():
     fit = StiefelFit(np.eye(256), model="full", N=N, d=d, max_batch=2)
     x = np.linalg.qr(np.random.default_rng(0).standard_normal((2, 3, 32, 16)))[0]
     with pytest.raises(OtnError, match="no primal cache"):
-        fit._cached = (fit._handle(3, 2, 2), 2, None)
+        fit._cached = (fit._handle(3, 2, 2), 2, None, False)
         fit.hvp_cached(x)
     with pytest.raises(ValueError, match="does not fit model"):
         fit.cost(np.zeros((1, 3, 32, 8)))

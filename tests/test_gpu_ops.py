@@ -234,7 +234,7 @@ def test_super2ortho_device_argument_checks():
     from opentn_b200 import transformations as T
     from opentn_b200._lib import OtnError
     with pytest.raises(OtnError):
-        T.super2ortho_batch(np.zeros((1, 256, 256)), 4)                       # full-sites Choi (256 x 256) stays on the host
+        T.super2ortho_batch(np.zeros((1, 256, 256)), 17)                      # full-sites Choi (256 x 256): rank <= 16 on the device
     with pytest.raises(OtnError):
         T.super2ortho_batch(np.eye(16)[None], 17)
     with pytest.raises(NotImplementedError):
