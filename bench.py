@@ -553,15 +553,21 @@ def c4_leg(torch, dist, rank, world, device, barrier, max_over_ranks, cpu, seeds
     from opentn_b200 import sweep
     from opentn_b200 import transformations as T
     Lnn = [T.get_kitaev_nn_linbladian(1.0)]
-    sweep.run_sweep(Lnn, N_SITES, D_LOC, C4_TAUS, C4_RANKS, list(range(2)), n_steps=C4_STEPS, niter=1, device=device, rank=rank,
-                    world=world, gather=world > 1)                                   # warm-up: contexts, kernel attributes
+    t_fit = time.perf_counter()
+    fit = sweep.make_fit(Lnn, N_SITES, D_LOC, C4_TAUS, device=device)               # targets: device Liouvillian + batched expm
+    torch.cuda.synchronize()
+    t_fit = time.perf_counter() - t_fit
+    # warm-up with the full batch sizes: creates the handles (work buffers) of every isometry shape and configures the kernels
+    sweep.run_sweep(Lnn, N_SITES, D_LOC, C4_TAUS, C4_RANKS, list(range(seeds_per_cell)), n_steps=C4_STEPS, niter=1, device=device,
+                    rank=rank, world=world, gather=world > 1, fit=fit, to_host=False)
     barrier()
     tm = {}
     t0 = time.perf_counter()
     res = sweep.run_sweep(Lnn, N_SITES, D_LOC, C4_TAUS, C4_RANKS, list(range(seeds_per_cell)), n_steps=C4_STEPS, niter=niter,
-                          device=device, rank=rank, world=world, gather=world > 1, timings=tm, to_host=False)
+                          device=device, rank=rank, world=world, gather=world > 1, timings=tm, to_host=False, fit=fit)
     torch.cuda.synchronize()
     wall = max_over_ranks(time.perf_counter() - t0)
+    fit.close()
     setup_s, solve_s, gather_s = (max_over_ranks(tm.get(k, 0.0)) for k in ("setup_s", "solve_s", "gather_s"))
     barrier()
     n_inst = len(C4_TAUS) * len(C4_RANKS) * seeds_per_cell
@@ -575,7 +581,10 @@ def c4_leg(torch, dist, rank, world, device, barrier, max_over_ranks, cpu, seeds
            "setup_s": setup_s, "solve_s": solve_s, "gather_s": gather_s,
            "instances_returned_rank0": got, "improved_fraction": improved,
            "status_nonzero": int(sum((r["status"] != 0).sum() for r in res.values())),
-           "partition": "contiguous pieces of the K-major (K, tau) cell list per rank; one all-gather per K group at the end"}
+           "target_setup_s": t_fit,
+           "partition": "K-major (K, tau) cell list dealt to the ranks in a snake (cheap and expensive cells paired); one packed "
+                        "all-gather per K group at the end; handles created by a warm-up sweep (not timed), targets by make_fit "
+                        "(target_setup_s, not in wall_s)"}
     if cpu is not None and world == 1:
         picks = [(C4_RANKS[c % 4], (c // 4) % 4, c % seeds_per_cell) for c in range(cpu.cores)]     # (K, tau index, seed) cycling
         jobs, dev_f0 = [], []
@@ -946,15 +955,17 @@ def run_gpu(args):
         pass
     peak_source = ("cuBLAS DGEMM 8192^3 via torch.matmul, best of 3, measured in this run (MEASURED_PEAKS.json has no FP64 figure; "
                    "DMMA issue-rate ceiling 148 SM x 128 flop/clk x 1.965 GHz = 37.2 TFLOP/s)")
-    roofline = {"bound": "tensor", "kernel": "gemm_dmma_kernel (FP64 DMMA.8x8x4), block-diagonal chain: one 144^3 (48x48 tiles) and one "
-                                             "128^3 (64x64 tiles) product per chain product",
-                "peak": peak_tf, "unit": "TFLOP/s", "traffic": 4.84e8,
-                "traffic_note": "dram read+write of one single-product launch of the 144-block kernel over 1024 instances, ncu --set "
-                                "full (profiles/ncu_struct_r01.txt: 340 MB + 144 MB); algorithmic 3*144^2*8*1024 = 5.10e8 B (the zero "
-                                "padding is partly never written); the 128-block launch: 372 MB vs 4.03e8 B",
+    roofline = {"bound": "tensor", "kernel": "chain_fused_kernel<144,72,24,4> + chain_fused_kernel<128,64,32,4> (FP64 DMMA.8x8x4): one CTA per "
+                                             "instance and diagonal block runs all 18 chain products of a U1 (csrc/chain_fused.cuh); one launch per block and step",
+                "peak": peak_tf, "unit": "TFLOP/s", "traffic": 6.65e9,
+                "traffic_note": "dram read+write of one launch of the 144-block kernel over 1024 instances, ncu --set full "
+                                "(profiles/ncu_step_r02.txt: 4.64 GB + 2.01 GB; the 128-block launch: 3.14 + 1.58 GB).  Operand bytes of the 18 "
+                                "products counted once per product (36 reads + 12 writes of 144^2*8 B per instance) = 8.15e9 B: the "
+                                "re-reads of intermediates partly hit L2; the kernel is tensor-pipe bound (89 % active, DRAM 25 %)",
                 "peak_source": peak_source, "peak_committed_r01": peak_file}
     roofline.update(roofline_of(pms, pln, pfl, ms_prof, args.steps))
-    roofline["note"] = ("`achieved` counts EXECUTED flops of the block-diagonal evaluation (2*(144*144*136 + 128*128*120) per product: "
+    roofline["note"] = ("launches_timed counts fork..join groups (both blocks' launches of a step run concurrently on two streams and are timed as one group). "
+                        "`achieved` counts EXECUTED flops of the block-diagonal evaluation (2*(144*144*136 + 128*128*120) per product: "
                         "output tiles are zero-padded to 144 / 128, the contraction stops at 136 / 120; 2*(136^3+120^3) useful). Dense-equivalent rate (SURVEY 8d algorithmic count, 2*256^3 per product) is "
                         "`step_tflops_dense_equivalent`; the dense formulation itself is measured in `dense_formulation`.")
     roofline["step_tflops_dense_equivalent"] = FLOPS_PER_TRIPLE * BATCH / (ms_per_step * 1e-3) / 1e12

@@ -78,12 +78,24 @@ def random_stiefel_device(seeds, m, n, p, device=None):
 
 
 def plan_cells(ranks, n_taus, world, rank):
-    """(K, tau index) cells of the sweep owned by `rank`: the K-major cell list cut into `world` contiguous, equally long pieces.
-    A rank therefore works on as few distinct isometry shapes as possible (one handle, one large batch per shape) instead of a
-    1/world slice of every shape -- small batches are launch-latency bound, large ones are not."""
+    """(K, tau index) cells of the sweep owned by `rank`.  The K-major cell list is dealt out in a snake (0, 1, .., w-1, w-1, .., 1,
+    0, 0, 1, ..): every rank gets the same number of cells, and cheap cells (small K, i.e. small isometries) are paired with
+    expensive ones, so the ranks finish together.  Within a rank, cells of the same K form one batch (one handle per shape)."""
     cells = [(K, ti) for K in ranks for ti in range(n_taus)]
-    lo, hi = (len(cells) * rank) // world, (len(cells) * (rank + 1)) // world
-    return cells[lo:hi]
+    mine = []
+    for i, cell in enumerate(cells):
+        j = i % (2 * world)
+        if (j if j < world else 2 * world - 1 - j) == rank:
+            mine.append(cell)
+    return mine
+
+
+def make_fit(lindbladians, N, d, taus, device=0, pbc=True):
+    """The cost object of a sweep: targets exp(tau L) for every tau (device Liouvillian assembly + one batched expm), one handle per
+    isometry shape created on first use.  Reuse it across `run_sweep` calls to keep the handles (work buffers) alive."""
+    T.set_device(device)
+    Lvec = T.create_2local_liouvillians(lindbladians, N, d, pbc=pbc, backend="cuda")[0]
+    return StiefelFit(T.exp_operator_sweep(Lvec, taus), model="local", N=N, d=d, metric="canonical", max_batch=1, device=device)
 
 
 def instance_seed(K, tau_index, seed):
@@ -112,9 +124,7 @@ def run_sweep(lindbladians, N, d, taus, ranks, seeds, n_steps=4, niter=10, devic
     t0 = time.perf_counter()
     own_fit = fit is None
     if own_fit:
-        Lvec = T.create_2local_liouvillians(lindbladians, N, d, pbc=pbc, backend="cuda")[0]
-        targets = T.exp_operator_sweep(Lvec, taus)
-        fit = StiefelFit(targets, model="local", N=N, d=d, metric="canonical", max_batch=1, device=device)
+        fit = make_fit(lindbladians, N, d, taus, device=device, pbc=pbc)
     cells = plan_cells(ranks, len(taus), world, rank)
     # Trotter layers of every tau this rank needs (16 x 16 expm on the host: microseconds), factorised per K on the device
     need_taus = sorted({ti for _, ti in cells})
@@ -202,6 +212,10 @@ def gather_groups(res, ranks, n_taus, n_seeds, world, names=None):
         for (name, shape, dtype), w in zip(fields, widths):
             merged[name] = full[:, o:o + w].reshape((full.shape[0],) + shape).to(dtype).contiguous()
             o += w
+        if "tau_index" in merged and "seed" in merged:        # canonical order whatever the partition: by (tau index, seed)
+            key = merged["tau_index"].to(torch.int64) * (1 << 32) + merged["seed"].to(torch.int64)
+            order = torch.argsort(key)
+            merged = {name: v[order] for name, v in merged.items()}
         out[K] = merged
     return out
 

@@ -73,7 +73,7 @@ def _cells_worker(rank, world, port, out_dir):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from opentn_b200 import sweep
-    ranks, n_taus, n_seeds, m = [2, 4, 8], 2, 3, 2                     # 6 cells: 3 per rank, K = 4 is split between the ranks
+    ranks, n_taus, n_seeds, m = [2, 4, 8], 2, 3, 2                     # 6 cells: 3 per rank, every K is split between the ranks
     cells = sweep.plan_cells(ranks, n_taus, world, rank)
     res = {}
     for K in sorted({k for k, _ in cells}):
@@ -106,7 +106,8 @@ def test_plan_cells_partition():
     ranks, n_taus = [2, 4, 8, 16], 4
     for world in (1, 2, 4, 8):
         owned = [sweep.plan_cells(ranks, n_taus, world, r) for r in range(world)]
-        assert sum(owned, []) == [(K, ti) for K in ranks for ti in range(n_taus)]        # a partition, K-major
+        assert sorted(sum(owned, [])) == sorted((K, ti) for K in ranks for ti in range(n_taus))       # a partition
         assert {len(o) for o in owned} == {16 // world}
-        assert all(len({K for K, _ in o}) == max(1, 4 // world) for o in owned)           # as few shapes per rank as possible
+        if world > 1:      # snake deal: every rank's cells pair small isometries with large ones
+            assert all(min(K for K, _ in o) <= 4 and max(K for K, _ in o) >= 8 for o in owned)
     assert sweep.instance_seed(16, 3, 255) != sweep.instance_seed(16, 2, 255)
