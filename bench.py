@@ -705,6 +705,40 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = _lib.load()
 
+    if args.workload in ("c4", "c5"):           # only that configuration's leg, as the line
+        def barrier_():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        def max_over_ranks_(v):
+            if world == 1:
+                return v
+            t = torch.tensor([v], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        cpu_pool = CpuPool() if (not args.no_cpu and world == 1) else None
+        try:
+            if args.workload == "c4":
+                leg = c4_leg(torch, dist, rank, world, local_rank, barrier_, max_over_ranks_, cpu_pool)
+                line = {"metric": "trust-region fits/sec (config 4: tau x rank x seed sweep, 4096 fits x 5 iterations)", "value": leg["fits_per_sec"],
+                        "unit": "fits/s", "scaling": "strong", "ms_per_step": 1e3 * leg["wall_s"]}
+            else:
+                leg = c5_leg(torch, dist, rank, world, local_rank, barrier_, max_over_ranks_, with_cpu=cpu_pool is not None)
+                line = {"metric": "row-sharded N=6 complex composition (config 5), real TFLOP/s aggregate", "value": leg["value_tflops"],
+                        "unit": "TFLOP/s", "scaling": "strong",
+                        "ms_per_step": leg.get("fused_peer_store", leg["single_gpu"])["ms"]}
+        finally:
+            if cpu_pool is not None:
+                cpu_pool.close()
+        line.update({"n_gpus": world, "steps": 1, "warmup": 1, "higher_is_better": True, "vs_baseline": None, "dtype": "f64",
+                     "data": "synthetic", "config": {"workload": leg["workload"]}, args.workload: leg})
+        if rank == 0:
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
     # ---- set-up (not timed): target, inputs -----------------------------------------------------------------------
     Lvec = T.create_kitaev_liouvillians(N_SITES, D_LOC, 1.0, pbc=False)[0]
     target = T.exp_operator_dt(Lvec, 4.0)

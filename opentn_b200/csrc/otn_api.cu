@@ -1070,6 +1070,29 @@ static int back_layer(otn_problem* h, int batch, const int* active, int l, const
     return 0;
 }
 
+// fused-chain path, full-sites model in blocks: zraw = A(W_l) x and zdraw = A(W_l) eta + A(Wd_l) x for every layer in one launch
+static int back_all_layers(otn_problem* h, int batch, const int* active, const double* x, const double* eta) {
+    const long long SZ = h->SZ, S = (long long)h->m * SZ;
+    ProfScope ps(&h->prof, h->stream, CAT_BACK, 4.0 * h->K * (double)h->dim * h->dim * h->dim * h->dim * batch * h->m * 3);
+    BackAll P{};
+    for (int l = 0; l < h->m; ++l) {
+        if (l == 0) { P.W[l] = h->G; P.sW[l] = S; P.Wd[l] = h->Gd + (long long)h->tr.gd_final * SZ; P.sWd[l] = 2 * SZ; }
+        else { P.W[l] = layer_ptr(h->W, l, SZ); P.sW[l] = S; P.Wd[l] = h->Wd + (long long)l * SZ; P.sWd[l] = h->wd_stride; }
+    }
+    const int kp = (h->K + 7) & ~7;
+    dim3 grid(batch * 2, h->m);
+#define BAS3(KPV)                                                                                                          \
+    do {                                                                                                                   \
+        const size_t sm = BasSym3Cfg<16, 2, KPV>::SMEM_BYTES;                                                              \
+        OTN_TRY(set_smem(back_assemble_sym3_kernel<16, 2, KPV>, sm));                                                      \
+        back_assemble_sym3_kernel<16, 2, KPV><<<grid, 256, sm, h->stream>>>(P, x, eta, h->zraw, h->zdraw, h->sym, h->K, active, h->m); \
+    } while (0)
+    if (kp == 8) BAS3(8); else if (kp == 16) BAS3(16); else if (kp == 24) BAS3(24); else BAS3(32);
+#undef BAS3
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 static int reverse_chain(otn_problem* h, int batch, const int* active, const double* x, const double* eta_joint = nullptr) {
     const long long SZ = h->SZ, S = (long long)h->m * SZ;
     if (h->fused && h->m >= 2) {
@@ -1412,8 +1435,12 @@ static int triple_device(otn_problem* h, const double* x, const double* eta, int
         // forward, residual, reverse and tangent sweeps of every instance in ONE launch per diagonal block, then the pull-backs
         h->tr.tiles = tiles = h->tiles;
         OTN_TRY(hchain(h, batch, nullptr, CHAIN_TRIPLE));
-        for (int l = h->m - 1; l >= 0; --l) OTN_TRY(back_layer(h, batch, nullptr, l, x, false, joint ? eta : nullptr, joint));
-        for (int l = h->m - 1; l >= 0; --l) OTN_TRY(back_layer(h, batch, nullptr, l, x, true, eta, joint));
+        if (joint && h->dim == 16 && h->K <= 32 && h->m <= 16 && getenv("OTN_BACK_PER_LAYER") == nullptr) {   // env: A/B switch
+            OTN_TRY(back_all_layers(h, batch, nullptr, x, eta));          // every layer, W and Wd, in one launch
+        } else {
+            for (int l = h->m - 1; l >= 0; --l) OTN_TRY(back_layer(h, batch, nullptr, l, x, false, joint ? eta : nullptr, joint));
+            for (int l = h->m - 1; l >= 0; --l) OTN_TRY(back_layer(h, batch, nullptr, l, x, true, eta, joint));
+        }
         OTN_TRY(riem_launch(h, batch, nullptr, tiles, x, eta, true, f, rgrad, nullptr, heta));
         return 0;
     }

@@ -258,6 +258,150 @@ __global__ void __launch_bounds__(256) back_assemble_sym2_kernel(const double* _
     }
 }
 
+// ---- adjoint of the assembly, all layers and both cotangents in ONE launch (fused-chain path) ----------------------------------------
+// With the fused chain every layer cotangent W_l and its tangent Wd_l exist when the pull-backs start, so one kernel does, for
+// every (instance, layer):      zraw = A(W) x,      zdraw = A(W) eta + A(Wd) x
+// (A = the adjoint of the assembly above).  Versus back_assemble_sym2_kernel called 6 times per step: the rows of W AND Wd of
+// one b travel through the cp.async ring together with the 16 x KP slices x_b, eta_b they are contracted with (no per-CTA copy
+// of all of x / eta: 108 KB instead of 160 KB of shared memory, two CTAs per SM), one barrier serves 48 DMMA per warp instead of
+// 32 / 16, and x, eta, the decode constants and the launch are paid once instead of twice.
+struct BackAll {
+    const double* W[16]; long long sW[16];        // per layer: cotangent blocks of instance 0 and the instance stride
+    const double* Wd[16]; long long sWd[16];
+};
+
+template <int DIM, int AS, int KP>
+struct BasSym3Cfg {
+    static constexpr int STAGES = 3, D2 = DIM * DIM, DA = DIM / AS;
+    static constexpr int RAW = DA * D2;                       // rows {(a,b)}_a of one matrix
+    static constexpr int UB = KP * DIM;                       // x_b (or eta_b): [k][DIM], swizzled
+    static constexpr int STAGE = 2 * RAW + 2 * UB;
+    static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE * 8;
+};
+
+template <int DIM, int AS, int KP>
+__global__ void __launch_bounds__(256, 2) back_assemble_sym3_kernel(const BackAll P, const double* __restrict__ x, const double* __restrict__ eta,
+                                                                    double* __restrict__ zraw, double* __restrict__ zdraw, SymLayout L, int K,
+                                                                    const int* active, int m) {
+    using Cfg = BasSym3Cfg<DIM, AS, KP>;
+    constexpr int D2 = Cfg::D2, ST = Cfg::STAGES, DA = Cfg::DA, NS = DIM * (DIM + 1) / 2, NA = DIM * (DIM - 1) / 2;
+    constexpr int MI = DIM / 8, DQ = DIM / 4, SWZ = DIM / 4 - 1, NI = KP / 8;
+    static_assert(DA == 8, "one a value per warp");
+    extern __shared__ __align__(16) double sm[];
+    const int inst = blockIdx.x / AS, a_lo = (blockIdx.x - inst * AS) * DA, layer = blockIdx.y;
+    if (active != nullptr && active[inst] == 0) return;
+    const long long item = (long long)inst * m + layer;
+    const long long np = (long long)DIM * K * DIM;
+    const double* Ws = P.W[layer] + (long long)inst * P.sW[layer];
+    const double* Wa = Ws + L.off_a;
+    const double* Wds = P.Wd[layer] + (long long)inst * P.sWd[layer];
+    const double* Wda = Wds + L.off_a;
+    const double* xg = x + item * np;
+    const double* eg = eta + item * np;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+
+    auto load_stage = [&](int b, int s) {
+        double* dst = sm + s * Cfg::STAGE;
+        constexpr int CS = NS / 2, CA = NA / 2, CR = CS + CA;
+        for (int id = tid; id < 2 * DA * CR; id += 256) {
+            const int which = id / (DA * CR), rem = id - which * (DA * CR);
+            const int al = rem / CR, ch = rem - al * CR, a = a_lo + al;
+            const int lo = a < b ? a : b, hi = a < b ? b : a;
+            double* row = dst + which * Cfg::RAW + al * D2;
+            const double* S = which ? Wds : Ws;
+            const double* A = which ? Wda : Wa;
+            if (ch < CS) cp_async16(row + 2 * ch, S + (long long)pair_s(lo, hi, DIM) * L.Ds + 2 * ch);
+            else if (a != b) cp_async16(row + NS + 2 * (ch - CS), A + (long long)pair_a(lo, hi, DIM) * L.Da + 2 * (ch - CS));
+        }
+        // x_b, eta_b: rows (b, k), 4-column groups XOR-swizzled by (k & SWZ) (a swizzled group keeps its two halves contiguous)
+        double* ub = dst + 2 * Cfg::RAW;
+        for (int id = tid; id < 2 * KP * (DIM / 2); id += 256) {
+            const int which = id / (KP * (DIM / 2)), rem = id - which * (KP * (DIM / 2));
+            const int k = rem / (DIM / 2), c = 2 * (rem - k * (DIM / 2));
+            double* d = ub + which * Cfg::UB + k * DIM + (c ^ ((k & SWZ) << 2));
+            if (k < K) cp_async16(d, (which ? eg : xg) + (long long)(b * K + k) * DIM + c);
+            else { d[0] = 0.0; d[1] = 0.0; }
+        }
+    };
+#pragma unroll
+    for (int s = 0; s < ST - 1; ++s) { load_stage(s, s); cp_async_commit(); }
+
+    // per-lane decode constants: fragment element (row c_i = i*8+g, column d = dq*4+t)
+    int ixs[MI][DQ], ixa[MI][DQ];
+    double cfd[MI][DQ], scd[MI][DQ];
+    const double s2 = 1.41421356237309504880;
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int dq = 0; dq < DQ; ++dq) {
+            const int c = i * 8 + g, dd = dq * 4 + t, lo = c < dd ? c : dd, hi = c < dd ? dd : c;
+            ixs[i][dq] = pair_s(lo, hi, DIM);
+            ixa[i][dq] = (c == dd) ? NS : NS + pair_a(lo, hi, DIM);
+            cfd[i][dq] = (c == dd) ? s2 : 1.0;
+            scd[i][dq] = (c == dd) ? 0.0 : ((c < dd) ? 1.0 : -1.0);
+        }
+    int dsw[DQ];
+#pragma unroll
+    for (int dq = 0; dq < DQ; ++dq) dsw[dq] = g * DIM + (((dq ^ (g & SWZ)) << 2) + t);
+    double acc1[MI][NI][2], acc2[MI][NI][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) { acc1[i][j][0] = acc1[i][j][1] = 0.0; acc2[i][j][0] = acc2[i][j][1] = 0.0; }
+    const int a = a_lo + warp;
+
+    for (int b = 0; b < DIM; ++b) {
+        cp_async_wait<ST - 2>();
+        __syncthreads();                                   // stage b landed; stage b-1 fully consumed by every warp
+        if (b + ST - 1 < DIM) load_stage(b + ST - 1, (b + ST - 1) % ST);
+        cp_async_commit();
+        const double* stage = sm + (b % ST) * Cfg::STAGE;
+        const double* R = stage + warp * D2;
+        const double* Rd = stage + Cfg::RAW + warp * D2;
+        const double* ux = stage + 2 * Cfg::RAW;
+        const double* ue = ux + Cfg::UB;
+        const double nab = (a == b) ? s2 : 1.0;
+        const double sgo = (a == b) ? 0.0 : ((a < b) ? 1.0 : -1.0);
+#pragma unroll
+        for (int dq = 0; dq < DQ; ++dq) {
+            double wa[MI], wda[MI];
+#pragma unroll
+            for (int i = 0; i < MI; ++i) {
+                const double cs = nab * cfd[i][dq], ca = sgo * scd[i][dq];
+                const double ra = (a == b) ? 0.0 : R[ixa[i][dq]], rda = (a == b) ? 0.0 : Rd[ixa[i][dq]];
+                wa[i] = fma(ca, ra, cs * R[ixs[i][dq]]);
+                wda[i] = fma(ca, rda, cs * Rd[ixs[i][dq]]);
+            }
+#pragma unroll
+            for (int j = 0; j < NI; ++j) {
+                const double vx = ux[(j * 8) * DIM + dsw[dq]], ve = ue[(j * 8) * DIM + dsw[dq]];
+#pragma unroll
+                for (int i = 0; i < MI; ++i) {
+                    dmma884(acc1[i][j][0], acc1[i][j][1], wa[i], vx);
+                    dmma884(acc2[i][j][0], acc2[i][j][1], wa[i], ve);
+                    dmma884(acc2[i][j][0], acc2[i][j][1], wda[i], vx);
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+        const int c = i * 8 + g;
+#pragma unroll
+        for (int j = 0; j < NI; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int k = j * 8 + 2 * t + e;
+                if (k < K) {
+                    const long long og = item * np + (a * K + k) * DIM + c;
+                    zraw[og] = acc1[i][j][e];
+                    zdraw[og] = acc2[i][j][e];
+                }
+            }
+    }
+}
+
 // ---- blocks -> dense superoperator (otn_model in structured mode) ------------------------------------------------------
 //   M[(a,b),(c,d)] = cs_ab cs_cd Ms[{ab},{cd}] + ca_ab ca_cd Ma[{ab},{cd}],  cs = 1 (a==b) else 1/sqrt2,  ca = +-1/sqrt2, 0 on a==b
 __global__ void unblock_kernel(const double* __restrict__ blocks, long long in_stride, double* __restrict__ M, SymLayout L, int batch) {
