@@ -1070,10 +1070,15 @@ static int back_layer(otn_problem* h, int batch, const int* active, int l, const
     return 0;
 }
 
-// fused-chain path, full-sites model in blocks: zraw = A(W_l) x and zdraw = A(W_l) eta + A(Wd_l) x for every layer in one launch
-static int back_all_layers(otn_problem* h, int batch, const int* active, const double* x, const double* eta) {
+// fused-chain path, full-sites model in blocks: zraw = A(W_l) x (`grad`) and / or zdraw = A(W_l) eta + A(Wd_l) x (`tan`) for every
+// layer in one launch
+static bool back_all_ok(const otn_problem* h) {
+    return h->fused && h->structured && h->model == OTN_MODEL_FULL && h->dim == 16 && h->K <= 32 && h->m <= 16 && h->m >= 2 &&
+           getenv("OTN_BACK_PER_LAYER") == nullptr;               // env: A/B switch for measurements
+}
+static int back_all_layers(otn_problem* h, int batch, const int* active, const double* x, const double* eta, bool grad, bool tan) {
     const long long SZ = h->SZ, S = (long long)h->m * SZ;
-    ProfScope ps(&h->prof, h->stream, CAT_BACK, 4.0 * h->K * (double)h->dim * h->dim * h->dim * h->dim * batch * h->m * 3);
+    ProfScope ps(&h->prof, h->stream, CAT_BACK, 4.0 * h->K * (double)h->dim * h->dim * h->dim * h->dim * batch * h->m * ((grad ? 1 : 0) + (tan ? 2 : 0)));
     BackAll P{};
     for (int l = 0; l < h->m; ++l) {
         if (l == 0) { P.W[l] = h->G; P.sW[l] = S; P.Wd[l] = h->Gd + (long long)h->tr.gd_final * SZ; P.sWd[l] = 2 * SZ; }
@@ -1081,13 +1086,16 @@ static int back_all_layers(otn_problem* h, int batch, const int* active, const d
     }
     const int kp = (h->K + 7) & ~7;
     dim3 grid(batch * 2, h->m);
-#define BAS3(KPV)                                                                                                          \
+#define BAS3(KPV, GR, TN)                                                                                                  \
     do {                                                                                                                   \
         const size_t sm = BasSym3Cfg<16, 2, KPV>::SMEM_BYTES;                                                              \
-        OTN_TRY(set_smem(back_assemble_sym3_kernel<16, 2, KPV>, sm));                                                      \
-        back_assemble_sym3_kernel<16, 2, KPV><<<grid, 256, sm, h->stream>>>(P, x, eta, h->zraw, h->zdraw, h->sym, h->K, active, h->m); \
+        OTN_TRY(set_smem(back_assemble_sym3_kernel<16, 2, KPV, GR, TN>, sm));                                              \
+        back_assemble_sym3_kernel<16, 2, KPV, GR, TN><<<grid, 256, sm, h->stream>>>(P, x, eta, h->zraw, h->zdraw, h->sym, h->K, active, h->m); \
     } while (0)
-    if (kp == 8) BAS3(8); else if (kp == 16) BAS3(16); else if (kp == 24) BAS3(24); else BAS3(32);
+#define BAS3_K(GR, TN)                                                                                                     \
+    do { if (kp == 8) BAS3(8, GR, TN); else if (kp == 16) BAS3(16, GR, TN); else if (kp == 24) BAS3(24, GR, TN); else BAS3(32, GR, TN); } while (0)
+    if (grad && tan) BAS3_K(true, true); else if (tan) BAS3_K(false, true); else BAS3_K(true, false);
+#undef BAS3_K
 #undef BAS3
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -1097,6 +1105,7 @@ static int reverse_chain(otn_problem* h, int batch, const int* active, const dou
     const long long SZ = h->SZ, S = (long long)h->m * SZ;
     if (h->fused && h->m >= 2) {
         OTN_TRY(hchain(h, batch, active, CHAIN_REV));
+        if (back_all_ok(h) && eta_joint == nullptr) return back_all_layers(h, batch, active, x, nullptr, true, false);
         for (int l = h->m - 1; l >= 0; --l) OTN_TRY(back_layer(h, batch, active, l, x, false, eta_joint, eta_joint != nullptr));
         return 0;
     }
@@ -1127,6 +1136,7 @@ static int tangent_pass(otn_problem* h, int batch, const int* active, const doub
     if (!layers_built) OTN_TRY(build_layers(h, x, eta, batch, active, false));
     if (h->fused && m >= 2) {
         OTN_TRY(hchain(h, batch, active, CHAIN_TANGENT));
+        if (back_all_ok(h) && !joint) return back_all_layers(h, batch, active, x, eta, false, true);
         for (int l = m - 1; l >= 0; --l) OTN_TRY(back_layer(h, batch, active, l, x, true, eta, joint));
         return 0;
     }
@@ -1435,8 +1445,8 @@ static int triple_device(otn_problem* h, const double* x, const double* eta, int
         // forward, residual, reverse and tangent sweeps of every instance in ONE launch per diagonal block, then the pull-backs
         h->tr.tiles = tiles = h->tiles;
         OTN_TRY(hchain(h, batch, nullptr, CHAIN_TRIPLE));
-        if (joint && h->dim == 16 && h->K <= 32 && h->m <= 16 && getenv("OTN_BACK_PER_LAYER") == nullptr) {   // env: A/B switch
-            OTN_TRY(back_all_layers(h, batch, nullptr, x, eta));          // every layer, W and Wd, in one launch
+        if (back_all_ok(h)) {
+            OTN_TRY(back_all_layers(h, batch, nullptr, x, eta, true, true));          // every layer, W and Wd, in one launch
         } else {
             for (int l = h->m - 1; l >= 0; --l) OTN_TRY(back_layer(h, batch, nullptr, l, x, false, joint ? eta : nullptr, joint));
             for (int l = h->m - 1; l >= 0; --l) OTN_TRY(back_layer(h, batch, nullptr, l, x, true, eta, joint));

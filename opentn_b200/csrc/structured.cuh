@@ -279,7 +279,8 @@ struct BasSym3Cfg {
     static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE * 8;
 };
 
-template <int DIM, int AS, int KP>
+// GRAD: zraw = A(W) x is wanted; TAN: zdraw = A(W) eta + A(Wd) x is wanted (gradient only / HVP with cached primal / both)
+template <int DIM, int AS, int KP, bool GRAD, bool TAN>
 __global__ void __launch_bounds__(256, 2) back_assemble_sym3_kernel(const BackAll P, const double* __restrict__ x, const double* __restrict__ eta,
                                                                     double* __restrict__ zraw, double* __restrict__ zdraw, SymLayout L, int K,
                                                                     const int* active, int m) {
@@ -294,16 +295,16 @@ __global__ void __launch_bounds__(256, 2) back_assemble_sym3_kernel(const BackAl
     const long long np = (long long)DIM * K * DIM;
     const double* Ws = P.W[layer] + (long long)inst * P.sW[layer];
     const double* Wa = Ws + L.off_a;
-    const double* Wds = P.Wd[layer] + (long long)inst * P.sWd[layer];
-    const double* Wda = Wds + L.off_a;
+    const double* Wds = TAN ? P.Wd[layer] + (long long)inst * P.sWd[layer] : nullptr;
+    const double* Wda = TAN ? Wds + L.off_a : nullptr;
     const double* xg = x + item * np;
-    const double* eg = eta + item * np;
+    const double* eg = TAN ? eta + item * np : nullptr;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
 
     auto load_stage = [&](int b, int s) {
         double* dst = sm + s * Cfg::STAGE;
         constexpr int CS = NS / 2, CA = NA / 2, CR = CS + CA;
-        for (int id = tid; id < 2 * DA * CR; id += 256) {
+        for (int id = tid; id < (TAN ? 2 : 1) * DA * CR; id += 256) {
             const int which = id / (DA * CR), rem = id - which * (DA * CR);
             const int al = rem / CR, ch = rem - al * CR, a = a_lo + al;
             const int lo = a < b ? a : b, hi = a < b ? b : a;
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(256, 2) back_assemble_sym3_kernel(const BackAl
         }
         // x_b, eta_b: rows (b, k), 4-column groups XOR-swizzled by (k & SWZ) (a swizzled group keeps its two halves contiguous)
         double* ub = dst + 2 * Cfg::RAW;
-        for (int id = tid; id < 2 * KP * (DIM / 2); id += 256) {
+        for (int id = tid; id < (TAN ? 2 : 1) * KP * (DIM / 2); id += 256) {
             const int which = id / (KP * (DIM / 2)), rem = id - which * (KP * (DIM / 2));
             const int k = rem / (DIM / 2), c = 2 * (rem - k * (DIM / 2));
             double* d = ub + which * Cfg::UB + k * DIM + (c ^ ((k & SWZ) << 2));
@@ -368,18 +369,24 @@ __global__ void __launch_bounds__(256, 2) back_assemble_sym3_kernel(const BackAl
 #pragma unroll
             for (int i = 0; i < MI; ++i) {
                 const double cs = nab * cfd[i][dq], ca = sgo * scd[i][dq];
-                const double ra = (a == b) ? 0.0 : R[ixa[i][dq]], rda = (a == b) ? 0.0 : Rd[ixa[i][dq]];
+                const double ra = (a == b) ? 0.0 : R[ixa[i][dq]];
                 wa[i] = fma(ca, ra, cs * R[ixs[i][dq]]);
-                wda[i] = fma(ca, rda, cs * Rd[ixs[i][dq]]);
+                if (TAN) {
+                    const double rda = (a == b) ? 0.0 : Rd[ixa[i][dq]];
+                    wda[i] = fma(ca, rda, cs * Rd[ixs[i][dq]]);
+                }
             }
 #pragma unroll
             for (int j = 0; j < NI; ++j) {
-                const double vx = ux[(j * 8) * DIM + dsw[dq]], ve = ue[(j * 8) * DIM + dsw[dq]];
+                const double vx = ux[(j * 8) * DIM + dsw[dq]];
+                const double ve = TAN ? ue[(j * 8) * DIM + dsw[dq]] : 0.0;
 #pragma unroll
                 for (int i = 0; i < MI; ++i) {
-                    dmma884(acc1[i][j][0], acc1[i][j][1], wa[i], vx);
-                    dmma884(acc2[i][j][0], acc2[i][j][1], wa[i], ve);
-                    dmma884(acc2[i][j][0], acc2[i][j][1], wda[i], vx);
+                    if (GRAD) dmma884(acc1[i][j][0], acc1[i][j][1], wa[i], vx);
+                    if (TAN) {
+                        dmma884(acc2[i][j][0], acc2[i][j][1], wa[i], ve);
+                        dmma884(acc2[i][j][0], acc2[i][j][1], wda[i], vx);
+                    }
                 }
             }
         }
@@ -395,8 +402,8 @@ __global__ void __launch_bounds__(256, 2) back_assemble_sym3_kernel(const BackAl
                 const int k = j * 8 + 2 * t + e;
                 if (k < K) {
                     const long long og = item * np + (a * K + k) * DIM + c;
-                    zraw[og] = acc1[i][j][e];
-                    zdraw[og] = acc2[i][j][e];
+                    if (GRAD) zraw[og] = acc1[i][j][e];
+                    if (TAN) zdraw[og] = acc2[i][j][e];
                 }
             }
     }
