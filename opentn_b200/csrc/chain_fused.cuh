@@ -61,6 +61,13 @@ struct ChainCfg {
     static constexpr int OPER = DT * LDK;         // >= BK * LDM for DT >= 80
     static constexpr int STAGE = 2 * OPER;
     static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE * sizeof(double) + 2 * STAGES * sizeof(unsigned long long) + 16;
+    // warp id -> warp tile (row-major in the WARPS_M x WARPS_N grid), balancing the trimmed tile counts over warp id mod 4
+    // (tables packed 4 bits per warp into one constant: {0,2,3,4, 1,6,8,10, 5,7,9,11} and {0,1,2,5, 7,3,4,6})
+    __host__ __device__ static constexpr int tile_of_warp(int w) {
+        if (DT == 144 && WM == 72 && WN == 24) return (int)((0xb975a8614320ULL >> (4 * w)) & 15);
+        if (DT == 128 && WM == 64 && WN == 32) return (int)((0x64375210ULL >> (4 * w)) & 15);
+        return w;
+    }
     static_assert(DT % WM == 0 && DT % WN == 0 && WM % 8 == 0 && WN % 8 == 0, "warp tiles must tile the block in 8 x 8 MMA tiles");
     static_assert(CONS_WARPS % 4 == 0, "setmaxnreg works on whole warpgroups");
     static_assert(DT * LDK >= BK * LDM, "operand slot too small for the transposed layout");
@@ -151,7 +158,15 @@ __global__ void __launch_bounds__(ChainCfg<DT, WM, WN, STAGES>::THREADS, 1) chai
 
     // ================================================== consumers ==================================================
     reg_alloc<Cfg::CONS_REGS>();
-    const int wm0 = (warp / Cfg::WARPS_N) * WM, wn0 = (warp % Cfg::WARPS_N) * WN;
+    // Output tiles beyond the populated extent (136 of 144, 120 of 128) are zero padding: their MMAs are skipped (10.8 % / 12 % of
+    // the 8 x 8 tiles) and the padding in memory is never written (it is zero from the handle's creation).  The warps on the last
+    // row / column of the warp grid therefore have less work; `tile_of_warp` deals the warp tiles to the warp ids so that the four
+    // SM sub-partitions (warp id mod 4) carry nearly equal DMMA counts (75 / 75 / 72 / 67 of 289 instead of 81 each of 324).
+    const int wtile = Cfg::tile_of_warp(warp);
+    const int wm0 = (wtile / Cfg::WARPS_N) * WM, wn0 = (wtile % Cfg::WARPS_N) * WN;
+    // (the populated extent ends inside the last 8-wide tile row / column: 136 = 144 - 8, 120 = 128 - 8; anything else keeps all tiles)
+    const bool trim = p.kvalid == DT - 8;
+    const int mi_cnt = (trim && wm0 + WM == DT) ? MI - 1 : MI, ni_cnt = (trim && wn0 + WN == DT) ? NI - 1 : NI;
     const int g = lane >> 2, t = lane & 3;
     double acc[MI][NI][2];
 #pragma unroll
@@ -163,8 +178,11 @@ __global__ void __launch_bounds__(ChainCfg<DT, WM, WN, STAGES>::THREADS, 1) chai
     for (int i = 0; i < p.nops; ++i) {
         const ChainOp op = p.ops[i];
         const int ktiles = ktiles_one * (op.a2 != CH_NONE ? 2 : 1);
-        auto run = [&](auto TA_, auto TB_) {
+        // MC x NC = the 8 x 8 MMA tiles of this warp that are not padding: compile-time trip counts (a run-time predicate per DMMA
+        // costs an ISETP per DMMA and measured slower than not trimming at all)
+        auto run = [&](auto TA_, auto TB_, auto MC_, auto NC_) {
             constexpr bool TA = decltype(TA_)::value, TB = decltype(TB_)::value;
+            constexpr int MC = decltype(MC_)::value, NC = decltype(NC_)::value;
             int kt_in = 0;                                        // k-tile index inside the current product
             for (int kt = 0; kt < ktiles; ++kt, ++gt) {
                 const int slot = gt % STAGES;
@@ -173,21 +191,21 @@ __global__ void __launch_bounds__(ChainCfg<DT, WM, WN, STAGES>::THREADS, 1) chai
                 const double* Bs = As + Cfg::OPER;
                 const int kend = p.kvalid - kt_in * BK;           // < BK only in the last k-tile of a padded block
                 auto kstep = [&](int kk) {
-                    double a[MI], bf[NI];
+                    double a[MC], bf[NC];
 #pragma unroll
-                    for (int ii = 0; ii < MI; ++ii) {
+                    for (int ii = 0; ii < MC; ++ii) {
                         const int m = wm0 + ii * 8 + g;
                         a[ii] = TA ? As[(kk + t) * LDM + m] : As[m * LDK + kk + t];
                     }
 #pragma unroll
-                    for (int jj = 0; jj < NI; ++jj) {
+                    for (int jj = 0; jj < NC; ++jj) {
                         const int n = wn0 + jj * 8 + g;
                         bf[jj] = TB ? Bs[n * LDK + kk + t] : Bs[(kk + t) * LDM + n];
                     }
 #pragma unroll
-                    for (int ii = 0; ii < MI; ++ii)
+                    for (int ii = 0; ii < MC; ++ii)
 #pragma unroll
-                        for (int jj = 0; jj < NI; ++jj) dmma884(acc[ii][jj][0], acc[ii][jj][1], a[ii], bf[jj]);
+                        for (int jj = 0; jj < NC; ++jj) dmma884(acc[ii][jj][0], acc[ii][jj][1], a[ii], bf[jj]);
                 };
                 if (kend >= BK) {
 #pragma unroll
@@ -202,9 +220,17 @@ __global__ void __launch_bounds__(ChainCfg<DT, WM, WN, STAGES>::THREADS, 1) chai
             }
         };
         const bool ta = op.flags & CHF_TA, tb = op.flags & CHF_TB;
-        if (!ta && !tb) run(std::false_type{}, std::false_type{});
-        else if (!ta) run(std::false_type{}, std::true_type{});
-        else run(std::true_type{}, std::false_type{});
+        auto run_t = [&](auto MC_, auto NC_) {
+            if (!ta && !tb) run(std::false_type{}, std::false_type{}, MC_, NC_);
+            else if (!ta) run(std::false_type{}, std::true_type{}, MC_, NC_);
+            else run(std::true_type{}, std::false_type{}, MC_, NC_);
+        };
+        using IM = std::integral_constant<int, MI>; using IM1 = std::integral_constant<int, MI - 1>;
+        using IN = std::integral_constant<int, NI>; using IN1 = std::integral_constant<int, NI - 1>;
+        if (mi_cnt == MI && ni_cnt == NI) run_t(IM{}, IN{});
+        else if (mi_cnt == MI) run_t(IM{}, IN1{});
+        else if (ni_cnt == NI) run_t(IM1{}, IN{});
+        else run_t(IM1{}, IN1{});
 
         // ---- epilogue, per warp: C = acc (- T); partial sums of this warp's tile; accumulators reset ------------------------
         double* C = mat(op.c);
@@ -217,6 +243,7 @@ __global__ void __launch_bounds__(ChainCfg<DT, WM, WN, STAGES>::THREADS, 1) chai
             const long long row = wm0 + ii * 8 + g;
 #pragma unroll
             for (int jj = 0; jj < NI; ++jj) {
+                if (ii >= mi_cnt || jj >= ni_cnt) continue;        // zero padding: neither computed nor stored
                 const int col = wn0 + jj * 8 + 2 * t;
                 double2 v = make_double2(acc[ii][jj][0], acc[ii][jj][1]);
                 acc[ii][jj][0] = acc[ii][jj][1] = 0.0;

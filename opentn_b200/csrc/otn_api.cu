@@ -794,7 +794,10 @@ static int hchain(otn_problem* h, int batch, const int* active, int mode) {
             h->prof.fork(h->stream);
             if (i == 1) st = h->prof.side.st;
         }
-        ProfScope ps(&h->prof, st, CAT_GEMM, 2.0 * p.D * (double)p.D * p.kvalid * batch * prog.products);
+        // executed flops: output tiles that are pure padding are skipped by the kernel when the populated extent ends one 8-wide
+        // tile short of the block side (136 of 144, 120 of 128), and the contraction always stops at kvalid
+        const double side = (p.kvalid == p.D - 8) ? (double)p.kvalid : (double)p.D;
+        ProfScope ps(&h->prof, st, CAT_GEMM, 2.0 * side * side * p.kvalid * batch * prog.products);
         CUDA_TRY(chain_launch(p, batch, st));
     }
     return 0;
