@@ -582,8 +582,8 @@ def c4_leg(torch, dist, rank, world, device, barrier, max_over_ranks, cpu, seeds
            "instances_returned_rank0": got, "improved_fraction": improved,
            "status_nonzero": int(sum((r["status"] != 0).sum() for r in res.values())),
            "target_setup_s": t_fit,
-           "partition": "K-major (K, tau) cell list dealt to the ranks in a snake (cheap and expensive cells paired); one packed "
-                        "all-gather per K group at the end; handles created by a warm-up sweep (not timed), targets by make_fit "
+           "partition": "K-major (K, tau) cell list dealt to the ranks in a snake (cheap and expensive cells paired); ONE packed "
+                        "all-gather of the whole sweep at the end; handles created by a warm-up sweep (not timed), targets by make_fit "
                         "(target_setup_s, not in wall_s)"}
     if cpu is not None and world == 1:
         picks = [(C4_RANKS[c % 4], (c // 4) % 4, c % seeds_per_cell) for c in range(cpu.cores)]     # (K, tau index, seed) cycling

@@ -1097,7 +1097,19 @@ static int back_all_layers(otn_problem* h, int batch, const int* active, const d
     } while (0)
 #define BAS3_K(GR, TN)                                                                                                     \
     do { if (kp == 8) BAS3(8, GR, TN); else if (kp == 16) BAS3(16, GR, TN); else if (kp == 24) BAS3(24, GR, TN); else BAS3(32, GR, TN); } while (0)
-    if (grad && tan) BAS3_K(true, true); else if (tan) BAS3_K(false, true); else BAS3_K(true, false);
+#define BAS4(KPV, GR, TN)                                                                                                  \
+    do {                                                                                                                   \
+        const size_t sm = BasSym4Cfg<KPV>::SMEM_BYTES;                                                                     \
+        OTN_TRY(set_smem(back_assemble_sym4_kernel<KPV, GR, TN>, sm));                                                     \
+        back_assemble_sym4_kernel<KPV, GR, TN><<<grid, 256, sm, h->stream>>>(P, x, eta, h->zraw, h->zdraw, h->sym, h->K, active, h->m); \
+    } while (0)
+#define BAS4_K(GR, TN)                                                                                                     \
+    do { if (kp == 8) BAS4(8, GR, TN); else if (kp == 16) BAS4(16, GR, TN); else if (kp == 24) BAS4(24, GR, TN); else BAS4(32, GR, TN); } while (0)
+    static const bool v3 = getenv("OTN_BACK_V3") != nullptr;      // env: A/B switch for measurements (cp.async ring + CTA barrier version)
+    if (!v3) { if (grad && tan) BAS4_K(true, true); else if (tan) BAS4_K(false, true); else BAS4_K(true, false); }
+    else if (grad && tan) BAS3_K(true, true); else if (tan) BAS3_K(false, true); else BAS3_K(true, false);
+#undef BAS4_K
+#undef BAS4
 #undef BAS3_K
 #undef BAS3
     CUDA_TRY(cudaGetLastError());

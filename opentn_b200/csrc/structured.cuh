@@ -14,6 +14,7 @@
 //     Z[(a,k),c] = sum_{b,d} ( nu_ab nu_cd Ws[{ab},{cd}] + sg_ab sg_cd Wa[{ab},{cd}] ) x[(b,k),d]
 // with nu_ab = sqrt2 if a == b else 1, sg_ab = +1 (a<b), -1 (a>b), 0 (a == b).
 #pragma once
+#include <type_traits>
 #include "assemble.cuh"
 #include "otn_common.cuh"
 
@@ -392,6 +393,231 @@ __global__ void __launch_bounds__(256, 2) back_assemble_sym3_kernel(const BackAl
         }
     }
     cp_async_wait<0>();
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+        const int c = i * 8 + g;
+#pragma unroll
+        for (int j = 0; j < NI; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int k = j * 8 + 2 * t + e;
+                if (k < K) {
+                    const long long og = item * np + (a * K + k) * DIM + c;
+                    if (GRAD) zraw[og] = acc1[i][j][e];
+                    if (TAN) zdraw[og] = acc2[i][j][e];
+                }
+            }
+    }
+}
+
+// ---- pull-back, fourth version: no CTA-wide barrier, no per-thread copy addressing --------------------------------------------
+// ncu of back_assemble_sym3_kernel (profiles/ncu_step_r02.txt): 14 instructions per DMMA, 30 % of them IMAD -- the per-thread
+// address arithmetic of the cp.async ring -- tensor pipe 52 % active, one __syncthreads per b.  Here every warp owns one `a` and
+// streams ITS rows {a,b} of W / Wd (S row | A row = 2 KB per matrix) through a private 3-stage ring with 1-D bulk copies (TMA
+// engine, one lane issues, completion by transaction count on a per-warp mbarrier); the x_b / eta_b tiles are shared by the 8
+// warps of the CTA, copied by one warp per b (rotating) with cp.async into rows of 20 doubles (fragment loads take the minimum of
+// two wavefronts) and handed over by mbarriers (full: cp.async arrivals; empty: one arrival per warp, waited for one iteration
+// later).  The decode costs one FP64 instruction per fragment element: sign and sqrt2 factors that depend on (a,b) select one of
+// three loop bodies per b (a < b, a > b, a == b: warp-uniform), the ones that depend on (c,d) are static per fragment or, for the
+// four fragments that straddle the diagonal, an XOR of the sign bit; diagonal elements read the antisymmetric part from a
+// zero pad.
+template <int KP>
+struct BasSym4Cfg {
+    static constexpr int DIM = 16, NS = 136, NA = 120, ST = 3, WARPS = 8;
+    static constexpr int ROWB = (NS + NA) * 8;            // bytes: S row | A row of one matrix
+    static constexpr int WARP_STAGE = 2 * ROWB;           // W, Wd
+    static constexpr int XLD = 20;                        // doubles per row of an x_b / eta_b tile (16 + 4 zero pad)
+    static constexpr int XT = KP * XLD * 8;               // bytes per tile
+    static constexpr int STAGE = WARPS * WARP_STAGE + 2 * XT;
+    static constexpr int NBAR = WARPS * ST + 2 * ST;
+    static constexpr size_t SMEM_BYTES = (size_t)ST * STAGE + NBAR * 8;
+};
+
+template <int KP, bool GRAD, bool TAN>
+__global__ void __launch_bounds__(256, KP <= 16 ? 2 : 1) back_assemble_sym4_kernel(const BackAll P, const double* __restrict__ x, const double* __restrict__ eta,
+                                                                                   double* __restrict__ zraw, double* __restrict__ zdraw, SymLayout L, int K,
+                                                                                   const int* active, int m) {
+    using Cfg = BasSym4Cfg<KP>;
+    constexpr int DIM = Cfg::DIM, NS = Cfg::NS, NA = Cfg::NA, ST = Cfg::ST, MI = 2, DQ = 4, NI = KP / 8, XLD = Cfg::XLD;
+    constexpr int ROWB = Cfg::ROWB, WST = Cfg::WARP_STAGE, XT = Cfg::XT, STAGE = Cfg::STAGE;
+    extern __shared__ __align__(128) unsigned char smb[];
+    unsigned long long* fullr = reinterpret_cast<unsigned long long*>(smb + ST * STAGE);      // [warp][stage], count 1 + tx
+    unsigned long long* fullx = fullr + Cfg::WARPS * ST;                                          // [stage], 32 cp.async arrivals
+    unsigned long long* emptyx = fullx + ST;                                                      // [stage], one arrival per warp
+    const int inst = blockIdx.x >> 1, a_lo = (blockIdx.x & 1) * 8, layer = blockIdx.y;
+    if (active != nullptr && active[inst] == 0) return;
+    const long long item = (long long)inst * m + layer;
+    const long long np = (long long)DIM * K * DIM;
+    const double* Ws = P.W[layer] + (long long)inst * P.sW[layer];
+    const double* Wds = TAN ? P.Wd[layer] + (long long)inst * P.sWd[layer] : nullptr;
+    const double* xg = x + item * np;
+    const double* eg = TAN ? eta + item * np : nullptr;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int a = a_lo + warp;
+
+    if (tid == 0) {
+        for (int i = 0; i < Cfg::WARPS * ST; ++i) mbar_init(&fullr[i], 1);
+        for (int s = 0; s < ST; ++s) { mbar_init(&fullx[s], 32); mbar_init(&emptyx[s], Cfg::WARPS); }
+        mbar_fence_init();
+    }
+    for (int s = 0; s < ST; ++s) {                        // tiles start as zeros: pad columns and rows k >= K stay zero for good
+        double2* z = reinterpret_cast<double2*>(smb + s * STAGE + Cfg::WARPS * WST);
+        for (int i = tid; i < 2 * XT / 16; i += 256) z[i] = make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+
+    auto issue_rows = [&](int bb) {                       // lane 0 of every warp: rows {a,bb} of W (and Wd) into the warp's ring
+        const int s = bb % ST;
+        unsigned char* dst = smb + s * STAGE + warp * WST;
+        unsigned long long* bar = &fullr[warp * ST + s];
+        const int lo = a < bb ? a : bb, hi = a < bb ? bb : a;
+        const long long rs = (long long)pair_s(lo, hi, DIM) * L.Ds;
+        const bool off = a != bb;
+        const long long ra = off ? L.off_a + (long long)pair_a(lo, hi, DIM) * L.Da : 0;
+        mbar_arrive_expect_tx(bar, (unsigned)((NS * 8 + (off ? NA * 8 : 0)) * (TAN ? 2 : 1)));
+        bulk_g2s(dst, Ws + rs, NS * 8, bar);
+        if (off) bulk_g2s(dst + NS * 8, Ws + ra, NA * 8, bar);
+        if (TAN) {
+            bulk_g2s(dst + ROWB, Wds + rs, NS * 8, bar);
+            if (off) bulk_g2s(dst + ROWB + NS * 8, Wds + ra, NA * 8, bar);
+        }
+    };
+    auto issue_x = [&](int bb) {                          // one whole warp: x_bb (and eta_bb), rows (bb,k), 16-byte chunks
+        const int s = bb % ST;
+        unsigned char* xt = smb + s * STAGE + Cfg::WARPS * WST;
+#pragma unroll
+        for (int q = 0; q < KP / 4; ++q) {
+            const int k = (lane >> 3) + 4 * q;
+            if (k < K) {
+                const long long so = (long long)(bb * K + k) * DIM + (lane & 7) * 2;
+                cp_async16(xt + k * (XLD * 8) + (lane & 7) * 16, xg + so);
+                if (TAN) cp_async16(xt + XT + k * (XLD * 8) + (lane & 7) * 16, eg + so);
+            }
+        }
+        mbar_arrive_cp_async(&fullx[s]);
+    };
+    if (lane == 0) { issue_rows(0); issue_rows(1); }
+    if (warp < 2) issue_x(warp);
+
+    // per-lane constants.  Fragment element (i, dq): c = i*8 + g, d = dq*4 + t.  (0, dq>=2): c < d; (1, dq<2): c > d; the other
+    // four straddle the diagonal ("mixed", index q = i*2 + (dq&1)).  Addresses are 32-bit shared addresses of stage 0; stage, matrix
+    // and tile offsets are immediates of the loads.
+    const unsigned sm0 = (unsigned)__cvta_generic_to_shared(smb);
+    const unsigned zpad = sm0 + Cfg::WARPS * WST + DIM * 8;             // a zero pad of the x tile
+    unsigned pS[MI][DQ], pA[MI][DQ], pAd[4], sgm[4];
+    double cfm[4];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int dq = 0; dq < DQ; ++dq) {
+            const int c = i * 8 + g, dd = dq * 4 + t, lo = c < dd ? c : dd, hi = c < dd ? dd : c;
+            pS[i][dq] = sm0 + warp * WST + pair_s(lo, hi, DIM) * 8;
+            pA[i][dq] = (c == dd) ? zpad : sm0 + warp * WST + (NS + pair_a(lo, hi, DIM)) * 8;
+            if ((i == 0) == (dq < 2)) {
+                const int q = i * 2 + (dq & 1);
+                pAd[q] = (c == dd) ? zpad : pA[i][dq] + ROWB;
+                sgm[q] = (c > dd) ? 0x80000000u : 0u;
+                cfm[q] = (c == dd) ? 1.41421356237309504880 : 1.0;
+            }
+        }
+    const unsigned pU = sm0 + Cfg::WARPS * WST + (g * XLD + t) * 8;     // B fragments: x_b[k = j*8 + g][d = dq*4 + t]
+    double acc1[MI][NI][2], acc2[MI][NI][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) { acc1[i][j][0] = acc1[i][j][1] = 0.0; acc2[i][j][0] = acc2[i][j][1] = 0.0; }
+
+    struct Frag { double rs[MI], ra[MI], rds[MI], rda[MI], vx[NI], ve[NI]; };
+    // MODE: +1 (a < b), -1 (a > b), 0 (a == b: symmetric part only, weight sqrt2); SO: byte offset of the stage
+    auto load = [&](auto MODE_, auto SO_, auto DQ_, Frag& f) {
+        constexpr int MODE = decltype(MODE_)::value, SO = decltype(SO_)::value, dq = decltype(DQ_)::value;
+        static_for<MI>([&](auto I_) {
+            constexpr int i = decltype(I_)::value;
+            constexpr bool mixed = (i == 0) == (dq < 2);
+            constexpr int q = i * 2 + (dq & 1);
+            f.rs[i] = lds_f64<SO>(pS[i][dq]);
+            if (TAN) f.rds[i] = lds_f64<SO + ROWB>(pS[i][dq]);
+            if (MODE != 0) {
+                f.ra[i] = lds_f64<SO>(pA[i][dq]);
+                if (TAN) f.rda[i] = mixed ? lds_f64<SO>(pAd[q]) : lds_f64<SO + ROWB>(pA[i][dq]);
+            }
+        });
+        static_for<NI>([&](auto J_) {
+            constexpr int j = decltype(J_)::value;
+            f.vx[j] = lds_f64<SO + (j * 8 * XLD + dq * 4) * 8>(pU);
+            if (TAN) f.ve[j] = lds_f64<SO + XT + (j * 8 * XLD + dq * 4) * 8>(pU);
+        });
+    };
+    auto flip = [](double v, unsigned msk) { return __hiloint2double(__double2hiint(v) ^ (int)msk, __double2loint(v)); };
+    auto mma = [&](auto MODE_, auto DQ_, const Frag& f) {
+        constexpr int MODE = decltype(MODE_)::value, dq = decltype(DQ_)::value;
+        double wa[MI], wda[MI];
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+            const bool mixed = (i == 0) == (dq < 2);
+            const int q = i * 2 + (dq & 1);
+            if (MODE == 0) {
+                const double cf = mixed ? cfm[q] * 1.41421356237309504880 : 1.41421356237309504880;
+                wa[i] = cf * f.rs[i];
+                if (TAN) wda[i] = cf * f.rds[i];
+            } else if (!mixed) {
+                const bool plus = (i == 0) == (MODE > 0);             // sign of sigma_ab sigma_cd
+                wa[i] = plus ? f.rs[i] + f.ra[i] : f.rs[i] - f.ra[i];
+                if (TAN) wda[i] = plus ? f.rds[i] + f.rda[i] : f.rds[i] - f.rda[i];
+            } else {
+                const double ra = flip(f.ra[i], sgm[q]);
+                wa[i] = MODE > 0 ? fma(cfm[q], f.rs[i], ra) : fma(cfm[q], f.rs[i], -ra);
+                if (TAN) { const double rda = flip(f.rda[i], sgm[q]); wda[i] = MODE > 0 ? fma(cfm[q], f.rds[i], rda) : fma(cfm[q], f.rds[i], -rda); }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NI; ++j)
+#pragma unroll
+            for (int i = 0; i < MI; ++i) {
+                if (GRAD) dmma884(acc1[i][j][0], acc1[i][j][1], wa[i], f.vx[j]);
+                if (TAN) {
+                    dmma884(acc2[i][j][0], acc2[i][j][1], wa[i], f.ve[j]);
+                    dmma884(acc2[i][j][0], acc2[i][j][1], wda[i], f.vx[j]);
+                }
+            }
+    };
+    auto body = [&](auto MODE_, auto SO_) {                             // fragments of dq+1 are loaded before the DMMAs of dq
+        Frag f0, f1;
+        load(MODE_, SO_, std::integral_constant<int, 0>{}, f0);
+        load(MODE_, SO_, std::integral_constant<int, 1>{}, f1);
+        mma(MODE_, std::integral_constant<int, 0>{}, f0);
+        load(MODE_, SO_, std::integral_constant<int, 2>{}, f0);
+        mma(MODE_, std::integral_constant<int, 1>{}, f1);
+        load(MODE_, SO_, std::integral_constant<int, 3>{}, f1);
+        mma(MODE_, std::integral_constant<int, 2>{}, f0);
+        mma(MODE_, std::integral_constant<int, 3>{}, f1);
+    };
+
+    unsigned ph = 0;                                                    // parity of the ring's current round
+#pragma unroll 1
+    for (int b0 = 0; b0 < DIM; b0 += ST, ph ^= 1) {
+        static_for<ST>([&](auto S_) {
+            constexpr int s = decltype(S_)::value;
+            const int b = b0 + s;
+            if (b < DIM) {
+                if (b + 2 < DIM) {
+                    if (lane == 0) issue_rows(b + 2);                 // stage (b-1) % ST: this warp left it one iteration ago
+                    if (warp == (b & 7)) {
+                        if (b >= 1) mbar_wait(&emptyx[(s + 2) % ST], s == 0 ? ph ^ 1 : ph);     // every warp has left iteration b-1
+                        issue_x(b + 2);
+                    }
+                }
+                mbar_wait(&fullr[warp * ST + s], ph);
+                mbar_wait(&fullx[s], ph);
+                using SO = std::integral_constant<int, s * STAGE>;
+                if (b > a) body(std::integral_constant<int, 1>{}, SO{});
+                else if (b < a) body(std::integral_constant<int, -1>{}, SO{});
+                else body(std::integral_constant<int, 0>{}, SO{});
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&emptyx[s]);
+            }
+        });
+    }
 #pragma unroll
     for (int i = 0; i < MI; ++i) {
         const int c = i * 8 + g;

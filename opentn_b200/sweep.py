@@ -188,34 +188,51 @@ def gather_groups(res, ranks, n_taus, n_seeds, world, names=None):
         return res
     some = next(iter(res.values()))
     dev = some["f0"].device
+    # Layout of every rank's contribution, known to all ranks from the cell plan: K groups in the order of `ranks`, each
+    # counts[r][K] instances of width_K float64 values (all arrays of the group packed instance by instance; integers are exactly
+    # representable: indices, 32-bit seeds, status bits).  ONE collective carries the whole sweep.
+    plans = [plan_cells(ranks, n_taus, world, r) for r in range(world)]
+    counts = {K: [sum(1 for (kk, _) in plans[r] if kk == K) * n_seeds for r in range(world)] for K in ranks}
+    fields, width = {}, {}
+    for K in ranks:
+        mine = res.get(K)
+        fields[K] = [(name, tuple(mine[name].shape[1:]) if mine is not None else tuple(_tail_shape(name, like, K, some)), like.dtype)
+                     for name, like in some.items() if names is None or name in names]
+        width[K] = [int(np.prod(shape)) if shape else 1 for _, shape, _ in fields[K]]
+    offs = [{} for _ in range(world)]
+    for r in range(world):
+        o = 0
+        for K in ranks:
+            offs[r][K] = o
+            o += counts[K][r] * sum(width[K])
+        offs[r][None] = o
+    cap = max(offs[r][None] for r in range(world))
+    me = dist.get_rank()
+    flat = torch.zeros(max(cap, 1), dtype=torch.float64, device=dev)
+    for K in ranks:
+        mine = res.get(K)
+        if mine is None or counts[K][me] == 0:
+            continue
+        n = counts[K][me]
+        rows = torch.cat([mine[name].reshape(n, w).to(torch.float64) for (name, _, _), w in zip(fields[K], width[K])], dim=1)
+        flat[offs[me][K]: offs[me][K] + rows.numel()] = rows.reshape(-1)
+    parts = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(parts, flat)                         # (list form: also available on gloo, which the CPU tests use)
     out = {}
     for K in ranks:
-        # which ranks hold cells of this K, and how many instances each
-        counts = [sum(1 for (kk, _) in plan_cells(ranks, n_taus, world, r) if kk == K) * n_seeds for r in range(world)]
-        cap = max(counts)
-        mine = res.get(K)
-        # ONE collective per K group: every array of the group is packed, instance by instance, into a float64 row (integers are
-        # exactly representable: indices, 32-bit seeds, status bits)
-        fields = [(name, tuple(mine[name].shape[1:]) if mine is not None else tuple(_tail_shape(name, like, K, some)), like.dtype)
-                  for name, like in some.items() if names is None or name in names]
-        widths = [int(np.prod(shape)) if shape else 1 for _, shape, _ in fields]
-        pad = torch.zeros((cap, sum(widths)), dtype=torch.float64, device=dev)
-        if mine is not None:
-            o = 0
-            for (name, shape, _), w in zip(fields, widths):
-                pad[: mine[name].shape[0], o:o + w] = mine[name].reshape(mine[name].shape[0], w).to(torch.float64)
-                o += w
-        parts = [torch.empty_like(pad) for _ in range(world)]
-        dist.all_gather(parts, pad)                      # (list form: also available on gloo, which the CPU tests use)
-        full = torch.cat([parts[r][: counts[r]] for r in range(world)])
+        wk = sum(width[K])
+        full = torch.cat([parts[r][offs[r][K]: offs[r][K] + counts[K][r] * wk].view(counts[K][r], wk)
+                          for r in range(world) if counts[K][r]])
         merged, o = {}, 0
-        for (name, shape, dtype), w in zip(fields, widths):
-            merged[name] = full[:, o:o + w].reshape((full.shape[0],) + shape).to(dtype).contiguous()
+        for (name, shape, dtype), w in zip(fields[K], width[K]):
+            merged[name] = full[:, o:o + w].reshape((full.shape[0],) + shape).to(dtype)
             o += w
         if "tau_index" in merged and "seed" in merged:        # canonical order whatever the partition: by (tau index, seed)
             key = merged["tau_index"].to(torch.int64) * (1 << 32) + merged["seed"].to(torch.int64)
             order = torch.argsort(key)
             merged = {name: v[order] for name, v in merged.items()}
+        else:
+            merged = {name: v.contiguous() for name, v in merged.items()}
         out[K] = merged
     return out
 
