@@ -18,6 +18,7 @@
 // hits for the most recent ones); ordering = __threadfence() after the epilogue stores + the __syncthreads() every k-tile starts
 // with, and at least one whole product lies between a store and the first cp.async that reads it.
 #pragma once
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 
@@ -53,9 +54,13 @@ struct ChainCfg {
     static constexpr int PROD_WARPS = 4, PROD_THREADS = PROD_WARPS * 32;      // one producer warpgroup (cp.async)
     static constexpr int THREADS = (CONS_WARPS + PROD_WARPS) * 32;
     // registers: the producers give theirs up (setmaxnreg), the consumers take what the 64 K register file leaves
+    // setmaxnreg moves registers inside the pool the CTA was LAUNCHED with (launch registers x threads; what the SM has beyond that
+    // is not part of it -- asking for more blocks forever): the consumers get what the producers give up
     static constexpr int PROD_REGS = 56;
-    static constexpr int CONS_REGS_RAW = (65536 - PROD_THREADS * PROD_REGS) / (CONS_WARPS * 32);
-    static constexpr int CONS_REGS = (CONS_REGS_RAW > 232 ? 232 : CONS_REGS_RAW) / 8 * 8;
+    static constexpr int LAUNCH_REGS_RAW = 65536 / THREADS / 8 * 8;
+    static constexpr int LAUNCH_REGS = LAUNCH_REGS_RAW > 255 ? 248 : LAUNCH_REGS_RAW;
+    static constexpr int CONS_REGS_RAW = LAUNCH_REGS + PROD_THREADS * (LAUNCH_REGS - PROD_REGS) / (CONS_WARPS * 32) / 8 * 8;
+    static constexpr int CONS_REGS = CONS_REGS_RAW > 232 ? 232 : CONS_REGS_RAW;
     static constexpr int LDK = BK + 4;            // k-contiguous source:  [DT][BK + 4]
     static constexpr int LDM = DT + 4;            // m/n-contiguous source: [BK][DT + 4]
     static constexpr int OPER = DT * LDK;         // >= BK * LDM for DT >= 80
@@ -66,6 +71,9 @@ struct ChainCfg {
     __host__ __device__ static constexpr int tile_of_warp(int w) {
         if (DT == 144 && WM == 72 && WN == 24) return (int)((0xb975a8614320ULL >> (4 * w)) & 15);
         if (DT == 128 && WM == 64 && WN == 32) return (int)((0x64375210ULL >> (4 * w)) & 15);
+        // 16 warps of 32 x 32 on the 120-wide block: {16,16,12,12} MMA tiles on three sub-partitions, {16,16,16,9} on the fourth
+        // (57 of 225 at most; with 8 warps of 64 x 32 the best deal is 60)
+        if (DT == 128 && WM == 32 && WN == 32) return (int)((0xfb73aedc96418520ULL >> (4 * w)) & 15);
         return w;
     }
     static_assert(DT % WM == 0 && DT % WN == 0 && WM % 8 == 0 && WN % 8 == 0, "warp tiles must tile the block in 8 x 8 MMA tiles");
@@ -349,11 +357,13 @@ inline cudaError_t chain_launch_cfg(const ChainParams& p, int batch, cudaStream_
 
 inline bool chain_fused_supports(int D) { return D == 144 || D == 128; }
 // consumer warps = partial sums per instance and block
-inline int chain_fused_partials(int D) { return D == 144 ? 12 : 8; }
+inline bool chain_128_w8() { static const bool v = getenv("OTN_CHAIN_W8") != nullptr; return v; }   // env: A/B switch (8 warps of 64 x 32)
+inline int chain_fused_partials(int D) { return D == 144 ? 12 : (chain_128_w8() ? 8 : 16); }
 
 inline cudaError_t chain_launch(const ChainParams& p, int batch, cudaStream_t st) {
     if (p.D == 144) return chain_launch_cfg<144, 72, 24, 4>(p, batch, st);   // 12 consumer warps (3 per SM sub-partition) + 4 producer warps
-    if (p.D == 128) return chain_launch_cfg<128, 64, 32, 4>(p, batch, st);   //  8 consumer warps (2 per SM sub-partition) + 4 producer warps
+    if (p.D == 128 && chain_128_w8()) return chain_launch_cfg<128, 64, 32, 4>(p, batch, st);   //  8 consumer warps (2 per SM sub-partition)
+    if (p.D == 128) return chain_launch_cfg<128, 32, 32, 4>(p, batch, st);   // 16 consumer warps (4 per SM sub-partition) + 4 producer warps
     return cudaErrorInvalidValue;
 }
 
