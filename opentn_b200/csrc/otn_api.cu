@@ -837,7 +837,17 @@ static int build_layers(otn_problem* h, const double* x, const double* eta, int 
         OTN_TRY(set_smem(assemble_sym_kernel<DIMV, TG, PR>, sm));                                                    \
         assemble_sym_kernel<DIMV, TG, PR><<<items, 256, sm, h->stream>>>(x, eta, h->Y, h->Yd, h->sym, h->K, active, h->m); \
     } while (0)
-        if (h->dim == 16) { if (tangent && primal) ASM_SYM(16, true, true); else if (tangent) ASM_SYM(16, true, false); else ASM_SYM(16, false, true); }
+        static const bool v1 = getenv("OTN_ASM_V1") != nullptr;      // env: A/B switch for measurements (first version of the kernel)
+        if (h->dim == 16 && Kp <= 16 && !v1) {
+            const size_t sm2 = AsmSym2Cfg::smem_bytes(Kp, tangent);
+#define ASM_SYM2(TG, PR)                                                                                             \
+    do {                                                                                                             \
+        OTN_TRY(set_smem(assemble_sym2_kernel<TG, PR>, sm2));                                                        \
+        assemble_sym2_kernel<TG, PR><<<items, 256, sm2, h->stream>>>(x, eta, h->Y, h->Yd, h->sym, h->K, active, h->m); \
+    } while (0)
+            if (tangent && primal) ASM_SYM2(true, true); else if (tangent) ASM_SYM2(true, false); else ASM_SYM2(false, true);
+#undef ASM_SYM2
+        } else if (h->dim == 16) { if (tangent && primal) ASM_SYM(16, true, true); else if (tangent) ASM_SYM(16, true, false); else ASM_SYM(16, false, true); }
         else { if (tangent && primal) ASM_SYM(8, true, true); else if (tangent) ASM_SYM(8, true, false); else ASM_SYM(8, false, true); }
 #undef ASM_SYM
     } else if (h->dim == 16 || h->dim == 8) {

@@ -124,6 +124,139 @@ __global__ void __launch_bounds__(256) assemble_sym_kernel(const double* __restr
     }
 }
 
+// ---- assembly into blocks, second version (DIM = 16) ----------------------------------------------------------------------
+// ncu of assemble_sym_kernel (profiles/ncu_step_r02.txt): 14 instructions per DMMA, tensor pipe 51 % active, 37.7 M shared-memory
+// bank conflicts per launch (C fragments scattered with 8-byte stores into rows of 17 doubles, pair tables read per element).
+// Same decomposition -- one CTA per item, a warp computes the 16 x 16 product B = X_a^T X_b of a pair {a,b} with DMMA and folds it
+// into row {ab} of the symmetric and antisymmetric blocks -- but: a warp owns 17 CONSECUTIVE pairs (the a fragments stay in
+// registers while b runs), the product goes to shared memory twice, row-major in rows of 24 doubles (16-byte stores, conflict free)
+// and transposed in rows of 20 doubles (two wavefronts per store, the minimum), so that B[c][d] and B[d][c] are both read along
+// the output order; every per-lane index of the fold is computed once per kernel; x / eta arrive by cp.async.
+struct AsmSym2Cfg {
+    static constexpr int DIM = 16, NS = 136, NA = 120, LB = 24, LT = 20, SCR = DIM * LB + DIM * LT;     // doubles per warp
+    static size_t smem_bytes(int Kp, bool tangent) { return ((size_t)DIM * Kp * DIM * (tangent ? 2 : 1) + (size_t)8 * SCR) * 8; }
+};
+
+template <bool TANGENT, bool PRIMAL>
+__global__ void __launch_bounds__(256, 2) assemble_sym2_kernel(const double* __restrict__ x, const double* __restrict__ eta, double* __restrict__ Y,
+                                                               double* __restrict__ Yd, SymLayout L, int K, const int* active, int m) {
+    using Cfg = AsmSym2Cfg;
+    constexpr int DIM = Cfg::DIM, NS = Cfg::NS, MI = 2, LB = Cfg::LB, LT = Cfg::LT, RND = (NS + 31) / 32, PPW = NS / 8;
+    extern __shared__ __align__(16) double sm[];
+    const int item = blockIdx.x;
+    if (active != nullptr && active[item / m] == 0) return;
+    const int Kp = (K + 3) & ~3, rows = DIM * Kp, KQ = Kp / 4;
+    double* xs = sm;                                    // [a*Kp + k][16], 4-column groups XOR-swizzled by (row & 3)
+    double* es = xs + rows * DIM;
+    double* scr = es + (TANGENT ? rows * DIM : 0);
+    const long long np = (long long)DIM * K * DIM;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    for (int id = tid; id < rows * 8; id += 256) {      // 16-byte chunks
+        const int r = id >> 3, c = (id & 7) * 2, aa = r / Kp, k = r - aa * Kp;
+        const int o = r * DIM + (c ^ ((r & 3) << 2));
+        if (k < K) {
+            const long long so = (long long)item * np + (aa * K + k) * DIM + c;
+            cp_async16(xs + o, x + so);
+            if (TANGENT) cp_async16(es + o, eta + so);
+        } else {
+            xs[o] = xs[o + 1] = 0.0;
+            if (TANGENT) es[o] = es[o + 1] = 0.0;
+        }
+    }
+    cp_async_commit();
+
+    // fold constants of this lane: output columns ci = lane + 32 r of a block row <-> (c, d), c <= d
+    int offU[RND], offV[RND], pa[RND];
+    double wc[RND];
+#pragma unroll
+    for (int r = 0; r < RND; ++r) {
+        int ci = lane + 32 * r, c = 0;
+        if (ci >= NS) ci = NS - 1;                      // (masked at the store)
+        int rem = ci;
+        while (rem >= DIM - c) { rem -= DIM - c; ++c; }
+        const int dd = c + rem;
+        offU[r] = c * LB + dd;
+        offV[r] = DIM * LB + c * LT + dd;
+        pa[r] = (c < dd) ? pair_a(c, dd, DIM) : -1;
+        wc[r] = (c == dd) ? 0.70710678118654752440 : 1.0;
+    }
+    double* Bw = scr + warp * Cfg::SCR;                 // [16][LB] row-major | [16][LT] transposed
+    double* Ys = Y + (long long)item * L.slot;
+    double* Yds = Yd + (long long)item * L.slot;
+    cp_async_wait<0>();
+    __syncthreads();
+
+    // pairs pid = 17 warp .. 17 warp + 16 in the order of pair_s
+    int a = 0, b;
+    {
+        int rem = warp * PPW;
+        while (rem >= DIM - a) { rem -= DIM - a; ++a; }
+        b = a + rem;
+    }
+    const int fcol0 = g ^ (t << 2), fcol1 = (8 + g) ^ (t << 2);       // fragment columns c = 8 i + g behind the swizzle (row & 3 == t)
+    double xa[4][MI], ea[4][MI];
+    int a_loaded = -1;
+    auto fold = [&](const double (&acc)[MI][MI][2], double* Os, double* Oa, bool anti) {
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < MI; ++j) {
+                *reinterpret_cast<double2*>(Bw + (8 * i + g) * LB + 8 * j + 2 * t) = make_double2(acc[i][j][0], acc[i][j][1]);
+                Bw[DIM * LB + (8 * j + 2 * t) * LT + 8 * i + g] = acc[i][j][0];
+                Bw[DIM * LB + (8 * j + 2 * t + 1) * LT + 8 * i + g] = acc[i][j][1];
+            }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < RND; ++r) {
+            const double u = Bw[offU[r]], v = Bw[offV[r]];
+            if (r < RND - 1 || lane + 32 * r < NS) {
+                Os[lane + 32 * r] = wc[r] * (u + v);
+                if (anti && pa[r] >= 0) Oa[pa[r]] = u - v;
+            }
+        }
+        __syncwarp();
+    };
+#pragma unroll 1
+    for (int n = 0; n < PPW; ++n) {
+        if (a != a_loaded) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (q < KQ) {
+                    const int row = (a * Kp + 4 * q + t) * DIM;
+                    xa[q][0] = xs[row + fcol0]; xa[q][1] = xs[row + fcol1];
+                    if (TANGENT) { ea[q][0] = es[row + fcol0]; ea[q][1] = es[row + fcol1]; }
+                }
+            a_loaded = a;
+        }
+        double acc[MI][MI][2], accd[MI][MI][2];
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < MI; ++j) { acc[i][j][0] = acc[i][j][1] = 0.0; accd[i][j][0] = accd[i][j][1] = 0.0; }
+        const double nab = (a == b) ? 0.70710678118654752440 : 1.0;       // weight of a diagonal pair, folded into the b operand
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (q < KQ) {
+                const int row = (b * Kp + 4 * q + t) * DIM;
+                double xb[MI], eb[MI];
+                xb[0] = nab * xs[row + fcol0]; xb[1] = nab * xs[row + fcol1];
+                if (TANGENT) { eb[0] = nab * es[row + fcol0]; eb[1] = nab * es[row + fcol1]; }
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < MI; ++j) {
+                        if (PRIMAL) dmma884(acc[i][j][0], acc[i][j][1], xa[q][i], xb[j]);
+                        if (TANGENT) { dmma884(accd[i][j][0], accd[i][j][1], ea[q][i], xb[j]); dmma884(accd[i][j][0], accd[i][j][1], xa[q][i], eb[j]); }
+                    }
+            }
+        const long long rs = (long long)pair_s(a, b, DIM) * L.Ds;
+        const long long ra = L.off_a + ((a < b) ? (long long)pair_a(a, b, DIM) * L.Da : 0);
+        if (PRIMAL) fold(acc, Ys + rs, Ys + ra, a < b);
+        if (TANGENT) fold(accd, Yds + rs, Yds + ra, a < b);
+        if (++b == DIM) { ++a; b = a; }
+    }
+}
+
 // ---- adjoint of the assembly from cotangent blocks -----------------------------------------------------------------------
 // AS CTAs per instance, each owning DIM/AS values of the output index a; every CTA streams the rows {(a,b)}_a of Ws and Wa for
 // b = 0..DIM-1 through a 3-stage cp.async ring and feeds DMMA.  Versus the first version (dense tile decoded into shared
