@@ -130,10 +130,10 @@ __global__ void __launch_bounds__(256) assemble_sym_kernel(const double* __restr
 // Same decomposition -- one CTA per item, a warp computes the 16 x 16 product B = X_a^T X_b of a pair {a,b} with DMMA and folds it
 // into row {ab} of the symmetric and antisymmetric blocks -- but: a warp owns 17 CONSECUTIVE pairs (the a fragments stay in
 // registers while b runs), the product goes to shared memory twice, row-major in rows of 24 doubles (16-byte stores, conflict free)
-// and transposed in rows of 20 doubles (two wavefronts per store, the minimum), so that B[c][d] and B[d][c] are both read along
+// and transposed in rows of 18 doubles (every half-warp hits 16 distinct 8-byte banks), so that B[c][d] and B[d][c] are both read along
 // the output order; every per-lane index of the fold is computed once per kernel; x / eta arrive by cp.async.
 struct AsmSym2Cfg {
-    static constexpr int DIM = 16, NS = 136, NA = 120, LB = 24, LT = 20, SCR = DIM * LB + DIM * LT;     // doubles per warp
+    static constexpr int DIM = 16, NS = 136, NA = 120, LB = 24, LT = 18, SCR = DIM * LB + DIM * LT;     // doubles per warp
     static size_t smem_bytes(int Kp, bool tangent) { return ((size_t)DIM * Kp * DIM * (tangent ? 2 : 1) + (size_t)8 * SCR) * 8; }
 };
 
@@ -233,14 +233,18 @@ __global__ void __launch_bounds__(256, 2) assemble_sym2_kernel(const double* __r
         for (int i = 0; i < MI; ++i)
 #pragma unroll
             for (int j = 0; j < MI; ++j) { acc[i][j][0] = acc[i][j][1] = 0.0; accd[i][j][0] = accd[i][j][1] = 0.0; }
-        const double nab = (a == b) ? 0.70710678118654752440 : 1.0;       // weight of a diagonal pair, folded into the b operand
 #pragma unroll
         for (int q = 0; q < 4; ++q)
             if (q < KQ) {
                 const int row = (b * Kp + 4 * q + t) * DIM;
                 double xb[MI], eb[MI];
-                xb[0] = nab * xs[row + fcol0]; xb[1] = nab * xs[row + fcol1];
-                if (TANGENT) { eb[0] = nab * es[row + fcol0]; eb[1] = nab * es[row + fcol1]; }
+                xb[0] = xs[row + fcol0]; xb[1] = xs[row + fcol1];
+                if (TANGENT) { eb[0] = es[row + fcol0]; eb[1] = es[row + fcol1]; }
+                if (a == b) {                                           // weight 1/sqrt2 of a diagonal pair, folded into the b operand
+                    const double h = 0.70710678118654752440;
+                    xb[0] *= h; xb[1] *= h;
+                    if (TANGENT) { eb[0] *= h; eb[1] *= h; }
+                }
 #pragma unroll
                 for (int i = 0; i < MI; ++i)
 #pragma unroll
