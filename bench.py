@@ -989,13 +989,15 @@ def run_gpu(args):
         pass
     peak_source = ("cuBLAS DGEMM 8192^3 via torch.matmul, best of 3, measured in this run (MEASURED_PEAKS.json has no FP64 figure; "
                    "DMMA issue-rate ceiling 148 SM x 128 flop/clk x 1.965 GHz = 37.2 TFLOP/s)")
-    roofline = {"bound": "tensor", "kernel": "chain_fused_kernel<144,72,24,4> + chain_fused_kernel<128,64,32,4> (FP64 DMMA.8x8x4): one CTA per "
-                                             "instance and diagonal block runs all 18 chain products of a U1 (csrc/chain_fused.cuh); one launch per block and step",
-                "peak": peak_tf, "unit": "TFLOP/s", "traffic": 6.65e9,
-                "traffic_note": "dram read+write of one launch of the 144-block kernel over 1024 instances, ncu --set full "
-                                "(profiles/ncu_step_r02.txt: 4.64 GB + 2.01 GB; the 128-block launch: 3.14 + 1.58 GB).  Operand bytes of the 18 "
-                                "products counted once per product (36 reads + 12 writes of 144^2*8 B per instance) = 8.15e9 B: the "
-                                "re-reads of intermediates partly hit L2; the kernel is tensor-pipe bound (89 % active, DRAM 25 %)",
+    roofline = {"bound": "tensor", "kernel": "chain_fused_kernel<144,72,24,4> + chain_fused_kernel<128,32,32,4> (FP64 DMMA.8x8x4): one CTA per "
+                                             "instance and diagonal block runs all 18 chain products of a U1 (csrc/chain_fused.cuh); one launch per block and "
+                                             "pipeline chunk (512 instances), the two blocks' launches run concurrently and are timed as one group",
+                "peak": peak_tf, "unit": "TFLOP/s", "traffic": 5.51e9,
+                "traffic_note": "dram read+write of one timed group (both blocks, 512 instances), from ncu --set full of the 1024-instance "
+                                "launches (profiles/ncu_step_final_r02.txt: 144-block 4.66 GB read + 1.80 GB written, 128-block 3.16 + 1.39 GB), halved.  "
+                                "Operand bytes of the 18 products counted once per product (36 reads + 12 writes of 136^2*8 + 120^2*8 B per "
+                                "instance) = 6.5e9 B per group: the re-reads of intermediates partly hit L2; the kernels are tensor-pipe bound "
+                                "(85.5 % / 88.7 % active, DRAM 26-28 %)",
                 "peak_source": peak_source, "peak_committed_r01": peak_file}
     roofline.update(roofline_of(pms, pln, pfl, ms_prof, args.steps))
     roofline["note"] = ("launches_timed counts fork..join groups (both blocks' launches of a step run concurrently on two streams and are timed as one group). "

@@ -50,3 +50,33 @@ def test_n6_expm_on_device(n6, oracle):
     dt = time.perf_counter() - t0
     assert np.abs(got - T6).max() / np.abs(T6).max() < 1e-12
     print(f"otn_expm 4096^2: {dt:.2f} s incl. host<->device copies")
+
+
+def test_n6_rowsharded_cost_and_cotangents(n6, oracle, goldens):
+    """Config 5's building block at its real size: the row-sharded D = 4096 chain (RowShardedChain, world 1 here; two ranks in
+    test_gpu_rowsharded_multi.py) against the reference's N=6 cost anchor and against the handle path's gradient: the layer
+    cotangents W_l are pulled back with the oracle's adjoint of the Kronecker embedding and compared with StiefelFit's egrad-based
+    Riemannian gradient."""
+    import torch
+    from opentn_b200 import StiefelFit
+    from opentn_b200.rowsharded import RowShardedChain
+    P = oracle
+    T6, xs = n6
+    Ys = [torch.from_numpy(np.ascontiguousarray(np.real(y))).cuda() for y in P.local_layers_full(xs, 6, 2)]
+    Tre = torch.from_numpy(np.ascontiguousarray(T6.real)).cuda()
+    Tim = torch.from_numpy(np.ascontiguousarray(T6.imag)).cuda() if np.abs(T6.imag).max() > 0 else None
+    ch = RowShardedChain(4096)
+    f = ch.cost(Ys, Tre, Tim)
+    assert abs(f - goldens["known/n6_cost0"]) < 5e-9
+    assert abs(f - 0.5394470932876375) < 1e-11
+    if Tim is None:
+        f2, W = ch.cost_and_layer_cotangents(Ys, Tre)
+        assert abs(f2 - f) < 1e-12
+        spec = P.CostSpec(T6, "local", 6, 2)
+        fit = StiefelFit(T6, model="local", N=6, d=2, metric="euclidean")
+        _, g = fit.cost_grad(xs)
+        for l in range(len(xs)):
+            z = P._layer_vjp(spec, l, xs[l], W[l].cpu().numpy())
+            rg = P.gradient_ambient2riemannian(xs[l], z, 1.0, 1.0)
+            assert np.abs(rg - g[l]).max() / np.abs(g[l]).max() < 1e-9
+        fit.close()
