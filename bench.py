@@ -680,8 +680,69 @@ def c5_leg(torch, dist, rank, world, device, barrier, max_over_ranks, with_cpu):
             out["cpu"] = {"seconds_per_complex_product": t, "tflops_real_equivalent": 8.0 * D ** 3 / t / 1e12, "cores": os.cpu_count(),
                           "kind": "port", "sample": "one complex128 4096^3 product, numpy @ with all BLAS threads (transformations.py:850 on the host)"}
             out["speedup_vs_cpu"] = out["value_tflops"] / out["cpu"]["tflops_real_equivalent"]
+    torch.cuda.empty_cache()
+    out["fit"] = c5_fit_leg(torch, dist, rank, world, device, barrier, max_over_ranks)
     return out
 
+
+def c5_fit_leg(torch, dist, rank, world, device, barrier, max_over_ranks):
+    """Config 5 as a FIT: one dense N=6 instance (2-site ansatz, K = 16, m = 3 layers embedded to 4096 x 4096, Kitaev pbc target
+    exp(4L)), the whole unit of work U1 = (f, rgrad, H eta) and one trust-region iteration through a row-sharded handle
+    (StiefelFit.row_shard -> otn_rowshard_attach): every one of the 18 chain products of a U1 is split by rows, tiles stored into
+    all peers inside the GEMM, device-side barriers.  Efficiency against the un-sharded dense handle on one GPU, same run; results
+    bitwise equal.  (The factored evaluation does the same U1 in ~1.5 ms on one GPU without forming a D x D matrix: this leg is
+    about dense layers, the reference's formulation.)"""
+    import numpy as np
+    from opentn_b200 import StiefelFit
+    from opentn_b200 import transformations as T
+    T.set_device(device)
+    N, d, m, K, D = 6, 2, 3, 16, 4096
+    full = T.create_kitaev_liouvillians(N, d, 1.0, pbc=True, backend="cuda")[0]
+    target = np.ascontiguousarray(T.exp_operator_dt(full, 4.0, backend="cuda").real)
+    rng = np.random.default_rng(6)                              # same instance on every rank
+    xs = np.stack([np.linalg.qr(rng.standard_normal((4 * K, 4)))[0] for _ in range(m)])[None]
+    et = rng.standard_normal(xs.shape)
+    et = et - xs @ (0.5 * (np.swapaxes(xs, -1, -2) @ et + np.swapaxes(et, -1, -2) @ xs))     # tangent projection (stiefel.py:23-30)
+    xd, ed = torch.from_numpy(xs).cuda(), torch.from_numpy(et).cuda()
+    flops_u1 = 18 * 2.0 * D ** 3
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fit, reps=3):
+        outs = fit.triple(xd, ed)
+        barrier()
+        e0.record()
+        for _ in range(reps):
+            outs = fit.triple(xd, ed, out=outs)
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1)) / reps
+        barrier()
+        t0 = time.perf_counter()
+        _, rep = fit.tr_run(xd, niter=1)
+        torch.cuda.synchronize()
+        barrier()
+        tr_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+        return ms, outs, tr_ms, rep
+
+    solo = StiefelFit(target, model="local", N=N, d=d, metric="canonical", dense=True, device=device)
+    solo.triple(xd, ed)
+    stream = torch.cuda.current_stream()
+    ms1, o1, tr1, rep1 = timed(solo)
+    solo.close()
+    out = {"workload": f"dense N=6 2-site fit (D={D}, m={m}, K={K}): U1 = cost + Riemannian gradient + HVP = 18 real D^3 products, and one TR iteration",
+           "flops_per_u1": flops_u1,
+           "single_gpu": {"u1_ms": ms1, "tflops": flops_u1 / ms1 / 1e9, "tr_iteration_ms": tr1, "n_cg": int(rep1["n_cg"][0, 0]), "cost": float(o1[0][0])}}
+    if world > 1:
+        fit = StiefelFit(target, model="local", N=N, d=d, metric="canonical", dense=True, device=device).row_shard()
+        ms, o, trm, rep = timed(fit)
+        same = bool(torch.equal(o[0], o1[0]) and torch.equal(o[1], o1[1]) and torch.equal(o[2], o1[2]))
+        out["row_sharded"] = {"u1_ms": ms, "tflops": flops_u1 / ms / 1e9, "efficiency_vs_single_gpu": ms1 / (world * ms),
+                              "tr_iteration_ms": trm, "tr_efficiency_vs_single_gpu": tr1 / (world * trm), "n_cg": int(rep["n_cg"][0, 0]),
+                              "bitwise_equal_to_single_gpu": same, "tr_cost_equal": bool(np.array_equal(rep["f_iter"], rep1["f_iter"])),
+                              "barriers_ok": bool(fit.row_shard_ok())}
+        fit.close()
+    del stream
+    return out
 
 
 def run_gpu(args):

@@ -75,6 +75,10 @@ SIGNATURES = {
     "otn_ipc_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
     "otn_ipc_close": (C.c_int, [C.c_void_p, C.c_int]),
     "otn_ipc_free": (C.c_int, [C.c_void_p, C.c_int]),
+    "otn_rowshard_export": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "otn_rowshard_attach": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
+    "otn_rowshard_detach": (C.c_int, [C.c_void_p]),
+    "otn_rowshard_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "otn_expm": (C.c_int, [_dp, _dp, C.c_int, C.c_double, _dp, _dp, C.c_int]),
     "otn_super2ortho": (C.c_int, [_dp, C.c_int, C.c_int, C.c_int, _dp, C.c_int]),
     "otn_random_normal": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_int, _dp, C.c_int]),

@@ -39,8 +39,10 @@ struct GemmParams {
     double* partial;                         // partial sums: partial[b * partial_stride + tile]
     int partial_stride;                      // >= tiles of this launch (several launches may share one row per instance)
     // fused all-gather of a row-sharded product: every output tile is also stored into the same position of the peers'
-    // result matrices (NVLink peer-mapped pointers, batch == 1)
+    // result matrices (NVLink peer-mapped pointers; instance b at the same offset b * sC as in C), and the tile's partial sum
+    // into the peers' partial arrays (Ppeer[q] != nullptr: row-sharded handles, otn_rowshard_attach)
     double* Cpeer[7];
+    double* Ppeer[7];
     int npeer;
 };
 
@@ -194,7 +196,7 @@ gemm_dmma_kernel(const GemmParams p) {
                 part = fma(v.x, e.x, part); part = fma(v.y, e.y, part);
             }
             *reinterpret_cast<double2*>(C + row * D + col) = v;
-            for (int q = 0; q < p.npeer; ++q) *reinterpret_cast<double2*>(p.Cpeer[q] + row * D + col) = v;
+            for (int q = 0; q < p.npeer; ++q) *reinterpret_cast<double2*>(p.Cpeer[q] + (long long)b * p.sC + row * D + col) = v;
         }
     }
     if (p.epi != EPI_NONE) {
@@ -207,6 +209,8 @@ gemm_dmma_kernel(const GemmParams p) {
             double s = 0.0;
             for (int w = 0; w < Cfg::THREADS / 32; ++w) s += red[w];
             p.partial[(long long)b * p.partial_stride + tile] = s;
+            for (int q = 0; q < p.npeer; ++q)
+                if (p.Ppeer[q] != nullptr) p.Ppeer[q][(long long)b * p.partial_stride + tile] = s;
         }
     }
 }

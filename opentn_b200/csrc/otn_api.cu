@@ -302,6 +302,18 @@ struct otn_problem {
     int f_nsplit = 1;            // two-stage tile reduction when there are many tiles
     int *f_jrow = nullptr, *f_restrow = nullptr, *f_colidx = nullptr, *f_swaprow = nullptr;
     EmbedTables tables() const { return EmbedTables{tab, inv, D, q, nf}; }
+    // Row-sharded evaluation of the dense chain over the GPUs of one node (otn_rowshard_attach; BASELINE config 5): every rank
+    // holds the full handle and runs the whole program, but each chain product computes only the rows [rank D/world, ...) of its
+    // result and stores every tile (and the tile's partial sum) into the same array of all peers through IPC-mapped pointers.
+    struct RowShard {
+        enum { NARR = 8 };                       // arrays chain products write: P, G, W, Pd, Gd, Wd, part_f, part_s
+        int rank = 0, world = 1, epoch = 0;
+        double* base[NARR] = {}; size_t bytes[NARR] = {};
+        double* peer[NARR][7] = {};
+        int* flags = nullptr;                    // [64]: slot r = last epoch rank r has reached; slot 32 = time-out marker
+        int* peer_flags[7] = {};
+        bool exported = false;
+    } rs;
 };
 
 // Streamed submissions (otn_triple_submit) leave work in flight on the pipeline streams; every other entry point of the handle
@@ -328,6 +340,11 @@ extern "C" void otn_destroy(otn_problem* h) {
     if (!h) return;
     DeviceGuard dev_guard__(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int q = 0; q < 7; ++q) {            // row-sharded handle: unmap the peers' arrays
+        for (int a = 0; a < otn_problem::RowShard::NARR; ++a) if (h->rs.peer[a][q]) cudaIpcCloseMemHandle(h->rs.peer[a][q]);
+        if (h->rs.peer_flags[q]) cudaIpcCloseMemHandle(h->rs.peer_flags[q]);
+    }
+    if (h->rs.flags) cudaFree(h->rs.flags);
     if (h->prof.side.st) { cudaStreamSynchronize(h->prof.side.st); cudaStreamDestroy(h->prof.side.st); }
     if (h->s_back_own) { cudaStreamSynchronize(h->s_back_own); cudaStreamDestroy(h->s_back_own); }
     for (int i = 0; i < 2; ++i) if (h->s_backp[i]) { cudaStreamSynchronize(h->s_backp[i]); cudaStreamDestroy(h->s_backp[i]); }
@@ -719,7 +736,9 @@ extern "C" int otn_profile_read(otn_problem* h, double* ms, long long* launches,
 // pipeline pieces (all enqueue on h->stream; x / eta are device pointers [batch][m][np])
 // ---------------------------------------------------------------------------------------------------------------------
 // back stream (see otn_problem::s_back)
-static bool back_overlap(const otn_problem* h) { return h->s_back != nullptr && !h->prof.on && !h->prof.side.suspended && !h->factored; }
+static bool back_overlap(const otn_problem* h) {
+    return h->s_back != nullptr && !h->prof.on && !h->prof.side.suspended && !h->factored && h->rs.world == 1;   // row-sharded: one stream, see rs_barrier
+}
 // the back stream waits for everything enqueued so far on the main stream and, if the antisymmetric chain is out on it, the side stream
 static cudaStream_t back_begin(otn_problem* h) {
     cudaEventRecord(h->ev_bk_main, h->stream);
@@ -741,6 +760,45 @@ static void back_sync(otn_problem* h) {
     h->back_wd_pending = false;
 }
 
+// Row-sharded handles: device-side barrier between the ranks.  Every rank raises its slot in the flag array of every peer and spins
+// until all slots of its own array have reached the epoch (the same scheme as otn_peer_signal / otn_peer_wait, one kernel).  The
+// kernel before it on the stream has written its tiles into the peers' arrays: the system-scope fence orders those stores before
+// the flag.  A rank whose peers never arrive (a host-side failure over there) gives up after 30 s and marks slot 32 instead of
+// hanging the GPU; otn_rowshard_status reports it.
+struct RsPeerFlags { int* p[7]; };
+__global__ void rs_barrier_kernel(RsPeerFlags peers, volatile int* mine, int world, int rank, int epoch) {
+    __threadfence_system();
+    const int t = threadIdx.x;
+    if (t < world - 1) { volatile int* f = peers.p[t] + rank; *f = epoch; }
+    __threadfence_system();
+    if (t < world && t != rank) {
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (mine[t] < epoch) {
+            __nanosleep(100);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 30000000000ULL) { mine[32] = epoch; break; }
+        }
+    }
+    __threadfence_system();
+}
+static cudaError_t rs_barrier(otn_problem* h, cudaStream_t st) {
+    RsPeerFlags P{};
+    for (int q = 0; q < h->rs.world - 1; ++q) P.p[q] = h->rs.peer_flags[q];
+    rs_barrier_kernel<<<1, 32, 0, st>>>(P, h->rs.flags, h->rs.world, h->rs.rank, ++h->rs.epoch);
+    ++g_launches;
+    return cudaGetLastError();
+}
+// the same position inside peer q's copy of the array `ptr` points into
+static double* rs_peer(const otn_problem* h, int q, const double* ptr) {
+    for (int a = 0; a < otn_problem::RowShard::NARR; ++a) {
+        const char* lo = reinterpret_cast<const char*>(h->rs.base[a]);
+        const char* c = reinterpret_cast<const char*>(ptr);
+        if (lo != nullptr && c >= lo && c < lo + h->rs.bytes[a]) return reinterpret_cast<double*>(reinterpret_cast<char*>(h->rs.peer[a][q]) + (c - lo));
+    }
+    return nullptr;
+}
+
 // one chain product = one launch per diagonal block (1 block in the dense formulation, 2 in the structured one)
 static cudaError_t hgemm(otn_problem* h, const GemmParams& p0, bool ta, bool tb) {
     for (int i = 0; i < h->nblk; ++i) {
@@ -751,15 +809,39 @@ static cudaError_t hgemm(otn_problem* h, const GemmParams& p0, bool ta, bool tb)
         p.A1 += o; p.B1 += o; p.C += o;
         if (p.A2) { p.A2 += o; p.B2 += o; }
         if (p.epi != EPI_NONE) { p.E += o; p.partial += h->blkTileOff[i]; p.partial_stride = h->tiles; }
+        if (h->rs.world > 1) {
+            // Row window of this rank, tiles (and partial sums) also stored into every peer.  Barrier BEFORE the product: no peer
+            // may still be reading (in a replicated kernel enqueued since the last product) the array this product overwrites over
+            // there; barrier AFTER it: the result is complete on every rank before anything reads it.  Everything of a row-sharded
+            // handle runs on h->stream (no side / back stream), so stream order on each rank plus the two barriers is the whole
+            // ordering argument.
+            const int rows = p.D / h->rs.world;
+            p.row0 = h->rs.rank * rows; p.rows = rows;
+            if (p.epi != EPI_NONE) p.partial += h->rs.rank * gemm_plan(p.D, rows, 1).tiles;
+            p.npeer = h->rs.world - 1;
+            for (int q = 0; q < p.npeer; ++q) {
+                p.Cpeer[q] = rs_peer(h, q, p.C);
+                p.Ppeer[q] = (p.epi != EPI_NONE) ? rs_peer(h, q, p.partial) : nullptr;
+                if (p.Cpeer[q] == nullptr || (p.epi != EPI_NONE && p.Ppeer[q] == nullptr)) return cudaErrorInvalidValue;
+            }
+            cudaError_t eb = rs_barrier(h, h->stream);
+            if (eb != cudaSuccess) return eb;
+        }
         // executed flops: zero-padded k-steps beyond kvalid are skipped by the kernel
         cudaStream_t st = h->stream;
         if (h->nblk == 2 && h->prof.side.active()) {
             h->prof.fork(h->stream);                  // (first product after a join; no-op while the side stream is busy)
             if (i == 1) st = h->prof.side.st;
         }
-        ProfScope ps(&h->prof, st, CAT_GEMM, 2.0 * p.D * (double)p.rows * (p.kvalid > 0 ? p.kvalid : p.D) * p.batch * (p.A2 ? 2 : 1));
-        cudaError_t e = gemm_launch(p, ta, tb, st);
-        if (e != cudaSuccess) return e;
+        {
+            ProfScope ps(&h->prof, st, CAT_GEMM, 2.0 * p.D * (double)p.rows * (p.kvalid > 0 ? p.kvalid : p.D) * p.batch * (p.A2 ? 2 : 1));
+            cudaError_t e = gemm_launch(p, ta, tb, st);
+            if (e != cudaSuccess) return e;
+        }
+        if (h->rs.world > 1) {
+            cudaError_t eb = rs_barrier(h, h->stream);
+            if (eb != cudaSuccess) return eb;
+        }
     }
     return cudaSuccess;
 }
@@ -1654,7 +1736,7 @@ extern "C" int otn_triple(otn_problem* h, const double* x, const double* eta, in
     if (!x || !eta) return fail("null argument");
     const bool all_host = !is_device_ptr(x) && !is_device_ptr(eta) && (!f || !is_device_ptr(f)) && (!rgrad || !is_device_ptr(rgrad)) &&
                           (!heta || !is_device_ptr(heta));
-    if (all_host && batch >= 512) return triple_pipelined(h, x, eta, batch, f, rgrad, heta);
+    if (all_host && batch >= 512 && h->rs.world == 1) return triple_pipelined(h, x, eta, batch, f, rgrad, heta);
     const void *xd, *ed; void *fd, *gd, *hd;
     OTN_TRY(stage_in(x, xbytes(h, batch), h->in_x, h->stream, &xd));
     OTN_TRY(stage_in(eta, xbytes(h, batch), h->in_eta, h->stream, &ed));
@@ -1676,6 +1758,7 @@ extern "C" int otn_triple_submit(otn_problem* h, const double* x, const double* 
     OTN_TRY(check_batch(h, batch, /*drain=*/false));
     DeviceGuard dev_guard__(h->device);
     if (!x || !eta || !ticket) return fail("null argument");
+    if (h->rs.world > 1) return fail("otn_triple_submit: not available on a row-sharded handle (use otn_triple)");
     const bool dx = is_device_ptr(x);
     if (dx) {
         if (!f || !rgrad || !heta) return fail("otn_triple_submit with device arrays needs f, rgrad and heta");
@@ -2014,6 +2097,111 @@ extern "C" int otn_ipc_free(void* ptr, int device) {
     OTN_TRY(use_device(device));
     DeviceGuard dev_guard__(device);
     CUDA_TRY(cudaFree(ptr));
+    return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// row-sharded handles (BASELINE config 5: one dense N = 6 instance over the GPUs of a node)
+// ---------------------------------------------------------------------------------------------------------------------
+// One process per GPU, each with an identical handle (same sizes, target, OTN_FLAG_DENSE).  Protocol:
+//   otn_rowshard_export(h, mine)           -> 9 IPC handles (P, G, W, Pd, Gd, Wd, part_f, part_s, flags) of this rank
+//   (exchange `mine` between the ranks: all-gather of 9 * 64 bytes)
+//   otn_rowshard_attach(h, rank, world, all)   all = [world][9][64]
+// From then on every entry point of the handle (otn_cost, otn_cost_grad, otn_triple, otn_hvp_cached, otn_tr_run, ...) must be
+// called by ALL ranks with the same arguments: the replicated kernels (assembly, embedding, pull-backs, Riemannian epilogue, tCG)
+// run everywhere on identical data, the chain products are split by rows (hgemm).  Results are bitwise equal on every rank and
+// bitwise equal to the un-sharded handle (same tiles, same fixed-order partial sums).
+static int rs_arrays(otn_problem* h, double** base, size_t* bytes) {
+    const size_t B = (size_t)h->max_batch, SZ = (size_t)h->SZ, M = (size_t)h->m;
+    double* b[otn_problem::RowShard::NARR] = {h->P, h->G, h->W, h->Pd, h->Gd, h->Wd, h->part_f, h->part_s};
+    const size_t n[otn_problem::RowShard::NARR] = {B * M * SZ * 8, B * M * SZ * 8, B * M * SZ * 8, B * M * SZ * 8, B * 2 * SZ * 8,
+                                                   B * (size_t)h->wd_stride * 8, B * h->tiles * 8, B * h->tiles * 8};
+    for (int a = 0; a < otn_problem::RowShard::NARR; ++a) { base[a] = b[a]; bytes[a] = n[a]; }
+    return 0;
+}
+static int rs_check_handle(const otn_problem* h) {
+    if (!h) return fail("null handle");
+    if (h->structured || h->factored || h->fused || h->cplx)
+        return fail("row sharding applies to the dense chain: create the handle with OTN_FLAG_DENSE (real isometries)");
+    return 0;
+}
+
+extern "C" int otn_rowshard_export(otn_problem* h, unsigned char* handles) {
+    OTN_TRY(rs_check_handle(h));
+    if (!handles) return fail("null argument");
+    OTN_TRY(drain_pipeline(h));
+    DeviceGuard dev_guard__(h->device);
+    if (h->rs.flags == nullptr) {
+        CUDA_TRY(cudaMalloc(&h->rs.flags, 64 * sizeof(int)));
+        CUDA_TRY(cudaMemset(h->rs.flags, 0, 64 * sizeof(int)));
+    }
+    OTN_TRY(rs_arrays(h, h->rs.base, h->rs.bytes));
+    for (int a = 0; a <= otn_problem::RowShard::NARR; ++a) {
+        cudaIpcMemHandle_t hd;
+        void* ptr = (a < otn_problem::RowShard::NARR) ? (void*)h->rs.base[a] : (void*)h->rs.flags;
+        CUDA_TRY(cudaIpcGetMemHandle(&hd, ptr));
+        std::memcpy(handles + (size_t)a * 64, &hd, 64);
+    }
+    h->rs.exported = true;
+    return 0;
+}
+
+extern "C" int otn_rowshard_detach(otn_problem* h) {
+    if (!h) return fail("null handle");
+    DeviceGuard dev_guard__(h->device);
+    if (h->stream) CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for (int q = 0; q < 7; ++q) {
+        for (int a = 0; a < otn_problem::RowShard::NARR; ++a)
+            if (h->rs.peer[a][q]) { cudaIpcCloseMemHandle(h->rs.peer[a][q]); h->rs.peer[a][q] = nullptr; }
+        if (h->rs.peer_flags[q]) { cudaIpcCloseMemHandle(h->rs.peer_flags[q]); h->rs.peer_flags[q] = nullptr; }
+    }
+    h->rs.world = 1; h->rs.rank = 0;
+    return 0;
+}
+
+extern "C" int otn_rowshard_attach(otn_problem* h, int rank, int world, const unsigned char* all_handles) {
+    OTN_TRY(rs_check_handle(h));
+    if (!all_handles) return fail("null argument");
+    if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail("rank %d / world %d outside [0, 8]", rank, world);
+    if (!h->rs.exported) return fail("otn_rowshard_attach: call otn_rowshard_export first");
+    if (h->rs.world > 1) return fail("handle is already row-sharded (otn_rowshard_detach first)");
+    if (h->D % (64 * world) != 0) return fail("row sharding needs D = %d to be a multiple of 64 * world = %d", h->D, 64 * world);
+    if (gemm_plan(h->D, h->D / world, 1).kind != gemm_plan(h->D, h->D, 1).kind) return fail("row window changes the tile shape");
+    OTN_TRY(drain_pipeline(h));
+    DeviceGuard dev_guard__(h->device);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    int k = 0;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) continue;
+        for (int a = 0; a <= otn_problem::RowShard::NARR; ++a) {
+            cudaIpcMemHandle_t hd;
+            std::memcpy(&hd, all_handles + ((size_t)r * (otn_problem::RowShard::NARR + 1) + a) * 64, 64);
+            void* ptr = nullptr;
+            const cudaError_t e = cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                fail("cudaIpcOpenMemHandle (rank %d, array %d) failed: %s", r, a, cudaGetErrorString(e));
+                h->rs.world = 1; otn_rowshard_detach(h);
+                return -1;
+            }
+            if (a < otn_problem::RowShard::NARR) h->rs.peer[a][k] = (double*)ptr; else h->rs.peer_flags[k] = (int*)ptr;
+        }
+        ++k;
+    }
+    h->rs.rank = rank; h->rs.world = world; h->rs.epoch = 0;
+    h->cached_batch = 0;
+    return 0;
+}
+
+// 0 = healthy; 1 = a device-side barrier of this rank timed out (a peer never arrived): results since then are garbage
+extern "C" int otn_rowshard_status(otn_problem* h, int* timed_out) {
+    if (!h || !timed_out) return fail("null argument");
+    *timed_out = 0;
+    if (h->rs.flags == nullptr) return 0;
+    DeviceGuard dev_guard__(h->device);
+    int v = 0;
+    CUDA_TRY(cudaMemcpy(&v, h->rs.flags + 32, sizeof(int), cudaMemcpyDeviceToHost));
+    *timed_out = v != 0;
     return 0;
 }
 

@@ -131,7 +131,8 @@ extern "C" int otn_tr_run(otn_problem* h, double* x, int batch, const otn_tr_par
     // (stream capture cannot begin on the legacy default stream -- which is what otn_set_stream(h, 0) selects, e.g. torch's default
     // stream handle -- nor is it worth it on the per-thread default stream: plain launches there)
     const bool capturable = st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
-    const bool use_graph = small_batch && capturable && !h->prof.on && getenv("OTN_NO_GRAPH") == nullptr;   // env: A/B switch for measurements
+    const bool use_graph = small_batch && capturable && !h->prof.on && h->rs.world == 1 &&   // (a row-sharded handle's barrier epochs are launch arguments)
+                           getenv("OTN_NO_GRAPH") == nullptr;   // env: A/B switch for measurements
     struct SideSuspend {       // the captured tCG step stays on one stream
         SideStream& s; bool prev;
         SideSuspend(SideStream& s_, bool on) : s(s_), prev(s_.suspended) { if (on) s.suspended = true; }

@@ -137,6 +137,7 @@ class StiefelFit:
         self._tindex = None
         self._tindex_ver = 0
         self._cached = None
+        self._row_shard = None
         self.p = d ** N if model == "full" else d * d
         self.last_report = None
 
@@ -159,7 +160,53 @@ class StiefelFit:
             h.tindex_ver = 0
             h.tindex_len = cap
             self._handles[key] = h
+            if self._row_shard is not None:
+                self._attach_rows(h)
         return h
+
+    # ------------------------------------------------------------------ row sharding (BASELINE config 5)
+    def row_shard(self, group=None):
+        """Shard every chain product of this fit by rows over the ranks of `group` (default: the world group of
+        `torch.distributed`; one process per GPU of ONE node, `device` = this rank's GPU).  From here on ALL ranks must make the
+        same calls with the same arguments (cost / cost_grad / triple / hvp / tr_run ...): the D x D products -- what
+        `jax.grad` / `jax.jvp` spend their time on at D = 4096 (stiefel.py:423, 520) -- are split, each tile is stored into all
+        peers over NVLink inside the GEMM kernel, the small kernels run replicated.  Results are bitwise equal on every rank
+        and to the un-sharded fit.  Needs `dense=True` and D % (64 * world) == 0."""
+        import torch.distributed as dist
+        if self.dense is not True or self.factored:
+            raise ValueError("row_shard needs StiefelFit(..., dense=True): it shards the dense chain products")
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("row_shard needs an initialised torch.distributed process group")
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        if world > 8 or self.D % (64 * world) != 0:
+            raise ValueError(f"row_shard: D = {self.D} must be a multiple of 64 * world ({world} ranks, at most 8)")
+        self._row_shard = (rank, world, group)
+        for h in self._handles.values():
+            self._attach_rows(h)
+        return self
+
+    def _attach_rows(self, h: "_Handle"):
+        import torch.distributed as dist
+        rank, world, group = self._row_shard
+        if world == 1 or getattr(h, "row_sharded", False):
+            return
+        mine = C.create_string_buffer(9 * 64)
+        check(h._lib.otn_rowshard_export(h.h, mine))
+        allh = [None] * world
+        dist.all_gather_object(allh, bytes(mine.raw), group=group)
+        check(h._lib.otn_rowshard_attach(h.h, rank, world, b"".join(allh)))
+        h.row_sharded = True
+        dist.barrier(group=group)          # every rank has mapped its peers before the first product stores into them
+
+    def row_shard_ok(self) -> bool:
+        """False when a device-side barrier of this rank ever timed out (a peer stopped making the common calls)."""
+        ok = True
+        for h in self._handles.values():
+            if getattr(h, "row_sharded", False):
+                v = C.c_int()
+                check(h._lib.otn_rowshard_status(h.h, C.byref(v)))
+                ok = ok and v.value == 0
+        return ok
 
     def set_target_index(self, index):
         """Target id of each instance of subsequent batched calls (default all 0)."""
@@ -445,6 +492,16 @@ class StiefelFit:
         return (xw[0] if single else xw), report
 
     def close(self):
+        sharded = [h for h in self._handles.values() if getattr(h, "row_sharded", False)]
+        if sharded and self._row_shard is not None:
+            # collective: every rank unmaps its peers' arrays before any rank frees its own
+            import torch.distributed as dist
+            group = self._row_shard[2]
+            dist.barrier(group=group)
+            for h in sharded:
+                check(h._lib.otn_rowshard_detach(h.h))
+                h.row_sharded = False
+            dist.barrier(group=group)
         for h in self._handles.values():
             h.close()
         self._handles = {}

@@ -1,0 +1,142 @@
+"""Row-sharded HANDLE (otn_rowshard_attach / StiefelFit.row_shard; BASELINE config 5): every chain product of a full
+unit of work -- cost, Riemannian gradient, Hessian-vector product, trust-region iterations -- is split by rows over the ranks,
+each tile stored into all peers inside the GEMM kernel, ranks ordered by device-side barriers.
+
+Checked against the ORACLE (cost 1e-12, gradient / HVP 1e-10 relative) and, bitwise, against the un-sharded handle on the same
+GPU.  Two layouts: one process per GPU (needs >= 2 GPUs; NCCL world), and BOTH ranks on GPU 0 (gloo world; CUDA IPC maps the
+peer's arrays inside the same device, the two contexts time-slice) so that the sharded path is also exercised on a one-GPU box."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _problem(P, model, rng):
+    N, d = 4, 2
+    if model == "local":
+        m, K = 3, 4
+        xs = [P.random_stiefel(4 * K, 4, rng) for _ in range(m)]
+        T = P.exp_operator_dt(P.create_2local_liouvillians(P.get_kitaev_nn_linbladian(1.0), N, d, pbc=True)[0], 0.5)
+    else:
+        m, K = 3, 3
+        xs = [P.random_stiefel(16 * K, 16, rng) for _ in range(m)]
+        T = P.model_Ys_stiefel([P.random_stiefel(16 * K, 16, rng) for _ in range(m)]) + 0.05 * rng.standard_normal((256, 256))
+    etas = [P.project(x, rng.standard_normal(x.shape)) for x in xs]
+    return N, d, T, xs, etas
+
+
+def _worker(rank, world, port, out_dir, same_gpu):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dev = 0 if same_gpu else rank
+    torch.cuda.set_device(dev)
+    if same_gpu:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    else:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", dev))
+    from opentn_b200 import StiefelFit
+    from oracle import port as P
+    for model in ("local", "full"):
+        rng = np.random.default_rng(11)                 # the same problem on every rank
+        N, d, T, xs, etas = _problem(P, model, rng)
+        spec = P.CostSpec(T, model, N, d) if model == "local" else P.CostSpec(T, "full")
+        fo, go, ho = P.triple(spec, xs, etas, "canonical")
+        ref = StiefelFit(T, model=model, N=N, d=d, metric="canonical", dense=True, device=dev)      # un-sharded, same GPU
+        f1, g1, h1 = ref.triple(np.array(xs), np.array(etas))
+        x1, rep1 = ref.tr_run(np.array(xs), niter=3)
+        ref.close()
+        fit = StiefelFit(T, model=model, N=N, d=d, metric="canonical", dense=True, device=dev).row_shard()
+        for _ in range(2):                              # repeated: the barrier epochs must stay consistent
+            f, g, h = fit.triple(np.array(xs), np.array(etas))
+            assert abs(f - fo) < 1e-12 * max(1.0, abs(fo))
+            assert np.abs(g - np.array(go)).max() / np.abs(np.array(go)).max() < 1e-10
+            assert np.abs(h - np.array(ho)).max() / np.abs(np.array(ho)).max() < 1e-10
+            assert f == f1 and np.array_equal(g, g1) and np.array_equal(h, h1)          # bitwise equal to the un-sharded handle
+        # the other entry points: cost, cost + gradient, cached HVP, model matrix
+        assert fit(np.array(xs)) == f1
+        fc, gc = fit.cost_grad(np.array(xs))
+        assert fc == f1 and np.array_equal(gc, g1)
+        assert np.array_equal(fit.hvp_cached(np.array(etas)), h1)
+        # trust region: all ranks take the same decisions, iterates bitwise equal to the un-sharded solver
+        x2, rep2 = fit.tr_run(np.array(xs), niter=3)
+        assert np.array_equal(rep2["f_iter"], rep1["f_iter"]) and np.array_equal(rep2["n_cg"], rep1["n_cg"])
+        assert np.array_equal(x2, x1)
+        _, f_it, _, _ = P.trust_region_fit(spec, xs, "canonical", niter=3)
+        assert np.allclose(rep2["f_iter"][:, 0], f_it, rtol=1e-9)
+        assert fit.row_shard_ok()
+        # every rank holds the same numbers
+        mine = torch.from_numpy(np.concatenate([[f], g.ravel(), h.ravel(), x2.ravel()]))
+        if not same_gpu:
+            mine = mine.cuda()
+        both = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(both, mine)
+        assert all(torch.equal(b, both[0]) for b in both)
+        fit.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+
+
+def _spawn(world, tmp_path, same_gpu):
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), same_gpu), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
+
+
+@pytest.mark.timeout(600)
+def test_rowshard_handle_two_ranks_one_gpu(tmp_path):
+    """Both ranks on GPU 0: the peer arrays are CUDA-IPC mappings inside the same device."""
+    _spawn(2, tmp_path, same_gpu=True)
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("world", [2, 4])
+def test_rowshard_handle_one_rank_per_gpu(tmp_path, world):
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    _spawn(world, tmp_path, same_gpu=False)
+
+
+def test_rowshard_rejects_structured_handles():
+    """Only the dense chain is sharded: block-diagonal / factored / complex handles are refused with a clear error."""
+    import ctypes as C
+    from opentn_b200 import StiefelFit, _lib
+    from oracle import port as P
+    rng = np.random.default_rng(0)
+    xs = np.array([P.random_stiefel(16, 4, rng) for _ in range(3)])
+    T = P.exp_operator_dt(P.create_2local_liouvillians(P.get_kitaev_nn_linbladian(1.0), 4, 2, pbc=True)[0], 0.5)
+    fit = StiefelFit(T, model="local", N=4, d=2)          # AUTO -> factored
+    fit(xs)
+    (h,) = fit._handles.values()
+    buf = C.create_string_buffer(9 * 64)
+    assert h._lib.otn_rowshard_export(h.h, buf) != 0
+    assert b"OTN_FLAG_DENSE" in h._lib.otn_last_error()
+    with pytest.raises(ValueError, match="dense=True"):
+        fit.row_shard()
+    fit.close()
+    # a dense handle that was never exported cannot be attached; a world that does not divide D is refused
+    fit = StiefelFit(T, model="local", N=4, d=2, dense=True)
+    fit(xs)
+    (h,) = fit._handles.values()
+    assert h._lib.otn_rowshard_attach(h.h, 0, 2, bytes(2 * 9 * 64)) != 0
+    assert h._lib.otn_rowshard_export(h.h, buf) == 0
+    assert h._lib.otn_rowshard_attach(h.h, 0, 3, bytes(3 * 9 * 64)) != 0
+    assert b"multiple of 64" in h._lib.otn_last_error()
+    fit.close()
