@@ -728,10 +728,23 @@ def c5_fit_leg(torch, dist, rank, world, device, barrier, max_over_ranks):
     solo.triple(xd, ed)
     stream = torch.cuda.current_stream()
     ms1, o1, tr1, rep1 = timed(solo)
+    # where the single-GPU time goes (per-launch CUDA events; the kernels outside the chain are replicated on every rank)
+    import ctypes as C
+    from opentn_b200 import _lib
+    lib = _lib.load()
+    (hd,) = solo._handles.values()
+    lib.otn_profile_enable(hd.h, 1)
+    solo.triple(xd, ed, out=o1)
+    pms = (C.c_double * 6)(); pln = (C.c_longlong * 6)(); pfl = (C.c_double * 6)()
+    _lib.check(lib.otn_profile_read(hd.h, pms, pln, pfl))
+    lib.otn_profile_enable(hd.h, 0)
+    breakdown = {"chain_products_ms": pms[0], "kraus_assembly_and_embedding_ms": pms[1], "back_embedding_and_pull_back_ms": pms[2],
+                 "riemannian_epilogue_ms": pms[3], "launches": int(sum(pln))}
     solo.close()
     out = {"workload": f"dense N=6 2-site fit (D={D}, m={m}, K={K}): U1 = cost + Riemannian gradient + HVP = 18 real D^3 products, and one TR iteration",
            "flops_per_u1": flops_u1,
-           "single_gpu": {"u1_ms": ms1, "tflops": flops_u1 / ms1 / 1e9, "tr_iteration_ms": tr1, "n_cg": int(rep1["n_cg"][0, 0]), "cost": float(o1[0][0])}}
+           "single_gpu": {"u1_ms": ms1, "tflops": flops_u1 / ms1 / 1e9, "tr_iteration_ms": tr1, "n_cg": int(rep1["n_cg"][0, 0]), "cost": float(o1[0][0]),
+                          "profiled_u1_ms_by_category": breakdown}}
     if world > 1:
         fit = StiefelFit(target, model="local", N=N, d=d, metric="canonical", dense=True, device=device).row_shard()
         ms, o, trm, rep = timed(fit)

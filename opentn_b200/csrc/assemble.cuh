@@ -186,6 +186,108 @@ __global__ void __launch_bounds__(BEM_THREADS) back_embed_kernel(const double* _
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// back_embed for three Kronecker factors of side 16 (N = 6, d = 2: D = 4096), dense layout.  back_embed_kernel above gathers
+// every W[r,c] once per factor with 8-byte scattered loads from 96 CTAs (1.4 ms per layer and pass at D = 4096 -- more than a
+// row-sharded chain product on 8 GPUs).  Here the adjoint is contracted factor by factor, reading W in whole rows:
+//   stage 1 (WHICH = 2):  A[(i0,i1),(j0,j1)] = sum_{i2,j2} W[r(i0,i1,i2), c(j0,j1,j2)] Yl[i2,j2]
+//           (WHICH = 0):  B[(i1,i2),(j1,j2)] = sum_{i0,j0} W[r(i0,i1,i2), c(j0,j1,j2)] Yl[i0,j0]
+//   stage 2:  Wl_0[i0,j0] = sum_{i1,j1} A Yl[i1,j1];  Wl_1[i1,j1] = sum_{i0,j0} A Yl[i0,j0];  Wl_2[i2,j2] = sum_{i1,j1} B Yl[i1,j1]
+// and the same with dual numbers (Wd, Yld) for the tangent pass.  One stage-1 CTA owns the 16 rows that share the two kept row
+// digits: per column c it sums the 16 rows against Yl[., jw(c)] (coalesced row reads), then folds the 16 columns that share the
+// kept column digits through shared memory.  grid = (256, 2 = {A, B}, instances).  Fixed summation order: deterministic.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int BE3_THREADS = 256;
+constexpr size_t BE3_SMEM = (2 * 256 + 2 * 4096) * sizeof(double) + 4096 * sizeof(int);
+
+template <bool TANGENT>
+__global__ void __launch_bounds__(BE3_THREADS) back_embed3_stage1_kernel(const double* __restrict__ W, const double* __restrict__ Wd,
+                                                                         long long w_stride, long long wd_stride,
+                                                                         const double* __restrict__ Yl, const double* __restrict__ Yld,
+                                                                         double* __restrict__ AB, EmbedTables T, const int* active, int m, int layer) {
+    extern __shared__ __align__(16) double sm[];
+    const int inst = blockIdx.z;
+    if (active != nullptr && active[inst] == 0) return;
+    const int which = blockIdx.y == 0 ? 2 : 0;           // the factor contracted here
+    const int ka = which == 2 ? 0 : 1, kb = which == 2 ? 1 : 2;   // the two kept factors, in order
+    const int item = inst * m + layer, shift = layer & 1;
+    constexpr int D = 4096;
+    double* yl = sm; double* yld = sm + 256; double* s = sm + 512; double* sd = s + D;
+    int* rinv = reinterpret_cast<int*>(sd + D);
+    const unsigned* tab = T.tab + (size_t)shift * D;
+    for (int i = threadIdx.x; i < 256; i += BE3_THREADS) {
+        yl[i] = Yl[(long long)item * 256 + i];
+        yld[i] = TANGENT ? Yld[(long long)item * 256 + i] : 0.0;
+    }
+    for (int r = threadIdx.x; r < D; r += BE3_THREADS) {
+        const unsigned pk = tab[r];
+        rinv[loc_idx(pk, 0) + 16 * loc_idx(pk, 1) + 256 * loc_idx(pk, 2)] = r;
+    }
+    __syncthreads();
+    const int ia = blockIdx.x >> 4, ib = blockIdx.x & 15;
+    const int sa = 4 * ka, sb = 4 * kb, sw = 4 * which;    // digit f of the packed index sits at bit 4 f
+    const int rbase = (ia << sa) + (ib << sb);
+    const double* Wb = W + (long long)inst * w_stride;
+    const double* Wdb = TANGENT ? Wd + (long long)inst * wd_stride : nullptr;
+    for (int c = threadIdx.x; c < D; c += BE3_THREADS) {
+        const int jw = loc_idx(tab[c], which);
+        double acc = 0.0, accd = 0.0;
+#pragma unroll 4
+        for (int iw = 0; iw < 16; ++iw) {
+            const long long o = (long long)rinv[rbase + (iw << sw)] * D + c;
+            const double w = Wb[o], y = yl[iw * 16 + jw];
+            acc = fma(w, y, acc);
+            if (TANGENT) { accd = fma(Wdb[o], y, accd); accd = fma(w, yld[iw * 16 + jw], accd); }
+        }
+        s[c] = acc;
+        if (TANGENT) sd[c] = accd;
+    }
+    __syncthreads();
+    {
+        const int ja = threadIdx.x >> 4, jb = threadIdx.x & 15;
+        const int cbase = (ja << sa) + (jb << sb);
+        double acc = 0.0, accd = 0.0;
+        for (int jw = 0; jw < 16; ++jw) {
+            const int c = rinv[cbase + (jw << sw)];
+            acc += s[c];
+            if (TANGENT) accd += sd[c];
+        }
+        // AB[inst][{A, B}][{primal, dual}][(ia,ib)][(ja,jb)]
+        double* out = AB + (((long long)inst * 2 + blockIdx.y) * 2) * 65536 + (long long)blockIdx.x * 256 + threadIdx.x;
+        out[0] = acc;
+        if (TANGENT) out[65536] = accd;
+    }
+}
+
+// stage 2: grid = (3 factors, instances), 256 threads = the (i, j) of the local cotangent
+template <bool TANGENT>
+__global__ void __launch_bounds__(256) back_embed3_stage2_kernel(const double* __restrict__ AB, const double* __restrict__ Yl,
+                                                                 const double* __restrict__ Yld, double* __restrict__ Wl,
+                                                                 double* __restrict__ Wld, const int* active, int m, int layer) {
+    const int inst = blockIdx.y, f = blockIdx.x;
+    if (active != nullptr && active[inst] == 0) return;
+    const int item = inst * m + layer;
+    __shared__ double yl[256], yld[256];
+    yl[threadIdx.x] = Yl[(long long)item * 256 + threadIdx.x];
+    yld[threadIdx.x] = TANGENT ? Yld[(long long)item * 256 + threadIdx.x] : 0.0;
+    __syncthreads();
+    const int i = threadIdx.x >> 4, j = threadIdx.x & 15;
+    // f = 0: A[(i,u),(j,v)] Yl[u,v];  f = 1: A[(u,i),(v,j)] Yl[u,v];  f = 2: B[(u,i),(v,j)] Yl[u,v]
+    const double* M = AB + (((long long)inst * 2 + (f == 2 ? 1 : 0)) * 2) * 65536;
+    const double* Md = M + 65536;
+    double acc = 0.0, accd = 0.0;
+    for (int u = 0; u < 16; ++u)
+#pragma unroll 4
+        for (int v = 0; v < 16; ++v) {
+            const int o = (f == 0) ? ((i * 16 + u) * 256 + j * 16 + v) : ((u * 16 + i) * 256 + v * 16 + j);
+            const double a = M[o], y = yl[u * 16 + v];
+            acc = fma(a, y, acc);
+            if (TANGENT) { accd = fma(Md[o], y, accd); accd = fma(a, yld[u * 16 + v], accd); }
+        }
+    const long long o = ((long long)item * 3 + f) * 256 + threadIdx.x;
+    if (!TANGENT) Wl[o] = acc; else Wld[o] = accd;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // back_assemble: grid = (dim, instances), block 256, one launch per layer.  CTA (a, instance):
 //   Z[(a,k),c]  = sum_{b,d} (W[(a,b),(c,d)] + W[(b,a),(d,c)]) x[(b,k),d]
 //   Zd[(a,k),c] = sum_{b,d} (Wd[..] + Wd[..]^swap) x[(b,k),d] + (W[..] + W[..]^swap) eta[(b,k),d]       (TANGENT)

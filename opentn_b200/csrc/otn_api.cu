@@ -260,6 +260,7 @@ struct otn_problem {
     long long wd_stride = 0;     // per-instance stride of Wd
     // local model: [m][q*q] and per-factor partials [m][nf][q*q]
     double *Yl = nullptr, *Yld = nullptr, *Wl = nullptr, *Wld = nullptr;
+    double* be3 = nullptr;       // [max_batch][2][2][256*256]: stage-1 results of the 3-factor back-embedding (dense N = 6)
     // small per-instance state
     double *x = nullptr, *eta = nullptr, *zraw = nullptr, *zdraw = nullptr;   // [m][np]
     double *part_f = nullptr, *part_s = nullptr;                              // [tiles]
@@ -352,7 +353,7 @@ extern "C" void otn_destroy(otn_problem* h) {
     for (cudaEvent_t e : {h->prof.side.ev_fork, h->prof.side.ev_join}) if (e) cudaEventDestroy(e);
     for (void* ptr : {(void*)h->T_re, (void*)h->im2, (void*)h->tindex, (void*)h->tab, (void*)h->inv, (void*)h->symtab, (void*)h->t2f, (void*)h->Y, (void*)h->P,
                       (void*)h->G, (void*)h->W, (void*)h->Yd, (void*)h->Pd, (void*)h->Gd, (void*)h->Wd, (void*)h->Yl, (void*)h->Yld,
-                      (void*)h->Wl, (void*)h->Wld, (void*)h->x, (void*)h->eta, (void*)h->zraw, (void*)h->zdraw, (void*)h->part_f,
+                      (void*)h->Wl, (void*)h->Wld, (void*)h->be3, (void*)h->x, (void*)h->eta, (void*)h->zraw, (void*)h->zdraw, (void*)h->part_f,
                       (void*)h->part_s, (void*)h->f_Tt, (void*)h->f_Pst, (void*)h->f_Wp, (void*)h->f_Wp2, (void*)h->f_colw, (void*)h->f_jrow,
                       (void*)h->f_restrow, (void*)h->f_colidx, (void*)h->f_swaprow})
         if (ptr) cudaFree(ptr);
@@ -636,6 +637,8 @@ extern "C" int otn_create_ex(otn_problem** out, int N, int d, int m, int K, int 
         CREATE_TRY(cudaMalloc(&h->Yld, B * M * q2 * 8));
         CREATE_TRY(cudaMalloc(&h->Wl, B * M * h->nf * q2 * 8));
         CREATE_TRY(cudaMalloc(&h->Wld, B * M * h->nf * q2 * 8));
+        if (!h->structured && !h->factored && h->nf == 3 && h->q == 16 && getenv("OTN_BACK_EMBED_V1") == nullptr)   // env: A/B switch
+            CREATE_TRY(cudaMalloc(&h->be3, B * 4 * 65536 * 8));
     }
     if (!h->factored) {        // the factored evaluation never materialises a D x D work matrix
         for (double** ptr : {&h->Y, &h->P, &h->G, &h->W, &h->Yd, &h->Pd}) {
@@ -1055,7 +1058,7 @@ static int back_layer(otn_problem* h, int batch, const int* active, int l, const
     // back against x and W against eta separately (dense streaming kernel; block kernel outside the joint x / eta pass)
     const bool two_pullbacks = tangent && ((h->structured && h->model == OTN_MODEL_FULL) ? !primal_with_eta : (h->dim == 16 || h->dim == 8));
     ProfScope ps(&h->prof, bst, CAT_BACK, 4.0 * h->K * (double)h->dim * h->dim * h->dim * h->dim * batch * (tangent ? 2 : 1),
-                 ((h->model == OTN_MODEL_LOCAL && !h->factored) ? 1 : 0) + (two_pullbacks ? 2 : 1), ovl);
+                 ((h->model == OTN_MODEL_LOCAL && !h->factored) ? (h->be3 ? 2 : 1) : 0) + (two_pullbacks ? 2 : 1), ovl);
     if (ovl && tangent) h->back_wd_pending = true;
     const long long SZ = h->SZ, S = (long long)h->m * SZ;
     const double* Wfull = (l == 0) ? h->G : layer_ptr(h->W, l, SZ);                  // W_0 = G_0
@@ -1098,6 +1101,18 @@ static int back_layer(otn_problem* h, int batch, const int* active, int l, const
         } else if (h->structured) {
             if (!tangent) back_embed_sym_kernel<false><<<g, BEM_THREADS, sm, bst>>>(Wfull, nullptr, S, 0, h->Yl, h->Yld, h->Wl, h->Wld, h->tables(), h->sym, h->symtab, active, h->m, l);
             else back_embed_sym_kernel<true><<<g, BEM_THREADS, sm, bst>>>(Wfull, Wdfull, S, sWd, h->Yl, h->Yld, h->Wl, h->Wld, h->tables(), h->sym, h->symtab, active, h->m, l);
+        } else if (h->be3 != nullptr) {
+            // three factors of side 16 (N = 6): factor-by-factor contraction with whole-row reads of W (assemble.cuh)
+            dim3 g1(256, 2, batch), g2(3, batch);
+            if (!tangent) {
+                OTN_TRY(set_smem(back_embed3_stage1_kernel<false>, BE3_SMEM));
+                back_embed3_stage1_kernel<false><<<g1, BE3_THREADS, BE3_SMEM, bst>>>(Wfull, nullptr, S, 0, h->Yl, h->Yld, h->be3, h->tables(), active, h->m, l);
+                back_embed3_stage2_kernel<false><<<g2, 256, 0, bst>>>(h->be3, h->Yl, h->Yld, h->Wl, h->Wld, active, h->m, l);
+            } else {
+                OTN_TRY(set_smem(back_embed3_stage1_kernel<true>, BE3_SMEM));
+                back_embed3_stage1_kernel<true><<<g1, BE3_THREADS, BE3_SMEM, bst>>>(Wfull, Wdfull, S, sWd, h->Yl, h->Yld, h->be3, h->tables(), active, h->m, l);
+                back_embed3_stage2_kernel<true><<<g2, 256, 0, bst>>>(h->be3, h->Yl, h->Yld, h->Wl, h->Wld, active, h->m, l);
+            }
         } else if (!tangent) back_embed_kernel<false><<<g, BEM_THREADS, sm, bst>>>(Wfull, nullptr, S, 0, h->Yl, h->Yld, h->Wl, h->Wld, h->tables(), active, h->m, l);
         else back_embed_kernel<true><<<g, BEM_THREADS, sm, bst>>>(Wfull, Wdfull, S, sWd, h->Yl, h->Yld, h->Wl, h->Wld, h->tables(), active, h->m, l);
         CUDA_TRY(cudaGetLastError());
@@ -1576,7 +1591,7 @@ static void shift_instance_views(otn_problem* h, long long db) {
     auto mv = [&](double*& ptr, long long stride) { if (ptr) ptr += db * stride; };
     for (double** ptr : {&h->Y, &h->P, &h->G, &h->W, &h->Yd, &h->Pd}) mv(*ptr, m * SZ);
     mv(h->Gd, 2 * SZ); mv(h->Wd, h->wd_stride);
-    mv(h->Yl, m * q2); mv(h->Yld, m * q2); mv(h->Wl, m * h->nf * q2); mv(h->Wld, m * h->nf * q2);
+    mv(h->Yl, m * q2); mv(h->Yld, m * q2); mv(h->Wl, m * h->nf * q2); mv(h->Wld, m * h->nf * q2); mv(h->be3, 4 * 65536);
     for (double** ptr : {&h->x, &h->eta, &h->zraw, &h->zdraw}) mv(*ptr, m * h->np);
     mv(h->part_f, h->tiles); mv(h->part_s, h->tiles);
     if (h->factored) {

@@ -80,3 +80,33 @@ def test_n6_rowsharded_cost_and_cotangents(n6, oracle, goldens):
             rg = P.gradient_ambient2riemannian(xs[l], z, 1.0, 1.0)
             assert np.abs(rg - g[l]).max() / np.abs(g[l]).max() < 1e-9
         fit.close()
+
+
+def test_n6_dense_triple_equals_factored(n6, oracle):
+    """The dense D = 4096 path (embedding, chain, three-factor back-embedding `back_embed3_*`, pull-back) against the factored
+    evaluation of the same unit of work (which tests/test_gpu_factored.py pins to the oracle): f, Riemannian gradient and
+    Hessian-vector product at a random point and tangent, K = 4, both kernels of the back-embedding (OTN_BACK_EMBED_V1 = the
+    gather kernel)."""
+    import os
+    from opentn_b200 import StiefelFit
+    T6, _ = n6
+    rng = np.random.default_rng(4)
+    xs = np.array([oracle.random_stiefel(16, 4, rng) for _ in range(3)])
+    et = np.array([oracle.project(x, rng.standard_normal(x.shape)) for x in xs])
+    ref = StiefelFit(T6, model="local", N=6, d=2, metric="canonical", factored=True)
+    f0, g0, h0 = ref.triple(xs, et)
+    ref.close()
+    for v1 in (False, True):
+        if v1:
+            os.environ["OTN_BACK_EMBED_V1"] = "1"
+        try:
+            fit = StiefelFit(T6, model="local", N=6, d=2, metric="canonical", dense=True)
+            f, g, h = fit.triple(xs, et)
+            fc, gc = fit.cost_grad(xs)              # gradient-only pass (non-tangent back-embedding)
+            fit.close()
+        finally:
+            os.environ.pop("OTN_BACK_EMBED_V1", None)
+        assert abs(f - f0) < 1e-11 * abs(f0) and abs(fc - f0) < 1e-11 * abs(f0)
+        assert np.abs(g - g0).max() / np.abs(g0).max() < 1e-10
+        assert np.abs(gc - g0).max() / np.abs(g0).max() < 1e-10
+        assert np.abs(h - h0).max() / np.abs(h0).max() < 1e-10
