@@ -749,10 +749,33 @@ def c5_fit_leg(torch, dist, rank, world, device, barrier, max_over_ranks):
         fit = StiefelFit(target, model="local", N=N, d=d, metric="canonical", dense=True, device=device).row_shard()
         ms, o, trm, rep = timed(fit)
         same = bool(torch.equal(o[0], o1[0]) and torch.equal(o[1], o1[1]) and torch.equal(o[2], o1[2]))
+        # where the sharded time goes: per-launch events of this rank's kernels (the chain products include their peer stores;
+        # the device-side barriers are not in any category), once more with the peer stores switched off (numbers then garbage)
+        (hs,) = fit._handles.values()
+        diag = {}
+        for name, env in (("with_peer_stores", None), ("without_peer_stores", "1")):
+            if env:
+                os.environ["OTN_RS_NO_PEER_STORES"] = env
+            try:
+                scratch = tuple(t.clone() for t in o)
+                fit.triple(xd, ed, out=scratch)
+                barrier()
+                lib.otn_profile_enable(hs.h, 1)
+                t0 = time.perf_counter()
+                fit.triple(xd, ed, out=scratch)
+                torch.cuda.synchronize()
+                wall = 1e3 * (time.perf_counter() - t0)
+                _lib.check(lib.otn_profile_read(hs.h, pms, pln, pfl))
+                lib.otn_profile_enable(hs.h, 0)
+                barrier()
+            finally:
+                os.environ.pop("OTN_RS_NO_PEER_STORES", None)
+            diag[name] = {"u1_wall_ms_profiled": max_over_ranks(wall), "chain_products_ms": max_over_ranks(pms[0]),
+                          "replicated_kernels_ms": max_over_ranks(pms[1] + pms[2] + pms[3])}
         out["row_sharded"] = {"u1_ms": ms, "tflops": flops_u1 / ms / 1e9, "efficiency_vs_single_gpu": ms1 / (world * ms),
                               "tr_iteration_ms": trm, "tr_efficiency_vs_single_gpu": tr1 / (world * trm), "n_cg": int(rep["n_cg"][0, 0]),
                               "bitwise_equal_to_single_gpu": same, "tr_cost_equal": bool(np.array_equal(rep["f_iter"], rep1["f_iter"])),
-                              "barriers_ok": bool(fit.row_shard_ok())}
+                              "barriers_ok": bool(fit.row_shard_ok()), "diagnostics": diag}
         fit.close()
     del stream
     return out

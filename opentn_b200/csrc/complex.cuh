@@ -162,7 +162,7 @@ __device__ __forceinline__ void caddmul(cplx* Out, double alpha, const cplx* A, 
 }
 
 // smem: X | E | Z -> nu | Zd -> Dnu -> z | 8 p x p complex work matrices.  Partial sums come from the embedded chain:
-// sum part_f = 2 ||R||^2, sum part_s = 2 Re <R, Mdot>.
+// sum part_f = ||R||^2, sum part_s = Re <R, Mdot> (the chain products compute and reduce the upper half of each embedding only).
 template <bool HVP>
 __global__ void __launch_bounds__(ST_THREADS) criem_kernel(const CRiemParams P) {
     extern __shared__ __align__(16) double smraw[];
@@ -178,12 +178,12 @@ __global__ void __launch_bounds__(ST_THREADS) criem_kernel(const CRiemParams P) 
     if (threadIdx.x == 0) {
         double s = 0.0;
         for (int t = 0; t < P.tiles; ++t) s += P.part_f[(long long)inst * P.tiles + t];
-        const double f = sqrt(0.5 * s);
+        const double f = sqrt(s);
         sc[0] = f;
         if (HVP) {
             double d = 0.0;
             for (int t = 0; t < P.tiles; ++t) d += P.part_s[(long long)inst * P.tiles + t];
-            sc[1] = 0.5 * d;      // Re <R, Mdot> = f * fdot
+            sc[1] = d;            // Re <R, Mdot> = f * fdot
         }
         if (layer == 0 && P.f_out != nullptr) P.f_out[inst] = f;
     }

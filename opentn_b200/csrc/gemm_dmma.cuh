@@ -44,6 +44,11 @@ struct GemmParams {
     double* Cpeer[7];
     double* Ppeer[7];
     int npeer;
+    // Real embedding of complex matrices, emb(A) = [[Ar, -Ai], [Ai, Ar]] (side D = 2 * mirror): a product of embeddings is an
+    // embedding, so only its upper half is computed (rows [0, mirror): 4 instead of 8 real products per complex product) and
+    // every element is mirrored into the lower half -- (r, c) -> (r + mirror, c + mirror) for c < mirror, and
+    // -(r, c) -> (r + mirror, c - mirror) otherwise.  0 = off.  Partial sums then cover the upper half only.
+    int mirror;
 };
 
 template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool TA, bool TB>
@@ -196,6 +201,11 @@ gemm_dmma_kernel(const GemmParams p) {
                 part = fma(v.x, e.x, part); part = fma(v.y, e.y, part);
             }
             *reinterpret_cast<double2*>(C + row * D + col) = v;
+            if (p.mirror > 0) {
+                const bool left = col < p.mirror;
+                const double2 w = left ? v : make_double2(-v.x, -v.y);
+                *reinterpret_cast<double2*>(C + (row + p.mirror) * D + (left ? col + p.mirror : col - p.mirror)) = w;
+            }
             for (int q = 0; q < p.npeer; ++q) *reinterpret_cast<double2*>(p.Cpeer[q] + (long long)b * p.sC + row * D + col) = v;
         }
     }
@@ -277,6 +287,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p) {
                 if (p.epi == EPI_RESID) { v -= E[(long long)m * D + n]; part = fma(v, v, part); }
                 else if (p.epi == EPI_DOT) { part = fma(v, E[(long long)m * D + n], part); }
                 C[(long long)m * D + n] = v;
+                if (p.mirror > 0) C[(long long)(m + p.mirror) * D + (n < p.mirror ? n + p.mirror : n - p.mirror)] = (n < p.mirror) ? v : -v;
             }
         }
     if (p.epi != EPI_NONE) {

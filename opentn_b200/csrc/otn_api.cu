@@ -454,7 +454,7 @@ extern "C" int otn_create_ex(otn_problem** out, int N, int d, int m, int K, int 
     }
     h->tiles = 0;
     for (int i = 0; i < h->nblk; ++i) {
-        h->blkTiles[i] = h->fused ? chain_fused_partials(h->blkD[i]) : gemm_plan(h->blkD[i], h->blkD[i], 1).tiles;
+        h->blkTiles[i] = h->fused ? chain_fused_partials(h->blkD[i]) : gemm_plan(h->blkD[i], h->cplx ? h->blkD[i] / 2 : h->blkD[i], 1).tiles;
         h->blkTileOff[i] = h->tiles;
         h->tiles += h->blkTiles[i];
     }
@@ -812,6 +812,7 @@ static cudaError_t hgemm(otn_problem* h, const GemmParams& p0, bool ta, bool tb)
         p.A1 += o; p.B1 += o; p.C += o;
         if (p.A2) { p.A2 += o; p.B2 += o; }
         if (p.epi != EPI_NONE) { p.E += o; p.partial += h->blkTileOff[i]; p.partial_stride = h->tiles; }
+        if (h->cplx) { p.rows = p.D / 2; p.mirror = p.D / 2; }     // products of embeddings: upper half computed, lower half mirrored (gemm_dmma.cuh)
         if (h->rs.world > 1) {
             // Row window of this rank, tiles (and partial sums) also stored into every peer.  Barrier BEFORE the product: no peer
             // may still be reading (in a replicated kernel enqueued since the last product) the array this product overwrites over
@@ -822,6 +823,7 @@ static cudaError_t hgemm(otn_problem* h, const GemmParams& p0, bool ta, bool tb)
             p.row0 = h->rs.rank * rows; p.rows = rows;
             if (p.epi != EPI_NONE) p.partial += h->rs.rank * gemm_plan(p.D, rows, 1).tiles;
             p.npeer = h->rs.world - 1;
+            if (getenv("OTN_RS_NO_PEER_STORES") != nullptr) p.npeer = 0;      // env: timing diagnostic only (results are then incomplete)
             for (int q = 0; q < p.npeer; ++q) {
                 p.Cpeer[q] = rs_peer(h, q, p.C);
                 p.Ppeer[q] = (p.epi != EPI_NONE) ? rs_peer(h, q, p.partial) : nullptr;
@@ -978,7 +980,7 @@ static int build_layers(otn_problem* h, const double* x, const double* eta, int 
 
 __global__ void resid_kernel(const double* __restrict__ Y, long long sY, const double* __restrict__ T, long long sT, const int* tindex,
                              double* __restrict__ R, long long sR, const double* __restrict__ Rdot, long long sRd, double* partial,
-                             long long SZ, const int* active) {
+                             long long SZ, const int* active, double scale) {
     // m == 1 only (no GEMM to fuse into): R = Y - T and partial = ||R||^2, or partial = <R, Rdot> when Rdot != nullptr
     const int b = blockIdx.x;
     if (active != nullptr && active[b] == 0) return;
@@ -1000,7 +1002,7 @@ __global__ void resid_kernel(const double* __restrict__ Y, long long sY, const d
     if (threadIdx.x == 0) {
         double tot = 0.0;
         for (int w = 0; w < 8; ++w) tot += red[w];
-        partial[b] = tot;
+        partial[b] = tot * scale;       // complex handles: the sums run over the whole embedding = twice the complex quantity
     }
 }
 
@@ -1013,7 +1015,7 @@ static int forward_chain(otn_problem* h, int batch, const int* active, bool mode
     if (m == 1) {
         if (model_only) return 0;   // M = Y_0
         ProfScope ps(&h->prof, h->stream, CAT_OTHER, 0.0);
-        resid_kernel<<<batch, 256, 0, h->stream>>>(h->Y, S, h->T_re, SZ, h->tindex, h->G, S, nullptr, 0, h->part_f, SZ, active);
+        resid_kernel<<<batch, 256, 0, h->stream>>>(h->Y, S, h->T_re, SZ, h->tindex, h->G, S, nullptr, 0, h->part_f, SZ, active, h->cplx ? 0.5 : 1.0);
         *tiles_used = 1;
         CUDA_TRY(cudaGetLastError());
         return 0;
@@ -1267,7 +1269,7 @@ static int tangent_pass(otn_problem* h, int batch, const int* active, const doub
     if (m == 1) {
         CUDA_TRY(cudaMemcpy2DAsync(h->Gd, 2 * SZ * 8, h->Yd, S * 8, SZ * 8, batch, cudaMemcpyDeviceToDevice, h->stream));
         ProfScope ps(&h->prof, h->stream, CAT_OTHER, 0.0);
-        resid_kernel<<<batch, 256, 0, h->stream>>>(nullptr, 0, nullptr, 0, nullptr, h->G, S, h->Gd, 2 * SZ, h->part_s, SZ, active);
+        resid_kernel<<<batch, 256, 0, h->stream>>>(nullptr, 0, nullptr, 0, nullptr, h->G, S, h->Gd, 2 * SZ, h->part_s, SZ, active, h->cplx ? 0.5 : 1.0);
         CUDA_TRY(cudaGetLastError());
     }
     for (int l = 1; l < m; ++l) {
@@ -1439,7 +1441,7 @@ int otn_dev_cost(otn_problem* h, const double* x, int batch, const int* active, 
     else OTN_TRY(forward_chain(h, batch, active, false, &tiles));
     ProfScope ps(&h->prof, h->stream, CAT_OTHER, 0.0);
     cost_from_partials_kernel<<<(batch + 127) / 128, 128, 0, h->stream>>>(h->part_f, tiles, h->im2, h->tindex, f, batch, active,
-                                                                          h->cplx ? 0.5 : 1.0);   // ||emb(R)||^2 = 2 ||R||^2
+                                                                          1.0);   // (complex: the partials cover the upper half of emb(R) = ||R||^2)
     CUDA_TRY(cudaGetLastError());
     h->cached_batch = 0;
     return 0;
