@@ -168,9 +168,10 @@ int otn_ipc_close(void* ptr, int device);
 int otn_ipc_free(void* ptr, int device);
 /* ---- row-sharded handles (BASELINE config 5: ONE dense N = 6 instance over the GPUs of a node) ------------------------
  * One process per GPU, every rank creates the same handle with OTN_FLAG_DENSE (real isometries).  After
- *   otn_rowshard_export(h, mine)              mine = [9][64]: IPC handles of the arrays chain products write + the flag array
- *   (the host exchanges them: all-gather of 576 bytes per rank)
- *   otn_rowshard_attach(h, rank, world, all)  all = [world][9][64]
+ *   otn_rowshard_export(h, mine)              mine = [OTN_ROWSHARD_HANDLES][64]: IPC handles of the arrays written across ranks
+ *                                             (chain products, their partial sums, back-embedding scratch) + the flag array
+ *   (the host exchanges them: all-gather of 640 bytes per rank)
+ *   otn_rowshard_attach(h, rank, world, all)  all = [world][OTN_ROWSHARD_HANDLES][64]
  * every chain product of every entry point of the handle (otn_cost, otn_cost_grad, otn_triple, otn_hvp_cached, otn_model,
  * otn_tr_run) computes only the rows [rank D/world, (rank+1) D/world) of its result and stores each tile -- and the tile's
  * residual-norm / dot partial -- into the same array of every peer over NVLink (product fused with its all-gather); ranks are
@@ -180,7 +181,8 @@ int otn_ipc_free(void* ptr, int device);
  * (stiefel.py:423, 520 over compose_superops_list, transformations.py:841-851), which the reference could not finish
  * (experiments/trust_region_higher_sites.ipynb).  Needs D % (64 world) == 0, world <= 8.
  * otn_rowshard_status : *timed_out = 1 when a device-side barrier of this rank gave up after 30 s (a peer never arrived). */
-int otn_rowshard_export(otn_problem* p, unsigned char* handles_9x64);
+#define OTN_ROWSHARD_HANDLES 10
+int otn_rowshard_export(otn_problem* p, unsigned char* handles);
 int otn_rowshard_attach(otn_problem* p, int rank, int world, const unsigned char* all_handles);
 int otn_rowshard_detach(otn_problem* p);
 int otn_rowshard_status(otn_problem* p, int* timed_out);

@@ -197,13 +197,15 @@ __global__ void __launch_bounds__(BEM_THREADS) back_embed_kernel(const double* _
 // kept column digits through shared memory.  grid = (256, 2 = {A, B}, instances).  Fixed summation order: deterministic.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int BE3_THREADS = 256;
+struct Be3Peers { double* p[7]; int n; };      // the same scratch array on the other ranks of a row-sharded handle (n = 0: none)
 constexpr size_t BE3_SMEM = (2 * 256 + 2 * 4096) * sizeof(double) + 4096 * sizeof(int);
 
 template <bool TANGENT>
 __global__ void __launch_bounds__(BE3_THREADS) back_embed3_stage1_kernel(const double* __restrict__ W, const double* __restrict__ Wd,
                                                                          long long w_stride, long long wd_stride,
                                                                          const double* __restrict__ Yl, const double* __restrict__ Yld,
-                                                                         double* __restrict__ AB, EmbedTables T, const int* active, int m, int layer) {
+                                                                         double* __restrict__ AB, Be3Peers peers, int x0, EmbedTables T,
+                                                                         const int* active, int m, int layer) {
     extern __shared__ __align__(16) double sm[];
     const int inst = blockIdx.z;
     if (active != nullptr && active[inst] == 0) return;
@@ -223,7 +225,8 @@ __global__ void __launch_bounds__(BE3_THREADS) back_embed3_stage1_kernel(const d
         rinv[loc_idx(pk, 0) + 16 * loc_idx(pk, 1) + 256 * loc_idx(pk, 2)] = r;
     }
     __syncthreads();
-    const int ia = blockIdx.x >> 4, ib = blockIdx.x & 15;
+    const int bx = x0 + blockIdx.x;                       // (x0: first CTA of this rank on a row-sharded handle)
+    const int ia = bx >> 4, ib = bx & 15;
     const int sa = 4 * ka, sb = 4 * kb, sw = 4 * which;    // digit f of the packed index sits at bit 4 f
     const int rbase = (ia << sa) + (ib << sb);
     const double* Wb = W + (long long)inst * w_stride;
@@ -231,8 +234,8 @@ __global__ void __launch_bounds__(BE3_THREADS) back_embed3_stage1_kernel(const d
     for (int c = threadIdx.x; c < D; c += BE3_THREADS) {
         const int jw = loc_idx(tab[c], which);
         double acc = 0.0, accd = 0.0;
-#pragma unroll 4
-        for (int iw = 0; iw < 16; ++iw) {
+#pragma unroll
+        for (int iw = 0; iw < 16; ++iw) {                 // 16 (32 with the tangent) independent loads in flight per thread
             const long long o = (long long)rinv[rbase + (iw << sw)] * D + c;
             const double w = Wb[o], y = yl[iw * 16 + jw];
             acc = fma(w, y, acc);
@@ -252,9 +255,13 @@ __global__ void __launch_bounds__(BE3_THREADS) back_embed3_stage1_kernel(const d
             if (TANGENT) accd += sd[c];
         }
         // AB[inst][{A, B}][{primal, dual}][(ia,ib)][(ja,jb)]
-        double* out = AB + (((long long)inst * 2 + blockIdx.y) * 2) * 65536 + (long long)blockIdx.x * 256 + threadIdx.x;
-        out[0] = acc;
-        if (TANGENT) out[65536] = accd;
+        const long long o = (((long long)inst * 2 + blockIdx.y) * 2) * 65536 + (long long)bx * 256 + threadIdx.x;
+        AB[o] = acc;
+        if (TANGENT) AB[o + 65536] = accd;
+        for (int q = 0; q < peers.n; ++q) {
+            peers.p[q][o] = acc;
+            if (TANGENT) peers.p[q][o + 65536] = accd;
+        }
     }
 }
 

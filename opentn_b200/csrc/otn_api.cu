@@ -307,13 +307,15 @@ struct otn_problem {
     // holds the full handle and runs the whole program, but each chain product computes only the rows [rank D/world, ...) of its
     // result and stores every tile (and the tile's partial sum) into the same array of all peers through IPC-mapped pointers.
     struct RowShard {
-        enum { NARR = 8 };                       // arrays chain products write: P, G, W, Pd, Gd, Wd, part_f, part_s
+        enum { NARR = 9 };                       // arrays written across ranks: P, G, W, Pd, Gd, Wd, part_f, part_s, be3
         int rank = 0, world = 1, epoch = 0;
         double* base[NARR] = {}; size_t bytes[NARR] = {};
         double* peer[NARR][7] = {};
         int* flags = nullptr;                    // [64]: slot r = last epoch rank r has reached; slot 32 = time-out marker
         int* peer_flags[7] = {};
         bool exported = false;
+        cudaStream_t side = nullptr;             // second product of an independent pair (hgemm_pair)
+        cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     } rs;
 };
 
@@ -346,6 +348,8 @@ extern "C" void otn_destroy(otn_problem* h) {
         if (h->rs.peer_flags[q]) cudaIpcCloseMemHandle(h->rs.peer_flags[q]);
     }
     if (h->rs.flags) cudaFree(h->rs.flags);
+    if (h->rs.side) { cudaStreamSynchronize(h->rs.side); cudaStreamDestroy(h->rs.side); }
+    for (cudaEvent_t e : {h->rs.ev_fork, h->rs.ev_join}) if (e) cudaEventDestroy(e);
     if (h->prof.side.st) { cudaStreamSynchronize(h->prof.side.st); cudaStreamDestroy(h->prof.side.st); }
     if (h->s_back_own) { cudaStreamSynchronize(h->s_back_own); cudaStreamDestroy(h->s_back_own); }
     for (int i = 0; i < 2; ++i) if (h->s_backp[i]) { cudaStreamSynchronize(h->s_backp[i]); cudaStreamDestroy(h->s_backp[i]); }
@@ -802,6 +806,22 @@ static double* rs_peer(const otn_problem* h, int q, const double* ptr) {
     return nullptr;
 }
 
+// row-sharded handle: row window of this rank, tiles (and partial sums) also stored into every peer
+static cudaError_t rs_window(const otn_problem* h, GemmParams& p) {
+    const int rows = p.D / h->rs.world;
+    p.row0 = h->rs.rank * rows; p.rows = rows;
+    if (p.epi != EPI_NONE) p.partial += h->rs.rank * gemm_plan(p.D, rows, 1).tiles;
+    p.npeer = h->rs.world - 1;
+    if (getenv("OTN_RS_NO_PEER_STORES") != nullptr) p.npeer = 0;      // env: timing diagnostic only (results are then incomplete)
+    for (int q = 0; q < p.npeer; ++q) {
+        p.Cpeer[q] = rs_peer(h, q, p.C);
+        p.Ppeer[q] = (p.epi != EPI_NONE) ? rs_peer(h, q, p.partial) : nullptr;
+        if (p.Cpeer[q] == nullptr || (p.epi != EPI_NONE && p.Ppeer[q] == nullptr)) return cudaErrorInvalidValue;
+    }
+    return cudaSuccess;
+}
+static double gemm_flops(const GemmParams& p) { return 2.0 * p.D * (double)p.rows * (p.kvalid > 0 ? p.kvalid : p.D) * p.batch * (p.A2 ? 2 : 1); }
+
 // one chain product = one launch per diagonal block (1 block in the dense formulation, 2 in the structured one)
 static cudaError_t hgemm(otn_problem* h, const GemmParams& p0, bool ta, bool tb) {
     for (int i = 0; i < h->nblk; ++i) {
@@ -814,22 +834,13 @@ static cudaError_t hgemm(otn_problem* h, const GemmParams& p0, bool ta, bool tb)
         if (p.epi != EPI_NONE) { p.E += o; p.partial += h->blkTileOff[i]; p.partial_stride = h->tiles; }
         if (h->cplx) { p.rows = p.D / 2; p.mirror = p.D / 2; }     // products of embeddings: upper half computed, lower half mirrored (gemm_dmma.cuh)
         if (h->rs.world > 1) {
-            // Row window of this rank, tiles (and partial sums) also stored into every peer.  Barrier BEFORE the product: no peer
-            // may still be reading (in a replicated kernel enqueued since the last product) the array this product overwrites over
-            // there; barrier AFTER it: the result is complete on every rank before anything reads it.  Everything of a row-sharded
-            // handle runs on h->stream (no side / back stream), so stream order on each rank plus the two barriers is the whole
+            // Barrier BEFORE the product: no peer may still be reading (in a replicated kernel enqueued since the last product)
+            // the array this product overwrites over there; barrier AFTER it: the result is complete on every rank before
+            // anything reads it.  Everything of a row-sharded handle is ordered on h->stream (no back stream; the side stream of
+            // hgemm_pair forks and joins between the two barriers), so stream order on each rank plus the barriers is the whole
             // ordering argument.
-            const int rows = p.D / h->rs.world;
-            p.row0 = h->rs.rank * rows; p.rows = rows;
-            if (p.epi != EPI_NONE) p.partial += h->rs.rank * gemm_plan(p.D, rows, 1).tiles;
-            p.npeer = h->rs.world - 1;
-            if (getenv("OTN_RS_NO_PEER_STORES") != nullptr) p.npeer = 0;      // env: timing diagnostic only (results are then incomplete)
-            for (int q = 0; q < p.npeer; ++q) {
-                p.Cpeer[q] = rs_peer(h, q, p.C);
-                p.Ppeer[q] = (p.epi != EPI_NONE) ? rs_peer(h, q, p.partial) : nullptr;
-                if (p.Cpeer[q] == nullptr || (p.epi != EPI_NONE && p.Ppeer[q] == nullptr)) return cudaErrorInvalidValue;
-            }
-            cudaError_t eb = rs_barrier(h, h->stream);
+            cudaError_t eb = rs_window(h, p);
+            if (eb == cudaSuccess) eb = rs_barrier(h, h->stream);
             if (eb != cudaSuccess) return eb;
         }
         // executed flops: zero-padded k-steps beyond kvalid are skipped by the kernel
@@ -839,7 +850,7 @@ static cudaError_t hgemm(otn_problem* h, const GemmParams& p0, bool ta, bool tb)
             if (i == 1) st = h->prof.side.st;
         }
         {
-            ProfScope ps(&h->prof, st, CAT_GEMM, 2.0 * p.D * (double)p.rows * (p.kvalid > 0 ? p.kvalid : p.D) * p.batch * (p.A2 ? 2 : 1));
+            ProfScope ps(&h->prof, st, CAT_GEMM, gemm_flops(p));
             cudaError_t e = gemm_launch(p, ta, tb, st);
             if (e != cudaSuccess) return e;
         }
@@ -849,6 +860,36 @@ static cudaError_t hgemm(otn_problem* h, const GemmParams& p0, bool ta, bool tb)
         }
     }
     return cudaSuccess;
+}
+
+// Two chain products that do not depend on each other (W_l = G_l P_{l-1}^T and G_{l-1} = Y_l^T G_l of the reverse sweeps).  On a
+// row-sharded handle they share ONE barrier pair and run concurrently on two streams: at 8 GPUs one product is 512 tiles of
+// 64 x 64 -- 3.46 per SM, so a quarter of the SMs would carry a fourth tile while the others idle -- and the peer stores of one
+// product's epilogues overlap the other's math.  Everywhere else: the two products one after the other.
+static cudaError_t hgemm_pair(otn_problem* h, const GemmParams& a, bool ta_a, bool tb_a, const GemmParams& b, bool ta_b, bool tb_b) {
+    if (h->rs.world == 1 || h->rs.side == nullptr || h->prof.on || h->nblk != 1 || getenv("OTN_RS_NO_PAIRS") != nullptr) {   // env: A/B switch
+        cudaError_t e = hgemm(h, a, ta_a, tb_a);
+        return e != cudaSuccess ? e : hgemm(h, b, ta_b, tb_b);
+    }
+    GemmParams p[2] = {a, b};
+    for (GemmParams& q : p) {
+        q.D = h->blkD[0]; q.kvalid = 0;
+        if (q.epi != EPI_NONE) q.partial_stride = h->tiles;
+        cudaError_t e = rs_window(h, q);
+        if (e != cudaSuccess) return e;
+    }
+    cudaError_t e = rs_barrier(h, h->stream);
+    if (e != cudaSuccess) return e;
+    cudaEventRecord(h->rs.ev_fork, h->stream);
+    cudaStreamWaitEvent(h->rs.side, h->rs.ev_fork, 0);
+    g_launches += 2;
+    e = gemm_launch(p[0], ta_a, tb_a, h->stream);
+    if (e != cudaSuccess) return e;
+    e = gemm_launch(p[1], ta_b, tb_b, h->rs.side);
+    if (e != cudaSuccess) return e;
+    cudaEventRecord(h->rs.ev_join, h->rs.side);
+    cudaStreamWaitEvent(h->stream, h->rs.ev_join, 0);
+    return rs_barrier(h, h->stream);
 }
 static GemmParams gp(const otn_problem* h, int batch, const int* active) {
     GemmParams p{};
@@ -1105,16 +1146,30 @@ static int back_layer(otn_problem* h, int batch, const int* active, int l, const
             else back_embed_sym_kernel<true><<<g, BEM_THREADS, sm, bst>>>(Wfull, Wdfull, S, sWd, h->Yl, h->Yld, h->Wl, h->Wld, h->tables(), h->sym, h->symtab, active, h->m, l);
         } else if (h->be3 != nullptr) {
             // three factors of side 16 (N = 6): factor-by-factor contraction with whole-row reads of W (assemble.cuh)
-            dim3 g1(256, 2, batch), g2(3, batch);
+            // Row-sharded handle: the 256 stage-1 CTAs per pass are dealt to the ranks, each stores its rows of A / B into every
+            // peer; barriers around stage 1 as around a chain product (every output element has one producer: still bitwise equal).
+            Be3Peers peers{};
+            int x0 = 0, nx = 256;
+            if (h->rs.world > 1) {
+                nx = 256 / h->rs.world; x0 = h->rs.rank * nx;
+                peers.n = h->rs.world - 1;
+                for (int q = 0; q < peers.n; ++q) {
+                    peers.p[q] = rs_peer(h, q, h->be3);
+                    if (peers.p[q] == nullptr) return fail("row-sharded back-embedding: scratch not mapped");
+                }
+                CUDA_TRY(rs_barrier(h, h->stream));
+            }
+            dim3 g1(nx, 2, batch), g2(3, batch);
             if (!tangent) {
                 OTN_TRY(set_smem(back_embed3_stage1_kernel<false>, BE3_SMEM));
-                back_embed3_stage1_kernel<false><<<g1, BE3_THREADS, BE3_SMEM, bst>>>(Wfull, nullptr, S, 0, h->Yl, h->Yld, h->be3, h->tables(), active, h->m, l);
-                back_embed3_stage2_kernel<false><<<g2, 256, 0, bst>>>(h->be3, h->Yl, h->Yld, h->Wl, h->Wld, active, h->m, l);
+                back_embed3_stage1_kernel<false><<<g1, BE3_THREADS, BE3_SMEM, bst>>>(Wfull, nullptr, S, 0, h->Yl, h->Yld, h->be3, peers, x0, h->tables(), active, h->m, l);
             } else {
                 OTN_TRY(set_smem(back_embed3_stage1_kernel<true>, BE3_SMEM));
-                back_embed3_stage1_kernel<true><<<g1, BE3_THREADS, BE3_SMEM, bst>>>(Wfull, Wdfull, S, sWd, h->Yl, h->Yld, h->be3, h->tables(), active, h->m, l);
-                back_embed3_stage2_kernel<true><<<g2, 256, 0, bst>>>(h->be3, h->Yl, h->Yld, h->Wl, h->Wld, active, h->m, l);
+                back_embed3_stage1_kernel<true><<<g1, BE3_THREADS, BE3_SMEM, bst>>>(Wfull, Wdfull, S, sWd, h->Yl, h->Yld, h->be3, peers, x0, h->tables(), active, h->m, l);
             }
+            if (h->rs.world > 1) CUDA_TRY(rs_barrier(h, h->stream));
+            if (!tangent) back_embed3_stage2_kernel<false><<<g2, 256, 0, bst>>>(h->be3, h->Yl, h->Yld, h->Wl, h->Wld, active, h->m, l);
+            else back_embed3_stage2_kernel<true><<<g2, 256, 0, bst>>>(h->be3, h->Yl, h->Yld, h->Wl, h->Wld, active, h->m, l);
         } else if (!tangent) back_embed_kernel<false><<<g, BEM_THREADS, sm, bst>>>(Wfull, nullptr, S, 0, h->Yl, h->Yld, h->Wl, h->Wld, h->tables(), active, h->m, l);
         else back_embed_kernel<true><<<g, BEM_THREADS, sm, bst>>>(Wfull, Wdfull, S, sWd, h->Yl, h->Yld, h->Wl, h->Wld, h->tables(), active, h->m, l);
         CUDA_TRY(cudaGetLastError());
@@ -1238,15 +1293,19 @@ static int reverse_chain(otn_problem* h, int batch, const int* active, const dou
         p.A1 = layer_ptr(h->G, l, SZ); p.sA1 = S;
         p.B1 = (l == 1) ? h->Y : layer_ptr(h->P, l - 1, SZ); p.sB1 = S;
         p.C = layer_ptr(h->W, l, SZ); p.sC = S;
-        CUDA_TRY(hgemm(h, p, false, true));
-        const bool ovl = back_overlap(h);      // W_l goes to the back stream at once; the chain carries on underneath
-        if (ovl) OTN_TRY(back_layer(h, batch, active, l, x, false, eta_joint, eta_joint != nullptr));
         GemmParams r = gp(h, batch, active);                       // G_{l-1} = Y_l^T G_l
         r.A1 = layer_ptr(h->Y, l, SZ); r.sA1 = S;
         r.B1 = layer_ptr(h->G, l, SZ); r.sB1 = S;
         r.C = layer_ptr(h->G, l - 1, SZ); r.sC = S;
+        const bool ovl = back_overlap(h);      // W_l goes to the back stream at once; the chain carries on underneath
+        if (!ovl) {                            // (row-sharded handles: the two independent products as a concurrent pair)
+            CUDA_TRY(hgemm_pair(h, p, false, true, r, true, false));
+            OTN_TRY(back_layer(h, batch, active, l, x, false, eta_joint, eta_joint != nullptr));
+            continue;
+        }
+        CUDA_TRY(hgemm(h, p, false, true));
+        OTN_TRY(back_layer(h, batch, active, l, x, false, eta_joint, eta_joint != nullptr));
         CUDA_TRY(hgemm(h, r, true, false));
-        if (!ovl) OTN_TRY(back_layer(h, batch, active, l, x, false, eta_joint, eta_joint != nullptr));
     }
     OTN_TRY(back_layer(h, batch, active, 0, x, false, eta_joint, eta_joint != nullptr));
     return 0;
@@ -1295,14 +1354,18 @@ static int tangent_pass(otn_problem* h, int batch, const int* active, const doub
         p.A2 = layer_ptr(h->G, l, SZ); p.sA2 = S; p.B2 = Pdprev; p.sB2 = S;
         p.C = h->Wd; p.sC = SZ;
         if (h->back_wd_pending) back_sync(h);  // Wd is one buffer: the pull-back of the previous layer's Wd must have read it
-        CUDA_TRY(hgemm(h, p, false, true));
-        const bool ovl = back_overlap(h);
-        if (ovl) OTN_TRY(back_layer(h, batch, active, l, x, true, eta, joint));
         GemmParams r = gp(h, batch, active);                       // Ghat_{l-1} = Yd_l^T G_l + Y_l^T Ghat_l
         r.A1 = layer_ptr(h->Yd, l, SZ); r.sA1 = S; r.B1 = layer_ptr(h->G, l, SZ); r.sB1 = S;
         r.A2 = layer_ptr(h->Y, l, SZ); r.sA2 = S; r.B2 = Ghat; r.sB2 = 2 * SZ;
         r.C = h->Gd + (long long)(1 - cur) * SZ; r.sC = 2 * SZ;
-        CUDA_TRY(hgemm(h, r, true, false));
+        const bool ovl = back_overlap(h);
+        if (!ovl) {
+            CUDA_TRY(hgemm_pair(h, p, false, true, r, true, false));
+        } else {
+            CUDA_TRY(hgemm(h, p, false, true));
+            OTN_TRY(back_layer(h, batch, active, l, x, true, eta, joint));
+            CUDA_TRY(hgemm(h, r, true, false));
+        }
         if (!ovl) OTN_TRY(back_layer(h, batch, active, l, x, true, eta, joint));
         cur = 1 - cur;
     }
@@ -2122,18 +2185,19 @@ extern "C" int otn_ipc_free(void* ptr, int device) {
 // row-sharded handles (BASELINE config 5: one dense N = 6 instance over the GPUs of a node)
 // ---------------------------------------------------------------------------------------------------------------------
 // One process per GPU, each with an identical handle (same sizes, target, OTN_FLAG_DENSE).  Protocol:
-//   otn_rowshard_export(h, mine)           -> 9 IPC handles (P, G, W, Pd, Gd, Wd, part_f, part_s, flags) of this rank
-//   (exchange `mine` between the ranks: all-gather of 9 * 64 bytes)
-//   otn_rowshard_attach(h, rank, world, all)   all = [world][9][64]
+//   otn_rowshard_export(h, mine)           -> OTN_ROWSHARD_HANDLES = 10 IPC handles of this rank (P, G, W, Pd, Gd, Wd, part_f,
+//                                             part_s, back-embedding scratch, flags)
+//   (exchange `mine` between the ranks: all-gather of 10 * 64 bytes)
+//   otn_rowshard_attach(h, rank, world, all)   all = [world][10][64]
 // From then on every entry point of the handle (otn_cost, otn_cost_grad, otn_triple, otn_hvp_cached, otn_tr_run, ...) must be
 // called by ALL ranks with the same arguments: the replicated kernels (assembly, embedding, pull-backs, Riemannian epilogue, tCG)
 // run everywhere on identical data, the chain products are split by rows (hgemm).  Results are bitwise equal on every rank and
 // bitwise equal to the un-sharded handle (same tiles, same fixed-order partial sums).
 static int rs_arrays(otn_problem* h, double** base, size_t* bytes) {
     const size_t B = (size_t)h->max_batch, SZ = (size_t)h->SZ, M = (size_t)h->m;
-    double* b[otn_problem::RowShard::NARR] = {h->P, h->G, h->W, h->Pd, h->Gd, h->Wd, h->part_f, h->part_s};
+    double* b[otn_problem::RowShard::NARR] = {h->P, h->G, h->W, h->Pd, h->Gd, h->Wd, h->part_f, h->part_s, h->be3};
     const size_t n[otn_problem::RowShard::NARR] = {B * M * SZ * 8, B * M * SZ * 8, B * M * SZ * 8, B * M * SZ * 8, B * 2 * SZ * 8,
-                                                   B * (size_t)h->wd_stride * 8, B * h->tiles * 8, B * h->tiles * 8};
+                                                   B * (size_t)h->wd_stride * 8, B * h->tiles * 8, B * h->tiles * 8, B * 4 * 65536 * 8};
     for (int a = 0; a < otn_problem::RowShard::NARR; ++a) { base[a] = b[a]; bytes[a] = n[a]; }
     return 0;
 }
@@ -2157,6 +2221,8 @@ extern "C" int otn_rowshard_export(otn_problem* h, unsigned char* handles) {
     for (int a = 0; a <= otn_problem::RowShard::NARR; ++a) {
         cudaIpcMemHandle_t hd;
         void* ptr = (a < otn_problem::RowShard::NARR) ? (void*)h->rs.base[a] : (void*)h->rs.flags;
+        std::memset(handles + (size_t)a * 64, 0, 64);
+        if (ptr == nullptr) continue;                          // (the back-embedding scratch exists for three-factor layers only)
         CUDA_TRY(cudaIpcGetMemHandle(&hd, ptr));
         std::memcpy(handles + (size_t)a * 64, &hd, 64);
     }
@@ -2194,6 +2260,7 @@ extern "C" int otn_rowshard_attach(otn_problem* h, int rank, int world, const un
         for (int a = 0; a <= otn_problem::RowShard::NARR; ++a) {
             cudaIpcMemHandle_t hd;
             std::memcpy(&hd, all_handles + ((size_t)r * (otn_problem::RowShard::NARR + 1) + a) * 64, 64);
+            if (a < otn_problem::RowShard::NARR && h->rs.base[a] == nullptr) continue;
             void* ptr = nullptr;
             const cudaError_t e = cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess);
             if (e != cudaSuccess) {
@@ -2204,6 +2271,11 @@ extern "C" int otn_rowshard_attach(otn_problem* h, int rank, int world, const un
             if (a < otn_problem::RowShard::NARR) h->rs.peer[a][k] = (double*)ptr; else h->rs.peer_flags[k] = (int*)ptr;
         }
         ++k;
+    }
+    if (h->rs.side == nullptr) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->rs.side, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->rs.ev_fork, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->rs.ev_join, cudaEventDisableTiming));
     }
     h->rs.rank = rank; h->rs.world = world; h->rs.epoch = 0;
     h->cached_batch = 0;

@@ -190,7 +190,7 @@ class StiefelFit:
         rank, world, group = self._row_shard
         if world == 1 or getattr(h, "row_sharded", False):
             return
-        mine = C.create_string_buffer(9 * 64)
+        mine = C.create_string_buffer(10 * 64)
         check(h._lib.otn_rowshard_export(h.h, mine))
         allh = [None] * world
         dist.all_gather_object(allh, bytes(mine.raw), group=group)

@@ -88,9 +88,41 @@ def _worker(rank, world, port, out_dir, same_gpu):
         dist.all_gather(both, mine)
         assert all(torch.equal(b, both[0]) for b in both)
         fit.close()
+    if not same_gpu:
+        _n6_case(dev, world, dist, torch)
     dist.barrier()
     dist.destroy_process_group()
     open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+
+
+def _n6_case(dev, world, dist, torch):
+    """Config 5 at its real size (D = 4096, three Kronecker factors: the sharded three-factor back-embedding and the paired reverse
+    products are only exercised here): sharded U1 bitwise equal to the un-sharded dense handle, both equal to the factored
+    evaluation (pinned to the oracle in tests/test_gpu_factored.py) to 1e-10."""
+    from opentn_b200 import StiefelFit
+    from opentn_b200 import transformations as T
+    T.set_device(dev)
+    full = T.create_kitaev_liouvillians(6, 2, 1.0, pbc=True, backend="cuda")[0]
+    T6 = np.ascontiguousarray(T.exp_operator_dt(full, 4.0, backend="cuda").real)
+    rng = np.random.default_rng(8)
+    xs = np.stack([np.linalg.qr(rng.standard_normal((8, 4)))[0] for _ in range(3)])
+    et = rng.standard_normal(xs.shape)
+    et = et - xs @ (0.5 * (np.swapaxes(xs, -1, -2) @ et + np.swapaxes(et, -1, -2) @ xs))
+    ref = StiefelFit(T6, model="local", N=6, d=2, metric="canonical", factored=True, device=dev)
+    f0, g0, h0 = ref.triple(xs, et)
+    ref.close()
+    solo = StiefelFit(T6, model="local", N=6, d=2, metric="canonical", dense=True, device=dev)
+    f1, g1, h1 = solo.triple(xs, et)
+    solo.close()
+    fit = StiefelFit(T6, model="local", N=6, d=2, metric="canonical", dense=True, device=dev).row_shard()
+    f, g, h = fit.triple(xs, et)
+    assert f == f1 and np.array_equal(g, g1) and np.array_equal(h, h1)
+    assert abs(f - f0) < 1e-11 * abs(f0)
+    assert np.abs(g - g0).max() / np.abs(g0).max() < 1e-10 and np.abs(h - h0).max() / np.abs(h0).max() < 1e-10
+    fc, gc = fit.cost_grad(xs)
+    assert fc == f1 and np.array_equal(gc, g1)
+    assert fit.row_shard_ok()
+    fit.close()
 
 
 def _spawn(world, tmp_path, same_gpu):
@@ -125,7 +157,7 @@ def test_rowshard_rejects_structured_handles():
     fit = StiefelFit(T, model="local", N=4, d=2)          # AUTO -> factored
     fit(xs)
     (h,) = fit._handles.values()
-    buf = C.create_string_buffer(9 * 64)
+    buf = C.create_string_buffer(10 * 64)
     assert h._lib.otn_rowshard_export(h.h, buf) != 0
     assert b"OTN_FLAG_DENSE" in h._lib.otn_last_error()
     with pytest.raises(ValueError, match="dense=True"):
@@ -135,8 +167,8 @@ def test_rowshard_rejects_structured_handles():
     fit = StiefelFit(T, model="local", N=4, d=2, dense=True)
     fit(xs)
     (h,) = fit._handles.values()
-    assert h._lib.otn_rowshard_attach(h.h, 0, 2, bytes(2 * 9 * 64)) != 0
+    assert h._lib.otn_rowshard_attach(h.h, 0, 2, bytes(2 * 10 * 64)) != 0
     assert h._lib.otn_rowshard_export(h.h, buf) == 0
-    assert h._lib.otn_rowshard_attach(h.h, 0, 3, bytes(3 * 9 * 64)) != 0
+    assert h._lib.otn_rowshard_attach(h.h, 0, 3, bytes(3 * 10 * 64)) != 0
     assert b"multiple of 64" in h._lib.otn_last_error()
     fit.close()
