@@ -430,6 +430,67 @@ def latency_leg(torch, StiefelFit, device, cpu):
     return out
 
 
+def _complex_problem(B, K=8, m=3, seed=12):
+    """Synthetic complex full-sites instances (N=4: isometries of 16 K x 16, complex128) and a complex target near the model of a
+    hidden point; the same on the device and in the oracle worker (seeded)."""
+    import numpy as np
+    from oracle import complex_port as CP
+    rng, rng_x, rng_e = (np.random.default_rng(seed + i) for i in range(3))     # separate streams: instance b does not depend on B
+    dim = 16
+    T = CP.model([CP.random_stiefel(dim * K, dim, rng) for _ in range(m)])
+    T = T + 0.05 * (rng.standard_normal(T.shape) + 1j * rng.standard_normal(T.shape))
+    xs = np.array([[CP.random_stiefel(dim * K, dim, rng_x) for _ in range(m)] for _ in range(B)])
+    et = np.array([[CP.project(x, rng_e.standard_normal(x.shape) + 1j * rng_e.standard_normal(x.shape)) for x in xb] for xb in xs])
+    return T, xs, et
+
+
+def _cpu_complex_worker(args):
+    """(first, count) -> seconds for `count` complex U1 evaluations of the oracle (oracle/complex_port.py), one BLAS thread."""
+    first, count = args
+    from oracle import complex_port as CP
+    T, xs, et = _complex_problem(first + count)
+    t0 = time.perf_counter()
+    fs = []
+    for b in range(first, first + count):
+        f, _, _ = CP.triple(T, list(xs[b]), list(et[b]), "canonical")
+        fs.append(f)
+    return time.perf_counter() - t0, fs
+
+
+def complex_leg(torch, StiefelFit, device, cpu, B=64, K=8, m=3, steps=5):
+    """SURVEY 8f #4, complex isometries: U1 = (f, rgrad, H eta) for B complex N=4 full-sites instances (K = 8, m = 3) through the
+    complex handle (chain on the real embedding, upper half of every product computed and mirrored: 4 real D^3 products per complex
+    product), device-resident; the complex oracle on the same instances beside it (bounded sample, all cores, one instance each)."""
+    import numpy as np
+    T, xs, et = _complex_problem(B, K, m)
+    xd, ed = torch.from_numpy(xs).cuda(), torch.from_numpy(et).cuda()
+    fit = StiefelFit(T, model="full", N=4, d=2, metric="canonical", max_batch=B, device=device)
+    outs = fit.triple(xd, ed)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        outs = fit.triple(xd, ed, out=outs)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    f_dev = outs[0].cpu().numpy()
+    fit.close()
+    D = 256
+    out = {"workload": f"complex isometries, N=4 full-sites, m={m}, K={K}, B={B}: U1 per instance; chain on the real embedding (side {2 * D}), 4M products",
+           "u1_per_sec": B / (ms * 1e-3), "ms_per_step": ms,
+           "chain_tflops_real": 9 * (m - 1) * 4 * 2.0 * D ** 3 * B / (ms * 1e-3) / 1e12}
+    if cpu is not None:
+        n = min(cpu.cores, B)
+        res = cpu.pool.map(_cpu_complex_worker, [(c, 1) for c in range(n)])
+        sec = max(r[0] for r in res)
+        f_cpu = np.array([r[1][0] for r in res])
+        out["cpu"] = {"u1_per_sec": n / sec, "cores": n, "kind": "port", "sample": f"{n} of the {B} instances, one per core, oracle/complex_port.py triple",
+                      "cost_max_rel_diff_vs_device": float(np.max(np.abs(f_cpu - f_dev[:n]) / f_cpu))}
+        out["speedup_vs_cpu"] = out["u1_per_sec"] / out["cpu"]["u1_per_sec"]
+    return out
+
+
 def host_ceiling_leg(torch, dist, world, x_pin, g_pin, barrier, max_over_ranks, steps):
     """What the host side of the box can move: every rank copies one step's worth of inputs H2D and outputs D2H concurrently
     (two streams, pinned buffers, NO kernels).  The end-to-end U1 rate cannot exceed batch / this time, whatever the GPUs do."""
@@ -1039,6 +1100,10 @@ def run_gpu(args):
     latency = None
     if not args.no_latency and rank == 0 and world == 1:
         latency = latency_leg(torch, StiefelFit, local_rank, cpu_pool)
+    cplx = None
+    if not args.no_complex and rank == 0 and world == 1:
+        torch.cuda.empty_cache()
+        cplx = complex_leg(torch, StiefelFit, local_rank, cpu_pool)
     c4 = None
     if not args.no_c4:
         torch.cuda.empty_cache()
@@ -1158,7 +1223,7 @@ def run_gpu(args):
                                     "mode": "one blocking otn_triple call per step"}},
             "gpu_launches": int(launches), "device_resident": device_resident,
             "roofline": roofline, "dense_formulation": dense_leg, "cpu_baseline": cpu, "tr": tr, "final_gather_ms": gather_ms,
-            "two_site_model": two_site, "latency": latency, "c4": c4, "c5": c5}
+            "two_site_model": two_site, "latency": latency, "complex_isometries": cplx, "c4": c4, "c5": c5}
     line["e2e"]["host_ceiling"] = host_ceiling
     line["e2e"]["frac_of_host_ceiling"] = e2e_value / host_ceiling["u1_per_s_ceiling"]
     print(json.dumps(line))
@@ -1179,6 +1244,7 @@ def main():
     ap.add_argument("--no-local", action="store_true", help="skip the 2-site-model (factored evaluation) leg")
     ap.add_argument("--no-latency", action="store_true", help="skip the config-1 / config-2 single-instance latency leg")
     ap.add_argument("--no-c4", action="store_true", help="skip the config-4 sweep leg")
+    ap.add_argument("--no-complex", action="store_true", help="skip the complex-isometry U1 leg")
     ap.add_argument("--no-c5", action="store_true", help="skip the config-5 row-sharded N=6 composition leg")
     ap.add_argument("--min-warm-s", type=float, default=0.0,
                     help="keep warming up until this many seconds under load have passed (default 0 = exactly max(--warmup, 3) steps)")

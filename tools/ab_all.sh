@@ -3,7 +3,7 @@
 # under gpurun_out/ab_<name>.json; summary table on stdout).
 set -u
 mkdir -p gpurun_out
-F="--steps 20 --warmup 5 --no-cpu --no-dense --no-local --no-tr --no-latency --no-c4 --no-c5"
+F="--steps 20 --warmup 5 --no-cpu --no-dense --no-local --no-tr --no-latency --no-c4 --no-c5 --no-complex"
 run() { name=$1; shift; env "$@" timeout 150 python bench.py $F > gpurun_out/ab_$name.json 2> gpurun_out/ab_$name.err; }
 run default OTN_AB=0
 run back_v3 OTN_BACK_V3=1
