@@ -219,3 +219,18 @@ def test_liouvillian_term_lists_match_kron_route(monkeypatch):
             np.testing.assert_allclose(g, w, rtol=0, atol=1e-13)
     with pytest.raises(ValueError):
         T.create_2local_liouvillians(Li, 3, 2, backend="cuda")
+
+
+def test_row_shard_argument_checks():
+    """StiefelFit.row_shard (BASELINE config 5) validates on the host before anything touches a GPU: it shards the dense chain
+    only, needs an initialised process group, and a world size that divides D into row blocks of whole 64-row tiles."""
+    import torch.distributed as dist
+    from opentn_b200 import StiefelFit
+    T = np.eye(256)
+    with pytest.raises(ValueError, match="dense=True"):
+        StiefelFit(T, model="local", N=4, d=2).row_shard()
+    with pytest.raises(ValueError, match="dense=True"):
+        StiefelFit(T, model="local", N=4, d=2, factored=True).row_shard()
+    assert not dist.is_initialized()
+    with pytest.raises(RuntimeError, match="process group"):
+        StiefelFit(T, model="local", N=4, d=2, dense=True).row_shard()

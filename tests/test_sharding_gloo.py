@@ -111,3 +111,33 @@ def test_plan_cells_partition():
         if world > 1:      # snake deal: every rank's cells pair small isometries with large ones
             assert all(min(K for K, _ in o) <= 4 and max(K for K, _ in o) >= 8 for o in owned)
     assert sweep.instance_seed(16, 3, 255) != sweep.instance_seed(16, 2, 255)
+
+
+def _row_shard_worker(rank, world, port, out_dir):
+    """Host logic of StiefelFit.row_shard under a world-size-2 gloo group: rank / world bookkeeping and the divisibility check
+    (D = 256 over 2 ranks is fine; D = 64 is not: 64 % (64 * 2) != 0).  No handle is created, so no GPU is needed."""
+    import os
+    import numpy as np
+    import pytest
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from opentn_b200 import StiefelFit
+    fit = StiefelFit(np.eye(256), model="local", N=4, d=2, dense=True).row_shard()
+    assert fit._row_shard[:2] == (rank, world) and fit._handles == {}
+    with pytest.raises(ValueError, match="multiple of 64"):
+        StiefelFit(np.eye(64), model="full", N=3, d=2, dense=True).row_shard()
+    fit.close()                                   # nothing attached: no collective
+    dist.barrier()
+    dist.destroy_process_group()
+    open(os.path.join(out_dir, f"rs_ok{rank}"), "w").write("ok")
+
+
+def test_row_shard_host_logic_two_ranks(tmp_path):
+    import os
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_row_shard_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert all(os.path.exists(tmp_path / f"rs_ok{r}") for r in range(2))

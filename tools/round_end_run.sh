@@ -6,7 +6,7 @@ set -u
 WHAT="${1:-step}"
 mkdir -p gpurun_out
 if [ "$WHAT" = "step" ]; then
-timeout 600 python -m pytest tests -x -q -m gpu > gpurun_out/t_final.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/t_final.log
+timeout 900 python -m pytest tests -x -q -m gpu --durations=8 > gpurun_out/t_final.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/t_final.log
 timeout 400 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/bench_ref_final.json 2> gpurun_out/bench_ref_final.err; echo "ref rc=$?"
 timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; echo "bench rc=$?"
 F="--steps 2 --warmup 3 --no-cpu --no-tr --no-dense --no-local --no-latency --no-c4 --no-c5 --no-complex"
