@@ -810,6 +810,8 @@ def c5_fit_leg(torch, dist, rank, world, device, barrier, max_over_ranks):
         fit = StiefelFit(target, model="local", N=N, d=d, metric="canonical", dense=True, device=device).row_shard()
         ms, o, trm, rep = timed(fit)
         same = bool(torch.equal(o[0], o1[0]) and torch.equal(o[1], o1[1]) and torch.equal(o[2], o1[2]))
+        # (split-K CTA pairs, used when a rank has fewer than 6 tiles per SM, sum in another order: then not bitwise, but close)
+        rel = max(float((o[i] - o1[i]).abs().max() / o1[i].abs().max()) for i in range(3))
         # where the sharded time goes: per-launch events of this rank's kernels (the chain products include their peer stores;
         # the device-side barriers are not in any category), once more with the peer stores switched off (numbers then garbage)
         (hs,) = fit._handles.values()
@@ -835,7 +837,8 @@ def c5_fit_leg(torch, dist, rank, world, device, barrier, max_over_ranks):
                           "replicated_kernels_ms": max_over_ranks(pms[1] + pms[2] + pms[3])}
         out["row_sharded"] = {"u1_ms": ms, "tflops": flops_u1 / ms / 1e9, "efficiency_vs_single_gpu": ms1 / (world * ms),
                               "tr_iteration_ms": trm, "tr_efficiency_vs_single_gpu": tr1 / (world * trm), "n_cg": int(rep["n_cg"][0, 0]),
-                              "bitwise_equal_to_single_gpu": same, "tr_cost_equal": bool(np.array_equal(rep["f_iter"], rep1["f_iter"])),
+                              "bitwise_equal_to_single_gpu": same, "max_rel_diff_vs_single_gpu": rel,
+                              "tr_cost_rel_diff": float(np.max(np.abs(rep["f_iter"] - rep1["f_iter"]) / np.abs(rep1["f_iter"]))),
                               "barriers_ok": bool(fit.row_shard_ok()), "diagnostics": diag}
         fit.close()
     del stream

@@ -14,6 +14,8 @@
 #include <atomic>
 #include <cstdlib>
 
+#include <cooperative_groups.h>
+
 #include "otn_common.cuh"
 
 namespace otn {
@@ -49,6 +51,12 @@ struct GemmParams {
     // every element is mirrored into the lower half -- (r, c) -> (r + mirror, c + mirror) for c < mirror, and
     // -(r, c) -> (r + mirror, c - mirror) otherwise.  0 = off.  Partial sums then cover the upper half only.
     int mirror;
+    // Split-K over a pair of CTAs (thread-block cluster of 2; 64 x 64 tiles only): each CTA of the pair runs half of the k-tiles of
+    // one output tile (for a dual product: one product each), the second hands its accumulators to the first through distributed
+    // shared memory, which adds them (own + partner: a fixed order) and runs the epilogue.  Twice as many, half as long CTAs: for a
+    // launch with only 3-4 tiles per SM (a row-sharded D = 4096 product on 8 GPUs: 512 tiles on 148 SMs) the SMs end level, and
+    // the epilogues -- peer stores over NVLink -- of the first wave run under the math of the second.  0 = off.
+    int splitk;
 };
 
 template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool TA, bool TB>
@@ -64,7 +72,7 @@ struct GemmCfg {
     static constexpr size_t SMEM_BYTES = size_t(STAGES) * STAGE_ELEMS * sizeof(double);
 };
 
-template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool TA, bool TB>
+template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool TA, bool TB, int SPLIT = 1>
 __global__ void __launch_bounds__(GemmCfg<BM, BN, BK, WM, WN, STAGES, TA, TB>::THREADS)
 gemm_dmma_kernel(const GemmParams p) {
     using Cfg = GemmCfg<BM, BN, BK, WM, WN, STAGES, TA, TB>;
@@ -74,9 +82,11 @@ gemm_dmma_kernel(const GemmParams p) {
 
     const int tiles_n = p.D / BN;
     const int tiles = (p.rows / BM) * tiles_n;
-    const int b = blockIdx.x / tiles;
-    const int tile = blockIdx.x - b * tiles;
-    if (p.active != nullptr && p.active[b] == 0) return;
+    const int work = SPLIT == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // SPLIT == 2: CTAs 2w and 2w+1 are one cluster
+    const int half = SPLIT == 2 ? (int)(blockIdx.x & 1) : 0;
+    const int b = work / tiles;
+    const int tile = work - b * tiles;
+    if (p.active != nullptr && p.active[b] == 0) return;                         // (both CTAs of a pair leave together)
     const int m0 = p.row0 + (tile / tiles_n) * BM;
     const int n0 = (tile % tiles_n) * BN;
     const int D = p.D;
@@ -88,7 +98,10 @@ gemm_dmma_kernel(const GemmParams p) {
     const int nprod = (p.A2 != nullptr) ? 2 : 1;
     const int kvalid = p.kvalid > 0 ? p.kvalid : D;
     const int ktiles_one = (kvalid + BK - 1) / BK;
-    const int ktiles = ktiles_one * nprod;
+    const int ktiles_all = ktiles_one * nprod;
+    // this CTA's share of the k-tiles: all of them, or one half (a dual product splits into its two products)
+    const int kt_begin = (SPLIT == 2 && half == 1) ? (ktiles_all + 1) / 2 : 0;
+    const int ktiles = (SPLIT == 2) ? (half == 0 ? (ktiles_all + 1) / 2 : ktiles_all) : ktiles_all;
 
     const double* A1 = p.A1 + (long long)b * p.sA1;
     const double* B1 = p.B1 + (long long)b * p.sB1;
@@ -137,19 +150,19 @@ gemm_dmma_kernel(const GemmParams p) {
 
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < ktiles) load_tile(s, s);
+        if (kt_begin + s < ktiles) load_tile(kt_begin + s, s);
         cp_async_commit();
     }
 
-    for (int kt = 0; kt < ktiles; ++kt) {
+    for (int kt = kt_begin; kt < ktiles; ++kt) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
         {
             int nk = kt + STAGES - 1;
-            if (nk < ktiles) load_tile(nk, nk % STAGES);
+            if (nk < ktiles) load_tile(nk, (nk - kt_begin) % STAGES);
             cp_async_commit();
         }
-        const double* As = smem + (kt % STAGES) * Cfg::STAGE_ELEMS;
+        const double* As = smem + ((kt - kt_begin) % STAGES) * Cfg::STAGE_ELEMS;
         const double* Bs = As + Cfg::A_ELEMS;
         const int kend = kvalid - (kt < ktiles_one ? kt : kt - ktiles_one) * BK;   // < BK only in the last k-tile of a padded block
         auto kstep = [&](int kk) {
@@ -178,6 +191,37 @@ gemm_dmma_kernel(const GemmParams p) {
         }
     }
     cp_async_wait<0>();
+
+    if (SPLIT == 2) {
+        // the second CTA of the pair parks its accumulators in its (now idle) operand ring, thread-linear so that the first CTA's
+        // reads over distributed shared memory are coalesced; sum = own + partner
+        static_assert(SPLIT == 1 || (size_t)MI * NI * 2 * NT * sizeof(double) <= Cfg::SMEM_BYTES, "accumulators must fit the operand ring");
+        namespace cg = cooperative_groups;
+        cg::cluster_group cluster = cg::this_cluster();
+        __syncthreads();                                         // every warp is done reading the ring
+        if (half == 1) {
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NI; ++j) {
+                    smem[((i * NI + j) * 2 + 0) * NT + tid] = acc[i][j][0];
+                    smem[((i * NI + j) * 2 + 1) * NT + tid] = acc[i][j][1];
+                }
+        }
+        cluster.sync();
+        if (half == 0) {
+            const double* other = cluster.map_shared_rank(smem, 1);
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NI; ++j) {
+                    acc[i][j][0] += other[((i * NI + j) * 2 + 0) * NT + tid];
+                    acc[i][j][1] += other[((i * NI + j) * 2 + 1) * NT + tid];
+                }
+        }
+        cluster.sync();                                          // the partner's shared memory stays alive until it has been read
+        if (half == 1) return;
+    }
 
     // ---- epilogue ----
     double* C = p.C + (long long)b * p.sC;
@@ -348,10 +392,37 @@ inline cudaError_t launch_dmma(const GemmParams& p, int tiles, cudaStream_t st) 
     return cudaGetLastError();
 }
 
+// the split-K variant: clusters of two CTAs per output tile
+template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool TA, bool TB>
+inline cudaError_t launch_dmma_split2(const GemmParams& p, int tiles, cudaStream_t st) {
+    using Cfg = GemmCfg<BM, BN, BK, WM, WN, STAGES, TA, TB>;
+    auto kern = gemm_dmma_kernel<BM, BN, BK, WM, WN, STAGES, TA, TB, 2>;
+    static std::atomic<unsigned long long> configured{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ULL << (dev & 63);
+    if (!(configured.load(std::memory_order_acquire) & bit)) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured.fetch_or(bit, std::memory_order_release);
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(2LL * p.batch * tiles));
+    cfg.blockDim = dim3(Cfg::THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
 template <bool TA, bool TB>
 inline cudaError_t gemm_launch_t(const GemmParams& p, cudaStream_t st) {
     GemmPlan pl = gemm_plan(p.D, p.rows, p.batch);
     if (pl.kind == 1) return launch_dmma<128, 128, 16, 64, 32, 3, TA, TB>(p, pl.tiles, st);
+    if (pl.kind == 2 && p.splitk) return launch_dmma_split2<64, 64, 16, 32, 32, 3, TA, TB>(p, pl.tiles, st);
     if (pl.kind == 2) return launch_dmma<64, 64, 16, 32, 32, 3, TA, TB>(p, pl.tiles, st);
     if (pl.kind == 3) return launch_dmma<48, 48, 16, 24, 24, 3, TA, TB>(p, pl.tiles, st);
     gemm_simt_kernel<TA, TB><<<(unsigned)((long long)p.batch * pl.tiles), 256, 0, st>>>(p);

@@ -813,6 +813,16 @@ static cudaError_t rs_window(const otn_problem* h, GemmParams& p) {
     if (p.epi != EPI_NONE) p.partial += h->rs.rank * gemm_plan(p.D, rows, 1).tiles;
     p.npeer = h->rs.world - 1;
     if (getenv("OTN_RS_NO_PEER_STORES") != nullptr) p.npeer = 0;      // env: timing diagnostic only (results are then incomplete)
+    {
+        // split-K pairs (gemm_dmma.cuh) when the launch is too small to level the SMs: fewer than 6 tiles of 64 x 64 per SM and a
+        // contraction long enough to halve (env OTN_RS_SPLITK: "1" = always, "0" = never; for tests and A/B measurements).  The sum
+        // order differs from the un-split product, so such a launch is no longer bitwise equal to the one-GPU handle (it is still
+        // bitwise equal on all ranks: every element has one producer).
+        const char* env = getenv("OTN_RS_SPLITK");
+        const GemmPlan pl = gemm_plan(p.D, rows, p.batch);
+        const bool want = env ? (env[0] == '1') : ((long long)pl.tiles * p.batch < 6LL * 148 && p.D >= 1024);
+        p.splitk = (want && pl.kind == 2) ? 1 : 0;
+    }
     for (int q = 0; q < p.npeer; ++q) {
         p.Cpeer[q] = rs_peer(h, q, p.C);
         p.Ppeer[q] = (p.epi != EPI_NONE) ? rs_peer(h, q, p.partial) : nullptr;

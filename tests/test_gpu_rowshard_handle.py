@@ -88,6 +88,27 @@ def _worker(rank, world, port, out_dir, same_gpu):
         dist.all_gather(both, mine)
         assert all(torch.equal(b, both[0]) for b in both)
         fit.close()
+        # split-K CTA pairs (what a D = 4096 product on 8 GPUs uses; forced here): another summation order, so oracle tolerance
+        # instead of bitwise equality with the un-sharded handle -- but still the same bits on every rank
+        os.environ["OTN_RS_SPLITK"] = "1"
+        try:
+            fit = StiefelFit(T, model=model, N=N, d=d, metric="canonical", dense=True, device=dev).row_shard()
+            f, g, h = fit.triple(np.array(xs), np.array(etas))
+            assert abs(f - fo) < 1e-12 * max(1.0, abs(fo))
+            assert np.abs(g - np.array(go)).max() / np.abs(np.array(go)).max() < 1e-10
+            assert np.abs(h - np.array(ho)).max() / np.abs(np.array(ho)).max() < 1e-10
+            x3, rep3 = fit.tr_run(np.array(xs), niter=2)
+            assert np.allclose(rep3["f_iter"][:, 0], f_it[:2], rtol=1e-9)
+            mine = torch.from_numpy(np.concatenate([[f], g.ravel(), h.ravel(), x3.ravel()]))
+            if not same_gpu:
+                mine = mine.cuda()
+            both = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(both, mine)
+            assert all(torch.equal(b, both[0]) for b in both)
+            assert fit.row_shard_ok()
+            fit.close()
+        finally:
+            os.environ.pop("OTN_RS_SPLITK", None)
     if not same_gpu:
         _n6_case(dev, world, dist, torch)
     dist.barrier()
