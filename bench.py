@@ -810,7 +810,6 @@ def c5_fit_leg(torch, dist, rank, world, device, barrier, max_over_ranks):
         fit = StiefelFit(target, model="local", N=N, d=d, metric="canonical", dense=True, device=device).row_shard()
         ms, o, trm, rep = timed(fit)
         same = bool(torch.equal(o[0], o1[0]) and torch.equal(o[1], o1[1]) and torch.equal(o[2], o1[2]))
-        # (split-K CTA pairs, used when a rank has fewer than 6 tiles per SM, sum in another order: then not bitwise, but close)
         rel = max(float((o[i] - o1[i]).abs().max() / o1[i].abs().max()) for i in range(3))
         # where the sharded time goes: per-launch events of this rank's kernels (the chain products include their peer stores;
         # the device-side barriers are not in any category), once more with the peer stores switched off (numbers then garbage)

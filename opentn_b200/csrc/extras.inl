@@ -481,6 +481,7 @@ extern "C" int otn_gemm_rows_ex(const double* A1, const double* B1, const double
     for (int q = 0; q < npeer; ++q) p.Cpeer[q] = peers[q];
     p.epi = T ? EPI_RESID : EPI_NONE;
     if (T) { p.E = T; p.sE = 0; p.e_index = nullptr; p.partial = partial; p.partial_stride = gemm_plan(D, rows, 1).tiles; }
+    p.splitk = gemm_want_split(D);
     ++g_launches;
     CUDA_TRY(gemm_launch(p, transA != 0, transB != 0, (cudaStream_t)stream));
     return 0;

@@ -357,6 +357,16 @@ struct GemmPlan {
     int tiles;     // CTAs per instance (for the `partial` buffer)
 };
 
+// Split-K CTA pairs (GemmParams::splitk) for the large single-instance products (D >= 1024: the N = 6 chain, whole or row-sharded):
+// measured 2 % faster on a full D = 4096 product and 25 % on its 8-GPU row shard (512 tiles on 148 SMs).  The rule depends on D
+// only, so a row-sharded product and the one-GPU product sum in the same order and stay bitwise equal.
+// env OTN_SPLITK: "0" = never, "1" = always (tests, A/B measurements).
+inline int gemm_want_split(int D) {
+    const char* env = getenv("OTN_SPLITK");
+    if (env != nullptr) return env[0] == '1' ? 1 : 0;
+    return D >= 1024 ? 1 : 0;
+}
+
 inline GemmPlan gemm_plan(int D, int rows, int batch) {
     GemmPlan pl;
     static const int big_tile_min_d = [] { const char* e = getenv("OTN_GEMM_BIG_TILE_MIN_D"); return e ? atoi(e) : (1 << 30); }();   // 64x64 tiles measured faster even at D = 4096 (32.7 vs 30.0 TFLOP/s)

@@ -813,16 +813,6 @@ static cudaError_t rs_window(const otn_problem* h, GemmParams& p) {
     if (p.epi != EPI_NONE) p.partial += h->rs.rank * gemm_plan(p.D, rows, 1).tiles;
     p.npeer = h->rs.world - 1;
     if (getenv("OTN_RS_NO_PEER_STORES") != nullptr) p.npeer = 0;      // env: timing diagnostic only (results are then incomplete)
-    {
-        // split-K pairs (gemm_dmma.cuh) when the launch is too small to level the SMs: fewer than 6 tiles of 64 x 64 per SM and a
-        // contraction long enough to halve (env OTN_RS_SPLITK: "1" = always, "0" = never; for tests and A/B measurements).  The sum
-        // order differs from the un-split product, so such a launch is no longer bitwise equal to the one-GPU handle (it is still
-        // bitwise equal on all ranks: every element has one producer).
-        const char* env = getenv("OTN_RS_SPLITK");
-        const GemmPlan pl = gemm_plan(p.D, rows, p.batch);
-        const bool want = env ? (env[0] == '1') : ((long long)pl.tiles * p.batch < 6LL * 148 && p.D >= 1024);
-        p.splitk = (want && pl.kind == 2) ? 1 : 0;
-    }
     for (int q = 0; q < p.npeer; ++q) {
         p.Cpeer[q] = rs_peer(h, q, p.C);
         p.Ppeer[q] = (p.epi != EPI_NONE) ? rs_peer(h, q, p.partial) : nullptr;
@@ -843,6 +833,7 @@ static cudaError_t hgemm(otn_problem* h, const GemmParams& p0, bool ta, bool tb)
         if (p.A2) { p.A2 += o; p.B2 += o; }
         if (p.epi != EPI_NONE) { p.E += o; p.partial += h->blkTileOff[i]; p.partial_stride = h->tiles; }
         if (h->cplx) { p.rows = p.D / 2; p.mirror = p.D / 2; }     // products of embeddings: upper half computed, lower half mirrored (gemm_dmma.cuh)
+        if (!h->structured) p.splitk = gemm_want_split(p.D);       // large single-instance products: split-K CTA pairs
         if (h->rs.world > 1) {
             // Barrier BEFORE the product: no peer may still be reading (in a replicated kernel enqueued since the last product)
             // the array this product overwrites over there; barrier AFTER it: the result is complete on every rank before
@@ -883,7 +874,7 @@ static cudaError_t hgemm_pair(otn_problem* h, const GemmParams& a, bool ta_a, bo
     }
     GemmParams p[2] = {a, b};
     for (GemmParams& q : p) {
-        q.D = h->blkD[0]; q.kvalid = 0;
+        q.D = h->blkD[0]; q.kvalid = 0; q.splitk = gemm_want_split(q.D);
         if (q.epi != EPI_NONE) q.partial_stride = h->tiles;
         cudaError_t e = rs_window(h, q);
         if (e != cudaSuccess) return e;
@@ -2130,6 +2121,7 @@ extern "C" int otn_gemm_rows(const double* A1, const double* B1, const double* A
         if (!is_device_ptr(ptr)) return fail("otn_gemm_rows takes device pointers");
     GemmParams p{};
     p.A1 = A1; p.B1 = B1; p.A2 = A2; p.B2 = B2; p.C = C; p.D = D; p.row0 = row0; p.rows = rows; p.batch = 1; p.epi = EPI_NONE;
+    p.splitk = gemm_want_split(D);
     ++g_launches;
     CUDA_TRY(gemm_launch(p, transA != 0, transB != 0, (cudaStream_t)stream));
     return 0;
@@ -2151,6 +2143,7 @@ extern "C" int otn_gemm_rows_bcast(const double* A1, const double* B1, const dou
     p.A1 = A1; p.B1 = B1; p.A2 = A2; p.B2 = B2; p.C = C; p.D = D; p.row0 = row0; p.rows = rows; p.batch = 1; p.epi = EPI_NONE;
     p.npeer = npeer;
     for (int q = 0; q < npeer; ++q) p.Cpeer[q] = peers[q];
+    p.splitk = gemm_want_split(D);
     ++g_launches;
     CUDA_TRY(gemm_launch(p, transA != 0, transB != 0, (cudaStream_t)stream));
     return 0;

@@ -110,3 +110,27 @@ def test_n6_dense_triple_equals_factored(n6, oracle):
         assert np.abs(g - g0).max() / np.abs(g0).max() < 1e-10
         assert np.abs(gc - g0).max() / np.abs(g0).max() < 1e-10
         assert np.abs(h - h0).max() / np.abs(h0).max() < 1e-10
+
+
+def test_n6_split_k_pairs_match_unsplit(n6, oracle):
+    """D = 4096 products run as split-K CTA pairs (thread-block clusters of two, accumulators handed over through distributed
+    shared memory; csrc/gemm_dmma.cuh).  OTN_SPLITK=0 switches them off: same cost / gradient / HVP to rounding."""
+    import os
+    from opentn_b200 import StiefelFit
+    T6, _ = n6
+    rng = np.random.default_rng(5)
+    xs = np.array([oracle.random_stiefel(16, 4, rng) for _ in range(3)])
+    et = np.array([oracle.project(x, rng.standard_normal(x.shape)) for x in xs])
+    res = []
+    for split in ("1", "0"):
+        os.environ["OTN_SPLITK"] = split
+        try:
+            fit = StiefelFit(T6, model="local", N=6, d=2, metric="canonical", dense=True)
+            res.append(fit.triple(xs, et))
+            fit.close()
+        finally:
+            os.environ.pop("OTN_SPLITK", None)
+    (f1, g1, h1), (f0, g0, h0) = res
+    assert abs(f1 - f0) < 1e-13 * abs(f0)
+    assert np.abs(g1 - g0).max() / np.abs(g0).max() < 1e-12 and np.abs(h1 - h0).max() / np.abs(h0).max() < 1e-12
+    assert not (np.array_equal(g1, g0) and np.array_equal(h1, h0))        # the switch really selects another kernel
