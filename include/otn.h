@@ -180,6 +180,9 @@ int otn_ipc_free(void* ptr, int device);
  * equal on all ranks and to the un-sharded handle.  This shards what jax.grad / jax.jvp spend their time on at D = 4096
  * (stiefel.py:423, 520 over compose_superops_list, transformations.py:841-851), which the reference could not finish
  * (experiments/trust_region_higher_sites.ipynb).  Needs D % (64 world) == 0, world <= 8.
+ * The host places one barrier between the ranks after otn_rowshard_attach (every rank has mapped its peers and cleared its flags
+ * before the first product stores into them) and one before otn_rowshard_detach / otn_destroy (no rank frees arrays a peer still
+ * has mapped); StiefelFit.row_shard() / close() do both.
  * otn_rowshard_status : *timed_out = 1 when a device-side barrier of this rank gave up after 30 s (a peer never arrived). */
 #define OTN_ROWSHARD_HANDLES 10
 int otn_rowshard_export(otn_problem* p, unsigned char* handles);

@@ -45,6 +45,7 @@ struct ExpmCtx {
         GemmParams p{};
         p.A1 = A1; p.B1 = B1; p.A2 = A2; p.B2 = B2; p.C = C; p.D = D; p.row0 = 0; p.rows = D; p.batch = count; p.epi = EPI_NONE;
         p.sA1 = p.sB1 = p.sA2 = p.sB2 = p.sC = sb;
+        p.splitk = gemm_want_split(D);           // D >= 1024 (the N = 6 propagator): split-K CTA pairs
         ++g_launches;
         CUDA_TRY(gemm_launch(p, false, false, st));
         return 0;

@@ -1984,6 +1984,7 @@ extern "C" int otn_compose(const double* Ys, int count, int m, int D, double* M,
         p.B1 = prev; p.sB1 = sprev;
         double* outp = (l == m - 1) ? (double*)Md : S.b.as<double>() + (size_t)(l & 1) * count * SZ;
         p.C = outp; p.sC = SZ;
+        p.splitk = gemm_want_split(D);
         CUDA_TRY(gemm_launch(p, false, false, 0));
         prev = outp; sprev = SZ;
     }
@@ -2280,6 +2281,9 @@ extern "C" int otn_rowshard_attach(otn_problem* h, int rank, int world, const un
         CUDA_TRY(cudaEventCreateWithFlags(&h->rs.ev_fork, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&h->rs.ev_join, cudaEventDisableTiming));
     }
+    // barrier epochs restart at zero: clear the flags a previous attachment may have left behind.  No peer writes into them before
+    // the host-side barrier the caller places between this call and the first sharded call (see otn.h).
+    CUDA_TRY(cudaMemset(h->rs.flags, 0, 64 * sizeof(int)));
     h->rs.rank = rank; h->rs.world = world; h->rs.epoch = 0;
     h->cached_batch = 0;
     return 0;
