@@ -88,6 +88,24 @@ def _worker(rank, world, port, out_dir, same_gpu):
         dist.all_gather(both, mine)
         assert all(torch.equal(b, both[0]) for b in both)
         fit.close()
+        # a batch of two instances through one sharded handle (peer stores and partial sums are offset per instance)
+        xs2 = [P.random_stiefel(x.shape[0], x.shape[1], rng) for x in xs]
+        et2 = [P.project(x, rng.standard_normal(x.shape)) for x in xs2]
+        xb, eb = np.stack([np.array(xs), np.array(xs2)]), np.stack([np.array(etas), np.array(et2)])
+        ref = StiefelFit(T, model=model, N=N, d=d, metric="canonical", dense=True, device=dev, max_batch=2)
+        fb1, gb1, hb1 = ref.triple(xb, eb)
+        ref.close()
+        fit = StiefelFit(T, model=model, N=N, d=d, metric="canonical", dense=True, device=dev, max_batch=2).row_shard()
+        fb, gb, hb = fit.triple(xb, eb)
+        assert np.array_equal(fb, fb1) and np.array_equal(gb, gb1) and np.array_equal(hb, hb1)
+        assert fb[0] == f1 and np.array_equal(gb[0], g1)
+        fo2, go2, ho2 = P.triple(spec, xs2, et2, "canonical")
+        assert abs(fb[1] - fo2) < 1e-12 * max(1.0, abs(fo2))
+        assert np.abs(gb[1] - np.array(go2)).max() / np.abs(np.array(go2)).max() < 1e-10
+        assert np.abs(hb[1] - np.array(ho2)).max() / np.abs(np.array(ho2)).max() < 1e-10
+        xt, rept = fit.tr_run(xb, niter=2)
+        assert np.array_equal(rept["f_iter"][:, 0], rep1["f_iter"][:2, 0])
+        fit.close()
         # split-K CTA pairs (what every D >= 1024 product uses; forced here at D = 256): another summation order than `ref` above,
         # so oracle tolerance instead of bitwise equality -- but still the same bits on every rank
         os.environ["OTN_SPLITK"] = "1"
