@@ -183,6 +183,8 @@ int otn_ipc_free(void* ptr, int device);
  * The host places one barrier between the ranks after otn_rowshard_attach (every rank has mapped its peers and cleared its flags
  * before the first product stores into them) and one before otn_rowshard_detach / otn_destroy (no rank frees arrays a peer still
  * has mapped); StiefelFit.row_shard() / close() do both.
+ * Anything that changes the launch sequence -- otn_profile_enable, the OTN_* environment switches -- must be set alike on all
+ * ranks: the device-side barriers count launches.
  * otn_rowshard_status : *timed_out = 1 when a device-side barrier of this rank gave up after 30 s (a peer never arrived). */
 #define OTN_ROWSHARD_HANDLES 10
 int otn_rowshard_export(otn_problem* p, unsigned char* handles);
